@@ -1,0 +1,175 @@
+/* pgrt.h -- C ABI of the B200-native render loop that replaces, in rddrdhd/PGI_RayTracing,
+ *   (B1) the per-pixel loop  SimpleGuiDX11::Producer -> Raytracer::get_pixel -> Raytracer::trace
+ *        (src/pg/pg1_embree/simpleguidx11.cpp:86-128, raytracer.cpp:396-437, :237-394), and
+ *   (B2) the Embree 3 calls underneath it (rtcNewGeometry ... rtcCommitScene, rtcIntersect1, rtcInterpolate0;
+ *        src/pg/pg1_embree/raytracer.cpp:26-47, :71-127, :130-148, :249-253, :344).
+ *
+ * Plain C: opaque context, POD structs, pointers + sizes, int status (0 = PGRT_OK), no exceptions across the
+ * boundary, no torch / CUDA types in any signature (streams and device buffers travel as void*).
+ * All reference citations below are relative to src/pg/pg1_embree/ of the reference repository.
+ * The library is CUDA-only: there is no CPU fallback; pgrt_create fails when no sm_100 device is present.
+ */
+#ifndef PGRT_H_
+#define PGRT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGRT_OK 0
+#define PGRT_ERR_INVALID 1      /* bad argument / call order                               */
+#define PGRT_ERR_CUDA 2         /* a CUDA runtime call failed; see pgrt_last_error         */
+#define PGRT_ERR_NO_DEVICE 3    /* no usable GPU                                           */
+#define PGRT_ERR_OVERFLOW 4     /* secondary-ray queues overflowed even at the minimum batch */
+
+#define PGRT_INVALID_ID 0xFFFFFFFFu   /* = RTC_INVALID_GEOMETRY_ID, embree3/rtcore_common.h:45 */
+#define PGRT_IOR_AIR 1.000293f        /* material.h:15 */
+
+typedef struct pgrt_context pgrt_context;
+
+/* Fields of Material the path reads (material.h:96-108); filled by LoadMTL (objloader.cpp:53-208). */
+typedef struct pgrt_material {
+    float diffuse[3];     /* Kd as parsed (x,y,z)                      */
+    float specular[3];    /* Ks as parsed                              */
+    float shininess;      /* Ns                                        */
+    float ior;            /* Ni                                        */
+    int32_t type;         /* MTL "shader N": 4 = dielectric, else Phong (raytracer.cpp:293-325) */
+    int32_t diffuse_tex;  /* texture id given to pgrt_set_texture, -1 = none (Material::kDiffuseMapSlot) */
+} pgrt_material;
+
+/* LightSource (LightSource.h:11-15). */
+typedef struct pgrt_light {
+    float position[3];
+    float ambient[3];
+    float diffuse[3];
+    float specular[3];
+} pgrt_light;
+
+/* Everything get_pixel / trace hard-code (raytracer.cpp:398-400, :282, :450); defaults = pgrt_default_params. */
+typedef struct pgrt_render_params {
+    int32_t sampling_width;   /* 3   stratified grid per pixel, S = w*w samples (raytracer.cpp:398)          */
+    int32_t jitter;           /* 1   U[-0.5/w, 0.5/w) jitter (raytracer.cpp:408-410); 0 = sample at the cell corner */
+    float focal_distance;     /* 200 (raytracer.cpp:399)                                                    */
+    float aperture;           /* 5   (raytracer.cpp:400); 0 = thin-lens code path with no lens shift          */
+    int32_t max_depth;        /* 7   "level >= max_depth -> black" (raytracer.cpp:282)                       */
+    float gamma_level;        /* 0.5 UI slider default (raytracer.cpp:450); pixel = c^(2*gamma_level)         */
+    uint32_t seed;            /* counter-based RNG seed (replaces the clock-seeded mt19937, raytracer.cpp:407) */
+    int32_t camera_mode;      /* 0 thin lens generate_ray(x,y,f,a) PinHoleCamera.cpp:65-105; 1 pinhole :31-63 */
+    int32_t shader_mode;      /* 0 Whitted (trace as shipped); 1 Lambert (diffuse addend of :377 only);
+                                 2 normal shader (the commented block raytracer.cpp:274-280)                 */
+    int32_t reserved[7];
+} pgrt_render_params;
+
+typedef struct pgrt_build_stats {
+    uint32_t triangles;
+    uint32_t nodes;           /* wide nodes emitted                                              */
+    float build_ms;           /* device time of the whole commit (Morton .. collapse)            */
+    float sort_ms;
+    float sah_cost;           /* SAH cost of the emitted tree (Ct=1, Ci=1), for build-quality tests */
+    uint32_t reserved[3];
+} pgrt_build_stats;
+
+typedef struct pgrt_render_stats {
+    uint64_t rays_primary;    /* one per get_ray_hit call, by caller (raytracer.cpp:241, :164, :300, :310) */
+    uint64_t rays_shadow;
+    uint64_t rays_reflection;
+    uint64_t rays_refraction;
+    float frame_ms;           /* device time, first launch .. framebuffer ready                 */
+    float trace_ms;           /* sum of closest-hit traversal kernel launches (profiled renders only) */
+    float shade_ms;           /* sum of the other kernels (profiled renders only)               */
+    uint32_t trace_launches;
+    uint32_t launches;        /* kernels launched for this frame                                 */
+    uint32_t batches;         /* sample batches the frame was cut into                           */
+    uint32_t overflow_retries;
+    uint32_t reserved[5];
+} pgrt_render_stats;
+
+/* Layout-compatible with RTCRayHit (embree3/rtcore_ray.h:11-49), 80 bytes. */
+typedef struct pgrt_rayhit {
+    float org_x, org_y, org_z, tnear;
+    float dir_x, dir_y, dir_z, time;
+    float tfar;
+    uint32_t mask, id, flags;
+    float Ng_x, Ng_y, Ng_z, u, v;
+    uint32_t primID, geomID, instID;
+} pgrt_rayhit;
+
+/* ---- lifetime: replaces Raytracer::InitDeviceAndScene / ReleaseDeviceAndScene (raytracer.cpp:26-46),
+ *      i.e. rtcNewDevice + rtcNewScene / rtcReleaseScene + rtcReleaseDevice.  `device` = CUDA ordinal. */
+int pgrt_create(pgrt_context** ctx, int device);
+void pgrt_destroy(pgrt_context* ctx);
+/* replaces the rtcSetDeviceErrorFunction callback (raytracer.cpp:29-30, tutorials.cpp:9-26): last message, never NULL */
+const char* pgrt_last_error(const pgrt_context* ctx);
+/* optional: run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the context's own */
+int pgrt_set_stream(pgrt_context* ctx, void* cuda_stream);
+
+/* ---- scene upload: replaces the per-surface block of Raytracer::LoadScene (raytracer.cpp:71-125):
+ *      rtcNewGeometry + 4x rtcSetNewGeometryBuffer + rtcSetGeometryUserData + rtcCommitGeometry + rtcAttachGeometry.
+ *      pos / nrm: 9 floats per triangle (3 un-indexed corners, :105-111), uv: 6 floats per triangle (:113-114);
+ *      host pointers, borrowed for the call only.  *geom_id receives what rtcAttachGeometry would return (:123). */
+int pgrt_add_mesh(pgrt_context* ctx, const float* pos, const float* nrm, const float* uv, uint32_t n_triangles,
+                  int32_t material_id, uint32_t* geom_id);
+int pgrt_set_materials(pgrt_context* ctx, const pgrt_material* materials, int32_t n);
+/* raw top-down BGR(A) bytes exactly as Texture::Texture leaves them (texture.cpp:36-47): pitch bytes per row, bpp 3 or 4 */
+int pgrt_set_texture(pgrt_context* ctx, int32_t id, const uint8_t* bytes, int32_t width, int32_t height, int32_t pitch, int32_t bpp);
+/* SphericalMap's texture (SphericalMap.cpp:12-15) */
+int pgrt_set_envmap(pgrt_context* ctx, const uint8_t* bytes, int32_t width, int32_t height, int32_t pitch, int32_t bpp);
+int pgrt_set_lights(pgrt_context* ctx, const pgrt_light* lights, int32_t n);   /* lights_ (raytracer.cpp:66-68) */
+/* replaces rtcCommitScene (raytracer.cpp:127): GPU BVH build over everything added so far */
+int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats);
+int pgrt_clear_scene(pgrt_context* ctx);
+
+/* ---- camera: replaces PinHoleCamera::PinHoleCamera (PinHoleCamera.cpp:5-29), up = +Z (PinHoleCamera.h:36) */
+int pgrt_set_camera(pgrt_context* ctx, int32_t width, int32_t height, float fov_y, const float from[3], const float at[3]);
+void pgrt_default_params(pgrt_render_params* p);
+
+/* ---- the path: one Producer iteration (simpleguidx11.cpp:95-118).
+ *      rgba = width*height*4 floats, pixel (x,y) at (y*width+x)*4, row 0 = top, a = 1 (simpleguidx11.cpp:108-114).
+ *      pgrt_render          : host destination (device->host copy inside the call, as memcpy :121-124).
+ *      pgrt_render_device   : device destination, asynchronous on the context stream; stats may be NULL.
+ *      `profile` != 0 brackets every launch with events to fill trace_ms / shade_ms (serialises nothing). */
+int pgrt_render(pgrt_context* ctx, const pgrt_render_params* p, float* rgba_host, pgrt_render_stats* stats, int32_t profile);
+int pgrt_render_device(pgrt_context* ctx, const pgrt_render_params* p, void* rgba_device, pgrt_render_stats* stats, int32_t profile);
+/* single-pixel hook with the signature of SimpleGuiDX11::get_pixel (simpleguidx11.h:27): serves pixel (x,y) of
+ * the frame rendered by the last pgrt_render* call (re-renders when the camera, scene or params changed). */
+int pgrt_get_pixel(pgrt_context* ctx, const pgrt_render_params* p, int32_t x, int32_t y, float rgba[4]);
+/* primary hit of sample (0,0) of every pixel: what ray_hit.hit.geomID / primID hold at raytracer.cpp:247 */
+int pgrt_primary_ids(pgrt_context* ctx, const pgrt_render_params* p, uint32_t* geom_id_host, uint32_t* prim_id_host);
+
+/* ---- image-tile sharding (one process per GPU): this context renders tiles t with t % n_ranks == rank of the
+ *      32x8-pixel tile grid.  pgrt_render_shard_device writes the compact per-rank buffer
+ *      (pgrt_shard_pixels * 4 floats); pgrt_untile scatters n_ranks such buffers (concatenated, rank-major, each
+ *      pgrt_shard_pixels long) into the full frame.  No data-path collective lives here: the gather between is NCCL. */
+int pgrt_set_shard(pgrt_context* ctx, int32_t rank, int32_t n_ranks);
+uint64_t pgrt_shard_pixels(const pgrt_context* ctx);   /* padded pixel slots per rank (same on every rank) */
+int pgrt_render_shard_device(pgrt_context* ctx, const pgrt_render_params* p, void* shard_rgba_device, pgrt_render_stats* stats, int32_t profile);
+int pgrt_untile(pgrt_context* ctx, const void* gathered_device, int32_t n_ranks, void* rgba_device);
+
+/* ---- rtcIntersect1 over a batch (raytracer.cpp:130-148; semantics emb/doc/README.md:6331-6415):
+ *      closest hit in (tnear, tfar]; on hit writes tfar, u, v, Ng, primID, geomID; a miss leaves the record
+ *      untouched.  Host array of n RTCRayHit-compatible records. */
+int pgrt_intersect(pgrt_context* ctx, pgrt_rayhit* rayhits_host, uint64_t n);
+/* rtcInterpolate0 (raytracer.cpp:252, :344): slot 0 -> 3 floats (normal), slot 1 -> 2 floats (uv), per query */
+int pgrt_interpolate(pgrt_context* ctx, const uint32_t* geom_id, const uint32_t* prim_id, const float* u, const float* v,
+                     uint64_t n, int32_t slot, float* out_host);
+
+/* ---- device implementations of the path's leaf functions, exposed for per-function parity tests */
+int pgrt_eval_mix_srgb(pgrt_context* ctx, const float* c0, const float* c1, const float* alpha, uint64_t n, float* out);  /* utils.cpp:238-241 */
+int pgrt_eval_texture(pgrt_context* ctx, int32_t tex_id, const float* uv, uint64_t n, float* out3);  /* Texture::get_texel texture.cpp:77-130; id -1 = env texture */
+int pgrt_eval_envmap(pgrt_context* ctx, const float* dirs, uint64_t n, float* out4);                 /* SphericalMap::get_texel SphericalMap.cpp:17-29 */
+int pgrt_eval_gamma(pgrt_context* ctx, const float* in4, float gamma_level, uint64_t n, float* out4); /* Raytracer::gamma raytracer.cpp:439-446 */
+int pgrt_eval_primary_rays(pgrt_context* ctx, const pgrt_render_params* p, float* out9);             /* get_pixel :405-416 + generate_ray; 9 floats/ray */
+int pgrt_eval_secondary_rays(pgrt_context* ctx, const float* in11, uint64_t n, int32_t refraction, float* out9);  /* raytracer.cpp:178-235 */
+
+/* ---- introspection */
+uint32_t pgrt_num_triangles(const pgrt_context* ctx);
+uint32_t pgrt_num_geometries(const pgrt_context* ctx);
+uint64_t pgrt_kernel_launches(const pgrt_context* ctx);   /* kernels launched by this context since creation */
+const char* pgrt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGRT_H_ */

@@ -1,0 +1,724 @@
+// pgrt_api.cu -- C-ABI of libpgrt_b200.so (include/pgrt.h): context, scene upload, GPU BVH commit, frame orchestration.
+// No CPU fallback lives here: every entry point that computes launches CUDA kernels or fails.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "common.cuh"
+#include "bvh_build.cuh"
+#include "render.cuh"
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct HostTex { DevBuf<uint8_t> bytes; int w = 0, h = 0, pitch = 0, bpp = 0; bool set = false; };
+
+enum KClass { KC_TRACE = 0, KC_SHADE = 1 };
+
+}  // namespace
+
+struct pgrt_context {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err = "";
+    uint64_t launches = 0;
+
+    // host staging of the scene (what LoadScene hands over, pg1/raytracer.cpp:71-125)
+    std::vector<float> h_pos, h_nrm, h_uv;
+    std::vector<uint32_t> h_tri_geom, h_geom_first;
+    std::vector<int32_t> h_geom_material;
+    std::vector<pgrt_material> h_materials;
+    std::vector<pgrt_light> h_lights;
+    std::vector<HostTex> textures;
+    HostTex env;
+
+    // device scene
+    DevBuf<float> d_pos, d_nrm, d_uv;
+    DevBuf<uint32_t> d_tri_geom, d_geom_first;
+    DevBuf<int32_t> d_geom_material;
+    DevBuf<pgrt_material> d_materials;
+    DevBuf<pgrt_light> d_lights;
+    DevBuf<DevTexture> d_textures;
+    DevBuf<float4> d_shade, d_tris, d_nodes;
+    uint32_t n_tris = 0, root = 0;
+    bool committed = false, tables_dirty = true;
+    pgrt_build_stats last_build = {};
+
+    DevCamera cam = {};
+    bool cam_set = false;
+    ShardInfo shard = {0, 1, 0, 0};
+
+    // frame state
+    LevelBufs levels[PGRT_MAX_LEVELS + 1] = {};
+    DevBuf<float4> lv_f4[PGRT_MAX_LEVELS + 1][5];
+    DevBuf<uint2> lv_child[PGRT_MAX_LEVELS + 1];
+    DevBuf<uint32_t> lv_list[PGRT_MAX_LEVELS + 1][2];
+    DevBuf<Counters> d_counters;
+    DevBuf<float4> d_frame;
+    DevBuf<uint32_t> d_ids;
+    Counters* h_counters = nullptr;   // pinned
+    size_t max_batch_samples = (size_t)1 << 23;
+    size_t min_level_cap = (size_t)1 << 18;
+    double level_cap_factor = 2.0;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_class;
+    cudaEvent_t ev_frame0 = nullptr, ev_frame1 = nullptr;
+
+    // get_pixel cache
+    std::vector<float> px_cache; pgrt_render_params px_params = {}; bool px_valid = false;
+
+    int fail(int code, const std::string& msg) { err = msg; return code; }
+    int fail_cuda(cudaError_t e, const char* what, const char* file, int line) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+        err = buf;
+        return PGRT_ERR_CUDA;
+    }
+    DevScene dev_scene() const {
+        DevScene s = {};
+        s.nodes = d_nodes.p; s.tris = d_tris.p; s.shade = d_shade.p; s.geom_first = d_geom_first.p; s.geom_material = d_geom_material.p;
+        s.materials = d_materials.p; s.textures = d_textures.p; s.n_textures = (int32_t)textures.size();
+        s.env.data = env.set ? env.bytes.p : nullptr; s.env.width = env.w; s.env.height = env.h; s.env.pitch = env.pitch; s.env.bpp = env.bpp;
+        s.lights = d_lights.p; s.n_lights = (int32_t)h_lights.size(); s.n_tris = n_tris; s.root = root;
+        return s;
+    }
+};
+
+#define CHECK_CTX(ctx) do { if (!(ctx)) return PGRT_ERR_INVALID; } while (0)
+#define LAUNCH_OK() CUDA_TRY(cudaGetLastError())
+
+static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// --------------------------------------------------------------------------------------------------- lifetime
+extern "C" const char* pgrt_version(void) { return "pgrt-b200 0.1 (sm_100a)"; }
+
+extern "C" int pgrt_create(pgrt_context** out, int device) {
+    if (!out) return PGRT_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return PGRT_ERR_NO_DEVICE;
+    pgrt_context* ctx = new pgrt_context();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return PGRT_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PGRT_ERR_CUDA; }
+    ctx->stream = ctx->own_stream;
+    cudaEventCreate(&ctx->ev_frame0); cudaEventCreate(&ctx->ev_frame1);
+    if (cudaMallocHost((void**)&ctx->h_counters, sizeof(Counters)) != cudaSuccess) { delete ctx; return PGRT_ERR_CUDA; }
+    if (ctx->d_counters.ensure(1) != cudaSuccess) { delete ctx; return PGRT_ERR_CUDA; }
+    if (const char* e = getenv("PGRT_MAX_BATCH_SAMPLES")) ctx->max_batch_samples = std::max<size_t>(256, strtoull(e, nullptr, 10));
+    if (const char* e = getenv("PGRT_MIN_LEVEL_CAP")) ctx->min_level_cap = std::max<size_t>(64, strtoull(e, nullptr, 10));
+    if (const char* e = getenv("PGRT_LEVEL_CAP_FACTOR")) ctx->level_cap_factor = std::max(0.01, atof(e));
+    *out = ctx;
+    return PGRT_OK;
+}
+
+static void free_scene_device(pgrt_context* ctx) {
+    ctx->d_pos.release(); ctx->d_nrm.release(); ctx->d_uv.release(); ctx->d_tri_geom.release(); ctx->d_geom_first.release();
+    ctx->d_geom_material.release(); ctx->d_shade.release(); ctx->d_tris.release(); ctx->d_nodes.release();
+}
+
+extern "C" void pgrt_destroy(pgrt_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_scene_device(ctx);
+    ctx->d_materials.release(); ctx->d_lights.release(); ctx->d_textures.release();
+    for (auto& t : ctx->textures) t.bytes.release();
+    ctx->env.bytes.release();
+    for (int l = 0; l <= PGRT_MAX_LEVELS; ++l) {
+        for (int k = 0; k < 5; ++k) ctx->lv_f4[l][k].release();
+        ctx->lv_child[l].release(); ctx->lv_list[l][0].release(); ctx->lv_list[l][1].release();
+    }
+    ctx->d_counters.release(); ctx->d_frame.release(); ctx->d_ids.release();
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->ev_frame0) cudaEventDestroy(ctx->ev_frame0);
+    if (ctx->ev_frame1) cudaEventDestroy(ctx->ev_frame1);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" const char* pgrt_last_error(const pgrt_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int pgrt_set_stream(pgrt_context* ctx, void* s) {
+    CHECK_CTX(ctx);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return PGRT_OK;
+}
+
+// --------------------------------------------------------------------------------------------------- scene
+extern "C" int pgrt_clear_scene(pgrt_context* ctx) {
+    CHECK_CTX(ctx);
+    ctx->h_pos.clear(); ctx->h_nrm.clear(); ctx->h_uv.clear(); ctx->h_tri_geom.clear(); ctx->h_geom_first.clear(); ctx->h_geom_material.clear();
+    ctx->n_tris = 0; ctx->committed = false; ctx->px_valid = false;
+    return PGRT_OK;
+}
+
+extern "C" int pgrt_add_mesh(pgrt_context* ctx, const float* pos, const float* nrm, const float* uv, uint32_t T, int32_t material_id, uint32_t* geom_id) {
+    CHECK_CTX(ctx);
+    if (T && (!pos || !nrm || !uv)) return ctx->fail(PGRT_ERR_INVALID, "pgrt_add_mesh: null buffer");
+    if ((uint64_t)ctx->h_tri_geom.size() + T >= (1ull << 29)) return ctx->fail(PGRT_ERR_INVALID, "pgrt_add_mesh: more than 2^29 triangles");
+    const uint32_t g = (uint32_t)ctx->h_geom_first.size();
+    ctx->h_geom_first.push_back((uint32_t)ctx->h_tri_geom.size());
+    ctx->h_geom_material.push_back(material_id);
+    ctx->h_pos.insert(ctx->h_pos.end(), pos, pos + 9 * (size_t)T);
+    ctx->h_nrm.insert(ctx->h_nrm.end(), nrm, nrm + 9 * (size_t)T);
+    ctx->h_uv.insert(ctx->h_uv.end(), uv, uv + 6 * (size_t)T);
+    ctx->h_tri_geom.insert(ctx->h_tri_geom.end(), T, g);
+    if (geom_id) *geom_id = g;
+    ctx->committed = false; ctx->px_valid = false;
+    return PGRT_OK;
+}
+
+extern "C" int pgrt_set_materials(pgrt_context* ctx, const pgrt_material* m, int32_t n) {
+    CHECK_CTX(ctx);
+    if (n < 0 || (n && !m)) return ctx->fail(PGRT_ERR_INVALID, "pgrt_set_materials: bad arguments");
+    ctx->h_materials.assign(m, m + n); ctx->tables_dirty = true; ctx->px_valid = false;
+    return PGRT_OK;
+}
+
+extern "C" int pgrt_set_lights(pgrt_context* ctx, const pgrt_light* l, int32_t n) {
+    CHECK_CTX(ctx);
+    if (n < 0 || (n && !l)) return ctx->fail(PGRT_ERR_INVALID, "pgrt_set_lights: bad arguments");
+    ctx->h_lights.assign(l, l + n); ctx->tables_dirty = true; ctx->px_valid = false;
+    return PGRT_OK;
+}
+
+static int upload_tex(pgrt_context* ctx, HostTex& t, const uint8_t* bytes, int w, int h, int pitch, int bpp) {
+    if (!bytes || w <= 0 || h <= 0 || (bpp != 3 && bpp != 4) || pitch < w * bpp) return ctx->fail(PGRT_ERR_INVALID, "texture: bad arguments");
+    cudaSetDevice(ctx->device);
+    CUDA_TRY(t.bytes.ensure((size_t)pitch * h + 4));
+    CUDA_TRY(cudaMemcpyAsync(t.bytes.p, bytes, (size_t)pitch * h, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    t.w = w; t.h = h; t.pitch = pitch; t.bpp = bpp; t.set = true;
+    ctx->tables_dirty = true; ctx->px_valid = false;
+    return PGRT_OK;
+}
+
+extern "C" int pgrt_set_texture(pgrt_context* ctx, int32_t id, const uint8_t* bytes, int32_t w, int32_t h, int32_t pitch, int32_t bpp) {
+    CHECK_CTX(ctx);
+    if (id < 0 || id > 4096) return ctx->fail(PGRT_ERR_INVALID, "pgrt_set_texture: bad id");
+    if ((size_t)id >= ctx->textures.size()) ctx->textures.resize(id + 1);
+    return upload_tex(ctx, ctx->textures[id], bytes, w, h, pitch, bpp);
+}
+
+extern "C" int pgrt_set_envmap(pgrt_context* ctx, const uint8_t* bytes, int32_t w, int32_t h, int32_t pitch, int32_t bpp) {
+    CHECK_CTX(ctx);
+    return upload_tex(ctx, ctx->env, bytes, w, h, pitch, bpp);
+}
+
+static int upload_tables(pgrt_context* ctx) {
+    if (!ctx->tables_dirty) return PGRT_OK;
+    cudaSetDevice(ctx->device);
+    for (const auto& m : ctx->h_geom_material)
+        if (m < 0 || (size_t)m >= ctx->h_materials.size()) return ctx->fail(PGRT_ERR_INVALID, "a mesh references a material id that was never set");
+    CUDA_TRY(ctx->d_materials.ensure(ctx->h_materials.size()));
+    if (!ctx->h_materials.empty()) CUDA_TRY(cudaMemcpyAsync(ctx->d_materials.p, ctx->h_materials.data(), ctx->h_materials.size() * sizeof(pgrt_material), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx->d_lights.ensure(ctx->h_lights.size()));
+    if (!ctx->h_lights.empty()) CUDA_TRY(cudaMemcpyAsync(ctx->d_lights.p, ctx->h_lights.data(), ctx->h_lights.size() * sizeof(pgrt_light), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<DevTexture> dt(ctx->textures.size());
+    for (size_t i = 0; i < dt.size(); ++i) {
+        const HostTex& t = ctx->textures[i];
+        dt[i].data = t.set ? t.bytes.p : nullptr; dt[i].width = t.w; dt[i].height = t.h; dt[i].pitch = t.pitch; dt[i].bpp = t.bpp;
+    }
+    for (const auto& m : ctx->h_materials)
+        if (m.diffuse_tex >= 0 && ((size_t)m.diffuse_tex >= dt.size() || !dt[m.diffuse_tex].data)) return ctx->fail(PGRT_ERR_INVALID, "a material references a texture id that was never set");
+    CUDA_TRY(ctx->d_textures.ensure(dt.size()));
+    if (!dt.empty()) CUDA_TRY(cudaMemcpyAsync(ctx->d_textures.p, dt.data(), dt.size() * sizeof(DevTexture), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->tables_dirty = false;
+    return PGRT_OK;
+}
+
+// --------------------------------------------------------------------------------------------------- commit (GPU BVH build)
+extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
+    CHECK_CTX(ctx);
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const uint32_t N = (uint32_t)ctx->h_tri_geom.size();
+    ctx->n_tris = N; ctx->px_valid = false;
+    pgrt_build_stats bs = {}; bs.triangles = N;
+    const uint32_t G = (uint32_t)ctx->h_geom_first.size();
+    CUDA_TRY(ctx->d_geom_first.ensure(G)); CUDA_TRY(ctx->d_geom_material.ensure(G));
+    if (G) {
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_geom_first.p, ctx->h_geom_first.data(), G * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_geom_material.p, ctx->h_geom_material.data(), G * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    }
+    ctx->tables_dirty = true;
+    if (N == 0) {
+        ctx->root = 0; ctx->committed = true; ctx->last_build = bs;
+        if (stats) *stats = bs;
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return PGRT_OK;
+    }
+    CUDA_TRY(ctx->d_pos.ensure(9 * (size_t)N)); CUDA_TRY(ctx->d_nrm.ensure(9 * (size_t)N)); CUDA_TRY(ctx->d_uv.ensure(6 * (size_t)N));
+    CUDA_TRY(ctx->d_tri_geom.ensure(N));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_pos.p, ctx->h_pos.data(), 9 * (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_nrm.p, ctx->h_nrm.data(), 9 * (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_uv.p, ctx->h_uv.data(), 6 * (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_tri_geom.p, ctx->h_tri_geom.data(), (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx->d_shade.ensure(4 * (size_t)N)); CUDA_TRY(ctx->d_tris.ensure(3 * (size_t)N)); CUDA_TRY(ctx->d_nodes.ensure(4 * (size_t)std::max<uint32_t>(N - 1, 1)));
+
+    cudaEvent_t e0, e1, e2, e3;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+    // build temporaries
+    DevBuf<uint64_t> keys[2]; DevBuf<uint32_t> vals[2]; DevBuf<uint32_t> hist; DevBuf<SceneBounds> sb; DevBuf<float> sah;
+    DevBuf<int> ti[6]; DevBuf<float> tf[2];
+    const uint32_t n_tiles = div_up(N, RS_TILE);
+    int rc = PGRT_OK;
+    auto cleanup = [&]() {
+        keys[0].release(); keys[1].release(); vals[0].release(); vals[1].release(); hist.release(); sb.release(); sah.release();
+        for (auto& b : ti) b.release(); for (auto& b : tf) b.release();
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+    };
+#define BUILD_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = ctx->fail_cuda(e__, #call, __FILE__, __LINE__); cleanup(); return rc; } } while (0)
+    BUILD_TRY(keys[0].ensure(N)); BUILD_TRY(keys[1].ensure(N)); BUILD_TRY(vals[0].ensure(N)); BUILD_TRY(vals[1].ensure(N));
+    BUILD_TRY(hist.ensure(256 * (size_t)n_tiles)); BUILD_TRY(sb.ensure(1)); BUILD_TRY(sah.ensure(1));
+    BUILD_TRY(ti[0].ensure(N)); BUILD_TRY(ti[1].ensure(N)); BUILD_TRY(ti[2].ensure(2 * (size_t)N)); BUILD_TRY(ti[3].ensure(N)); BUILD_TRY(ti[4].ensure(N)); BUILD_TRY(ti[5].ensure(N));
+    BUILD_TRY(tf[0].ensure(6 * (size_t)N)); BUILD_TRY(tf[1].ensure(6 * (size_t)N));
+
+    BUILD_TRY(cudaEventRecord(e0, st));
+    k_pack_shade<<<div_up(N, 256), 256, 0, st>>>(ctx->d_nrm.p, ctx->d_uv.p, ctx->d_tri_geom.p, N, ctx->d_shade.p);
+    k_init_bounds<<<1, 32, 0, st>>>(sb.p);
+    k_scene_bounds<<<std::min<unsigned>(div_up(N, 256), ctx->sm_count * 8), 256, 0, st>>>(ctx->d_pos.p, N, sb.p);
+    k_morton<<<div_up(N, 256), 256, 0, st>>>(ctx->d_pos.p, N, sb.p, keys[0].p, vals[0].p);
+    ctx->launches += 4;
+    BUILD_TRY(cudaEventRecord(e1, st));
+    int cur = 0;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = pass * 8;
+        k_rs_hist<<<n_tiles, RS_THREADS, 0, st>>>(keys[cur].p, N, shift, hist.p, n_tiles);
+        k_rs_scan<<<1, 1024, 0, st>>>(hist.p, 256 * n_tiles);
+        k_rs_scatter<<<n_tiles, RS_THREADS, 0, st>>>(keys[cur].p, vals[cur].p, keys[cur ^ 1].p, vals[cur ^ 1].p, N, shift, hist.p, n_tiles);
+        cur ^= 1; ctx->launches += 3;
+    }
+    BUILD_TRY(cudaEventRecord(e2, st));
+    k_emit_tris<<<div_up(N, 256), 256, 0, st>>>(ctx->d_pos.p, vals[cur].p, N, ctx->d_tris.p);
+    ctx->launches += 1;
+    if (N <= PGRT_LEAF_MAX) {
+        ctx->root = (uint32_t)leaf_ref(0, (int)N);
+        bs.nodes = 0; bs.sah_cost = (float)N;
+    } else {
+        BinTree t; t.left = ti[0].p; t.right = ti[1].p; t.parent = ti[2].p; t.first = ti[3].p; t.last = ti[4].p; t.flag = ti[5].p; t.lo = tf[0].p; t.hi = tf[1].p;
+        k_karras<<<div_up(N - 1, 256), 256, 0, st>>>(keys[cur].p, (int)N, t);
+        k_refit<<<div_up(N, 256), 256, 0, st>>>(ctx->d_pos.p, vals[cur].p, (int)N, t);
+        k_emit_bvh2<<<div_up(N - 1, 256), 256, 0, st>>>((int)N, t, ctx->d_nodes.p);
+        BUILD_TRY(cudaMemsetAsync(sah.p, 0, sizeof(float), st));
+        k_sah_cost<<<div_up(N - 1, 256), 256, 0, st>>>((int)N, t, sah.p);
+        ctx->launches += 4;
+        ctx->root = 0;
+        bs.nodes = N - 1;
+    }
+    BUILD_TRY(cudaEventRecord(e3, st));
+    BUILD_TRY(cudaGetLastError());
+    BUILD_TRY(cudaStreamSynchronize(st));
+    if (N > PGRT_LEAF_MAX) BUILD_TRY(cudaMemcpy(&bs.sah_cost, sah.p, sizeof(float), cudaMemcpyDeviceToHost));
+    cudaEventElapsedTime(&bs.build_ms, e0, e3);
+    cudaEventElapsedTime(&bs.sort_ms, e1, e2);
+#undef BUILD_TRY
+    cleanup();
+    ctx->committed = true; ctx->last_build = bs;
+    if (stats) *stats = bs;
+    return PGRT_OK;
+}
+
+// --------------------------------------------------------------------------------------------------- camera / params
+extern "C" int pgrt_set_camera(pgrt_context* ctx, int32_t width, int32_t height, float fov_y, const float from[3], const float at[3]) {
+    CHECK_CTX(ctx);
+    if (width <= 0 || height <= 0 || !from || !at) return ctx->fail(PGRT_ERR_INVALID, "pgrt_set_camera: bad arguments");
+    // PinHoleCamera::PinHoleCamera (PinHoleCamera.cpp:5-29); this file is compiled without FMA contraction on the host too
+    DevCamera c;
+    c.width = width; c.height = height;
+    c.f_y = height / (2 * tanf(fov_y / 2));
+    c.from = v3(from[0], from[1], from[2]);
+    const V3 up = v3(0.0f, 0.0f, 1.0f);
+    V3 z_c = c.from - v3(at[0], at[1], at[2]);
+    V3 x_c = cross3(up, z_c);
+    V3 y_c = cross3(z_c, x_c);
+    z_c = normalize3(z_c); x_c = normalize3(x_c); y_c = normalize3(y_c);
+    c.M.m00 = x_c.x; c.M.m01 = y_c.x; c.M.m02 = z_c.x;
+    c.M.m10 = x_c.y; c.M.m11 = y_c.y; c.M.m12 = z_c.y;
+    c.M.m20 = x_c.z; c.M.m21 = y_c.z; c.M.m22 = z_c.z;
+    ctx->cam = c; ctx->cam_set = true; ctx->px_valid = false;
+    ctx->shard.tiles_x = (width + PGRT_TILE_W - 1) / PGRT_TILE_W;
+    ctx->shard.tiles_y = (height + PGRT_TILE_H - 1) / PGRT_TILE_H;
+    return PGRT_OK;
+}
+
+extern "C" void pgrt_default_params(pgrt_render_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof *p);
+    p->sampling_width = 3; p->jitter = 1; p->focal_distance = 200.0f; p->aperture = 5.0f; p->max_depth = 7; p->gamma_level = 0.5f;
+    p->seed = 1; p->camera_mode = 0; p->shader_mode = 0;
+}
+
+extern "C" int pgrt_set_shard(pgrt_context* ctx, int32_t rank, int32_t n_ranks) {
+    CHECK_CTX(ctx);
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return ctx->fail(PGRT_ERR_INVALID, "pgrt_set_shard: bad rank");
+    ctx->shard.rank = rank; ctx->shard.n_ranks = n_ranks; ctx->px_valid = false;
+    return PGRT_OK;
+}
+
+static uint64_t shard_slots(const pgrt_context* ctx) {
+    const uint64_t tiles = (uint64_t)ctx->shard.tiles_x * ctx->shard.tiles_y;
+    return (tiles + ctx->shard.n_ranks - 1) / ctx->shard.n_ranks * PGRT_TILE_PIXELS;
+}
+extern "C" uint64_t pgrt_shard_pixels(const pgrt_context* ctx) { return ctx ? shard_slots(ctx) : 0; }
+
+// --------------------------------------------------------------------------------------------------- frame
+static int ensure_levels(pgrt_context* ctx, int n_levels, size_t cap0, size_t capn) {
+    for (int l = 0; l <= n_levels; ++l) {   // one spare level so k_shade always has a (never written) "next"
+        const size_t cap = l == 0 ? cap0 : (l == n_levels ? 1 : capn);
+        for (int k = 0; k < 5; ++k) CUDA_TRY(ctx->lv_f4[l][k].ensure(cap));
+        CUDA_TRY(ctx->lv_child[l].ensure(cap)); CUDA_TRY(ctx->lv_list[l][0].ensure(cap)); CUDA_TRY(ctx->lv_list[l][1].ensure(cap));
+        LevelBufs& L = ctx->levels[l];
+        L.ray_o = ctx->lv_f4[l][0].p; L.ray_d = ctx->lv_f4[l][1].p; L.hit = ctx->lv_f4[l][2].p; L.color = ctx->lv_f4[l][3].p; L.dn_att = ctx->lv_f4[l][4].p;
+        L.dn_child = ctx->lv_child[l].p; L.phong_list = ctx->lv_list[l][0].p; L.diel_list = ctx->lv_list[l][1].p;
+        L.cap = (uint32_t)cap;
+    }
+    return PGRT_OK;
+}
+
+struct FrameTimer {
+    pgrt_context* ctx; bool on; size_t used = 0;
+    void begin(int cls) {
+        if (!on) return;
+        if (used + 2 > ctx->ev_pool.size()) {
+            if (ctx->ev_pool.size() >= 16384) { on = false; return; }
+            for (int k = 0; k < 256; ++k) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
+            ctx->ev_class.resize(ctx->ev_pool.size() / 2);
+        }
+        ctx->ev_class[used / 2] = cls;
+        cudaEventRecord(ctx->ev_pool[used], ctx->stream);
+    }
+    void end() { if (!on) return; cudaEventRecord(ctx->ev_pool[used + 1], ctx->stream); used += 2; }
+};
+
+static int validate_frame(pgrt_context* ctx, const pgrt_render_params* p) {
+    if (!p) return ctx->fail(PGRT_ERR_INVALID, "render: null params");
+    if (!ctx->committed) return ctx->fail(PGRT_ERR_INVALID, "render: pgrt_commit has not been called since the scene changed");
+    if (!ctx->cam_set) return ctx->fail(PGRT_ERR_INVALID, "render: pgrt_set_camera has not been called");
+    if (p->sampling_width < 1 || p->sampling_width > 64) return ctx->fail(PGRT_ERR_INVALID, "render: sampling_width out of range [1,64]");
+    if (p->max_depth < 0 || p->max_depth >= PGRT_MAX_LEVELS) return ctx->fail(PGRT_ERR_INVALID, "render: max_depth out of range [0,32]");
+    return upload_tables(ctx);
+}
+
+// dest_mode: 0 = full frame (W*H float4), 1 = compact shard buffer, 2 = ids only (geom/prim in d_ids)
+static int render_frame(pgrt_context* ctx, const pgrt_render_params* p, float4* dest, int dest_mode, pgrt_render_stats* stats, int profile) {
+    int rc = validate_frame(ctx, p);
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const int S = p->sampling_width * p->sampling_width;
+    const int n_levels = (dest_mode == 2) ? 1 : p->max_depth + 1;
+    const uint64_t total_slots = shard_slots(ctx);
+    uint64_t batch_slots = std::max<uint64_t>(PGRT_TILE_PIXELS, ctx->max_batch_samples / S / PGRT_TILE_PIXELS * PGRT_TILE_PIXELS);
+    batch_slots = std::min(batch_slots, total_slots);
+    const DevScene sc = ctx->dev_scene();
+    const unsigned trace_grid = ctx->sm_count * 16, shade_grid = ctx->sm_count * 8;
+    pgrt_render_stats rs = {};
+    FrameTimer tm{ctx, profile != 0};
+    for (;;) {
+        const size_t cap0 = (size_t)batch_slots * S;
+        const size_t capn = std::max<size_t>(ctx->min_level_cap, (size_t)(ctx->level_cap_factor * (double)cap0));
+        rc = ensure_levels(ctx, n_levels, cap0, capn);
+        if (rc) return rc;
+        tm.used = 0; rs.launches = 0; rs.trace_launches = 0; rs.batches = 0;
+        Counters* cnt = ctx->d_counters.p;
+        CUDA_TRY(cudaEventRecord(ctx->ev_frame0, st));
+        k_frame_begin<<<1, 32, 0, st>>>(cnt); rs.launches++;
+        for (uint64_t slot0 = 0; slot0 < total_slots; slot0 += batch_slots) {
+            const uint32_t n_slots = (uint32_t)std::min<uint64_t>(batch_slots, total_slots - slot0);
+            const uint32_t n0 = n_slots * (uint32_t)S;
+            rs.batches++;
+            k_batch_begin<<<1, 64, 0, st>>>(cnt); rs.launches++;
+            tm.begin(KC_SHADE);
+            k_raygen<<<div_up(n0, 256), 256, 0, st>>>(ctx->cam, *p, ctx->shard, (uint32_t)slot0, n_slots, ctx->levels[0], cnt); rs.launches++;
+            tm.end();
+            for (int l = 0; l < n_levels; ++l) {
+                tm.begin(KC_TRACE);
+                k_trace<<<trace_grid, 128, 0, st>>>(sc, ctx->levels[l], &cnt->n_rays[l]); rs.launches++; rs.trace_launches++;
+                tm.end();
+                if (dest_mode == 2) break;
+                tm.begin(KC_SHADE);
+                k_shade<<<shade_grid, 256, 0, st>>>(sc, *p, l, ctx->levels[l], ctx->levels[l + 1], cnt); rs.launches++;
+                tm.end();
+                tm.begin(KC_TRACE);   // Phong = shading preamble + one inline shadow traversal per light
+                k_phong<<<trace_grid, 128, 0, st>>>(sc, *p, l, ctx->levels[l], cnt); rs.launches++; rs.trace_launches++;
+                tm.end();
+            }
+            if (dest_mode == 2) {
+                uint32_t* geom = ctx->d_ids.p; uint32_t* prim = geom + (size_t)ctx->cam.width * ctx->cam.height;
+                k_primary_ids<<<div_up(n_slots, 256), 256, 0, st>>>(sc, ctx->cam, ctx->shard, (uint32_t)slot0, n_slots, S, ctx->levels[0].hit, geom, prim); rs.launches++;
+            } else {
+                tm.begin(KC_SHADE);
+                for (int l = n_levels - 2; l >= 0; --l) { k_combine<<<shade_grid, 256, 0, st>>>(l, ctx->levels[l], ctx->levels[l + 1], cnt); rs.launches++; }
+                k_resolve<<<div_up(n_slots, 256), 256, 0, st>>>(ctx->cam, *p, ctx->shard, (uint32_t)slot0, n_slots, ctx->levels[0].color, dest, dest_mode == 1); rs.launches++;
+                tm.end();
+            }
+            unsigned long long valid_px;
+            {   // primary rays = valid pixels of this batch * S (host-side count; partial tiles hold unused slots)
+                uint64_t v = 0;
+                const uint32_t W = ctx->cam.width, H = ctx->cam.height;
+                for (uint64_t k = slot0 / PGRT_TILE_PIXELS; k < (slot0 + n_slots) / PGRT_TILE_PIXELS; ++k) {
+                    const uint64_t t = k * ctx->shard.n_ranks + ctx->shard.rank;
+                    if (t >= (uint64_t)ctx->shard.tiles_x * ctx->shard.tiles_y) continue;
+                    const uint32_t tx = (uint32_t)(t % ctx->shard.tiles_x), ty = (uint32_t)(t / ctx->shard.tiles_x);
+                    const uint32_t w = std::min<uint32_t>(PGRT_TILE_W, W - tx * PGRT_TILE_W), h = std::min<uint32_t>(PGRT_TILE_H, H - ty * PGRT_TILE_H);
+                    v += (uint64_t)w * h;
+                }
+                valid_px = v * S;
+            }
+            k_batch_end<<<1, 32, 0, st>>>(cnt, valid_px); rs.launches++;
+        }
+        CUDA_TRY(cudaEventRecord(ctx->ev_frame1, st));
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_counters, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        LAUNCH_OK();
+        CUDA_TRY(cudaStreamSynchronize(st));
+        ctx->launches += rs.launches;
+        if (!ctx->h_counters->overflow) break;
+        rs.overflow_retries++;
+        if (batch_slots <= PGRT_TILE_PIXELS) return ctx->fail(PGRT_ERR_OVERFLOW, "render: secondary-ray queues overflow at the minimum batch; raise PGRT_MIN_LEVEL_CAP");
+        batch_slots = std::max<uint64_t>(PGRT_TILE_PIXELS, batch_slots / 2 / PGRT_TILE_PIXELS * PGRT_TILE_PIXELS);
+    }
+    rs.rays_primary = ctx->h_counters->tot_primary; rs.rays_shadow = ctx->h_counters->tot_shadow;
+    rs.rays_reflection = ctx->h_counters->tot_reflection; rs.rays_refraction = ctx->h_counters->tot_refraction;
+    cudaEventElapsedTime(&rs.frame_ms, ctx->ev_frame0, ctx->ev_frame1);
+    if (profile) {
+        for (size_t k = 0; k + 1 < tm.used + 1 && k < tm.used; k += 2) {
+            float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
+            if (ctx->ev_class[k / 2] == KC_TRACE) rs.trace_ms += ms; else rs.shade_ms += ms;
+        }
+    }
+    if (stats) *stats = rs;
+    return PGRT_OK;
+}
+
+extern "C" int pgrt_render_device(pgrt_context* ctx, const pgrt_render_params* p, void* rgba_device, pgrt_render_stats* stats, int32_t profile) {
+    CHECK_CTX(ctx);
+    if (!rgba_device) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_device: null destination");
+    if (ctx->shard.n_ranks != 1) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_device: context is sharded; use pgrt_render_shard_device");
+    return render_frame(ctx, p, (float4*)rgba_device, 0, stats, profile);
+}
+
+extern "C" int pgrt_render(pgrt_context* ctx, const pgrt_render_params* p, float* rgba_host, pgrt_render_stats* stats, int32_t profile) {
+    CHECK_CTX(ctx);
+    if (!rgba_host) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render: null destination");
+    if (ctx->shard.n_ranks != 1) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render: context is sharded; use pgrt_render_shard_device");
+    if (!ctx->cam_set) return ctx->fail(PGRT_ERR_INVALID, "render: pgrt_set_camera has not been called");
+    cudaSetDevice(ctx->device);
+    const size_t npx = (size_t)ctx->cam.width * ctx->cam.height;
+    CUDA_TRY(ctx->d_frame.ensure(npx));
+    int rc = render_frame(ctx, p, ctx->d_frame.p, 0, stats, profile);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(rgba_host, ctx->d_frame.p, npx * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PGRT_OK;
+}
+
+extern "C" int pgrt_get_pixel(pgrt_context* ctx, const pgrt_render_params* p, int32_t x, int32_t y, float rgba[4]) {
+    CHECK_CTX(ctx);
+    if (!p || !rgba || !ctx->cam_set || x < 0 || y < 0 || x >= ctx->cam.width || y >= ctx->cam.height) return ctx->fail(PGRT_ERR_INVALID, "pgrt_get_pixel: bad arguments");
+    if (!ctx->px_valid || memcmp(&ctx->px_params, p, sizeof *p) != 0) {
+        ctx->px_cache.resize((size_t)ctx->cam.width * ctx->cam.height * 4);
+        int rc = pgrt_render(ctx, p, ctx->px_cache.data(), nullptr, 0);
+        if (rc) return rc;
+        ctx->px_params = *p; ctx->px_valid = true;
+    }
+    memcpy(rgba, &ctx->px_cache[((size_t)y * ctx->cam.width + x) * 4], 16);
+    return PGRT_OK;
+}
+
+extern "C" int pgrt_primary_ids(pgrt_context* ctx, const pgrt_render_params* p, uint32_t* geom_host, uint32_t* prim_host) {
+    CHECK_CTX(ctx);
+    if (!geom_host || !prim_host) return ctx->fail(PGRT_ERR_INVALID, "pgrt_primary_ids: null destination");
+    if (!ctx->cam_set) return ctx->fail(PGRT_ERR_INVALID, "render: pgrt_set_camera has not been called");
+    cudaSetDevice(ctx->device);
+    const size_t npx = (size_t)ctx->cam.width * ctx->cam.height;
+    CUDA_TRY(ctx->d_ids.ensure(2 * npx));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_ids.p, 0xFF, 2 * npx * sizeof(uint32_t), ctx->stream));
+    int rc = render_frame(ctx, p, nullptr, 2, nullptr, 0);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(geom_host, ctx->d_ids.p, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(prim_host, ctx->d_ids.p + npx, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PGRT_OK;
+}
+
+extern "C" int pgrt_render_shard_device(pgrt_context* ctx, const pgrt_render_params* p, void* shard_rgba_device, pgrt_render_stats* stats, int32_t profile) {
+    CHECK_CTX(ctx);
+    if (!shard_rgba_device) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_shard_device: null destination");
+    return render_frame(ctx, p, (float4*)shard_rgba_device, 1, stats, profile);
+}
+
+extern "C" int pgrt_untile(pgrt_context* ctx, const void* gathered_device, int32_t n_ranks, void* rgba_device) {
+    CHECK_CTX(ctx);
+    if (!gathered_device || !rgba_device || n_ranks < 1 || !ctx->cam_set) return ctx->fail(PGRT_ERR_INVALID, "pgrt_untile: bad arguments");
+    cudaSetDevice(ctx->device);
+    const uint64_t tiles = (uint64_t)ctx->shard.tiles_x * ctx->shard.tiles_y;
+    const uint32_t spr = (uint32_t)((tiles + n_ranks - 1) / n_ranks * PGRT_TILE_PIXELS);
+    k_untile<<<div_up((size_t)spr * n_ranks, 256), 256, 0, ctx->stream>>>(ctx->cam, n_ranks, ctx->shard.tiles_x, ctx->shard.tiles_y, spr, (const float4*)gathered_device, (float4*)rgba_device);
+    ctx->launches++;
+    LAUNCH_OK();
+    return PGRT_OK;
+}
+
+// --------------------------------------------------------------------------------------------------- batch queries
+extern "C" int pgrt_intersect(pgrt_context* ctx, pgrt_rayhit* rh, uint64_t n) {
+    CHECK_CTX(ctx);
+    if (!ctx->committed) return ctx->fail(PGRT_ERR_INVALID, "pgrt_intersect: scene not committed");
+    if (n == 0) return PGRT_OK;
+    if (!rh) return ctx->fail(PGRT_ERR_INVALID, "pgrt_intersect: null rays");
+    int rc = upload_tables(ctx); if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    DevBuf<pgrt_rayhit> d;
+    CUDA_TRY(d.ensure(n));
+    cudaError_t e = cudaMemcpyAsync(d.p, rh, n * sizeof(pgrt_rayhit), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        k_intersect<<<std::min<unsigned>(div_up(n, 128), ctx->sm_count * 16), 128, 0, ctx->stream>>>(ctx->dev_scene(), ctx->d_pos.p, d.p, n);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rh, d.p, n * sizeof(pgrt_rayhit), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    d.release();
+    if (e != cudaSuccess) return ctx->fail_cuda(e, "pgrt_intersect", __FILE__, __LINE__);
+    return PGRT_OK;
+}
+
+namespace {
+// small RAII helper for the eval entry points: host -> device -> kernel -> host
+struct Scratch {
+    std::vector<void*> ptrs;
+    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+    void* up(const void* h, size_t bytes, cudaStream_t st) {
+        void* d = nullptr;
+        if (cudaMalloc(&d, std::max<size_t>(bytes, 16)) != cudaSuccess) return nullptr;
+        ptrs.push_back(d);
+        if (h && cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return nullptr;
+        return d;
+    }
+};
+}  // namespace
+
+#define EVAL_FINISH(dptr, hptr, bytes)                                                                  \
+    do {                                                                                                \
+        ctx->launches++;                                                                                \
+        CUDA_TRY(cudaGetLastError());                                                                   \
+        CUDA_TRY(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));              \
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));                                                   \
+        return PGRT_OK;                                                                                 \
+    } while (0)
+
+extern "C" int pgrt_interpolate(pgrt_context* ctx, const uint32_t* geom, const uint32_t* prim, const float* u, const float* v, uint64_t n, int32_t slot, float* out) {
+    CHECK_CTX(ctx);
+    if (!ctx->committed || !geom || !prim || !u || !v || !out || (slot != 0 && slot != 1)) return ctx->fail(PGRT_ERR_INVALID, "pgrt_interpolate: bad arguments");
+    for (uint64_t i = 0; i < n; ++i) {
+        if (geom[i] >= ctx->h_geom_first.size()) return ctx->fail(PGRT_ERR_INVALID, "pgrt_interpolate: geomID out of range");
+        const uint32_t end = geom[i] + 1 < ctx->h_geom_first.size() ? ctx->h_geom_first[geom[i] + 1] : ctx->n_tris;
+        if (ctx->h_geom_first[geom[i]] + prim[i] >= end) return ctx->fail(PGRT_ERR_INVALID, "pgrt_interpolate: primID out of range");
+    }
+    cudaSetDevice(ctx->device);
+    Scratch s; const size_t w = slot == 0 ? 3 : 2;
+    void* dg = s.up(geom, n * 4, ctx->stream); void* dp = s.up(prim, n * 4, ctx->stream); void* du = s.up(u, n * 4, ctx->stream); void* dv = s.up(v, n * 4, ctx->stream);
+    void* dout = s.up(nullptr, n * w * 4, ctx->stream);
+    if (!dg || !dp || !du || !dv || !dout) return ctx->fail(PGRT_ERR_CUDA, "pgrt_interpolate: allocation failed");
+    k_interpolate<<<div_up(n, 256), 256, 0, ctx->stream>>>(ctx->dev_scene(), (uint32_t*)dg, (uint32_t*)dp, (float*)du, (float*)dv, n, slot, (float*)dout);
+    EVAL_FINISH(dout, out, n * w * 4);
+}
+
+extern "C" int pgrt_eval_mix_srgb(pgrt_context* ctx, const float* c0, const float* c1, const float* alpha, uint64_t n, float* out) {
+    CHECK_CTX(ctx);
+    if (!c0 || !c1 || !alpha || !out) return ctx->fail(PGRT_ERR_INVALID, "pgrt_eval_mix_srgb: null buffer");
+    cudaSetDevice(ctx->device);
+    Scratch s;
+    void* a = s.up(c0, n * 16, ctx->stream); void* b = s.up(c1, n * 16, ctx->stream); void* al = s.up(alpha, n * 4, ctx->stream); void* o = s.up(nullptr, n * 16, ctx->stream);
+    if (!a || !b || !al || !o) return ctx->fail(PGRT_ERR_CUDA, "pgrt_eval_mix_srgb: allocation failed");
+    k_eval_mix<<<div_up(n, 256), 256, 0, ctx->stream>>>((float4*)a, (float4*)b, (float*)al, n, (float4*)o);
+    EVAL_FINISH(o, out, n * 16);
+}
+
+extern "C" int pgrt_eval_texture(pgrt_context* ctx, int32_t tex_id, const float* uv, uint64_t n, float* out3) {
+    CHECK_CTX(ctx);
+    if (!uv || !out3) return ctx->fail(PGRT_ERR_INVALID, "pgrt_eval_texture: null buffer");
+    const HostTex* t = tex_id < 0 ? &ctx->env : ((size_t)tex_id < ctx->textures.size() ? &ctx->textures[tex_id] : nullptr);
+    if (!t || !t->set) return ctx->fail(PGRT_ERR_INVALID, "pgrt_eval_texture: no such texture");
+    cudaSetDevice(ctx->device);
+    DevTexture dt; dt.data = t->bytes.p; dt.width = t->w; dt.height = t->h; dt.pitch = t->pitch; dt.bpp = t->bpp;
+    Scratch s;
+    void* d = s.up(uv, n * 8, ctx->stream); void* o = s.up(nullptr, n * 12, ctx->stream);
+    if (!d || !o) return ctx->fail(PGRT_ERR_CUDA, "pgrt_eval_texture: allocation failed");
+    k_eval_texture<<<div_up(n, 256), 256, 0, ctx->stream>>>(dt, (float2*)d, n, (float*)o);
+    EVAL_FINISH(o, out3, n * 12);
+}
+
+extern "C" int pgrt_eval_envmap(pgrt_context* ctx, const float* dirs, uint64_t n, float* out4) {
+    CHECK_CTX(ctx);
+    if (!dirs || !out4) return ctx->fail(PGRT_ERR_INVALID, "pgrt_eval_envmap: null buffer");
+    cudaSetDevice(ctx->device);
+    DevTexture dt; dt.data = ctx->env.set ? ctx->env.bytes.p : nullptr; dt.width = ctx->env.w; dt.height = ctx->env.h; dt.pitch = ctx->env.pitch; dt.bpp = ctx->env.bpp;
+    Scratch s;
+    void* d = s.up(dirs, n * 12, ctx->stream); void* o = s.up(nullptr, n * 16, ctx->stream);
+    if (!d || !o) return ctx->fail(PGRT_ERR_CUDA, "pgrt_eval_envmap: allocation failed");
+    k_eval_env<<<div_up(n, 256), 256, 0, ctx->stream>>>(dt, (float*)d, n, (float4*)o);
+    EVAL_FINISH(o, out4, n * 16);
+}
+
+extern "C" int pgrt_eval_gamma(pgrt_context* ctx, const float* in4, float gamma_level, uint64_t n, float* out4) {
+    CHECK_CTX(ctx);
+    if (!in4 || !out4) return ctx->fail(PGRT_ERR_INVALID, "pgrt_eval_gamma: null buffer");
+    cudaSetDevice(ctx->device);
+    Scratch s;
+    void* d = s.up(in4, n * 16, ctx->stream); void* o = s.up(nullptr, n * 16, ctx->stream);
+    if (!d || !o) return ctx->fail(PGRT_ERR_CUDA, "pgrt_eval_gamma: allocation failed");
+    k_eval_gamma<<<div_up(n, 256), 256, 0, ctx->stream>>>((float4*)d, gamma_level, n, (float4*)o);
+    EVAL_FINISH(o, out4, n * 16);
+}
+
+extern "C" int pgrt_eval_primary_rays(pgrt_context* ctx, const pgrt_render_params* p, float* out9) {
+    CHECK_CTX(ctx);
+    if (!p || !out9 || !ctx->cam_set || p->sampling_width < 1) return ctx->fail(PGRT_ERR_INVALID, "pgrt_eval_primary_rays: bad arguments");
+    cudaSetDevice(ctx->device);
+    const uint64_t n = (uint64_t)ctx->cam.width * ctx->cam.height * p->sampling_width * p->sampling_width;
+    Scratch s;
+    void* o = s.up(nullptr, n * 36, ctx->stream);
+    if (!o) return ctx->fail(PGRT_ERR_CUDA, "pgrt_eval_primary_rays: allocation failed");
+    k_eval_primary<<<div_up(n, 256), 256, 0, ctx->stream>>>(ctx->cam, *p, (float*)o);
+    EVAL_FINISH(o, out9, n * 36);
+}
+
+extern "C" int pgrt_eval_secondary_rays(pgrt_context* ctx, const float* in11, uint64_t n, int32_t refraction, float* out9) {
+    CHECK_CTX(ctx);
+    if (!in11 || !out9) return ctx->fail(PGRT_ERR_INVALID, "pgrt_eval_secondary_rays: null buffer");
+    cudaSetDevice(ctx->device);
+    Scratch s;
+    void* d = s.up(in11, n * 44, ctx->stream); void* o = s.up(nullptr, n * 36, ctx->stream);
+    if (!d || !o) return ctx->fail(PGRT_ERR_CUDA, "pgrt_eval_secondary_rays: allocation failed");
+    k_eval_secondary<<<div_up(n, 256), 256, 0, ctx->stream>>>((float*)d, n, refraction, (float*)o);
+    EVAL_FINISH(o, out9, n * 36);
+}
+
+// --------------------------------------------------------------------------------------------------- introspection
+extern "C" uint32_t pgrt_num_triangles(const pgrt_context* ctx) { return ctx ? (uint32_t)ctx->h_tri_geom.size() : 0; }
+extern "C" uint32_t pgrt_num_geometries(const pgrt_context* ctx) { return ctx ? (uint32_t)ctx->h_geom_first.size() : 0; }
+extern "C" uint64_t pgrt_kernel_launches(const pgrt_context* ctx) { return ctx ? ctx->launches : 0; }
