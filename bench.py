@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 render loop (BASELINE.json metric: Mrays/s, avenger Whitted 1080p).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+A "step" is one frame = one pass of the hot path (pg1/simpleguidx11.cpp:95-118) over every pixel of the frame.
+Workload (N=1 default) = BASELINE.json configs[1]: avenger (stand-in mesh, the reference's OBJ is absent) 1920x1080,
+Whitted, depth cut-off 10, 1 spp un-jittered.  For N>1 the same frame is cut into 32x8 tiles dealt round-robin to
+the ranks (strong scaling: total work fixed) and gathered to rank 0 over NCCL every step.
+
+value  : rays/s of whole frames, scene resident in HBM, timed with CUDA events per step, L2 flushed between steps.
+e2e    : the same metric through the host-buffer C-ABI call (pgrt_set_camera + pgrt_render into pinned host memory).
+--impl reference : the CPU restatement of the reference's loop (oracle/; the reference itself cannot be built here)
+                   on all host cores, same config, same metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mrays/s (prim+secondary), avenger Whitted 1080p"
+UNIT = "Mrays/s"
+
+
+def workload(name: str):
+    """Scene + params + config description of a named BASELINE.json config."""
+    from pgi_raytracing_b200 import scenes
+
+    if name == "c1":
+        sc = scenes.avenger_proxy()
+        p = dict(sampling_width=1, jitter=0, aperture=0.0, max_depth=7)
+        desc = "C1 avenger(stand-in) 640x480 Whitted depth7 1spp"
+    elif name == "c2":
+        sc = scenes.avenger_proxy()
+        sc.camera = scenes.Camera(1920, 1080, sc.camera.fov_y, sc.camera.view_from, sc.camera.view_at)
+        p = dict(sampling_width=1, jitter=0, aperture=0.0, max_depth=10)
+        desc = "C2 avenger(stand-in) 1920x1080 Whitted depth10 1spp"
+    elif name == "c3":
+        sc = scenes.avenger_proxy()
+        sc.camera = scenes.Camera(3840, 2160, sc.camera.fov_y, sc.camera.view_from, sc.camera.view_at)
+        p = dict(sampling_width=8, jitter=1, aperture=5.0, focal_distance=200.0, max_depth=7, seed=1)
+        desc = "C3 avenger(stand-in) 3840x2160 thin-lens f200 a5 64spp depth7"
+    elif name == "c5":
+        sc = scenes.triangle_soup(10_000_000, seed=1)
+        p = dict(sampling_width=2, jitter=1, aperture=0.0, max_depth=7, seed=1, shader_mode=1)
+        desc = "C5 soup 10M tris 3840x2160 Lambert 4spp"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return sc, p, desc
+
+
+def algorithmic_bytes_per_ray(n_tris: int) -> float:
+    """SURVEY.md section 8(d) contract figure: 32 (ray in) + 16 (hit out) + 80*D + 4*48, D = ceil(log8(N/4))."""
+    d = max(1, math.ceil(math.log(max(n_tris, 8) / 4.0, 8)))
+    return 48.0 + 80.0 * d + 192.0
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle restatement of the reference loop on all host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle.oracle import Oracle, make_params
+
+    sc, p, desc = workload(args.workload)
+    orc = Oracle(sc)
+    cores = orc.max_threads()
+    W, H = sc.camera.width, sc.camera.height
+    # bounded sample: a centred horizontal band of the frame sized to keep each step around a second
+    S = p["sampling_width"] ** 2
+    rows = H if W * H * S <= 4_000_000 else max(8, int(4_000_000 / (W * S)) // 8 * 8)
+    y0 = (H - rows) // 2
+    region = (0, y0, W, y0 + rows)
+    pr = make_params(**p)
+    for _ in range(args.warmup):
+        orc.render(pr, want_ids=False, threads=0, region=region)
+    t0 = time.perf_counter(); rays = 0
+    for _ in range(args.steps):
+        _, _, _, st = orc.render(pr, want_ids=False, threads=0, region=region)
+        rays += st["total"]
+    dt = time.perf_counter() - t0
+    v = rays / dt / 1e6
+    sample = f"rows {y0}..{y0 + rows} of {H} ({rows * W} px x {S} spp) per step, all host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "note": "CPU restatement of the reference loop (oracle/): the Windows/D3D11/Embree reference cannot be built here"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline(sc, p, budget_s=12.0):
+    """Oracle timed on the host cores on a bounded sample of the same workload."""
+    from oracle.oracle import Oracle, make_params
+
+    orc = Oracle(sc)
+    cores = orc.max_threads()
+    W, H = sc.camera.width, sc.camera.height
+    S = p["sampling_width"] ** 2
+    rows = H if W * H * S <= 4_000_000 else max(8, int(4_000_000 / (W * S)) // 8 * 8)
+    y0 = (H - rows) // 2
+    region = (0, y0, W, y0 + rows)
+    pr = make_params(**p)
+    orc.render(pr, want_ids=False, threads=0, region=region)
+    t0 = time.perf_counter(); rays = 0; n = 0
+    while True:
+        _, _, _, st = orc.render(pr, want_ids=False, threads=0, region=region)
+        rays += st["total"]; n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 20:
+            break
+    dt = time.perf_counter() - t0
+    # one-thread figure (the reference as shipped renders on one thread, pg1/simpleguidx11.cpp:104) on a thin band
+    band = (0, H // 2 - 4, W, H // 2 + 4)
+    t1 = time.perf_counter()
+    _, _, _, st1 = orc.render(pr, want_ids=False, threads=1, region=band)
+    dt1 = time.perf_counter() - t1
+    return {"value": rays / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} x rows {y0}..{y0 + rows} of {H} at {W} px x {S} spp, all {cores} host threads; single-thread {st1['total'] / dt1 / 1e6:.3f} Mrays/s on 8 rows"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from pgi_raytracing_b200 import raytracer_for, default_params
+    from pgi_raytracing_b200.dist import ShardedRenderer
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the render loop has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    sc, p, desc = workload(args.workload)
+    rt = raytracer_for(sc, device=local)
+    stream = torch.cuda.current_stream()
+    rt.set_stream(stream.cuda_stream)
+    params = default_params(**p)
+    sr = ShardedRenderer(rt, rank, world, dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        sr.render(params)
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    rays = 0; launches = 0; trace_ms = 0.0; trace_launches = 0; stats = None
+    launches0 = rt.kernel_launches()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        barrier()
+        ev[k][0].record(stream)
+        stats = sr.render(params, profile=True)
+        ev[k][1].record(stream)
+        rays += stats["total"]; trace_ms += stats["trace_ms"]; trace_launches += stats["trace_launches"]
+    barrier()
+    launches = rt.kernel_launches() - launches0
+    clocks = sampler.stop()
+    step_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(rays), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    total_ms = float(step_ms.item()); total_rays = float(tot[0].item())
+    value = total_rays / (total_ms * 1e-3) / 1e6
+
+    # e2e: host-buffer C-ABI call, camera re-sent every step, framebuffer copied back to pinned host memory every step
+    e2e = None
+    if world == 1:
+        rt.set_shard(0, 1)
+        host = torch.empty((rt.height, rt.width, 4), dtype=torch.float32).pin_memory()
+        c = sc.camera
+        for _ in range(3):
+            rt.render_host_ptr(host.data_ptr(), params)
+        torch.cuda.synchronize()
+        e_rays = 0; t_e2e = 0.0
+        for k in range(args.steps):
+            flush.fill_(k & 0xFF); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rt.set_camera(c.width, c.height, c.fov_y, c.view_from, c.view_at)
+            st = rt.render_host_ptr(host.data_ptr(), params)
+            t_e2e += time.perf_counter() - t0
+            e_rays += st["total"]
+        e2e = {"value": e_rays / t_e2e / 1e6, "unit": UNIT, "h2d_bytes_per_step": 4 * (2 + 1 + 3 + 3) + 64,
+               "d2h_bytes_per_step": rt.width * rt.height * 16, "ms_per_step": t_e2e / args.steps * 1e3}
+    else:
+        # multi-GPU e2e: rank 0 additionally copies the gathered frame to pinned host memory every step
+        host = torch.empty((rt.height, rt.width, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+        barrier()
+        t0 = time.perf_counter(); e_rays = 0
+        for k in range(args.steps):
+            st = sr.render(params)
+            if rank == 0:
+                host.copy_(sr.frame, non_blocking=True)
+            torch.cuda.synchronize()
+            e_rays += st["total"]
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        er = torch.tensor([float(e_rays)], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX); dist.all_reduce(er, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(er.item()) / float(dt.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 4 * (2 + 1 + 3 + 3) + 64,
+               "d2h_bytes_per_step": rt.width * rt.height * 16, "ms_per_step": float(dt.item()) / args.steps * 1e3}
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        b_ray = algorithmic_bytes_per_ray(sc.ntris)
+        rays_per_rank = rays   # rank 0's own rays and kernel times
+        achieved = rays_per_rank * b_ray / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (achieved / peaks["hbm_gbs"]) if achieved else None,
+                "traffic": None, "kernel": "k_trace + k_phong (closest-hit traversal launches)", "bytes_per_ray": b_ray,
+                "launch_ms_avg": trace_ms / max(trace_launches, 1), "peak_kind": peak_kind,
+                "note": "algorithmic bytes = SURVEY 8(d) contract figure x rays traced; the avenger working set is L2-resident, see DESIGN.md"}
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic", "config": {"workload": desc, "triangles": sc.ntris, "rays_per_frame": total_rays / args.steps,
+                                                "parallelism": f"tiles32x8/rr x{world}", "l2": "flushed between timed steps (256 MiB fill)",
+                                                "bvh": rt.build_stats},
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(tot[1].item()), "roofline": roof}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(sc, p)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -192,6 +192,15 @@ class Oracle:
         self.lib.orc_secondary_rays(_p(items), C.c_uint64(items.shape[0]), int(refraction), _p(out))
         return out
 
+    def interpolate(self, geom, prim, u, v, slot: int) -> np.ndarray:
+        geom = np.ascontiguousarray(geom, np.uint32); prim = np.ascontiguousarray(prim, np.uint32)
+        u = np.ascontiguousarray(u, np.float32); v = np.ascontiguousarray(v, np.float32)
+        out = np.zeros((geom.shape[0], 3 if slot == 0 else 2), np.float32)
+        rc = self.lib.orc_interpolate(self.h, _p(geom), _p(prim), _p(u), _p(v), C.c_uint64(geom.shape[0]), int(slot), _p(out))
+        if rc:
+            raise RuntimeError("orc_interpolate: id out of range")
+        return out
+
     def rng_u01(self, seed, pixel, sample, dim) -> float:
         return float(self.lib.orc_rng_u01(seed, pixel, sample, dim))
 

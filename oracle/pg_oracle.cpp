@@ -790,6 +790,19 @@ void orc_secondary_rays(const float* in, uint64_t n, int refraction, float* out)
         o[0] = r.ox; o[1] = r.oy; o[2] = r.oz; o[3] = r.tnear; o[4] = r.dx; o[5] = r.dy; o[6] = r.dz; o[7] = r.time; o[8] = r.tfar;
     }
 }
+// rtcInterpolate0 (raytracer.cpp:252, :344): slot 0 -> normal (3 floats), slot 1 -> uv (2 floats)
+int orc_interpolate(void* h, const uint32_t* geom, const uint32_t* prim, const float* u, const float* v, uint64_t n, int slot, float* out) {
+    Scene& s = *(Scene*)h; FtzGuard g;
+    orc_params p = {}; Tracer tr(s, p, true);
+    for (uint64_t i = 0; i < n; ++i) {
+        if (geom[i] >= s.geom_first.size()) return 1;
+        Hit hit = {0.0f, u[i], v[i], s.geom_first[geom[i]] + prim[i]};
+        if (hit.tri >= s.ntris()) return 1;
+        if (slot == 0) { const V3 nn = tr.interp_normal(hit); out[3 * i] = nn.x; out[3 * i + 1] = nn.y; out[3 * i + 2] = nn.z; }
+        else tr.interp_uv(hit, out[2 * i], out[2 * i + 1]);
+    }
+    return 0;
+}
 float orc_rng_u01(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t dim) { return rng_u01(seed, pixel, sample, dim); }
 int orc_max_threads() {
 #ifdef _OPENMP

@@ -1,0 +1,352 @@
+"""Parity of the CUDA path with the CPU oracle, through the C ABI (``libpgrt_b200.so``), on the B200.
+
+Bars (BASELINE.json north_star / SURVEY.md section 8d): primary (geomID, primID) equal on >= 99.9 % of pixels; 8-bit
+image within 2 LSB on >= 99.5 % of pixels and PSNR >= 45 dB; ray counts within 0.1 %; intersection records
+(t, u, v, ids) bit-exact; integer / index work bit-exact.  Tolerances for floating point are written at each test.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden
+from pgi_raytracing_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+INVALID = 0xFFFFFFFF
+
+
+@pytest.fixture(scope="module")
+def P():
+    import pgi_raytracing_b200 as p
+    return p
+
+
+@pytest.fixture(scope="module")
+def cornell_pair(P, oracle_mod, cornell):
+    return P.raytracer_for(cornell), oracle_mod.Oracle(cornell)
+
+
+@pytest.fixture(scope="module")
+def avenger(P, oracle_mod):
+    sc = scenes.avenger_proxy()
+    return sc, P.raytracer_for(sc), oracle_mod.Oracle(sc)
+
+
+def image_bars(P, ref, img):
+    a, b = P.to_srgb8(ref).astype(int), P.to_srgb8(img).astype(int)
+    d = np.abs(a - b).max(axis=-1)
+    mse = np.mean((a - b) ** 2.0)
+    psnr = 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+    return float(np.mean(d <= 2)), psnr
+
+
+# ------------------------------------------------------------------------------------------------ known answers
+def test_T1_through_the_abi(P, oracle_mod):
+    """pg1/tutorials.cpp:142-167 through pgrt_intersect / pgrt_interpolate."""
+    rt = P.raytracer_for(scenes.single_triangle())
+    rh = oracle_mod.make_rayhits([[0.1, 0.2, 2.0]], [[0.0, 0.0, -1.0]], tnear=np.finfo(np.float32).tiny)
+    out = rt.intersect(rh)
+    assert out["geomID"][0] == 0 and out["primID"][0] == 0 and out["tfar"][0] == np.float32(2.0)
+    assert (out["Ng_x"][0], out["Ng_y"][0], out["Ng_z"][0]) == (0.0, 0.0, 6.0)
+    n = rt.interpolate([0], [0], out["u"], out["v"], 0)[0]; uv = rt.interpolate([0], [0], out["u"], out["v"], 1)[0]
+    assert "normal = (%0.3f, %0.3f, %0.3f)" % tuple(n) == "normal = (0.000, 0.000, 1.000)"
+    assert "tex_coord = (%0.3f, %0.3f)" % tuple(uv) == "tex_coord = (0.050, 0.933)"
+    miss = rt.intersect(oracle_mod.make_rayhits([[5.0, 5.0, 2.0]], [[0.0, 0.0, -1.0]]))
+    assert miss["geomID"][0] == INVALID and miss["tfar"][0] == np.finfo(np.float32).max      # untouched on a miss
+
+
+def test_T2_through_the_abi(P):
+    """pg1/tutorials.cpp:170-178 on the reference's data/test4.png fixture."""
+    sc = scenes.single_triangle()
+    buf = golden("test4_bgra.npy")
+    sc.textures = [scenes.Image(np.ascontiguousarray(buf), 64, buf.shape[0], buf.shape[1], 4)]
+    rt = P.raytracer_for(sc)
+    texel = rt.texture_get_texel(0, [[(1.0 / 64) * 2.5, 0.0]])[0]
+    assert "(r = %0.3f, g = %0.3f, b = %0.3f)" % tuple(texel) == "(r = 1.000, g = 0.000, b = 0.500)"
+
+
+def test_empty_scene_renders_the_env_map(P, oracle_mod):
+    sc = scenes.Scene("empty", [], scenes.avenger_materials(), env=scenes.make_envmap(256, 128, 2), camera=scenes.Camera(64, 40))
+    rt = P.raytracer_for(sc); o = oracle_mod.Oracle(sc)
+    p = dict(sampling_width=1, jitter=0, aperture=0.0)
+    img, st = rt.render(p); ref = o.render(oracle_mod.make_params(**p))[0]
+    assert st["primary"] == 64 * 40 and st["shadow"] == 0
+    ok, psnr = image_bars(P, ref, img)
+    assert ok >= 0.995
+
+
+# ------------------------------------------------------------------------------------------------ leaf functions
+def test_primary_rays_bit_exact(cornell_pair, oracle_mod):
+    """Camera + jitter + lens sampling are plain IEEE float ops and integer hashing on both sides: bit-exact."""
+    rt, o = cornell_pair
+    for p in (dict(sampling_width=1, jitter=0, aperture=0.0), dict(sampling_width=3, seed=7), dict(sampling_width=2, camera_mode=1, seed=3)):
+        a = rt.primary_rays(p); b = o.primary_rays(oracle_mod.make_params(**p))
+        assert np.array_equal(a, b), p
+
+
+def test_secondary_rays_bit_exact(cornell_pair):
+    rt, o = cornell_pair
+    rng = np.random.default_rng(5)
+    n = 5000
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    nn = rng.normal(size=(n, 3)); nn /= np.linalg.norm(nn, axis=1, keepdims=True)
+    flip = np.sum(d * nn, axis=1) > 0; nn[flip] *= -1
+    hp = rng.uniform(-100, 100, (n, 3))
+    ior = np.where(rng.random(n) < 0.5, 1.000293, 1.5)
+    items = np.concatenate([d, nn, hp, ior[:, None], (2.500293 - ior)[:, None]], axis=1).astype(np.float32)
+    for refr in (False, True):
+        a = rt.secondary_rays(items, refr); b = o.secondary_rays(items, refr)
+        assert np.array_equal(a, b, equal_nan=True)
+    assert np.isnan(rt.secondary_rays(items, True)[:, 4]).sum() > 100          # TIR cases are exercised and agree
+
+
+def test_mix_srgb(cornell_pair):
+    """double pow on both sides; CUDA's pow is within 2 ulp of glibc's in double => float results differ by <= 1 ulp."""
+    rt, o = cornell_pair
+    rng = np.random.default_rng(6)
+    n = 20000
+    c0 = rng.uniform(-0.2, 1.3, (n, 4)).astype(np.float32); c1 = rng.uniform(-0.2, 1.3, (n, 4)).astype(np.float32)
+    al = rng.uniform(0, 1, n).astype(np.float32)
+    a, b = rt.mix_srgb(c0, c1, al), o.mix_srgb(c0, c1, al)
+    assert np.max(np.abs(a - b)) <= 1.2e-7 and np.mean(a == b) > 0.99
+
+
+def test_gamma(cornell_pair):
+    rt, o = cornell_pair
+    rng = np.random.default_rng(7)
+    c = rng.uniform(-0.1, 1.5, (20000, 4)).astype(np.float32)
+    for g in (0.5, 0.25, 1.0):
+        a, b = rt.gamma(c, g), o.gamma(c, g)
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        assert np.nanmax(np.abs(a - b) / np.maximum(np.abs(b), 1e-6)) <= 3e-7      # <= ~2 ulp relative
+
+
+def test_texture_get_texel_including_out_of_range(cornell_pair):
+    """Bilinear fetch is plain float arithmetic: bit-exact, including the black-texel rules, the wrap column and
+    clamped out-of-range coordinates (tiled model UVs)."""
+    rt, o = cornell_pair
+    rng = np.random.default_rng(8)
+    uv = rng.uniform(-0.5, 1.5, (20000, 2)).astype(np.float32)
+    grid = (np.arange(0, 65)[:, None] / np.float32(64)).astype(np.float32)
+    uv = np.concatenate([uv, np.concatenate([grid, grid[::-1]], axis=1), rng.uniform(0, 1, (20000, 2)).astype(np.float32)])
+    for tex in (0, 1, -1):
+        a, b = rt.texture_get_texel(tex, uv), o.texture_get_texel(tex, uv)
+        assert np.array_equal(a, b), tex
+
+
+def test_env_get_texel(cornell_pair):
+    """(u,v) come from atan2f / asinf: 1-ulp differences move the bilinear weights by ~1e-4 texel; tolerance 2e-3 in
+    colour, with a 0.1 % budget for samples that land exactly on a texel boundary (black-texel rule)."""
+    rt, o = cornell_pair
+    rng = np.random.default_rng(9)
+    d = rng.normal(size=(50000, 3)).astype(np.float32)
+    a, b = rt.env_get_texel(d), o.env_get_texel(d)
+    bad = np.abs(a - b).max(axis=1) > 2e-3
+    assert bad.mean() <= 1e-3
+    assert np.mean(np.all(a == b, axis=1)) > 0.5
+
+
+# ------------------------------------------------------------------------------------------------ intersection
+def test_intersect_bit_exact_vs_brute_force(cornell_pair, oracle_mod):
+    rt, o = cornell_pair
+    rng = np.random.default_rng(10)
+    n = 20000
+    org = rng.uniform(-150, 150, (n, 3)).astype(np.float32); org[:, 2] = np.abs(org[:, 2])
+    target = rng.uniform(-70, 70, (n, 3)).astype(np.float32); target[:, 2] = rng.uniform(-5, 60, n)
+    d = (target - org) * rng.uniform(0.01, 3.0, (n, 1)).astype(np.float32)
+    d[:100, 0] = 0.0; d[100:200, 1] = 0.0; d[200:300, 2] = 0.0                      # axis-parallel components
+    rh = oracle_mod.make_rayhits(org, d, tnear=0.01)
+    a = rt.intersect(rh); b = o.intersect(rh, brute=True)
+    assert (b["geomID"] != INVALID).mean() > 0.3
+    for f in ("tfar", "u", "v", "geomID", "primID", "Ng_x", "Ng_y", "Ng_z"):
+        assert np.array_equal(a[f], b[f]), f
+
+
+def test_intersect_soup_and_duplicates(P, oracle_mod):
+    """Random soup + exactly coincident duplicate triangles: ties resolve to the lowest primID on both sides."""
+    sc = scenes.triangle_soup(5000, seed=4, resolution=(96, 54))
+    m = sc.meshes[0]
+    sc.meshes.append(scenes.Mesh("dup", m.pos[:500].copy(), m.nrm[:500].copy(), m.uv[:500].copy(), 0))
+    rt = P.raytracer_for(sc); o = oracle_mod.Oracle(sc)
+    rays = o.primary_rays(oracle_mod.make_params(sampling_width=2, jitter=1, aperture=0.0))
+    rh = oracle_mod.make_rayhits(rays[:, :3], rays[:, 4:7], tnear=0.01)
+    a = rt.intersect(rh); b = o.intersect(rh, brute=True)
+    for f in ("tfar", "u", "v", "geomID", "primID"):
+        assert np.array_equal(a[f], b[f]), f
+    assert not np.any((a["geomID"] == 1) & (a["primID"] < 500))                    # the duplicate never wins the tie
+
+
+def test_interpolate_bit_exact(avenger):
+    sc, rt, o = avenger
+    rng = np.random.default_rng(11)
+    n = 5000
+    geom = rng.integers(0, len(sc.meshes), n).astype(np.uint32)
+    prim = np.array([rng.integers(0, sc.meshes[g].ntris) for g in geom], np.uint32)
+    u = rng.random(n).astype(np.float32) * 0.5; v = rng.random(n).astype(np.float32) * 0.5
+    for slot in (0, 1):
+        assert np.array_equal(rt.interpolate(geom, prim, u, v, slot), o.interpolate(geom, prim, u, v, slot))
+
+
+# ------------------------------------------------------------------------------------------------ frames
+@pytest.mark.parametrize("tag", ["c1", "dof3x3", "lambert", "pinhole_depth3"])
+def test_frames_vs_committed_golden(P, cornell, tag):
+    """CUDA frames against the committed oracle renders (no oracle needed at run time)."""
+    z = np.load(os.path.join(GOLDEN, f"cornell_{tag}.npz"))
+    p = json.loads(str(z["params"]))
+    rt = P.raytracer_for(cornell)
+    img, st = rt.render(p)
+    g, pr = rt.primary_ids(p)
+    assert np.mean((g == z["geom"]) & (pr == z["prim"])) >= 0.999
+    ok, psnr = image_bars(P, z["rgba"], img)
+    assert ok >= 0.995 and psnr >= 45.0, (ok, psnr)
+    assert [st["primary"], st["shadow"], st["reflection"], st["refraction"]] == list(z["rays"])
+
+
+def test_avenger_C1_parity_gates(P, oracle_mod, avenger):
+    """Config C1: 640x480, Whitted, depth 7, 1 spp un-jittered, aperture 0."""
+    sc, rt, o = avenger
+    p = dict(sampling_width=1, jitter=0, aperture=0.0, max_depth=7)
+    ref, g0, p0, st0 = o.render(oracle_mod.make_params(**p))
+    img, st = rt.render(p)
+    g1, p1 = rt.primary_ids(p)
+    assert np.mean((g0 == g1) & (p0 == p1)) >= 0.999
+    ok, psnr = image_bars(P, ref, img)
+    assert ok >= 0.995 and psnr >= 45.0, (ok, psnr)
+    for k in ("primary", "shadow", "reflection", "refraction"):
+        assert abs(st[k] - st0[k]) <= 1e-3 * max(st0[k], 1), (k, st[k], st0[k])
+    assert st["reflection"] > 1000 and st["refraction"] > 1000 and st["shadow"] > 50000
+
+
+def test_avenger_default_render_3x3_dof(P, oracle_mod, avenger):
+    """The reference's shipped settings (3x3 stratified, thin lens f=200 a=5) with the shared counter RNG, on a crop-sized frame."""
+    sc, rt, o = avenger
+    rt.set_camera(320, 240, sc.camera.fov_y, sc.camera.view_from, sc.camera.view_at)
+    o.set_camera(320, 240, sc.camera.fov_y, sc.camera.view_from, sc.camera.view_at)
+    try:
+        p = dict(seed=21)
+        ref, g0, p0, st0 = o.render(oracle_mod.make_params(**p))
+        img, st = rt.render(p)
+        ok, psnr = image_bars(P, ref, img)
+        assert ok >= 0.995 and psnr >= 45.0, (ok, psnr)
+        assert st["primary"] == 320 * 240 * 9
+        for k in ("shadow", "reflection", "refraction"):
+            assert abs(st[k] - st0[k]) <= 1e-3 * max(st0[k], 1), (k, st[k], st0[k])
+    finally:
+        rt.set_camera(640, 480, sc.camera.fov_y, sc.camera.view_from, sc.camera.view_at)
+        o.set_camera(640, 480, sc.camera.fov_y, sc.camera.view_from, sc.camera.view_at)
+
+
+def test_multiple_lights_sum_in_order(P, oracle_mod, cornell):
+    """The commented coloured lights of pg1/raytracer.cpp:54-63 plus the white one."""
+    sc = scenes.cornell_like()
+    sc.camera = cornell.camera
+    sc.lights = [scenes.Light((-10, 0, 200), (0.8, 0.2, 0.2), (0.8, 0.2, 0.2), (0.8, 0.2, 0.2)),
+                 scenes.Light((0, 80, 150), (0.2, 0.8, 0.2), (0.2, 0.8, 0.2), (0.2, 0.8, 0.2)), scenes.Light()]
+    rt = P.raytracer_for(sc); o = oracle_mod.Oracle(sc)
+    p = dict(sampling_width=1, jitter=0, aperture=0.0)
+    ref, _, _, st0 = o.render(oracle_mod.make_params(**p)); img, st = rt.render(p)
+    ok, psnr = image_bars(P, ref, img)
+    assert ok >= 0.995 and psnr >= 45.0
+    assert st["shadow"] == st0["shadow"] and st["shadow"] > 2 * 64 * 48 * 0.3
+
+
+def test_get_pixel_hook_serves_the_rendered_frame(cornell_pair):
+    """The reference's plug-in hook Color4f get_pixel(x, y, t) (pg1/simpleguidx11.h:27)."""
+    rt, o = cornell_pair
+    p = dict(sampling_width=1, jitter=0, aperture=0.0)
+    img, _ = rt.render(p)
+    for (x, y) in ((0, 0), (63, 47), (31, 20)):
+        px = rt.get_pixel(x, y, 0.0, p)
+        assert np.array_equal(np.array(px, np.float32), img[y, x], equal_nan=True)
+
+
+# ------------------------------------------------------------------------------------------------ size-independent properties
+def test_render_is_deterministic_and_batching_invariant(P, cornell, monkeypatch):
+    rt = P.raytracer_for(cornell)
+    p = dict(seed=2)
+    a, sa = rt.render(p); b, sb = rt.render(p)
+    assert np.array_equal(a, b, equal_nan=True)
+    monkeypatch.setenv("PGRT_MAX_BATCH_SAMPLES", "4096")            # many small batches
+    rt2 = P.raytracer_for(cornell)
+    c, sc_ = rt2.render(p)
+    assert sc_["batches"] > 1 and np.array_equal(a, c, equal_nan=True)
+    assert (sa["shadow"], sa["reflection"], sa["refraction"]) == (sc_["shadow"], sc_["reflection"], sc_["refraction"])
+
+
+def test_queue_overflow_falls_back_to_smaller_batches(P, cornell, monkeypatch):
+    monkeypatch.setenv("PGRT_MIN_LEVEL_CAP", "2048"); monkeypatch.setenv("PGRT_LEVEL_CAP_FACTOR", "0.05")
+    rt = P.raytracer_for(cornell)
+    p = dict(seed=2)
+    img, st = rt.render(p)
+    assert st["overflow_retries"] >= 1
+    monkeypatch.delenv("PGRT_MIN_LEVEL_CAP"); monkeypatch.delenv("PGRT_LEVEL_CAP_FACTOR")
+    ref, _ = P.raytracer_for(cornell).render(p)
+    assert np.array_equal(img, ref, equal_nan=True)
+
+
+def test_sharded_render_is_bit_identical_to_single_gpu(P, avenger):
+    """Tile sharding must not change any pixel: emulate 1/2/3/8 ranks on one GPU, un-tile with the CUDA kernel."""
+    import torch
+    sc, rt, o = avenger
+    p = dict(sampling_width=2, seed=3)
+    full, st_full = rt.render(p)
+    try:
+        for n in (2, 3, 8):
+            spr = None; bufs = []; rays = 0
+            for r in range(n):
+                rt.set_shard(r, n)
+                spr = rt.shard_pixels()
+                t = torch.zeros((spr, 4), dtype=torch.float32, device="cuda")
+                torch.cuda.synchronize()                     # the library renders on its own stream
+                st = rt.render_shard_device(t.data_ptr(), p)
+                torch.cuda.synchronize()
+                bufs.append(t); rays += st["total"]
+            g = torch.cat(bufs)
+            out = torch.zeros((rt.height, rt.width, 4), dtype=torch.float32, device="cuda")
+            torch.cuda.synchronize()
+            rt.untile(g.data_ptr(), n, out.data_ptr())
+            torch.cuda.synchronize()
+            assert np.array_equal(out.cpu().numpy(), full, equal_nan=True), n
+            assert rays == st_full["total"]
+            from pgi_raytracing_b200 import dist as D
+            assert np.array_equal(D.untile_numpy(g.cpu().numpy(), rt.width, rt.height, n), full, equal_nan=True)
+    finally:
+        rt.set_shard(0, 1)
+
+
+def test_full_size_1080p_properties(P, avenger):
+    """BASELINE config C2 at full size, through properties that need no CPU render: ray accounting identities,
+    determinism, depth monotonicity, and agreement of pgrt_intersect with the frame's own primary ids."""
+    sc, rt, o = avenger
+    rt.set_camera(1920, 1080, sc.camera.fov_y, sc.camera.view_from, sc.camera.view_at)
+    try:
+        p = dict(sampling_width=1, jitter=0, aperture=0.0, max_depth=10)
+        a, sa = rt.render(p); b, sb = rt.render(p)
+        assert np.array_equal(a, b, equal_nan=True) and sa["total"] == sb["total"]
+        assert sa["primary"] == 1920 * 1080 and sa["refraction"] <= sa["reflection"]
+        s7 = rt.render(dict(p, max_depth=7))[1]
+        assert s7["reflection"] <= sa["reflection"] and s7["primary"] == sa["primary"]
+        assert np.all(a[..., 3] == 1.0)
+        g, pr = rt.primary_ids(p)
+        rays = rt.primary_rays(p)
+        sel = np.random.default_rng(0).integers(0, 1920 * 1080, 50000)
+        from oracle.oracle import make_rayhits
+        rh = make_rayhits(rays[sel, :3], rays[sel, 4:7], tnear=0.01)
+        hit = rt.intersect(rh)
+        assert np.array_equal(hit["geomID"], g.reshape(-1)[sel]) and np.array_equal(hit["primID"], pr.reshape(-1)[sel])
+    finally:
+        rt.set_camera(640, 480, sc.camera.fov_y, sc.camera.view_from, sc.camera.view_at)
+
+
+def test_errors_are_reported_not_thrown(P):
+    rt = P.Raytracer(64, 48, 0.7, (0, 0, 10), (0, 0, 0))
+    with pytest.raises(P.PgrtError) as e:
+        rt.render(dict())                       # nothing committed
+    assert e.value.code == 1 and "commit" in str(e.value)
+    rt.LoadScene(scenes.single_triangle())
+    with pytest.raises(P.PgrtError):
+        rt.render(dict(sampling_width=0))
+    with pytest.raises(P.PgrtError):
+        rt.render(dict(max_depth=64))

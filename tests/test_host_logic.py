@@ -1,0 +1,100 @@
+"""Host-side logic that needs no GPU: tile sharding arithmetic, stand-in scene generators, OBJ writer, bench helpers."""
+import os
+
+import numpy as np
+import pytest
+
+from pgi_raytracing_b200 import scenes
+from pgi_raytracing_b200 import dist as D
+
+
+@pytest.mark.parametrize("wh", [(640, 480), (1920, 1080), (3840, 2160), (100, 37), (33, 9), (5, 3)])
+@pytest.mark.parametrize("n_ranks", [1, 2, 3, 8])
+def test_tiles_partition_the_frame_exactly(wh, n_ranks):
+    w, h = wh
+    seen = np.zeros((h, w), np.int32)
+    for r in range(n_ranks):
+        x, y, valid = D.slot_pixels(w, h, r, n_ranks)
+        assert x.shape[0] == D.shard_pixels(w, h, n_ranks)
+        np.add.at(seen, (y[valid], x[valid]), 1)
+    assert np.all(seen == 1)
+
+
+def test_tile_untile_roundtrip_and_warp_coherence():
+    w, h, n = 100, 37, 3
+    frame = np.random.default_rng(0).random((h, w, 4)).astype(np.float32)
+    g = np.concatenate([D.tile_numpy(frame, r, n) for r in range(n)])
+    assert np.array_equal(D.untile_numpy(g, w, h, n), frame)
+    # 32 consecutive slots cover an 8x4 pixel block (coherent primary rays within a warp)
+    x, y, valid = D.slot_pixels(640, 480, 0, 1)
+    assert np.ptp(x[:32]) == 7 and np.ptp(y[:32]) == 3
+    # round-robin dealing: rank r of n owns tiles r, r+n, ...
+    x1, y1, _ = D.slot_pixels(640, 480, 1, 4)
+    assert (x1[0], y1[0]) == (32, 0) and (x1[256], y1[256]) == (32 * 5, 0)
+
+
+def test_avenger_proxy_shape_and_determinism():
+    a = scenes.avenger_proxy(detail=0.05, with_images=False)
+    b = scenes.avenger_proxy(detail=0.05, with_images=False)
+    assert len(a.meshes) == 94 and len(a.materials) == 5                    # the counts the reference's screenshot shows
+    assert [m.type for m in a.materials] == [3, 4, 3, 3, 3]
+    assert sum(1 for m in a.meshes if a.materials[m.material].type == 4) == 1   # one closed dielectric shell
+    assert {a.materials[m.material].diffuse_tex for m in a.meshes} == {-1, 0, 1}
+    for ma, mb in zip(a.meshes, b.meshes):
+        assert np.array_equal(ma.pos, mb.pos) and np.array_equal(ma.nrm, mb.nrm) and np.array_equal(ma.uv, mb.uv)
+    allp = np.concatenate([m.pos.reshape(-1, 3) for m in a.meshes])
+    assert allp.min() > -110 and allp.max() < 110
+    for m in a.meshes:
+        assert m.pos.dtype == np.float32 and m.pos.shape == (m.ntris, 3, 3) and m.uv.shape == (m.ntris, 3, 2)
+        assert np.allclose(np.linalg.norm(m.nrm, axis=-1), 1.0, atol=1e-4)
+
+
+def test_full_detail_triangle_count():
+    sc = scenes.avenger_proxy(with_images=False)
+    assert 1.5e5 < sc.ntris < 2.5e5
+
+
+def test_soup_matches_config_c5_statistics():
+    sc = scenes.triangle_soup(20000, seed=1)
+    p = sc.meshes[0].pos
+    c = p.mean(axis=1)
+    assert c.min() > -101.5 and c.max() < 101.5 and abs(c.mean()) < 2.0
+    e = np.abs(p[:, 1] - p[:, 0])
+    assert e.max() <= 1.0 and 0.45 < e.mean() < 0.55
+    assert np.array_equal(scenes.triangle_soup(20000, seed=1).meshes[0].pos, p)
+    assert not np.array_equal(scenes.triangle_soup(20000, seed=2).meshes[0].pos, p)
+
+
+def test_images_are_bgr_topdown_with_freeimage_pitch():
+    rgb = np.zeros((2, 3, 3), np.uint8); rgb[0, 1] = (10, 20, 30)
+    im = scenes.Image.from_rgb(rgb)
+    assert (im.width, im.height, im.bpp, im.pitch) == (3, 2, 3, 12)
+    assert list(im.data[0, 3:6]) == [30, 20, 10]
+    env = scenes.make_envmap(256, 128, seed=1)
+    assert env.data.shape == (128, 768) and env.data.std() > 10
+    assert np.array_equal(env.data, scenes.make_envmap(256, 128, seed=1).data)
+
+
+def test_obj_writer_emits_the_dialect_loadobj_reads(tmp_path):
+    sc = scenes.cornell_like()
+    path = os.path.join(tmp_path, "scene.obj")
+    scenes.write_obj(sc, path, mtl_text=scenes.AVENGER_MTL_TEXT)
+    lines = open(path).read().splitlines()
+    assert lines[1].startswith("mtllib scene.mtl")
+    assert sum(1 for l in lines if l.startswith("g ")) == len(sc.meshes)
+    assert sum(1 for l in lines if l.startswith("f ")) == sc.ntris
+    assert sum(1 for l in lines if l.startswith("v ")) == 3 * sc.ntris
+    f = next(l for l in lines if l.startswith("f "))
+    assert f == "f 1/1/1 2/2/2 3/3/3"
+    # float32 values survive the text round trip
+    v = next(l for l in lines if l.startswith("v ")).split()[1:]
+    assert np.array_equal(np.array(v, np.float64).astype(np.float32), sc.meshes[0].pos[0, 0])
+    assert "Ks 1.0. 1.0 1.0" in open(os.path.join(tmp_path, "scene.mtl")).read()
+
+
+def test_bench_contract_figures():
+    import bench
+    assert bench.algorithmic_bytes_per_ray(200_000) == 720.0        # N = 2e5 -> D = 6
+    assert bench.algorithmic_bytes_per_ray(10_000_000) == 880.0     # N = 1e7 -> D = 8
+    sc, p, desc = bench.workload("c1")
+    assert (sc.camera.width, sc.camera.height) == (640, 480) and p["max_depth"] == 7 and p["sampling_width"] == 1
