@@ -13,10 +13,11 @@ struct Col3 { float r, g, b; };      // structs.h:16
 __device__ __forceinline__ Col3 tex_get_pixel(const DevTexture& t, int x, int y) {
     x = min(max(x, 0), t.width - 1); y = min(max(y, 0), t.height - 1);
     const uint8_t* p = t.data + (size_t)y * t.pitch + (size_t)x * t.bpp;
+    // __fdiv_rn: under -ftz=true nvcc rewrites "x / 255.0f" as "x * (1/255.0f)", which is not the IEEE quotient
     Col3 c;
-    c.r = (float)__ldg(p) / 255.0f;
-    c.g = (float)__ldg(p + 1) / 255.0f;
-    c.b = (float)__ldg(p + 2) / 255.0f;
+    c.r = __fdiv_rn((float)__ldg(p), 255.0f);
+    c.g = __fdiv_rn((float)__ldg(p + 1), 255.0f);
+    c.b = __fdiv_rn((float)__ldg(p + 2), 255.0f);
     return c;
 }
 
