@@ -76,6 +76,8 @@ typedef struct pgrt_render_stats {
     uint64_t rays_shadow;
     uint64_t rays_reflection;
     uint64_t rays_refraction;
+    uint64_t nodes_visited;   /* BVH nodes fetched / triangles tested over all closest-hit queries (profile & 2 renders only) */
+    uint64_t tris_tested;
     float frame_ms;           /* device time, first launch .. framebuffer ready                 */
     float trace_ms;           /* sum of closest-hit traversal kernel launches (profiled renders only) */
     float shade_ms;           /* sum of the other kernels (profiled renders only)               */
@@ -83,8 +85,19 @@ typedef struct pgrt_render_stats {
     uint32_t launches;        /* kernels launched for this frame                                 */
     uint32_t batches;         /* sample batches the frame was cut into                           */
     uint32_t overflow_retries;
-    uint32_t reserved[5];
+    uint32_t max_nodes_per_ray;   /* worst single query (profile & 2 renders only)             */
+    uint32_t reserved[4];
 } pgrt_render_stats;
+
+/* One recursion level of trace() (raytracer.cpp:237, `level`) in the last rendered frame. */
+typedef struct pgrt_level_stats {
+    uint64_t rays;            /* closest-hit queries issued by trace() at this level (level 0 = primary)   */
+    uint64_t shadow_rays;     /* is_illuminated queries issued by Phong hits of this level                 */
+    uint64_t nodes, tris;     /* BVH nodes fetched / triangles tested by `rays` (profile bit 1 only)       */
+    uint64_t shadow_nodes, shadow_tris;
+    uint32_t max_nodes, shadow_max_nodes;   /* worst single query                                            */
+    float trace_ms, shade_ms; /* profile bit 0 only                                                         */
+} pgrt_level_stats;
 
 /* Layout-compatible with RTCRayHit (embree3/rtcore_ray.h:11-49), 80 bytes. */
 typedef struct pgrt_rayhit {
@@ -129,7 +142,8 @@ void pgrt_default_params(pgrt_render_params* p);
  *      rgba = width*height*4 floats, pixel (x,y) at (y*width+x)*4, row 0 = top, a = 1 (simpleguidx11.cpp:108-114).
  *      pgrt_render          : host destination (device->host copy inside the call, as memcpy :121-124).
  *      pgrt_render_device   : device destination, asynchronous on the context stream; stats may be NULL.
- *      `profile` != 0 brackets every launch with events to fill trace_ms / shade_ms (serialises nothing). */
+ *      `profile` bit 0 brackets every launch with events to fill trace_ms / shade_ms (serialises nothing);
+ *      bit 1 runs the instrumented traversal that counts nodes / triangles per query (slower; same image). */
 int pgrt_render(pgrt_context* ctx, const pgrt_render_params* p, float* rgba_host, pgrt_render_stats* stats, int32_t profile);
 int pgrt_render_device(pgrt_context* ctx, const pgrt_render_params* p, void* rgba_device, pgrt_render_stats* stats, int32_t profile);
 /* single-pixel hook with the signature of SimpleGuiDX11::get_pixel (simpleguidx11.h:27): serves pixel (x,y) of
@@ -166,6 +180,7 @@ int pgrt_eval_secondary_rays(pgrt_context* ctx, const float* in11, uint64_t n, i
 /* ---- introspection */
 uint32_t pgrt_num_triangles(const pgrt_context* ctx);
 uint32_t pgrt_num_geometries(const pgrt_context* ctx);
+int pgrt_last_level_stats(const pgrt_context* ctx, int32_t level, pgrt_level_stats* out);   /* levels 0 .. max_depth of the last frame */
 uint64_t pgrt_kernel_launches(const pgrt_context* ctx);   /* kernels launched by this context since creation */
 const char* pgrt_version(void);
 

@@ -39,8 +39,15 @@ class BuildStats(C.Structure):
 
 class RenderStats(C.Structure):
     _fields_ = [("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_reflection", C.c_uint64), ("rays_refraction", C.c_uint64),
-                ("frame_ms", C.c_float), ("trace_ms", C.c_float), ("shade_ms", C.c_float), ("trace_launches", C.c_uint32),
-                ("launches", C.c_uint32), ("batches", C.c_uint32), ("overflow_retries", C.c_uint32), ("reserved", C.c_uint32 * 5)]
+                ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("frame_ms", C.c_float), ("trace_ms", C.c_float), ("shade_ms", C.c_float), ("trace_launches", C.c_uint32),
+                ("launches", C.c_uint32), ("batches", C.c_uint32), ("overflow_retries", C.c_uint32), ("max_nodes_per_ray", C.c_uint32),
+                ("reserved", C.c_uint32 * 4)]
+
+
+class LevelStats(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("nodes", C.c_uint64), ("tris", C.c_uint64),
+                ("shadow_nodes", C.c_uint64), ("shadow_tris", C.c_uint64), ("max_nodes", C.c_uint32), ("shadow_max_nodes", C.c_uint32),
+                ("trace_ms", C.c_float), ("shade_ms", C.c_float)]
 
 
 # every symbol include/pgrt.h declares: name -> (restype, argtypes)
@@ -78,6 +85,7 @@ SYMBOLS = {
     "pgrt_eval_secondary_rays": (C.c_int, [_VP, _VP, _U64, _I32, _VP]),
     "pgrt_num_triangles": (_U32, [_VP]),
     "pgrt_num_geometries": (_U32, [_VP]),
+    "pgrt_last_level_stats": (C.c_int, [_VP, _I32, C.POINTER(LevelStats)]),
     "pgrt_kernel_launches": (_U64, [_VP]),
 }
 

@@ -120,7 +120,8 @@ class Raytracer:
     def _stats(rs: L.RenderStats) -> dict:
         d = dict(primary=rs.rays_primary, shadow=rs.rays_shadow, reflection=rs.rays_reflection, refraction=rs.rays_refraction,
                  frame_ms=rs.frame_ms, trace_ms=rs.trace_ms, shade_ms=rs.shade_ms, trace_launches=rs.trace_launches,
-                 launches=rs.launches, batches=rs.batches, overflow_retries=rs.overflow_retries)
+                 launches=rs.launches, batches=rs.batches, overflow_retries=rs.overflow_retries,
+                 nodes_visited=rs.nodes_visited, tris_tested=rs.tris_tested, max_nodes_per_ray=rs.max_nodes_per_ray)
         d["total"] = d["primary"] + d["shadow"] + d["reflection"] + d["refraction"]
         return d
 
@@ -218,6 +219,16 @@ class Raytracer:
     def secondary_rays(self, items, refraction: bool):
         items = np.ascontiguousarray(items, np.float32); out = np.empty((items.shape[0], 9), np.float32)
         self._check(self.lib.pgrt_eval_secondary_rays(self.h, _ptr(items), items.shape[0], int(refraction), _ptr(out)))
+        return out
+
+    def level_stats(self) -> list:
+        """Per-recursion-level counters of the last frame (``pgrt_last_level_stats``)."""
+        out = []
+        for l in range(64):
+            ls = L.LevelStats()
+            if self.lib.pgrt_last_level_stats(self.h, l, C.byref(ls)) != L.PGRT_OK:
+                break
+            out.append({k: getattr(ls, k) for k, _ in L.LevelStats._fields_})
         return out
 
     def kernel_launches(self) -> int:

@@ -77,7 +77,9 @@ struct pgrt_context {
     size_t min_level_cap = (size_t)1 << 18;
     double level_cap_factor = 2.0;
     std::vector<cudaEvent_t> ev_pool;
-    std::vector<int> ev_class;
+    std::vector<int> ev_class, ev_level;
+    pgrt_level_stats level_stats[PGRT_MAX_LEVELS + 1] = {};
+    int level_stats_n = 0;
     cudaEvent_t ev_frame0 = nullptr, ev_frame1 = nullptr;
 
     // get_pixel cache
@@ -401,14 +403,14 @@ static int ensure_levels(pgrt_context* ctx, int n_levels, size_t cap0, size_t ca
 
 struct FrameTimer {
     pgrt_context* ctx; bool on; size_t used = 0;
-    void begin(int cls) {
+    void begin(int cls, int level = 0) {
         if (!on) return;
         if (used + 2 > ctx->ev_pool.size()) {
             if (ctx->ev_pool.size() >= 16384) { on = false; return; }
             for (int k = 0; k < 256; ++k) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
-            ctx->ev_class.resize(ctx->ev_pool.size() / 2);
+            ctx->ev_class.resize(ctx->ev_pool.size() / 2); ctx->ev_level.resize(ctx->ev_pool.size() / 2);
         }
-        ctx->ev_class[used / 2] = cls;
+        ctx->ev_class[used / 2] = cls; ctx->ev_level[used / 2] = level;
         cudaEventRecord(ctx->ev_pool[used], ctx->stream);
     }
     void end() { if (!on) return; cudaEventRecord(ctx->ev_pool[used + 1], ctx->stream); used += 2; }
@@ -437,7 +439,8 @@ static int render_frame(pgrt_context* ctx, const pgrt_render_params* p, float4* 
     const DevScene sc = ctx->dev_scene();
     const unsigned trace_grid = ctx->sm_count * 16, shade_grid = ctx->sm_count * 8;
     pgrt_render_stats rs = {};
-    FrameTimer tm{ctx, profile != 0};
+    FrameTimer tm{ctx, (profile & 1) != 0};
+    const bool count = (profile & 2) != 0;
     for (;;) {
         const size_t cap0 = (size_t)batch_slots * S;
         const size_t capn = std::max<size_t>(ctx->min_level_cap, (size_t)(ctx->level_cap_factor * (double)cap0));
@@ -456,15 +459,19 @@ static int render_frame(pgrt_context* ctx, const pgrt_render_params* p, float4* 
             k_raygen<<<div_up(n0, 256), 256, 0, st>>>(ctx->cam, *p, ctx->shard, (uint32_t)slot0, n_slots, ctx->levels[0], cnt); rs.launches++;
             tm.end();
             for (int l = 0; l < n_levels; ++l) {
-                tm.begin(KC_TRACE);
-                k_trace<<<trace_grid, 128, 0, st>>>(sc, ctx->levels[l], &cnt->n_rays[l]); rs.launches++; rs.trace_launches++;
+                tm.begin(KC_TRACE, l);
+                if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, ctx->levels[l], l, cnt);
+                else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, ctx->levels[l], l, cnt);
+                rs.launches++; rs.trace_launches++;
                 tm.end();
                 if (dest_mode == 2) break;
-                tm.begin(KC_SHADE);
+                tm.begin(KC_SHADE, l);
                 k_shade<<<shade_grid, 256, 0, st>>>(sc, *p, l, ctx->levels[l], ctx->levels[l + 1], cnt); rs.launches++;
                 tm.end();
-                tm.begin(KC_TRACE);   // Phong = shading preamble + one inline shadow traversal per light
-                k_phong<<<trace_grid, 128, 0, st>>>(sc, *p, l, ctx->levels[l], cnt); rs.launches++; rs.trace_launches++;
+                tm.begin(KC_TRACE, l);   // Phong = shading preamble + one inline shadow traversal per light
+                if (count) k_phong<true><<<trace_grid, 128, 0, st>>>(sc, *p, l, ctx->levels[l], cnt);
+                else k_phong<false><<<trace_grid, 128, 0, st>>>(sc, *p, l, ctx->levels[l], cnt);
+                rs.launches++; rs.trace_launches++;
                 tm.end();
             }
             if (dest_mode == 2) {
@@ -504,10 +511,21 @@ static int render_frame(pgrt_context* ctx, const pgrt_render_params* p, float4* 
     rs.rays_primary = ctx->h_counters->tot_primary; rs.rays_shadow = ctx->h_counters->tot_shadow;
     rs.rays_reflection = ctx->h_counters->tot_reflection; rs.rays_refraction = ctx->h_counters->tot_refraction;
     cudaEventElapsedTime(&rs.frame_ms, ctx->ev_frame0, ctx->ev_frame1);
-    if (profile) {
-        for (size_t k = 0; k + 1 < tm.used + 1 && k < tm.used; k += 2) {
+    const Counters& hc = *ctx->h_counters;
+    ctx->level_stats_n = n_levels;
+    for (int l = 0; l <= PGRT_MAX_LEVELS; ++l) {
+        pgrt_level_stats& ls = ctx->level_stats[l];
+        ls = pgrt_level_stats{};
+        ls.rays = hc.lv_rays[l]; ls.shadow_rays = hc.lv_shadow[l]; ls.nodes = hc.lv_nodes[l]; ls.tris = hc.lv_tris[l];
+        ls.shadow_nodes = hc.lv_sh_nodes[l]; ls.shadow_tris = hc.lv_sh_tris[l]; ls.max_nodes = hc.lv_max_nodes[l]; ls.shadow_max_nodes = hc.lv_sh_max_nodes[l];
+        rs.nodes_visited += ls.nodes + ls.shadow_nodes; rs.tris_tested += ls.tris + ls.shadow_tris;
+        rs.max_nodes_per_ray = std::max(rs.max_nodes_per_ray, std::max(ls.max_nodes, ls.shadow_max_nodes));
+    }
+    if (tm.on || tm.used) {
+        for (size_t k = 0; k < tm.used; k += 2) {
             float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
-            if (ctx->ev_class[k / 2] == KC_TRACE) rs.trace_ms += ms; else rs.shade_ms += ms;
+            pgrt_level_stats& ls = ctx->level_stats[ctx->ev_level[k / 2]];
+            if (ctx->ev_class[k / 2] == KC_TRACE) { rs.trace_ms += ms; ls.trace_ms += ms; } else { rs.shade_ms += ms; ls.shade_ms += ms; }
         }
     }
     if (stats) *stats = rs;
@@ -719,6 +737,11 @@ extern "C" int pgrt_eval_secondary_rays(pgrt_context* ctx, const float* in11, ui
 }
 
 // --------------------------------------------------------------------------------------------------- introspection
+extern "C" int pgrt_last_level_stats(const pgrt_context* ctx, int32_t level, pgrt_level_stats* out) {
+    if (!ctx || !out || level < 0 || level >= ctx->level_stats_n) return PGRT_ERR_INVALID;
+    *out = ctx->level_stats[level];
+    return PGRT_OK;
+}
 extern "C" uint32_t pgrt_num_triangles(const pgrt_context* ctx) { return ctx ? (uint32_t)ctx->h_tri_geom.size() : 0; }
 extern "C" uint32_t pgrt_num_geometries(const pgrt_context* ctx) { return ctx ? (uint32_t)ctx->h_geom_first.size() : 0; }
 extern "C" uint64_t pgrt_kernel_launches(const pgrt_context* ctx) { return ctx ? ctx->launches : 0; }

@@ -37,7 +37,21 @@ struct Counters {
     uint32_t pad;
     unsigned long long shadow, reflection, refraction;          // this batch
     unsigned long long tot_shadow, tot_reflection, tot_refraction, tot_primary;   // this frame
+    // per-level frame totals; the traversal columns are filled by instrumented renders only (profile bit 1)
+    unsigned long long lv_rays[PGRT_MAX_LEVELS + 1], lv_shadow[PGRT_MAX_LEVELS + 1];
+    unsigned long long lv_nodes[PGRT_MAX_LEVELS + 1], lv_tris[PGRT_MAX_LEVELS + 1];
+    unsigned long long lv_sh_nodes[PGRT_MAX_LEVELS + 1], lv_sh_tris[PGRT_MAX_LEVELS + 1];
+    uint32_t lv_max_nodes[PGRT_MAX_LEVELS + 1], lv_sh_max_nodes[PGRT_MAX_LEVELS + 1];
 };
+
+__device__ __forceinline__ void flush_trav_counts(unsigned long long nodes, unsigned long long tris, uint32_t mx,
+                                                  unsigned long long* g_nodes, unsigned long long* g_tris, uint32_t* g_max) {
+    for (int o = 16; o > 0; o >>= 1) {
+        nodes += __shfl_xor_sync(0xffffffffu, nodes, o); tris += __shfl_xor_sync(0xffffffffu, tris, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0 && nodes) { atomicAdd(g_nodes, nodes); atomicAdd(g_tris, tris); atomicMax(g_max, mx); }
+}
 
 struct ShardInfo { int32_t rank, n_ranks, tiles_x, tiles_y; };
 
@@ -96,14 +110,21 @@ __global__ void __launch_bounds__(256) k_raygen(DevCamera cam, pgrt_render_param
 }
 
 // ---- K7: closest hit for one queue (get_ray_hit, raytracer.cpp:130-148)
-__global__ void __launch_bounds__(128) k_trace(DevScene sc, LevelBufs L, const uint32_t* __restrict__ count) {
-    const uint32_t n = min(*count, L.cap);
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace(DevScene sc, LevelBufs L, int level, Counters* cnt) {
+    const uint32_t n = min(cnt->n_rays[level], L.cap);
+    unsigned long long my_nodes = 0, my_tris = 0; uint32_t my_max = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 o = L.ray_o[i], d = L.ray_d[i];
         HitRec h; h.t = FLT_MAX; h.u = 0.f; h.v = 0.f; h.tri = PGRT_INVALID_ID;
-        if (d.w >= 0.0f) h = trace_closest(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, FLT_MAX);
+        if (d.w >= 0.0f) {
+            TravCount tc; tc.nodes = 0; tc.tris = 0;
+            h = trace_closest_t<COUNT>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, FLT_MAX, tc);
+            if (COUNT) { my_nodes += tc.nodes; my_tris += tc.tris; my_max = max(my_max, tc.nodes); }
+        }
         L.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
     }
+    if (COUNT) flush_trav_counts(my_nodes, my_tris, my_max, &cnt->lv_nodes[level], &cnt->lv_tris[level], &cnt->lv_max_nodes[level]);
 }
 
 // rtcInterpolate0 (raytracer.cpp:252, :344): w*a0 + u*a1 + v*a2, fused as Embree's madd chain
@@ -223,9 +244,11 @@ __global__ void __launch_bounds__(256) k_shade(DevScene sc, pgrt_render_params p
 
 // ---- K8b/K9: Phong sum with the shadow query inline (raytracer.cpp:325-386, is_illuminated :150-176,
 //      LightSource::GenerateRay LightSource.cpp:11-32)
+template <bool COUNT>
 __global__ void __launch_bounds__(128) k_phong(DevScene sc, pgrt_render_params p, int level, LevelBufs L, Counters* cnt) {
     const uint32_t n = cnt->n_phong[level];
     unsigned long long my_shadow = 0;
+    unsigned long long my_nodes = 0, my_tris = 0; uint32_t my_max = 0;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint32_t i = L.phong_list[k];
         const float4 o = L.ray_o[i], d = L.ray_d[i], h = L.hit[i];
@@ -247,7 +270,9 @@ __global__ void __launch_bounds__(128) k_phong(DevScene sc, pgrt_render_params p
                 // the shadow ray leaves the light with the hit POSITION as its direction (sic, LightSource.cpp:18-20)
                 const float tfar = l2norm3(v3(lp.x - f.hitp.x, lp.y - f.hitp.y, lp.z - f.hitp.z));
                 my_shadow++;
-                const HitRec sh = trace_closest(sc, lp, f.hitp, 0.01f, tfar);
+                TravCount tc; tc.nodes = 0; tc.tris = 0;
+                const HitRec sh = trace_closest_t<COUNT>(sc, lp, f.hitp, 0.01f, tfar, tc);
+                if (COUNT) { my_nodes += tc.nodes; my_tris += tc.tris; my_max = max(my_max, tc.nodes); }
                 if (sh.tri == PGRT_INVALID_ID) lit = true;
                 else {                                                          // :166-172: a dielectric occluder does not shadow
                     const uint32_t g = __float_as_uint(__ldg(sc.shade + 4 * (size_t)sh.tri + 3).w);
@@ -275,7 +300,8 @@ __global__ void __launch_bounds__(128) k_phong(DevScene sc, pgrt_render_params p
         L.color[i] = make_float4(blue, green, red, 1.0f);                      // :385
     }
     for (int o = 16; o > 0; o >>= 1) my_shadow += __shfl_xor_sync(0xffffffffu, my_shadow, o);
-    if ((threadIdx.x & 31) == 0 && my_shadow) atomicAdd(&cnt->shadow, my_shadow);
+    if ((threadIdx.x & 31) == 0 && my_shadow) { atomicAdd(&cnt->shadow, my_shadow); atomicAdd(&cnt->lv_shadow[level], my_shadow); }
+    if (COUNT) flush_trav_counts(my_nodes, my_tris, my_max, &cnt->lv_sh_nodes[level], &cnt->lv_sh_tris[level], &cnt->lv_sh_max_nodes[level]);
 }
 
 // ---- K10: post-order combine of one level's dielectric nodes (raytracer.cpp:318-321)
@@ -347,9 +373,15 @@ __global__ void k_batch_begin(Counters* c) {
     if (t == 0) { c->shadow = 0; c->reflection = 0; c->refraction = 0; }
 }
 __global__ void k_batch_end(Counters* c, unsigned long long primary) {
-    if (threadIdx.x == 0) { c->tot_shadow += c->shadow; c->tot_reflection += c->reflection; c->tot_refraction += c->refraction; c->tot_primary += primary; }
+    if (threadIdx.x <= PGRT_MAX_LEVELS && threadIdx.x > 0) c->lv_rays[threadIdx.x] += c->n_rays[threadIdx.x];
+    if (threadIdx.x == 0) { c->lv_rays[0] += primary; c->tot_shadow += c->shadow; c->tot_reflection += c->reflection; c->tot_refraction += c->refraction; c->tot_primary += primary; }
 }
 __global__ void k_frame_begin(Counters* c) {
+    const int t = threadIdx.x;
+    if (t <= PGRT_MAX_LEVELS) {
+        c->lv_rays[t] = 0; c->lv_shadow[t] = 0; c->lv_nodes[t] = 0; c->lv_tris[t] = 0; c->lv_sh_nodes[t] = 0; c->lv_sh_tris[t] = 0;
+        c->lv_max_nodes[t] = 0; c->lv_sh_max_nodes[t] = 0;
+    }
     if (threadIdx.x == 0) { c->overflow = 0; c->tot_shadow = 0; c->tot_reflection = 0; c->tot_refraction = 0; c->tot_primary = 0; }
 }
 

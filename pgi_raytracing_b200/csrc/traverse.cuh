@@ -41,7 +41,10 @@ __device__ __forceinline__ V3 tri_ng(const float* __restrict__ pos, uint32_t id)
 
 // Binary-node traversal (layout in bvh_build.cuh, k_emit_bvh2).  Slab tests use FMA and a padded far bound:
 // they only cull, the hit record comes from tri_test alone.
-__device__ __forceinline__ HitRec trace_closest(const DevScene& sc, V3 O, V3 D, float tnear, float tfar) {
+struct TravCount { uint32_t nodes, tris; };   // instrumented renders only (profile bit 1)
+
+template <bool COUNT>
+__device__ __forceinline__ HitRec trace_closest_t(const DevScene& sc, V3 O, V3 D, float tnear, float tfar, TravCount& tc) {
     HitRec best; best.t = tfar; best.u = 0.0f; best.v = 0.0f; best.tri = PGRT_INVALID_ID;
     if (sc.n_tris == 0) return best;
     const float ooeps = 8.271806e-25f;   // 2^-80
@@ -55,6 +58,7 @@ __device__ __forceinline__ HitRec trace_closest(const DevScene& sc, V3 O, V3 D, 
     const float4* __restrict__ nodes = sc.nodes;
     while (true) {
         if (cur >= 0) {
+            if (COUNT) tc.nodes++;
             const float4 n0 = __ldg(nodes + 4 * (size_t)cur), n1 = __ldg(nodes + 4 * (size_t)cur + 1);
             const float4 n2 = __ldg(nodes + 4 * (size_t)cur + 2), n3 = __ldg(nodes + 4 * (size_t)cur + 3);
             const float far_pad = best.t * 1.0000005f;
@@ -80,10 +84,16 @@ __device__ __forceinline__ HitRec trace_closest(const DevScene& sc, V3 O, V3 D, 
         } else {
             const uint32_t code = (uint32_t)~cur;
             const uint32_t first = code >> 2, cnt = (code & 3u) + 1u;
+            if (COUNT) tc.tris += cnt;
             for (uint32_t k = 0; k < cnt; ++k) tri_test(sc.tris, first + k, O, D, tnear, tfar, best);
             if (sp == 0) break;
             cur = stack[--sp];
         }
     }
     return best;
+}
+
+__device__ __forceinline__ HitRec trace_closest(const DevScene& sc, V3 O, V3 D, float tnear, float tfar) {
+    TravCount tc;
+    return trace_closest_t<false>(sc, O, D, tnear, tfar, tc);
 }
