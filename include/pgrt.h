@@ -59,7 +59,9 @@ typedef struct pgrt_render_params {
     int32_t camera_mode;      /* 0 thin lens generate_ray(x,y,f,a) PinHoleCamera.cpp:65-105; 1 pinhole :31-63 */
     int32_t shader_mode;      /* 0 Whitted (trace as shipped); 1 Lambert (diffuse addend of :377 only);
                                  2 normal shader (the commented block raytracer.cpp:274-280)                 */
-    int32_t reserved[7];
+    int32_t scheduler;        /* 0 dynamic: one persistent kernel owns every ray of level >= 1 (default);
+                                 1 level-synchronous wavefront (one queue per recursion level).  Same image, bit for bit. */
+    int32_t reserved[6];
 } pgrt_render_params;
 
 typedef struct pgrt_build_stats {

@@ -12,6 +12,7 @@
 #include <stdint.h>
 #include <float.h>
 #include <math.h>
+#include <string.h>
 #include "../../include/pgrt.h"
 
 #define PGRT_TILE_W 32
@@ -45,12 +46,61 @@ __host__ __device__ __forceinline__ V3 mul3(const M3& a, V3 b) {
     return v3(a.m00 * b.x + a.m01 * b.y + a.m02 * b.z, a.m10 * b.x + a.m11 * b.y + a.m12 * b.z, a.m20 * b.x + a.m21 * b.y + a.m22 * b.z);
 }
 
-#ifdef __CUDACC__
-// Embree 3 vec3 forms on FMA hardware (restated): dot = madd(x,x,madd(y,y,z*z)), cross = msub(..)
-__device__ __forceinline__ float e_dot(V3 a, V3 b) { return __fmaf_rn(a.x, b.x, __fmaf_rn(a.y, b.y, a.z * b.z)); }
-__device__ __forceinline__ V3 e_cross(V3 a, V3 b) {
-    return v3(__fmaf_rn(a.y, b.z, -(a.z * b.y)), __fmaf_rn(a.z, b.x, -(a.x * b.z)), __fmaf_rn(a.x, b.y, -(a.y * b.x)));
+// ---- host/device portability of the BVH code: the wide-node encoder and the traversal (bvh8.cuh, traverse.cuh) are
+// plain functions that also compile with g++, so tests/ can run them on the CPU (tests/emul/) before a GPU is spent.
+#if defined(__CUDACC__)
+#define PG_HD __host__ __device__ __forceinline__
+#else
+#define PG_HD inline
+#endif
+PG_HD float pg_fma(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);   // one correctly rounded operation on both sides (host builds use -mfma -ffp-contract=off)
+#endif
 }
+PG_HD uint32_t pg_f2u(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+PG_HD float pg_u2f(uint32_t u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+PG_HD int pg_bfind(uint32_t v) {   // index of the highest set bit, v != 0
+#ifdef __CUDA_ARCH__
+    return 31 - __clz((int)v);
+#else
+    return 31 - __builtin_clz(v);
+#endif
+}
+PG_HD int pg_popc(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+PG_HD float4 pg_ldg4(const float4* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+// Embree 3 vec3 forms on FMA hardware (restated): dot = madd(x,x,madd(y,y,z*z)), cross = msub(..)
+PG_HD float e_dot(V3 a, V3 b) { return pg_fma(a.x, b.x, pg_fma(a.y, b.y, a.z * b.z)); }
+PG_HD V3 e_cross(V3 a, V3 b) {
+    return v3(pg_fma(a.y, b.z, -(a.z * b.y)), pg_fma(a.z, b.x, -(a.x * b.z)), pg_fma(a.x, b.y, -(a.y * b.x)));
+}
+#ifdef __CUDACC__
 __device__ __forceinline__ float f_expf(float x) { return (float)exp((double)x); }
 __device__ __forceinline__ float f_powf(float x, float y) { return (float)pow((double)x, (double)y); }
 __device__ __forceinline__ float f_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }

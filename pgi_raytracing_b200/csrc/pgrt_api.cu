@@ -69,6 +69,11 @@ struct pgrt_context {
     DevBuf<float4> lv_f4[PGRT_MAX_LEVELS + 1][5];
     DevBuf<uint2> lv_child[PGRT_MAX_LEVELS + 1];
     DevBuf<uint32_t> lv_list[PGRT_MAX_LEVELS + 1][2];
+    DevBuf<uint32_t> l0_pending;
+    // ray pool of the dynamic scheduler (levels >= 1)
+    RayPool pool = {};
+    DevBuf<float4> pool_f4[4]; DevBuf<uint2> pool_u2[2]; DevBuf<uint32_t> pool_u32[1];
+    int secondary_grid = 0;
     DevBuf<Counters> d_counters;
     DevBuf<float4> d_frame;
     DevBuf<uint32_t> d_ids;
@@ -149,6 +154,8 @@ extern "C" void pgrt_destroy(pgrt_context* ctx) {
         for (int k = 0; k < 5; ++k) ctx->lv_f4[l][k].release();
         ctx->lv_child[l].release(); ctx->lv_list[l][0].release(); ctx->lv_list[l][1].release();
     }
+    ctx->l0_pending.release();
+    for (auto& b : ctx->pool_f4) b.release(); for (auto& b : ctx->pool_u2) b.release(); for (auto& b : ctx->pool_u32) b.release();
     ctx->d_counters.release(); ctx->d_frame.release(); ctx->d_ids.release();
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->ev_frame0) cudaEventDestroy(ctx->ev_frame0);
@@ -388,6 +395,17 @@ static uint64_t shard_slots(const pgrt_context* ctx) {
 extern "C" uint64_t pgrt_shard_pixels(const pgrt_context* ctx) { return ctx ? shard_slots(ctx) : 0; }
 
 // --------------------------------------------------------------------------------------------------- frame
+static int ensure_pool(pgrt_context* ctx, size_t cap) {
+    for (auto& b : ctx->pool_f4) CUDA_TRY(b.ensure(cap));
+    for (auto& b : ctx->pool_u2) CUDA_TRY(b.ensure(cap));
+    for (auto& b : ctx->pool_u32) CUDA_TRY(b.ensure(cap));
+    RayPool& P = ctx->pool;
+    P.ray_o = ctx->pool_f4[0].p; P.ray_d = ctx->pool_f4[1].p; P.color = ctx->pool_f4[2].p; P.att = ctx->pool_f4[3].p;
+    P.child = ctx->pool_u2[0].p; P.link = ctx->pool_u2[1].p; P.pending = ctx->pool_u32[0].p;
+    P.cap = (uint32_t)cap;
+    return PGRT_OK;
+}
+
 static int ensure_levels(pgrt_context* ctx, int n_levels, size_t cap0, size_t capn) {
     for (int l = 0; l <= n_levels; ++l) {   // one spare level so k_shade always has a (never written) "next"
         const size_t cap = l == 0 ? cap0 : (l == n_levels ? 1 : capn);
@@ -396,8 +414,11 @@ static int ensure_levels(pgrt_context* ctx, int n_levels, size_t cap0, size_t ca
         LevelBufs& L = ctx->levels[l];
         L.ray_o = ctx->lv_f4[l][0].p; L.ray_d = ctx->lv_f4[l][1].p; L.hit = ctx->lv_f4[l][2].p; L.color = ctx->lv_f4[l][3].p; L.dn_att = ctx->lv_f4[l][4].p;
         L.dn_child = ctx->lv_child[l].p; L.phong_list = ctx->lv_list[l][0].p; L.diel_list = ctx->lv_list[l][1].p;
+        L.pending = nullptr;
         L.cap = (uint32_t)cap;
     }
+    CUDA_TRY(ctx->l0_pending.ensure(cap0));
+    ctx->levels[0].pending = ctx->l0_pending.p;
     return PGRT_OK;
 }
 
@@ -422,6 +443,7 @@ static int validate_frame(pgrt_context* ctx, const pgrt_render_params* p) {
     if (!ctx->cam_set) return ctx->fail(PGRT_ERR_INVALID, "render: pgrt_set_camera has not been called");
     if (p->sampling_width < 1 || p->sampling_width > 64) return ctx->fail(PGRT_ERR_INVALID, "render: sampling_width out of range [1,64]");
     if (p->max_depth < 0 || p->max_depth >= PGRT_MAX_LEVELS) return ctx->fail(PGRT_ERR_INVALID, "render: max_depth out of range [0,32]");
+    if (p->scheduler != 0 && p->scheduler != 1) return ctx->fail(PGRT_ERR_INVALID, "render: scheduler must be 0 (dynamic) or 1 (level-synchronous)");
     return upload_tables(ctx);
 }
 
@@ -438,18 +460,25 @@ static int render_frame(pgrt_context* ctx, const pgrt_render_params* p, float4* 
     batch_slots = std::min(batch_slots, total_slots);
     const DevScene sc = ctx->dev_scene();
     const unsigned trace_grid = ctx->sm_count * 16, shade_grid = ctx->sm_count * 8;
+    const bool dyn = p->scheduler == 0 && dest_mode != 2 && n_levels > 1;
+    if (dyn && ctx->secondary_grid == 0) {
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_secondary<false>, 128, 0));
+        ctx->secondary_grid = ctx->sm_count * std::max(1, std::min(per_sm, 8));
+    }
     pgrt_render_stats rs = {};
     FrameTimer tm{ctx, (profile & 1) != 0};
     const bool count = (profile & 2) != 0;
     for (;;) {
         const size_t cap0 = (size_t)batch_slots * S;
         const size_t capn = std::max<size_t>(ctx->min_level_cap, (size_t)(ctx->level_cap_factor * (double)cap0));
-        rc = ensure_levels(ctx, n_levels, cap0, capn);
+        rc = ensure_levels(ctx, dyn ? 1 : n_levels, cap0, capn);
         if (rc) return rc;
+        if (dyn) { rc = ensure_pool(ctx, capn * (size_t)std::min(n_levels - 1, 4)); if (rc) return rc; }   // one pool replaces the per-level queues
         tm.used = 0; rs.launches = 0; rs.trace_launches = 0; rs.batches = 0;
         Counters* cnt = ctx->d_counters.p;
         CUDA_TRY(cudaEventRecord(ctx->ev_frame0, st));
-        k_frame_begin<<<1, 32, 0, st>>>(cnt); rs.launches++;
+        k_frame_begin<<<1, 64, 0, st>>>(cnt); rs.launches++;
         for (uint64_t slot0 = 0; slot0 < total_slots; slot0 += batch_slots) {
             const uint32_t n_slots = (uint32_t)std::min<uint64_t>(batch_slots, total_slots - slot0);
             const uint32_t n0 = n_slots * (uint32_t)S;
@@ -458,28 +487,53 @@ static int render_frame(pgrt_context* ctx, const pgrt_render_params* p, float4* 
             tm.begin(KC_SHADE);
             k_raygen<<<div_up(n0, 256), 256, 0, st>>>(ctx->cam, *p, ctx->shard, (uint32_t)slot0, n_slots, ctx->levels[0], cnt); rs.launches++;
             tm.end();
-            for (int l = 0; l < n_levels; ++l) {
-                tm.begin(KC_TRACE, l);
-                if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, ctx->levels[l], l, cnt);
-                else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, ctx->levels[l], l, cnt);
+            if (dyn) {
+                // level 0 as a wavefront (coherent primary rays), every deeper level inside the persistent kernel
+                const RayPool P = ctx->pool;
+                LevelBufs Ln = {}; Ln.ray_o = P.ray_o; Ln.ray_d = P.ray_d; Ln.cap = P.cap;
+                tm.begin(KC_TRACE, 0);
+                if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, ctx->levels[0], 0, cnt);
+                else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, ctx->levels[0], 0, cnt);
                 rs.launches++; rs.trace_launches++;
                 tm.end();
-                if (dest_mode == 2) break;
-                tm.begin(KC_SHADE, l);
-                k_shade<<<shade_grid, 256, 0, st>>>(sc, *p, l, ctx->levels[l], ctx->levels[l + 1], cnt); rs.launches++;
+                tm.begin(KC_SHADE, 0);
+                k_shade<<<shade_grid, 256, 0, st>>>(sc, *p, 0, ctx->levels[0], Ln, P, 1, cnt); rs.launches++;
                 tm.end();
-                tm.begin(KC_TRACE, l);   // Phong = shading preamble + one inline shadow traversal per light
-                if (count) k_phong<true><<<trace_grid, 128, 0, st>>>(sc, *p, l, ctx->levels[l], cnt);
-                else k_phong<false><<<trace_grid, 128, 0, st>>>(sc, *p, l, ctx->levels[l], cnt);
+                tm.begin(KC_TRACE, 0);
+                if (count) k_phong<true><<<trace_grid, 128, 0, st>>>(sc, *p, 0, ctx->levels[0], cnt);
+                else k_phong<false><<<trace_grid, 128, 0, st>>>(sc, *p, 0, ctx->levels[0], cnt);
                 rs.launches++; rs.trace_launches++;
                 tm.end();
+                tm.begin(KC_TRACE, 1);
+                const size_t smem = (size_t)4 * p->max_depth * (PGRT_WSTACK + 1) * sizeof(uint32_t);   // <= 33.3 KB at max_depth 32
+                if (count) k_secondary<true><<<ctx->secondary_grid, 128, smem, st>>>(sc, *p, ctx->levels[0], P, cnt);
+                else k_secondary<false><<<ctx->secondary_grid, 128, smem, st>>>(sc, *p, ctx->levels[0], P, cnt);
+                rs.launches++; rs.trace_launches++;
+                tm.end();
+            } else {
+                for (int l = 0; l < n_levels; ++l) {
+                    tm.begin(KC_TRACE, l);
+                    if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, ctx->levels[l], l, cnt);
+                    else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, ctx->levels[l], l, cnt);
+                    rs.launches++; rs.trace_launches++;
+                    tm.end();
+                    if (dest_mode == 2) break;
+                    tm.begin(KC_SHADE, l);
+                    k_shade<<<shade_grid, 256, 0, st>>>(sc, *p, l, ctx->levels[l], ctx->levels[l + 1], ctx->pool, 0, cnt); rs.launches++;
+                    tm.end();
+                    tm.begin(KC_TRACE, l);   // Phong = shading preamble + one inline shadow traversal per light
+                    if (count) k_phong<true><<<trace_grid, 128, 0, st>>>(sc, *p, l, ctx->levels[l], cnt);
+                    else k_phong<false><<<trace_grid, 128, 0, st>>>(sc, *p, l, ctx->levels[l], cnt);
+                    rs.launches++; rs.trace_launches++;
+                    tm.end();
+                }
             }
             if (dest_mode == 2) {
                 uint32_t* geom = ctx->d_ids.p; uint32_t* prim = geom + (size_t)ctx->cam.width * ctx->cam.height;
                 k_primary_ids<<<div_up(n_slots, 256), 256, 0, st>>>(sc, ctx->cam, ctx->shard, (uint32_t)slot0, n_slots, S, ctx->levels[0].hit, geom, prim); rs.launches++;
             } else {
                 tm.begin(KC_SHADE);
-                for (int l = n_levels - 2; l >= 0; --l) { k_combine<<<shade_grid, 256, 0, st>>>(l, ctx->levels[l], ctx->levels[l + 1], cnt); rs.launches++; }
+                if (!dyn) for (int l = n_levels - 2; l >= 0; --l) { k_combine<<<shade_grid, 256, 0, st>>>(l, ctx->levels[l], ctx->levels[l + 1], cnt); rs.launches++; }
                 k_resolve<<<div_up(n_slots, 256), 256, 0, st>>>(ctx->cam, *p, ctx->shard, (uint32_t)slot0, n_slots, ctx->levels[0].color, dest, dest_mode == 1); rs.launches++;
                 tm.end();
             }
@@ -496,13 +550,14 @@ static int render_frame(pgrt_context* ctx, const pgrt_render_params* p, float4* 
                 }
                 valid_px = v * S;
             }
-            k_batch_end<<<1, 32, 0, st>>>(cnt, valid_px); rs.launches++;
+            k_batch_end<<<1, 64, 0, st>>>(cnt, valid_px, dyn ? 1 : 0); rs.launches++;
         }
         CUDA_TRY(cudaEventRecord(ctx->ev_frame1, st));
         CUDA_TRY(cudaMemcpyAsync(ctx->h_counters, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         LAUNCH_OK();
         CUDA_TRY(cudaStreamSynchronize(st));
         ctx->launches += rs.launches;
+        if (ctx->h_counters->watchdog) return ctx->fail(PGRT_ERR_CUDA, "render: internal error in the persistent secondary-ray kernel (mini-stack bound violated)");
         if (!ctx->h_counters->overflow) break;
         rs.overflow_retries++;
         if (batch_slots <= PGRT_TILE_PIXELS) return ctx->fail(PGRT_ERR_OVERFLOW, "render: secondary-ray queues overflow at the minimum batch; raise PGRT_MIN_LEVEL_CAP");

@@ -11,6 +11,15 @@
 //   backward, level = max_depth-1 .. 0 : k_combine resolves each dielectric node from its two children (post-order).
 //   k_resolve averages the samples of a pixel in sx-major order and applies gamma (raytracer.cpp:421-446).
 //
+// Two schedulers drive levels >= 1 (pgrt_render_params.scheduler), bit-identical in every output:
+//   1  level-synchronous: the three forward kernels per level, then k_combine per level (as described above).
+//   0  dynamic (default): ONE persistent kernel, k_secondary, owns every ray of level >= 1.  Warps claim rays from a
+//      single pool in allocation order, trace + shade them in place, append the reflection / refraction rays of
+//      dielectric hits to the same pool (consumable at once by any idle warp), and resolve the non-linear combine
+//      by continuation: a finished node decrements its parent's pending count and the last child to arrive
+//      evaluates mix_srgb for the parent and keeps climbing.  No per-level barrier exists, so the few long
+//      traversals of a level no longer serialise the frame (profiles/r1_level_stats_bvh2_lbvh.txt).
+//
 // Pixel order: 32x8 tiles dealt round-robin to ranks; inside a tile 8x4 blocks so a warp's primary rays are coherent.
 #pragma once
 #include "common.cuh"
@@ -26,6 +35,21 @@ struct LevelBufs {
     uint2* dn_child;        // dielectric nodes: level+1 slots of the reflection / refraction child (PGRT_INVALID_ID = none)
     uint32_t* phong_list;
     uint32_t* diel_list;
+    uint32_t* pending;      // dynamic scheduler, level 0 only: children of a dielectric node not yet resolved
+    uint32_t cap;
+};
+
+// Pool of every ray of level >= 1 (dynamic scheduler).  A record is written once, by the warp that shaded its parent
+// (the same warp traces it later); values that cross warps (colours, pending counts) go through ld.cg / st.cg and
+// atomics only: L1 is not coherent between SMs and a 32-B sector holds two neighbouring records.
+struct RayPool {
+    float4* ray_o;          // org.xyz, tnear
+    float4* ray_d;          // dir.xyz, time; time < 0 marks a reserved-but-unused slot
+    float4* color;          // value trace() returns for this node
+    float4* att;            // dielectric nodes: attenuation rgb, R
+    uint2* child;           // dielectric nodes: pool slots of the reflection / refraction child
+    uint2* link;            // x = parent record, y = level | child bit << 8 | (parent is a level-0 record) << 9
+    uint32_t* pending;      // dielectric nodes: children not yet resolved
     uint32_t cap;
 };
 
@@ -34,7 +58,8 @@ struct Counters {
     uint32_t n_phong[PGRT_MAX_LEVELS + 1];
     uint32_t n_diel[PGRT_MAX_LEVELS + 1];
     uint32_t overflow;
-    uint32_t pad;
+    uint32_t watchdog;      // dynamic scheduler: a bounded wait expired (never expected; reported as an error)
+    uint32_t pad0;
     unsigned long long shadow, reflection, refraction;          // this batch
     unsigned long long tot_shadow, tot_reflection, tot_refraction, tot_primary;   // this frame
     // per-level frame totals; the traversal columns are filled by instrumented renders only (profile bit 1)
@@ -42,6 +67,8 @@ struct Counters {
     unsigned long long lv_nodes[PGRT_MAX_LEVELS + 1], lv_tris[PGRT_MAX_LEVELS + 1];
     unsigned long long lv_sh_nodes[PGRT_MAX_LEVELS + 1], lv_sh_tris[PGRT_MAX_LEVELS + 1];
     uint32_t lv_max_nodes[PGRT_MAX_LEVELS + 1], lv_sh_max_nodes[PGRT_MAX_LEVELS + 1];
+    // dynamic scheduler: pool records allocated / level-1 records (frozen before k_secondary) / level-1 records claimed
+    uint32_t q_tail, q_l1, q_head, pad1;
 };
 
 __device__ __forceinline__ void flush_trav_counts(unsigned long long nodes, unsigned long long tris, uint32_t mx,
@@ -164,77 +191,172 @@ __device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool pred, in
     return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
 }
 
-// ---- K8: classification + dielectric expansion + env map (raytracer.cpp:247-323, :390-393)
-__global__ void __launch_bounds__(256) k_shade(DevScene sc, pgrt_render_params p, int level, LevelBufs L, LevelBufs Ln, Counters* cnt) {
+// ---- K8 (per ray): classification of one (ray, hit) pair = the head of trace() (raytracer.cpp:247-323, :390-393)
+enum ShadeKind { SK_FINAL = 0, SK_PHONG = 1, SK_DIEL = 2 };
+struct ShadeOut {
+    int kind;
+    float4 color;           // SK_FINAL: the value trace() returns
+    HitFrame f;             // SK_PHONG / SK_DIEL
+    RayRec refl, refr;      // SK_DIEL
+    float4 att;             // SK_DIEL: attenuation rgb, R
+    bool has_refr;          // SK_DIEL: the refraction ray exists (no total internal reflection)
+};
+
+__device__ __forceinline__ void shade_classify(const DevScene& sc, const pgrt_render_params& p, int level, float4 o, float4 d, float4 h, ShadeOut& s) {
+    s.kind = SK_FINAL; s.has_refr = false;
+    s.color = make_float4(0.f, 0.f, 0.f, 1.f);
+    s.att = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t tri = __float_as_uint(h.w);
+    if (d.w < 0.0f) return;                                             // unused slot of a partial tile / dead pool slot
+    if (tri == PGRT_INVALID_ID) {                                       // :390-393
+        const V3 dirn = normalize3(v3(d.x, d.y, d.z));
+        const Col4 c = env_get_texel(sc.env, dirn.x, dirn.y, dirn.z);
+        s.color = make_float4(c.r, c.g, c.b, c.a);
+        return;
+    }
+    s.f = hit_frame(sc, o, d, h);
+    const pgrt_material& mat = sc.materials[sc.geom_material[s.f.geom]];
+    if (p.shader_mode == 2) {                                           // :274-280
+        s.color = make_float4((s.f.n.x + 1) / 2, (s.f.n.y + 1) / 2, (s.f.n.z + 1) / 2, 1.0f);
+    } else if (level >= p.max_depth) {                                  // :282-283
+        s.color = make_float4(0.f, 0.f, 0.f, 1.f);
+    } else if (mat.type == 4 && p.shader_mode == 0) {                   // :294-323
+        float n1, n2;
+        if (d.w == PGRT_IOR_AIR) { n1 = PGRT_IOR_AIR; n2 = mat.ior; } else { n1 = mat.ior; n2 = PGRT_IOR_AIR; }   // :261-267
+        s.kind = SK_DIEL;
+        s.refl = make_reflection_ray(s.f.dirn, s.f.n, s.f.hitp, n1);
+        s.att.x = f_expf(-(1 - mat.diffuse[0]) * h.x);
+        s.att.y = f_expf(-(1 - mat.diffuse[1]) * h.x);
+        s.att.z = f_expf(-(1 - mat.diffuse[2]) * h.x);
+        s.refr = make_refraction_ray(s.f.dirn, s.f.n, n1, n2, s.f.hitp);
+        s.has_refr = (s.refr.d.x == s.refr.d.x);                        // :309
+        if (s.has_refr) {
+            const V3 v = -s.f.dirn;
+            const float cos1 = fabsf(dot3(s.f.n, v));
+            const float alpha = (n1 - n2) / (n1 + n2);
+            s.att.w = (float)((double)(alpha * alpha + (1 - (alpha * alpha))) * pow((double)(1 - cos1), 5.0));   // :316
+        }
+    } else {
+        s.kind = SK_PHONG;
+    }
+}
+
+// ---- K8b/K9 (per ray): Phong sum with the shadow query inline (raytracer.cpp:325-386, is_illuminated :150-176,
+//      LightSource::GenerateRay LightSource.cpp:11-32)
+struct TravAcc { unsigned long long nodes, tris; uint32_t mx; };
+
+template <bool COUNT>
+__device__ __forceinline__ float4 phong_eval(const DevScene& sc, const pgrt_render_params& p, float4 o, float4 d, const HitFrame& f,
+                                             unsigned long long& my_shadow, TravAcc& acc) {
+    const pgrt_material& mat = sc.materials[sc.geom_material[f.geom]];
+    float blue = 0, green = 0, red = 0;
+    float m_d_r, m_d_g, m_d_b;
+    if (mat.diffuse_tex < 0 || mat.diffuse_tex >= sc.n_textures) {         // :338-341
+        m_d_r = mat.diffuse[2]; m_d_g = mat.diffuse[1]; m_d_b = mat.diffuse[0];
+    } else {                                                                // :343-348
+        const Col3 texel = tex_get_texel(sc.textures[mat.diffuse_tex], f.tu, 1.0f - f.tv);
+        m_d_r = texel.r; m_d_g = texel.g; m_d_b = texel.b;
+    }
+    for (int li = 0; li < sc.n_lights; ++li) {                              // :351
+        const pgrt_light& light = sc.lights[li];
+        const V3 lp = v3(light.position[0], light.position[1], light.position[2]);
+        bool lit = false;
+        if (!(dot3(f.n, lp) < 0)) {                                         // :155
+            // the shadow ray leaves the light with the hit POSITION as its direction (sic, LightSource.cpp:18-20)
+            const float tfar = l2norm3(v3(lp.x - f.hitp.x, lp.y - f.hitp.y, lp.z - f.hitp.z));
+            my_shadow++;
+            TravCount tc; tc.nodes = 0; tc.tris = 0;
+            const HitRec sh = trace_closest_t<COUNT>(sc, lp, f.hitp, 0.01f, tfar, tc);
+            if (COUNT) { acc.nodes += tc.nodes; acc.tris += tc.tris; acc.mx = max(acc.mx, tc.nodes); }
+            if (sh.tri == PGRT_INVALID_ID) lit = true;
+            else {                                                          // :166-172: a dielectric occluder does not shadow
+                const uint32_t g = __float_as_uint(__ldg(sc.shade + 4 * (size_t)sh.tri + 3).w);
+                lit = sc.materials[sc.geom_material[g]].type == 4;
+            }
+        }
+        if (lit) {
+            const V3 light_vector = normalize3(v3(lp.x - f.hitp.x, lp.y - f.hitp.y, lp.z - f.hitp.z));
+            const V3 camera_vector = normalize3(v3(o.x - d.x, o.y - d.y, o.z - d.z));   // :360 (sic)
+            const float i_d_r = light.diffuse[2], i_d_g = light.diffuse[1], i_d_b = light.diffuse[0];
+            const float i_s_r = light.specular[2], i_s_g = light.specular[1], i_s_b = light.specular[0];
+            const float m_s_r = mat.specular[2], m_s_g = mat.specular[1], m_s_b = mat.specular[0];
+            const float ndl = dot3(f.n, light_vector);
+            const V3 l_r = normalize3(2 * (ndl)*f.n - light_vector);
+            if (p.shader_mode == 1) {
+                blue += i_d_b * m_d_b * ndl; green += i_d_g * m_d_g * ndl; red += i_d_r * m_d_r * ndl;
+            } else {
+                const float spec = f_powf(dot3(camera_vector, l_r), mat.shininess);
+                blue += (i_d_b * m_d_b * ndl + i_s_b * m_s_b * spec);
+                green += (i_d_g * m_d_g * ndl + i_s_g * m_s_g * spec);
+                red += (i_d_r * m_d_r * ndl + i_s_r * m_s_r * spec);
+            }
+        }
+    }
+    return make_float4(blue, green, red, 1.0f);                            // :385
+}
+
+// ---- K10 (per node): value of a dielectric node from its children (raytracer.cpp:318-321)
+__device__ __forceinline__ float4 combine_node(float4 att, float4 a, bool has_b, float4 b) {
+    if (has_b) {
+        Col4 c0, c1; c0.r = a.x; c0.g = a.y; c0.b = a.z; c0.a = a.w; c1.r = b.x; c1.g = b.y; c1.b = b.z; c1.a = b.w;
+        const Col4 c = mix_srgb(c0, c1, att.w);
+        return make_float4(c.r * att.x, c.g * att.y, c.b * att.z, 1.0f);
+    }
+    return make_float4(a.x * att.x, a.y * att.y, a.z * att.z, 1.0f);
+}
+
+// ---- K8 (kernel): one level of the wavefront.  With `dyn` set (level 0 of the dynamic scheduler) the children go
+//      to the ray pool (Ln aliases its ray arrays) together with their parent link, and are published at once.
+__global__ void __launch_bounds__(256) k_shade(DevScene sc, pgrt_render_params p, int level, LevelBufs L, LevelBufs Ln, RayPool P, int dyn, Counters* cnt) {
     const uint32_t n = min(cnt->n_rays[level], L.cap);
     const int lane = threadIdx.x & 31;
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     unsigned long long my_refl = 0, my_refr = 0;
     for (uint32_t base = warp_id * 32u; base < n; base += n_warps * 32u) {
         const uint32_t i = base + lane;
-        bool is_phong = false, is_diel = false, has_refr = false;
-        RayRec refl, refr;
-        float4 att = make_float4(0.f, 0.f, 0.f, 0.f);
+        ShadeOut s; s.kind = SK_FINAL; s.has_refr = false;
+        bool is_phong = false, is_diel = false;
         if (i < n) {
-            const float4 o = L.ray_o[i], d = L.ray_d[i], h = L.hit[i];
-            const uint32_t tri = __float_as_uint(h.w);
-            if (d.w < 0.0f) {
-                L.color[i] = make_float4(0.f, 0.f, 0.f, 1.f);   // unused slot of a partial tile
-            } else if (tri == PGRT_INVALID_ID) {
-                const V3 dirn = normalize3(v3(d.x, d.y, d.z));
-                const Col4 c = env_get_texel(sc.env, dirn.x, dirn.y, dirn.z);
-                L.color[i] = make_float4(c.r, c.g, c.b, c.a);
-            } else {
-                const HitFrame f = hit_frame(sc, o, d, h);
-                const pgrt_material& mat = sc.materials[sc.geom_material[f.geom]];
-                if (p.shader_mode == 2) {                                       // :274-280
-                    L.color[i] = make_float4((f.n.x + 1) / 2, (f.n.y + 1) / 2, (f.n.z + 1) / 2, 1.0f);
-                } else if (level >= p.max_depth) {                              // :282-283
-                    L.color[i] = make_float4(0.f, 0.f, 0.f, 1.f);
-                } else if (mat.type == 4 && p.shader_mode == 0) {               // :294-323
-                    float n1, n2;
-                    if (d.w == PGRT_IOR_AIR) { n1 = PGRT_IOR_AIR; n2 = mat.ior; } else { n1 = mat.ior; n2 = PGRT_IOR_AIR; }   // :261-267
-                    is_diel = true;
-                    refl = make_reflection_ray(f.dirn, f.n, f.hitp, n1);
-                    att.x = f_expf(-(1 - mat.diffuse[0]) * h.x);
-                    att.y = f_expf(-(1 - mat.diffuse[1]) * h.x);
-                    att.z = f_expf(-(1 - mat.diffuse[2]) * h.x);
-                    refr = make_refraction_ray(f.dirn, f.n, n1, n2, f.hitp);
-                    has_refr = (refr.d.x == refr.d.x);                          // :309
-                    if (has_refr) {
-                        const V3 v = -f.dirn;
-                        const float cos1 = fabsf(dot3(f.n, v));
-                        const float alpha = (n1 - n2) / (n1 + n2);
-                        att.w = (float)((double)(alpha * alpha + (1 - (alpha * alpha))) * pow((double)(1 - cos1), 5.0));   // :316
-                    }
-                } else {
-                    is_phong = true;
-                }
-            }
+            shade_classify(sc, p, level, L.ray_o[i], L.ray_d[i], L.hit[i], s);
+            is_phong = s.kind == SK_PHONG; is_diel = s.kind == SK_DIEL;
+            if (s.kind == SK_FINAL) L.color[i] = s.color;
         }
+        const bool has_refr = is_diel && s.has_refr;
         const uint32_t pslot = warp_append(&cnt->n_phong[level], is_phong, lane);
         if (is_phong) L.phong_list[pslot] = i;
         const uint32_t dslot = warp_append(&cnt->n_diel[level], is_diel, lane);
-        const uint32_t rl = warp_append(&cnt->n_rays[level + 1], is_diel, lane);
-        const uint32_t rr = warp_append(&cnt->n_rays[level + 1], has_refr, lane);
+        uint32_t* next_count = dyn ? &cnt->q_tail : &cnt->n_rays[level + 1];
+        const uint32_t rl = warp_append(next_count, is_diel, lane);
+        const uint32_t rr = warp_append(next_count, has_refr, lane);
         if (is_diel) {
             L.diel_list[dslot] = i;
             uint2 ch = make_uint2(PGRT_INVALID_ID, PGRT_INVALID_ID);
             if (rl < Ln.cap && (!has_refr || rr < Ln.cap)) {
                 ch.x = rl;
-                Ln.ray_o[rl] = make_float4(refl.o.x, refl.o.y, refl.o.z, refl.tnear);
-                Ln.ray_d[rl] = make_float4(refl.d.x, refl.d.y, refl.d.z, refl.time);
+                Ln.ray_o[rl] = make_float4(s.refl.o.x, s.refl.o.y, s.refl.o.z, s.refl.tnear);
+                Ln.ray_d[rl] = make_float4(s.refl.d.x, s.refl.d.y, s.refl.d.z, s.refl.time);
                 my_refl++;
                 if (has_refr) {
                     ch.y = rr;
-                    Ln.ray_o[rr] = make_float4(refr.o.x, refr.o.y, refr.o.z, refr.tnear);
-                    Ln.ray_d[rr] = make_float4(refr.d.x, refr.d.y, refr.d.z, refr.time);
+                    Ln.ray_o[rr] = make_float4(s.refr.o.x, s.refr.o.y, s.refr.o.z, s.refr.tnear);
+                    Ln.ray_d[rr] = make_float4(s.refr.d.x, s.refr.d.y, s.refr.d.z, s.refr.time);
                     my_refr++;
+                }
+                if (dyn) {
+                    const uint32_t meta = (uint32_t)(level + 1) | (1u << 9);
+                    P.link[rl] = make_uint2(i, meta);
+                    if (has_refr) P.link[rr] = make_uint2(i, meta | (1u << 8));
+                    L.pending[i] = has_refr ? 2u : 1u;
                 }
             } else {
                 cnt->overflow = 1u;   // the frame is re-rendered in smaller batches
+                if (dyn) {            // reserved slots inside the pool are claimed by k_secondary: mark them dead
+                    if (rl < Ln.cap) Ln.ray_d[rl] = make_float4(0.f, 0.f, 0.f, -1.0f);
+                    if (has_refr && rr < Ln.cap) Ln.ray_d[rr] = make_float4(0.f, 0.f, 0.f, -1.0f);
+                    L.color[i] = make_float4(0.f, 0.f, 0.f, 1.f);
+                }
             }
-            L.dn_att[i] = att;
+            L.dn_att[i] = s.att;
             L.dn_child[i] = ch;
         }
     }
@@ -242,69 +364,25 @@ __global__ void __launch_bounds__(256) k_shade(DevScene sc, pgrt_render_params p
     if (lane == 0) { if (my_refl) atomicAdd(&cnt->reflection, my_refl); if (my_refr) atomicAdd(&cnt->refraction, my_refr); }
 }
 
-// ---- K8b/K9: Phong sum with the shadow query inline (raytracer.cpp:325-386, is_illuminated :150-176,
-//      LightSource::GenerateRay LightSource.cpp:11-32)
+// ---- K8b/K9 (kernel)
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_phong(DevScene sc, pgrt_render_params p, int level, LevelBufs L, Counters* cnt) {
     const uint32_t n = cnt->n_phong[level];
+    if (level == 0 && blockIdx.x == 0 && threadIdx.x == 0) cnt->q_l1 = cnt->q_tail;   // dynamic scheduler: the level-1 rays are complete
     unsigned long long my_shadow = 0;
-    unsigned long long my_nodes = 0, my_tris = 0; uint32_t my_max = 0;
+    TravAcc acc; acc.nodes = 0; acc.tris = 0; acc.mx = 0;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint32_t i = L.phong_list[k];
         const float4 o = L.ray_o[i], d = L.ray_d[i], h = L.hit[i];
         const HitFrame f = hit_frame(sc, o, d, h);
-        const pgrt_material& mat = sc.materials[sc.geom_material[f.geom]];
-        float blue = 0, green = 0, red = 0;
-        float m_d_r, m_d_g, m_d_b;
-        if (mat.diffuse_tex < 0 || mat.diffuse_tex >= sc.n_textures) {         // :338-341
-            m_d_r = mat.diffuse[2]; m_d_g = mat.diffuse[1]; m_d_b = mat.diffuse[0];
-        } else {                                                                // :343-348
-            const Col3 texel = tex_get_texel(sc.textures[mat.diffuse_tex], f.tu, 1.0f - f.tv);
-            m_d_r = texel.r; m_d_g = texel.g; m_d_b = texel.b;
-        }
-        for (int li = 0; li < sc.n_lights; ++li) {                              // :351
-            const pgrt_light& light = sc.lights[li];
-            const V3 lp = v3(light.position[0], light.position[1], light.position[2]);
-            bool lit = false;
-            if (!(dot3(f.n, lp) < 0)) {                                         // :155
-                // the shadow ray leaves the light with the hit POSITION as its direction (sic, LightSource.cpp:18-20)
-                const float tfar = l2norm3(v3(lp.x - f.hitp.x, lp.y - f.hitp.y, lp.z - f.hitp.z));
-                my_shadow++;
-                TravCount tc; tc.nodes = 0; tc.tris = 0;
-                const HitRec sh = trace_closest_t<COUNT>(sc, lp, f.hitp, 0.01f, tfar, tc);
-                if (COUNT) { my_nodes += tc.nodes; my_tris += tc.tris; my_max = max(my_max, tc.nodes); }
-                if (sh.tri == PGRT_INVALID_ID) lit = true;
-                else {                                                          // :166-172: a dielectric occluder does not shadow
-                    const uint32_t g = __float_as_uint(__ldg(sc.shade + 4 * (size_t)sh.tri + 3).w);
-                    lit = sc.materials[sc.geom_material[g]].type == 4;
-                }
-            }
-            if (lit) {
-                const V3 light_vector = normalize3(v3(lp.x - f.hitp.x, lp.y - f.hitp.y, lp.z - f.hitp.z));
-                const V3 camera_vector = normalize3(v3(o.x - d.x, o.y - d.y, o.z - d.z));   // :360 (sic)
-                const float i_d_r = light.diffuse[2], i_d_g = light.diffuse[1], i_d_b = light.diffuse[0];
-                const float i_s_r = light.specular[2], i_s_g = light.specular[1], i_s_b = light.specular[0];
-                const float m_s_r = mat.specular[2], m_s_g = mat.specular[1], m_s_b = mat.specular[0];
-                const float ndl = dot3(f.n, light_vector);
-                const V3 l_r = normalize3(2 * (ndl)*f.n - light_vector);
-                if (p.shader_mode == 1) {
-                    blue += i_d_b * m_d_b * ndl; green += i_d_g * m_d_g * ndl; red += i_d_r * m_d_r * ndl;
-                } else {
-                    const float spec = f_powf(dot3(camera_vector, l_r), mat.shininess);
-                    blue += (i_d_b * m_d_b * ndl + i_s_b * m_s_b * spec);
-                    green += (i_d_g * m_d_g * ndl + i_s_g * m_s_g * spec);
-                    red += (i_d_r * m_d_r * ndl + i_s_r * m_s_r * spec);
-                }
-            }
-        }
-        L.color[i] = make_float4(blue, green, red, 1.0f);                      // :385
+        L.color[i] = phong_eval<COUNT>(sc, p, o, d, f, my_shadow, acc);
     }
     for (int o = 16; o > 0; o >>= 1) my_shadow += __shfl_xor_sync(0xffffffffu, my_shadow, o);
     if ((threadIdx.x & 31) == 0 && my_shadow) { atomicAdd(&cnt->shadow, my_shadow); atomicAdd(&cnt->lv_shadow[level], my_shadow); }
-    if (COUNT) flush_trav_counts(my_nodes, my_tris, my_max, &cnt->lv_sh_nodes[level], &cnt->lv_sh_tris[level], &cnt->lv_sh_max_nodes[level]);
+    if (COUNT) flush_trav_counts(acc.nodes, acc.tris, acc.mx, &cnt->lv_sh_nodes[level], &cnt->lv_sh_tris[level], &cnt->lv_sh_max_nodes[level]);
 }
 
-// ---- K10: post-order combine of one level's dielectric nodes (raytracer.cpp:318-321)
+// ---- K10 (kernel): post-order combine of one level's dielectric nodes (level-synchronous scheduler)
 __global__ void __launch_bounds__(256) k_combine(int level, LevelBufs L, LevelBufs Ln, const Counters* __restrict__ cnt) {
     const uint32_t n = cnt->n_diel[level];
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -313,17 +391,174 @@ __global__ void __launch_bounds__(256) k_combine(int level, LevelBufs L, LevelBu
         const uint2 ch = L.dn_child[i];
         float4 out = make_float4(0.f, 0.f, 0.f, 1.f);
         if (ch.x != PGRT_INVALID_ID) {
-            const float4 a = Ln.color[ch.x];
-            if (ch.y != PGRT_INVALID_ID) {
-                const float4 b = Ln.color[ch.y];
-                Col4 c0, c1; c0.r = a.x; c0.g = a.y; c0.b = a.z; c0.a = a.w; c1.r = b.x; c1.g = b.y; c1.b = b.z; c1.a = b.w;
-                const Col4 c = mix_srgb(c0, c1, att.w);
-                out = make_float4(c.r * att.x, c.g * att.y, c.b * att.z, 1.0f);
-            } else {
-                out = make_float4(a.x * att.x, a.y * att.y, a.z * att.z, 1.0f);
-            }
+            const bool has_b = ch.y != PGRT_INVALID_ID;
+            out = combine_node(att, Ln.color[ch.x], has_b, has_b ? Ln.color[ch.y] : make_float4(0.f, 0.f, 0.f, 0.f));
         }
         L.color[i] = out;
+    }
+}
+
+// ---- dynamic scheduler: every ray of level >= 1 in one persistent kernel (see the file header)
+// Each warp claims a share of the level-1 rays with one atomicAdd and then owns their whole sub-trees: children go to
+// the warp's own per-level mini-stacks in shared memory and are popped deepest level first, 32 at a time.
+// Popping deepest-first means a level receives children only in an iteration that has just drained it, so no level
+// ever holds more than 64 entries (2 children x 32 lanes): PGRT_WSTACK per level is exact, not a guess.
+// No warp ever waits for another one: there is no queue to poll and nothing to time out.
+#define PGRT_WSTACK 64
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_secondary(DevScene sc, pgrt_render_params p, LevelBufs L0, RayPool P, Counters* cnt) {
+    extern __shared__ uint32_t pgrt_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_lv = p.max_depth;                                   // rays exist at levels 1 .. max_depth
+    uint32_t* stk = pgrt_smem + (size_t)warp * n_lv * (PGRT_WSTACK + 1);   // [n_lv][PGRT_WSTACK] slots, then [n_lv] counts
+    uint32_t* lvc = stk + (size_t)n_lv * PGRT_WSTACK;
+    for (int l = lane; l < n_lv; l += 32) lvc[l] = 0;
+    __syncwarp();
+    const uint32_t n_l1 = min(cnt->q_l1, P.cap);
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    // the phase is latency-bound (few rays, dependent chains): spread the level-1 rays over all warps, so a warp
+    // runs as few lanes as possible (less divergence, and an iteration lasts as long as its slowest lane)
+    const uint32_t share = min(32u, max(1u, (n_l1 + n_warps - 1u) / n_warps));
+    unsigned long long my_shadow = 0, my_refl = 0, my_refr = 0;
+    int top = 0;                                                    // deepest non-empty level, 0 = none
+    for (;;) {
+        if (top == 0) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&cnt->q_head, share);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n_l1) break;
+            const uint32_t n = min(share, n_l1 - base);
+            if ((uint32_t)lane < n) stk[lane] = base + (uint32_t)lane;
+            if (lane == 0) lvc[0] = n;
+            __syncwarp();
+            top = 1;
+        }
+        // ---- pop up to 32 records, deepest level first
+        uint32_t i = PGRT_INVALID_ID; int level = 0;
+        {
+            uint32_t taken = 0;
+            for (int l = top; l >= 1 && taken < 32u; --l) {
+                const uint32_t c = lvc[l - 1];
+                const uint32_t take = min(c, 32u - taken);
+                if ((uint32_t)lane >= taken && (uint32_t)lane < taken + take) { i = stk[(size_t)(l - 1) * PGRT_WSTACK + c - 1u - ((uint32_t)lane - taken)]; level = l; }
+                __syncwarp();
+                if (lane == 0) lvc[l - 1] = c - take;
+                taken += take;
+            }
+            __syncwarp();
+        }
+        const bool usable = i != PGRT_INVALID_ID;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(0.f, 0.f, 0.f, -1.0f);
+        uint2 lk = make_uint2(0u, 0u);
+        if (usable) { o = __ldcg(&P.ray_o[i]); d = __ldcg(&P.ray_d[i]); lk = __ldcg(&P.link[i]); }
+        const bool live = usable && d.w >= 0.0f;
+
+        // ---- trace() for this ray: closest hit, classification, Phong (with its shadow query)
+        ShadeOut s; s.kind = SK_FINAL; s.has_refr = false;
+        bool final_ = false;
+        float4 col = make_float4(0.f, 0.f, 0.f, 1.f);
+        if (live) {
+            TravCount tc; tc.nodes = 0; tc.tris = 0;
+            const HitRec hr = trace_closest_t<COUNT>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, FLT_MAX, tc);
+            atomicAdd(&cnt->lv_rays[level], 1ull);
+            if (COUNT) {
+                atomicAdd(&cnt->lv_nodes[level], (unsigned long long)tc.nodes);
+                atomicAdd(&cnt->lv_tris[level], (unsigned long long)tc.tris); atomicMax(&cnt->lv_max_nodes[level], tc.nodes);
+            }
+            shade_classify(sc, p, level, o, d, make_float4(hr.t, hr.u, hr.v, __uint_as_float(hr.tri)), s);
+            if (s.kind == SK_FINAL) { col = s.color; final_ = true; }
+            else if (s.kind == SK_PHONG) {
+                const unsigned long long sh0 = my_shadow;
+                TravAcc a1; a1.nodes = 0; a1.tris = 0; a1.mx = 0;
+                col = phong_eval<COUNT>(sc, p, o, d, s.f, my_shadow, a1);
+                final_ = true;
+                if (my_shadow != sh0) atomicAdd(&cnt->lv_shadow[level], my_shadow - sh0);
+                if (COUNT) {
+                    atomicAdd(&cnt->lv_sh_nodes[level], a1.nodes); atomicAdd(&cnt->lv_sh_tris[level], a1.tris);
+                    atomicMax(&cnt->lv_sh_max_nodes[level], a1.mx);
+                }
+            }
+        }
+
+        // ---- dielectric hits: two pool records for the children (all 32 lanes take part in the aggregated atomics)
+        const bool is_diel = live && s.kind == SK_DIEL;
+        bool has_refr = is_diel && s.has_refr;
+        const uint32_t rl = warp_append(&cnt->q_tail, is_diel, lane);
+        const uint32_t rr = warp_append(&cnt->q_tail, has_refr, lane);
+        bool push = false;
+        if (is_diel) {
+            if (rl < P.cap && (!has_refr || rr < P.cap)) {
+                const uint32_t meta = (uint32_t)(level + 1);
+                __stcg(&P.ray_o[rl], make_float4(s.refl.o.x, s.refl.o.y, s.refl.o.z, s.refl.tnear));
+                __stcg(&P.ray_d[rl], make_float4(s.refl.d.x, s.refl.d.y, s.refl.d.z, s.refl.time));
+                __stcg(&P.link[rl], make_uint2(i, meta));
+                my_refl++;
+                if (has_refr) {
+                    __stcg(&P.ray_o[rr], make_float4(s.refr.o.x, s.refr.o.y, s.refr.o.z, s.refr.tnear));
+                    __stcg(&P.ray_d[rr], make_float4(s.refr.d.x, s.refr.d.y, s.refr.d.z, s.refr.time));
+                    __stcg(&P.link[rr], make_uint2(i, meta | (1u << 8)));
+                    my_refr++;
+                }
+                __stcg(&P.att[i], s.att);
+                __stcg(&P.child[i], make_uint2(rl, has_refr ? rr : PGRT_INVALID_ID));
+                __stcg(&P.pending[i], has_refr ? 2u : 1u);
+                push = true;
+            } else {
+                cnt->overflow = 1u;   // black; the frame is re-rendered in smaller batches
+                final_ = true; has_refr = false;
+            }
+        }
+        // ---- push the children on the mini-stack of their level (lanes grouped by level with match_any)
+        int new_top = top;
+        #pragma unroll
+        for (int kind = 0; kind < 2; ++kind) {
+            const bool need = push && (kind == 0 || has_refr);
+            const int clevel = need ? level + 1 : 0;
+            const unsigned grp = __match_any_sync(0xffffffffu, clevel);
+            uint32_t basec = 0;
+            if (need) {
+                basec = lvc[clevel - 1];
+                const uint32_t pos = basec + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+                if (pos < PGRT_WSTACK) stk[(size_t)(clevel - 1) * PGRT_WSTACK + pos] = kind == 0 ? rl : rr;
+                else cnt->watchdog = 2u;   // cannot happen (see the bound above); never write out of bounds
+            }
+            __syncwarp();
+            if (need && lane == __ffs(grp) - 1) lvc[clevel - 1] = min(basec + (uint32_t)__popc(grp), (uint32_t)PGRT_WSTACK);
+            __syncwarp();
+            new_top = max(new_top, clevel);
+        }
+        for (int o2 = 16; o2 > 0; o2 >>= 1) new_top = max(new_top, __shfl_xor_sync(0xffffffffu, new_top, o2));
+        top = new_top;
+        while (top > 0 && lvc[top - 1] == 0u) --top;
+
+        // ---- continuation: hand the value to the parent; the last child to arrive evaluates the parent and climbs on
+        if (final_) {
+            uint32_t node = i; uint2 nlk = lk; float4 c = col;
+            for (;;) {
+                __stcg(&P.color[node], c);
+                const uint32_t par = nlk.x; const bool par_l0 = (nlk.y >> 9) & 1u;
+                __threadfence();
+                const uint32_t old = atomicSub(par_l0 ? &L0.pending[par] : &P.pending[par], 1u);
+                if (old != 1u) break;
+                __threadfence();
+                const uint2 ch = par_l0 ? __ldcg(&L0.dn_child[par]) : __ldcg(&P.child[par]);
+                const float4 att = par_l0 ? __ldcg(&L0.dn_att[par]) : __ldcg(&P.att[par]);
+                const bool has_b = ch.y != PGRT_INVALID_ID;
+                c = combine_node(att, __ldcg(&P.color[ch.x]), has_b, has_b ? __ldcg(&P.color[ch.y]) : make_float4(0.f, 0.f, 0.f, 0.f));
+                if (par_l0) { L0.color[par] = c; break; }
+                node = par; nlk = __ldcg(&P.link[par]);
+            }
+        }
+        __syncwarp();
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        my_shadow += __shfl_xor_sync(0xffffffffu, my_shadow, o); my_refl += __shfl_xor_sync(0xffffffffu, my_refl, o); my_refr += __shfl_xor_sync(0xffffffffu, my_refr, o);
+    }
+    if (lane == 0) {
+        if (my_shadow) atomicAdd(&cnt->shadow, my_shadow);
+        if (my_refl) atomicAdd(&cnt->reflection, my_refl);
+        if (my_refr) atomicAdd(&cnt->refraction, my_refr);
     }
 }
 
@@ -370,10 +605,10 @@ __global__ void __launch_bounds__(256) k_primary_ids(DevScene sc, DevCamera cam,
 __global__ void k_batch_begin(Counters* c) {
     const int t = threadIdx.x;
     if (t <= PGRT_MAX_LEVELS) { c->n_rays[t] = 0; c->n_phong[t] = 0; c->n_diel[t] = 0; }
-    if (t == 0) { c->shadow = 0; c->reflection = 0; c->refraction = 0; }
+    if (t == 0) { c->shadow = 0; c->reflection = 0; c->refraction = 0; c->q_head = 0; c->q_l1 = 0; c->q_tail = 0; }
 }
-__global__ void k_batch_end(Counters* c, unsigned long long primary) {
-    if (threadIdx.x <= PGRT_MAX_LEVELS && threadIdx.x > 0) c->lv_rays[threadIdx.x] += c->n_rays[threadIdx.x];
+__global__ void k_batch_end(Counters* c, unsigned long long primary, int dyn) {
+    if (!dyn && threadIdx.x <= PGRT_MAX_LEVELS && threadIdx.x > 0) c->lv_rays[threadIdx.x] += c->n_rays[threadIdx.x];
     if (threadIdx.x == 0) { c->lv_rays[0] += primary; c->tot_shadow += c->shadow; c->tot_reflection += c->reflection; c->tot_refraction += c->refraction; c->tot_primary += primary; }
 }
 __global__ void k_frame_begin(Counters* c) {
@@ -382,7 +617,7 @@ __global__ void k_frame_begin(Counters* c) {
         c->lv_rays[t] = 0; c->lv_shadow[t] = 0; c->lv_nodes[t] = 0; c->lv_tris[t] = 0; c->lv_sh_nodes[t] = 0; c->lv_sh_tris[t] = 0;
         c->lv_max_nodes[t] = 0; c->lv_sh_max_nodes[t] = 0;
     }
-    if (threadIdx.x == 0) { c->overflow = 0; c->tot_shadow = 0; c->tot_reflection = 0; c->tot_refraction = 0; c->tot_primary = 0; }
+    if (threadIdx.x == 0) { c->overflow = 0; c->watchdog = 0; c->tot_shadow = 0; c->tot_reflection = 0; c->tot_refraction = 0; c->tot_primary = 0; }
 }
 
 // ---- batch rtcIntersect1 over RTCRayHit-compatible records (device copies)

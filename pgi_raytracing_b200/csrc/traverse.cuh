@@ -10,23 +10,23 @@ struct HitRec { float t, u, v; uint32_t tri; };   // tri = flat triangle id, PGR
 
 // Embree 3 TriangleM / Moeller-Trumbore formulation, restated (same operation order as the oracle states):
 //   C = v0 - O; R = C x D; Ng = e2 x e1; den = Ng.D; U = R.e2; V = R.e1; T = Ng.C  (sign of den folded in)
-__device__ __forceinline__ void tri_test(const float4* __restrict__ tris, uint32_t k, V3 O, V3 D, float tnear, float tfar, HitRec& best) {
-    const float4 q0 = __ldg(tris + 3 * (size_t)k), q1 = __ldg(tris + 3 * (size_t)k + 1), q2 = __ldg(tris + 3 * (size_t)k + 2);
+PG_HD void tri_test(const float4* __restrict__ tris, uint32_t k, V3 O, V3 D, float tnear, float tfar, HitRec& best) {
+    const float4 q0 = pg_ldg4(tris + 3 * (size_t)k), q1 = pg_ldg4(tris + 3 * (size_t)k + 1), q2 = pg_ldg4(tris + 3 * (size_t)k + 2);
     const V3 v0 = v3(q0.x, q0.y, q0.z), e1 = v3(q1.x, q1.y, q1.z), e2 = v3(q2.x, q2.y, q2.z);
     const V3 Ng = e_cross(e2, e1);
     const V3 C = v0 - O;
     const V3 R = e_cross(C, D);
     const float den = e_dot(Ng, D);
     const float absDen = fabsf(den);
-    const uint32_t sgn = __float_as_uint(den) & 0x80000000u;
-    const float U = __uint_as_float(__float_as_uint(e_dot(R, e2)) ^ sgn);
-    const float V = __uint_as_float(__float_as_uint(e_dot(R, e1)) ^ sgn);
+    const uint32_t sgn = pg_f2u(den) & 0x80000000u;
+    const float U = pg_u2f(pg_f2u(e_dot(R, e2)) ^ sgn);
+    const float V = pg_u2f(pg_f2u(e_dot(R, e1)) ^ sgn);
     if (!(den != 0.0f && U >= 0.0f && V >= 0.0f && U + V <= absDen)) return;
-    const float T = __uint_as_float(__float_as_uint(e_dot(Ng, C)) ^ sgn);
+    const float T = pg_u2f(pg_f2u(e_dot(Ng, C)) ^ sgn);
     if (!(absDen * tnear < T && T <= absDen * tfar)) return;
     const float rcp = 1.0f / absDen;
     const float t = T * rcp;
-    const uint32_t id = __float_as_uint(q0.w);
+    const uint32_t id = pg_f2u(q0.w);
     if (t < best.t || (t == best.t && id < best.tri)) { best.t = t; best.u = U * rcp; best.v = V * rcp; best.tri = id; }
 }
 

@@ -275,10 +275,30 @@ def test_render_is_deterministic_and_batching_invariant(P, cornell, monkeypatch)
     assert (sa["shadow"], sa["reflection"], sa["refraction"]) == (sc_["shadow"], sc_["reflection"], sc_["refraction"])
 
 
-def test_queue_overflow_falls_back_to_smaller_batches(P, cornell, monkeypatch):
-    monkeypatch.setenv("PGRT_MIN_LEVEL_CAP", "2048"); monkeypatch.setenv("PGRT_LEVEL_CAP_FACTOR", "0.05")
+def test_schedulers_agree_bit_for_bit(P, cornell, avenger):
+    """The persistent dynamic scheduler (continuation-passing combine, no level barrier) and the level-synchronous
+    wavefront evaluate the same tree with the same arithmetic: frames and ray counts must be identical."""
+    sc, rt, o = avenger
+    cases = [(P.raytracer_for(cornell), dict(seed=5)), (P.raytracer_for(cornell), dict(seed=5, max_depth=1)),
+             (rt, dict(sampling_width=1, jitter=0, aperture=0.0, max_depth=10)), (rt, dict(sampling_width=2, seed=9, max_depth=4))]
+    for r, p in cases:
+        a, sa = r.render(dict(p, scheduler=0)); b, sb = r.render(dict(p, scheduler=1))
+        assert np.array_equal(a, b, equal_nan=True), p
+        for k in ("primary", "shadow", "reflection", "refraction"):
+            assert sa[k] == sb[k], (k, p)
+        assert sa["launches"] < sb["launches"] or p.get("max_depth") == 1
+    la = rt.render(dict(cases[2][1], scheduler=0), profile=3)[1]; lv0 = rt.level_stats()
+    lb = rt.render(dict(cases[2][1], scheduler=1), profile=3)[1]; lv1 = rt.level_stats()
+    assert [x["rays"] for x in lv0] == [x["rays"] for x in lv1] and [x["shadow_rays"] for x in lv0] == [x["shadow_rays"] for x in lv1]
+    assert (la["nodes_visited"], la["tris_tested"]) == (lb["nodes_visited"], lb["tris_tested"]) and la["nodes_visited"] > 0
+
+
+@pytest.mark.parametrize("scheduler", [0, 1])
+def test_queue_overflow_falls_back_to_smaller_batches(P, cornell, monkeypatch, scheduler):
+    # the dynamic scheduler keeps ONE pool (4 x cap) for all levels; the worst 32x8 tile of this frame needs 8385 records
+    monkeypatch.setenv("PGRT_MIN_LEVEL_CAP", "2500" if scheduler == 0 else "2048"); monkeypatch.setenv("PGRT_LEVEL_CAP_FACTOR", "0.05")
     rt = P.raytracer_for(cornell)
-    p = dict(seed=2)
+    p = dict(seed=2, scheduler=scheduler)
     img, st = rt.render(p)
     assert st["overflow_retries"] >= 1
     monkeypatch.delenv("PGRT_MIN_LEVEL_CAP"); monkeypatch.delenv("PGRT_LEVEL_CAP_FACTOR")
