@@ -66,10 +66,15 @@ typedef struct pgrt_render_params {
 
 typedef struct pgrt_build_stats {
     uint32_t triangles;
-    uint32_t nodes;           /* wide nodes emitted                                              */
+    uint32_t nodes;           /* 8-wide nodes emitted (80 B each)                                */
     float build_ms;           /* device time of the whole commit (Morton .. collapse)            */
-    float sort_ms;
-    float sah_cost;           /* SAH cost of the emitted tree (Ct=1, Ci=1), for build-quality tests */
+    float sort_ms;            /* radix sort of the Morton keys                                   */
+    float sah_cost;           /* SAH cost of the emitted wide tree: sum(area(node)) + sum(area(leaf slot) * triangles),
+                                 over area(root)                                                  */
+    float tree_ms;            /* binary tree over the Morton order (PLOC passes)                 */
+    float collapse_ms;        /* collapse to the wide layout + triangle re-layout                */
+    uint32_t depth;           /* levels of the wide tree                                         */
+    uint32_t ploc_passes;     /* multi-block PLOC passes (the last <= 512 clusters finish in one block) */
     uint32_t reserved[3];
 } pgrt_build_stats;
 

@@ -34,7 +34,8 @@ class RenderParams(C.Structure):
 
 class BuildStats(C.Structure):
     _fields_ = [("triangles", C.c_uint32), ("nodes", C.c_uint32), ("build_ms", C.c_float), ("sort_ms", C.c_float),
-                ("sah_cost", C.c_float), ("reserved", C.c_uint32 * 3)]
+                ("sah_cost", C.c_float), ("tree_ms", C.c_float), ("collapse_ms", C.c_float), ("depth", C.c_uint32),
+                ("ploc_passes", C.c_uint32), ("reserved", C.c_uint32 * 3)]
 
 
 class RenderStats(C.Structure):

@@ -105,7 +105,7 @@ class Raytracer:
     def commit(self) -> dict:
         bs = L.BuildStats()
         self._check(self.lib.pgrt_commit(self.h, C.byref(bs)))
-        self.build_stats = dict(triangles=bs.triangles, nodes=bs.nodes, build_ms=bs.build_ms, sort_ms=bs.sort_ms, sah_cost=bs.sah_cost)
+        self.build_stats = {k: getattr(bs, k) for k, _ in L.BuildStats._fields_ if k != "reserved"}
         return self.build_stats
 
     # ---- the path

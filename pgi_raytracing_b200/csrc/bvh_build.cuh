@@ -9,6 +9,7 @@
 //   K5  k_emit_*            collapse to the traversal layout + triangle re-layout (3 x float4 per triangle)
 #pragma once
 #include "common.cuh"
+#include "bvh8.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // ordered-int float atomics
@@ -314,4 +315,250 @@ __global__ void __launch_bounds__(256) k_sah_cost(int n, BinTree t, float* __res
     }
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0 && c != 0.0f) atomicAdd(out, c);
+}
+
+// ===================================================================================================
+// K4: PLOC -- agglomerative refinement of the Morton order (Meister & Bittner, "Parallel Locally-Ordered Clustering
+// for BVH Construction", TVCG 2018).  Clusters start as the Morton-sorted triangles; every pass each cluster finds,
+// among its PLOC_R neighbours on either side in the current order, the one whose merged box has the smallest
+// surface area; mutual pairs merge into a new binary node, everything else is carried over, and the array is
+// compacted in order.  The minimum of (area, lower index, higher index) over all pairs in range is always mutual,
+// so every pass merges at least one pair.  Node ids are assigned by prefix sums, so the tree is deterministic.
+//
+// Binary tree layout shared with the collapse (Bvh2View in bvh8.cuh): leaves 0..N-1, internal nodes N..2N-2 in
+// creation order (root = 2N-2), b0 = (lo, left), b1 = (hi, right), count = triangles below.
+#define PLOC_R 16
+#define PLOC_THREADS 256
+
+__global__ void __launch_bounds__(256) k_ploc_init(const float* __restrict__ pos, const uint32_t* __restrict__ vals, uint32_t n,
+                                                   float4* __restrict__ b0, float4* __restrict__ b1, uint32_t* __restrict__ count, uint32_t* __restrict__ cid) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float lo[3], hi[3];
+    tri_aabb(pos + 9 * (size_t)vals[k], lo, hi);
+    b0[k] = make_float4(lo[0], lo[1], lo[2], __uint_as_float(0xFFFFFFFFu));
+    b1[k] = make_float4(hi[0], hi[1], hi[2], __uint_as_float(0xFFFFFFFFu));
+    count[k] = 1u; cid[k] = k;
+}
+
+__device__ __forceinline__ float merged_half_area(const float* a_lo, const float* a_hi, float blx, float bly, float blz, float bhx, float bhy, float bhz) {
+    const float dx = fmaxf(a_hi[0], bhx) - fminf(a_lo[0], blx), dy = fmaxf(a_hi[1], bhy) - fminf(a_lo[1], bly), dz = fmaxf(a_hi[2], bhz) - fminf(a_lo[2], blz);
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void __launch_bounds__(PLOC_THREADS) k_ploc_nn(const float4* __restrict__ b0, const float4* __restrict__ b1, const uint32_t* __restrict__ cid,
+                                                          uint32_t n, int* __restrict__ nn) {
+    __shared__ float sb[6][PLOC_THREADS + 2 * PLOC_R];
+    const long first = (long)blockIdx.x * PLOC_THREADS - PLOC_R;
+    for (int k = threadIdx.x; k < PLOC_THREADS + 2 * PLOC_R; k += PLOC_THREADS) {
+        const long g = first + k;
+        if (g >= 0 && g < (long)n) {
+            const uint32_t node = cid[g];
+            const float4 lo = b0[node], hi = b1[node];
+            sb[0][k] = lo.x; sb[1][k] = lo.y; sb[2][k] = lo.z; sb[3][k] = hi.x; sb[4][k] = hi.y; sb[5][k] = hi.z;
+        }
+    }
+    __syncthreads();
+    const long i = (long)blockIdx.x * PLOC_THREADS + threadIdx.x;
+    if (i >= (long)n) return;
+    const int me = threadIdx.x + PLOC_R;
+    const float lo[3] = {sb[0][me], sb[1][me], sb[2][me]}, hi[3] = {sb[3][me], sb[4][me], sb[5][me]};
+    float best = FLT_MAX; int bj = -1;
+#pragma unroll 4
+    for (int off = -PLOC_R; off <= PLOC_R; ++off) {
+        const long j = i + off;
+        if (off == 0 || j < 0 || j >= (long)n) continue;
+        const int k = me + off;
+        const float a = merged_half_area(lo, hi, sb[0][k], sb[1][k], sb[2][k], sb[3][k], sb[4][k], sb[5][k]);
+        if (a < best) { best = a; bj = (int)j; }   // ascending j, strict <: ties keep the lower index
+    }
+    nn[i] = bj;
+}
+
+// flags of cluster i: bit 0 = survives into the next pass, bit 1 = creates a node (the lower index of a mutual pair)
+__device__ __forceinline__ uint32_t ploc_flags(const int* __restrict__ nn, uint32_t i, uint32_t n) {
+    if (i >= n) return 0u;
+    const int j = nn[i];
+    const bool mutual = j >= 0 && nn[j] == (int)i;
+    if (mutual) return (uint32_t)j > i ? 3u : 0u;
+    return 1u;
+}
+
+__global__ void __launch_bounds__(PLOC_THREADS) k_ploc_count(const int* __restrict__ nn, uint32_t n, uint2* __restrict__ block_sums) {
+    const uint32_t f = ploc_flags(nn, blockIdx.x * PLOC_THREADS + threadIdx.x, n);
+    const int v = __syncthreads_count(f & 1u), m = __syncthreads_count(f & 2u);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = make_uint2((uint32_t)v, (uint32_t)m);
+}
+
+// exclusive scan of the per-block (survivors, merges) in place; totals -> out[0]
+__global__ void __launch_bounds__(1024) k_ploc_scan(uint2* __restrict__ sums, uint32_t nb, uint2* __restrict__ totals) {
+    __shared__ uint2 wsum[32];
+    __shared__ uint2 carry;
+    if (threadIdx.x == 0) carry = make_uint2(0u, 0u);
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint2 v = i < nb ? sums[i] : make_uint2(0u, 0u);
+        uint2 inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t tx = __shfl_up_sync(0xffffffffu, inc.x, o), ty = __shfl_up_sync(0xffffffffu, inc.y, o);
+            if ((threadIdx.x & 31) >= o) { inc.x += tx; inc.y += ty; }
+        }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const uint2 w = wsum[threadIdx.x]; uint2 wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t tx = __shfl_up_sync(0xffffffffu, wi.x, o), ty = __shfl_up_sync(0xffffffffu, wi.y, o);
+                if (threadIdx.x >= o) { wi.x += tx; wi.y += ty; }
+            }
+            wsum[threadIdx.x] = make_uint2(wi.x - w.x, wi.y - w.y);
+        }
+        __syncthreads();
+        const uint2 c = carry, ws = wsum[threadIdx.x >> 5];
+        if (i < nb) sums[i] = make_uint2(c.x + ws.x + inc.x - v.x, c.y + ws.y + inc.y - v.y);
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = make_uint2(c.x + ws.x + inc.x, c.y + ws.y + inc.y);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *totals = carry;
+}
+
+__global__ void __launch_bounds__(PLOC_THREADS) k_ploc_apply(const int* __restrict__ nn, const uint32_t* __restrict__ cid_in, uint32_t n,
+                                                             const uint2* __restrict__ block_offs, uint32_t next_node,
+                                                             float4* __restrict__ b0, float4* __restrict__ b1, uint32_t* __restrict__ count,
+                                                             uint32_t* __restrict__ cid_out) {
+    __shared__ uint32_t wv[PLOC_THREADS / 32], wm[PLOC_THREADS / 32];
+    const uint32_t i = blockIdx.x * PLOC_THREADS + threadIdx.x;
+    const uint32_t f = ploc_flags(nn, i, n);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned bv = __ballot_sync(0xffffffffu, f & 1u), bm = __ballot_sync(0xffffffffu, f & 2u);
+    if (lane == 0) { wv[warp] = __popc(bv); wm[warp] = __popc(bm); }
+    __syncthreads();
+    uint32_t pv = 0, pm = 0;
+    for (int w = 0; w < warp; ++w) { pv += wv[w]; pm += wm[w]; }
+    if (!(f & 1u)) return;
+    const uint2 off = block_offs[blockIdx.x];
+    const uint32_t dst = off.x + pv + __popc(bv & ((1u << lane) - 1u));
+    uint32_t node = cid_in[i];
+    if (f & 2u) {
+        const uint32_t other = cid_in[nn[i]];
+        const uint32_t id = next_node + off.y + pm + __popc(bm & ((1u << lane) - 1u));
+        const float4 al = b0[node], ah = b1[node], bl = b0[other], bh = b1[other];
+        b0[id] = make_float4(fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z), __uint_as_float(node));
+        b1[id] = make_float4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), __uint_as_float(other));
+        count[id] = count[node] + count[other];
+        node = id;
+    }
+    cid_out[dst] = node;
+}
+
+// the last passes (n <= PLOC_FINISH clusters) in one block, boxes and ids in shared memory
+#define PLOC_FINISH 512
+__global__ void __launch_bounds__(PLOC_FINISH) k_ploc_finish(const uint32_t* __restrict__ cid_in, uint32_t n, uint32_t next_node,
+                                                             float4* __restrict__ b0, float4* __restrict__ b1, uint32_t* __restrict__ count) {
+    __shared__ uint32_t s_cid[2][PLOC_FINISH], s_cnt[2][PLOC_FINISH];
+    __shared__ float s_box[2][6][PLOC_FINISH];
+    __shared__ int s_nn[PLOC_FINISH];
+    __shared__ uint32_t wv[PLOC_FINISH / 32], wm[PLOC_FINISH / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int cur = 0;
+    if ((uint32_t)tid < n) {
+        const uint32_t node = cid_in[tid];
+        const float4 lo = b0[node], hi = b1[node];
+        s_cid[0][tid] = node; s_cnt[0][tid] = count[node];
+        s_box[0][0][tid] = lo.x; s_box[0][1][tid] = lo.y; s_box[0][2][tid] = lo.z; s_box[0][3][tid] = hi.x; s_box[0][4][tid] = hi.y; s_box[0][5][tid] = hi.z;
+    }
+    __syncthreads();
+    while (n > 1) {
+        if ((uint32_t)tid < n) {
+            const float lo[3] = {s_box[cur][0][tid], s_box[cur][1][tid], s_box[cur][2][tid]}, hi[3] = {s_box[cur][3][tid], s_box[cur][4][tid], s_box[cur][5][tid]};
+            float best = FLT_MAX; int bj = -1;
+            for (int off = -PLOC_R; off <= PLOC_R; ++off) {
+                const int j = tid + off;
+                if (off == 0 || j < 0 || j >= (int)n) continue;
+                const float a = merged_half_area(lo, hi, s_box[cur][0][j], s_box[cur][1][j], s_box[cur][2][j], s_box[cur][3][j], s_box[cur][4][j], s_box[cur][5][j]);
+                if (a < best) { best = a; bj = j; }
+            }
+            s_nn[tid] = bj;
+        }
+        __syncthreads();
+        const uint32_t f = ploc_flags(s_nn, (uint32_t)tid, n);
+        const unsigned bv = __ballot_sync(0xffffffffu, f & 1u), bm = __ballot_sync(0xffffffffu, f & 2u);
+        if (lane == 0) { wv[warp] = __popc(bv); wm[warp] = __popc(bm); }
+        __syncthreads();
+        uint32_t pv = 0, pm = 0, tv = 0, tmg = 0;
+        for (int w = 0; w < PLOC_FINISH / 32; ++w) { if (w < warp) { pv += wv[w]; pm += wm[w]; } tv += wv[w]; tmg += wm[w]; }
+        if (f & 1u) {
+            const uint32_t dst = pv + __popc(bv & ((1u << lane) - 1u));
+            uint32_t node = s_cid[cur][tid], cnt = s_cnt[cur][tid];
+            float bx[6];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) bx[a] = s_box[cur][a][tid];
+            if (f & 2u) {
+                const int j = s_nn[tid];
+                const uint32_t other = s_cid[cur][j];
+                const uint32_t id = next_node + pm + __popc(bm & ((1u << lane) - 1u));
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { bx[a] = fminf(bx[a], s_box[cur][a][j]); bx[3 + a] = fmaxf(bx[3 + a], s_box[cur][3 + a][j]); }
+                cnt += s_cnt[cur][j];
+                b0[id] = make_float4(bx[0], bx[1], bx[2], __uint_as_float(node));
+                b1[id] = make_float4(bx[3], bx[4], bx[5], __uint_as_float(other));
+                count[id] = cnt;
+                node = id;
+            }
+            s_cid[cur ^ 1][dst] = node; s_cnt[cur ^ 1][dst] = cnt;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) s_box[cur ^ 1][a][dst] = bx[a];
+        }
+        __syncthreads();
+        n = tv; next_node += tmg; cur ^= 1;
+    }
+}
+
+// the Karras tree (k_karras + k_refit) in the layout above: leaf k -> node k, internal j -> node N + j (root = N)
+__global__ void __launch_bounds__(256) k_lbvh_to_b2(int n, BinTree t, const uint32_t* __restrict__ vals, float4* __restrict__ b0, float4* __restrict__ b1,
+                                                    uint32_t* __restrict__ count) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 2 * n - 1) return;
+    // source numbering: internal 0..n-2, leaves n-1..2n-2
+    const bool leaf = k >= n - 1;
+    const int dst = leaf ? k - (n - 1) : n + k;
+    auto remap = [n](int c) { return (uint32_t)(c >= n - 1 ? c - (n - 1) : n + c); };
+    const float* lo = t.lo + 3 * (size_t)k; const float* hi = t.hi + 3 * (size_t)k;
+    b0[dst] = make_float4(lo[0], lo[1], lo[2], __uint_as_float(leaf ? 0xFFFFFFFFu : remap(t.left[k])));
+    b1[dst] = make_float4(hi[0], hi[1], hi[2], __uint_as_float(leaf ? 0xFFFFFFFFu : remap(t.right[k])));
+    count[dst] = leaf ? 1u : (uint32_t)(t.last[k] - t.first[k] + 1);
+}
+
+// ===================================================================================================
+// K5: collapse to the wide layout, one tree level per launch, one thread per wide node (bvh8_gather / bvh8_emit).
+// work item = (binary root, wide node index); children of a node are contiguous (child_base from one atomicAdd),
+// as are its leaf triangles (tri_base).  The hit record never depends on the layout (ties resolve by flat id).
+struct CollapseCounters { uint32_t nodes, tris, next_items, pad; float sah; };
+
+__global__ void __launch_bounds__(128) k_collapse(Bvh2View t, const float* __restrict__ pos, const uint2* __restrict__ items, uint32_t n_items,
+                                                  uint2* __restrict__ next_items, CollapseCounters* __restrict__ cc,
+                                                  float4* __restrict__ nodes, float4* __restrict__ tris) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    float sah = 0.0f;
+    if (k < n_items) {
+        const uint2 it = items[k];
+        Wide8 w;
+        bvh8_gather(t, it.x, w);
+        int n_int, n_tri;
+        bvh8_counts(t, w, n_int, n_tri);
+        const uint32_t child_base = n_int ? atomicAdd(&cc->nodes, (uint32_t)n_int) : 0u;
+        const uint32_t tri_base = n_tri ? atomicAdd(&cc->tris, (uint32_t)n_tri) : 0u;
+        uint32_t ic[8];
+        bvh8_emit(t, it.x, w, child_base, tri_base, pos, nodes + 5 * (size_t)it.y, tris, ic, sah);
+        if (n_int) {
+            const uint32_t q = atomicAdd(&cc->next_items, (uint32_t)n_int);
+            for (int r = 0; r < n_int; ++r) next_items[q + r] = make_uint2(ic[r], child_base + (uint32_t)r);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) sah += __shfl_xor_sync(0xffffffffu, sah, o);
+    if ((threadIdx.x & 31) == 0 && sah != 0.0f) atomicAdd(&cc->sah, sah);
 }

@@ -78,6 +78,7 @@ struct pgrt_context {
     DevBuf<float4> d_frame;
     DevBuf<uint32_t> d_ids;
     Counters* h_counters = nullptr;   // pinned
+    uint32_t* h_pin = nullptr;        // pinned scratch for small read-backs of the build
     size_t max_batch_samples = (size_t)1 << 23;
     size_t min_level_cap = (size_t)1 << 18;
     double level_cap_factor = 2.0;
@@ -129,6 +130,7 @@ extern "C" int pgrt_create(pgrt_context** out, int device) {
     ctx->stream = ctx->own_stream;
     cudaEventCreate(&ctx->ev_frame0); cudaEventCreate(&ctx->ev_frame1);
     if (cudaMallocHost((void**)&ctx->h_counters, sizeof(Counters)) != cudaSuccess) { delete ctx; return PGRT_ERR_CUDA; }
+    if (cudaMallocHost((void**)&ctx->h_pin, 256) != cudaSuccess) { delete ctx; return PGRT_ERR_CUDA; }
     if (ctx->d_counters.ensure(1) != cudaSuccess) { delete ctx; return PGRT_ERR_CUDA; }
     if (const char* e = getenv("PGRT_MAX_BATCH_SAMPLES")) ctx->max_batch_samples = std::max<size_t>(256, strtoull(e, nullptr, 10));
     if (const char* e = getenv("PGRT_MIN_LEVEL_CAP")) ctx->min_level_cap = std::max<size_t>(64, strtoull(e, nullptr, 10));
@@ -161,6 +163,7 @@ extern "C" void pgrt_destroy(pgrt_context* ctx) {
     if (ctx->ev_frame0) cudaEventDestroy(ctx->ev_frame0);
     if (ctx->ev_frame1) cudaEventDestroy(ctx->ev_frame1);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -286,32 +289,44 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
     CUDA_TRY(cudaMemcpyAsync(ctx->d_nrm.p, ctx->h_nrm.data(), 9 * (size_t)N * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_uv.p, ctx->h_uv.data(), 6 * (size_t)N * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_tri_geom.p, ctx->h_tri_geom.data(), (size_t)N * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx->d_shade.ensure(4 * (size_t)N)); CUDA_TRY(ctx->d_tris.ensure(3 * (size_t)N)); CUDA_TRY(ctx->d_nodes.ensure(4 * (size_t)std::max<uint32_t>(N - 1, 1)));
+    CUDA_TRY(ctx->d_shade.ensure(4 * (size_t)N)); CUDA_TRY(ctx->d_tris.ensure(3 * (size_t)N)); CUDA_TRY(ctx->d_nodes.ensure(5 * (size_t)N));
 
-    cudaEvent_t e0, e1, e2, e3;
-    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+    cudaEvent_t e0, e1, e2, e3, e4;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3); cudaEventCreate(&e4);
     // build temporaries
-    DevBuf<uint64_t> keys[2]; DevBuf<uint32_t> vals[2]; DevBuf<uint32_t> hist; DevBuf<SceneBounds> sb; DevBuf<float> sah;
+    DevBuf<uint64_t> keys[2]; DevBuf<uint32_t> vals[2]; DevBuf<uint32_t> hist; DevBuf<SceneBounds> sb;
+    DevBuf<float4> b0, b1; DevBuf<uint32_t> bcount, cid[2]; DevBuf<int> nn; DevBuf<uint2> bsums, items[2]; DevBuf<CollapseCounters> cc;
     DevBuf<int> ti[6]; DevBuf<float> tf[2];
     const uint32_t n_tiles = div_up(N, RS_TILE);
+    const bool use_lbvh = getenv("PGRT_BUILDER") && !strcmp(getenv("PGRT_BUILDER"), "lbvh");
     int rc = PGRT_OK;
     auto cleanup = [&]() {
-        keys[0].release(); keys[1].release(); vals[0].release(); vals[1].release(); hist.release(); sb.release(); sah.release();
+        keys[0].release(); keys[1].release(); vals[0].release(); vals[1].release(); hist.release(); sb.release();
+        b0.release(); b1.release(); bcount.release(); cid[0].release(); cid[1].release(); nn.release(); bsums.release(); items[0].release(); items[1].release(); cc.release();
         for (auto& b : ti) b.release(); for (auto& b : tf) b.release();
-        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3); cudaEventDestroy(e4);
     };
 #define BUILD_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = ctx->fail_cuda(e__, #call, __FILE__, __LINE__); cleanup(); return rc; } } while (0)
     BUILD_TRY(keys[0].ensure(N)); BUILD_TRY(keys[1].ensure(N)); BUILD_TRY(vals[0].ensure(N)); BUILD_TRY(vals[1].ensure(N));
-    BUILD_TRY(hist.ensure(256 * (size_t)n_tiles)); BUILD_TRY(sb.ensure(1)); BUILD_TRY(sah.ensure(1));
-    BUILD_TRY(ti[0].ensure(N)); BUILD_TRY(ti[1].ensure(N)); BUILD_TRY(ti[2].ensure(2 * (size_t)N)); BUILD_TRY(ti[3].ensure(N)); BUILD_TRY(ti[4].ensure(N)); BUILD_TRY(ti[5].ensure(N));
-    BUILD_TRY(tf[0].ensure(6 * (size_t)N)); BUILD_TRY(tf[1].ensure(6 * (size_t)N));
+    BUILD_TRY(hist.ensure(256 * (size_t)n_tiles)); BUILD_TRY(sb.ensure(1));
+    BUILD_TRY(b0.ensure(2 * (size_t)N)); BUILD_TRY(b1.ensure(2 * (size_t)N)); BUILD_TRY(bcount.ensure(2 * (size_t)N));
+    BUILD_TRY(items[0].ensure(N)); BUILD_TRY(items[1].ensure(N)); BUILD_TRY(cc.ensure(1));
+    if (use_lbvh) {
+        BUILD_TRY(ti[0].ensure(N)); BUILD_TRY(ti[1].ensure(N)); BUILD_TRY(ti[2].ensure(2 * (size_t)N)); BUILD_TRY(ti[3].ensure(N)); BUILD_TRY(ti[4].ensure(N)); BUILD_TRY(ti[5].ensure(N));
+        BUILD_TRY(tf[0].ensure(6 * (size_t)N)); BUILD_TRY(tf[1].ensure(6 * (size_t)N));
+        BUILD_TRY(cid[0].ensure(N));
+    } else {
+        BUILD_TRY(cid[0].ensure(N)); BUILD_TRY(cid[1].ensure(N)); BUILD_TRY(nn.ensure(N)); BUILD_TRY(bsums.ensure(div_up(N, PLOC_THREADS) + 1));
+    }
 
+    // ---- K1: Morton keys of the centroids
     BUILD_TRY(cudaEventRecord(e0, st));
     k_pack_shade<<<div_up(N, 256), 256, 0, st>>>(ctx->d_nrm.p, ctx->d_uv.p, ctx->d_tri_geom.p, N, ctx->d_shade.p);
     k_init_bounds<<<1, 32, 0, st>>>(sb.p);
     k_scene_bounds<<<std::min<unsigned>(div_up(N, 256), ctx->sm_count * 8), 256, 0, st>>>(ctx->d_pos.p, N, sb.p);
     k_morton<<<div_up(N, 256), 256, 0, st>>>(ctx->d_pos.p, N, sb.p, keys[0].p, vals[0].p);
     ctx->launches += 4;
+    // ---- K2: radix sort
     BUILD_TRY(cudaEventRecord(e1, st));
     int cur = 0;
     for (int pass = 0; pass < 8; ++pass) {
@@ -322,30 +337,79 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
         cur ^= 1; ctx->launches += 3;
     }
     BUILD_TRY(cudaEventRecord(e2, st));
-    k_emit_tris<<<div_up(N, 256), 256, 0, st>>>(ctx->d_pos.p, vals[cur].p, N, ctx->d_tris.p);
-    ctx->launches += 1;
-    if (N <= PGRT_LEAF_MAX) {
-        ctx->root = (uint32_t)leaf_ref(0, (int)N);
-        bs.nodes = 0; bs.sah_cost = (float)N;
+    // ---- K3/K4: binary tree over the Morton order
+    uint32_t root2 = 0, passes = 0;
+    if (use_lbvh) {
+        if (N >= 2) {
+            BinTree t; t.left = ti[0].p; t.right = ti[1].p; t.parent = ti[2].p; t.first = ti[3].p; t.last = ti[4].p; t.flag = ti[5].p; t.lo = tf[0].p; t.hi = tf[1].p;
+            k_karras<<<div_up(N - 1, 256), 256, 0, st>>>(keys[cur].p, (int)N, t);
+            k_refit<<<div_up(N, 256), 256, 0, st>>>(ctx->d_pos.p, vals[cur].p, (int)N, t);
+            k_lbvh_to_b2<<<div_up(2 * (size_t)N - 1, 256), 256, 0, st>>>((int)N, t, vals[cur].p, b0.p, b1.p, bcount.p);
+            ctx->launches += 3;
+            root2 = N;
+        } else {
+            k_ploc_init<<<1, 256, 0, st>>>(ctx->d_pos.p, vals[cur].p, N, b0.p, b1.p, bcount.p, cid[0].p);
+            ctx->launches += 1;
+        }
     } else {
-        BinTree t; t.left = ti[0].p; t.right = ti[1].p; t.parent = ti[2].p; t.first = ti[3].p; t.last = ti[4].p; t.flag = ti[5].p; t.lo = tf[0].p; t.hi = tf[1].p;
-        k_karras<<<div_up(N - 1, 256), 256, 0, st>>>(keys[cur].p, (int)N, t);
-        k_refit<<<div_up(N, 256), 256, 0, st>>>(ctx->d_pos.p, vals[cur].p, (int)N, t);
-        k_emit_bvh2<<<div_up(N - 1, 256), 256, 0, st>>>((int)N, t, ctx->d_nodes.p);
-        BUILD_TRY(cudaMemsetAsync(sah.p, 0, sizeof(float), st));
-        k_sah_cost<<<div_up(N - 1, 256), 256, 0, st>>>((int)N, t, sah.p);
-        ctx->launches += 4;
-        ctx->root = 0;
-        bs.nodes = N - 1;
+        k_ploc_init<<<div_up(N, 256), 256, 0, st>>>(ctx->d_pos.p, vals[cur].p, N, b0.p, b1.p, bcount.p, cid[0].p);
+        ctx->launches += 1;
+        uint32_t n = N, next = N; int c = 0;
+        while (n > PLOC_FINISH) {
+            const uint32_t nb = div_up(n, PLOC_THREADS);
+            k_ploc_nn<<<nb, PLOC_THREADS, 0, st>>>(b0.p, b1.p, cid[c].p, n, nn.p);
+            k_ploc_count<<<nb, PLOC_THREADS, 0, st>>>(nn.p, n, bsums.p);
+            k_ploc_scan<<<1, 1024, 0, st>>>(bsums.p, nb, bsums.p + nb);
+            k_ploc_apply<<<nb, PLOC_THREADS, 0, st>>>(nn.p, cid[c].p, n, bsums.p, next, b0.p, b1.p, bcount.p, cid[c ^ 1].p);
+            ctx->launches += 4; passes++;
+            BUILD_TRY(cudaMemcpyAsync(ctx->h_pin, bsums.p + nb, sizeof(uint2), cudaMemcpyDeviceToHost, st));
+            BUILD_TRY(cudaStreamSynchronize(st));
+            const uint32_t survivors = ctx->h_pin[0], merges = ctx->h_pin[1];
+            if (merges == 0 || survivors >= n) { rc = ctx->fail(PGRT_ERR_CUDA, "pgrt_commit: PLOC pass made no progress"); cleanup(); return rc; }
+            n = survivors; next += merges; c ^= 1;
+        }
+        if (n > 1) { k_ploc_finish<<<1, PLOC_FINISH, 0, st>>>(cid[c].p, n, next, b0.p, b1.p, bcount.p); ctx->launches += 1; }
+        root2 = N >= 2 ? 2 * N - 2 : 0;
     }
     BUILD_TRY(cudaEventRecord(e3, st));
+    // ---- K5: collapse to the 8-wide quantised layout, one level per launch
+    Bvh2View view; view.b0 = b0.p; view.b1 = b1.p; view.count = bcount.p; view.leaf_tri = vals[cur].p; view.n_leaves = N;
+    {
+        CollapseCounters init = {}; init.nodes = 1;
+        const uint2 first = make_uint2(root2, 0u);
+        BUILD_TRY(cudaMemcpyAsync(cc.p, &init, sizeof init, cudaMemcpyHostToDevice, st));
+        BUILD_TRY(cudaMemcpyAsync(items[0].p, &first, sizeof first, cudaMemcpyHostToDevice, st));
+    }
+    uint32_t n_items = 1, depth = 0; int ic = 0;
+    CollapseCounters hcc = {};
+    while (n_items) {
+        k_collapse<<<div_up(n_items, 128), 128, 0, st>>>(view, ctx->d_pos.p, items[ic].p, n_items, items[ic ^ 1].p, cc.p, ctx->d_nodes.p, ctx->d_tris.p);
+        ctx->launches += 1; depth++;
+        BUILD_TRY(cudaMemcpyAsync(ctx->h_pin, cc.p, sizeof(CollapseCounters), cudaMemcpyDeviceToHost, st));
+        BUILD_TRY(cudaMemsetAsync(&cc.p->next_items, 0, sizeof(uint32_t), st));
+        BUILD_TRY(cudaStreamSynchronize(st));
+        memcpy(&hcc, ctx->h_pin, sizeof hcc);
+        n_items = hcc.next_items; ic ^= 1;
+        if (depth > 4096) break;
+    }
+    BUILD_TRY(cudaEventRecord(e4, st));
     BUILD_TRY(cudaGetLastError());
+    float4 rb[2];
+    BUILD_TRY(cudaMemcpyAsync(&rb[0], b0.p + root2, sizeof(float4), cudaMemcpyDeviceToHost, st));
+    BUILD_TRY(cudaMemcpyAsync(&rb[1], b1.p + root2, sizeof(float4), cudaMemcpyDeviceToHost, st));
     BUILD_TRY(cudaStreamSynchronize(st));
-    if (N > PGRT_LEAF_MAX) BUILD_TRY(cudaMemcpy(&bs.sah_cost, sah.p, sizeof(float), cudaMemcpyDeviceToHost));
-    cudaEventElapsedTime(&bs.build_ms, e0, e3);
+    if (hcc.tris != N) { rc = ctx->fail(PGRT_ERR_CUDA, "pgrt_commit: collapse emitted a wrong number of triangles"); cleanup(); return rc; }
+    if (depth + 2 > PGRT_STACK8) { rc = ctx->fail(PGRT_ERR_INVALID, "pgrt_commit: the tree is deeper than the traversal stack (degenerate input)"); cleanup(); return rc; }
+    const float ra = box_half_area(rb[0], rb[1]);
+    bs.nodes = hcc.nodes; bs.sah_cost = ra > 0.0f ? hcc.sah / ra : (float)N;
+    bs.depth = depth; bs.ploc_passes = passes;
+    cudaEventElapsedTime(&bs.build_ms, e0, e4);
     cudaEventElapsedTime(&bs.sort_ms, e1, e2);
+    cudaEventElapsedTime(&bs.tree_ms, e2, e3);
+    cudaEventElapsedTime(&bs.collapse_ms, e3, e4);
 #undef BUILD_TRY
     cleanup();
+    ctx->root = 0;
     ctx->committed = true; ctx->last_build = bs;
     if (stats) *stats = bs;
     return PGRT_OK;

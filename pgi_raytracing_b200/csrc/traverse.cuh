@@ -5,6 +5,7 @@
 // p0 as base.  Ties in t resolve to the lowest flat triangle id (order independent).
 #pragma once
 #include "common.cuh"
+#include "bvh8.cuh"
 
 struct HitRec { float t, u, v; uint32_t tri; };   // tri = flat triangle id, PGRT_INVALID_ID = miss
 
@@ -37,14 +38,96 @@ __device__ __forceinline__ V3 tri_ng(const float* __restrict__ pos, uint32_t id)
     return e_cross(v2 - v0, v0 - v1);
 }
 
+// ---- wide-node traversal (layout and slot order in bvh8.cuh).  Box tests use FMA and padded bounds: they only cull,
+// the hit record comes from tri_test alone, so the result does not depend on the tree (ties: lowest flat id).
+struct TravCount { uint32_t nodes, tris; };   // instrumented renders only (profile bit 1)
+
+PG_HD uint32_t slab4(uint32_t meta4, uint32_t nx4, uint32_t ny4, uint32_t nz4, uint32_t fx4, uint32_t fy4, uint32_t fz4,
+                     float sx, float sy, float sz, float ax, float ay, float az, float tnear, float far_pad, uint32_t octinv4) {
+    // four children at once: meta bytes -> (bit index, child bits); inner children are re-indexed by the ray octant
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xFFu;
+    const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int sh = 8 * j;
+        const float tx0 = pg_fma((float)((nx4 >> sh) & 0xFFu), sx, ax), tx1 = pg_fma((float)((fx4 >> sh) & 0xFFu), sx, ax);
+        const float ty0 = pg_fma((float)((ny4 >> sh) & 0xFFu), sy, ay), ty1 = pg_fma((float)((fy4 >> sh) & 0xFFu), sy, ay);
+        const float tz0 = pg_fma((float)((nz4 >> sh) & 0xFFu), sz, az), tz1 = pg_fma((float)((fz4 >> sh) & 0xFFu), sz, az);
+        const float tmin = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, tnear));
+        const float tmax = fminf(fminf(tx1, ty1), fminf(tz1, far_pad));
+        if (tmin <= tmax * 1.0000005f) hitmask |= ((child_bits4 >> sh) & 0xFFu) << ((bit_index4 >> sh) & 0xFFu);
+    }
+    return hitmask;
+}
+
+template <bool COUNT>
+PG_HD HitRec trace_closest8(const float4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t n_tris, V3 O, V3 D,
+                            float tnear, float tfar, TravCount& tc) {
+    HitRec best; best.t = tfar; best.u = 0.0f; best.v = 0.0f; best.tri = PGRT_INVALID_ID;
+    if (n_tris == 0) return best;
+    const float ooeps = 8.271806e-25f;   // 2^-80
+    const float idx = 1.0f / (fabsf(D.x) > ooeps ? D.x : copysignf(ooeps, D.x));
+    const float idy = 1.0f / (fabsf(D.y) > ooeps ? D.y : copysignf(ooeps, D.y));
+    const float idz = 1.0f / (fabsf(D.z) > ooeps ? D.z : copysignf(ooeps, D.z));
+    const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;
+    const uint32_t octinv = (negx ? 0u : 4u) | (negy ? 0u : 2u) | (negz ? 0u : 1u);
+    const uint32_t octinv4 = octinv * 0x01010101u;
+    uint2 stack[PGRT_STACK8];
+    int sp = 0;
+    uint2 ng = make_uint2(0u, 0x80000000u);     // node group: x = first child node, y = hit bits (31..24) | imask (7..0)
+    for (;;) {
+        uint2 tg = make_uint2(0u, 0u);          // triangle group: x = first triangle, y = hit bits (23..0)
+        if (ng.y > 0x00FFFFFFu) {
+            const uint32_t hits = ng.y;
+            const int bit = pg_bfind(hits);
+            ng.y &= ~(1u << bit);
+            if (ng.y > 0x00FFFFFFu) stack[sp++] = ng;
+            const uint32_t slot = (uint32_t)(bit - 24) ^ octinv;
+            const uint32_t rel = (uint32_t)pg_popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
+            const float4* __restrict__ nd = nodes + 5 * (size_t)(ng.x + rel);
+            const float4 n0 = pg_ldg4(nd), n1 = pg_ldg4(nd + 1), n2 = pg_ldg4(nd + 2), n3 = pg_ldg4(nd + 3), n4 = pg_ldg4(nd + 4);
+            if (COUNT) tc.nodes++;
+            const uint32_t eb = pg_f2u(n0.w);
+            const float sx = pg_u2f((eb & 0xFFu) << 23) * idx, sy = pg_u2f(((eb >> 8) & 0xFFu) << 23) * idy, sz = pg_u2f(((eb >> 16) & 0xFFu) << 23) * idz;
+            const float ax = (n0.x - O.x) * idx, ay = (n0.y - O.y) * idy, az = (n0.z - O.z) * idz;
+            const float far_pad = best.t * 1.0000005f;
+            // near / far planes by ray sign
+            const uint32_t lox0 = pg_f2u(n2.x), lox1 = pg_f2u(n2.y), loy0 = pg_f2u(n2.z), loy1 = pg_f2u(n2.w);
+            const uint32_t loz0 = pg_f2u(n3.x), loz1 = pg_f2u(n3.y), hix0 = pg_f2u(n3.z), hix1 = pg_f2u(n3.w);
+            const uint32_t hiy0 = pg_f2u(n4.x), hiy1 = pg_f2u(n4.y), hiz0 = pg_f2u(n4.z), hiz1 = pg_f2u(n4.w);
+            uint32_t hitmask = slab4(pg_f2u(n1.z), negx ? hix0 : lox0, negy ? hiy0 : loy0, negz ? hiz0 : loz0, negx ? lox0 : hix0, negy ? loy0 : hiy0,
+                                     negz ? loz0 : hiz0, sx, sy, sz, ax, ay, az, tnear, far_pad, octinv4);
+            hitmask |= slab4(pg_f2u(n1.w), negx ? hix1 : lox1, negy ? hiy1 : loy1, negz ? hiz1 : loz1, negx ? lox1 : hix1, negy ? loy1 : hiy1,
+                             negz ? loz1 : hiz1, sx, sy, sz, ax, ay, az, tnear, far_pad, octinv4);
+            ng.x = pg_f2u(n1.x);
+            ng.y = (hitmask & 0xFF000000u) | (eb >> 24);
+            tg.x = pg_f2u(n1.y);
+            tg.y = hitmask & 0x00FFFFFFu;
+        }
+        while (tg.y) {
+            const int bit = pg_bfind(tg.y);
+            tg.y &= ~(1u << bit);
+            if (COUNT) tc.tris++;
+            tri_test(tris, tg.x + (uint32_t)bit, O, D, tnear, tfar, best);
+        }
+        if (ng.y <= 0x00FFFFFFu) {
+            if (sp == 0) break;
+            ng = stack[--sp];
+        }
+    }
+    return best;
+}
+
+#ifdef __CUDACC__
 #define PGRT_STACK 128
 
 // Binary-node traversal (layout in bvh_build.cuh, k_emit_bvh2).  Slab tests use FMA and a padded far bound:
 // they only cull, the hit record comes from tri_test alone.
-struct TravCount { uint32_t nodes, tris; };   // instrumented renders only (profile bit 1)
-
 template <bool COUNT>
-__device__ __forceinline__ HitRec trace_closest_t(const DevScene& sc, V3 O, V3 D, float tnear, float tfar, TravCount& tc) {
+__device__ __forceinline__ HitRec trace_closest2(const DevScene& sc, V3 O, V3 D, float tnear, float tfar, TravCount& tc) {
     HitRec best; best.t = tfar; best.u = 0.0f; best.v = 0.0f; best.tri = PGRT_INVALID_ID;
     if (sc.n_tris == 0) return best;
     const float ooeps = 8.271806e-25f;   // 2^-80
@@ -93,7 +176,17 @@ __device__ __forceinline__ HitRec trace_closest_t(const DevScene& sc, V3 O, V3 D
     return best;
 }
 
+template <bool COUNT>
+__device__ __forceinline__ HitRec trace_closest_t(const DevScene& sc, V3 O, V3 D, float tnear, float tfar, TravCount& tc) {
+#ifdef PGRT_USE_BVH2
+    return trace_closest2<COUNT>(sc, O, D, tnear, tfar, tc);
+#else
+    return trace_closest8<COUNT>(sc.nodes, sc.tris, sc.n_tris, O, D, tnear, tfar, tc);
+#endif
+}
+
 __device__ __forceinline__ HitRec trace_closest(const DevScene& sc, V3 O, V3 D, float tnear, float tfar) {
     TravCount tc;
     return trace_closest_t<false>(sc, O, D, tnear, tfar, tc);
 }
+#endif  // __CUDACC__

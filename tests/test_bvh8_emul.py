@@ -1,0 +1,121 @@
+"""The wide-node encoder and the traversal of csrc/bvh8.cuh + csrc/traverse.cuh, compiled with g++ and run on the CPU.
+
+The GPU build kernels call the same PG_HD functions once per wide node, so this covers the slot assignment, the 8-bit
+quantisation (conservative decode), the meta / imask encoding and the stack traversal before a GPU is involved.
+Expected: bit-identical hit records to a brute-force loop over the same triangle test, for any binary tree.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from pgi_raytracing_b200 import scenes
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "emul", "bvh8_emul.cpp")
+LIB = os.path.join(HERE, "emul", "libbvh8_emul.so")
+CSRC = os.path.join(os.path.dirname(HERE), "pgi_raytracing_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("bvh8.cuh", "traverse.cuh", "common.cuh")]
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([cxx, "-O2", "-std=c++17", "-mavx2", "-mfma", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
+                               "-I/usr/local/cuda/include", "-o", LIB, SRC])
+    lib = C.CDLL(LIB)
+    lib.emul_build.restype = C.c_void_p; lib.emul_build.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
+    lib.emul_free.argtypes = [C.c_void_p]
+    lib.emul_nodes.restype = C.c_uint32; lib.emul_nodes.argtypes = [C.c_void_p]
+    lib.emul_depth.restype = C.c_uint32; lib.emul_depth.argtypes = [C.c_void_p]
+    lib.emul_sah.restype = C.c_double; lib.emul_sah.argtypes = [C.c_void_p]
+    lib.emul_check.restype = C.c_uint64; lib.emul_check.argtypes = [C.c_void_p]
+    lib.emul_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
+    return lib
+
+
+def scene_pos(sc):
+    return np.ascontiguousarray(np.concatenate([m.pos.reshape(-1, 9) for m in sc.meshes]).astype(np.float32))
+
+
+def random_rays(pos, n, seed):
+    rng = np.random.default_rng(seed)
+    lo, hi = pos.reshape(-1, 3).min(0), pos.reshape(-1, 3).max(0)
+    ext = np.maximum(hi - lo, 1.0)
+    org = rng.uniform(lo - 0.5 * ext, hi + 0.5 * ext, (n, 3))
+    tgt = rng.uniform(lo, hi, (n, 3))
+    pick = rng.integers(0, pos.shape[0], n // 2)                                          # half the rays aim at a triangle
+    w = rng.dirichlet((1.0, 1.0, 1.0), n // 2)[:, :, None]
+    tgt[n // 2:n // 2 + pick.shape[0]] = (pos[pick].reshape(-1, 3, 3) * w).sum(1)
+    d = (tgt - org) * rng.uniform(0.05, 3.0, (n, 1))
+    d[:50, 0] = 0.0; d[50:100, 1] = 0.0; d[100:150, 2] = 0.0; d[150:160, :2] = 0.0      # axis-parallel rays
+    org[160:400] = tgt[160:400]                                                           # origins inside the scene (secondary-like)
+    d[160:400] = rng.normal(size=(240, 3))
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, :3] = org; rays[:, 3] = 0.01; rays[:, 4:7] = d; rays[:, 7] = np.finfo(np.float32).max
+    rays[400:500, 7] = rng.uniform(0.2, 1.5, 100)                                         # bounded tfar (shadow-like)
+    return rays
+
+
+def trace(lib, h, rays, brute):
+    out = np.zeros((rays.shape[0], 4), np.float32); st = np.zeros((rays.shape[0], 2), np.uint32)
+    lib.emul_trace(h, rays.ctypes.data, rays.shape[0], out.ctypes.data, st.ctypes.data, int(brute))
+    return out, st
+
+
+CASES = {
+    "single": lambda: scenes.single_triangle(),
+    "cornell": lambda: scenes.cornell_like(),
+    "soup3000": lambda: scenes.triangle_soup(3000, seed=5, resolution=(32, 32)),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("builder", [0, 1])
+def test_wide_tree_structure_and_hits(emul, name, builder):
+    pos = scene_pos(CASES[name]())
+    h = emul.emul_build(pos.ctypes.data, pos.shape[0], builder)
+    try:
+        assert emul.emul_check(h) == 0                       # every triangle once, decoded boxes conservative, meta consistent
+        assert emul.emul_depth(h) <= 32                      # PGRT_STACK8 = 40 entries
+        rays = random_rays(pos, 1500 if pos.shape[0] > 100 else 600, seed=3)
+        a, st = trace(emul, h, rays, False); b, _ = trace(emul, h, rays, True)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        hit = b.view(np.uint32)[:, 3] != 0xFFFFFFFF
+        assert hit.mean() > 0.1
+        if pos.shape[0] > 1000:                              # the tree prunes: far fewer triangle tests than brute force
+            assert st[:, 1].mean() < 0.05 * pos.shape[0]
+    finally:
+        emul.emul_free(h)
+
+
+def test_duplicates_and_degenerates(emul):
+    """Coincident duplicates (ties -> lowest flat id), zero-area triangles and a flat (axis-aligned) sheet."""
+    rng = np.random.default_rng(1)
+    base = scene_pos(scenes.triangle_soup(400, seed=2, resolution=(8, 8)))
+    sheet = np.zeros((200, 9), np.float32)
+    sheet[:, [0, 3, 6]] = rng.uniform(-50, 50, (200, 3)); sheet[:, [1, 4, 7]] = rng.uniform(-50, 50, (200, 3)); sheet[:, [2, 5, 8]] = 7.0
+    degenerate = np.repeat(rng.uniform(-50, 50, (20, 3)).astype(np.float32), 3, axis=0).reshape(20, 9)
+    pos = np.ascontiguousarray(np.concatenate([base, base[:100], sheet, degenerate]).astype(np.float32))
+    h = emul.emul_build(pos.ctypes.data, pos.shape[0], 0)
+    try:
+        assert emul.emul_check(h) == 0
+        rays = random_rays(pos, 1200, seed=4)
+        a, _ = trace(emul, h, rays, False); b, _ = trace(emul, h, rays, True)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        ids = a.view(np.uint32)[:, 3]
+        assert not np.any((ids >= 400) & (ids < 500))        # the duplicate copy never wins a tie
+    finally:
+        emul.emul_free(h)
+
+
+def test_ploc_tree_is_better_than_median_split(emul):
+    pos = scene_pos(scenes.cornell_like())
+    h0 = emul.emul_build(pos.ctypes.data, pos.shape[0], 0); h1 = emul.emul_build(pos.ctypes.data, pos.shape[0], 1)
+    try:
+        assert emul.emul_sah(h0) < emul.emul_sah(h1)
+    finally:
+        emul.emul_free(h0); emul.emul_free(h1)
