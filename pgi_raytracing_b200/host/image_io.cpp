@@ -1,0 +1,380 @@
+// image_io.cpp -- see image_io.h.  The JPEG decoder follows the published baseline process (ITU T.81) with the
+// arithmetic the IJG library made the de-facto standard, so that the bytes agree with what FreeImage (libjpeg inside)
+// hands the reference: 13-bit fixed-point "slow integer" inverse DCT after Loeffler-Ligtenberg-Moschytz, triangle-filter
+// ("fancy") 2x chroma up-sampling with the alternating 7/8 and 1/2 rounding biases, 16-bit fixed-point YCbCr -> RGB.
+#include "image_io.h"
+#include <cctype>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace {
+
+bool fail(std::string* e, const char* msg) { if (e) *e = msg; return false; }
+
+bool read_all(const char* file_name, std::vector<uint8_t>& out) {
+    FILE* f = fopen(file_name, "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END); const long n = ftell(f); fseek(f, 0, SEEK_SET);
+    out.resize(n > 0 ? (size_t)n : 0);
+    const size_t got = out.empty() ? 0 : fread(out.data(), 1, out.size(), f);
+    fclose(f);
+    out.resize(got);
+    return true;
+}
+
+void alloc_bgr(RawImage& im, int w, int h, int bpp) {
+    im.width = w; im.height = h; im.bpp = bpp; im.pitch = (w * bpp + 3) & ~3;
+    im.bytes.assign((size_t)im.pitch * h, 0);
+}
+
+// ------------------------------------------------------------------------------------------------ JPEG
+const int ZIGZAG[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                        35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+struct Huff {
+    uint8_t bits[17] = {0}; uint8_t vals[256] = {0};
+    int mincode[17], maxcode[18], valptr[17];
+    uint16_t look[512];      // 9-bit lookahead: (length << 8) | symbol, 0 = longer code
+    bool present = false;
+    void build() {
+        int code = 0, k = 0;
+        for (int l = 1; l <= 16; ++l) {
+            valptr[l] = k; mincode[l] = code;
+            code += bits[l]; k += bits[l];
+            maxcode[l] = bits[l] ? code - 1 : -1;
+            code <<= 1;
+        }
+        maxcode[17] = 0x7fffffff;
+        memset(look, 0, sizeof look);
+        code = 0; k = 0;
+        for (int l = 1; l <= 9; ++l) {
+            for (int i = 0; i < bits[l]; ++i, ++k, ++code) {
+                const int first = code << (9 - l);
+                for (int f = 0; f < (1 << (9 - l)); ++f) look[first + f] = (uint16_t)((l << 8) | vals[k]);
+            }
+            code <<= 1;
+        }
+        present = true;
+    }
+};
+
+struct BitReader {
+    const uint8_t* p; const uint8_t* end;
+    uint32_t acc = 0; int n = 0; bool hit_marker = false;
+    void fill() {
+        while (n <= 24) {
+            int b = 0;
+            if (!hit_marker && p < end) {
+                b = *p;
+                if (b == 0xFF) {
+                    if (p + 1 < end && p[1] == 0x00) p += 2;
+                    else { hit_marker = true; b = 0; }
+                } else ++p;
+            }
+            acc |= (uint32_t)b << (24 - n);
+            n += 8;
+        }
+    }
+    int peek(int k) { if (n < k) fill(); return (int)(acc >> (32 - k)); }
+    void skip(int k) { acc <<= k; n -= k; }
+    int get(int k) { if (k == 0) return 0; const int v = peek(k); skip(k); return v; }
+    void reset() { acc = 0; n = 0; hit_marker = false; }
+};
+
+inline int decode_symbol(BitReader& br, const Huff& h) {
+    const int look = br.peek(9);
+    const uint16_t e = h.look[look];
+    if (e) { br.skip(e >> 8); return e & 0xFF; }
+    int code = br.peek(16);
+    for (int l = 10; l <= 16; ++l) {
+        const int c = code >> (16 - l);
+        if (c <= h.maxcode[l] && h.maxcode[l] >= 0) { br.skip(l); return h.vals[h.valptr[l] + c - h.mincode[l]]; }
+    }
+    br.skip(16);
+    return 0;
+}
+
+inline int extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
+
+// slow-but-accurate integer inverse DCT (LL&M), CONST_BITS = 13, PASS1_BITS = 2; output range-limited to 0..255 after +128
+inline int descale(long x, int n) { return (int)((x + (1L << (n - 1))) >> n); }
+void idct_islow(const int* in /*dequantised, natural order*/, uint8_t* out, int stride) {
+    const long F_0_298 = 2446, F_0_390 = 3196, F_0_541 = 4433, F_0_765 = 6270, F_0_899 = 7373, F_1_175 = 9633, F_1_501 = 12299, F_1_847 = 15137,
+               F_1_961 = 16069, F_2_053 = 16819, F_2_562 = 20995, F_3_072 = 25172;
+    long ws[64];
+    for (int c = 0; c < 8; ++c) {
+        const int* p = in + c;
+        if (!p[8] && !p[16] && !p[24] && !p[32] && !p[40] && !p[48] && !p[56]) {
+            const long dc = (long)p[0] << 2;
+            for (int r = 0; r < 8; ++r) ws[r * 8 + c] = dc;
+            continue;
+        }
+        long z2 = p[16], z3 = p[48];
+        long z1 = (z2 + z3) * F_0_541;
+        long tmp2 = z1 + z3 * (-F_1_847), tmp3 = z1 + z2 * F_0_765;
+        z2 = p[0]; z3 = p[32];
+        long tmp0 = (z2 + z3) << 13, tmp1 = (z2 - z3) << 13;
+        const long tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+        tmp0 = p[56]; tmp1 = p[40]; tmp2 = p[24]; tmp3 = p[8];
+        z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2; long z4 = tmp1 + tmp3;
+        const long z5 = (z3 + z4) * F_1_175;
+        tmp0 *= F_0_298; tmp1 *= F_2_053; tmp2 *= F_3_072; tmp3 *= F_1_501;
+        z1 *= -F_0_899; z2 *= -F_2_562; z3 *= -F_1_961; z4 *= -F_0_390;
+        z3 += z5; z4 += z5;
+        tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+        ws[0 * 8 + c] = descale(tmp10 + tmp3, 11); ws[7 * 8 + c] = descale(tmp10 - tmp3, 11);
+        ws[1 * 8 + c] = descale(tmp11 + tmp2, 11); ws[6 * 8 + c] = descale(tmp11 - tmp2, 11);
+        ws[2 * 8 + c] = descale(tmp12 + tmp1, 11); ws[5 * 8 + c] = descale(tmp12 - tmp1, 11);
+        ws[3 * 8 + c] = descale(tmp13 + tmp0, 11); ws[4 * 8 + c] = descale(tmp13 - tmp0, 11);
+    }
+    auto clamp8 = [](long v) { v += 128; return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); };
+    for (int r = 0; r < 8; ++r) {
+        const long* p = ws + r * 8;
+        uint8_t* o = out + (size_t)r * stride;
+        long z2 = p[2], z3 = p[6];
+        long z1 = (z2 + z3) * F_0_541;
+        long tmp2 = z1 + z3 * (-F_1_847), tmp3 = z1 + z2 * F_0_765;
+        long tmp0 = (p[0] + p[4]) << 13, tmp1 = (p[0] - p[4]) << 13;
+        const long tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+        tmp0 = p[7]; tmp1 = p[5]; tmp2 = p[3]; tmp3 = p[1];
+        z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2; long z4 = tmp1 + tmp3;
+        const long z5 = (z3 + z4) * F_1_175;
+        tmp0 *= F_0_298; tmp1 *= F_2_053; tmp2 *= F_3_072; tmp3 *= F_1_501;
+        z1 *= -F_0_899; z2 *= -F_2_562; z3 *= -F_1_961; z4 *= -F_0_390;
+        z3 += z5; z4 += z5;
+        tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+        o[0] = clamp8(descale(tmp10 + tmp3, 18)); o[7] = clamp8(descale(tmp10 - tmp3, 18));
+        o[1] = clamp8(descale(tmp11 + tmp2, 18)); o[6] = clamp8(descale(tmp11 - tmp2, 18));
+        o[2] = clamp8(descale(tmp12 + tmp1, 18)); o[5] = clamp8(descale(tmp12 - tmp1, 18));
+        o[3] = clamp8(descale(tmp13 + tmp0, 18)); o[4] = clamp8(descale(tmp13 - tmp0, 18));
+    }
+}
+
+struct Component { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0; int bw = 0, bh = 0; std::vector<uint8_t> plane; int stride = 0; };
+
+}  // namespace
+
+bool DecodeJpeg(const uint8_t* d, size_t size, RawImage& out, std::string* error) {
+    if (size < 4 || d[0] != 0xFF || d[1] != 0xD8) return fail(error, "not a JPEG stream");
+    uint16_t qt[4][64]; bool have_qt[4] = {false, false, false, false};
+    Huff dc[4], ac[4];
+    Component comp[3]; int ncomp = 0, width = 0, height = 0, restart = 0;
+    size_t i = 2;
+    bool sof = false;
+    while (i + 4 <= size) {
+        if (d[i] != 0xFF) { ++i; continue; }
+        const int m = d[i + 1];
+        if (m == 0xFF) { ++i; continue; }
+        if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7) || m == 0x01) { i += 2; continue; }
+        if (m == 0xD9) break;
+        const size_t len = ((size_t)d[i + 2] << 8) | d[i + 3];
+        if (len < 2 || i + 2 + len > size) return fail(error, "truncated JPEG segment");
+        const uint8_t* s = d + i + 4; const uint8_t* se = d + i + 2 + len;
+        if (m == 0xDB) {
+            while (s < se) {
+                const int pq = *s >> 4, tq = *s & 15; ++s;
+                if (tq > 3) return fail(error, "bad quantisation table id");
+                for (int k = 0; k < 64; ++k) { qt[tq][ZIGZAG[k]] = pq ? (uint16_t)((s[0] << 8) | s[1]) : s[0]; s += pq ? 2 : 1; }
+                have_qt[tq] = true;
+            }
+        } else if (m == 0xC4) {
+            while (s < se) {
+                const int tc = *s >> 4, th = *s & 15; ++s;
+                if (th > 3) return fail(error, "bad Huffman table id");
+                Huff& h = tc ? ac[th] : dc[th];
+                int total = 0;
+                for (int l = 1; l <= 16; ++l) { h.bits[l] = *s++; total += h.bits[l]; }
+                if (total > 256 || s + total > se) return fail(error, "bad Huffman table");
+                memcpy(h.vals, s, total); s += total;
+                h.build();
+            }
+        } else if (m == 0xC0 || m == 0xC1) {
+            if (s[0] != 8) return fail(error, "only 8-bit JPEG is supported");
+            height = (s[1] << 8) | s[2]; width = (s[3] << 8) | s[4]; ncomp = s[5];
+            if ((ncomp != 1 && ncomp != 3) || width <= 0 || height <= 0) return fail(error, "unsupported JPEG component count");
+            for (int c = 0; c < ncomp; ++c) { comp[c].id = s[6 + 3 * c]; comp[c].h = s[7 + 3 * c] >> 4; comp[c].v = s[7 + 3 * c] & 15; comp[c].tq = s[8 + 3 * c]; }
+            sof = true;
+        } else if (m == 0xC2 || (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC)) {
+            return fail(error, "only baseline (SOF0) JPEG is supported");
+        } else if (m == 0xDD) {
+            restart = (s[0] << 8) | s[1];
+        } else if (m == 0xDA) {
+            if (!sof) return fail(error, "SOS before SOF");
+            const int ns = s[0];
+            if (ns != ncomp) return fail(error, "non-interleaved scans are not supported");
+            for (int k = 0; k < ns; ++k) {
+                const int id = s[1 + 2 * k];
+                for (int c = 0; c < ncomp; ++c) if (comp[c].id == id) { comp[c].td = s[2 + 2 * k] >> 4; comp[c].ta = s[2 + 2 * k] & 15; }
+            }
+            // ---- entropy-coded data
+            int hmax = 1, vmax = 1;
+            for (int c = 0; c < ncomp; ++c) { hmax = comp[c].h > hmax ? comp[c].h : hmax; vmax = comp[c].v > vmax ? comp[c].v : vmax; }
+            const int mcux = (width + 8 * hmax - 1) / (8 * hmax), mcuy = (height + 8 * vmax - 1) / (8 * vmax);
+            for (int c = 0; c < ncomp; ++c) {
+                if (!have_qt[comp[c].tq] || !dc[comp[c].td].present || !ac[comp[c].ta].present) return fail(error, "missing JPEG table");
+                comp[c].bw = mcux * comp[c].h; comp[c].bh = mcuy * comp[c].v;
+                comp[c].stride = comp[c].bw * 8;
+                comp[c].plane.assign((size_t)comp[c].stride * comp[c].bh * 8, 0);
+                comp[c].pred = 0;
+            }
+            BitReader br; br.p = se; br.end = d + size;
+            int coef[64], to_restart = restart;
+            for (int my = 0; my < mcuy; ++my)
+                for (int mx = 0; mx < mcux; ++mx) {
+                    if (restart && to_restart == 0) {
+                        // byte-align, expect RSTn
+                        br.reset();
+                        while (br.p + 1 < br.end && !(br.p[0] == 0xFF && br.p[1] >= 0xD0 && br.p[1] <= 0xD7)) ++br.p;
+                        if (br.p + 1 < br.end) br.p += 2;
+                        for (int c = 0; c < ncomp; ++c) comp[c].pred = 0;
+                        to_restart = restart;
+                    }
+                    for (int c = 0; c < ncomp; ++c) {
+                        Component& C = comp[c];
+                        for (int by = 0; by < C.v; ++by)
+                            for (int bx = 0; bx < C.h; ++bx) {
+                                memset(coef, 0, sizeof coef);
+                                const int t = decode_symbol(br, dc[C.td]);
+                                const int diff = t ? extend(br.get(t), t) : 0;
+                                C.pred += diff;
+                                coef[0] = C.pred * qt[C.tq][0];
+                                for (int k = 1; k < 64;) {
+                                    const int rs = decode_symbol(br, ac[C.ta]);
+                                    const int r = rs >> 4, sz = rs & 15;
+                                    if (sz == 0) { if (r == 15) { k += 16; continue; } break; }
+                                    k += r;
+                                    if (k > 63) break;
+                                    const int nat = ZIGZAG[k];
+                                    coef[nat] = extend(br.get(sz), sz) * qt[C.tq][nat];
+                                    ++k;
+                                }
+                                const int X = (mx * C.h + bx) * 8, Y = (my * C.v + by) * 8;
+                                idct_islow(coef, &C.plane[(size_t)Y * C.stride + X], C.stride);
+                            }
+                    }
+                    if (restart) --to_restart;
+                }
+            // ---- up-sampling + colour conversion
+            alloc_bgr(out, width, height, 3);
+            if (ncomp == 1) {
+                for (int y = 0; y < height; ++y)
+                    for (int x = 0; x < width; ++x) {
+                        const uint8_t v = comp[0].plane[(size_t)y * comp[0].stride + x];
+                        uint8_t* o = &out.bytes[(size_t)y * out.pitch + 3 * x]; o[0] = o[1] = o[2] = v;
+                    }
+                return true;
+            }
+            const bool h2v2 = comp[0].h == 2 && comp[0].v == 2 && comp[1].h == 1 && comp[1].v == 1 && comp[2].h == 1 && comp[2].v == 1;
+            const bool h1v1 = comp[0].h == 1 && comp[0].v == 1 && comp[1].h == 1 && comp[1].v == 1 && comp[2].h == 1 && comp[2].v == 1;
+            if (!h2v2 && !h1v1) return fail(error, "unsupported chroma sub-sampling (only 4:4:4 and 4:2:0)");
+            std::vector<uint8_t> up[2];
+            const int cw = (width + 1) / 2, chh = (height + 1) / 2;     // down-sampled size actually carrying image data
+            if (h2v2) {
+                for (int c = 0; c < 2; ++c) {
+                    const Component& C = comp[1 + c];
+                    up[c].assign((size_t)width * height + 2 * width + 4, 0);
+                    std::vector<int> colsum(cw);
+                    for (int y = 0; y < height; ++y) {
+                        const int r = y >> 1;
+                        int rn = (y & 1) ? r + 1 : r - 1;                 // nearer neighbour row; edges replicate
+                        rn = rn < 0 ? 0 : (rn >= chh ? chh - 1 : rn);
+                        const uint8_t* a = &C.plane[(size_t)r * C.stride]; const uint8_t* b = &C.plane[(size_t)rn * C.stride];
+                        for (int x = 0; x < cw; ++x) colsum[x] = 3 * a[x] + b[x];
+                        uint8_t* o = &up[c][(size_t)y * width];
+                        for (int x = 0; x < cw; ++x) {
+                            const int cur = colsum[x], last = x > 0 ? colsum[x - 1] : 0, next = x + 1 < cw ? colsum[x + 1] : 0;
+                            const int e0 = x == 0 ? (cur * 4 + 8) >> 4 : (cur * 3 + last + 8) >> 4;
+                            const int e1 = x + 1 == cw ? (cur * 4 + 7) >> 4 : (cur * 3 + next + 7) >> 4;
+                            if (2 * x < width) o[2 * x] = (uint8_t)e0;
+                            if (2 * x + 1 < width) o[2 * x + 1] = (uint8_t)e1;
+                        }
+                    }
+                }
+            }
+            for (int y = 0; y < height; ++y) {
+                const uint8_t* Y = &comp[0].plane[(size_t)y * comp[0].stride];
+                const uint8_t* Cb = h2v2 ? &up[0][(size_t)y * width] : &comp[1].plane[(size_t)y * comp[1].stride];
+                const uint8_t* Cr = h2v2 ? &up[1][(size_t)y * width] : &comp[2].plane[(size_t)y * comp[2].stride];
+                uint8_t* o = &out.bytes[(size_t)y * out.pitch];
+                for (int x = 0; x < width; ++x) {
+                    const int yy = Y[x], cb = Cb[x] - 128, cr = Cr[x] - 128;
+                    int r = yy + (int)((91881L * cr + 32768) >> 16);
+                    int g = yy + (int)((-22554L * cb - 46802L * cr + 32768) >> 16);
+                    int b = yy + (int)((116130L * cb + 32768) >> 16);
+                    r = r < 0 ? 0 : (r > 255 ? 255 : r); g = g < 0 ? 0 : (g > 255 ? 255 : g); b = b < 0 ? 0 : (b > 255 ? 255 : b);
+                    o[3 * x] = (uint8_t)b; o[3 * x + 1] = (uint8_t)g; o[3 * x + 2] = (uint8_t)r;
+                }
+            }
+            return true;
+        }
+        i += 2 + len;
+    }
+    return fail(error, "no scan found in JPEG stream");
+}
+
+bool LoadImageFile(const char* file_name, RawImage& out, std::string* error) {
+    std::vector<uint8_t> d;
+    if (!read_all(file_name, d)) return fail(error, "cannot open image file");
+    if (d.size() >= 2 && d[0] == 0xFF && d[1] == 0xD8) return DecodeJpeg(d.data(), d.size(), out, error);
+    if (d.size() >= 2 && d[0] == 'P' && d[1] == '6') {          // binary PPM, maxval 255
+        size_t p = 2; int vals[3], got = 0;
+        while (got < 3 && p < d.size()) {
+            while (p < d.size() && (isspace(d[p]) || d[p] == '#')) { if (d[p] == '#') while (p < d.size() && d[p] != '\n') ++p; else ++p; }
+            int v = 0; bool any = false;
+            while (p < d.size() && d[p] >= '0' && d[p] <= '9') { v = v * 10 + (d[p] - '0'); ++p; any = true; }
+            if (!any) break;
+            vals[got++] = v;
+        }
+        if (got != 3 || vals[2] != 255 || p >= d.size()) return fail(error, "unsupported PPM");
+        ++p;
+        if (d.size() - p < (size_t)vals[0] * vals[1] * 3) return fail(error, "truncated PPM");
+        alloc_bgr(out, vals[0], vals[1], 3);
+        for (int y = 0; y < vals[1]; ++y)
+            for (int x = 0; x < vals[0]; ++x) {
+                const uint8_t* s = &d[p + ((size_t)y * vals[0] + x) * 3]; uint8_t* o = &out.bytes[(size_t)y * out.pitch + 3 * x];
+                o[0] = s[2]; o[1] = s[1]; o[2] = s[0];
+            }
+        return true;
+    }
+    if (d.size() >= 54 && d[0] == 'B' && d[1] == 'M') {          // uncompressed 24 / 32-bit BMP
+        auto u32 = [&](size_t o) { return (uint32_t)d[o] | ((uint32_t)d[o + 1] << 8) | ((uint32_t)d[o + 2] << 16) | ((uint32_t)d[o + 3] << 24); };
+        const uint32_t off = u32(10); const int w = (int)u32(18); int h = (int)u32(22); const int bits = d[28] | (d[29] << 8); const uint32_t compr = u32(30);
+        const bool top_down = h < 0; if (top_down) h = -h;
+        if ((bits != 24 && bits != 32) || compr != 0 || w <= 0 || h <= 0) return fail(error, "unsupported BMP");
+        const int bpp = bits / 8, src_pitch = (w * bpp + 3) & ~3;
+        if (d.size() < off + (size_t)src_pitch * h) return fail(error, "truncated BMP");
+        alloc_bgr(out, w, h, bpp);
+        for (int y = 0; y < h; ++y) memcpy(&out.bytes[(size_t)y * out.pitch], &d[off + (size_t)(top_down ? y : h - 1 - y) * src_pitch], (size_t)w * bpp);
+        return true;
+    }
+    return fail(error, "unknown image format (JPEG, PPM P6 and BMP are supported)");
+}
+
+static inline uint8_t to8(float c) { if (!(c == c)) return 0; c = c < 0.f ? 0.f : (c > 1.f ? 1.f : c); return (uint8_t)std::floor(c * 255.0f + 0.5f); }
+
+bool WritePPM(const char* file_name, const float* rgba, int width, int height) {
+    FILE* f = fopen(file_name, "wb");
+    if (!f) return false;
+    fprintf(f, "P6\n%d %d\n255\n", width, height);
+    std::vector<uint8_t> row((size_t)width * 3);
+    for (int y = 0; y < height; ++y) {
+        for (int x = 0; x < width; ++x) for (int c = 0; c < 3; ++c) row[3 * x + c] = to8(rgba[((size_t)y * width + x) * 4 + c]);
+        fwrite(row.data(), 1, row.size(), f);
+    }
+    fclose(f);
+    return true;
+}
+
+bool WritePFM(const char* file_name, const float* rgba, int width, int height) {
+    FILE* f = fopen(file_name, "wb");
+    if (!f) return false;
+    fprintf(f, "PF\n%d %d\n-1.0\n", width, height);
+    std::vector<float> row((size_t)width * 3);
+    for (int y = height - 1; y >= 0; --y) {
+        for (int x = 0; x < width; ++x) for (int c = 0; c < 3; ++c) row[3 * x + c] = rgba[((size_t)y * width + x) * 4 + c];
+        fwrite(row.data(), sizeof(float), row.size(), f);
+    }
+    fclose(f);
+    return true;
+}

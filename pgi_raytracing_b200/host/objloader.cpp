@@ -1,0 +1,254 @@
+// objloader.cpp -- see objloader.h.  Behaviour kept from the reference (pg1/objloader.cpp), line by line where it
+// decides what the scene IS:
+//   * any line whose first character is 'm' names a material library (":273-279"); libraries load before geometry;
+//   * only "v ", "vn", "vt" records; normals are normalised on load (:323); "vt" keeps u, v;
+//   * faces need all of v/vt/vn, 1-based, digits only (:458-466); three corners = triangle, four = quad split
+//     (0,1,2) + (0,2,3) (:455-471); the corner count is the number of spaces in the trimmed line (:431-439);
+//   * a surface is what lies between two 'g' lines, flushed at the next 'g' (or the end) with the LAST "usemtl" seen,
+//     matched by exact name, first match (:382-400, :479-495); a 'g' with no faces since the last flush only renames;
+//   * MTL keys match by PREFIX on the trimmed line, every key tested independently (:131-186); sscanf-style partial
+//     parses keep the defaults of Material() for the fields not read ("Ks 1.0. 1.0 1.0" -> (1.0, 0.8, 0.8));
+//   * a material is pushed when the next "newmtl" arrives unless one of that name exists; the last one always (:112-120,
+//     :193-198).
+// Defined where the reference is undefined: faces with another corner count are skipped; indices out of range are
+// skipped; faces before the first 'g' go to a surface named "" ; a property line before any "newmtl" is ignored.
+#include "objloader.h"
+#include <cctype>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace {
+
+bool read_file(const char* file_name, std::string& out) {
+    FILE* f = fopen(file_name, "rb");
+    if (!f) { printf("File %s not found.\n", file_name); return false; }
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    out.resize(n > 0 ? (size_t)n : 0);
+    const size_t got = out.empty() ? 0 : fread(&out[0], 1, out.size(), f);
+    fclose(f);
+    out.resize(got);
+    return true;
+}
+
+// one line at a time, "\n"-separated, empty lines skipped (strtok semantics), '\r' left for the trims
+struct Lines {
+    const char* p; const char* end;
+    explicit Lines(const std::string& s) : p(s.data()), end(s.data() + s.size()) {}
+    bool next(const char*& b, const char*& e) {
+        while (p < end && *p == '\n') ++p;
+        if (p >= end) return false;
+        b = p;
+        while (p < end && *p != '\n') ++p;
+        e = p;
+        return true;
+    }
+};
+
+inline void trim(const char*& b, const char*& e) {
+    while (b < e && isspace((unsigned char)*b)) ++b;
+    while (e > b && isspace((unsigned char)e[-1])) --e;
+}
+
+// "%*s %s": skip the first token, return the second
+std::string second_token(const char* b, const char* e) {
+    while (b < e && isspace((unsigned char)*b)) ++b;
+    while (b < e && !isspace((unsigned char)*b)) ++b;
+    while (b < e && isspace((unsigned char)*b)) ++b;
+    const char* t = b;
+    while (b < e && !isspace((unsigned char)*b)) ++b;
+    return std::string(t, b);
+}
+
+// "%*s %f %f %f" with scanf's partial-assignment behaviour: stops at the first field that does not parse
+int scan_floats(const char* b, const char* e, float* dst[], int n) {
+    std::string tmp(b, e);
+    const char* s = tmp.c_str();
+    while (*s && isspace((unsigned char)*s)) ++s;
+    while (*s && !isspace((unsigned char)*s)) ++s;
+    int got = 0;
+    for (; got < n; ++got) {
+        char* after = nullptr;
+        const float v = strtof(s, &after);
+        if (after == s) break;
+        *dst[got] = v;
+        s = after;
+    }
+    return got;
+}
+
+inline bool starts_with(const char* b, const char* e, const char* key) {
+    const size_t n = strlen(key);
+    return (size_t)(e - b) >= n && memcmp(b, key, n) == 0;
+}
+
+bool material_exists(const std::vector<Material*>& materials, const std::string& name) {
+    for (const Material* m : materials) if (m->get_name() == name) return true;
+    return false;
+}
+
+Texture* texture_proxy(const std::string& full_name, TextureCache& cache) {   // pg1/objloader.cpp:28-44
+    auto it = cache.find(full_name);
+    if (it != cache.end()) return it->second;
+    Texture* t = new Texture(full_name.c_str());
+    cache[full_name] = t;
+    return t;
+}
+
+TextureCache g_default_cache;
+
+// "%[0-9]/%[0-9]/%[0-9]" then atoi - 1
+bool parse_corner(const char* b, const char* e, int idx[3]) {
+    for (int k = 0; k < 3; ++k) {
+        const char* d = b;
+        long v = 0;
+        while (d < e && *d >= '0' && *d <= '9') { v = v * 10 + (*d - '0'); if (v > 0x7fffffff) return false; ++d; }
+        if (d == b) return false;
+        idx[k] = (int)v - 1;
+        b = d;
+        if (k < 2) { if (b >= e || *b != '/') return false; ++b; }
+    }
+    return true;
+}
+
+}  // namespace
+
+void ReleaseTextureCache(TextureCache& cache) {
+    for (auto& kv : cache) delete kv.second;
+    cache.clear();
+}
+
+int LoadMTL(const char* file_name, const char* path, std::vector<Material*>& materials, TextureCache* cache) {
+    std::string text;
+    if (!read_file(file_name, text)) return -1;
+    TextureCache& tc = cache ? *cache : g_default_cache;
+    Material* material = nullptr;
+    std::string material_name;
+    Lines lines(text);
+    const char *b, *e;
+    while (lines.next(b, e)) {
+        if (*b == '#') continue;
+        if (starts_with(b, e, "newmtl")) {
+            if (material) {
+                material->set_name(material_name.c_str());
+                if (!material_exists(materials, material_name)) materials.push_back(material); else delete material;
+            }
+            material_name = second_token(b, e);
+            material = new Material();
+            continue;
+        }
+        trim(b, e);
+        if (!material || b >= e) continue;
+        float* v3a[3] = {&material->ambient.x, &material->ambient.y, &material->ambient.z};
+        float* v3t[3] = {&material->refractivity.x, &material->refractivity.y, &material->refractivity.z};
+        float* v3d[3] = {&material->diffuse.x, &material->diffuse.y, &material->diffuse.z};
+        float* v3s[3] = {&material->specular.x, &material->specular.y, &material->specular.z};
+        float* v3e[3] = {&material->emission.x, &material->emission.y, &material->emission.z};
+        if (starts_with(b, e, "Ka")) scan_floats(b, e, v3a, 3);
+        if (starts_with(b, e, "shader")) { float t = 0; float* p[1] = {&t}; if (scan_floats(b, e, p, 1) == 1) material->type = (int)t; }
+        if (starts_with(b, e, "Ni")) { float* p[1] = {&material->ior}; scan_floats(b, e, p, 1); }
+        if (starts_with(b, e, "Tf")) scan_floats(b, e, v3t, 3);
+        if (starts_with(b, e, "Kd")) scan_floats(b, e, v3d, 3);
+        if (starts_with(b, e, "Ks")) scan_floats(b, e, v3s, 3);
+        if (starts_with(b, e, "Ke")) scan_floats(b, e, v3e, 3);
+        if (starts_with(b, e, "Ns")) { float* p[1] = {&material->shininess}; scan_floats(b, e, p, 1); }
+        if (starts_with(b, e, "map_Kd")) material->set_texture(Material::kDiffuseMapSlot, texture_proxy(std::string(path) + second_token(b, e), tc));
+        if (starts_with(b, e, "map_Ks")) material->set_texture(Material::kSpecularMapSlot, texture_proxy(std::string(path) + second_token(b, e), tc));
+        if (starts_with(b, e, "map_D")) material->set_texture(Material::kOpacityMapSlot, texture_proxy(std::string(path) + second_token(b, e), tc));
+        if (starts_with(b, e, "map_bump")) {   // "%*s %*s %f %s": map_bump -bm <f> <file>
+            std::string rest(b, e);
+            char name[256] = {0}; float bm = 0;
+            if (sscanf(rest.c_str(), "%*s %*s %f %255s", &bm, name) == 2)
+                material->set_texture(Material::kNormalMapSlot, texture_proxy(std::string(path) + name, tc));
+        }
+    }
+    if (material) { material->set_name(material_name.c_str()); materials.push_back(material); }
+    return 0;
+}
+
+int LoadOBJ(const char* file_name, std::vector<Surface*>& surfaces, std::vector<Material*>& materials, const bool flip_yz,
+            const Vector3 /*default_color: vertex colours are never read by the path*/, TextureCache* cache) {
+    std::string text;
+    if (!read_file(file_name, text)) return -1;
+    std::string path;
+    if (const char* slash = strrchr(file_name, '/')) path.assign(file_name, slash - file_name + 1);
+
+    // material libraries first (the reference's first pass): they do not depend on anything else in the file
+    {
+        Lines lines(text);
+        const char *b, *e;
+        while (lines.next(b, e))
+            if (*b == 'm') LoadMTL((path + second_token(b, e)).c_str(), path.c_str(), materials, cache);
+    }
+    // one pass for coordinates and faces: OBJ indices are absolute, so a face may only refer to records that the
+    // reference's separate second pass would also have collected -- all of them.  Collect first, then build.
+    std::vector<Vector3> vertices, normals; std::vector<Coord2f> tex_coords;
+    {
+        Lines lines(text);
+        const char *b, *e;
+        while (lines.next(b, e)) {
+            if (*b != 'v' || e - b < 2) continue;
+            Vector3 v; float* p[3] = {&v.x, &v.y, &v.z};
+            if (b[1] == ' ' || b[1] == 'n') {
+                if (flip_yz) { p[1] = &v.z; p[2] = &v.y; }
+                scan_floats(b, e, p, 3);
+                if (flip_yz) v.y *= -1;
+                if (b[1] == 'n') { v.Normalize(); normals.push_back(v); } else vertices.push_back(v);
+            } else if (b[1] == 't') {
+                Coord2f t{0.0f, 0.0f}; float w = 0; float* q[3] = {&t.u, &t.v, &w};
+                scan_floats(b, e, q, 3);
+                tex_coords.push_back(t);
+            }
+        }
+    }
+    printf("%zu vertices, %zu normals and %zu texture coords.\n", vertices.size(), normals.size(), tex_coords.size());
+
+    int no_surfaces = 0;
+    std::string group_name, material_name;
+    Surface* current = new Surface();
+    auto flush = [&]() {
+        if (current->no_triangles() == 0) return;
+        Surface* s = new Surface(group_name, 0);
+        s->positions.swap(current->positions); s->normals.swap(current->normals); s->tex_coords.swap(current->tex_coords);
+        for (Material* m : materials) if (m->get_name() == material_name) { s->set_material(m); break; }
+        surfaces.push_back(s);
+        ++no_surfaces;
+    };
+    Lines lines(text);
+    const char *b, *e;
+    while (lines.next(b, e)) {
+        switch (*b) {
+        case 'g': flush(); group_name = second_token(b, e); break;
+        case 'u': material_name = second_token(b, e); break;
+        case 'f': {
+            trim(b, e);
+            int spaces = 0;
+            for (const char* c = b; c < e; ++c) spaces += (*c == ' ');
+            if (spaces != 3 && spaces != 4) break;
+            int idx[4][3]; bool ok = true;
+            const char* c = b;
+            while (c < e && !isspace((unsigned char)*c)) ++c;      // the "f" token
+            for (int k = 0; k < spaces && ok; ++k) {
+                while (c < e && isspace((unsigned char)*c)) ++c;
+                const char* t = c;
+                while (c < e && !isspace((unsigned char)*c)) ++c;
+                ok = parse_corner(t, c, idx[k]) && idx[k][0] >= 0 && (size_t)idx[k][0] < vertices.size() && idx[k][1] >= 0 &&
+                     (size_t)idx[k][1] < tex_coords.size() && idx[k][2] >= 0 && (size_t)idx[k][2] < normals.size();
+            }
+            if (!ok) break;
+            const int order[6] = {0, 1, 2, 0, 2, 3};
+            for (int k = 0; k < (spaces == 4 ? 6 : 3); ++k) {
+                const int* i = idx[order[k]];
+                current->push_corner(vertices[i[0]], normals[i[2]], tex_coords[i[1]]);
+            }
+        } break;
+        default: break;
+        }
+    }
+    flush();
+    delete current;
+    printf("%d group(s), %zu material(s)\n", no_surfaces, materials.size());
+    return no_surfaces;
+}

@@ -1,0 +1,17 @@
+// objloader.h -- LoadOBJ / LoadMTL (pg1/objloader.h:19-20, pg1/objloader.cpp:53-507), same signatures and the same
+// observable behaviour, rebuilt as single-pass tokenisers that fill SoA surfaces (surface.h) instead of the
+// reference's three strtok passes over two copies of the file.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+#include "surface.h"
+
+// Textures created while loading are owned by this cache (the reference leaks them through Material::~Material's
+// mismatched delete[], pg1/material.cpp:59); free with ReleaseTextureCache after the scene is uploaded or dropped.
+typedef std::map<std::string, Texture*> TextureCache;
+void ReleaseTextureCache(TextureCache& cache);
+
+int LoadMTL(const char* file_name, const char* path, std::vector<Material*>& materials, TextureCache* cache = nullptr);
+int LoadOBJ(const char* file_name, std::vector<Surface*>& surfaces, std::vector<Material*>& materials, const bool flip_yz = false,
+            const Vector3 default_color = Vector3(0.5f, 0.5f, 0.5f), TextureCache* cache = nullptr);

@@ -1,0 +1,279 @@
+"""The C++ host surface (pgi_raytracing_b200/host/): LoadOBJ / LoadMTL, Texture + image decode, PinHoleCamera, and --
+on the GPU -- Raytracer over the C ABI.  Driven through the flat C test API of host/pg1_capi.cpp.
+
+Reference behaviour cited: pg1/objloader.cpp:53-507 (loader), pg1/texture.cpp:5-54 (decode to top-down BGR, 4-byte pitch),
+pg1/PinHoleCamera.cpp:5-105, pg1/raytracer.cpp:48-128 (LoadScene).
+"""
+import ctypes as C
+import io
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+from pgi_raytracing_b200 import scenes
+
+PKG = os.path.join(ROOT, "pgi_raytracing_b200")
+HOST_LIB = os.path.join(PKG, "libpg1_host.so")
+
+
+@pytest.fixture(scope="module")
+def host():
+    subprocess.check_call(["make", "-C", os.path.join(PKG, "csrc"), "-s"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", os.path.join(PKG, "host"), "-s"], stdout=subprocess.DEVNULL)
+    lib = C.CDLL(HOST_LIB)
+    VP = C.c_void_p
+    for name, res, args in [
+        ("pg1_last_error", C.c_char_p, []), ("pg1_load_obj", VP, [C.c_char_p, C.c_int]), ("pg1_load_mtl", VP, [C.c_char_p, C.c_char_p]),
+        ("pg1_free_scene", None, [VP]), ("pg1_scene_rc", C.c_int, [VP]), ("pg1_num_surfaces", C.c_int, [VP]), ("pg1_num_materials", C.c_int, [VP]),
+        ("pg1_surface_triangles", C.c_int, [VP, C.c_int]), ("pg1_surface_name", C.c_char_p, [VP, C.c_int]), ("pg1_surface_material", C.c_int, [VP, C.c_int]),
+        ("pg1_surface_data", None, [VP, C.c_int, VP, VP, VP]), ("pg1_material", C.c_char_p, [VP, C.c_int, VP]),
+        ("pg1_load_image", VP, [C.c_char_p]), ("pg1_image_info", None, [VP, VP]), ("pg1_image_bytes", None, [VP, VP]), ("pg1_free_image", None, [VP]),
+        ("pg1_write_ppm", C.c_int, [C.c_char_p, VP, C.c_int, C.c_int]),
+        ("pg1_camera_ray", None, [C.c_int, C.c_int, C.c_float, VP, VP, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, VP]),
+        ("pg1_raytracer_create", VP, [C.c_int, C.c_int, C.c_float, VP, VP, C.c_char_p]), ("pg1_raytracer_destroy", None, [VP]),
+        ("pg1_raytracer_load_scene", C.c_int, [VP, C.c_char_p, C.c_char_p]),
+        ("pg1_raytracer_set", None, [VP, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_uint]),
+        ("pg1_raytracer_render", C.c_int, [VP, VP, VP]), ("pg1_raytracer_get_pixel", C.c_int, [VP, C.c_int, C.c_int, VP]),
+        ("pg1_raytracer_counts", C.c_int, [VP, VP]),
+    ]:
+        fn = getattr(lib, name); fn.restype = res; fn.argtypes = args
+    return lib
+
+
+def load_image(host, path):
+    h = host.pg1_load_image(path.encode())
+    assert h, host.pg1_last_error()
+    info = (C.c_int * 4)(); host.pg1_image_info(h, info)
+    w, hh, pitch, bpp = list(info)
+    buf = np.zeros((hh, pitch), np.uint8); host.pg1_image_bytes(h, buf.ctypes.data)
+    host.pg1_free_image(h)
+    return buf, w, hh, pitch, bpp
+
+
+def scene_arrays(host, h, i):
+    n = host.pg1_surface_triangles(h, i)
+    pos = np.zeros((n, 9), np.float32); nrm = np.zeros((n, 9), np.float32); uv = np.zeros((n, 6), np.float32)
+    host.pg1_surface_data(h, i, pos.ctypes.data, nrm.ctypes.data, uv.ctypes.data)
+    return pos, nrm, uv
+
+
+def material(host, h, i):
+    out = np.zeros(16, np.float32)
+    name = host.pg1_material(h, i, out.ctypes.data).decode()
+    return name, out
+
+
+# ------------------------------------------------------------------------------------------------ image decode
+def _test_picture(w, h, seed):
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:w]
+    img = np.stack([127 + 120 * np.sin(x / 17.0 + seed), 127 + 120 * np.cos(y / 11.0), (x * 3 + y * 5) % 256], -1)
+    img += rng.normal(0, 12, img.shape)
+    img[h // 3:h // 3 + 9, :, :] = 255; img[:, w // 2:w // 2 + 3, :] = 0          # hard edges
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("size,subsampling,quality,restart", [((64, 48), 2, 90, 0), ((67, 45), 2, 75, 0), ((640, 308), 2, 85, 0),
+                                                              ((33, 17), 0, 95, 0), ((200, 100), 0, 80, 5), ((129, 65), 2, 60, 3)])
+def test_jpeg_decoder_matches_libjpeg(host, tmp_path, size, subsampling, quality, restart):
+    """Baseline JPEG -> top-down BGR rows with a 4-byte pitch, byte for byte what libjpeg (inside FreeImage / Pillow)
+    decodes: islow IDCT, fancy 4:2:0 up-sampling, fixed-point YCbCr."""
+    from PIL import Image
+    w, h = size
+    p = str(tmp_path / "t.jpg")
+    kw = dict(restart_marker_blocks=restart) if restart else {}
+    Image.fromarray(_test_picture(w, h, w + h)).save(p, "JPEG", quality=quality, subsampling=subsampling, **kw)
+    ref = np.asarray(Image.open(p).convert("RGB"))
+    buf, ww, hh, pitch, bpp = load_image(host, p)
+    assert (ww, hh, bpp, pitch) == (w, h, 3, (3 * w + 3) // 4 * 4)
+    got = buf[:, :3 * w].reshape(h, w, 3)[..., ::-1]
+    assert np.array_equal(got, ref)
+
+
+def test_reference_textures_decode_like_libjpeg(host):
+    """The reference's own JPEGs, when the mount is present (this container only)."""
+    from PIL import Image
+    d = "/root/reference/data"
+    if not os.path.isdir(d):
+        pytest.skip("reference data not mounted")
+    for name in ("4150p04.jpg", "3069bp13.jpg", "spherical_map_windows.jpg", "PalmTrees/posx.jpg"):
+        ref = np.asarray(Image.open(os.path.join(d, name)).convert("RGB"))
+        buf, w, h, pitch, bpp = load_image(host, os.path.join(d, name))
+        got = buf[:, :3 * w].reshape(h, w, 3)[..., ::-1]
+        assert np.array_equal(got, ref), name
+
+
+def test_ppm_and_bmp(host, tmp_path):
+    from PIL import Image
+    img = _test_picture(37, 21, 1)
+    for ext, fmt in (("ppm", "PPM"), ("bmp", "BMP")):
+        p = str(tmp_path / f"t.{ext}"); Image.fromarray(img).save(p, fmt)
+        buf, w, h, pitch, bpp = load_image(host, p)
+        assert np.array_equal(buf[:, :3 * w].reshape(h, w, 3)[..., ::-1], img)
+        assert np.array_equal(buf, scenes.Image.from_rgb(img).data)          # same bytes the Python harness hands to the ABI
+    assert host.pg1_load_image(str(tmp_path / "missing.jpg").encode()) is None
+
+
+# ------------------------------------------------------------------------------------------------ loader
+def test_load_obj_round_trip(host, tmp_path):
+    """write_obj -> LoadOBJ: surfaces in group order, un-indexed corners bit-exact, materials by last usemtl."""
+    sc = scenes.cornell_like()
+    path = str(tmp_path / "scene.obj")
+    scenes.write_obj(sc, path)
+    h = host.pg1_load_obj(path.encode(), 0)
+    try:
+        assert host.pg1_scene_rc(h) == len(sc.meshes) == host.pg1_num_surfaces(h)
+        assert host.pg1_num_materials(h) == len(sc.materials)
+        for i, m in enumerate(sc.meshes):
+            pos, nrm, uv = scene_arrays(host, h, i)
+            assert host.pg1_surface_name(h, i).decode() == m.name
+            assert host.pg1_surface_material(h, i) == m.material
+            assert np.array_equal(pos, m.pos.reshape(-1, 9)) and np.array_equal(uv, m.uv.reshape(-1, 6))
+            n = m.nrm.reshape(-1, 3).astype(np.float32)                       # normals are re-normalised on load (objloader.cpp:323)
+            sq = (n[:, 0] * n[:, 0] + n[:, 1] * n[:, 1] + n[:, 2] * n[:, 2]).astype(np.float32)
+            rn = (np.float32(1) / np.sqrt(sq, dtype=np.float32)).astype(np.float32)
+            assert np.array_equal(nrm.reshape(-1, 3), (n * rn[:, None]).astype(np.float32))
+    finally:
+        host.pg1_free_scene(h)
+
+
+def test_mtl_parse_matches_the_reference_fixture(host, tmp_path):
+    """tests/golden/avenger_mtl_parse.json was made with glibc sscanf on the reference's data/6887_allied_avenger.mtl
+    (prefix key matching, partial parses keep Material() defaults: Ks 1.0. 1.0 1.0 -> (1.0, 0.8, 0.8))."""
+    p = str(tmp_path / "a.mtl")
+    open(p, "w").write(scenes.AVENGER_MTL_TEXT)
+    h = host.pg1_load_mtl(p.encode(), (str(tmp_path) + "/").encode())
+    try:
+        with open(os.path.join(GOLDEN, "avenger_mtl_parse.json")) as f:
+            gold = json.load(f)
+        assert host.pg1_num_materials(h) == len(gold) == 5
+        for i, g in enumerate(gold):
+            name, v = material(host, h, i)
+            assert name == g["name"]
+            want = np.array(g["ambient"] + g["diffuse"] + g["specular"] + g["emission"] + [g["shininess"], g["ior"], g["type"]], np.float32)
+            assert np.array_equal(v[:15], want), name
+    finally:
+        host.pg1_free_scene(h)
+
+
+def test_loader_quirks(host, tmp_path):
+    obj = tmp_path / "q.obj"
+    (tmp_path / "q.mtl").write_text("newmtl a\nKd 1 0 0\nshader 4\nnewmtl b\n  Kd 0 1 0\nnewmtl a\nKd 0 0 1\nKdx 9 9 9\n# Kd 5 5 5\nnewmtl c\nNs 7\n")
+    obj.write_text("\n".join([
+        "mtllib q.mtl", "v 0 0 0", "v 1 0 0", "v 1 1 0", "v 0 1 0", "vn 0 0 2", "vt 0.25 0.75 0", "vt 1 1",
+        "f 1/1/1 2/1/1 3/2/1",                    # before any g: surface named ""
+        "g first", "usemtl b", "f 1/1/1 2/1/1 3/1/1 4/2/1",   # quad -> (0,1,2) (0,2,3)
+        "usemtl a",                               # the LAST usemtl before the flush wins
+        "g renamed_without_faces", "g second", "usemtl nosuch",
+        "f 1/1/1 2/1/1 3/1/1", "f 1//1 2//1 3//1",            # missing vt: skipped
+        "f 1/1/1 2/1/1 9/1/1",                                # index out of range: skipped
+        "f  1/1/1 2/1/1 3/1/1",                               # double space = 4 spaces with 3 corners: skipped (undefined in the reference)
+        "", "g third", "usemtl c", "f 3/2/1 2/1/1 1/1/1  "]) + "\n")
+    h = host.pg1_load_obj(str(obj).encode(), 0)
+    try:
+        assert host.pg1_num_materials(h) == 3                   # a, b, (the second "a" is dropped: the name exists), c (the last is always pushed)
+        assert [material(host, h, i)[0] for i in range(3)] == ["a", "b", "c"]
+        assert host.pg1_num_surfaces(h) == 4
+        assert [host.pg1_surface_name(h, i).decode() for i in range(4)] == ["", "first", "second", "third"]
+        assert [host.pg1_surface_triangles(h, i) for i in range(4)] == [1, 2, 1, 1]
+        assert host.pg1_surface_material(h, 1) == 0            # "a": the last usemtl seen before the next g
+        assert host.pg1_surface_material(h, 2) == -1           # no such material
+        pos, nrm, uv = scene_arrays(host, h, 1)
+        assert pos.reshape(2, 3, 3)[1].tolist() == [[0, 0, 0], [1, 1, 0], [0, 1, 0]]
+        assert np.allclose(nrm.reshape(-1, 3), [0, 0, 1]) and uv.reshape(2, 3, 2)[1].tolist() == [[0.25, 0.75], [0.25, 0.75], [1, 1]]
+        name, v = material(host, h, 0)
+        assert v[3:6].tolist() == [1, 0, 0] and int(v[14]) == 4
+    finally:
+        host.pg1_free_scene(h)
+    h = host.pg1_load_obj(str(tmp_path / "absent.obj").encode(), 0)
+    assert host.pg1_scene_rc(h) == -1
+    host.pg1_free_scene(h)
+
+
+# ------------------------------------------------------------------------------------------------ camera
+def test_host_camera_matches_the_oracle(host, oracle_mod, cornell):
+    o = oracle_mod.Oracle(cornell)
+    c = cornell.camera
+    f = (C.c_float * 3)(*c.view_from); a = (C.c_float * 3)(*c.view_at)
+    for mode in (1, 0):
+        rays = o.primary_rays(oracle_mod.make_params(sampling_width=1, jitter=0, aperture=0.0, camera_mode=mode))
+        out = np.zeros(9, np.float32)
+        for (x, y) in ((0, 0), (17, 5), (c.width - 1, c.height - 1)):
+            host.pg1_camera_ray(c.width, c.height, c.fov_y, f, a, float(x), float(y), 0 if mode == 1 else 1, 200.0, 0.0, 0.0, out.ctypes.data)
+            ref = rays[y * c.width + x].copy()
+            if mode == 0:
+                ref[7] = 0.0                       # generate_ray leaves time = 0; get_pixel overwrites it with IOR_AIR (raytracer.cpp:416)
+            else:
+                ref[7] = 0.0
+            assert np.array_equal(out[:8], ref[:8]), (mode, x, y)
+
+
+# ------------------------------------------------------------------------------------------------ Raytracer on the GPU
+def _write_scene_files(sc, d):
+    """OBJ + MTL + textures (PPM) + env (PPM) for Raytracer::LoadScene."""
+    from PIL import Image
+    for i, t in enumerate(sc.textures):
+        rgb = t.data[:, :t.width * t.bpp].reshape(t.height, t.width, t.bpp)[..., 2::-1]
+        Image.fromarray(np.ascontiguousarray(rgb)).save(os.path.join(d, f"tex{i}.ppm"), "PPM")
+    for m in sc.materials:
+        m.map_kd = f"tex{m.diffuse_tex}.ppm" if m.diffuse_tex >= 0 else ""
+    scenes.write_obj(sc, os.path.join(d, "scene.obj"))
+    e = sc.env
+    rgb = e.data[:, :e.width * e.bpp].reshape(e.height, e.width, e.bpp)[..., 2::-1]
+    Image.fromarray(np.ascontiguousarray(rgb)).save(os.path.join(d, "env.ppm"), "PPM")
+
+
+@pytest.mark.gpu
+def test_cpp_raytracer_renders_the_same_frame_as_the_abi(host, tmp_path, cornell):
+    """Raytracer(w,h,fov,from,at) + LoadScene(obj, bg) + RenderFrame / get_pixel in C++ == the same scene through the
+    Python mirror (bit for bit: same ABI calls underneath, same bytes in)."""
+    import pgi_raytracing_b200 as P
+    sc = scenes.cornell_like(); sc.camera = cornell.camera
+    _write_scene_files(sc, str(tmp_path))
+    # the OBJ loader re-normalises normals: give the Python side the same arrays
+    h = host.pg1_load_obj(str(tmp_path / "scene.obj").encode(), 0)
+    for i, m in enumerate(sc.meshes):
+        pos, nrm, uv = scene_arrays(host, h, i)
+        m.nrm = nrm.reshape(m.nrm.shape)
+    host.pg1_free_scene(h)
+    c = sc.camera
+    f = (C.c_float * 3)(*c.view_from); a = (C.c_float * 3)(*c.view_at)
+    rt = host.pg1_raytracer_create(c.width, c.height, c.fov_y, f, a, b"threads=0,verbose=3")
+    assert rt, host.pg1_last_error()
+    try:
+        assert host.pg1_raytracer_load_scene(rt, str(tmp_path / "scene.obj").encode(), str(tmp_path / "env.ppm").encode()) == 0, host.pg1_last_error()
+        counts = (C.c_int * 2)(); host.pg1_raytracer_counts(rt, counts)
+        assert list(counts) == [len(sc.meshes), len(sc.materials)]
+        ref_rt = P.raytracer_for(sc)
+        for params in (dict(), dict(sampling_width=1, jitter=0, aperture=0.0, max_depth=3)):
+            p = P.default_params(**params)
+            host.pg1_raytracer_set(rt, p.sampling_width, p.jitter, p.focal_distance, p.aperture, p.max_depth, p.gamma_level, p.seed)
+            img = np.zeros((c.height, c.width, 4), np.float32); rays = (C.c_ulonglong * 4)()
+            assert host.pg1_raytracer_render(rt, img.ctypes.data, rays) == 0, host.pg1_last_error()
+            ref, st = ref_rt.render(params)
+            assert np.array_equal(img, ref, equal_nan=True)
+            assert list(rays) == [st["primary"], st["shadow"], st["reflection"], st["refraction"]]
+            px = np.zeros(4, np.float32)
+            assert host.pg1_raytracer_get_pixel(rt, 10, 7, px.ctypes.data) == 0
+            assert np.array_equal(px, ref[7, 10], equal_nan=True)
+    finally:
+        host.pg1_raytracer_destroy(rt)
+
+
+@pytest.mark.gpu
+def test_pg1_b200_executable(tmp_path, cornell):
+    """The headless counterpart of the reference's executable: loads OBJ + env, renders, writes a PPM."""
+    from PIL import Image
+    sc = scenes.cornell_like(); sc.camera = cornell.camera
+    _write_scene_files(sc, str(tmp_path))
+    exe = os.path.join(PKG, "pg1_b200")
+    out = subprocess.run([exe, str(tmp_path / "scene.obj"), str(tmp_path / "env.ppm"), "--width", "96", "--height", "64", "--frames", "2",
+                          "--out", str(tmp_path / "frame.ppm")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert f"Surfaces = {len(sc.meshes)}" in out.stdout and "Mrays/s" in out.stdout
+    img = np.asarray(Image.open(str(tmp_path / "frame.ppm")))
+    assert img.shape == (64, 96, 3) and img.std() > 5
