@@ -9,8 +9,11 @@ Workload (N=1 default) = BASELINE.json configs[1]: avenger (stand-in mesh, the r
 Whitted, depth cut-off 10, 1 spp un-jittered.  For N>1 the same frame is cut into 32x8 tiles dealt round-robin to
 the ranks (strong scaling: total work fixed) and gathered to rank 0 over NCCL every step.
 
-value  : rays/s of whole frames, scene resident in HBM, timed with CUDA events per step, L2 flushed between steps.
-e2e    : the same metric through the host-buffer C-ABI call (pgrt_set_camera + pgrt_render into pinned host memory).
+value  : rays/s of K whole frames, scene resident in HBM, device time between two CUDA events around all K steps; the
+         Producer loop renders frames forever (pg1/simpleguidx11.cpp:95-125), so up to --inflight frames (default 4) are
+         in flight per GPU (own stream each, pgrt_render*_begin / pgrt_render_end); L2 is flushed before every step.
+e2e    : the same metric through the host-buffer C-ABI call every step (pgrt_set_camera + pgrt_render_begin into pinned
+         host memory + pgrt_render_end), wall clock.
 --impl reference : the CPU restatement of the reference's loop (oracle/; the reference itself cannot be built here)
                    on all host cores, same config, same metric.
 """
@@ -195,10 +198,10 @@ def run_ours(args):
 
     sc, p, desc = workload(args.workload)
     rt = raytracer_for(sc, device=local)
-    stream = torch.cuda.current_stream()
-    rt.set_stream(stream.cuda_stream)
     params = default_params(**p)
-    sr = ShardedRenderer(rt, rank, world, dev)
+    depth = max(1, min(args.inflight, 4))
+    K, W = args.steps, max(args.warmup, 3)
+    sr = ShardedRenderer(rt, rank, world, dev, depth=depth)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -206,24 +209,40 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        sr.render(params)
-    barrier()
-    sampler = ClockSampler(local); sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    rays = 0; launches = 0; trace_ms = 0.0; trace_launches = 0; stats = None
-    launches0 = rt.kernel_launches()
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)
+    def l2_flush(k):
+        def f(stream):
+            with torch.cuda.stream(stream):
+                flush.fill_(k & 0xFF)
+        return f
+
+    def run_frames(n, timed):
+        """n frames, `depth` in flight; every frame is preceded by an L2 flush on its own stream.  Returns (device ms, rays)."""
+        comm = torch.cuda.current_stream()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         barrier()
-        ev[k][0].record(stream)
-        stats = sr.render(params, profile=True)
-        ev[k][1].record(stream)
-        rays += stats["total"]; trace_ms += stats["trace_ms"]; trace_launches += stats["trace_launches"]
-    barrier()
+        t0.record(comm)
+        for s in sr.slot_streams:
+            s.wait_event(t0)
+        rays = 0
+        for k in range(n):
+            if k >= depth:
+                rays += sr.end(k - depth)["total"]
+            sr.begin(k, params, before=l2_flush(k))
+        for k in range(max(0, n - depth), n):
+            rays += sr.end(k)["total"]
+        for s in sr.slot_streams:
+            comm.wait_stream(s)
+        t1.record(comm)
+        barrier()
+        return t0.elapsed_time(t1), rays
+
+    run_frames(max(W, 2 * depth), False)   # every slot allocates its queues on first use: keep that out of the timed region
+    sampler = ClockSampler(local); sampler.start()
+    launches0 = rt.kernel_launches()
+    total_ms, rays = run_frames(K, True)
     launches = rt.kernel_launches() - launches0
     clocks = sampler.stop()
-    step_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+    step_ms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(rays), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)
@@ -231,56 +250,78 @@ def run_ours(args):
     total_ms = float(step_ms.item()); total_rays = float(tot[0].item())
     value = total_rays / (total_ms * 1e-3) / 1e6
 
-    # e2e: host-buffer C-ABI call, camera re-sent every step, framebuffer copied back to pinned host memory every step
-    e2e = None
+    # roofline of the dominant kernels: the same frames one at a time with every launch bracketed by CUDA events on its stream
+    trace_ms = 0.0; trace_launches = 0; prof_rays = 0; lv = None; prof_frame_ms = 0.0
+    n_prof = min(K, 10)
+    for k in range(n_prof):
+        sr.begin(k, params, profile=1, before=l2_flush(k))
+        st = sr.end(k)
+        trace_ms += st["trace_ms"]; trace_launches += st["trace_launches"]; prof_rays += st["total"]; prof_frame_ms += st["frame_ms"]
+    lv = rt.level_stats()
+    barrier()
+
+    # e2e: the host-buffer C-ABI call every step (camera re-sent, frame copied back to pinned host memory), `depth` in flight
+    c = sc.camera
     if world == 1:
-        rt.set_shard(0, 1)
-        host = torch.empty((rt.height, rt.width, 4), dtype=torch.float32).pin_memory()
-        c = sc.camera
-        for _ in range(3):
-            rt.render_host_ptr(host.data_ptr(), params)
-        torch.cuda.synchronize()
-        e_rays = 0; t_e2e = 0.0
-        for k in range(args.steps):
-            flush.fill_(k & 0xFF); torch.cuda.synchronize()
+        hosts = [torch.empty((rt.height, rt.width, 4), dtype=torch.float32).pin_memory() for _ in range(depth)]
+
+        def e2e_frames(n):
+            e_rays = 0
+            torch.cuda.synchronize()
             t0 = time.perf_counter()
-            rt.set_camera(c.width, c.height, c.fov_y, c.view_from, c.view_at)
-            st = rt.render_host_ptr(host.data_ptr(), params)
-            t_e2e += time.perf_counter() - t0
-            e_rays += st["total"]
+            for k in range(n):
+                if k >= depth:
+                    e_rays += rt.render_end((k - depth) % depth)["total"]
+                l2_flush(k)(sr.slot_streams[k % depth])
+                rt.set_camera(c.width, c.height, c.fov_y, c.view_from, c.view_at)
+                rt.render_begin(k % depth, params, host_ptr=hosts[k % depth].data_ptr())
+            for k in range(max(0, n - depth), n):
+                e_rays += rt.render_end(k % depth)["total"]
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0, e_rays
+
+        rt.set_shard(0, 1)
+        e2e_frames(2 * depth)
+        t_e2e, e_rays = e2e_frames(K)
         e2e = {"value": e_rays / t_e2e / 1e6, "unit": UNIT, "h2d_bytes_per_step": 4 * (2 + 1 + 3 + 3) + 64,
-               "d2h_bytes_per_step": rt.width * rt.height * 16, "ms_per_step": t_e2e / args.steps * 1e3}
+               "d2h_bytes_per_step": rt.width * rt.height * 16, "ms_per_step": t_e2e / K * 1e3}
     else:
         # multi-GPU e2e: rank 0 additionally copies the gathered frame to pinned host memory every step
         host = torch.empty((rt.height, rt.width, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
         barrier()
         t0 = time.perf_counter(); e_rays = 0
-        for k in range(args.steps):
-            st = sr.render(params)
+        for k in range(K):
+            if k >= depth:
+                e_rays += sr.end(k - depth)["total"]
+            sr.begin(k, params, before=l2_flush(k))
             if rank == 0:
                 host.copy_(sr.frame, non_blocking=True)
-            torch.cuda.synchronize()
-            e_rays += st["total"]
+        for k in range(max(0, K - depth), K):
+            e_rays += sr.end(k)["total"]
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         er = torch.tensor([float(e_rays)], dtype=torch.float64, device=dev)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX); dist.all_reduce(er, op=dist.ReduceOp.SUM)
         e2e = {"value": float(er.item()) / float(dt.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 4 * (2 + 1 + 3 + 3) + 64,
-               "d2h_bytes_per_step": rt.width * rt.height * 16, "ms_per_step": float(dt.item()) / args.steps * 1e3}
+               "d2h_bytes_per_step": rt.width * rt.height * 16, "ms_per_step": float(dt.item()) / K * 1e3}
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         b_ray = algorithmic_bytes_per_ray(sc.ntris)
-        rays_per_rank = rays   # rank 0's own rays and kernel times
-        achieved = rays_per_rank * b_ray / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None
+        achieved = prof_rays * b_ray / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None
         roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (achieved / peaks["hbm_gbs"]) if achieved else None,
-                "traffic": None, "kernel": "k_trace + k_phong (closest-hit traversal launches)", "bytes_per_ray": b_ray,
-                "launch_ms_avg": trace_ms / max(trace_launches, 1), "peak_kind": peak_kind,
-                "note": "algorithmic bytes = SURVEY 8(d) contract figure x rays traced; the avenger working set is L2-resident, see DESIGN.md"}
-        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-               "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-               "data": "synthetic", "config": {"workload": desc, "triangles": sc.ntris, "rays_per_frame": total_rays / args.steps,
-                                                "parallelism": f"tiles32x8/rr x{world}", "l2": "flushed between timed steps (256 MiB fill)",
+                "traffic": None, "kernel": "k_trace + k_phong + k_secondary (every closest-hit query of the frame)", "bytes_per_ray": b_ray,
+                "launch_ms_avg": trace_ms / max(trace_launches, 1), "launches_per_frame": trace_launches / max(n_prof, 1), "peak_kind": peak_kind,
+                "frame_ms_unpipelined": prof_frame_ms / max(n_prof, 1),
+                "level0_trace_ms": lv[0]["trace_ms"] if lv else None, "secondary_ms": lv[1]["trace_ms"] if lv and len(lv) > 1 else None,
+                "note": "algorithmic bytes = SURVEY 8(d) contract figure (720 B/ray at this size) x rays of rank 0, over the summed device time of the "
+                        "traversal launches measured one frame at a time (CUDA events on the launching stream, L2 flushed before each frame); the "
+                        "working set is L2-resident and the kernels are issue-/latency-bound, see DESIGN.md 3.3"}
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic", "config": {"workload": desc, "triangles": sc.ntris, "rays_per_frame": total_rays / K,
+                                                "parallelism": f"tiles32x8/rr x{world}", "frames_in_flight": depth,
+                                                "l2": "flushed before every timed step on that step's stream (256 MiB fill)",
                                                 "bvh": rt.build_stats},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(tot[1].item()), "roofline": roof}
         if world == 1 and not args.no_cpu_baseline:
@@ -298,6 +339,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=4, help="frames in flight per GPU (1 = one frame at a time)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -24,6 +24,8 @@ extern "C" {
 #define PGRT_ERR_NO_DEVICE 3    /* no usable GPU                                           */
 #define PGRT_ERR_OVERFLOW 4     /* secondary-ray queues overflowed even at the minimum batch */
 
+#define PGRT_MAX_INFLIGHT 4            /* frame slots of a context (pipelined frames)             */
+
 #define PGRT_INVALID_ID 0xFFFFFFFFu   /* = RTC_INVALID_GEOMETRY_ID, embree3/rtcore_common.h:45 */
 #define PGRT_IOR_AIR 1.000293f        /* material.h:15 */
 
@@ -75,7 +77,8 @@ typedef struct pgrt_build_stats {
     float collapse_ms;        /* collapse to the wide layout + triangle re-layout                */
     uint32_t depth;           /* levels of the wide tree                                         */
     uint32_t ploc_passes;     /* multi-block PLOC passes (the last <= 512 clusters finish in one block) */
-    uint32_t reserved[3];
+    uint32_t node_bytes;      /* 80 = quantised planes, 208 = float planes (chosen by scene size; PGRT_NODE_LAYOUT=q8|f32) */
+    uint32_t reserved[2];
 } pgrt_build_stats;
 
 typedef struct pgrt_render_stats {
@@ -153,6 +156,19 @@ void pgrt_default_params(pgrt_render_params* p);
  *      bit 1 runs the instrumented traversal that counts nodes / triangles per query (slower; same image). */
 int pgrt_render(pgrt_context* ctx, const pgrt_render_params* p, float* rgba_host, pgrt_render_stats* stats, int32_t profile);
 int pgrt_render_device(pgrt_context* ctx, const pgrt_render_params* p, void* rgba_device, pgrt_render_stats* stats, int32_t profile);
+/* ---- pipelined frames.  Producer renders frames forever (simpleguidx11.cpp:95-125); a context can keep up to
+ *      PGRT_MAX_INFLIGHT of them in flight, each in its own slot (own CUDA stream, queues and counters), so that the
+ *      latency-bound tail of one frame and its device->host copy overlap the next frame's primary rays.
+ *      *_begin enqueues the whole frame and returns without waiting for the GPU (host destinations should be pinned);
+ *      pgrt_render_end waits for that slot, handles the rare queue-overflow retry and fills the stats.
+ *      pgrt_render / pgrt_render_device / pgrt_render_shard_device are begin + end on slot 0.
+ *      The scene, camera and shard may only change while no frame is in flight. */
+int pgrt_render_begin(pgrt_context* ctx, const pgrt_render_params* p, float* rgba_host, int32_t slot, int32_t profile);
+int pgrt_render_device_begin(pgrt_context* ctx, const pgrt_render_params* p, void* rgba_device, int32_t slot, int32_t profile);
+int pgrt_render_shard_device_begin(pgrt_context* ctx, const pgrt_render_params* p, void* shard_rgba_device, int32_t slot, int32_t profile);
+int pgrt_render_end(pgrt_context* ctx, int32_t slot, pgrt_render_stats* stats);
+void* pgrt_slot_stream(pgrt_context* ctx, int32_t slot);                          /* cudaStream_t of a slot (slot 0 = pgrt_set_stream's) */
+int pgrt_stream_wait_slot(pgrt_context* ctx, int32_t slot, void* cuda_stream);    /* make `cuda_stream` wait for the slot's frame        */
 /* single-pixel hook with the signature of SimpleGuiDX11::get_pixel (simpleguidx11.h:27): serves pixel (x,y) of
  * the frame rendered by the last pgrt_render* call (re-renders when the camera, scene or params changed). */
 int pgrt_get_pixel(pgrt_context* ctx, const pgrt_render_params* p, int32_t x, int32_t y, float rgba[4]);
@@ -167,6 +183,7 @@ int pgrt_set_shard(pgrt_context* ctx, int32_t rank, int32_t n_ranks);
 uint64_t pgrt_shard_pixels(const pgrt_context* ctx);   /* padded pixel slots per rank (same on every rank) */
 int pgrt_render_shard_device(pgrt_context* ctx, const pgrt_render_params* p, void* shard_rgba_device, pgrt_render_stats* stats, int32_t profile);
 int pgrt_untile(pgrt_context* ctx, const void* gathered_device, int32_t n_ranks, void* rgba_device);
+int pgrt_untile_on_stream(pgrt_context* ctx, const void* gathered_device, int32_t n_ranks, void* rgba_device, void* cuda_stream);   /* same, on the stream the gather ran on */
 
 /* ---- rtcIntersect1 over a batch (raytracer.cpp:130-148; semantics emb/doc/README.md:6331-6415):
  *      closest hit in (tnear, tfar]; on hit writes tfar, u, v, Ng, primID, geomID; a miss leaves the record

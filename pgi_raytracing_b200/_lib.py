@@ -10,11 +10,12 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpgrt_b200.so")
+LIB_PATH = os.environ.get("PGRT_LIB") or os.path.join(_HERE, "libpgrt_b200.so")   # PGRT_LIB: A/B builds of the same ABI (tools/)
 CSRC = os.path.join(_HERE, "csrc")
 
 PGRT_OK, PGRT_ERR_INVALID, PGRT_ERR_CUDA, PGRT_ERR_NO_DEVICE, PGRT_ERR_OVERFLOW = 0, 1, 2, 3, 4
 INVALID_ID = 0xFFFFFFFF
+MAX_INFLIGHT = 4
 
 
 class Material(C.Structure):
@@ -35,7 +36,7 @@ class RenderParams(C.Structure):
 class BuildStats(C.Structure):
     _fields_ = [("triangles", C.c_uint32), ("nodes", C.c_uint32), ("build_ms", C.c_float), ("sort_ms", C.c_float),
                 ("sah_cost", C.c_float), ("tree_ms", C.c_float), ("collapse_ms", C.c_float), ("depth", C.c_uint32),
-                ("ploc_passes", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+                ("ploc_passes", C.c_uint32), ("node_bytes", C.c_uint32), ("reserved", C.c_uint32 * 2)]
 
 
 class RenderStats(C.Structure):
@@ -70,12 +71,19 @@ SYMBOLS = {
     "pgrt_default_params": (None, [C.POINTER(RenderParams)]),
     "pgrt_render": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, C.POINTER(RenderStats), _I32]),
     "pgrt_render_device": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, C.POINTER(RenderStats), _I32]),
+    "pgrt_render_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),
+    "pgrt_render_device_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),
+    "pgrt_render_shard_device_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),
+    "pgrt_render_end": (C.c_int, [_VP, _I32, C.POINTER(RenderStats)]),
+    "pgrt_slot_stream": (_VP, [_VP, _I32]),
+    "pgrt_stream_wait_slot": (C.c_int, [_VP, _I32, _VP]),
     "pgrt_get_pixel": (C.c_int, [_VP, C.POINTER(RenderParams), _I32, _I32, C.POINTER(_F)]),
     "pgrt_primary_ids": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _VP]),
     "pgrt_set_shard": (C.c_int, [_VP, _I32, _I32]),
     "pgrt_shard_pixels": (_U64, [_VP]),
     "pgrt_render_shard_device": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, C.POINTER(RenderStats), _I32]),
     "pgrt_untile": (C.c_int, [_VP, _VP, _I32, _VP]),
+    "pgrt_untile_on_stream": (C.c_int, [_VP, _VP, _I32, _VP, _VP]),
     "pgrt_intersect": (C.c_int, [_VP, _VP, _U64]),
     "pgrt_interpolate": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _U64, _I32, _VP]),
     "pgrt_eval_mix_srgb": (C.c_int, [_VP, _VP, _VP, _VP, _U64, _VP]),

@@ -145,6 +145,29 @@ class Raytracer:
         self._check(self.lib.pgrt_render(self.h, C.byref(p), C.c_void_p(host_ptr), C.byref(rs), int(profile)))
         return self._stats(rs)
 
+    # ---- pipelined frames (pgrt_render*_begin / pgrt_render_end): up to MAX_INFLIGHT frames in flight
+    def render_begin(self, slot: int, params=None, *, host_ptr: int = 0, device_ptr: int = 0, shard_ptr: int = 0, profile: int = 0):
+        """Enqueue one frame in ``slot`` and return without waiting for the GPU.  Exactly one destination."""
+        p = self._params(params)
+        if host_ptr:
+            rc = self.lib.pgrt_render_begin(self.h, C.byref(p), C.c_void_p(host_ptr), slot, int(profile))
+        elif device_ptr:
+            rc = self.lib.pgrt_render_device_begin(self.h, C.byref(p), C.c_void_p(device_ptr), slot, int(profile))
+        else:
+            rc = self.lib.pgrt_render_shard_device_begin(self.h, C.byref(p), C.c_void_p(shard_ptr), slot, int(profile))
+        self._check(rc)
+
+    def render_end(self, slot: int) -> dict:
+        rs = L.RenderStats()
+        self._check(self.lib.pgrt_render_end(self.h, slot, C.byref(rs)))
+        return self._stats(rs)
+
+    def slot_stream(self, slot: int) -> int:
+        return int(self.lib.pgrt_slot_stream(self.h, slot) or 0)
+
+    def stream_wait_slot(self, slot: int, cuda_stream_ptr: int):
+        self._check(self.lib.pgrt_stream_wait_slot(self.h, slot, C.c_void_p(cuda_stream_ptr)))
+
     def get_pixel(self, x: int, y: int, t: float = 0.0, params=None):
         """``Color4f get_pixel(x, y, t)`` (pg1/raytracer.cpp:396-437); ``t`` is ignored, as in the reference."""
         p = self._params(params)
@@ -170,8 +193,11 @@ class Raytracer:
         self._check(self.lib.pgrt_render_shard_device(self.h, C.byref(p), C.c_void_p(device_ptr), C.byref(rs), int(profile)))
         return self._stats(rs)
 
-    def untile(self, gathered_ptr: int, n_ranks: int, out_ptr: int):
-        self._check(self.lib.pgrt_untile(self.h, C.c_void_p(gathered_ptr), n_ranks, C.c_void_p(out_ptr)))
+    def untile(self, gathered_ptr: int, n_ranks: int, out_ptr: int, cuda_stream_ptr: int | None = None):
+        if cuda_stream_ptr is None:
+            self._check(self.lib.pgrt_untile(self.h, C.c_void_p(gathered_ptr), n_ranks, C.c_void_p(out_ptr)))
+        else:
+            self._check(self.lib.pgrt_untile_on_stream(self.h, C.c_void_p(gathered_ptr), n_ranks, C.c_void_p(out_ptr), C.c_void_p(cuda_stream_ptr)))
 
     # ---- rtcIntersect1 / rtcInterpolate0 batches
     def intersect(self, rayhits: np.ndarray) -> np.ndarray:

@@ -19,8 +19,19 @@
 //           = 001 | 11sss                internal child: wide node child_base + (number of internal slots below s)
 //           = unary(n) << 5 | offset     leaf child: n <= 3 triangles at tri_base + offset (offset <= 21)
 // imask bit s is set for internal children.  Triangles: 3 x float4 each (v0 | flat id, v0 - v1, v2 - v0), 48 B.
+//
+// Second layout, PGRT_LAYOUT_F32 (13 x float4 = 208 B): the same node with the 48 planes kept as floats,
+//   f0 = (child_base, tri_base, meta[0..3], meta[4..7]);  f[1 + 2*p + h] = plane p (lo.x, lo.y, lo.z, hi.x, hi.y, hi.z) of slots 4h..4h+3.
+// It costs 2.6x the bytes and removes the 48 integer->float conversions per node visit (the decode is 30 % of the
+// instructions of a visit, profiles/r1_ncu_bvh8_q8_k_trace_k_secondary.txt); pgrt_commit picks it while the node array stays far below L2
+// capacity (the traversal is then issue-bound, not memory-bound) and the quantised one otherwise.
 #pragma once
 #include "common.cuh"
+
+#define PGRT_LAYOUT_Q8 0
+#define PGRT_LAYOUT_F32 1
+#define PGRT_NODE_F4_Q8 5         // float4 per node
+#define PGRT_NODE_F4_F32 13
 
 #define PGRT_LEAF_TRIS 3          // triangles per leaf slot
 #define PGRT_STACK8 40            // traversal stack entries (one pushed per level at most; commit checks the depth)
@@ -103,7 +114,7 @@ PG_HD void bvh8_write_tri(const float* __restrict__ pos, uint32_t id, float4* __
 // binary roots of its internal children in child order (int_children[r] becomes wide node child_base + r).
 // Returns SAH terms of this node through sah (node term + leaf terms, un-normalised half areas).
 PG_HD void bvh8_emit(const Bvh2View& t, uint32_t root, const Wide8& w, uint32_t child_base, uint32_t tri_base, const float* __restrict__ pos,
-                     float4* __restrict__ node_out, float4* __restrict__ tris, uint32_t* int_children, float& sah) {
+                     float4* __restrict__ node_out, float4* __restrict__ tris, uint32_t* int_children, float& sah, int layout = PGRT_LAYOUT_Q8) {
     const float4 nlo = t.b0[root], nhi = t.b1[root];
     const uint32_t ex = bvh8_exponent(nlo.x, nhi.x), ey = bvh8_exponent(nlo.y, nhi.y), ez = bvh8_exponent(nlo.z, nhi.z);
     const float sx = pg_u2f(ex << 23), sy = pg_u2f(ey << 23), sz = pg_u2f(ez << 23);
@@ -130,14 +141,16 @@ PG_HD void bvh8_emit(const Bvh2View& t, uint32_t root, const Wide8& w, uint32_t 
     }
     // ---- per-slot encoding
     uint32_t meta[8], q[6][8];
+    float fb[6][8];                     // exact child boxes (F32 layout); empty slots get an inverted box
     uint32_t imask = 0, n_int = 0, tri_off = 0;
     sah = box_half_area(nlo, nhi);
     for (int s = 0; s < 8; ++s) {
-        meta[s] = 0; for (int a = 0; a < 6; ++a) q[a][s] = 0;
+        meta[s] = 0; for (int a = 0; a < 6; ++a) { q[a][s] = 0; fb[a][s] = a < 3 ? FLT_MAX : -FLT_MAX; }
         const int k = slot_child[s];
         if (k < 0) continue;
         const uint32_t c = w.ch[k];
         const float4 lo = t.b0[c], hi = t.b1[c];
+        fb[0][s] = lo.x; fb[1][s] = lo.y; fb[2][s] = lo.z; fb[3][s] = hi.x; fb[4][s] = hi.y; fb[5][s] = hi.z;
         const float clo[3] = {lo.x, lo.y, lo.z}, chi[3] = {hi.x, hi.y, hi.z}, base[3] = {nlo.x, nlo.y, nlo.z}, step[3] = {sx, sy, sz};
         for (int a = 0; a < 3; ++a) {
             float ql = floorf((clo[a] - base[a]) / step[a]);
@@ -164,6 +177,12 @@ PG_HD void bvh8_emit(const Bvh2View& t, uint32_t root, const Wide8& w, uint32_t 
                 else { st[sp++] = pg_f2u(t.b1[x].w); st[sp++] = pg_f2u(t.b0[x].w); }
             }
         }
+    }
+    if (layout == PGRT_LAYOUT_F32) {
+        node_out[0] = make_float4(pg_u2f(child_base), pg_u2f(tri_base), pg_u2f(pack4(meta)), pg_u2f(pack4(meta + 4)));
+        for (int a = 0; a < 6; ++a)
+            for (int h = 0; h < 2; ++h) node_out[1 + 2 * a + h] = make_float4(fb[a][4 * h], fb[a][4 * h + 1], fb[a][4 * h + 2], fb[a][4 * h + 3]);
+        return;
     }
     node_out[0] = make_float4(nlo.x, nlo.y, nlo.z, pg_u2f(ex | (ey << 8) | (ez << 16) | (imask << 24)));
     node_out[1] = make_float4(pg_u2f(child_base), pg_u2f(tri_base), pg_u2f(pack4(meta)), pg_u2f(pack4(meta + 4)));

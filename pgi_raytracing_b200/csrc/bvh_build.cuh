@@ -541,7 +541,7 @@ struct CollapseCounters { uint32_t nodes, tris, next_items, pad; float sah; };
 
 __global__ void __launch_bounds__(128) k_collapse(Bvh2View t, const float* __restrict__ pos, const uint2* __restrict__ items, uint32_t n_items,
                                                   uint2* __restrict__ next_items, CollapseCounters* __restrict__ cc,
-                                                  float4* __restrict__ nodes, float4* __restrict__ tris) {
+                                                  float4* __restrict__ nodes, float4* __restrict__ tris, int layout) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     float sah = 0.0f;
     if (k < n_items) {
@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(128) k_collapse(Bvh2View t, const float* __res
         const uint32_t child_base = n_int ? atomicAdd(&cc->nodes, (uint32_t)n_int) : 0u;
         const uint32_t tri_base = n_tri ? atomicAdd(&cc->tris, (uint32_t)n_tri) : 0u;
         uint32_t ic[8];
-        bvh8_emit(t, it.x, w, child_base, tri_base, pos, nodes + 5 * (size_t)it.y, tris, ic, sah);
+        bvh8_emit(t, it.x, w, child_base, tri_base, pos, nodes + (size_t)(layout == PGRT_LAYOUT_F32 ? PGRT_NODE_F4_F32 : PGRT_NODE_F4_Q8) * it.y, tris, ic, sah, layout);
         if (n_int) {
             const uint32_t q = atomicAdd(&cc->next_items, (uint32_t)n_int);
             for (int r = 0; r < n_int; ++r) next_items[q + r] = make_uint2(ic[r], child_base + (uint32_t)r);

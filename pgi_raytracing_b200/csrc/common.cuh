@@ -130,7 +130,8 @@ struct DevScene {
     const pgrt_light* lights;
     int32_t n_lights;
     uint32_t n_tris;
-    uint32_t root;            // encoded root reference
+    uint32_t root;            // encoded root reference (binary layout only)
+    int32_t node_layout;      // PGRT_LAYOUT_Q8 (80 B nodes) or PGRT_LAYOUT_F32 (208 B nodes), bvh8.cuh
 };
 
 #define CUDA_TRY(call)                                                                                  \

@@ -30,12 +30,55 @@ struct HostTex { DevBuf<uint8_t> bytes; int w = 0, h = 0, pitch = 0, bpp = 0; bo
 
 enum KClass { KC_TRACE = 0, KC_SHADE = 1 };
 
+// everything one frame in flight owns
+struct FrameSlot {
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    LevelBufs levels[PGRT_MAX_LEVELS + 1] = {};
+    DevBuf<float4> lv_f4[PGRT_MAX_LEVELS + 1][5];
+    DevBuf<uint2> lv_child[PGRT_MAX_LEVELS + 1];
+    DevBuf<uint32_t> lv_list[PGRT_MAX_LEVELS + 1][2];
+    DevBuf<uint32_t> l0_pending;
+    RayPool pool = {};                // every ray of level >= 1 (dynamic scheduler)
+    DevBuf<float4> pool_f4[4]; DevBuf<uint2> pool_u2[2]; DevBuf<uint32_t> pool_u32[1];
+    DevBuf<Counters> d_counters;
+    DevBuf<float4> d_frame;           // device frame behind a host destination
+    Counters* h_counters = nullptr;   // pinned
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_class, ev_level;
+    size_t ev_used = 0;
+    cudaEvent_t ev_frame0 = nullptr, ev_frame1 = nullptr, ev_done = nullptr;
+    // the frame in flight
+    bool busy = false;
+    pgrt_render_params params = {};
+    float4* dest = nullptr; int dest_mode = 0; float* host_dst = nullptr; int profile = 0;
+    uint64_t batch_slots = 0; int n_levels = 0; bool dyn = false;
+    pgrt_render_stats rs = {};
+
+    void release() {
+        for (int l = 0; l <= PGRT_MAX_LEVELS; ++l) {
+            for (int k = 0; k < 5; ++k) lv_f4[l][k].release();
+            lv_child[l].release(); lv_list[l][0].release(); lv_list[l][1].release();
+        }
+        l0_pending.release();
+        for (auto& b : pool_f4) b.release(); for (auto& b : pool_u2) b.release(); for (auto& b : pool_u32) b.release();
+        d_counters.release(); d_frame.release();
+        for (auto e : ev_pool) cudaEventDestroy(e);
+        ev_pool.clear();
+        if (ev_frame0) cudaEventDestroy(ev_frame0);
+        if (ev_frame1) cudaEventDestroy(ev_frame1);
+        if (ev_done) cudaEventDestroy(ev_done);
+        if (h_counters) cudaFreeHost(h_counters);
+        if (own_stream) cudaStreamDestroy(own_stream);
+        ev_frame0 = ev_frame1 = ev_done = nullptr; h_counters = nullptr; own_stream = stream = nullptr;
+    }
+};
+
 }  // namespace
 
 struct pgrt_context {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t stream = nullptr;    // = slots[0].stream: scene uploads, commit, eval entry points, synchronous renders
     std::string err = "";
     uint64_t launches = 0;
 
@@ -57,6 +100,7 @@ struct pgrt_context {
     DevBuf<DevTexture> d_textures;
     DevBuf<float4> d_shade, d_tris, d_nodes;
     uint32_t n_tris = 0, root = 0;
+    int node_layout = PGRT_LAYOUT_Q8;
     bool committed = false, tables_dirty = true;
     pgrt_build_stats last_build = {};
 
@@ -64,29 +108,17 @@ struct pgrt_context {
     bool cam_set = false;
     ShardInfo shard = {0, 1, 0, 0};
 
-    // frame state
-    LevelBufs levels[PGRT_MAX_LEVELS + 1] = {};
-    DevBuf<float4> lv_f4[PGRT_MAX_LEVELS + 1][5];
-    DevBuf<uint2> lv_child[PGRT_MAX_LEVELS + 1];
-    DevBuf<uint32_t> lv_list[PGRT_MAX_LEVELS + 1][2];
-    DevBuf<uint32_t> l0_pending;
-    // ray pool of the dynamic scheduler (levels >= 1)
-    RayPool pool = {};
-    DevBuf<float4> pool_f4[4]; DevBuf<uint2> pool_u2[2]; DevBuf<uint32_t> pool_u32[1];
+    // frame state: PGRT_MAX_INFLIGHT independent frame slots, each with its own stream, queues and counters, so the
+    // latency-bound tail of one frame (k_secondary) and its device->host copy overlap the next frame's primary work
+    FrameSlot slots[PGRT_MAX_INFLIGHT];
     int secondary_grid = 0;
-    DevBuf<Counters> d_counters;
-    DevBuf<float4> d_frame;
     DevBuf<uint32_t> d_ids;
-    Counters* h_counters = nullptr;   // pinned
     uint32_t* h_pin = nullptr;        // pinned scratch for small read-backs of the build
     size_t max_batch_samples = (size_t)1 << 23;
     size_t min_level_cap = (size_t)1 << 18;
     double level_cap_factor = 2.0;
-    std::vector<cudaEvent_t> ev_pool;
-    std::vector<int> ev_class, ev_level;
     pgrt_level_stats level_stats[PGRT_MAX_LEVELS + 1] = {};
     int level_stats_n = 0;
-    cudaEvent_t ev_frame0 = nullptr, ev_frame1 = nullptr;
 
     // get_pixel cache
     std::vector<float> px_cache; pgrt_render_params px_params = {}; bool px_valid = false;
@@ -103,7 +135,7 @@ struct pgrt_context {
         s.nodes = d_nodes.p; s.tris = d_tris.p; s.shade = d_shade.p; s.geom_first = d_geom_first.p; s.geom_material = d_geom_material.p;
         s.materials = d_materials.p; s.textures = d_textures.p; s.n_textures = (int32_t)textures.size();
         s.env.data = env.set ? env.bytes.p : nullptr; s.env.width = env.w; s.env.height = env.h; s.env.pitch = env.pitch; s.env.bpp = env.bpp;
-        s.lights = d_lights.p; s.n_lights = (int32_t)h_lights.size(); s.n_tris = n_tris; s.root = root;
+        s.lights = d_lights.p; s.n_lights = (int32_t)h_lights.size(); s.n_tris = n_tris; s.root = root; s.node_layout = node_layout;
         return s;
     }
 };
@@ -116,6 +148,8 @@ static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1
 // --------------------------------------------------------------------------------------------------- lifetime
 extern "C" const char* pgrt_version(void) { return "pgrt-b200 0.1 (sm_100a)"; }
 
+extern "C" void pgrt_destroy(pgrt_context* ctx);
+
 extern "C" int pgrt_create(pgrt_context** out, int device) {
     if (!out) return PGRT_ERR_INVALID;
     *out = nullptr;
@@ -126,12 +160,16 @@ extern "C" int pgrt_create(pgrt_context** out, int device) {
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return PGRT_ERR_NO_DEVICE; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PGRT_ERR_CUDA; }
-    ctx->stream = ctx->own_stream;
-    cudaEventCreate(&ctx->ev_frame0); cudaEventCreate(&ctx->ev_frame1);
-    if (cudaMallocHost((void**)&ctx->h_counters, sizeof(Counters)) != cudaSuccess) { delete ctx; return PGRT_ERR_CUDA; }
-    if (cudaMallocHost((void**)&ctx->h_pin, 256) != cudaSuccess) { delete ctx; return PGRT_ERR_CUDA; }
-    if (ctx->d_counters.ensure(1) != cudaSuccess) { delete ctx; return PGRT_ERR_CUDA; }
+    for (FrameSlot& S : ctx->slots) {
+        bool ok = cudaStreamCreateWithFlags(&S.own_stream, cudaStreamNonBlocking) == cudaSuccess;
+        S.stream = S.own_stream;
+        ok = ok && cudaEventCreate(&S.ev_frame0) == cudaSuccess && cudaEventCreate(&S.ev_frame1) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaMallocHost((void**)&S.h_counters, sizeof(Counters)) == cudaSuccess && S.d_counters.ensure(1) == cudaSuccess;
+        if (!ok) { pgrt_destroy(ctx); return PGRT_ERR_CUDA; }
+    }
+    ctx->stream = ctx->slots[0].stream;
+    if (cudaMallocHost((void**)&ctx->h_pin, 256) != cudaSuccess) { pgrt_destroy(ctx); return PGRT_ERR_CUDA; }
     if (const char* e = getenv("PGRT_MAX_BATCH_SAMPLES")) ctx->max_batch_samples = std::max<size_t>(256, strtoull(e, nullptr, 10));
     if (const char* e = getenv("PGRT_MIN_LEVEL_CAP")) ctx->min_level_cap = std::max<size_t>(64, strtoull(e, nullptr, 10));
     if (const char* e = getenv("PGRT_LEVEL_CAP_FACTOR")) ctx->level_cap_factor = std::max(0.01, atof(e));
@@ -144,27 +182,21 @@ static void free_scene_device(pgrt_context* ctx) {
     ctx->d_geom_material.release(); ctx->d_shade.release(); ctx->d_tris.release(); ctx->d_nodes.release();
 }
 
+static void sync_all_slots(pgrt_context* ctx) {
+    for (FrameSlot& S : ctx->slots) if (S.stream) cudaStreamSynchronize(S.stream);
+}
+
 extern "C" void pgrt_destroy(pgrt_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    sync_all_slots(ctx);
     free_scene_device(ctx);
     ctx->d_materials.release(); ctx->d_lights.release(); ctx->d_textures.release();
     for (auto& t : ctx->textures) t.bytes.release();
     ctx->env.bytes.release();
-    for (int l = 0; l <= PGRT_MAX_LEVELS; ++l) {
-        for (int k = 0; k < 5; ++k) ctx->lv_f4[l][k].release();
-        ctx->lv_child[l].release(); ctx->lv_list[l][0].release(); ctx->lv_list[l][1].release();
-    }
-    ctx->l0_pending.release();
-    for (auto& b : ctx->pool_f4) b.release(); for (auto& b : ctx->pool_u2) b.release(); for (auto& b : ctx->pool_u32) b.release();
-    ctx->d_counters.release(); ctx->d_frame.release(); ctx->d_ids.release();
-    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
-    if (ctx->ev_frame0) cudaEventDestroy(ctx->ev_frame0);
-    if (ctx->ev_frame1) cudaEventDestroy(ctx->ev_frame1);
-    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    for (FrameSlot& S : ctx->slots) S.release();
+    ctx->d_ids.release();
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
 
@@ -173,9 +205,15 @@ extern "C" const char* pgrt_last_error(const pgrt_context* ctx) { return ctx ? c
 extern "C" int pgrt_set_stream(pgrt_context* ctx, void* s) {
     CHECK_CTX(ctx);
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    sync_all_slots(ctx);
+    ctx->slots[0].stream = s ? (cudaStream_t)s : ctx->slots[0].own_stream;
+    ctx->stream = ctx->slots[0].stream;
     return PGRT_OK;
+}
+
+extern "C" void* pgrt_slot_stream(pgrt_context* ctx, int32_t slot) {
+    if (!ctx || slot < 0 || slot >= PGRT_MAX_INFLIGHT) return nullptr;
+    return (void*)ctx->slots[slot].stream;
 }
 
 // --------------------------------------------------------------------------------------------------- scene
@@ -219,6 +257,7 @@ extern "C" int pgrt_set_lights(pgrt_context* ctx, const pgrt_light* l, int32_t n
 static int upload_tex(pgrt_context* ctx, HostTex& t, const uint8_t* bytes, int w, int h, int pitch, int bpp) {
     if (!bytes || w <= 0 || h <= 0 || (bpp != 3 && bpp != 4) || pitch < w * bpp) return ctx->fail(PGRT_ERR_INVALID, "texture: bad arguments");
     cudaSetDevice(ctx->device);
+    sync_all_slots(ctx);
     CUDA_TRY(t.bytes.ensure((size_t)pitch * h + 4));
     CUDA_TRY(cudaMemcpyAsync(t.bytes.p, bytes, (size_t)pitch * h, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -242,6 +281,7 @@ extern "C" int pgrt_set_envmap(pgrt_context* ctx, const uint8_t* bytes, int32_t 
 static int upload_tables(pgrt_context* ctx) {
     if (!ctx->tables_dirty) return PGRT_OK;
     cudaSetDevice(ctx->device);
+    sync_all_slots(ctx);
     for (const auto& m : ctx->h_geom_material)
         if (m < 0 || (size_t)m >= ctx->h_materials.size()) return ctx->fail(PGRT_ERR_INVALID, "a mesh references a material id that was never set");
     CUDA_TRY(ctx->d_materials.ensure(ctx->h_materials.size()));
@@ -266,6 +306,7 @@ static int upload_tables(pgrt_context* ctx) {
 extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
     CHECK_CTX(ctx);
     cudaSetDevice(ctx->device);
+    sync_all_slots(ctx);
     cudaStream_t st = ctx->stream;
     const uint32_t N = (uint32_t)ctx->h_tri_geom.size();
     ctx->n_tris = N; ctx->px_valid = false;
@@ -289,7 +330,13 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
     CUDA_TRY(cudaMemcpyAsync(ctx->d_nrm.p, ctx->h_nrm.data(), 9 * (size_t)N * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_uv.p, ctx->h_uv.data(), 6 * (size_t)N * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_tri_geom.p, ctx->h_tri_geom.data(), (size_t)N * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx->d_shade.ensure(4 * (size_t)N)); CUDA_TRY(ctx->d_tris.ensure(3 * (size_t)N)); CUDA_TRY(ctx->d_nodes.ensure(5 * (size_t)N));
+    // node layout: un-quantised planes while the node array stays far below L2 capacity (the traversal is issue-bound
+    // there and the decode is 30 % of a node visit), the 80-B quantised node otherwise; PGRT_NODE_LAYOUT=q8|f32 overrides
+    int layout = ((double)N * 0.15 * PGRT_NODE_F4_F32 * 16.0 <= 48e6) ? PGRT_LAYOUT_F32 : PGRT_LAYOUT_Q8;
+    if (const char* e = getenv("PGRT_NODE_LAYOUT")) layout = !strcmp(e, "f32") ? PGRT_LAYOUT_F32 : (!strcmp(e, "q8") ? PGRT_LAYOUT_Q8 : layout);
+    const size_t node_f4 = layout == PGRT_LAYOUT_F32 ? PGRT_NODE_F4_F32 : PGRT_NODE_F4_Q8;
+    ctx->node_layout = layout;
+    CUDA_TRY(ctx->d_shade.ensure(4 * (size_t)N)); CUDA_TRY(ctx->d_tris.ensure(3 * (size_t)N)); CUDA_TRY(ctx->d_nodes.ensure(node_f4 * (size_t)N));
 
     cudaEvent_t e0, e1, e2, e3, e4;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3); cudaEventCreate(&e4);
@@ -383,7 +430,7 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
     uint32_t n_items = 1, depth = 0; int ic = 0;
     CollapseCounters hcc = {};
     while (n_items) {
-        k_collapse<<<div_up(n_items, 128), 128, 0, st>>>(view, ctx->d_pos.p, items[ic].p, n_items, items[ic ^ 1].p, cc.p, ctx->d_nodes.p, ctx->d_tris.p);
+        k_collapse<<<div_up(n_items, 128), 128, 0, st>>>(view, ctx->d_pos.p, items[ic].p, n_items, items[ic ^ 1].p, cc.p, ctx->d_nodes.p, ctx->d_tris.p, layout);
         ctx->launches += 1; depth++;
         BUILD_TRY(cudaMemcpyAsync(ctx->h_pin, cc.p, sizeof(CollapseCounters), cudaMemcpyDeviceToHost, st));
         BUILD_TRY(cudaMemsetAsync(&cc.p->next_items, 0, sizeof(uint32_t), st));
@@ -402,7 +449,7 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
     if (depth + 2 > PGRT_STACK8) { rc = ctx->fail(PGRT_ERR_INVALID, "pgrt_commit: the tree is deeper than the traversal stack (degenerate input)"); cleanup(); return rc; }
     const float ra = box_half_area(rb[0], rb[1]);
     bs.nodes = hcc.nodes; bs.sah_cost = ra > 0.0f ? hcc.sah / ra : (float)N;
-    bs.depth = depth; bs.ploc_passes = passes;
+    bs.depth = depth; bs.ploc_passes = passes; bs.node_bytes = (uint32_t)(node_f4 * 16);
     cudaEventElapsedTime(&bs.build_ms, e0, e4);
     cudaEventElapsedTime(&bs.sort_ms, e1, e2);
     cudaEventElapsedTime(&bs.tree_ms, e2, e3);
@@ -459,46 +506,46 @@ static uint64_t shard_slots(const pgrt_context* ctx) {
 extern "C" uint64_t pgrt_shard_pixels(const pgrt_context* ctx) { return ctx ? shard_slots(ctx) : 0; }
 
 // --------------------------------------------------------------------------------------------------- frame
-static int ensure_pool(pgrt_context* ctx, size_t cap) {
-    for (auto& b : ctx->pool_f4) CUDA_TRY(b.ensure(cap));
-    for (auto& b : ctx->pool_u2) CUDA_TRY(b.ensure(cap));
-    for (auto& b : ctx->pool_u32) CUDA_TRY(b.ensure(cap));
-    RayPool& P = ctx->pool;
-    P.ray_o = ctx->pool_f4[0].p; P.ray_d = ctx->pool_f4[1].p; P.color = ctx->pool_f4[2].p; P.att = ctx->pool_f4[3].p;
-    P.child = ctx->pool_u2[0].p; P.link = ctx->pool_u2[1].p; P.pending = ctx->pool_u32[0].p;
+static int ensure_pool(pgrt_context* ctx, FrameSlot& S, size_t cap) {
+    for (auto& b : S.pool_f4) CUDA_TRY(b.ensure(cap));
+    for (auto& b : S.pool_u2) CUDA_TRY(b.ensure(cap));
+    for (auto& b : S.pool_u32) CUDA_TRY(b.ensure(cap));
+    RayPool& P = S.pool;
+    P.ray_o = S.pool_f4[0].p; P.ray_d = S.pool_f4[1].p; P.color = S.pool_f4[2].p; P.att = S.pool_f4[3].p;
+    P.child = S.pool_u2[0].p; P.link = S.pool_u2[1].p; P.pending = S.pool_u32[0].p;
     P.cap = (uint32_t)cap;
     return PGRT_OK;
 }
 
-static int ensure_levels(pgrt_context* ctx, int n_levels, size_t cap0, size_t capn) {
+static int ensure_levels(pgrt_context* ctx, FrameSlot& S, int n_levels, size_t cap0, size_t capn) {
     for (int l = 0; l <= n_levels; ++l) {   // one spare level so k_shade always has a (never written) "next"
         const size_t cap = l == 0 ? cap0 : (l == n_levels ? 1 : capn);
-        for (int k = 0; k < 5; ++k) CUDA_TRY(ctx->lv_f4[l][k].ensure(cap));
-        CUDA_TRY(ctx->lv_child[l].ensure(cap)); CUDA_TRY(ctx->lv_list[l][0].ensure(cap)); CUDA_TRY(ctx->lv_list[l][1].ensure(cap));
-        LevelBufs& L = ctx->levels[l];
-        L.ray_o = ctx->lv_f4[l][0].p; L.ray_d = ctx->lv_f4[l][1].p; L.hit = ctx->lv_f4[l][2].p; L.color = ctx->lv_f4[l][3].p; L.dn_att = ctx->lv_f4[l][4].p;
-        L.dn_child = ctx->lv_child[l].p; L.phong_list = ctx->lv_list[l][0].p; L.diel_list = ctx->lv_list[l][1].p;
+        for (int k = 0; k < 5; ++k) CUDA_TRY(S.lv_f4[l][k].ensure(cap));
+        CUDA_TRY(S.lv_child[l].ensure(cap)); CUDA_TRY(S.lv_list[l][0].ensure(cap)); CUDA_TRY(S.lv_list[l][1].ensure(cap));
+        LevelBufs& L = S.levels[l];
+        L.ray_o = S.lv_f4[l][0].p; L.ray_d = S.lv_f4[l][1].p; L.hit = S.lv_f4[l][2].p; L.color = S.lv_f4[l][3].p; L.dn_att = S.lv_f4[l][4].p;
+        L.dn_child = S.lv_child[l].p; L.phong_list = S.lv_list[l][0].p; L.diel_list = S.lv_list[l][1].p;
         L.pending = nullptr;
         L.cap = (uint32_t)cap;
     }
-    CUDA_TRY(ctx->l0_pending.ensure(cap0));
-    ctx->levels[0].pending = ctx->l0_pending.p;
+    CUDA_TRY(S.l0_pending.ensure(cap0));
+    S.levels[0].pending = S.l0_pending.p;
     return PGRT_OK;
 }
 
 struct FrameTimer {
-    pgrt_context* ctx; bool on; size_t used = 0;
+    FrameSlot* S; bool on;
     void begin(int cls, int level = 0) {
         if (!on) return;
-        if (used + 2 > ctx->ev_pool.size()) {
-            if (ctx->ev_pool.size() >= 16384) { on = false; return; }
-            for (int k = 0; k < 256; ++k) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
-            ctx->ev_class.resize(ctx->ev_pool.size() / 2); ctx->ev_level.resize(ctx->ev_pool.size() / 2);
+        if (S->ev_used + 2 > S->ev_pool.size()) {
+            if (S->ev_pool.size() >= 16384) { on = false; return; }
+            for (int k = 0; k < 256; ++k) { cudaEvent_t e; cudaEventCreate(&e); S->ev_pool.push_back(e); }
+            S->ev_class.resize(S->ev_pool.size() / 2); S->ev_level.resize(S->ev_pool.size() / 2);
         }
-        ctx->ev_class[used / 2] = cls; ctx->ev_level[used / 2] = level;
-        cudaEventRecord(ctx->ev_pool[used], ctx->stream);
+        S->ev_class[S->ev_used / 2] = cls; S->ev_level[S->ev_used / 2] = level;
+        cudaEventRecord(S->ev_pool[S->ev_used], S->stream);
     }
-    void end() { if (!on) return; cudaEventRecord(ctx->ev_pool[used + 1], ctx->stream); used += 2; }
+    void end() { if (!on) return; cudaEventRecord(S->ev_pool[S->ev_used + 1], S->stream); S->ev_used += 2; }
 };
 
 static int validate_frame(pgrt_context* ctx, const pgrt_render_params* p) {
@@ -511,127 +558,169 @@ static int validate_frame(pgrt_context* ctx, const pgrt_render_params* p) {
     return upload_tables(ctx);
 }
 
+// Enqueues one frame on the slot's stream: every launch, the read-back of the counters and (host destinations) of the
+// frame itself.  Nothing here waits for the GPU once the slot's buffers exist.
 // dest_mode: 0 = full frame (W*H float4), 1 = compact shard buffer, 2 = ids only (geom/prim in d_ids)
-static int render_frame(pgrt_context* ctx, const pgrt_render_params* p, float4* dest, int dest_mode, pgrt_render_stats* stats, int profile) {
+static int enqueue_frame(pgrt_context* ctx, FrameSlot& S) {
+    cudaStream_t st = S.stream;
+    const pgrt_render_params* p = &S.params;
+    const int dest_mode = S.dest_mode, profile = S.profile;
+    float4* dest = S.dest;
+    const int SPP = p->sampling_width * p->sampling_width;
+    const int n_levels = S.n_levels;
+    const uint64_t total_slots = shard_slots(ctx);
+    const uint64_t batch_slots = S.batch_slots;
+    const DevScene sc = ctx->dev_scene();
+    const unsigned trace_grid = ctx->sm_count * 16, shade_grid = ctx->sm_count * 8;
+    const bool dyn = S.dyn;
+    FrameTimer tm{&S, (profile & 1) != 0};
+    const bool count = (profile & 2) != 0;
+    pgrt_render_stats& rs = S.rs;
+    const size_t cap0 = (size_t)batch_slots * SPP;
+    const size_t capn = std::max<size_t>(ctx->min_level_cap, (size_t)(ctx->level_cap_factor * (double)cap0));
+    int rc = ensure_levels(ctx, S, dyn ? 1 : n_levels, cap0, capn);
+    if (rc) return rc;
+    if (dyn) { rc = ensure_pool(ctx, S, capn * (size_t)std::min(n_levels - 1, 4)); if (rc) return rc; }   // one pool replaces the per-level queues
+    if (S.host_dst) CUDA_TRY(S.d_frame.ensure((size_t)ctx->cam.width * ctx->cam.height));
+    S.ev_used = 0; rs.launches = 0; rs.trace_launches = 0; rs.batches = 0;
+    Counters* cnt = S.d_counters.p;
+    CUDA_TRY(cudaEventRecord(S.ev_frame0, st));
+    k_frame_begin<<<1, 64, 0, st>>>(cnt); rs.launches++;
+    for (uint64_t slot0 = 0; slot0 < total_slots; slot0 += batch_slots) {
+        const uint32_t n_slots = (uint32_t)std::min<uint64_t>(batch_slots, total_slots - slot0);
+        const uint32_t n0 = n_slots * (uint32_t)SPP;
+        rs.batches++;
+        k_batch_begin<<<1, 64, 0, st>>>(cnt); rs.launches++;
+        tm.begin(KC_SHADE);
+        k_raygen<<<div_up(n0, 256), 256, 0, st>>>(ctx->cam, *p, ctx->shard, (uint32_t)slot0, n_slots, S.levels[0], cnt); rs.launches++;
+        tm.end();
+        if (dyn) {
+            // level 0 as a wavefront (coherent primary rays), every deeper level inside the persistent kernel
+            const RayPool P = S.pool;
+            LevelBufs Ln = {}; Ln.ray_o = P.ray_o; Ln.ray_d = P.ray_d; Ln.cap = P.cap;
+            tm.begin(KC_TRACE, 0);
+            if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, S.levels[0], 0, cnt);
+            else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, S.levels[0], 0, cnt);
+            rs.launches++; rs.trace_launches++;
+            tm.end();
+            tm.begin(KC_SHADE, 0);
+            k_shade<<<shade_grid, 256, 0, st>>>(sc, *p, 0, S.levels[0], Ln, P, 1, cnt); rs.launches++;
+            tm.end();
+            tm.begin(KC_TRACE, 0);
+            if (count) k_phong<true><<<trace_grid, 128, 0, st>>>(sc, *p, 0, S.levels[0], cnt);
+            else k_phong<false><<<trace_grid, 128, 0, st>>>(sc, *p, 0, S.levels[0], cnt);
+            rs.launches++; rs.trace_launches++;
+            tm.end();
+            tm.begin(KC_TRACE, 1);
+            const size_t smem = (size_t)4 * p->max_depth * (PGRT_WSTACK + 1) * sizeof(uint32_t);   // <= 33.3 KB at max_depth 32
+            if (count) k_secondary<true><<<ctx->secondary_grid, 128, smem, st>>>(sc, *p, S.levels[0], P, cnt);
+            else k_secondary<false><<<ctx->secondary_grid, 128, smem, st>>>(sc, *p, S.levels[0], P, cnt);
+            rs.launches++; rs.trace_launches++;
+            tm.end();
+        } else {
+            for (int l = 0; l < n_levels; ++l) {
+                tm.begin(KC_TRACE, l);
+                if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, S.levels[l], l, cnt);
+                else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, S.levels[l], l, cnt);
+                rs.launches++; rs.trace_launches++;
+                tm.end();
+                if (dest_mode == 2) break;
+                tm.begin(KC_SHADE, l);
+                k_shade<<<shade_grid, 256, 0, st>>>(sc, *p, l, S.levels[l], S.levels[l + 1], S.pool, 0, cnt); rs.launches++;
+                tm.end();
+                tm.begin(KC_TRACE, l);   // Phong = shading preamble + one inline shadow traversal per light
+                if (count) k_phong<true><<<trace_grid, 128, 0, st>>>(sc, *p, l, S.levels[l], cnt);
+                else k_phong<false><<<trace_grid, 128, 0, st>>>(sc, *p, l, S.levels[l], cnt);
+                rs.launches++; rs.trace_launches++;
+                tm.end();
+            }
+        }
+        if (dest_mode == 2) {
+            uint32_t* geom = ctx->d_ids.p; uint32_t* prim = geom + (size_t)ctx->cam.width * ctx->cam.height;
+            k_primary_ids<<<div_up(n_slots, 256), 256, 0, st>>>(sc, ctx->cam, ctx->shard, (uint32_t)slot0, n_slots, SPP, S.levels[0].hit, geom, prim); rs.launches++;
+        } else {
+            tm.begin(KC_SHADE);
+            if (!dyn) for (int l = n_levels - 2; l >= 0; --l) { k_combine<<<shade_grid, 256, 0, st>>>(l, S.levels[l], S.levels[l + 1], cnt); rs.launches++; }
+            k_resolve<<<div_up(n_slots, 256), 256, 0, st>>>(ctx->cam, *p, ctx->shard, (uint32_t)slot0, n_slots, S.levels[0].color, S.host_dst ? S.d_frame.p : dest, dest_mode == 1); rs.launches++;
+            tm.end();
+        }
+        unsigned long long valid_px;
+        {   // primary rays = valid pixels of this batch * S (host-side count; partial tiles hold unused slots)
+            uint64_t v = 0;
+            const uint32_t W = ctx->cam.width, H = ctx->cam.height;
+            for (uint64_t k = slot0 / PGRT_TILE_PIXELS; k < (slot0 + n_slots) / PGRT_TILE_PIXELS; ++k) {
+                const uint64_t t = k * ctx->shard.n_ranks + ctx->shard.rank;
+                if (t >= (uint64_t)ctx->shard.tiles_x * ctx->shard.tiles_y) continue;
+                const uint32_t tx = (uint32_t)(t % ctx->shard.tiles_x), ty = (uint32_t)(t / ctx->shard.tiles_x);
+                const uint32_t w = std::min<uint32_t>(PGRT_TILE_W, W - tx * PGRT_TILE_W), h = std::min<uint32_t>(PGRT_TILE_H, H - ty * PGRT_TILE_H);
+                v += (uint64_t)w * h;
+            }
+            valid_px = v * SPP;
+        }
+        k_batch_end<<<1, 64, 0, st>>>(cnt, valid_px, dyn ? 1 : 0); rs.launches++;
+    }
+    CUDA_TRY(cudaEventRecord(S.ev_frame1, st));
+    CUDA_TRY(cudaMemcpyAsync(S.h_counters, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    if (S.host_dst)   // the memcpy of simpleguidx11.cpp:121-124; overlaps the next frame when the destination is pinned
+        CUDA_TRY(cudaMemcpyAsync(S.host_dst, S.d_frame.p, (size_t)ctx->cam.width * ctx->cam.height * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(S.ev_done, st));
+    LAUNCH_OK();
+    ctx->launches += rs.launches;
+    return PGRT_OK;
+}
+
+static int frame_begin(pgrt_context* ctx, int slot, const pgrt_render_params* p, float4* dest, int dest_mode, float* host_dst, int profile) {
+    if (slot < 0 || slot >= PGRT_MAX_INFLIGHT) return ctx->fail(PGRT_ERR_INVALID, "render: slot out of range");
+    FrameSlot& S = ctx->slots[slot];
+    if (S.busy) return ctx->fail(PGRT_ERR_INVALID, "render: the slot still holds a frame in flight (call pgrt_render_end first)");
     int rc = validate_frame(ctx, p);
     if (rc) return rc;
     cudaSetDevice(ctx->device);
-    cudaStream_t st = ctx->stream;
-    const int S = p->sampling_width * p->sampling_width;
-    const int n_levels = (dest_mode == 2) ? 1 : p->max_depth + 1;
-    const uint64_t total_slots = shard_slots(ctx);
-    uint64_t batch_slots = std::max<uint64_t>(PGRT_TILE_PIXELS, ctx->max_batch_samples / S / PGRT_TILE_PIXELS * PGRT_TILE_PIXELS);
-    batch_slots = std::min(batch_slots, total_slots);
-    const DevScene sc = ctx->dev_scene();
-    const unsigned trace_grid = ctx->sm_count * 16, shade_grid = ctx->sm_count * 8;
-    const bool dyn = p->scheduler == 0 && dest_mode != 2 && n_levels > 1;
-    if (dyn && ctx->secondary_grid == 0) {
+    S.params = *p; S.dest = dest; S.dest_mode = dest_mode; S.host_dst = host_dst; S.profile = profile;
+    const int SPP = p->sampling_width * p->sampling_width;
+    S.n_levels = (dest_mode == 2) ? 1 : p->max_depth + 1;
+    S.dyn = p->scheduler == 0 && dest_mode != 2 && S.n_levels > 1;
+    if (S.dyn && ctx->secondary_grid == 0) {
+        // the persistent kernel is latency-bound and runs beside other frames' kernels (sweep: profiles/r1_sweep_secondary.txt)
         int per_sm = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_secondary<false>, 128, 0));
-        ctx->secondary_grid = ctx->sm_count * std::max(1, std::min(per_sm, 8));
+        int want = 4;
+        if (const char* e = getenv("PGRT_SECONDARY_CTAS_PER_SM")) want = std::max(1, atoi(e));
+        ctx->secondary_grid = ctx->sm_count * std::max(1, std::min(per_sm, want));
     }
-    pgrt_render_stats rs = {};
-    FrameTimer tm{ctx, (profile & 1) != 0};
-    const bool count = (profile & 2) != 0;
+    const uint64_t total_slots = shard_slots(ctx);
+    uint64_t batch_slots = std::max<uint64_t>(PGRT_TILE_PIXELS, ctx->max_batch_samples / SPP / PGRT_TILE_PIXELS * PGRT_TILE_PIXELS);
+    S.batch_slots = std::min(batch_slots, total_slots);
+    S.rs = pgrt_render_stats{};
+    rc = enqueue_frame(ctx, S);
+    if (rc) return rc;
+    S.busy = true;
+    return PGRT_OK;
+}
+
+static int frame_end(pgrt_context* ctx, int slot, pgrt_render_stats* stats) {
+    if (slot < 0 || slot >= PGRT_MAX_INFLIGHT) return ctx->fail(PGRT_ERR_INVALID, "render: slot out of range");
+    FrameSlot& S = ctx->slots[slot];
+    if (!S.busy) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_end: no frame in flight in this slot");
+    cudaSetDevice(ctx->device);
+    S.busy = false;
     for (;;) {
-        const size_t cap0 = (size_t)batch_slots * S;
-        const size_t capn = std::max<size_t>(ctx->min_level_cap, (size_t)(ctx->level_cap_factor * (double)cap0));
-        rc = ensure_levels(ctx, dyn ? 1 : n_levels, cap0, capn);
+        CUDA_TRY(cudaStreamSynchronize(S.stream));
+        if (S.h_counters->watchdog) return ctx->fail(PGRT_ERR_CUDA, "render: internal error in the persistent secondary-ray kernel (mini-stack bound violated)");
+        if (!S.h_counters->overflow) break;
+        // a secondary-ray queue overflowed: render the frame again in smaller batches (rare; sizes are generous)
+        const uint32_t retries = S.rs.overflow_retries + 1;
+        if (S.batch_slots <= PGRT_TILE_PIXELS) return ctx->fail(PGRT_ERR_OVERFLOW, "render: secondary-ray queues overflow at the minimum batch; raise PGRT_MIN_LEVEL_CAP");
+        S.batch_slots = std::max<uint64_t>(PGRT_TILE_PIXELS, S.batch_slots / 2 / PGRT_TILE_PIXELS * PGRT_TILE_PIXELS);
+        S.rs = pgrt_render_stats{}; S.rs.overflow_retries = retries;
+        int rc = enqueue_frame(ctx, S);
         if (rc) return rc;
-        if (dyn) { rc = ensure_pool(ctx, capn * (size_t)std::min(n_levels - 1, 4)); if (rc) return rc; }   // one pool replaces the per-level queues
-        tm.used = 0; rs.launches = 0; rs.trace_launches = 0; rs.batches = 0;
-        Counters* cnt = ctx->d_counters.p;
-        CUDA_TRY(cudaEventRecord(ctx->ev_frame0, st));
-        k_frame_begin<<<1, 64, 0, st>>>(cnt); rs.launches++;
-        for (uint64_t slot0 = 0; slot0 < total_slots; slot0 += batch_slots) {
-            const uint32_t n_slots = (uint32_t)std::min<uint64_t>(batch_slots, total_slots - slot0);
-            const uint32_t n0 = n_slots * (uint32_t)S;
-            rs.batches++;
-            k_batch_begin<<<1, 64, 0, st>>>(cnt); rs.launches++;
-            tm.begin(KC_SHADE);
-            k_raygen<<<div_up(n0, 256), 256, 0, st>>>(ctx->cam, *p, ctx->shard, (uint32_t)slot0, n_slots, ctx->levels[0], cnt); rs.launches++;
-            tm.end();
-            if (dyn) {
-                // level 0 as a wavefront (coherent primary rays), every deeper level inside the persistent kernel
-                const RayPool P = ctx->pool;
-                LevelBufs Ln = {}; Ln.ray_o = P.ray_o; Ln.ray_d = P.ray_d; Ln.cap = P.cap;
-                tm.begin(KC_TRACE, 0);
-                if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, ctx->levels[0], 0, cnt);
-                else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, ctx->levels[0], 0, cnt);
-                rs.launches++; rs.trace_launches++;
-                tm.end();
-                tm.begin(KC_SHADE, 0);
-                k_shade<<<shade_grid, 256, 0, st>>>(sc, *p, 0, ctx->levels[0], Ln, P, 1, cnt); rs.launches++;
-                tm.end();
-                tm.begin(KC_TRACE, 0);
-                if (count) k_phong<true><<<trace_grid, 128, 0, st>>>(sc, *p, 0, ctx->levels[0], cnt);
-                else k_phong<false><<<trace_grid, 128, 0, st>>>(sc, *p, 0, ctx->levels[0], cnt);
-                rs.launches++; rs.trace_launches++;
-                tm.end();
-                tm.begin(KC_TRACE, 1);
-                const size_t smem = (size_t)4 * p->max_depth * (PGRT_WSTACK + 1) * sizeof(uint32_t);   // <= 33.3 KB at max_depth 32
-                if (count) k_secondary<true><<<ctx->secondary_grid, 128, smem, st>>>(sc, *p, ctx->levels[0], P, cnt);
-                else k_secondary<false><<<ctx->secondary_grid, 128, smem, st>>>(sc, *p, ctx->levels[0], P, cnt);
-                rs.launches++; rs.trace_launches++;
-                tm.end();
-            } else {
-                for (int l = 0; l < n_levels; ++l) {
-                    tm.begin(KC_TRACE, l);
-                    if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, ctx->levels[l], l, cnt);
-                    else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, ctx->levels[l], l, cnt);
-                    rs.launches++; rs.trace_launches++;
-                    tm.end();
-                    if (dest_mode == 2) break;
-                    tm.begin(KC_SHADE, l);
-                    k_shade<<<shade_grid, 256, 0, st>>>(sc, *p, l, ctx->levels[l], ctx->levels[l + 1], ctx->pool, 0, cnt); rs.launches++;
-                    tm.end();
-                    tm.begin(KC_TRACE, l);   // Phong = shading preamble + one inline shadow traversal per light
-                    if (count) k_phong<true><<<trace_grid, 128, 0, st>>>(sc, *p, l, ctx->levels[l], cnt);
-                    else k_phong<false><<<trace_grid, 128, 0, st>>>(sc, *p, l, ctx->levels[l], cnt);
-                    rs.launches++; rs.trace_launches++;
-                    tm.end();
-                }
-            }
-            if (dest_mode == 2) {
-                uint32_t* geom = ctx->d_ids.p; uint32_t* prim = geom + (size_t)ctx->cam.width * ctx->cam.height;
-                k_primary_ids<<<div_up(n_slots, 256), 256, 0, st>>>(sc, ctx->cam, ctx->shard, (uint32_t)slot0, n_slots, S, ctx->levels[0].hit, geom, prim); rs.launches++;
-            } else {
-                tm.begin(KC_SHADE);
-                if (!dyn) for (int l = n_levels - 2; l >= 0; --l) { k_combine<<<shade_grid, 256, 0, st>>>(l, ctx->levels[l], ctx->levels[l + 1], cnt); rs.launches++; }
-                k_resolve<<<div_up(n_slots, 256), 256, 0, st>>>(ctx->cam, *p, ctx->shard, (uint32_t)slot0, n_slots, ctx->levels[0].color, dest, dest_mode == 1); rs.launches++;
-                tm.end();
-            }
-            unsigned long long valid_px;
-            {   // primary rays = valid pixels of this batch * S (host-side count; partial tiles hold unused slots)
-                uint64_t v = 0;
-                const uint32_t W = ctx->cam.width, H = ctx->cam.height;
-                for (uint64_t k = slot0 / PGRT_TILE_PIXELS; k < (slot0 + n_slots) / PGRT_TILE_PIXELS; ++k) {
-                    const uint64_t t = k * ctx->shard.n_ranks + ctx->shard.rank;
-                    if (t >= (uint64_t)ctx->shard.tiles_x * ctx->shard.tiles_y) continue;
-                    const uint32_t tx = (uint32_t)(t % ctx->shard.tiles_x), ty = (uint32_t)(t / ctx->shard.tiles_x);
-                    const uint32_t w = std::min<uint32_t>(PGRT_TILE_W, W - tx * PGRT_TILE_W), h = std::min<uint32_t>(PGRT_TILE_H, H - ty * PGRT_TILE_H);
-                    v += (uint64_t)w * h;
-                }
-                valid_px = v * S;
-            }
-            k_batch_end<<<1, 64, 0, st>>>(cnt, valid_px, dyn ? 1 : 0); rs.launches++;
-        }
-        CUDA_TRY(cudaEventRecord(ctx->ev_frame1, st));
-        CUDA_TRY(cudaMemcpyAsync(ctx->h_counters, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-        LAUNCH_OK();
-        CUDA_TRY(cudaStreamSynchronize(st));
-        ctx->launches += rs.launches;
-        if (ctx->h_counters->watchdog) return ctx->fail(PGRT_ERR_CUDA, "render: internal error in the persistent secondary-ray kernel (mini-stack bound violated)");
-        if (!ctx->h_counters->overflow) break;
-        rs.overflow_retries++;
-        if (batch_slots <= PGRT_TILE_PIXELS) return ctx->fail(PGRT_ERR_OVERFLOW, "render: secondary-ray queues overflow at the minimum batch; raise PGRT_MIN_LEVEL_CAP");
-        batch_slots = std::max<uint64_t>(PGRT_TILE_PIXELS, batch_slots / 2 / PGRT_TILE_PIXELS * PGRT_TILE_PIXELS);
     }
-    rs.rays_primary = ctx->h_counters->tot_primary; rs.rays_shadow = ctx->h_counters->tot_shadow;
-    rs.rays_reflection = ctx->h_counters->tot_reflection; rs.rays_refraction = ctx->h_counters->tot_refraction;
-    cudaEventElapsedTime(&rs.frame_ms, ctx->ev_frame0, ctx->ev_frame1);
-    const Counters& hc = *ctx->h_counters;
-    ctx->level_stats_n = n_levels;
+    pgrt_render_stats& rs = S.rs;
+    const Counters& hc = *S.h_counters;
+    rs.rays_primary = hc.tot_primary; rs.rays_shadow = hc.tot_shadow; rs.rays_reflection = hc.tot_reflection; rs.rays_refraction = hc.tot_refraction;
+    cudaEventElapsedTime(&rs.frame_ms, S.ev_frame0, S.ev_frame1);
+    ctx->level_stats_n = S.n_levels;
     for (int l = 0; l <= PGRT_MAX_LEVELS; ++l) {
         pgrt_level_stats& ls = ctx->level_stats[l];
         ls = pgrt_level_stats{};
@@ -640,36 +729,62 @@ static int render_frame(pgrt_context* ctx, const pgrt_render_params* p, float4* 
         rs.nodes_visited += ls.nodes + ls.shadow_nodes; rs.tris_tested += ls.tris + ls.shadow_tris;
         rs.max_nodes_per_ray = std::max(rs.max_nodes_per_ray, std::max(ls.max_nodes, ls.shadow_max_nodes));
     }
-    if (tm.on || tm.used) {
-        for (size_t k = 0; k < tm.used; k += 2) {
-            float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
-            pgrt_level_stats& ls = ctx->level_stats[ctx->ev_level[k / 2]];
-            if (ctx->ev_class[k / 2] == KC_TRACE) { rs.trace_ms += ms; ls.trace_ms += ms; } else { rs.shade_ms += ms; ls.shade_ms += ms; }
-        }
+    for (size_t k = 0; k < S.ev_used; k += 2) {
+        float ms = 0.f; cudaEventElapsedTime(&ms, S.ev_pool[k], S.ev_pool[k + 1]);
+        pgrt_level_stats& ls = ctx->level_stats[S.ev_level[k / 2]];
+        if (S.ev_class[k / 2] == KC_TRACE) { rs.trace_ms += ms; ls.trace_ms += ms; } else { rs.shade_ms += ms; ls.shade_ms += ms; }
     }
     if (stats) *stats = rs;
     return PGRT_OK;
+}
+
+static int render_frame(pgrt_context* ctx, const pgrt_render_params* p, float4* dest, int dest_mode, float* host_dst, pgrt_render_stats* stats, int profile) {
+    int rc = frame_begin(ctx, 0, p, dest, dest_mode, host_dst, profile);
+    if (rc) return rc;
+    return frame_end(ctx, 0, stats);
 }
 
 extern "C" int pgrt_render_device(pgrt_context* ctx, const pgrt_render_params* p, void* rgba_device, pgrt_render_stats* stats, int32_t profile) {
     CHECK_CTX(ctx);
     if (!rgba_device) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_device: null destination");
     if (ctx->shard.n_ranks != 1) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_device: context is sharded; use pgrt_render_shard_device");
-    return render_frame(ctx, p, (float4*)rgba_device, 0, stats, profile);
+    return render_frame(ctx, p, (float4*)rgba_device, 0, nullptr, stats, profile);
 }
 
 extern "C" int pgrt_render(pgrt_context* ctx, const pgrt_render_params* p, float* rgba_host, pgrt_render_stats* stats, int32_t profile) {
     CHECK_CTX(ctx);
     if (!rgba_host) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render: null destination");
     if (ctx->shard.n_ranks != 1) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render: context is sharded; use pgrt_render_shard_device");
-    if (!ctx->cam_set) return ctx->fail(PGRT_ERR_INVALID, "render: pgrt_set_camera has not been called");
+    return render_frame(ctx, p, nullptr, 0, rgba_host, stats, profile);
+}
+
+// ---- pipelined frames
+extern "C" int pgrt_render_begin(pgrt_context* ctx, const pgrt_render_params* p, float* rgba_host, int32_t slot, int32_t profile) {
+    CHECK_CTX(ctx);
+    if (!rgba_host) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_begin: null destination");
+    if (ctx->shard.n_ranks != 1) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_begin: context is sharded; use pgrt_render_shard_device_begin");
+    return frame_begin(ctx, slot, p, nullptr, 0, rgba_host, profile);
+}
+extern "C" int pgrt_render_device_begin(pgrt_context* ctx, const pgrt_render_params* p, void* rgba_device, int32_t slot, int32_t profile) {
+    CHECK_CTX(ctx);
+    if (!rgba_device) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_device_begin: null destination");
+    if (ctx->shard.n_ranks != 1) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_device_begin: context is sharded; use pgrt_render_shard_device_begin");
+    return frame_begin(ctx, slot, p, (float4*)rgba_device, 0, nullptr, profile);
+}
+extern "C" int pgrt_render_shard_device_begin(pgrt_context* ctx, const pgrt_render_params* p, void* shard_rgba_device, int32_t slot, int32_t profile) {
+    CHECK_CTX(ctx);
+    if (!shard_rgba_device) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_shard_device_begin: null destination");
+    return frame_begin(ctx, slot, p, (float4*)shard_rgba_device, 1, nullptr, profile);
+}
+extern "C" int pgrt_render_end(pgrt_context* ctx, int32_t slot, pgrt_render_stats* stats) {
+    CHECK_CTX(ctx);
+    return frame_end(ctx, slot, stats);
+}
+extern "C" int pgrt_stream_wait_slot(pgrt_context* ctx, int32_t slot, void* cuda_stream) {
+    CHECK_CTX(ctx);
+    if (slot < 0 || slot >= PGRT_MAX_INFLIGHT) return ctx->fail(PGRT_ERR_INVALID, "pgrt_stream_wait_slot: slot out of range");
     cudaSetDevice(ctx->device);
-    const size_t npx = (size_t)ctx->cam.width * ctx->cam.height;
-    CUDA_TRY(ctx->d_frame.ensure(npx));
-    int rc = render_frame(ctx, p, ctx->d_frame.p, 0, stats, profile);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(rgba_host, ctx->d_frame.p, npx * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)cuda_stream, ctx->slots[slot].ev_done, 0));
     return PGRT_OK;
 }
 
@@ -694,7 +809,7 @@ extern "C" int pgrt_primary_ids(pgrt_context* ctx, const pgrt_render_params* p, 
     const size_t npx = (size_t)ctx->cam.width * ctx->cam.height;
     CUDA_TRY(ctx->d_ids.ensure(2 * npx));
     CUDA_TRY(cudaMemsetAsync(ctx->d_ids.p, 0xFF, 2 * npx * sizeof(uint32_t), ctx->stream));
-    int rc = render_frame(ctx, p, nullptr, 2, nullptr, 0);
+    int rc = render_frame(ctx, p, nullptr, 2, nullptr, nullptr, 0);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(geom_host, ctx->d_ids.p, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(prim_host, ctx->d_ids.p + npx, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -705,16 +820,26 @@ extern "C" int pgrt_primary_ids(pgrt_context* ctx, const pgrt_render_params* p, 
 extern "C" int pgrt_render_shard_device(pgrt_context* ctx, const pgrt_render_params* p, void* shard_rgba_device, pgrt_render_stats* stats, int32_t profile) {
     CHECK_CTX(ctx);
     if (!shard_rgba_device) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_shard_device: null destination");
-    return render_frame(ctx, p, (float4*)shard_rgba_device, 1, stats, profile);
+    return render_frame(ctx, p, (float4*)shard_rgba_device, 1, nullptr, stats, profile);
 }
+
+static int untile_on(pgrt_context* ctx, const void* gathered_device, int32_t n_ranks, void* rgba_device, cudaStream_t st);
 
 extern "C" int pgrt_untile(pgrt_context* ctx, const void* gathered_device, int32_t n_ranks, void* rgba_device) {
     CHECK_CTX(ctx);
+    return untile_on(ctx, gathered_device, n_ranks, rgba_device, ctx->stream);
+}
+extern "C" int pgrt_untile_on_stream(pgrt_context* ctx, const void* gathered_device, int32_t n_ranks, void* rgba_device, void* cuda_stream) {
+    CHECK_CTX(ctx);
+    return untile_on(ctx, gathered_device, n_ranks, rgba_device, (cudaStream_t)cuda_stream);
+}
+
+static int untile_on(pgrt_context* ctx, const void* gathered_device, int32_t n_ranks, void* rgba_device, cudaStream_t st) {
     if (!gathered_device || !rgba_device || n_ranks < 1 || !ctx->cam_set) return ctx->fail(PGRT_ERR_INVALID, "pgrt_untile: bad arguments");
     cudaSetDevice(ctx->device);
     const uint64_t tiles = (uint64_t)ctx->shard.tiles_x * ctx->shard.tiles_y;
     const uint32_t spr = (uint32_t)((tiles + n_ranks - 1) / n_ranks * PGRT_TILE_PIXELS);
-    k_untile<<<div_up((size_t)spr * n_ranks, 256), 256, 0, ctx->stream>>>(ctx->cam, n_ranks, ctx->shard.tiles_x, ctx->shard.tiles_y, spr, (const float4*)gathered_device, (float4*)rgba_device);
+    k_untile<<<div_up((size_t)spr * n_ranks, 256), 256, 0, st>>>(ctx->cam, n_ranks, ctx->shard.tiles_x, ctx->shard.tiles_y, spr, (const float4*)gathered_device, (float4*)rgba_device);
     ctx->launches++;
     LAUNCH_OK();
     return PGRT_OK;

@@ -405,9 +405,12 @@ __global__ void __launch_bounds__(256) k_combine(int level, LevelBufs L, LevelBu
 // ever holds more than 64 entries (2 children x 32 lanes): PGRT_WSTACK per level is exact, not a guess.
 // No warp ever waits for another one: there is no queue to poll and nothing to time out.
 #define PGRT_WSTACK 64
+#ifndef PGRT_SEC_MIN_BLOCKS
+#define PGRT_SEC_MIN_BLOCKS 4     // register cap of k_secondary = 65536 / (128 * this)
+#endif
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_secondary(DevScene sc, pgrt_render_params p, LevelBufs L0, RayPool P, Counters* cnt) {
+__global__ void __launch_bounds__(128, PGRT_SEC_MIN_BLOCKS) k_secondary(DevScene sc, pgrt_render_params p, LevelBufs L0, RayPool P, Counters* cnt) {
     extern __shared__ uint32_t pgrt_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_lv = p.max_depth;                                   // rays exist at levels 1 .. max_depth

@@ -80,6 +80,13 @@ __device__ __forceinline__ Col4 mix_srgb(Col4 c0, Col4 c1, float alpha) {
 
 // ---- Raytracer::gamma (raytracer.cpp:439-446)
 __device__ __forceinline__ Col4 gamma_correct(Col4 in, float gamma_level) {
+    if (gamma_level == 0.5f) {
+        // the slider default (raytracer.cpp:450): pow(c, 0.5) correctly rounded IS sqrt(c) correctly rounded (NaN for c < 0
+        // on both; -0 squares to +0 either way), and sqrtf is IEEE here (-prec-sqrt=true); six double pow per pixel saved
+        const float sb = sqrtf(in.b), sg = sqrtf(in.g), sr = sqrtf(in.r);
+        Col4 o; o.r = sb * sb; o.g = sg * sg; o.b = sr * sr; o.a = 1.0f;
+        return o;
+    }
     const float b = f_powf(in.b, gamma_level) * f_powf(in.b, gamma_level);
     const float g = f_powf(in.g, gamma_level) * f_powf(in.g, gamma_level);
     const float r = f_powf(in.r, gamma_level) * f_powf(in.r, gamma_level);

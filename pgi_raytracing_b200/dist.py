@@ -75,27 +75,51 @@ def gather_shards(shard, group=None, dst: int = 0):
 
 
 class ShardedRenderer:
-    """One rank of a tile-sharded render: ``render()`` = local tiles -> gather -> (rank 0) un-tile."""
+    """One rank of a tile-sharded render.  ``begin(k)`` enqueues this rank's tiles of frame k in slot k % depth and,
+    on the communication stream (torch's current stream), the gather to rank 0 and the un-tile; ``end(k)`` collects
+    the stats.  With depth > 1 the gather of one frame overlaps the rendering of the next."""
 
-    def __init__(self, raytracer, rank: int, world: int, device):
+    def __init__(self, raytracer, rank: int, world: int, device, depth: int = 1):
         import torch
 
-        self.rt, self.rank, self.world, self.device = raytracer, rank, world, device
+        self.rt, self.rank, self.world, self.device, self.depth = raytracer, rank, world, device, depth
         raytracer.set_shard(rank, world)
         self.n_slots = raytracer.shard_pixels()
-        self.shard = torch.zeros((self.n_slots, 4), dtype=torch.float32, device=device)
         self.frame = torch.zeros((raytracer.height, raytracer.width, 4), dtype=torch.float32, device=device) if rank == 0 else None
-        self._gathered = torch.empty((world, self.n_slots, 4), dtype=torch.float32, device=device) if (rank == 0 and world > 1) else None
+        self.shards = [torch.zeros((self.n_slots, 4), dtype=torch.float32, device=device) for _ in range(depth)]
+        self.gathered = [torch.empty((world, self.n_slots, 4), dtype=torch.float32, device=device) if (rank == 0 and world > 1) else None
+                         for _ in range(depth)]
+        self.slot_streams = [torch.cuda.ExternalStream(raytracer.slot_stream(i), device=device) for i in range(depth)]
+        self.comm_done = [None] * depth
+        torch.cuda.synchronize(device)
 
-    def render(self, params=None, profile=False):
+    def begin(self, k: int, params=None, profile: int = 0, before=None):
+        """``before(stream)``: optional work to enqueue on the slot's stream ahead of the frame (bench: the L2 flush)."""
+        import torch
         import torch.distributed as dist
 
-        if self.world == 1:   # nothing to gather: resolve straight into the frame
-            return self.rt.render_device(self.frame.data_ptr(), params, profile=profile)
-        st = self.rt.render_shard_device(self.shard.data_ptr(), params, profile=profile)
+        s = k % self.depth
+        comm = torch.cuda.current_stream(self.device)
+        if self.comm_done[s] is not None:          # the slot's shard buffer is free once its last gather has run
+            self.slot_streams[s].wait_event(self.comm_done[s])
+        if before is not None:
+            before(self.slot_streams[s])
+        if self.world == 1:                          # nothing to gather: resolve straight into the frame
+            self.rt.render_begin(s, params, device_ptr=self.frame.data_ptr(), profile=profile)
+            return
+        self.rt.render_begin(s, params, shard_ptr=self.shards[s].data_ptr(), profile=profile)
+        self.rt.stream_wait_slot(s, comm.cuda_stream)
         if self.rank == 0:
-            dist.gather(self.shard, list(self._gathered.unbind(0)), dst=0)
-            self.rt.untile(self._gathered.data_ptr(), self.world, self.frame.data_ptr())
+            dist.gather(self.shards[s], list(self.gathered[s].unbind(0)), dst=0)
+            self.rt.untile(self.gathered[s].data_ptr(), self.world, self.frame.data_ptr(), comm.cuda_stream)
         else:
-            dist.gather(self.shard, None, dst=0)
-        return st
+            dist.gather(self.shards[s], None, dst=0)
+        ev = torch.cuda.Event(); ev.record(comm)
+        self.comm_done[s] = ev
+
+    def end(self, k: int) -> dict:
+        return self.rt.render_end(k % self.depth)
+
+    def render(self, params=None, profile=False):
+        self.begin(0, params, int(profile))
+        return self.end(0)

@@ -22,7 +22,7 @@ struct Tree {
     std::vector<float4> b0, b1; std::vector<uint32_t> count, leaf_tri;
     std::vector<float4> nodes, tris;
     std::vector<float> pos;
-    uint32_t n = 0, n_nodes = 0, depth = 0, root = 0;
+    uint32_t n = 0, n_nodes = 0, depth = 0, root = 0; int layout = PGRT_LAYOUT_Q8;
     double sah = 0;
 };
 
@@ -43,8 +43,10 @@ void tri_box(const float* p, float lo[3], float hi[3]) {
 
 extern "C" {
 
-void* emul_build(const float* pos, uint32_t n, int builder /*0 = PLOC, 1 = median split*/) {
+void* emul_build(const float* pos, uint32_t n, int builder /*0 = PLOC, 1 = median split*/, int layout /*PGRT_LAYOUT_Q8 / _F32*/) {
     Tree* t = new Tree();
+    t->layout = layout;
+    const size_t node_f4 = layout == PGRT_LAYOUT_F32 ? PGRT_NODE_F4_F32 : PGRT_NODE_F4_Q8;
     t->n = n; t->pos.assign(pos, pos + 9 * (size_t)n);
     if (n == 0) return t;
     // Morton order (k_scene_bounds + k_morton + radix sort, restated)
@@ -126,7 +128,7 @@ void* emul_build(const float* pos, uint32_t n, int builder /*0 = PLOC, 1 = media
     }
     // ---- collapse, breadth first (what k_collapse does with one thread per wide node)
     Bvh2View v{t->b0.data(), t->b1.data(), t->count.data(), t->leaf_tri.data(), n};
-    t->nodes.resize(5 * (size_t)std::max<uint32_t>(n, 1)); t->tris.resize(3 * (size_t)n);
+    t->nodes.resize(node_f4 * (size_t)std::max<uint32_t>(n, 1)); t->tris.resize(3 * (size_t)n);
     std::vector<std::pair<uint32_t, uint32_t>> cur{{t->root, 0u}}, nxt;
     uint32_t node_count = 1, tri_count = 0;
     while (!cur.empty()) {
@@ -138,7 +140,7 @@ void* emul_build(const float* pos, uint32_t n, int builder /*0 = PLOC, 1 = media
             const uint32_t cb = node_count, tb = tri_count;
             node_count += ni; tri_count += nt;
             uint32_t ic[8]; float sah;
-            bvh8_emit(v, b2, w, cb, tb, t->pos.data(), &t->nodes[5 * (size_t)wi], t->tris.data(), ic, sah);
+            bvh8_emit(v, b2, w, cb, tb, t->pos.data(), &t->nodes[node_f4 * (size_t)wi], t->tris.data(), ic, sah, layout);
             t->sah += sah;
             for (int r = 0; r < ni; ++r) nxt.push_back({ic[r], cb + r});
         }
@@ -169,7 +171,8 @@ void emul_trace(void* h, const float* rays, uint64_t n, float* out, uint32_t* st
             best.t = r[7]; best.u = 0; best.v = 0; best.tri = PGRT_INVALID_ID;
             for (uint32_t k = 0; k < t->n; ++k) tri_test(t->tris.data(), k, O, D, r[3], r[7], best);
         } else {
-            best = trace_closest8<true>(t->nodes.data(), t->tris.data(), t->n, O, D, r[3], r[7], tc);
+            best = t->layout == PGRT_LAYOUT_F32 ? trace_closest8f<true>(t->nodes.data(), t->tris.data(), t->n, O, D, r[3], r[7], tc)
+                                                : trace_closest8<true>(t->nodes.data(), t->tris.data(), t->n, O, D, r[3], r[7], tc);
         }
         out[4 * i] = best.t; out[4 * i + 1] = best.u; out[4 * i + 2] = best.v; memcpy(&out[4 * i + 3], &best.tri, 4);
         if (stats) { stats[2 * i] = tc.nodes; stats[2 * i + 1] = tc.tris; }
@@ -179,7 +182,7 @@ void emul_trace(void* h, const float* rays, uint64_t n, float* out, uint32_t* st
 // structural check: every node's decoded child boxes contain the true boxes below; returns the number of violations
 uint64_t emul_check(void* h) {
     Tree* t = (Tree*)h;
-    if (t->n == 0) return 0;
+    if (t->n == 0 || t->layout != PGRT_LAYOUT_Q8) return 0;   // the structural walk decodes the quantised layout
     uint64_t bad = 0;
     std::vector<uint8_t> seen(t->n, 0);
     // exact box of the subtree under wide node wi, while checking each decoded slot box against it

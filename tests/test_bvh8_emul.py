@@ -27,7 +27,7 @@ def emul():
         subprocess.check_call([cxx, "-O2", "-std=c++17", "-mavx2", "-mfma", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
                                "-I/usr/local/cuda/include", "-o", LIB, SRC])
     lib = C.CDLL(LIB)
-    lib.emul_build.restype = C.c_void_p; lib.emul_build.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
+    lib.emul_build.restype = C.c_void_p; lib.emul_build.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int]
     lib.emul_free.argtypes = [C.c_void_p]
     lib.emul_nodes.restype = C.c_uint32; lib.emul_nodes.argtypes = [C.c_void_p]
     lib.emul_depth.restype = C.c_uint32; lib.emul_depth.argtypes = [C.c_void_p]
@@ -54,6 +54,9 @@ def random_rays(pos, n, seed):
     d[:50, 0] = 0.0; d[50:100, 1] = 0.0; d[100:150, 2] = 0.0; d[150:160, :2] = 0.0      # axis-parallel rays
     org[160:400] = tgt[160:400]                                                           # origins inside the scene (secondary-like)
     d[160:400] = rng.normal(size=(240, 3))
+    far = slice(500, min(700, n)); nf = max(0, min(700, n) - 500)                         # far origins: plane*idir - O*idir cancels
+    org[far] = tgt[far] + rng.normal(size=(nf, 3)) * ext * 40.0
+    d[far] = (tgt[far] - org[far]) * rng.uniform(0.5, 2.0, (nf, 1))
     rays = np.zeros((n, 8), np.float32)
     rays[:, :3] = org; rays[:, 3] = 0.01; rays[:, 4:7] = d; rays[:, 7] = np.finfo(np.float32).max
     rays[400:500, 7] = rng.uniform(0.2, 1.5, 100)                                         # bounded tfar (shadow-like)
@@ -75,9 +78,10 @@ CASES = {
 
 @pytest.mark.parametrize("name", list(CASES))
 @pytest.mark.parametrize("builder", [0, 1])
-def test_wide_tree_structure_and_hits(emul, name, builder):
+@pytest.mark.parametrize("layout", [0, 1])          # 0 = 80-B quantised nodes, 1 = 208-B float planes
+def test_wide_tree_structure_and_hits(emul, name, builder, layout):
     pos = scene_pos(CASES[name]())
-    h = emul.emul_build(pos.ctypes.data, pos.shape[0], builder)
+    h = emul.emul_build(pos.ctypes.data, pos.shape[0], builder, layout)
     try:
         assert emul.emul_check(h) == 0                       # every triangle once, decoded boxes conservative, meta consistent
         assert emul.emul_depth(h) <= 32                      # PGRT_STACK8 = 40 entries
@@ -100,7 +104,12 @@ def test_duplicates_and_degenerates(emul):
     sheet[:, [0, 3, 6]] = rng.uniform(-50, 50, (200, 3)); sheet[:, [1, 4, 7]] = rng.uniform(-50, 50, (200, 3)); sheet[:, [2, 5, 8]] = 7.0
     degenerate = np.repeat(rng.uniform(-50, 50, (20, 3)).astype(np.float32), 3, axis=0).reshape(20, 9)
     pos = np.ascontiguousarray(np.concatenate([base, base[:100], sheet, degenerate]).astype(np.float32))
-    h = emul.emul_build(pos.ctypes.data, pos.shape[0], 0)
+    for layout in (0, 1):
+        h = emul.emul_build(pos.ctypes.data, pos.shape[0], 0, layout)
+        _check_degenerates(emul, h, pos)
+
+
+def _check_degenerates(emul, h, pos):
     try:
         assert emul.emul_check(h) == 0
         rays = random_rays(pos, 1200, seed=4)
@@ -114,7 +123,7 @@ def test_duplicates_and_degenerates(emul):
 
 def test_ploc_tree_is_better_than_median_split(emul):
     pos = scene_pos(scenes.cornell_like())
-    h0 = emul.emul_build(pos.ctypes.data, pos.shape[0], 0); h1 = emul.emul_build(pos.ctypes.data, pos.shape[0], 1)
+    h0 = emul.emul_build(pos.ctypes.data, pos.shape[0], 0, 0); h1 = emul.emul_build(pos.ctypes.data, pos.shape[0], 1, 0)
     try:
         assert emul.emul_sah(h0) < emul.emul_sah(h1)
     finally:

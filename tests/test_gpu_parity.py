@@ -275,6 +275,33 @@ def test_render_is_deterministic_and_batching_invariant(P, cornell, monkeypatch)
     assert (sa["shadow"], sa["reflection"], sa["refraction"]) == (sc_["shadow"], sc_["reflection"], sc_["refraction"])
 
 
+def test_pipelined_frames_equal_synchronous_frames(P, avenger):
+    """pgrt_render_begin / pgrt_render_end: four frames in flight in four slots (own streams, queues, counters) give the
+    frames and ray counts of four synchronous renders; slots are reusable; a busy slot refuses a second frame."""
+    import torch
+    sc, rt, o = avenger
+    plist = [dict(sampling_width=1, jitter=0, aperture=0.0, max_depth=10), dict(sampling_width=2, seed=4), dict(seed=9, max_depth=3), dict(seed=11, scheduler=1)]
+    ref = [rt.render(p) for p in plist]
+    bufs = [torch.empty((rt.height, rt.width, 4), dtype=torch.float32).pin_memory() for _ in plist]
+    for rnd in range(2):
+        for k, p in enumerate(plist):
+            rt.render_begin(k, p, host_ptr=bufs[k].data_ptr())
+        with pytest.raises(P.PgrtError):
+            rt.render_begin(1, plist[1], host_ptr=bufs[1].data_ptr())
+        for k in reversed(range(len(plist))):
+            st = rt.render_end(k)
+            assert np.array_equal(bufs[k].numpy(), ref[k][0], equal_nan=True), (rnd, k)
+            assert [st[x] for x in ("primary", "shadow", "reflection", "refraction")] == [ref[k][1][x] for x in ("primary", "shadow", "reflection", "refraction")]
+            bufs[k].zero_()
+    with pytest.raises(P.PgrtError):
+        rt.render_end(0)                       # nothing in flight
+    dev = torch.zeros((rt.height, rt.width, 4), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    rt.render_begin(2, plist[0], device_ptr=dev.data_ptr()); rt.render_end(2)
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.cpu().numpy(), ref[0][0], equal_nan=True)
+
+
 def test_schedulers_agree_bit_for_bit(P, cornell, avenger):
     """The persistent dynamic scheduler (continuation-passing combine, no level barrier) and the level-synchronous
     wavefront evaluate the same tree with the same arithmetic: frames and ray counts must be identical."""
