@@ -166,6 +166,18 @@ int pgrt_render_device(pgrt_context* ctx, const pgrt_render_params* p, void* rgb
 int pgrt_render_begin(pgrt_context* ctx, const pgrt_render_params* p, float* rgba_host, int32_t slot, int32_t profile);
 int pgrt_render_device_begin(pgrt_context* ctx, const pgrt_render_params* p, void* rgba_device, int32_t slot, int32_t profile);
 int pgrt_render_shard_device_begin(pgrt_context* ctx, const pgrt_render_params* p, void* shard_rgba_device, int32_t slot, int32_t profile);
+/* sharded context, full-frame destination: this rank's tiles are stored at their final place (y*width + x) of a frame
+ * that may live on ANOTHER GPU (a peer-mapped pointer: CUDA IPC / NVLink).  The resolve kernel then IS the gather: no
+ * collective moves pixels; the caller only needs a completion barrier before rank 0 reads the frame. */
+/* frames shared between the processes of one box: rank 0 allocates and exports, the others import (cudaIpc*; the
+ * mapping is opened from the importing context's own device, so its kernels reach the memory over NVLink) */
+int pgrt_frame_alloc(pgrt_context* ctx, uint64_t bytes, void** device_ptr);
+int pgrt_frame_free(pgrt_context* ctx, void* device_ptr);
+int pgrt_frame_export(pgrt_context* ctx, void* device_ptr, uint8_t handle[64]);
+int pgrt_frame_import(pgrt_context* ctx, const uint8_t handle[64], void** device_ptr);
+int pgrt_frame_unmap(pgrt_context* ctx, void* device_ptr);
+int pgrt_enable_peer_access(pgrt_context* ctx, int32_t peer_device);   /* let this context's kernels store into memory of `peer_device` */
+int pgrt_render_shard_to_frame_begin(pgrt_context* ctx, const pgrt_render_params* p, void* frame_device, int32_t slot, int32_t profile);
 int pgrt_render_end(pgrt_context* ctx, int32_t slot, pgrt_render_stats* stats);
 void* pgrt_slot_stream(pgrt_context* ctx, int32_t slot);                          /* cudaStream_t of a slot (slot 0 = pgrt_set_stream's) */
 int pgrt_stream_wait_slot(pgrt_context* ctx, int32_t slot, void* cuda_stream);    /* make `cuda_stream` wait for the slot's frame        */
@@ -178,7 +190,8 @@ int pgrt_primary_ids(pgrt_context* ctx, const pgrt_render_params* p, uint32_t* g
 /* ---- image-tile sharding (one process per GPU): this context renders tiles t with t % n_ranks == rank of the
  *      32x8-pixel tile grid.  pgrt_render_shard_device writes the compact per-rank buffer
  *      (pgrt_shard_pixels * 4 floats); pgrt_untile scatters n_ranks such buffers (concatenated, rank-major, each
- *      pgrt_shard_pixels long) into the full frame.  No data-path collective lives here: the gather between is NCCL. */
+ *      pgrt_shard_pixels long) into the full frame.  No data-path collective lives here: the gather between is NCCL.
+ *      pgrt_render_shard_to_frame_begin (below) skips both: tiles go straight into rank 0's frame over NVLink. */
 int pgrt_set_shard(pgrt_context* ctx, int32_t rank, int32_t n_ranks);
 uint64_t pgrt_shard_pixels(const pgrt_context* ctx);   /* padded pixel slots per rank (same on every rank) */
 int pgrt_render_shard_device(pgrt_context* ctx, const pgrt_render_params* p, void* shard_rgba_device, pgrt_render_stats* stats, int32_t profile);

@@ -74,6 +74,13 @@ SYMBOLS = {
     "pgrt_render_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),
     "pgrt_render_device_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),
     "pgrt_render_shard_device_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),
+    "pgrt_frame_alloc": (C.c_int, [_VP, _U64, C.POINTER(_VP)]),
+    "pgrt_frame_free": (C.c_int, [_VP, _VP]),
+    "pgrt_frame_export": (C.c_int, [_VP, _VP, C.c_char_p]),
+    "pgrt_frame_import": (C.c_int, [_VP, C.c_char_p, C.POINTER(_VP)]),
+    "pgrt_frame_unmap": (C.c_int, [_VP, _VP]),
+    "pgrt_enable_peer_access": (C.c_int, [_VP, _I32]),
+    "pgrt_render_shard_to_frame_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),
     "pgrt_render_end": (C.c_int, [_VP, _I32, C.POINTER(RenderStats)]),
     "pgrt_slot_stream": (_VP, [_VP, _I32]),
     "pgrt_stream_wait_slot": (C.c_int, [_VP, _I32, _VP]),

@@ -146,10 +146,14 @@ class Raytracer:
         return self._stats(rs)
 
     # ---- pipelined frames (pgrt_render*_begin / pgrt_render_end): up to MAX_INFLIGHT frames in flight
-    def render_begin(self, slot: int, params=None, *, host_ptr: int = 0, device_ptr: int = 0, shard_ptr: int = 0, profile: int = 0):
-        """Enqueue one frame in ``slot`` and return without waiting for the GPU.  Exactly one destination."""
+    def render_begin(self, slot: int, params=None, *, host_ptr: int = 0, device_ptr: int = 0, shard_ptr: int = 0, frame_ptr: int = 0,
+                     profile: int = 0):
+        """Enqueue one frame in ``slot`` and return without waiting for the GPU.  Exactly one destination
+        (``frame_ptr``: sharded context, tiles stored at their final place of a possibly peer-mapped full frame)."""
         p = self._params(params)
-        if host_ptr:
+        if frame_ptr:
+            rc = self.lib.pgrt_render_shard_to_frame_begin(self.h, C.byref(p), C.c_void_p(frame_ptr), slot, int(profile))
+        elif host_ptr:
             rc = self.lib.pgrt_render_begin(self.h, C.byref(p), C.c_void_p(host_ptr), slot, int(profile))
         elif device_ptr:
             rc = self.lib.pgrt_render_device_begin(self.h, C.byref(p), C.c_void_p(device_ptr), slot, int(profile))
@@ -161,6 +165,31 @@ class Raytracer:
         rs = L.RenderStats()
         self._check(self.lib.pgrt_render_end(self.h, slot, C.byref(rs)))
         return self._stats(rs)
+
+    # ---- frames shared between the processes of one box (CUDA IPC)
+    def frame_alloc(self, nbytes: int) -> int:
+        ptr = C.c_void_p()
+        self._check(self.lib.pgrt_frame_alloc(self.h, nbytes, C.byref(ptr)))
+        return int(ptr.value)
+
+    def frame_free(self, ptr: int):
+        self._check(self.lib.pgrt_frame_free(self.h, C.c_void_p(ptr)))
+
+    def frame_export(self, ptr: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.pgrt_frame_export(self.h, C.c_void_p(ptr), buf))
+        return buf.raw
+
+    def frame_import(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        self._check(self.lib.pgrt_frame_import(self.h, handle, C.byref(ptr)))
+        return int(ptr.value)
+
+    def frame_unmap(self, ptr: int):
+        self._check(self.lib.pgrt_frame_unmap(self.h, C.c_void_p(ptr)))
+
+    def enable_peer_access(self, peer_device: int):
+        self._check(self.lib.pgrt_enable_peer_access(self.h, peer_device))
 
     def slot_stream(self, slot: int) -> int:
         return int(self.lib.pgrt_slot_stream(self.h, slot) or 0)

@@ -112,6 +112,7 @@ struct pgrt_context {
     // latency-bound tail of one frame (k_secondary) and its device->host copy overlap the next frame's primary work
     FrameSlot slots[PGRT_MAX_INFLIGHT];
     int secondary_grid = 0;
+    bool fuse_raygen = true;          // PGRT_FUSE_RAYGEN=0 restores the stored level-0 ray queue (k_raygen)
     DevBuf<uint32_t> d_ids;
     uint32_t* h_pin = nullptr;        // pinned scratch for small read-backs of the build
     size_t max_batch_samples = (size_t)1 << 23;
@@ -170,6 +171,7 @@ extern "C" int pgrt_create(pgrt_context** out, int device) {
     }
     ctx->stream = ctx->slots[0].stream;
     if (cudaMallocHost((void**)&ctx->h_pin, 256) != cudaSuccess) { pgrt_destroy(ctx); return PGRT_ERR_CUDA; }
+    if (const char* e = getenv("PGRT_FUSE_RAYGEN")) ctx->fuse_raygen = atoi(e) != 0;
     if (const char* e = getenv("PGRT_MAX_BATCH_SAMPLES")) ctx->max_batch_samples = std::max<size_t>(256, strtoull(e, nullptr, 10));
     if (const char* e = getenv("PGRT_MIN_LEVEL_CAP")) ctx->min_level_cap = std::max<size_t>(64, strtoull(e, nullptr, 10));
     if (const char* e = getenv("PGRT_LEVEL_CAP_FACTOR")) ctx->level_cap_factor = std::max(0.01, atof(e));
@@ -590,25 +592,29 @@ static int enqueue_frame(pgrt_context* ctx, FrameSlot& S) {
         const uint32_t n_slots = (uint32_t)std::min<uint64_t>(batch_slots, total_slots - slot0);
         const uint32_t n0 = n_slots * (uint32_t)SPP;
         rs.batches++;
-        k_batch_begin<<<1, 64, 0, st>>>(cnt); rs.launches++;
-        tm.begin(KC_SHADE);
-        k_raygen<<<div_up(n0, 256), 256, 0, st>>>(ctx->cam, *p, ctx->shard, (uint32_t)slot0, n_slots, S.levels[0], cnt); rs.launches++;
-        tm.end();
+        k_batch_begin<<<1, 64, 0, st>>>(cnt, n0); rs.launches++;
+        Gen0 g0; g0.cam = ctx->cam; g0.sh = ctx->shard; g0.slot0 = (uint32_t)slot0; g0.n_slots = n_slots; g0.spp = SPP; g0.on = ctx->fuse_raygen ? 1 : 0;
+        Gen0 gN = g0; gN.on = 0;
+        if (!g0.on) {
+            tm.begin(KC_SHADE);
+            k_raygen<<<div_up(n0, 256), 256, 0, st>>>(ctx->cam, *p, ctx->shard, (uint32_t)slot0, n_slots, S.levels[0], cnt); rs.launches++;
+            tm.end();
+        }
         if (dyn) {
             // level 0 as a wavefront (coherent primary rays), every deeper level inside the persistent kernel
             const RayPool P = S.pool;
             LevelBufs Ln = {}; Ln.ray_o = P.ray_o; Ln.ray_d = P.ray_d; Ln.cap = P.cap;
             tm.begin(KC_TRACE, 0);
-            if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, S.levels[0], 0, cnt);
-            else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, S.levels[0], 0, cnt);
+            if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], 0, cnt);
+            else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], 0, cnt);
             rs.launches++; rs.trace_launches++;
             tm.end();
             tm.begin(KC_SHADE, 0);
-            k_shade<<<shade_grid, 256, 0, st>>>(sc, *p, 0, S.levels[0], Ln, P, 1, cnt); rs.launches++;
+            k_shade<<<shade_grid, 256, 0, st>>>(sc, *p, g0, 0, S.levels[0], Ln, P, 1, cnt); rs.launches++;
             tm.end();
             tm.begin(KC_TRACE, 0);
-            if (count) k_phong<true><<<trace_grid, 128, 0, st>>>(sc, *p, 0, S.levels[0], cnt);
-            else k_phong<false><<<trace_grid, 128, 0, st>>>(sc, *p, 0, S.levels[0], cnt);
+            if (count) k_phong<true><<<trace_grid, 128, 0, st>>>(sc, *p, g0, 0, S.levels[0], cnt);
+            else k_phong<false><<<trace_grid, 128, 0, st>>>(sc, *p, g0, 0, S.levels[0], cnt);
             rs.launches++; rs.trace_launches++;
             tm.end();
             tm.begin(KC_TRACE, 1);
@@ -620,17 +626,17 @@ static int enqueue_frame(pgrt_context* ctx, FrameSlot& S) {
         } else {
             for (int l = 0; l < n_levels; ++l) {
                 tm.begin(KC_TRACE, l);
-                if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, S.levels[l], l, cnt);
-                else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, S.levels[l], l, cnt);
+                if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, S.levels[l], l, cnt);
+                else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, S.levels[l], l, cnt);
                 rs.launches++; rs.trace_launches++;
                 tm.end();
                 if (dest_mode == 2) break;
                 tm.begin(KC_SHADE, l);
-                k_shade<<<shade_grid, 256, 0, st>>>(sc, *p, l, S.levels[l], S.levels[l + 1], S.pool, 0, cnt); rs.launches++;
+                k_shade<<<shade_grid, 256, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], S.levels[l + 1], S.pool, 0, cnt); rs.launches++;
                 tm.end();
                 tm.begin(KC_TRACE, l);   // Phong = shading preamble + one inline shadow traversal per light
-                if (count) k_phong<true><<<trace_grid, 128, 0, st>>>(sc, *p, l, S.levels[l], cnt);
-                else k_phong<false><<<trace_grid, 128, 0, st>>>(sc, *p, l, S.levels[l], cnt);
+                if (count) k_phong<true><<<trace_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], cnt);
+                else k_phong<false><<<trace_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], cnt);
                 rs.launches++; rs.trace_launches++;
                 tm.end();
             }
@@ -775,6 +781,65 @@ extern "C" int pgrt_render_shard_device_begin(pgrt_context* ctx, const pgrt_rend
     CHECK_CTX(ctx);
     if (!shard_rgba_device) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_shard_device_begin: null destination");
     return frame_begin(ctx, slot, p, (float4*)shard_rgba_device, 1, nullptr, profile);
+}
+extern "C" int pgrt_render_shard_to_frame_begin(pgrt_context* ctx, const pgrt_render_params* p, void* frame_device, int32_t slot, int32_t profile) {
+    CHECK_CTX(ctx);
+    if (!frame_device) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_shard_to_frame_begin: null destination");
+    return frame_begin(ctx, slot, p, (float4*)frame_device, 0, nullptr, profile);   // full-frame addressing, this rank's tiles only
+}
+// ---- frames shared between the processes of one box (one process per GPU): CUDA IPC over NVLink
+extern "C" int pgrt_frame_alloc(pgrt_context* ctx, uint64_t bytes, void** device_ptr) {
+    CHECK_CTX(ctx);
+    if (!device_ptr || !bytes) return ctx->fail(PGRT_ERR_INVALID, "pgrt_frame_alloc: bad arguments");
+    cudaSetDevice(ctx->device);
+    CUDA_TRY(cudaMalloc(device_ptr, bytes));
+    CUDA_TRY(cudaMemset(*device_ptr, 0, bytes));
+    return PGRT_OK;
+}
+extern "C" int pgrt_frame_free(pgrt_context* ctx, void* device_ptr) {
+    CHECK_CTX(ctx);
+    cudaSetDevice(ctx->device);
+    sync_all_slots(ctx);
+    CUDA_TRY(cudaFree(device_ptr));
+    return PGRT_OK;
+}
+extern "C" int pgrt_frame_export(pgrt_context* ctx, void* device_ptr, uint8_t handle[64]) {
+    CHECK_CTX(ctx);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaSetDevice(ctx->device);
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, device_ptr));
+    memcpy(handle, &h, 64);
+    return PGRT_OK;
+}
+extern "C" int pgrt_frame_import(pgrt_context* ctx, const uint8_t handle[64], void** device_ptr) {
+    CHECK_CTX(ctx);
+    if (!device_ptr) return ctx->fail(PGRT_ERR_INVALID, "pgrt_frame_import: null pointer");
+    cudaSetDevice(ctx->device);   // opened from THIS device: peer access to the owner is enabled lazily by the driver
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PGRT_OK;
+}
+extern "C" int pgrt_frame_unmap(pgrt_context* ctx, void* device_ptr) {
+    CHECK_CTX(ctx);
+    cudaSetDevice(ctx->device);
+    sync_all_slots(ctx);
+    CUDA_TRY(cudaIpcCloseMemHandle(device_ptr));
+    return PGRT_OK;
+}
+
+extern "C" int pgrt_enable_peer_access(pgrt_context* ctx, int32_t peer_device) {
+    CHECK_CTX(ctx);
+    cudaSetDevice(ctx->device);
+    if (peer_device == ctx->device) return PGRT_OK;
+    int can = 0;
+    CUDA_TRY(cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+    if (!can) return ctx->fail(PGRT_ERR_INVALID, "pgrt_enable_peer_access: the two devices have no peer path");
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return PGRT_OK; }
+    CUDA_TRY(e);
+    return PGRT_OK;
 }
 extern "C" int pgrt_render_end(pgrt_context* ctx, int32_t slot, pgrt_render_stats* stats) {
     CHECK_CTX(ctx);

@@ -136,13 +136,29 @@ __global__ void __launch_bounds__(256) k_raygen(DevCamera cam, pgrt_render_param
     L.ray_d[j] = make_float4(r.d.x, r.d.y, r.d.z, r.time);
 }
 
+// Level 0 without a stored ray queue: the primary ray of slot j is a pure function of (camera, params, shard, j), so
+// k_trace / k_shade / k_phong regenerate it instead of reading 32 B that k_raygen would have had to write first
+// (66 MB written + 3 x 66 MB read per 1080p frame otherwise).  `on` = 0 reads the level's stored rays.
+struct Gen0 { DevCamera cam; ShardInfo sh; uint32_t slot0, n_slots; int spp; int on; };
+
+__device__ __forceinline__ void load_ray(const LevelBufs& L, const Gen0& g, const pgrt_render_params& p, uint32_t j, float4& o, float4& d) {
+    if (!g.on) { o = L.ray_o[j]; d = L.ray_d[j]; return; }
+    const uint32_t slot = g.slot0 + j / (uint32_t)g.spp;
+    int x, y;
+    if (!slot_to_pixel(g.sh, g.cam.width, g.cam.height, slot, x, y)) { o = make_float4(0.f, 0.f, 0.f, 0.f); d = make_float4(0.f, 0.f, 0.f, -1.0f); return; }
+    const RayRec r = primary_ray(g.cam, p, x, y, (int)(j % (uint32_t)g.spp));
+    o = make_float4(r.o.x, r.o.y, r.o.z, r.tnear);
+    d = make_float4(r.d.x, r.d.y, r.d.z, r.time);
+}
+
 // ---- K7: closest hit for one queue (get_ray_hit, raytracer.cpp:130-148)
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace(DevScene sc, LevelBufs L, int level, Counters* cnt) {
+__global__ void __launch_bounds__(128) k_trace(DevScene sc, pgrt_render_params p, Gen0 g0, LevelBufs L, int level, Counters* cnt) {
     const uint32_t n = min(cnt->n_rays[level], L.cap);
     unsigned long long my_nodes = 0, my_tris = 0; uint32_t my_max = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 o = L.ray_o[i], d = L.ray_d[i];
+        float4 o, d;
+        load_ray(L, g0, p, i, o, d);
         HitRec h; h.t = FLT_MAX; h.u = 0.f; h.v = 0.f; h.tri = PGRT_INVALID_ID;
         if (d.w >= 0.0f) {
             TravCount tc; tc.nodes = 0; tc.tris = 0;
@@ -307,7 +323,7 @@ __device__ __forceinline__ float4 combine_node(float4 att, float4 a, bool has_b,
 
 // ---- K8 (kernel): one level of the wavefront.  With `dyn` set (level 0 of the dynamic scheduler) the children go
 //      to the ray pool (Ln aliases its ray arrays) together with their parent link, and are published at once.
-__global__ void __launch_bounds__(256) k_shade(DevScene sc, pgrt_render_params p, int level, LevelBufs L, LevelBufs Ln, RayPool P, int dyn, Counters* cnt) {
+__global__ void __launch_bounds__(256) k_shade(DevScene sc, pgrt_render_params p, Gen0 g0, int level, LevelBufs L, LevelBufs Ln, RayPool P, int dyn, Counters* cnt) {
     const uint32_t n = min(cnt->n_rays[level], L.cap);
     const int lane = threadIdx.x & 31;
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -317,7 +333,9 @@ __global__ void __launch_bounds__(256) k_shade(DevScene sc, pgrt_render_params p
         ShadeOut s; s.kind = SK_FINAL; s.has_refr = false;
         bool is_phong = false, is_diel = false;
         if (i < n) {
-            shade_classify(sc, p, level, L.ray_o[i], L.ray_d[i], L.hit[i], s);
+            float4 o, d;
+            load_ray(L, g0, p, i, o, d);
+            shade_classify(sc, p, level, o, d, L.hit[i], s);
             is_phong = s.kind == SK_PHONG; is_diel = s.kind == SK_DIEL;
             if (s.kind == SK_FINAL) L.color[i] = s.color;
         }
@@ -366,14 +384,16 @@ __global__ void __launch_bounds__(256) k_shade(DevScene sc, pgrt_render_params p
 
 // ---- K8b/K9 (kernel)
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_phong(DevScene sc, pgrt_render_params p, int level, LevelBufs L, Counters* cnt) {
+__global__ void __launch_bounds__(128) k_phong(DevScene sc, pgrt_render_params p, Gen0 g0, int level, LevelBufs L, Counters* cnt) {
     const uint32_t n = cnt->n_phong[level];
     if (level == 0 && blockIdx.x == 0 && threadIdx.x == 0) cnt->q_l1 = cnt->q_tail;   // dynamic scheduler: the level-1 rays are complete
     unsigned long long my_shadow = 0;
     TravAcc acc; acc.nodes = 0; acc.tris = 0; acc.mx = 0;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint32_t i = L.phong_list[k];
-        const float4 o = L.ray_o[i], d = L.ray_d[i], h = L.hit[i];
+        float4 o, d;
+        load_ray(L, g0, p, i, o, d);
+        const float4 h = L.hit[i];
         const HitFrame f = hit_frame(sc, o, d, h);
         L.color[i] = phong_eval<COUNT>(sc, p, o, d, f, my_shadow, acc);
     }
@@ -605,9 +625,9 @@ __global__ void __launch_bounds__(256) k_primary_ids(DevScene sc, DevCamera cam,
     geom[(size_t)y * cam.width + x] = g; prim[(size_t)y * cam.width + x] = pr;
 }
 
-__global__ void k_batch_begin(Counters* c) {
+__global__ void k_batch_begin(Counters* c, uint32_t n0) {
     const int t = threadIdx.x;
-    if (t <= PGRT_MAX_LEVELS) { c->n_rays[t] = 0; c->n_phong[t] = 0; c->n_diel[t] = 0; }
+    if (t <= PGRT_MAX_LEVELS) { c->n_rays[t] = t == 0 ? n0 : 0u; c->n_phong[t] = 0; c->n_diel[t] = 0; }
     if (t == 0) { c->shadow = 0; c->reflection = 0; c->refraction = 0; c->q_head = 0; c->q_l1 = 0; c->q_tail = 0; }
 }
 __global__ void k_batch_end(Counters* c, unsigned long long primary, int dyn) {

@@ -108,9 +108,16 @@ PG_HD HitRec trace_closest8f(const float4* __restrict__ nodes, const float4* __r
     uint2 stack[PGRT_STACK8];
     int sp = 0;
     uint2 ng = make_uint2(0u, 0x80000000u);
+    uint2 tg = make_uint2(0u, 0u);
+    // while-while: a lane keeps descending until it holds triangles to test (or runs out of nodes), so the warp enters
+    // the triangle phase with as many lanes as possible instead of once per node step
     for (;;) {
-        uint2 tg = make_uint2(0u, 0u);
-        if (ng.y > 0x00FFFFFFu) {
+        bool done = false;
+        while (tg.y == 0u) {
+            if (ng.y <= 0x00FFFFFFu) {
+                if (sp == 0) { done = true; break; }
+                ng = stack[--sp];
+            }
             const uint32_t hits = ng.y;
             const int bit = pg_bfind(hits);
             ng.y &= ~(1u << bit);
@@ -134,15 +141,12 @@ PG_HD HitRec trace_closest8f(const float4* __restrict__ nodes, const float4* __r
             tg.x = pg_f2u(f0.y);
             tg.y = hitmask & 0x00FFFFFFu;
         }
+        if (done) break;
         while (tg.y) {
             const int bit = pg_bfind(tg.y);
             tg.y &= ~(1u << bit);
             if (COUNT) tc.tris++;
             tri_test(tris, tg.x + (uint32_t)bit, O, D, tnear, tfar, best);
-        }
-        if (ng.y <= 0x00FFFFFFu) {
-            if (sp == 0) break;
-            ng = stack[--sp];
         }
     }
     return best;
@@ -163,9 +167,14 @@ PG_HD HitRec trace_closest8(const float4* __restrict__ nodes, const float4* __re
     uint2 stack[PGRT_STACK8];
     int sp = 0;
     uint2 ng = make_uint2(0u, 0x80000000u);     // node group: x = first child node, y = hit bits (31..24) | imask (7..0)
-    for (;;) {
-        uint2 tg = make_uint2(0u, 0u);          // triangle group: x = first triangle, y = hit bits (23..0)
-        if (ng.y > 0x00FFFFFFu) {
+    uint2 tg = make_uint2(0u, 0u);              // triangle group: x = first triangle, y = hit bits (23..0)
+    for (;;) {                                  // while-while, see trace_closest8f
+        bool done = false;
+        while (tg.y == 0u) {
+            if (ng.y <= 0x00FFFFFFu) {
+                if (sp == 0) { done = true; break; }
+                ng = stack[--sp];
+            }
             const uint32_t hits = ng.y;
             const int bit = pg_bfind(hits);
             ng.y &= ~(1u << bit);
@@ -192,15 +201,12 @@ PG_HD HitRec trace_closest8(const float4* __restrict__ nodes, const float4* __re
             tg.x = pg_f2u(n1.y);
             tg.y = hitmask & 0x00FFFFFFu;
         }
+        if (done) break;
         while (tg.y) {
             const int bit = pg_bfind(tg.y);
             tg.y &= ~(1u << bit);
             if (COUNT) tc.tris++;
             tri_test(tris, tg.x + (uint32_t)bit, O, D, tnear, tfar, best);
-        }
-        if (ng.y <= 0x00FFFFFFu) {
-            if (sp == 0) break;
-            ng = stack[--sp];
         }
     }
     return best;

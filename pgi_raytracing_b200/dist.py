@@ -74,24 +74,86 @@ def gather_shards(shard, group=None, dst: int = 0):
     return None
 
 
-class ShardedRenderer:
-    """One rank of a tile-sharded render.  ``begin(k)`` enqueues this rank's tiles of frame k in slot k % depth and,
-    on the communication stream (torch's current stream), the gather to rank 0 and the un-tile; ``end(k)`` collects
-    the stats.  With depth > 1 the gather of one frame overlaps the rendering of the next."""
+class _DevicePtr:
+    """A raw device pointer with the CUDA array interface, so torch can view it without copying."""
 
-    def __init__(self, raytracer, rank: int, world: int, device, depth: int = 1):
+    def __init__(self, ptr: int, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2, "strides": None}
+
+
+def share_frames(raytracer, n_frames: int, rank: int, device, group=None):
+    """``n_frames`` full frames in rank 0's memory, mapped into every rank (``pgrt_frame_alloc / _export / _import``:
+    CUDA IPC, opened from each rank's own device, so its resolve kernel stores into them over NVLink).
+    Returns (pointers valid on this rank, rank-0 torch views or None); (None, None) when any rank cannot map them."""
+    import torch
+    import torch.distributed as dist
+
+    nbytes = raytracer.width * raytracer.height * 16
+    ok, ptrs, handles = 1, None, [None]
+    try:
+        if rank == 0:
+            ptrs = [raytracer.frame_alloc(nbytes) for _ in range(n_frames)]
+            handles = [[raytracer.frame_export(p) for p in ptrs]]
+    except Exception:
+        ok = 0
+    dist.broadcast_object_list(handles, src=0, group=group)
+    try:
+        if rank != 0:
+            if handles[0] is None:
+                ok = 0
+            else:
+                ptrs = [raytracer.frame_import(h) for h in handles[0]]
+    except Exception:
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) != 1:
+        return None, None
+    views = None
+    if rank == 0:
+        views = [torch.as_tensor(_DevicePtr(p, (raytracer.height, raytracer.width, 4)), device=device) for p in ptrs]
+    return ptrs, views
+
+
+class ShardedRenderer:
+    """One rank of a tile-sharded render, ``depth`` frames in flight.
+
+    mode "p2p" (default on GPUs when the frames can be peer-mapped): every rank's resolve kernel stores its tiles
+    straight into rank 0's frame over NVLink (``pgrt_render_shard_to_frame_begin``); the only collective is a 4-byte
+    NCCL all-reduce per frame that serves as the completion barrier.  mode "nccl": compact per-rank tile buffers,
+    ``gather`` to rank 0, un-tile kernel.  ``begin(k)`` enqueues frame k; ``end(k)`` collects this rank's stats;
+    on rank 0, ``frames[k % depth]`` holds frame k once the communication stream has passed ``ready[k % depth]``."""
+
+    def __init__(self, raytracer, rank: int, world: int, device, depth: int = 1, mode: str = "auto"):
         import torch
 
         self.rt, self.rank, self.world, self.device, self.depth = raytracer, rank, world, device, depth
         raytracer.set_shard(rank, world)
         self.n_slots = raytracer.shard_pixels()
-        self.frame = torch.zeros((raytracer.height, raytracer.width, 4), dtype=torch.float32, device=device) if rank == 0 else None
-        self.shards = [torch.zeros((self.n_slots, 4), dtype=torch.float32, device=device) for _ in range(depth)]
-        self.gathered = [torch.empty((world, self.n_slots, 4), dtype=torch.float32, device=device) if (rank == 0 and world > 1) else None
-                         for _ in range(depth)]
         self.slot_streams = [torch.cuda.ExternalStream(raytracer.slot_stream(i), device=device) for i in range(depth)]
-        self.comm_done = [None] * depth
+        self.frames = None
+        self.mode = "local" if world == 1 else mode
+        self.frame_ptrs = None
+        if self.mode in ("auto", "p2p"):
+            self.frame_ptrs, views = share_frames(raytracer, depth, rank, device)
+            if self.frame_ptrs is None and self.mode == "p2p":
+                raise RuntimeError("ShardedRenderer: the frames of rank 0 cannot be peer-mapped (CUDA IPC)")
+            self.mode = "p2p" if self.frame_ptrs is not None else "nccl"
+            if self.mode == "p2p":
+                self.frames = views
+        if self.mode != "p2p" and rank == 0:
+            self.frames = [torch.zeros((raytracer.height, raytracer.width, 4), dtype=torch.float32, device=device) for _ in range(depth)]
+        if self.mode == "nccl":
+            self.shards = [torch.zeros((self.n_slots, 4), dtype=torch.float32, device=device) for _ in range(depth)]
+            self.gathered = [torch.empty((world, self.n_slots, 4), dtype=torch.float32, device=device) if rank == 0 else None for _ in range(depth)]
+        self.token = torch.zeros(1, dtype=torch.float32, device=device)
+        self.ready = [None] * depth          # event on the communication stream: frame of this slot complete on rank 0
+        self.history = {}                    # step -> ready event (kept for the last `depth` steps)
         torch.cuda.synchronize(device)
+
+    @property
+    def frame(self):
+        return self.frames[0] if self.frames else None
 
     def begin(self, k: int, params=None, profile: int = 0, before=None):
         """``before(stream)``: optional work to enqueue on the slot's stream ahead of the frame (bench: the L2 flush)."""
@@ -100,22 +162,33 @@ class ShardedRenderer:
 
         s = k % self.depth
         comm = torch.cuda.current_stream(self.device)
-        if self.comm_done[s] is not None:          # the slot's shard buffer is free once its last gather has run
-            self.slot_streams[s].wait_event(self.comm_done[s])
+        # the slot's destination is free once what consumed its last frame has run: that work sits on rank 0's
+        # communication stream before the barrier of the NEXT step, so waiting for that barrier (here, on every rank) suffices
+        prev = self.history.get(k - self.depth + 1 if self.depth > 1 else k - 1)
+        if prev is not None and k >= self.depth and self.mode != "local":
+            self.slot_streams[s].wait_event(prev)
         if before is not None:
             before(self.slot_streams[s])
-        if self.world == 1:                          # nothing to gather: resolve straight into the frame
-            self.rt.render_begin(s, params, device_ptr=self.frame.data_ptr(), profile=profile)
-            return
-        self.rt.render_begin(s, params, shard_ptr=self.shards[s].data_ptr(), profile=profile)
-        self.rt.stream_wait_slot(s, comm.cuda_stream)
-        if self.rank == 0:
-            dist.gather(self.shards[s], list(self.gathered[s].unbind(0)), dst=0)
-            self.rt.untile(self.gathered[s].data_ptr(), self.world, self.frame.data_ptr(), comm.cuda_stream)
+        if self.mode == "local":
+            self.rt.render_begin(s, params, device_ptr=self.frames[s].data_ptr(), profile=profile)
+        elif self.mode == "p2p":
+            self.rt.render_begin(s, params, frame_ptr=self.frame_ptrs[s], profile=profile)
+            self.rt.stream_wait_slot(s, comm.cuda_stream)
+            dist.all_reduce(self.token)          # completion barrier: 4 bytes; the pixels travelled inside the resolve kernel
         else:
-            dist.gather(self.shards[s], None, dst=0)
+            self.rt.render_begin(s, params, shard_ptr=self.shards[s].data_ptr(), profile=profile)
+            self.rt.stream_wait_slot(s, comm.cuda_stream)
+            if self.rank == 0:
+                dist.gather(self.shards[s], list(self.gathered[s].unbind(0)), dst=0)
+                self.rt.untile(self.gathered[s].data_ptr(), self.world, self.frames[s].data_ptr(), comm.cuda_stream)
+            else:
+                dist.gather(self.shards[s], None, dst=0)
+        if self.mode == "local":
+            self.rt.stream_wait_slot(s, comm.cuda_stream)
         ev = torch.cuda.Event(); ev.record(comm)
-        self.comm_done[s] = ev
+        self.ready[s] = ev
+        self.history[k] = ev
+        self.history.pop(k - 2 * self.depth - 2, None)
 
     def end(self, k: int) -> dict:
         return self.rt.render_end(k % self.depth)

@@ -275,6 +275,25 @@ def test_render_is_deterministic_and_batching_invariant(P, cornell, monkeypatch)
     assert (sa["shadow"], sa["reflection"], sa["refraction"]) == (sc_["shadow"], sc_["reflection"], sc_["refraction"])
 
 
+def test_build_and_queue_variants_render_the_same_frame(P, cornell, monkeypatch):
+    """Knobs that change HOW the frame is computed must not change it: stored vs regenerated level-0 rays,
+    quantised vs float node planes, Karras LBVH vs PLOC tree (the hit record does not depend on the tree)."""
+    p = dict(seed=6)
+    ref, st0 = P.raytracer_for(cornell).render(p)
+    for env in (dict(PGRT_FUSE_RAYGEN="0"), dict(PGRT_NODE_LAYOUT="q8"), dict(PGRT_NODE_LAYOUT="f32"), dict(PGRT_BUILDER="lbvh"),
+                dict(PGRT_BUILDER="lbvh", PGRT_NODE_LAYOUT="q8", PGRT_FUSE_RAYGEN="0")):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        rt = P.raytracer_for(cornell)
+        img, st = rt.render(p)
+        for k in env:
+            monkeypatch.delenv(k)
+        assert np.array_equal(img, ref, equal_nan=True), env
+        assert [st[x] for x in ("primary", "shadow", "reflection", "refraction")] == [st0[x] for x in ("primary", "shadow", "reflection", "refraction")]
+        if "PGRT_NODE_LAYOUT" in env:
+            assert rt.build_stats["node_bytes"] == (80 if env["PGRT_NODE_LAYOUT"] == "q8" else 208)
+
+
 def test_pipelined_frames_equal_synchronous_frames(P, avenger):
     """pgrt_render_begin / pgrt_render_end: four frames in flight in four slots (own streams, queues, counters) give the
     frames and ray counts of four synchronous renders; slots are reusable; a busy slot refuses a second frame."""
@@ -397,3 +416,17 @@ def test_errors_are_reported_not_thrown(P):
         rt.render(dict(sampling_width=0))
     with pytest.raises(P.PgrtError):
         rt.render(dict(max_depth=64))
+
+
+def test_two_ranks_p2p_and_nccl_gather_are_bit_identical():
+    """One process per GPU: the peer-mapped direct-write path (resolve kernel stores into rank 0's frame over NVLink,
+    4-byte NCCL all-reduce as the barrier) and the NCCL gather path against a single-GPU render (tools/p2p_check.py).
+    Needs two GPUs; the single-GPU box of the round-end run skips it."""
+    import subprocess, sys, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29531", os.path.join(root, "tools", "p2p_check.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "p2p: 2 ranks" in out.stdout and "mode used = p2p" in out.stdout and "nccl: 2 ranks" in out.stdout
