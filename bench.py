@@ -34,6 +34,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "Mrays/s (prim+secondary), avenger Whitted 1080p"
+# dram__bytes_read.sum + dram__bytes_write.sum of one C2 frame's traversal launches, from the committed ncu --set full capture
+# (profiles/r1_ncu_bvh8_f32w_k_trace_k_secondary.txt: k_trace 7.82 MB + 0.43 MB, k_secondary 10.87 MB + 0.02 MB; k_phong is negligible).
+# The algorithmic figure for the same launches is 2.84 M rays x 720 B = 2.05 GB: the working set lives in L1/L2, not in HBM.
+NCU_TRAFFIC_BYTES = int(7.819264e6 + 428544 + 10.873856e6 + 17920)
 UNIT = "Mrays/s"
 
 
@@ -203,7 +207,7 @@ def run_ours(args):
     sc, p, desc = workload(args.workload)
     rt = raytracer_for(sc, device=local)
     params = default_params(**p)
-    depth = max(1, min(args.inflight, 4))
+    depth = max(1, min(args.inflight if args.inflight > 0 else (4 if world <= 2 else 8), 8))
     K, W = args.steps, max(args.warmup, 3)
     sr = ShardedRenderer(rt, rank, world, dev, depth=depth)
     flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev)   # 168 MB > the 126 MB L2
@@ -314,7 +318,8 @@ def run_ours(args):
         b_ray = algorithmic_bytes_per_ray(sc.ntris)
         achieved = prof_rays * b_ray / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None
         roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (achieved / peaks["hbm_gbs"]) if achieved else None,
-                "traffic": None, "kernel": "k_trace + k_phong + k_secondary (every closest-hit query of the frame)", "bytes_per_ray": b_ray,
+                "traffic": NCU_TRAFFIC_BYTES if args.workload == "c2" else None,
+                "kernel": "k_trace + k_phong + k_secondary (every closest-hit query of the frame)", "bytes_per_ray": b_ray,
                 "launch_ms_avg": trace_ms / max(trace_launches, 1), "launches_per_frame": trace_launches / max(n_prof, 1), "peak_kind": peak_kind,
                 "frame_ms_unpipelined": prof_frame_ms / max(n_prof, 1),
                 "level0_trace_ms": lv[0]["trace_ms"] if lv else None, "secondary_ms": lv[1]["trace_ms"] if lv and len(lv) > 1 else None,
@@ -343,7 +348,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=4, help="frames in flight per GPU (1 = one frame at a time)")
+    ap.add_argument("--inflight", type=int, default=0, help="frames in flight per GPU (1 = one frame at a time; 0 = 4 up to 2 GPUs, 8 beyond)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -24,7 +24,7 @@ extern "C" {
 #define PGRT_ERR_NO_DEVICE 3    /* no usable GPU                                           */
 #define PGRT_ERR_OVERFLOW 4     /* secondary-ray queues overflowed even at the minimum batch */
 
-#define PGRT_MAX_INFLIGHT 4            /* frame slots of a context (pipelined frames)             */
+#define PGRT_MAX_INFLIGHT 8            /* frame slots of a context (pipelined frames)             */
 
 #define PGRT_INVALID_ID 0xFFFFFFFFu   /* = RTC_INVALID_GEOMETRY_ID, embree3/rtcore_common.h:45 */
 #define PGRT_IOR_AIR 1.000293f        /* material.h:15 */

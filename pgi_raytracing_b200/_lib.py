@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 PGRT_OK, PGRT_ERR_INVALID, PGRT_ERR_CUDA, PGRT_ERR_NO_DEVICE, PGRT_ERR_OVERFLOW = 0, 1, 2, 3, 4
 INVALID_ID = 0xFFFFFFFF
-MAX_INFLIGHT = 4
+MAX_INFLIGHT = 8
 
 
 class Material(C.Structure):

@@ -20,18 +20,21 @@
 //           = unary(n) << 5 | offset     leaf child: n <= 3 triangles at tri_base + offset (offset <= 21)
 // imask bit s is set for internal children.  Triangles: 3 x float4 each (v0 | flat id, v0 - v1, v2 - v0), 48 B.
 //
-// Second layout, PGRT_LAYOUT_F32 (13 x float4 = 208 B): the same node with the 48 planes kept as floats,
-//   f0 = (child_base, tri_base, meta[0..3], meta[4..7]);  f[1 + 2*p + h] = plane p (lo.x, lo.y, lo.z, hi.x, hi.y, hi.z) of slots 4h..4h+3.
-// It costs 2.6x the bytes and removes the 48 integer->float conversions per node visit (the decode is 30 % of the
-// instructions of a visit, profiles/r1_ncu_bvh8_q8_k_trace_k_secondary.txt); pgrt_commit picks it while the node array stays far below L2
-// capacity (the traversal is then issue-bound, not memory-bound) and the quantised one otherwise.
+// Second layout, PGRT_LAYOUT_F32 (15 x float4 = 240 B): the same node with everything the visit needs pre-decoded,
+//   f0 = (child_base, tri_base, imask, 0)
+//   f1, f2 = one 32-bit hit-mask word per slot: 1 << (24 + s) for an internal child, unary(n) << offset for a leaf
+//   f[3 + 2*p + h] = plane p (lo.x, lo.y, lo.z, hi.x, hi.y, hi.z) of slots 4h..4h+3, as floats.
+// It costs 3x the bytes and removes, per node visit, the 48 integer->float conversions (30 % of the instructions of a
+// visit, profiles/r1_ncu_bvh8_q8_k_trace_k_secondary.txt) and the per-slot variable shifts that assemble the hit mask
+// (another 20 %, profiles/r1_ncu_bvh8_f32_k_trace_k_shade.txt); pgrt_commit picks it while the node array stays far
+// below L2 capacity (the traversal is then issue-bound, not memory-bound) and the quantised one otherwise.
 #pragma once
 #include "common.cuh"
 
 #define PGRT_LAYOUT_Q8 0
 #define PGRT_LAYOUT_F32 1
 #define PGRT_NODE_F4_Q8 5         // float4 per node
-#define PGRT_NODE_F4_F32 13
+#define PGRT_NODE_F4_F32 15
 
 #define PGRT_LEAF_TRIS 3          // triangles per leaf slot
 #define PGRT_STACK8 40            // traversal stack entries (one pushed per level at most; commit checks the depth)
@@ -179,9 +182,13 @@ PG_HD void bvh8_emit(const Bvh2View& t, uint32_t root, const Wide8& w, uint32_t 
         }
     }
     if (layout == PGRT_LAYOUT_F32) {
-        node_out[0] = make_float4(pg_u2f(child_base), pg_u2f(tri_base), pg_u2f(pack4(meta)), pg_u2f(pack4(meta + 4)));
+        uint32_t word[8];
+        for (int s = 0; s < 8; ++s) word[s] = (imask >> s) & 1u ? 1u << (24 + s) : (meta[s] >> 5) << (meta[s] & 31u);
+        node_out[0] = make_float4(pg_u2f(child_base), pg_u2f(tri_base), pg_u2f(imask), 0.0f);
+        node_out[1] = make_float4(pg_u2f(word[0]), pg_u2f(word[1]), pg_u2f(word[2]), pg_u2f(word[3]));
+        node_out[2] = make_float4(pg_u2f(word[4]), pg_u2f(word[5]), pg_u2f(word[6]), pg_u2f(word[7]));
         for (int a = 0; a < 6; ++a)
-            for (int h = 0; h < 2; ++h) node_out[1 + 2 * a + h] = make_float4(fb[a][4 * h], fb[a][4 * h + 1], fb[a][4 * h + 2], fb[a][4 * h + 3]);
+            for (int h = 0; h < 2; ++h) node_out[3 + 2 * a + h] = make_float4(fb[a][4 * h], fb[a][4 * h + 1], fb[a][4 * h + 2], fb[a][4 * h + 3]);
         return;
     }
     node_out[0] = make_float4(nlo.x, nlo.y, nlo.z, pg_u2f(ex | (ey << 8) | (ez << 16) | (imask << 24)));

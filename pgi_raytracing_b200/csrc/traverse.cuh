@@ -63,25 +63,21 @@ PG_HD uint32_t slab4(uint32_t meta4, uint32_t nx4, uint32_t ny4, uint32_t nz4, u
     return hitmask;
 }
 
-// F32 layout: the same hit-mask logic on un-quantised planes, four slots per call
-PG_HD uint32_t slab4f(uint32_t meta4, float4 nx, float4 ny, float4 nz, float4 fx, float4 fy, float4 fz, float idx, float idy, float idz,
-                      float oodx, float oody, float oodz, float tnear, float far_pad, float pad_abs, uint32_t octinv4) {
-    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-    const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xFFu;
-    const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
-    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+// F32 layout: slab tests on float planes, four slots per call; a hit ORs the slot's pre-shifted word into the mask
+PG_HD uint32_t slab4f(float4 w, float4 nx, float4 ny, float4 nz, float4 fx, float4 fy, float4 fz, float idx, float idy, float idz,
+                      float oodx, float oody, float oodz, float tnear, float far_pad, float pad_abs) {
     const float nxs[4] = {nx.x, nx.y, nx.z, nx.w}, nys[4] = {ny.x, ny.y, ny.z, ny.w}, nzs[4] = {nz.x, nz.y, nz.z, nz.w};
     const float fxs[4] = {fx.x, fx.y, fx.z, fx.w}, fys[4] = {fy.x, fy.y, fy.z, fy.w}, fzs[4] = {fz.x, fz.y, fz.z, fz.w};
+    const uint32_t ws[4] = {pg_f2u(w.x), pg_f2u(w.y), pg_f2u(w.z), pg_f2u(w.w)};
     uint32_t hitmask = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int sh = 8 * j;
         const float tx0 = pg_fma(nxs[j], idx, -oodx), tx1 = pg_fma(fxs[j], idx, -oodx);
         const float ty0 = pg_fma(nys[j], idy, -oody), ty1 = pg_fma(fys[j], idy, -oody);
         const float tz0 = pg_fma(nzs[j], idz, -oodz), tz1 = pg_fma(fzs[j], idz, -oodz);
         const float tmin = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, tnear));
         const float tmax = fminf(fminf(tx1, ty1), fminf(tz1, far_pad));
-        if (tmin <= pg_fma(tmax, 1.0000005f, pad_abs)) hitmask |= ((child_bits4 >> sh) & 0xFFu) << ((bit_index4 >> sh) & 0xFFu);
+        if (tmin <= pg_fma(tmax, 1.0000005f, pad_abs)) hitmask |= ws[j];
     }
     return hitmask;
 }
@@ -101,10 +97,11 @@ PG_HD HitRec trace_closest8f(const float4* __restrict__ nodes, const float4* __r
     const float pad_abs = 2.3841858e-7f * fmaxf(fmaxf(fabsf(oodx), fabsf(oody)), fabsf(oodz));   // 2^-22 * max |O * idir|
     const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;
     const uint32_t octinv = (negx ? 0u : 4u) | (negy ? 0u : 2u) | (negz ? 0u : 1u);
-    const uint32_t octinv4 = octinv * 0x01010101u;
-    // near / far planes by ray sign, as float4 offsets inside the node (plane p of half h = 1 + 2*p + h)
-    const int onx = 1 + 2 * (negx ? 3 : 0), ony = 1 + 2 * (negy ? 4 : 1), onz = 1 + 2 * (negz ? 5 : 2);
-    const int ofx = 1 + 2 * (negx ? 0 : 3), ofy = 1 + 2 * (negy ? 1 : 4), ofz = 1 + 2 * (negz ? 2 : 5);
+    // near / far planes by ray sign, as float4 offsets inside the node (plane p of half h = 3 + 2*p + h)
+    const int onx = 3 + 2 * (negx ? 3 : 0), ony = 3 + 2 * (negy ? 4 : 1), onz = 3 + 2 * (negz ? 5 : 2);
+    const int ofx = 3 + 2 * (negx ? 0 : 3), ofy = 3 + 2 * (negy ? 1 : 4), ofz = 3 + 2 * (negz ? 2 : 5);
+    // internal hits sit at bit 24 + s; the traversal wants them at 24 + (s ^ octinv): three delta swaps, masked per ray
+    const uint32_t sw1 = (octinv & 1u) ? 0x55000000u : 0u, sw2 = (octinv & 2u) ? 0x33000000u : 0u, sw4 = (octinv & 4u) ? 0x0F000000u : 0u;
     uint2 stack[PGRT_STACK8];
     int sp = 0;
     uint2 ng = make_uint2(0u, 0x80000000u);
@@ -125,19 +122,19 @@ PG_HD HitRec trace_closest8f(const float4* __restrict__ nodes, const float4* __r
             const uint32_t slot = (uint32_t)(bit - 24) ^ octinv;
             const uint32_t rel = (uint32_t)pg_popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
             const float4* __restrict__ nd = nodes + PGRT_NODE_F4_F32 * (size_t)(ng.x + rel);
-            const float4 f0 = pg_ldg4(nd);
+            const float4 f0 = pg_ldg4(nd), w0 = pg_ldg4(nd + 1), w1 = pg_ldg4(nd + 2);
             const float4 nx0 = pg_ldg4(nd + onx), ny0 = pg_ldg4(nd + ony), nz0 = pg_ldg4(nd + onz), fx0 = pg_ldg4(nd + ofx), fy0 = pg_ldg4(nd + ofy), fz0 = pg_ldg4(nd + ofz);
             const float4 nx1 = pg_ldg4(nd + onx + 1), ny1 = pg_ldg4(nd + ony + 1), nz1 = pg_ldg4(nd + onz + 1), fx1 = pg_ldg4(nd + ofx + 1), fy1 = pg_ldg4(nd + ofy + 1), fz1 = pg_ldg4(nd + ofz + 1);
             if (COUNT) tc.nodes++;
             const float far_pad = pg_fma(best.t, 1.0000005f, pad_abs);
-            const uint32_t m0 = pg_f2u(f0.z), m1 = pg_f2u(f0.w);
-            uint32_t hitmask = slab4f(m0, nx0, ny0, nz0, fx0, fy0, fz0, idx, idy, idz, oodx, oody, oodz, tnear, far_pad, pad_abs, octinv4);
-            hitmask |= slab4f(m1, nx1, ny1, nz1, fx1, fy1, fz1, idx, idy, idz, oodx, oody, oodz, tnear, far_pad, pad_abs, octinv4);
-            // imask from the meta bytes: bit 4 of (m & m << 1) marks an internal slot; gather the four flags of each word
-            const uint32_t in0 = ((m0 & (m0 << 1)) & 0x10101010u) >> 4, in1 = ((m1 & (m1 << 1)) & 0x10101010u) >> 4;
-            const uint32_t imask = ((in0 * 0x01020408u) >> 24) | (((in1 * 0x01020408u) >> 24) << 4);
+            uint32_t hitmask = slab4f(w0, nx0, ny0, nz0, fx0, fy0, fz0, idx, idy, idz, oodx, oody, oodz, tnear, far_pad, pad_abs);
+            hitmask |= slab4f(w1, nx1, ny1, nz1, fx1, fy1, fz1, idx, idy, idz, oodx, oody, oodz, tnear, far_pad, pad_abs);
+            uint32_t x;
+            x = ((hitmask >> 1) ^ hitmask) & sw1; hitmask ^= x ^ (x << 1);
+            x = ((hitmask >> 2) ^ hitmask) & sw2; hitmask ^= x ^ (x << 2);
+            x = ((hitmask >> 4) ^ hitmask) & sw4; hitmask ^= x ^ (x << 4);
             ng.x = pg_f2u(f0.x);
-            ng.y = (hitmask & 0xFF000000u) | imask;
+            ng.y = (hitmask & 0xFF000000u) | pg_f2u(f0.z);
             tg.x = pg_f2u(f0.y);
             tg.y = hitmask & 0x00FFFFFFu;
         }

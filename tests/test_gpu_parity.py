@@ -291,7 +291,7 @@ def test_build_and_queue_variants_render_the_same_frame(P, cornell, monkeypatch)
         assert np.array_equal(img, ref, equal_nan=True), env
         assert [st[x] for x in ("primary", "shadow", "reflection", "refraction")] == [st0[x] for x in ("primary", "shadow", "reflection", "refraction")]
         if "PGRT_NODE_LAYOUT" in env:
-            assert rt.build_stats["node_bytes"] == (80 if env["PGRT_NODE_LAYOUT"] == "q8" else 208)
+            assert rt.build_stats["node_bytes"] == (80 if env["PGRT_NODE_LAYOUT"] == "q8" else 240)
 
 
 def test_pipelined_frames_equal_synchronous_frames(P, avenger):
@@ -430,3 +430,41 @@ def test_two_ranks_p2p_and_nccl_gather_are_bit_identical():
                           "--master-port", "29531", os.path.join(root, "tools", "p2p_check.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "p2p: 2 ranks" in out.stdout and "mode used = p2p" in out.stdout and "nccl: 2 ranks" in out.stdout
+
+
+def test_dof_converges_to_the_same_mean_for_different_seeds(P, oracle_mod, cornell):
+    """north_star: 'DOF is compared as a converged mean'.  The reference seeds its samplers from the clock; here two
+    different seeds stand for two runs: GPU (seed 5) and oracle (seed 77), 12x12 samples per pixel, thin lens f=200 a=5.
+    Same seeds are bit-level parity (golden tests above); different seeds must agree as means."""
+    rt = P.raytracer_for(cornell); o = oracle_mod.Oracle(cornell)
+    img, _ = rt.render(dict(sampling_width=12, seed=5))
+    ref = o.render(oracle_mod.make_params(sampling_width=12, seed=77))[0]
+    a, b = P.to_srgb8(ref).astype(float), P.to_srgb8(img).astype(float)
+    psnr = 10 * np.log10(255.0 ** 2 / np.mean((a - b) ** 2))
+    assert psnr >= 30.0, psnr                      # 144 spp Monte-Carlo noise of two independent runs
+    assert abs(a.mean() - b.mean()) <= 0.5         # no bias: means of the whole frame within half an LSB
+    img2, _ = rt.render(dict(sampling_width=12, seed=77))
+    ok, psnr_same = image_bars(P, ref, img2)
+    assert ok >= 0.995 and psnr_same >= 45.0       # and with the SAME seed the usual bars hold
+
+
+def test_large_soup_quantised_nodes_match_the_oracle_bvh(P, oracle_mod):
+    """300 k random triangles: above the tests' usual sizes, through the 80-B quantised layout (forced) and the float
+    one; closest hits bit-exact against the oracle's own BVH traversal (brute force would take minutes)."""
+    import os as _os
+    sc = scenes.triangle_soup(300_000, seed=9, resolution=(160, 90))
+    o = oracle_mod.Oracle(sc)
+    rays = o.primary_rays(oracle_mod.make_params(sampling_width=2, jitter=1, aperture=0.0, seed=4))
+    rh = oracle_mod.make_rayhits(rays[:, :3], rays[:, 4:7], tnear=0.01)
+    b = o.intersect(rh, brute=False)
+    assert (b["geomID"] != INVALID).mean() > 0.2
+    for layout in ("q8", "f32"):
+        _os.environ["PGRT_NODE_LAYOUT"] = layout
+        try:
+            rt = P.raytracer_for(sc)
+        finally:
+            del _os.environ["PGRT_NODE_LAYOUT"]
+        assert rt.build_stats["node_bytes"] == (80 if layout == "q8" else 240)
+        a = rt.intersect(rh)
+        for f in ("tfar", "u", "v", "geomID", "primID"):
+            assert np.array_equal(a[f], b[f]), (layout, f)
