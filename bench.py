@@ -78,6 +78,12 @@ def algorithmic_bytes_per_ray(n_tris: int) -> float:
     return 48.0 + 80.0 * d + 192.0
 
 
+def flop_per_ray(n_tris: int) -> float:
+    """8 slab tests x 24 flop per node + 4 Moeller-Trumbore x 45: F_ray = 192*D + 180."""
+    d = max(1, math.ceil(math.log(max(n_tris, 8) / 4.0, 8)))
+    return 192.0 * d + 180.0
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -210,7 +216,7 @@ def run_ours(args):
     depth = max(1, min(args.inflight if args.inflight > 0 else (4 if world <= 2 else 8), 8))
     K, W = args.steps, max(args.warmup, 3)
     sr = ShardedRenderer(rt, rank, world, dev, depth=depth)
-    flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev)   # 168 MB > the 126 MB L2
+    FLUSH_BYTES = 160 << 20   # 168 MB > the 126 MB L2
 
     def barrier():
         if world > 1:
@@ -219,9 +225,10 @@ def run_ours(args):
 
     def l2_flush(k):
         def f(stream):
-            with torch.cuda.stream(stream):
-                flush.fill_(k & 0xFF)
+            rt.flush_l2(k % depth, FLUSH_BYTES, k & 0xFF)   # a 168 MB fill on that frame's own stream
         return f
+
+    host_issue = [0.0, 0]
 
     def run_frames(n, timed):
         """n frames, `depth` in flight; every frame is preceded by an L2 flush on its own stream.  Returns (device ms, rays)."""
@@ -235,7 +242,9 @@ def run_ours(args):
         for k in range(n):
             if k >= depth:
                 rays += sr.end(k - depth)["total"]
+            h0 = time.perf_counter()
             sr.begin(k, params, before=l2_flush(k))
+            host_issue[0] += time.perf_counter() - h0; host_issue[1] += 1
         for k in range(max(0, n - depth), n):
             rays += sr.end(k)["total"]
         for s in sr.slot_streams:
@@ -245,10 +254,13 @@ def run_ours(args):
         return t0.elapsed_time(t1), rays
 
     run_frames(max(W, 2 * depth), False)   # every slot allocates its queues on first use: keep that out of the timed region
+    host_issue[0] = 0.0; host_issue[1] = 0
+    sr.host_s, sr.host_n = [0.0, 0.0, 0.0, 0.0], 0
     sampler = ClockSampler(local); sampler.start()
     launches0 = rt.kernel_launches()
     total_ms, rays = run_frames(K, True)
     launches = rt.kernel_launches() - launches0
+    host_parts = [x / max(sr.host_n, 1) * 1e6 for x in sr.host_s]
     clocks = sampler.stop()
     step_ms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(rays), float(launches)], dtype=torch.float64, device=dev)
@@ -280,7 +292,7 @@ def run_ours(args):
             for k in range(n):
                 if k >= depth:
                     e_rays += rt.render_end((k - depth) % depth)["total"]
-                l2_flush(k)(sr.slot_streams[k % depth])
+                rt.flush_l2(k % depth, FLUSH_BYTES, k & 0xFF)
                 rt.set_camera(c.width, c.height, c.fov_y, c.view_from, c.view_at)
                 rt.render_begin(k % depth, params, host_ptr=hosts[k % depth].data_ptr())
             for k in range(max(0, n - depth), n):
@@ -322,6 +334,9 @@ def run_ours(args):
                 "kernel": "k_trace + k_phong + k_secondary (every closest-hit query of the frame)", "bytes_per_ray": b_ray,
                 "launch_ms_avg": trace_ms / max(trace_launches, 1), "launches_per_frame": trace_launches / max(n_prof, 1), "peak_kind": peak_kind,
                 "frame_ms_unpipelined": prof_frame_ms / max(n_prof, 1),
+                "fp32": {"flop_per_ray": flop_per_ray(sc.ntris), "achieved_tflops": value * 1e6 * flop_per_ray(sc.ntris) / 1e12,
+                         "peak_tflops": 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12,
+                         "note": "SURVEY 8(d) contract figure F_ray = 192*D + 180 on the pipelined whole-frame rate; peak = 148 SM x 128 lanes x 2 x max SM clock"},
                 "level0_trace_ms": lv[0]["trace_ms"] if lv else None, "secondary_ms": lv[1]["trace_ms"] if lv and len(lv) > 1 else None,
                 "note": "algorithmic bytes = SURVEY 8(d) contract figure (720 B/ray at this size) x rays of rank 0, over the summed device time of the "
                         "traversal launches measured one frame at a time (CUDA events on the launching stream, L2 flushed before each frame); the "
@@ -330,6 +345,8 @@ def run_ours(args):
                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "config": {"workload": desc, "triangles": sc.ntris, "rays_per_frame": total_rays / K,
                                                 "parallelism": f"tiles32x8/rr x{world}", "frames_in_flight": depth, "gather": sr.mode,
+                                                "host_issue_us_per_step": host_issue[0] / max(host_issue[1], 1) * 1e6,
+                                                "host_issue_parts_us": dict(zip(("flush", "render_begin", "barrier", "event"), host_parts)),
                                                 "l2": "flushed before every timed step on that step's stream (160 MiB fill > 126 MB L2)",
                                                 "bvh": rt.build_stats},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(tot[1].item()), "roofline": roof}

@@ -214,6 +214,10 @@ int pgrt_eval_gamma(pgrt_context* ctx, const float* in4, float gamma_level, uint
 int pgrt_eval_primary_rays(pgrt_context* ctx, const pgrt_render_params* p, float* out9);             /* get_pixel :405-416 + generate_ray; 9 floats/ray */
 int pgrt_eval_secondary_rays(pgrt_context* ctx, const float* in11, uint64_t n, int32_t refraction, float* out9);  /* raytracer.cpp:178-235 */
 
+/* ---- measurement helper: stream `bytes` of writes through a scratch buffer on the slot's stream (evicts the 126 MB L2
+ *      when bytes exceeds it); benchmarks call it before every timed frame */
+int pgrt_debug_flush_l2(pgrt_context* ctx, int32_t slot, uint64_t bytes, uint32_t value);
+
 /* ---- introspection */
 uint32_t pgrt_num_triangles(const pgrt_context* ctx);
 uint32_t pgrt_num_geometries(const pgrt_context* ctx);

@@ -79,6 +79,7 @@ SYMBOLS = {
     "pgrt_frame_export": (C.c_int, [_VP, _VP, C.c_char_p]),
     "pgrt_frame_import": (C.c_int, [_VP, C.c_char_p, C.POINTER(_VP)]),
     "pgrt_frame_unmap": (C.c_int, [_VP, _VP]),
+    "pgrt_debug_flush_l2": (C.c_int, [_VP, _I32, _U64, _U32]),
     "pgrt_enable_peer_access": (C.c_int, [_VP, _I32]),
     "pgrt_render_shard_to_frame_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),
     "pgrt_render_end": (C.c_int, [_VP, _I32, C.POINTER(RenderStats)]),

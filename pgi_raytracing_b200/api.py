@@ -188,6 +188,10 @@ class Raytracer:
     def frame_unmap(self, ptr: int):
         self._check(self.lib.pgrt_frame_unmap(self.h, C.c_void_p(ptr)))
 
+    def flush_l2(self, slot: int, nbytes: int = 160 << 20, value: int = 0):
+        """Measurement helper (``pgrt_debug_flush_l2``): evict L2 on the slot's stream before a timed frame."""
+        self._check(self.lib.pgrt_debug_flush_l2(self.h, slot, nbytes, value))
+
     def enable_peer_access(self, peer_device: int):
         self._check(self.lib.pgrt_enable_peer_access(self.h, peer_device))
 

@@ -250,7 +250,9 @@ __device__ __forceinline__ void shade_classify(const DevScene& sc, const pgrt_re
             const V3 v = -s.f.dirn;
             const float cos1 = fabsf(dot3(s.f.n, v));
             const float alpha = (n1 - n2) / (n1 + n2);
-            s.att.w = (float)((double)(alpha * alpha + (1 - (alpha * alpha))) * pow((double)(1 - cos1), 5.0));   // :316
+            // :316  pow(1 - cos1, 5) in double: five exact-ish products (<= 2 ulp of a double, invisible after the cast to float)
+            const double q1 = (double)(1 - cos1), q2 = q1 * q1;
+            s.att.w = (float)((double)(alpha * alpha + (1 - (alpha * alpha))) * (q2 * q2 * q1));
         }
     } else {
         s.kind = SK_PHONG;

@@ -147,6 +147,8 @@ class ShardedRenderer:
             self.shards = [torch.zeros((self.n_slots, 4), dtype=torch.float32, device=device) for _ in range(depth)]
             self.gathered = [torch.empty((world, self.n_slots, 4), dtype=torch.float32, device=device) if rank == 0 else None for _ in range(depth)]
         self.token = torch.zeros(1, dtype=torch.float32, device=device)
+        self._events = [torch.cuda.Event() for _ in range(4 * depth + 8)]   # recycled: an event is dead 2*depth+2 steps later
+        self.host_s, self.host_n = [0.0, 0.0, 0.0, 0.0], 0                 # host time per part of begin() (bench reports it)
         self.ready = [None] * depth          # event on the communication stream: frame of this slot complete on rank 0
         self.history = {}                    # step -> ready event (kept for the last `depth` steps)
         torch.cuda.synchronize(device)
@@ -157,9 +159,11 @@ class ShardedRenderer:
 
     def begin(self, k: int, params=None, profile: int = 0, before=None):
         """``before(stream)``: optional work to enqueue on the slot's stream ahead of the frame (bench: the L2 flush)."""
+        import time
         import torch
         import torch.distributed as dist
 
+        t = [time.perf_counter()]
         s = k % self.depth
         comm = torch.cuda.current_stream(self.device)
         # the slot's destination is free once what consumed its last frame has run: that work sits on rank 0's
@@ -169,26 +173,35 @@ class ShardedRenderer:
             self.slot_streams[s].wait_event(prev)
         if before is not None:
             before(self.slot_streams[s])
+        t.append(time.perf_counter())
         if self.mode == "local":
             self.rt.render_begin(s, params, device_ptr=self.frames[s].data_ptr(), profile=profile)
+            t.append(time.perf_counter())
+            self.rt.stream_wait_slot(s, comm.cuda_stream)
         elif self.mode == "p2p":
             self.rt.render_begin(s, params, frame_ptr=self.frame_ptrs[s], profile=profile)
+            t.append(time.perf_counter())
             self.rt.stream_wait_slot(s, comm.cuda_stream)
             dist.all_reduce(self.token)          # completion barrier: 4 bytes; the pixels travelled inside the resolve kernel
         else:
             self.rt.render_begin(s, params, shard_ptr=self.shards[s].data_ptr(), profile=profile)
+            t.append(time.perf_counter())
             self.rt.stream_wait_slot(s, comm.cuda_stream)
             if self.rank == 0:
                 dist.gather(self.shards[s], list(self.gathered[s].unbind(0)), dst=0)
                 self.rt.untile(self.gathered[s].data_ptr(), self.world, self.frames[s].data_ptr(), comm.cuda_stream)
             else:
                 dist.gather(self.shards[s], None, dst=0)
-        if self.mode == "local":
-            self.rt.stream_wait_slot(s, comm.cuda_stream)
-        ev = torch.cuda.Event(); ev.record(comm)
+        t.append(time.perf_counter())
+        ev = self._events[k % len(self._events)]
+        ev.record(comm)
         self.ready[s] = ev
         self.history[k] = ev
         self.history.pop(k - 2 * self.depth - 2, None)
+        t.append(time.perf_counter())
+        for i in range(4):                       # host seconds spent in: wait+before, render_begin, barrier/gather, event
+            self.host_s[i] += t[i + 1] - t[i]
+        self.host_n += 1
 
     def end(self, k: int) -> dict:
         return self.rt.render_end(k % self.depth)
