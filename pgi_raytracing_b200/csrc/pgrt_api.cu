@@ -919,6 +919,7 @@ extern "C" int pgrt_debug_flush_l2(pgrt_context* ctx, int32_t slot, uint64_t byt
     cudaSetDevice(ctx->device);
     if (ctx->flush_buf.n < bytes / 16) { sync_all_slots(ctx); CUDA_TRY(ctx->flush_buf.ensure(bytes / 16)); }
     k_l2_flush<<<ctx->sm_count * 8, 256, 0, ctx->slots[slot].stream>>>(ctx->flush_buf.p, bytes / 16, value);
+    ctx->launches++;
     LAUNCH_OK();
     return PGRT_OK;
 }
