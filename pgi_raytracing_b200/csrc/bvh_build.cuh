@@ -4,9 +4,9 @@
 //   K1  k_scene_bounds      centroid bounds of all triangles (block reduce + ordered-int atomics)
 //   K1b k_morton            63-bit Morton key of each centroid (21 bits / axis) + identity permutation
 //   K2  radix sort          LSD, 8 bits / pass, stable (equal keys keep flat-id order => deterministic tree)
-//   K3  k_karras            Karras 2012 hierarchy emit over the sorted keys (N-1 internal nodes)
-//   K3b k_refit             bottom-up AABB fit with one atomic flag per internal node
-//   K5  k_emit_*            collapse to the traversal layout + triangle re-layout (3 x float4 per triangle)
+//   K4  k_ploc_*            PLOC: agglomerative refinement of the Morton order into a binary tree (default)
+//   K3  k_karras, k_refit   Karras 2012 hierarchy over the sorted keys + bottom-up AABB fit (PGRT_BUILDER=lbvh, for comparison)
+//   K5  k_collapse          collapse to the 8-wide traversal layout + triangle re-layout (3 x float4 per triangle), bvh8.cuh
 #pragma once
 #include "common.cuh"
 #include "bvh8.cuh"
@@ -252,69 +252,6 @@ __global__ void __launch_bounds__(256) k_refit(const float* __restrict__ pos, co
         }
         p = t.parent[p];
     }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// K5a: triangle re-layout into leaf order: (v0, flat id) (e1 = v0 - v1, 0) (e2 = v2 - v0, 0); 48 B, 16-B aligned.
-__global__ void __launch_bounds__(256) k_emit_tris(const float* __restrict__ pos, const uint32_t* __restrict__ vals, uint32_t n, float4* __restrict__ tris) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const uint32_t id = vals[k];
-    const float* p = pos + 9 * (size_t)id;
-    const V3 v0 = v3(p[0], p[1], p[2]), v1 = v3(p[3], p[4], p[5]), v2 = v3(p[6], p[7], p[8]);
-    const V3 e1 = v0 - v1, e2 = v2 - v0;
-    tris[3 * (size_t)k + 0] = make_float4(v0.x, v0.y, v0.z, __uint_as_float(id));
-    tris[3 * (size_t)k + 1] = make_float4(e1.x, e1.y, e1.z, 0.0f);
-    tris[3 * (size_t)k + 2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
-}
-
-// K5b (binary layout): node i = 4 x float4
-//   n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)   n1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
-//   n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)   n3 = (ref0, ref1, 0, 0) as int bits
-//   ref >= 0: internal node index; ref < 0: leaf, ~ref = (first triangle << 2) | (count - 1), count <= PGRT_LEAF_MAX.
-__host__ __device__ __forceinline__ int leaf_ref(int first, int count) { return ~((first << 2) | (count - 1)); }
-
-__global__ void __launch_bounds__(256) k_emit_bvh2(int n, BinTree t, float4* __restrict__ nodes) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    int ref[2];
-    const int ch[2] = {t.left[i], t.right[i]};
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        if (ch[c] >= n - 1) ref[c] = leaf_ref(ch[c] - (n - 1), 1);
-        else {
-            const int f = t.first[ch[c]], l = t.last[ch[c]];
-            ref[c] = (l - f + 1 <= PGRT_LEAF_MAX) ? leaf_ref(f, l - f + 1) : ch[c];
-        }
-    }
-    const float* l0 = t.lo + 3 * (size_t)ch[0]; const float* h0 = t.hi + 3 * (size_t)ch[0];
-    const float* l1 = t.lo + 3 * (size_t)ch[1]; const float* h1 = t.hi + 3 * (size_t)ch[1];
-    nodes[4 * (size_t)i + 0] = make_float4(l0[0], h0[0], l0[1], h0[1]);
-    nodes[4 * (size_t)i + 1] = make_float4(l1[0], h1[0], l1[1], h1[1]);
-    nodes[4 * (size_t)i + 2] = make_float4(l0[2], h0[2], l1[2], h1[2]);
-    nodes[4 * (size_t)i + 3] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), 0.0f, 0.0f);
-}
-
-// SAH cost of the emitted binary tree: sum over reachable internal nodes of area(child)/area(root) * (leaf ? count : 1)
-__global__ void __launch_bounds__(256) k_sah_cost(int n, BinTree t, float* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float c = 0.0f;
-    if (i < n - 1 && (t.last[i] - t.first[i] + 1) > PGRT_LEAF_MAX) {
-        const float rx = t.hi[0] - t.lo[0], ry = t.hi[1] - t.lo[1], rz = t.hi[2] - t.lo[2];
-        const float ra = rx * ry + ry * rz + rz * rx;
-        const int ch[2] = {t.left[i], t.right[i]};
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const float* l = t.lo + 3 * (size_t)ch[k]; const float* h = t.hi + 3 * (size_t)ch[k];
-            const float dx = h[0] - l[0], dy = h[1] - l[1], dz = h[2] - l[2];
-            const float a = dx * dy + dy * dz + dz * dx;
-            int cnt = 1;
-            if (ch[k] < n - 1) { const int m = t.last[ch[k]] - t.first[ch[k]] + 1; cnt = m <= PGRT_LEAF_MAX ? m : 1; }
-            c += (ra > 0.0f ? a / ra : 0.0f) * (float)cnt;
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && c != 0.0f) atomicAdd(out, c);
 }
 
 // ===================================================================================================

@@ -19,7 +19,6 @@
 #define PGRT_TILE_H 8
 #define PGRT_TILE_PIXELS (PGRT_TILE_W * PGRT_TILE_H)
 #define PGRT_MAX_LEVELS 33            // max_depth <= 32
-#define PGRT_LEAF_MAX 3               // triangles per leaf of the emitted tree
 
 struct V3 { float x, y, z; };
 
@@ -88,6 +87,13 @@ PG_HD int pg_popc(uint32_t v) {
     return __builtin_popcount(v);
 #endif
 }
+PG_HD float pg_rcp(float x) {      // IEEE-rounded reciprocal: the same value as 1.0f / x on the host, without the division routine
+#ifdef __CUDA_ARCH__
+    return __frcp_rn(x);
+#else
+    return 1.0f / x;
+#endif
+}
 PG_HD float4 pg_ldg4(const float4* p) {
 #ifdef __CUDA_ARCH__
     return __ldg(p);
@@ -118,7 +124,7 @@ struct DevCamera {            // PinHoleCamera.h:30-41
 
 // Per-frame constant block handed to the kernels by value.
 struct DevScene {
-    const float4* nodes;      // wide / binary nodes (see bvh.cuh)
+    const float4* nodes;      // 8-wide nodes, root = node 0 (bvh8.cuh)
     const float4* tris;       // 3 x float4 per triangle in leaf order: (v0, id) (e1, -) (e2, -)
     const float4* shade;      // 4 x float4 per triangle in flat order: normals + uv + geomID
     const uint32_t* geom_first;     // geomID -> first flat triangle id
@@ -130,7 +136,6 @@ struct DevScene {
     const pgrt_light* lights;
     int32_t n_lights;
     uint32_t n_tris;
-    uint32_t root;            // encoded root reference (binary layout only)
     int32_t node_layout;      // PGRT_LAYOUT_Q8 (80 B nodes) or PGRT_LAYOUT_F32 (208 B nodes), bvh8.cuh
 };
 

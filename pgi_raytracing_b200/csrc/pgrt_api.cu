@@ -102,7 +102,7 @@ struct pgrt_context {
     DevBuf<pgrt_light> d_lights;
     DevBuf<DevTexture> d_textures;
     DevBuf<float4> d_shade, d_tris, d_nodes;
-    uint32_t n_tris = 0, root = 0;
+    uint32_t n_tris = 0;
     int node_layout = PGRT_LAYOUT_Q8;
     bool committed = false, tables_dirty = true;
     pgrt_build_stats last_build = {};
@@ -141,7 +141,7 @@ struct pgrt_context {
         s.nodes = d_nodes.p; s.tris = d_tris.p; s.shade = d_shade.p; s.geom_first = d_geom_first.p; s.geom_material = d_geom_material.p;
         s.materials = d_materials.p; s.textures = d_textures.p; s.n_textures = (int32_t)textures.size();
         s.env.data = env.set ? env.bytes.p : nullptr; s.env.width = env.w; s.env.height = env.h; s.env.pitch = env.pitch; s.env.bpp = env.bpp;
-        s.lights = d_lights.p; s.n_lights = (int32_t)h_lights.size(); s.n_tris = n_tris; s.root = root; s.node_layout = node_layout;
+        s.lights = d_lights.p; s.n_lights = (int32_t)h_lights.size(); s.n_tris = n_tris; s.node_layout = node_layout;
         return s;
     }
 };
@@ -327,7 +327,7 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
     }
     ctx->tables_dirty = true;
     if (N == 0) {
-        ctx->root = 0; ctx->committed = true; ctx->last_build = bs;
+        ctx->committed = true; ctx->last_build = bs;
         if (stats) *stats = bs;
         CUDA_TRY(cudaStreamSynchronize(st));
         return PGRT_OK;
@@ -464,7 +464,6 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
     cudaEventElapsedTime(&bs.collapse_ms, e3, e4);
 #undef BUILD_TRY
     cleanup();
-    ctx->root = 0;
     ctx->committed = true; ctx->last_build = bs;
     if (stats) *stats = bs;
     return PGRT_OK;

@@ -108,8 +108,9 @@ __device__ __forceinline__ RayRec primary_ray(const DevCamera& cam, const pgrt_r
     RayRec r;
     if (p.camera_mode == 1) r = camera_ray_pinhole(cam, new_x, new_y);
     else {
-        const float l1 = rng_uniform(-p.aperture / 2.0f, p.aperture / 2.0f, rng_u01(p.seed, pixel, (uint32_t)s, 2));
-        const float l2 = rng_uniform(-p.aperture / 2.0f, p.aperture / 2.0f, rng_u01(p.seed, pixel, (uint32_t)s, 3));
+        // aperture 0: (0 - (-0)) * u + (-0) is +0 for every u, so the two hashes are skipped
+        const float l1 = p.aperture != 0.0f ? rng_uniform(-p.aperture / 2.0f, p.aperture / 2.0f, rng_u01(p.seed, pixel, (uint32_t)s, 2)) : 0.0f;
+        const float l2 = p.aperture != 0.0f ? rng_uniform(-p.aperture / 2.0f, p.aperture / 2.0f, rng_u01(p.seed, pixel, (uint32_t)s, 3)) : 0.0f;
         r = camera_ray_lens(cam, new_x, new_y, p.focal_distance, l1, l2);
     }
     r.time = PGRT_IOR_AIR;   // raytracer.cpp:416

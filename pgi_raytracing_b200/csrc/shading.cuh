@@ -8,16 +8,21 @@
 struct Col4 { float r, g, b, a; };   // structs.h:11-14
 struct Col3 { float r, g, b; };      // structs.h:16
 
+__device__ __forceinline__ float byte_over_255(uint8_t byte) {
+    const float b = (float)byte, r = 0.003921568859368563f;   // (float)(1.0f / 255.0f)
+    const float q = b * r;
+    return __fmaf_rn(__fmaf_rn(-q, 255.0f, b), r, q);
+}
+
 // ---- Texture::get_pixel (texture.cpp:56-62): bytes are B,G,R(,A); the returned .r carries the BLUE byte.
 // The reference does not bounds-check; out-of-range texel indices are defined here by clamping (as the oracle does).
 __device__ __forceinline__ Col3 tex_get_pixel(const DevTexture& t, int x, int y) {
     x = min(max(x, 0), t.width - 1); y = min(max(y, 0), t.height - 1);
     const uint8_t* p = t.data + (size_t)y * t.pitch + (size_t)x * t.bpp;
-    // __fdiv_rn: under -ftz=true nvcc rewrites "x / 255.0f" as "x * (1/255.0f)", which is not the IEEE quotient
+    // byte / 255.0f, correctly rounded, without the IEEE division routine: q = b * (1/255) is off by at most one ulp and
+    // one residual step repairs it -- exact for all 256 inputs (tests/test_host_logic.py checks the identity)
     Col3 c;
-    c.r = __fdiv_rn((float)__ldg(p), 255.0f);
-    c.g = __fdiv_rn((float)__ldg(p + 1), 255.0f);
-    c.b = __fdiv_rn((float)__ldg(p + 2), 255.0f);
+    c.r = byte_over_255(__ldg(p)); c.g = byte_over_255(__ldg(p + 1)); c.b = byte_over_255(__ldg(p + 2));
     return c;
 }
 

@@ -88,9 +88,9 @@ PG_HD HitRec trace_closest8f(const float4* __restrict__ nodes, const float4* __r
     HitRec best; best.t = tfar; best.u = 0.0f; best.v = 0.0f; best.tri = PGRT_INVALID_ID;
     if (n_tris == 0) return best;
     const float ooeps = 8.271806e-25f;   // 2^-80
-    const float idx = 1.0f / (fabsf(D.x) > ooeps ? D.x : copysignf(ooeps, D.x));
-    const float idy = 1.0f / (fabsf(D.y) > ooeps ? D.y : copysignf(ooeps, D.y));
-    const float idz = 1.0f / (fabsf(D.z) > ooeps ? D.z : copysignf(ooeps, D.z));
+    const float idx = pg_rcp(fabsf(D.x) > ooeps ? D.x : copysignf(ooeps, D.x));
+    const float idy = pg_rcp(fabsf(D.y) > ooeps ? D.y : copysignf(ooeps, D.y));
+    const float idz = pg_rcp(fabsf(D.z) > ooeps ? D.z : copysignf(ooeps, D.z));
     const float oodx = O.x * idx, oody = O.y * idy, oodz = O.z * idz;
     // plane * idir - O * idir cancels when the origin is far from the box compared with t: the rounding of O * idir
     // (2^-24 of its magnitude) is an ABSOLUTE error on t, so the culling bounds carry an absolute pad as well
@@ -155,9 +155,9 @@ PG_HD HitRec trace_closest8(const float4* __restrict__ nodes, const float4* __re
     HitRec best; best.t = tfar; best.u = 0.0f; best.v = 0.0f; best.tri = PGRT_INVALID_ID;
     if (n_tris == 0) return best;
     const float ooeps = 8.271806e-25f;   // 2^-80
-    const float idx = 1.0f / (fabsf(D.x) > ooeps ? D.x : copysignf(ooeps, D.x));
-    const float idy = 1.0f / (fabsf(D.y) > ooeps ? D.y : copysignf(ooeps, D.y));
-    const float idz = 1.0f / (fabsf(D.z) > ooeps ? D.z : copysignf(ooeps, D.z));
+    const float idx = pg_rcp(fabsf(D.x) > ooeps ? D.x : copysignf(ooeps, D.x));
+    const float idy = pg_rcp(fabsf(D.y) > ooeps ? D.y : copysignf(ooeps, D.y));
+    const float idz = pg_rcp(fabsf(D.z) > ooeps ? D.z : copysignf(ooeps, D.z));
     const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;
     const uint32_t octinv = (negx ? 0u : 4u) | (negy ? 0u : 2u) | (negz ? 0u : 1u);
     const uint32_t octinv4 = octinv * 0x01010101u;
@@ -210,68 +210,10 @@ PG_HD HitRec trace_closest8(const float4* __restrict__ nodes, const float4* __re
 }
 
 #ifdef __CUDACC__
-#define PGRT_STACK 128
-
-// Binary-node traversal (layout in bvh_build.cuh, k_emit_bvh2).  Slab tests use FMA and a padded far bound:
-// they only cull, the hit record comes from tri_test alone.
-template <bool COUNT>
-__device__ __forceinline__ HitRec trace_closest2(const DevScene& sc, V3 O, V3 D, float tnear, float tfar, TravCount& tc) {
-    HitRec best; best.t = tfar; best.u = 0.0f; best.v = 0.0f; best.tri = PGRT_INVALID_ID;
-    if (sc.n_tris == 0) return best;
-    const float ooeps = 8.271806e-25f;   // 2^-80
-    const float idx = 1.0f / (fabsf(D.x) > ooeps ? D.x : copysignf(ooeps, D.x));
-    const float idy = 1.0f / (fabsf(D.y) > ooeps ? D.y : copysignf(ooeps, D.y));
-    const float idz = 1.0f / (fabsf(D.z) > ooeps ? D.z : copysignf(ooeps, D.z));
-    const float oodx = O.x * idx, oody = O.y * idy, oodz = O.z * idz;
-    int stack[PGRT_STACK];
-    int sp = 0;
-    int cur = (int)sc.root;
-    const float4* __restrict__ nodes = sc.nodes;
-    while (true) {
-        if (cur >= 0) {
-            if (COUNT) tc.nodes++;
-            const float4 n0 = __ldg(nodes + 4 * (size_t)cur), n1 = __ldg(nodes + 4 * (size_t)cur + 1);
-            const float4 n2 = __ldg(nodes + 4 * (size_t)cur + 2), n3 = __ldg(nodes + 4 * (size_t)cur + 3);
-            const float far_pad = best.t * 1.0000005f;
-            const float c0lox = __fmaf_rn(n0.x, idx, -oodx), c0hix = __fmaf_rn(n0.y, idx, -oodx);
-            const float c0loy = __fmaf_rn(n0.z, idy, -oody), c0hiy = __fmaf_rn(n0.w, idy, -oody);
-            const float c0loz = __fmaf_rn(n2.x, idz, -oodz), c0hiz = __fmaf_rn(n2.y, idz, -oodz);
-            const float c1lox = __fmaf_rn(n1.x, idx, -oodx), c1hix = __fmaf_rn(n1.y, idx, -oodx);
-            const float c1loy = __fmaf_rn(n1.z, idy, -oody), c1hiy = __fmaf_rn(n1.w, idy, -oody);
-            const float c1loz = __fmaf_rn(n2.z, idz, -oodz), c1hiz = __fmaf_rn(n2.w, idz, -oodz);
-            const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tnear));
-            const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), far_pad));
-            const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tnear));
-            const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), far_pad));
-            const bool h0 = c0min <= c0max * 1.0000005f, h1 = c1min <= c1max * 1.0000005f;
-            const int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
-            if (h0 && h1) {
-                const bool swp = c1min < c0min;
-                cur = swp ? r1 : r0;
-                stack[sp++] = swp ? r0 : r1;
-            } else if (h0) cur = r0;
-            else if (h1) cur = r1;
-            else { if (sp == 0) break; cur = stack[--sp]; }
-        } else {
-            const uint32_t code = (uint32_t)~cur;
-            const uint32_t first = code >> 2, cnt = (code & 3u) + 1u;
-            if (COUNT) tc.tris += cnt;
-            for (uint32_t k = 0; k < cnt; ++k) tri_test(sc.tris, first + k, O, D, tnear, tfar, best);
-            if (sp == 0) break;
-            cur = stack[--sp];
-        }
-    }
-    return best;
-}
-
 template <bool COUNT>
 __device__ __forceinline__ HitRec trace_closest_t(const DevScene& sc, V3 O, V3 D, float tnear, float tfar, TravCount& tc) {
-#ifdef PGRT_USE_BVH2
-    return trace_closest2<COUNT>(sc, O, D, tnear, tfar, tc);
-#else
     if (sc.node_layout == PGRT_LAYOUT_F32) return trace_closest8f<COUNT>(sc.nodes, sc.tris, sc.n_tris, O, D, tnear, tfar, tc);
     return trace_closest8<COUNT>(sc.nodes, sc.tris, sc.n_tris, O, D, tnear, tfar, tc);
-#endif
 }
 
 __device__ __forceinline__ HitRec trace_closest(const DevScene& sc, V3 O, V3 D, float tnear, float tfar) {

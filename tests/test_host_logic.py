@@ -98,3 +98,17 @@ def test_bench_contract_figures():
     assert bench.algorithmic_bytes_per_ray(10_000_000) == 880.0     # N = 1e7 -> D = 8
     sc, p, desc = bench.workload("c1")
     assert (sc.camera.width, sc.camera.height) == (640, 480) and p["max_depth"] == 7 and p["sampling_width"] == 1
+
+
+def test_byte_over_255_identity():
+    """csrc/shading.cuh byte_over_255: q = b*r, q + fma(-q, 255, b)*r is the correctly rounded b / 255.0f for all bytes
+    (float64 stands in for the two FMAs: every product here is exact in 53 bits)."""
+    import numpy as np
+    b = np.arange(256, dtype=np.float32)
+    ref = (b / np.float32(255.0)).astype(np.float32)
+    r = np.float32(0.003921568859368563)
+    assert r == np.float32(1.0) / np.float32(255.0)
+    q = (b * r).astype(np.float32)
+    e = (b.astype(np.float64) - q.astype(np.float64) * 255.0).astype(np.float32)
+    q2 = (q.astype(np.float64) + e.astype(np.float64) * np.float64(r)).astype(np.float32)
+    assert np.array_equal(q2, ref) and np.count_nonzero(q != ref) > 50
