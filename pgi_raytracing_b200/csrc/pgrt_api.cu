@@ -117,6 +117,8 @@ struct pgrt_context {
     int secondary_grid = 0;
     bool fuse_raygen = true;          // PGRT_FUSE_RAYGEN=0 restores the stored level-0 ray queue (k_raygen)
     bool use_graphs = true;           // PGRT_GRAPHS=0: every frame as individual launches
+    int trace_refill = 32;            // k_trace claims new rays once this many lanes of a warp are idle (PGRT_TRACE_REFILL, 1..32); 32 = whole-warp chunks, the fastest for coherent primary rays (profiles/r1_sweep_trace_refill.txt)
+    int trace_ctas_per_sm = 6;        // persistent k_trace grid (PGRT_TRACE_CTAS_PER_SM)
     DevBuf<uint32_t> d_ids;
     DevBuf<uint4> flush_buf;          // pgrt_debug_flush_l2
     uint32_t* h_pin = nullptr;        // pinned scratch for small read-backs of the build
@@ -178,6 +180,8 @@ extern "C" int pgrt_create(pgrt_context** out, int device) {
     if (cudaMallocHost((void**)&ctx->h_pin, 256) != cudaSuccess) { pgrt_destroy(ctx); return PGRT_ERR_CUDA; }
     if (const char* e = getenv("PGRT_FUSE_RAYGEN")) ctx->fuse_raygen = atoi(e) != 0;
     if (const char* e = getenv("PGRT_GRAPHS")) ctx->use_graphs = atoi(e) != 0;
+    if (const char* e = getenv("PGRT_TRACE_REFILL")) ctx->trace_refill = std::min(32, std::max(1, atoi(e)));
+    if (const char* e = getenv("PGRT_TRACE_CTAS_PER_SM")) ctx->trace_ctas_per_sm = std::min(16, std::max(1, atoi(e)));
     if (const char* e = getenv("PGRT_MAX_BATCH_SAMPLES")) ctx->max_batch_samples = std::max<size_t>(256, strtoull(e, nullptr, 10));
     if (const char* e = getenv("PGRT_MIN_LEVEL_CAP")) ctx->min_level_cap = std::max<size_t>(64, strtoull(e, nullptr, 10));
     if (const char* e = getenv("PGRT_LEVEL_CAP_FACTOR")) ctx->level_cap_factor = std::max(0.01, atof(e));
@@ -590,7 +594,7 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
     const uint64_t total_slots = shard_slots(ctx);
     const uint64_t batch_slots = S.batch_slots;
     const DevScene sc = ctx->dev_scene();
-    const unsigned trace_grid = ctx->sm_count * 16, shade_grid = ctx->sm_count * 8;
+    const unsigned trace_grid = ctx->sm_count * ctx->trace_ctas_per_sm, phong_grid = ctx->sm_count * 16, shade_grid = ctx->sm_count * 8;
     const bool dyn = S.dyn;
     FrameTimer tm{&S, (profile & 1) != 0};
     const bool count = (profile & 2) != 0;
@@ -615,16 +619,16 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
             const RayPool P = S.pool;
             LevelBufs Ln = {}; Ln.ray_o = P.ray_o; Ln.ray_d = P.ray_d; Ln.cap = P.cap;
             tm.begin(KC_TRACE, 0);
-            if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], 0, cnt);
-            else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], 0, cnt);
+            if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], 0, ctx->trace_refill, cnt);
+            else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], 0, ctx->trace_refill, cnt);
             rs.launches++; rs.trace_launches++;
             tm.end();
             tm.begin(KC_SHADE, 0);
             k_shade<<<shade_grid, 256, 0, st>>>(sc, *p, g0, 0, S.levels[0], Ln, P, 1, cnt); rs.launches++;
             tm.end();
             tm.begin(KC_TRACE, 0);
-            if (count) k_phong<true><<<trace_grid, 128, 0, st>>>(sc, *p, g0, 0, S.levels[0], cnt);
-            else k_phong<false><<<trace_grid, 128, 0, st>>>(sc, *p, g0, 0, S.levels[0], cnt);
+            if (count) k_phong<true><<<phong_grid, 128, 0, st>>>(sc, *p, g0, 0, S.levels[0], cnt);
+            else k_phong<false><<<phong_grid, 128, 0, st>>>(sc, *p, g0, 0, S.levels[0], cnt);
             rs.launches++; rs.trace_launches++;
             tm.end();
             tm.begin(KC_TRACE, 1);
@@ -636,8 +640,8 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
         } else {
             for (int l = 0; l < n_levels; ++l) {
                 tm.begin(KC_TRACE, l);
-                if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, S.levels[l], l, cnt);
-                else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, S.levels[l], l, cnt);
+                if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, S.levels[l], l, ctx->trace_refill, cnt);
+                else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, S.levels[l], l, ctx->trace_refill, cnt);
                 rs.launches++; rs.trace_launches++;
                 tm.end();
                 if (dest_mode == 2) break;
@@ -645,8 +649,8 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
                 k_shade<<<shade_grid, 256, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], S.levels[l + 1], S.pool, 0, cnt); rs.launches++;
                 tm.end();
                 tm.begin(KC_TRACE, l);   // Phong = shading preamble + one inline shadow traversal per light
-                if (count) k_phong<true><<<trace_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], cnt);
-                else k_phong<false><<<trace_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], cnt);
+                if (count) k_phong<true><<<phong_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], cnt);
+                else k_phong<false><<<phong_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], cnt);
                 rs.launches++; rs.trace_launches++;
                 tm.end();
             }
@@ -700,7 +704,7 @@ static uint64_t frame_key(pgrt_context* ctx, const FrameSlot& S) {
     h = fnv1a(S.levels, sizeof(LevelBufs) * (size_t)(S.n_levels + 1), h); h = fnv1a(&S.pool, sizeof S.pool, h);
     const void* extra[3] = {S.d_frame.p, S.d_counters.p, S.stream};
     h = fnv1a(extra, sizeof extra, h);
-    const int flags[3] = {S.dyn ? 1 : 0, ctx->fuse_raygen ? 1 : 0, ctx->secondary_grid};
+    const int flags[5] = {S.dyn ? 1 : 0, ctx->fuse_raygen ? 1 : 0, ctx->secondary_grid, ctx->trace_refill, ctx->trace_ctas_per_sm};
     return fnv1a(flags, sizeof flags, h) | 1ull;
 }
 

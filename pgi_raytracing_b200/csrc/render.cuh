@@ -69,6 +69,7 @@ struct Counters {
     uint32_t lv_max_nodes[PGRT_MAX_LEVELS + 1], lv_sh_max_nodes[PGRT_MAX_LEVELS + 1];
     // dynamic scheduler: pool records allocated / level-1 records (frozen before k_secondary) / level-1 records claimed
     uint32_t q_tail, q_l1, q_head, pad1;
+    uint32_t trace_next[PGRT_MAX_LEVELS + 1];   // k_trace: rays of the level's queue claimed so far
 };
 
 __device__ __forceinline__ void flush_trav_counts(unsigned long long nodes, unsigned long long tris, uint32_t mx,
@@ -152,23 +153,64 @@ __device__ __forceinline__ void load_ray(const LevelBufs& L, const Gen0& g, cons
     d = make_float4(r.d.x, r.d.y, r.d.z, r.time);
 }
 
-// ---- K7: closest hit for one queue (get_ray_hit, raytracer.cpp:130-148)
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace(DevScene sc, pgrt_render_params p, Gen0 g0, LevelBufs L, int level, Counters* cnt) {
-    const uint32_t n = min(cnt->n_rays[level], L.cap);
+// ---- K7: closest hit for one queue (get_ray_hit, raytracer.cpp:130-148).
+// Persistent warps with ray replacement: a warp claims rays from the queue counter, traverses them a few while-while
+// rounds at a time, and whenever at least `refill` of its lanes have finished it claims new rays for exactly those
+// lanes (ballot + one atomicAdd per warp), so a few long traversals do not keep 31 lanes idle until they end.
+// refill = 32 degenerates to "a fresh 32-ray chunk when the whole warp is done".
+#define PGRT_TRACE_ROUNDS 2
+
+template <class RC, bool COUNT>
+__device__ __forceinline__ void trace_queue(const DevScene& sc, const pgrt_render_params& p, const Gen0& g0, const LevelBufs& L, int level, Counters* cnt,
+                                            uint32_t n, int refill) {
+    const int lane = threadIdx.x & 31;
+    uint32_t* next = &cnt->trace_next[level];
+    uint2 stack[PGRT_STACK8];
+    RC r; TravState s; TravCount tc;
+    trav_init(s, FLT_MAX);
+    tc.nodes = 0; tc.tris = 0;
+    uint32_t j = PGRT_INVALID_ID;
+    bool more = true;
     unsigned long long my_nodes = 0, my_tris = 0; uint32_t my_max = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 o, d;
-        load_ray(L, g0, p, i, o, d);
-        HitRec h; h.t = FLT_MAX; h.u = 0.f; h.v = 0.f; h.tri = PGRT_INVALID_ID;
-        if (d.w >= 0.0f) {
-            TravCount tc; tc.nodes = 0; tc.tris = 0;
-            h = trace_closest_t<COUNT>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, FLT_MAX, tc);
-            if (COUNT) { my_nodes += tc.nodes; my_tris += tc.tris; my_max = max(my_max, tc.nodes); }
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, j == PGRT_INVALID_ID);
+        if (more && ((int)__popc(idle) >= refill || idle == 0xffffffffu)) {
+            const uint32_t need = (uint32_t)__popc(idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(next, need);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + need >= n) more = false;
+            if (j == PGRT_INVALID_ID) {
+                const uint32_t mine = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                if (mine < n) {
+                    float4 o, d;
+                    load_ray(L, g0, p, mine, o, d);
+                    if (d.w >= 0.0f && sc.n_tris != 0) {
+                        j = mine;
+                        ray_ctx_init(r, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, FLT_MAX);
+                        trav_init(s, FLT_MAX);
+                        tc.nodes = 0; tc.tris = 0;
+                    } else {
+                        L.hit[mine] = make_float4(FLT_MAX, 0.f, 0.f, __uint_as_float(PGRT_INVALID_ID));   // unused slot / empty scene
+                    }
+                }
+            }
         }
-        L.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
+        if (__ballot_sync(0xffffffffu, j != PGRT_INVALID_ID) == 0u) { if (!more) break; continue; }
+        if (j != PGRT_INVALID_ID && trav_advance<RC, COUNT>(sc.nodes, sc.tris, r, s, stack, tc, PGRT_TRACE_ROUNDS)) {
+            L.hit[j] = make_float4(s.best.t, s.best.u, s.best.v, __uint_as_float(s.best.tri));
+            if (COUNT) { my_nodes += tc.nodes; my_tris += tc.tris; my_max = max(my_max, tc.nodes); }
+            j = PGRT_INVALID_ID;
+        }
     }
     if (COUNT) flush_trav_counts(my_nodes, my_tris, my_max, &cnt->lv_nodes[level], &cnt->lv_tris[level], &cnt->lv_max_nodes[level]);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace(DevScene sc, pgrt_render_params p, Gen0 g0, LevelBufs L, int level, int refill, Counters* cnt) {
+    const uint32_t n = min(cnt->n_rays[level], L.cap);
+    if (sc.node_layout == PGRT_LAYOUT_F32) trace_queue<RayCtxF, COUNT>(sc, p, g0, L, level, cnt, n, refill);
+    else trace_queue<RayCtxQ, COUNT>(sc, p, g0, L, level, cnt, n, refill);
 }
 
 // rtcInterpolate0 (raytracer.cpp:252, :344): w*a0 + u*a1 + v*a2, fused as Embree's madd chain
@@ -630,7 +672,7 @@ __global__ void __launch_bounds__(256) k_primary_ids(DevScene sc, DevCamera cam,
 
 __global__ void k_batch_begin(Counters* c, uint32_t n0) {
     const int t = threadIdx.x;
-    if (t <= PGRT_MAX_LEVELS) { c->n_rays[t] = t == 0 ? n0 : 0u; c->n_phong[t] = 0; c->n_diel[t] = 0; }
+    if (t <= PGRT_MAX_LEVELS) { c->n_rays[t] = t == 0 ? n0 : 0u; c->n_phong[t] = 0; c->n_diel[t] = 0; c->trace_next[t] = 0; }
     if (t == 0) { c->shadow = 0; c->reflection = 0; c->refraction = 0; c->q_head = 0; c->q_l1 = 0; c->q_tail = 0; }
 }
 __global__ void k_batch_end(Counters* c, unsigned long long primary, int dyn) {

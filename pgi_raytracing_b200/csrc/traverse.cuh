@@ -82,131 +82,158 @@ PG_HD uint32_t slab4f(float4 w, float4 nx, float4 ny, float4 nz, float4 fx, floa
     return hitmask;
 }
 
+// ---- per-ray constants of the two layouts, the visit of one node, and a resumable traversal built from them.
+// trav_advance runs a bounded number of while-while rounds, so the same code serves the run-to-completion queries
+// (trace_closest8 / trace_closest8f: shadow rays, pgrt_intersect, k_secondary, the CPU emulation) and the persistent
+// k_trace, which swaps finished rays for new ones between rounds.
+struct RayCtxF {                       // PGRT_LAYOUT_F32
+    V3 O, D; float tnear, tfar;
+    float idx, idy, idz, oodx, oody, oodz, pad_abs;
+    int onx, ony, onz, ofx, ofy, ofz;  // float4 offsets of the near / far planes inside a node, by ray sign
+    uint32_t octinv, sw1, sw2, sw4;    // delta-swap masks that move internal hit bits from 24 + s to 24 + (s ^ octinv)
+};
+struct RayCtxQ {                       // PGRT_LAYOUT_Q8
+    V3 O, D; float tnear, tfar;
+    float idx, idy, idz;
+    bool negx, negy, negz;
+    uint32_t octinv, octinv4;
+};
+
+PG_HD void ray_ctx_init(RayCtxF& r, V3 O, V3 D, float tnear, float tfar) {
+    r.O = O; r.D = D; r.tnear = tnear; r.tfar = tfar;
+    const float ooeps = 8.271806e-25f;   // 2^-80
+    r.idx = pg_rcp(fabsf(D.x) > ooeps ? D.x : copysignf(ooeps, D.x));
+    r.idy = pg_rcp(fabsf(D.y) > ooeps ? D.y : copysignf(ooeps, D.y));
+    r.idz = pg_rcp(fabsf(D.z) > ooeps ? D.z : copysignf(ooeps, D.z));
+    r.oodx = O.x * r.idx; r.oody = O.y * r.idy; r.oodz = O.z * r.idz;
+    // plane * idir - O * idir cancels when the origin is far from the box compared with t: the rounding of O * idir
+    // (2^-24 of its magnitude) is an ABSOLUTE error on t, so the culling bounds carry an absolute pad as well
+    r.pad_abs = 2.3841858e-7f * fmaxf(fmaxf(fabsf(r.oodx), fabsf(r.oody)), fabsf(r.oodz));   // 2^-22 * max |O * idir|
+    const bool negx = r.idx < 0.0f, negy = r.idy < 0.0f, negz = r.idz < 0.0f;
+    r.octinv = (negx ? 0u : 4u) | (negy ? 0u : 2u) | (negz ? 0u : 1u);
+    // plane p of half h sits at float4 3 + 2*p + h
+    r.onx = 3 + 2 * (negx ? 3 : 0); r.ony = 3 + 2 * (negy ? 4 : 1); r.onz = 3 + 2 * (negz ? 5 : 2);
+    r.ofx = 3 + 2 * (negx ? 0 : 3); r.ofy = 3 + 2 * (negy ? 1 : 4); r.ofz = 3 + 2 * (negz ? 2 : 5);
+    r.sw1 = (r.octinv & 1u) ? 0x55000000u : 0u; r.sw2 = (r.octinv & 2u) ? 0x33000000u : 0u; r.sw4 = (r.octinv & 4u) ? 0x0F000000u : 0u;
+}
+
+PG_HD void ray_ctx_init(RayCtxQ& r, V3 O, V3 D, float tnear, float tfar) {
+    r.O = O; r.D = D; r.tnear = tnear; r.tfar = tfar;
+    const float ooeps = 8.271806e-25f;
+    r.idx = pg_rcp(fabsf(D.x) > ooeps ? D.x : copysignf(ooeps, D.x));
+    r.idy = pg_rcp(fabsf(D.y) > ooeps ? D.y : copysignf(ooeps, D.y));
+    r.idz = pg_rcp(fabsf(D.z) > ooeps ? D.z : copysignf(ooeps, D.z));
+    r.negx = r.idx < 0.0f; r.negy = r.idy < 0.0f; r.negz = r.idz < 0.0f;
+    r.octinv = (r.negx ? 0u : 4u) | (r.negy ? 0u : 2u) | (r.negz ? 0u : 1u);
+    r.octinv4 = r.octinv * 0x01010101u;
+}
+
+// one node: returns the hit mask (bits 31..24 internal children in traversal priority order, bits 23..0 triangles)
+PG_HD uint32_t node_visit(const float4* __restrict__ nodes, uint32_t ni, const RayCtxF& r, float best_t, uint32_t& child_base, uint32_t& tri_base,
+                          uint32_t& imask) {
+    const float4* __restrict__ nd = nodes + PGRT_NODE_F4_F32 * (size_t)ni;
+    const float4 f0 = pg_ldg4(nd), w0 = pg_ldg4(nd + 1), w1 = pg_ldg4(nd + 2);
+    const float4 nx0 = pg_ldg4(nd + r.onx), ny0 = pg_ldg4(nd + r.ony), nz0 = pg_ldg4(nd + r.onz), fx0 = pg_ldg4(nd + r.ofx), fy0 = pg_ldg4(nd + r.ofy), fz0 = pg_ldg4(nd + r.ofz);
+    const float4 nx1 = pg_ldg4(nd + r.onx + 1), ny1 = pg_ldg4(nd + r.ony + 1), nz1 = pg_ldg4(nd + r.onz + 1), fx1 = pg_ldg4(nd + r.ofx + 1), fy1 = pg_ldg4(nd + r.ofy + 1), fz1 = pg_ldg4(nd + r.ofz + 1);
+    const float far_pad = pg_fma(best_t, 1.0000005f, r.pad_abs);
+    uint32_t hitmask = slab4f(w0, nx0, ny0, nz0, fx0, fy0, fz0, r.idx, r.idy, r.idz, r.oodx, r.oody, r.oodz, r.tnear, far_pad, r.pad_abs);
+    hitmask |= slab4f(w1, nx1, ny1, nz1, fx1, fy1, fz1, r.idx, r.idy, r.idz, r.oodx, r.oody, r.oodz, r.tnear, far_pad, r.pad_abs);
+    uint32_t x;
+    x = ((hitmask >> 1) ^ hitmask) & r.sw1; hitmask ^= x ^ (x << 1);
+    x = ((hitmask >> 2) ^ hitmask) & r.sw2; hitmask ^= x ^ (x << 2);
+    x = ((hitmask >> 4) ^ hitmask) & r.sw4; hitmask ^= x ^ (x << 4);
+    child_base = pg_f2u(f0.x); tri_base = pg_f2u(f0.y); imask = pg_f2u(f0.z);
+    return hitmask;
+}
+
+PG_HD uint32_t node_visit(const float4* __restrict__ nodes, uint32_t ni, const RayCtxQ& r, float best_t, uint32_t& child_base, uint32_t& tri_base,
+                          uint32_t& imask) {
+    const float4* __restrict__ nd = nodes + PGRT_NODE_F4_Q8 * (size_t)ni;
+    const float4 n0 = pg_ldg4(nd), n1 = pg_ldg4(nd + 1), n2 = pg_ldg4(nd + 2), n3 = pg_ldg4(nd + 3), n4 = pg_ldg4(nd + 4);
+    const uint32_t eb = pg_f2u(n0.w);
+    const float sx = pg_u2f((eb & 0xFFu) << 23) * r.idx, sy = pg_u2f(((eb >> 8) & 0xFFu) << 23) * r.idy, sz = pg_u2f(((eb >> 16) & 0xFFu) << 23) * r.idz;
+    const float ax = (n0.x - r.O.x) * r.idx, ay = (n0.y - r.O.y) * r.idy, az = (n0.z - r.O.z) * r.idz;
+    const float far_pad = best_t * 1.0000005f;
+    const uint32_t lox0 = pg_f2u(n2.x), lox1 = pg_f2u(n2.y), loy0 = pg_f2u(n2.z), loy1 = pg_f2u(n2.w);
+    const uint32_t loz0 = pg_f2u(n3.x), loz1 = pg_f2u(n3.y), hix0 = pg_f2u(n3.z), hix1 = pg_f2u(n3.w);
+    const uint32_t hiy0 = pg_f2u(n4.x), hiy1 = pg_f2u(n4.y), hiz0 = pg_f2u(n4.z), hiz1 = pg_f2u(n4.w);
+    uint32_t hitmask = slab4(pg_f2u(n1.z), r.negx ? hix0 : lox0, r.negy ? hiy0 : loy0, r.negz ? hiz0 : loz0, r.negx ? lox0 : hix0, r.negy ? loy0 : hiy0,
+                             r.negz ? loz0 : hiz0, sx, sy, sz, ax, ay, az, r.tnear, far_pad, r.octinv4);
+    hitmask |= slab4(pg_f2u(n1.w), r.negx ? hix1 : lox1, r.negy ? hiy1 : loy1, r.negz ? hiz1 : loz1, r.negx ? lox1 : hix1, r.negy ? loy1 : hiy1,
+                     r.negz ? loz1 : hiz1, sx, sy, sz, ax, ay, az, r.tnear, far_pad, r.octinv4);
+    child_base = pg_f2u(n1.x); tri_base = pg_f2u(n1.y); imask = eb >> 24;
+    return hitmask;
+}
+
+struct TravState {
+    uint2 ng;        // node group: x = first child node, y = hit bits (31..24) | imask (7..0)
+    uint2 tg;        // triangle group: x = first triangle, y = hit bits (23..0)
+    int sp;
+    HitRec best;
+};
+
+PG_HD void trav_init(TravState& s, float tfar) {
+    s.ng = make_uint2(0u, 0x80000000u); s.tg = make_uint2(0u, 0u); s.sp = 0;
+    s.best.t = tfar; s.best.u = 0.0f; s.best.v = 0.0f; s.best.tri = PGRT_INVALID_ID;
+}
+
+// Up to `rounds` while-while rounds (a lane descends until it holds triangles to test or runs out of nodes, then tests
+// them); returns true once the ray is finished.
+template <class RC, bool COUNT>
+PG_HD bool trav_advance(const float4* __restrict__ nodes, const float4* __restrict__ tris, const RC& r, TravState& s, uint2* stack, TravCount& tc, int rounds) {
+    for (int it = 0; it < rounds; ++it) {
+        while (s.tg.y == 0u) {
+            if (s.ng.y <= 0x00FFFFFFu) {
+                if (s.sp == 0) return true;
+                s.ng = stack[--s.sp];
+            }
+            const uint32_t hits = s.ng.y;
+            const int bit = pg_bfind(hits);
+            s.ng.y &= ~(1u << bit);
+            if (s.ng.y > 0x00FFFFFFu) stack[s.sp++] = s.ng;
+            const uint32_t slot = (uint32_t)(bit - 24) ^ r.octinv;
+            const uint32_t rel = (uint32_t)pg_popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
+            uint32_t child_base, tri_base, imask;
+            const uint32_t hitmask = node_visit(nodes, s.ng.x + rel, r, s.best.t, child_base, tri_base, imask);
+            if (COUNT) tc.nodes++;
+            s.ng.x = child_base;
+            s.ng.y = (hitmask & 0xFF000000u) | imask;
+            s.tg.x = tri_base;
+            s.tg.y = hitmask & 0x00FFFFFFu;
+        }
+        while (s.tg.y) {
+            const int bit = pg_bfind(s.tg.y);
+            s.tg.y &= ~(1u << bit);
+            if (COUNT) tc.tris++;
+            tri_test(tris, s.tg.x + (uint32_t)bit, r.O, r.D, r.tnear, r.tfar, s.best);
+        }
+    }
+    return false;
+}
+
+template <class RC, bool COUNT>
+PG_HD HitRec trace_closest_rc(const float4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t n_tris, V3 O, V3 D, float tnear, float tfar,
+                              TravCount& tc) {
+    TravState s;
+    trav_init(s, tfar);
+    if (n_tris == 0) return s.best;
+    RC r;
+    ray_ctx_init(r, O, D, tnear, tfar);
+    uint2 stack[PGRT_STACK8];
+    while (!trav_advance<RC, COUNT>(nodes, tris, r, s, stack, tc, 1 << 30)) {}
+    return s.best;
+}
+
 template <bool COUNT>
 PG_HD HitRec trace_closest8f(const float4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t n_tris, V3 O, V3 D,
                              float tnear, float tfar, TravCount& tc) {
-    HitRec best; best.t = tfar; best.u = 0.0f; best.v = 0.0f; best.tri = PGRT_INVALID_ID;
-    if (n_tris == 0) return best;
-    const float ooeps = 8.271806e-25f;   // 2^-80
-    const float idx = pg_rcp(fabsf(D.x) > ooeps ? D.x : copysignf(ooeps, D.x));
-    const float idy = pg_rcp(fabsf(D.y) > ooeps ? D.y : copysignf(ooeps, D.y));
-    const float idz = pg_rcp(fabsf(D.z) > ooeps ? D.z : copysignf(ooeps, D.z));
-    const float oodx = O.x * idx, oody = O.y * idy, oodz = O.z * idz;
-    // plane * idir - O * idir cancels when the origin is far from the box compared with t: the rounding of O * idir
-    // (2^-24 of its magnitude) is an ABSOLUTE error on t, so the culling bounds carry an absolute pad as well
-    const float pad_abs = 2.3841858e-7f * fmaxf(fmaxf(fabsf(oodx), fabsf(oody)), fabsf(oodz));   // 2^-22 * max |O * idir|
-    const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;
-    const uint32_t octinv = (negx ? 0u : 4u) | (negy ? 0u : 2u) | (negz ? 0u : 1u);
-    // near / far planes by ray sign, as float4 offsets inside the node (plane p of half h = 3 + 2*p + h)
-    const int onx = 3 + 2 * (negx ? 3 : 0), ony = 3 + 2 * (negy ? 4 : 1), onz = 3 + 2 * (negz ? 5 : 2);
-    const int ofx = 3 + 2 * (negx ? 0 : 3), ofy = 3 + 2 * (negy ? 1 : 4), ofz = 3 + 2 * (negz ? 2 : 5);
-    // internal hits sit at bit 24 + s; the traversal wants them at 24 + (s ^ octinv): three delta swaps, masked per ray
-    const uint32_t sw1 = (octinv & 1u) ? 0x55000000u : 0u, sw2 = (octinv & 2u) ? 0x33000000u : 0u, sw4 = (octinv & 4u) ? 0x0F000000u : 0u;
-    uint2 stack[PGRT_STACK8];
-    int sp = 0;
-    uint2 ng = make_uint2(0u, 0x80000000u);
-    uint2 tg = make_uint2(0u, 0u);
-    // while-while: a lane keeps descending until it holds triangles to test (or runs out of nodes), so the warp enters
-    // the triangle phase with as many lanes as possible instead of once per node step
-    for (;;) {
-        bool done = false;
-        while (tg.y == 0u) {
-            if (ng.y <= 0x00FFFFFFu) {
-                if (sp == 0) { done = true; break; }
-                ng = stack[--sp];
-            }
-            const uint32_t hits = ng.y;
-            const int bit = pg_bfind(hits);
-            ng.y &= ~(1u << bit);
-            if (ng.y > 0x00FFFFFFu) stack[sp++] = ng;
-            const uint32_t slot = (uint32_t)(bit - 24) ^ octinv;
-            const uint32_t rel = (uint32_t)pg_popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
-            const float4* __restrict__ nd = nodes + PGRT_NODE_F4_F32 * (size_t)(ng.x + rel);
-            const float4 f0 = pg_ldg4(nd), w0 = pg_ldg4(nd + 1), w1 = pg_ldg4(nd + 2);
-            const float4 nx0 = pg_ldg4(nd + onx), ny0 = pg_ldg4(nd + ony), nz0 = pg_ldg4(nd + onz), fx0 = pg_ldg4(nd + ofx), fy0 = pg_ldg4(nd + ofy), fz0 = pg_ldg4(nd + ofz);
-            const float4 nx1 = pg_ldg4(nd + onx + 1), ny1 = pg_ldg4(nd + ony + 1), nz1 = pg_ldg4(nd + onz + 1), fx1 = pg_ldg4(nd + ofx + 1), fy1 = pg_ldg4(nd + ofy + 1), fz1 = pg_ldg4(nd + ofz + 1);
-            if (COUNT) tc.nodes++;
-            const float far_pad = pg_fma(best.t, 1.0000005f, pad_abs);
-            uint32_t hitmask = slab4f(w0, nx0, ny0, nz0, fx0, fy0, fz0, idx, idy, idz, oodx, oody, oodz, tnear, far_pad, pad_abs);
-            hitmask |= slab4f(w1, nx1, ny1, nz1, fx1, fy1, fz1, idx, idy, idz, oodx, oody, oodz, tnear, far_pad, pad_abs);
-            uint32_t x;
-            x = ((hitmask >> 1) ^ hitmask) & sw1; hitmask ^= x ^ (x << 1);
-            x = ((hitmask >> 2) ^ hitmask) & sw2; hitmask ^= x ^ (x << 2);
-            x = ((hitmask >> 4) ^ hitmask) & sw4; hitmask ^= x ^ (x << 4);
-            ng.x = pg_f2u(f0.x);
-            ng.y = (hitmask & 0xFF000000u) | pg_f2u(f0.z);
-            tg.x = pg_f2u(f0.y);
-            tg.y = hitmask & 0x00FFFFFFu;
-        }
-        if (done) break;
-        while (tg.y) {
-            const int bit = pg_bfind(tg.y);
-            tg.y &= ~(1u << bit);
-            if (COUNT) tc.tris++;
-            tri_test(tris, tg.x + (uint32_t)bit, O, D, tnear, tfar, best);
-        }
-    }
-    return best;
+    return trace_closest_rc<RayCtxF, COUNT>(nodes, tris, n_tris, O, D, tnear, tfar, tc);
 }
 
 template <bool COUNT>
 PG_HD HitRec trace_closest8(const float4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t n_tris, V3 O, V3 D,
                             float tnear, float tfar, TravCount& tc) {
-    HitRec best; best.t = tfar; best.u = 0.0f; best.v = 0.0f; best.tri = PGRT_INVALID_ID;
-    if (n_tris == 0) return best;
-    const float ooeps = 8.271806e-25f;   // 2^-80
-    const float idx = pg_rcp(fabsf(D.x) > ooeps ? D.x : copysignf(ooeps, D.x));
-    const float idy = pg_rcp(fabsf(D.y) > ooeps ? D.y : copysignf(ooeps, D.y));
-    const float idz = pg_rcp(fabsf(D.z) > ooeps ? D.z : copysignf(ooeps, D.z));
-    const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;
-    const uint32_t octinv = (negx ? 0u : 4u) | (negy ? 0u : 2u) | (negz ? 0u : 1u);
-    const uint32_t octinv4 = octinv * 0x01010101u;
-    uint2 stack[PGRT_STACK8];
-    int sp = 0;
-    uint2 ng = make_uint2(0u, 0x80000000u);     // node group: x = first child node, y = hit bits (31..24) | imask (7..0)
-    uint2 tg = make_uint2(0u, 0u);              // triangle group: x = first triangle, y = hit bits (23..0)
-    for (;;) {                                  // while-while, see trace_closest8f
-        bool done = false;
-        while (tg.y == 0u) {
-            if (ng.y <= 0x00FFFFFFu) {
-                if (sp == 0) { done = true; break; }
-                ng = stack[--sp];
-            }
-            const uint32_t hits = ng.y;
-            const int bit = pg_bfind(hits);
-            ng.y &= ~(1u << bit);
-            if (ng.y > 0x00FFFFFFu) stack[sp++] = ng;
-            const uint32_t slot = (uint32_t)(bit - 24) ^ octinv;
-            const uint32_t rel = (uint32_t)pg_popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
-            const float4* __restrict__ nd = nodes + 5 * (size_t)(ng.x + rel);
-            const float4 n0 = pg_ldg4(nd), n1 = pg_ldg4(nd + 1), n2 = pg_ldg4(nd + 2), n3 = pg_ldg4(nd + 3), n4 = pg_ldg4(nd + 4);
-            if (COUNT) tc.nodes++;
-            const uint32_t eb = pg_f2u(n0.w);
-            const float sx = pg_u2f((eb & 0xFFu) << 23) * idx, sy = pg_u2f(((eb >> 8) & 0xFFu) << 23) * idy, sz = pg_u2f(((eb >> 16) & 0xFFu) << 23) * idz;
-            const float ax = (n0.x - O.x) * idx, ay = (n0.y - O.y) * idy, az = (n0.z - O.z) * idz;
-            const float far_pad = best.t * 1.0000005f;
-            // near / far planes by ray sign
-            const uint32_t lox0 = pg_f2u(n2.x), lox1 = pg_f2u(n2.y), loy0 = pg_f2u(n2.z), loy1 = pg_f2u(n2.w);
-            const uint32_t loz0 = pg_f2u(n3.x), loz1 = pg_f2u(n3.y), hix0 = pg_f2u(n3.z), hix1 = pg_f2u(n3.w);
-            const uint32_t hiy0 = pg_f2u(n4.x), hiy1 = pg_f2u(n4.y), hiz0 = pg_f2u(n4.z), hiz1 = pg_f2u(n4.w);
-            uint32_t hitmask = slab4(pg_f2u(n1.z), negx ? hix0 : lox0, negy ? hiy0 : loy0, negz ? hiz0 : loz0, negx ? lox0 : hix0, negy ? loy0 : hiy0,
-                                     negz ? loz0 : hiz0, sx, sy, sz, ax, ay, az, tnear, far_pad, octinv4);
-            hitmask |= slab4(pg_f2u(n1.w), negx ? hix1 : lox1, negy ? hiy1 : loy1, negz ? hiz1 : loz1, negx ? lox1 : hix1, negy ? loy1 : hiy1,
-                             negz ? loz1 : hiz1, sx, sy, sz, ax, ay, az, tnear, far_pad, octinv4);
-            ng.x = pg_f2u(n1.x);
-            ng.y = (hitmask & 0xFF000000u) | (eb >> 24);
-            tg.x = pg_f2u(n1.y);
-            tg.y = hitmask & 0x00FFFFFFu;
-        }
-        if (done) break;
-        while (tg.y) {
-            const int bit = pg_bfind(tg.y);
-            tg.y &= ~(1u << bit);
-            if (COUNT) tc.tris++;
-            tri_test(tris, tg.x + (uint32_t)bit, O, D, tnear, tfar, best);
-        }
-    }
-    return best;
+    return trace_closest_rc<RayCtxQ, COUNT>(nodes, tris, n_tris, O, D, tnear, tfar, tc);
 }
 
 #ifdef __CUDACC__
