@@ -124,7 +124,7 @@ struct pgrt_context {
     uint32_t* h_pin = nullptr;        // pinned scratch for small read-backs of the build
     size_t max_batch_samples = (size_t)1 << 23;
     size_t min_level_cap = (size_t)1 << 18;
-    double level_cap_factor = 2.0;
+    double level_cap_factor = 0.5;   // queue capacity of the deeper levels per primary sample (x4 for the one pool of the dynamic scheduler); overflow = retry in smaller batches
     pgrt_level_stats level_stats[PGRT_MAX_LEVELS + 1] = {};
     int level_stats_n = 0;
 

@@ -6,6 +6,7 @@
 #include <cctype>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -153,6 +154,171 @@ void idct_islow(const int* in /*dequantised, natural order*/, uint8_t* out, int 
 
 struct Component { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0; int bw = 0, bh = 0; std::vector<uint8_t> plane; int stride = 0; };
 
+
+// ------------------------------------------------------------------------------------------------ PNG
+// Non-interlaced 8-bit PNG (grey, grey+alpha, RGB, RGBA, palette) -> top-down BGR(A): zlib inflate (RFC 1950/1951:
+// stored, fixed and dynamic Huffman blocks) + the five scan-line filters of the PNG specification.  The reference
+// reaches the same bytes through FreeImage (pg1/texture.cpp:15-50; tutorial_2 loads data/test4.png, 64x32 RGBA).
+struct Inflater {
+    const uint8_t* p; const uint8_t* end; uint32_t acc = 0; int n = 0; bool bad = false;
+    int bit() { if (n == 0) { if (p >= end) { bad = true; return 0; } acc = *p++; n = 8; } const int b = acc & 1; acc >>= 1; --n; return b; }
+    uint32_t bits(int k) { uint32_t v = 0; for (int i = 0; i < k; ++i) v |= (uint32_t)bit() << i; return v; }
+};
+struct HuffTable {
+    uint16_t count[16] = {0}; uint16_t symbol[320] = {0};
+    void build(const uint8_t* lengths, int n) {
+        for (int i = 0; i < 16; ++i) count[i] = 0;
+        for (int i = 0; i < n; ++i) count[lengths[i]]++;
+        count[0] = 0;
+        uint16_t offs[16]; offs[1] = 0;
+        for (int i = 1; i < 15; ++i) offs[i + 1] = (uint16_t)(offs[i] + count[i]);
+        for (int i = 0; i < n; ++i) if (lengths[i]) symbol[offs[lengths[i]]++] = (uint16_t)i;
+    }
+    int decode(Inflater& in) const {
+        int code = 0, first = 0, index = 0;
+        for (int len = 1; len <= 15; ++len) {
+            code |= in.bit();
+            const int c = count[len];
+            if (code - c < first) return symbol[index + (code - first)];
+            index += c; first += c; first <<= 1; code <<= 1;
+            if (in.bad) return -1;
+        }
+        return -1;
+    }
+};
+
+bool inflate_zlib(const uint8_t* d, size_t size, std::vector<uint8_t>& out) {
+    if (size < 6) return false;
+    Inflater in; in.p = d + 2; in.end = d + size;      // 2-byte zlib header; the Adler-32 trailer is not checked
+    static const uint16_t LBASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    static const uint16_t LEXT[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    static const uint16_t DBASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+    static const uint16_t DEXT[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+    for (;;) {
+        const int last = in.bit();
+        const uint32_t type = in.bits(2);
+        if (in.bad) return false;
+        if (type == 0) {
+            in.n = 0;
+            if (in.p + 4 > in.end) return false;
+            const uint32_t len = in.p[0] | (in.p[1] << 8); in.p += 4;
+            if (in.p + len > in.end) return false;
+            out.insert(out.end(), in.p, in.p + len); in.p += len;
+        } else if (type == 1 || type == 2) {
+            HuffTable lit, dist; uint8_t lengths[320];
+            if (type == 1) {
+                for (int i = 0; i < 144; ++i) lengths[i] = 8;
+                for (int i = 144; i < 256; ++i) lengths[i] = 9;
+                for (int i = 256; i < 280; ++i) lengths[i] = 7;
+                for (int i = 280; i < 288; ++i) lengths[i] = 8;
+                lit.build(lengths, 288);
+                for (int i = 0; i < 30; ++i) lengths[i] = 5;
+                dist.build(lengths, 30);
+            } else {
+                const int nlen = (int)in.bits(5) + 257, ndist = (int)in.bits(5) + 1, ncode = (int)in.bits(4) + 4;
+                static const uint8_t ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+                uint8_t cl[19] = {0};
+                for (int i = 0; i < ncode; ++i) cl[ORDER[i]] = (uint8_t)in.bits(3);
+                HuffTable clt; clt.build(cl, 19);
+                int idx = 0;
+                while (idx < nlen + ndist) {
+                    const int sym = clt.decode(in);
+                    if (sym < 0) return false;
+                    if (sym < 16) lengths[idx++] = (uint8_t)sym;
+                    else {
+                        int rep, val = 0;
+                        if (sym == 16) { if (idx == 0) return false; val = lengths[idx - 1]; rep = 3 + (int)in.bits(2); }
+                        else if (sym == 17) rep = 3 + (int)in.bits(3);
+                        else rep = 11 + (int)in.bits(7);
+                        if (idx + rep > nlen + ndist) return false;
+                        while (rep--) lengths[idx++] = (uint8_t)val;
+                    }
+                }
+                lit.build(lengths, nlen); dist.build(lengths + nlen, ndist);
+            }
+            for (;;) {
+                const int sym = lit.decode(in);
+                if (sym < 0 || in.bad) return false;
+                if (sym < 256) out.push_back((uint8_t)sym);
+                else if (sym == 256) break;
+                else {
+                    if (sym > 285) return false;
+                    const int len = LBASE[sym - 257] + (int)in.bits(LEXT[sym - 257]);
+                    const int ds = dist.decode(in);
+                    if (ds < 0 || ds > 29) return false;
+                    const size_t dd = DBASE[ds] + in.bits(DEXT[ds]);
+                    if (dd > out.size()) return false;
+                    const size_t from = out.size() - dd;
+                    for (int i = 0; i < len; ++i) out.push_back(out[from + i]);
+                }
+            }
+        } else return false;
+        if (last) break;
+    }
+    return !in.bad;
+}
+
+bool decode_png(const uint8_t* d, size_t size, RawImage& out, std::string* error) {
+    static const uint8_t SIG[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    if (size < 33 || memcmp(d, SIG, 8) != 0) return fail(error, "not a PNG stream");
+    auto be32 = [&](size_t o) { return ((uint32_t)d[o] << 24) | ((uint32_t)d[o + 1] << 16) | ((uint32_t)d[o + 2] << 8) | d[o + 3]; };
+    int w = 0, h = 0, depth = 0, ctype = 0, interlace = 0;
+    std::vector<uint8_t> idat, plte, trns;
+    for (size_t i = 8; i + 12 <= size;) {
+        const uint32_t len = be32(i);
+        if (i + 12 + (size_t)len > size) return fail(error, "truncated PNG chunk");
+        const uint8_t* c = d + i + 8;
+        if (!memcmp(d + i + 4, "IHDR", 4)) { w = (int)be32(i + 8); h = (int)be32(i + 12); depth = c[8]; ctype = c[9]; interlace = c[12]; }
+        else if (!memcmp(d + i + 4, "PLTE", 4)) plte.assign(c, c + len);
+        else if (!memcmp(d + i + 4, "tRNS", 4)) trns.assign(c, c + len);
+        else if (!memcmp(d + i + 4, "IDAT", 4)) idat.insert(idat.end(), c, c + len);
+        else if (!memcmp(d + i + 4, "IEND", 4)) break;
+        i += 12 + (size_t)len;
+    }
+    if (w <= 0 || h <= 0 || depth != 8 || interlace != 0) return fail(error, "unsupported PNG (8-bit non-interlaced only)");
+    int ch;
+    switch (ctype) { case 0: ch = 1; break; case 2: ch = 3; break; case 3: ch = 1; break; case 4: ch = 2; break; case 6: ch = 4; break; default: return fail(error, "unsupported PNG colour type"); }
+    std::vector<uint8_t> raw;
+    raw.reserve((size_t)(w * ch + 1) * h);
+    if (!inflate_zlib(idat.data(), idat.size(), raw) || raw.size() < (size_t)(w * ch + 1) * h) return fail(error, "PNG inflate failed");
+    const int stride = w * ch;
+    std::vector<uint8_t> img((size_t)stride * h);
+    for (int y = 0; y < h; ++y) {
+        const uint8_t f = raw[(size_t)y * (stride + 1)];
+        const uint8_t* src = &raw[(size_t)y * (stride + 1) + 1];
+        uint8_t* dst = &img[(size_t)y * stride];
+        const uint8_t* up = y ? dst - stride : nullptr;
+        for (int x = 0; x < stride; ++x) {
+            const int a = x >= ch ? dst[x - ch] : 0, b = up ? up[x] : 0, c = (up && x >= ch) ? up[x - ch] : 0;
+            int v = src[x];
+            switch (f) {
+                case 0: break;
+                case 1: v += a; break;
+                case 2: v += b; break;
+                case 3: v += (a + b) >> 1; break;
+                case 4: { const int pa = abs(b - c), pb = abs(a - c), pc = abs(a + b - 2 * c); v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); } break;
+                default: return fail(error, "bad PNG filter");
+            }
+            dst[x] = (uint8_t)v;
+        }
+    }
+    const bool alpha = ctype == 4 || ctype == 6 || (ctype == 3 && !trns.empty());
+    alloc_bgr(out, w, h, alpha ? 4 : 3);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const uint8_t* s = &img[(size_t)y * stride + (size_t)x * ch];
+            uint8_t r, g, b, a = 255;
+            if (ctype == 0) { r = g = b = s[0]; }
+            else if (ctype == 4) { r = g = b = s[0]; a = s[1]; }
+            else if (ctype == 3) {
+                if ((size_t)s[0] * 3 + 2 >= plte.size()) return fail(error, "PNG palette index out of range");
+                r = plte[s[0] * 3]; g = plte[s[0] * 3 + 1]; b = plte[s[0] * 3 + 2]; a = s[0] < trns.size() ? trns[s[0]] : 255;
+            } else { r = s[0]; g = s[1]; b = s[2]; if (ctype == 6) a = s[3]; }
+            uint8_t* o = &out.bytes[(size_t)y * out.pitch + (size_t)x * out.bpp];
+            o[0] = b; o[1] = g; o[2] = r; if (alpha) o[3] = a;
+        }
+    return true;
+}
 }  // namespace
 
 bool DecodeJpeg(const uint8_t* d, size_t size, RawImage& out, std::string* error) {
@@ -317,6 +483,7 @@ bool LoadImageFile(const char* file_name, RawImage& out, std::string* error) {
     std::vector<uint8_t> d;
     if (!read_all(file_name, d)) return fail(error, "cannot open image file");
     if (d.size() >= 2 && d[0] == 0xFF && d[1] == 0xD8) return DecodeJpeg(d.data(), d.size(), out, error);
+    if (d.size() >= 8 && d[0] == 0x89 && d[1] == 'P' && d[2] == 'N' && d[3] == 'G') return decode_png(d.data(), d.size(), out, error);
     if (d.size() >= 2 && d[0] == 'P' && d[1] == '6') {          // binary PPM, maxval 255
         size_t p = 2; int vals[3], got = 0;
         while (got < 3 && p < d.size()) {
@@ -348,7 +515,7 @@ bool LoadImageFile(const char* file_name, RawImage& out, std::string* error) {
         for (int y = 0; y < h; ++y) memcpy(&out.bytes[(size_t)y * out.pitch], &d[off + (size_t)(top_down ? y : h - 1 - y) * src_pitch], (size_t)w * bpp);
         return true;
     }
-    return fail(error, "unknown image format (JPEG, PPM P6 and BMP are supported)");
+    return fail(error, "unknown image format (JPEG, PNG, PPM P6 and BMP are supported)");
 }
 
 static inline uint8_t to8(float c) { if (!(c == c)) return 0; c = c < 0.f ? 0.f : (c > 1.f ? 1.f : c); return (uint8_t)std::floor(c * 255.0f + 0.5f); }

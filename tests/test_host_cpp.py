@@ -277,3 +277,42 @@ def test_pg1_b200_executable(tmp_path, cornell):
     assert f"Surfaces = {len(sc.meshes)}" in out.stdout and "Mrays/s" in out.stdout
     img = np.asarray(Image.open(str(tmp_path / "frame.ppm")))
     assert img.shape == (64, 96, 3) and img.std() > 5
+
+
+@pytest.mark.parametrize("mode,size,level", [("RGBA", (64, 32), 9), ("RGB", (37, 21), 6), ("L", (50, 7), 1), ("LA", (9, 40), 9), ("P", (33, 33), 9), ("RGB", (300, 200), 0)])
+def test_png_decoder(host, tmp_path, mode, size, level):
+    """8-bit non-interlaced PNG (zlib inflate incl. stored / fixed / dynamic blocks, all five filters) -> top-down BGR(A)."""
+    from PIL import Image
+    w, h = size
+    rgb = _test_picture(w, h, w * 3 + h)
+    rng = np.random.default_rng(w + h)
+    alpha = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    if mode == "RGBA":
+        im = Image.fromarray(np.dstack([rgb, alpha]), "RGBA")
+    elif mode == "LA":
+        im = Image.fromarray(np.dstack([rgb[..., 0], alpha]), "LA")
+    elif mode == "L":
+        im = Image.fromarray(rgb[..., 1], "L")
+    elif mode == "P":
+        im = Image.fromarray(rgb).quantize(64)
+    else:
+        im = Image.fromarray(rgb)
+    p = str(tmp_path / "t.png")
+    im.save(p, "PNG", compress_level=level)
+    ref = np.asarray(Image.open(p).convert("RGBA" if mode in ("RGBA", "LA") else "RGB"))
+    buf, ww, hh, pitch, bpp = load_image(host, p)
+    assert (ww, hh, bpp) == (w, h, ref.shape[-1]) and pitch == (w * bpp + 3) // 4 * 4
+    got = buf[:, :bpp * w].reshape(h, w, bpp)
+    assert np.array_equal(got[..., 2::-1], ref[..., :3])
+    if bpp == 4:
+        assert np.array_equal(got[..., 3], ref[..., 3])
+
+
+def test_tutorial_2_fixture_through_the_cpp_texture(host):
+    """pg1/tutorials.cpp:170-178 loads data/test4.png; the committed golden holds its FreeImage-style BGRA bytes."""
+    p = "/root/reference/data/test4.png"
+    if not os.path.exists(p):
+        pytest.skip("reference data not mounted")
+    buf, w, h, pitch, bpp = load_image(host, p)
+    assert (w, h, bpp) == (64, 32, 4)
+    assert np.array_equal(buf, np.load(os.path.join(GOLDEN, "test4_bgra.npy")))
