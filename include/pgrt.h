@@ -63,7 +63,10 @@ typedef struct pgrt_render_params {
                                  2 normal shader (the commented block raytracer.cpp:274-280)                 */
     int32_t scheduler;        /* 0 dynamic: one persistent kernel owns every ray of level >= 1 (default);
                                  1 level-synchronous wavefront (one queue per recursion level).  Same image, bit for bit. */
-    int32_t reserved[6];
+    int32_t shadow_mode;      /* 0 is_illuminated as shipped (shadow rays that leave the light towards the hit POSITION,
+                                 raytracer.cpp:150-176, LightSource.cpp:11-32: the parity contract); 1 the hard shadows of the
+                                 README's to-do list (README.md:20): hit point -> light.  Non-default, no reference counterpart. */
+    int32_t reserved[5];
 } pgrt_render_params;
 
 typedef struct pgrt_build_stats {

@@ -30,7 +30,7 @@ class Light(C.Structure):
 class RenderParams(C.Structure):
     _fields_ = [("sampling_width", C.c_int32), ("jitter", C.c_int32), ("focal_distance", C.c_float), ("aperture", C.c_float),
                 ("max_depth", C.c_int32), ("gamma_level", C.c_float), ("seed", C.c_uint32), ("camera_mode", C.c_int32),
-                ("shader_mode", C.c_int32), ("scheduler", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("shader_mode", C.c_int32), ("scheduler", C.c_int32), ("shadow_mode", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class BuildStats(C.Structure):

@@ -566,6 +566,7 @@ static int validate_frame(pgrt_context* ctx, const pgrt_render_params* p) {
     if (p->sampling_width < 1 || p->sampling_width > 64) return ctx->fail(PGRT_ERR_INVALID, "render: sampling_width out of range [1,64]");
     if (p->max_depth < 0 || p->max_depth >= PGRT_MAX_LEVELS) return ctx->fail(PGRT_ERR_INVALID, "render: max_depth out of range [0,32]");
     if (p->scheduler != 0 && p->scheduler != 1) return ctx->fail(PGRT_ERR_INVALID, "render: scheduler must be 0 (dynamic) or 1 (level-synchronous)");
+    if (p->shadow_mode != 0 && p->shadow_mode != 1) return ctx->fail(PGRT_ERR_INVALID, "render: shadow_mode must be 0 (as shipped) or 1 (hit point -> light)");
     return upload_tables(ctx);
 }
 

@@ -322,7 +322,23 @@ __device__ __forceinline__ float4 phong_eval(const DevScene& sc, const pgrt_rend
         const pgrt_light& light = sc.lights[li];
         const V3 lp = v3(light.position[0], light.position[1], light.position[2]);
         bool lit = false;
-        if (!(dot3(f.n, lp) < 0)) {                                         // :155
+        if (p.shadow_mode == 1) {
+            // README "To do: hard shadows" (README.md:20), behind a non-default flag: the ray the reference meant to
+            // cast -- from the hit point towards the light, in units of that segment -- with the same rule that the
+            // closest occluder decides and a dielectric one does not shadow.  Not part of the parity contract.
+            const V3 to_light = v3(lp.x - f.hitp.x, lp.y - f.hitp.y, lp.z - f.hitp.z);
+            if (!(dot3(f.n, to_light) < 0)) {
+                my_shadow++;
+                TravCount tc; tc.nodes = 0; tc.tris = 0;
+                const HitRec sh = trace_closest_t<COUNT>(sc, f.hitp, to_light, 1e-3f, 1.0f, tc);
+                if (COUNT) { acc.nodes += tc.nodes; acc.tris += tc.tris; acc.mx = max(acc.mx, tc.nodes); }
+                if (sh.tri == PGRT_INVALID_ID) lit = true;
+                else {
+                    const uint32_t g = __float_as_uint(__ldg(sc.shade + 4 * (size_t)sh.tri + 3).w);
+                    lit = sc.materials[sc.geom_material[g]].type == 4;
+                }
+            }
+        } else if (!(dot3(f.n, lp) < 0)) {                                  // :155
             // the shadow ray leaves the light with the hit POSITION as its direction (sic, LightSource.cpp:18-20)
             const float tfar = l2norm3(v3(lp.x - f.hitp.x, lp.y - f.hitp.y, lp.z - f.hitp.z));
             my_shadow++;

@@ -492,3 +492,19 @@ def test_graph_replay_of_frames(P, cornell, monkeypatch):
     monkeypatch.setenv("PGRT_GRAPHS", "0")
     plain = P.raytracer_for(cornell)
     assert np.array_equal(plain.render(p)[0], frames[0][0], equal_nan=True)
+
+
+def test_hard_shadows_flag_is_opt_in(P, cornell):
+    """shadow_mode = 1 (README to-do 'hard shadows', no reference counterpart): shadows appear -- fewer lit Phong hits,
+    some pixels darker, none brighter than 1 LSB -- and the default stays the shipped behaviour, bit for bit."""
+    rt = P.raytracer_for(cornell)
+    p = dict(sampling_width=1, jitter=0, aperture=0.0)
+    a, sa = rt.render(p); b, sb = rt.render(dict(p, shadow_mode=1)); c, _ = rt.render(dict(p, shadow_mode=0))
+    assert np.array_equal(a, c, equal_nan=True)
+    qa, qb = P.to_srgb8(a).astype(int), P.to_srgb8(b).astype(int)
+    # hard shadows only remove light from Phong hits seen directly; through glass the non-linear mix may move either way
+    assert (qb.sum(-1) < qa.sum(-1) - 6).mean() > 0.01
+    assert sb["primary"] == sa["primary"] and sb["shadow"] > 0
+    for bad in (2, -1):
+        with pytest.raises(P.PgrtError):
+            rt.render(dict(p, shadow_mode=bad))
