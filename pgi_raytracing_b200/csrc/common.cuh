@@ -109,6 +109,15 @@ PG_HD V3 e_cross(V3 a, V3 b) {
 #ifdef __CUDACC__
 __device__ __forceinline__ float f_expf(float x) { return (float)exp((double)x); }
 __device__ __forceinline__ float f_powf(float x, float y) { return (float)pow((double)x, (double)y); }
+// the same for a small whole exponent (MTL "Ns 32"): square-and-multiply in double is within 3 ulp of a DOUBLE of pow(),
+// which never survives the rounding to float; saves the ~200-instruction double pow per lit Phong hit
+__device__ __forceinline__ float f_powf_whole(float x, float y) {
+    const int n = (int)y;
+    if ((float)n != y || n < 1 || n > 256) return f_powf(x, y);
+    double b = (double)x, r = 1.0;
+    for (int e = n; e; e >>= 1) { if (e & 1) r *= b; if (e > 1) b *= b; }
+    return (float)r;
+}
 __device__ __forceinline__ float f_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
 __device__ __forceinline__ float f_asinf(float x) { return (float)asin((double)x); }
 #endif

@@ -140,8 +140,30 @@ __global__ void __launch_bounds__(256) k_raygen(DevCamera cam, pgrt_render_param
 
 // Level 0 without a stored ray queue: the primary ray of slot j is a pure function of (camera, params, shard, j), so
 // k_trace / k_shade / k_phong regenerate it instead of reading 32 B that k_raygen would have had to write first
-// (66 MB written + 3 x 66 MB read per 1080p frame otherwise).  `on` = 0 reads the level's stored rays.
+// (66 MB written + 3 x 66 MB read per 1080p frame otherwise); it stores the direction (16 B) for the shading kernels,
+// which recompute only the origin.  `on` = 0 reads the level's stored rays.
 struct Gen0 { DevCamera cam; ShardInfo sh; uint32_t slot0, n_slots; int spp; int on; };
+
+// origin only (the part of primary_ray that needs no normalisation): camera position plus the lens shift
+__device__ __forceinline__ float4 primary_origin(const DevCamera& cam, const pgrt_render_params& p, int xp, int yp, int s) {
+    if (p.camera_mode == 1) return make_float4(cam.from.x, cam.from.y, cam.from.z, 0.001f);
+    const uint32_t pixel = (uint32_t)(yp * cam.width + xp);
+    const float l1 = p.aperture != 0.0f ? rng_uniform(-p.aperture / 2.0f, p.aperture / 2.0f, rng_u01(p.seed, pixel, (uint32_t)s, 2)) : 0.0f;
+    const float l2 = p.aperture != 0.0f ? rng_uniform(-p.aperture / 2.0f, p.aperture / 2.0f, rng_u01(p.seed, pixel, (uint32_t)s, 3)) : 0.0f;
+    const V3 shift = mul3(cam.M, v3(l1, l2, 0.0f));
+    return make_float4(cam.from.x + shift.x, cam.from.y + shift.y, cam.from.z + shift.z, 0.01f);
+}
+
+// k_shade / k_phong at level 0: k_trace has stored the direction it generated (16 B); only the origin is recomputed
+__device__ __forceinline__ void load_ray_shade(const LevelBufs& L, const Gen0& g, const pgrt_render_params& p, uint32_t j, float4& o, float4& d) {
+    d = L.ray_d[j];
+    if (!g.on) { o = L.ray_o[j]; return; }
+    o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d.w < 0.0f) return;
+    int x, y;
+    slot_to_pixel(g.sh, g.cam.width, g.cam.height, g.slot0 + j / (uint32_t)g.spp, x, y);
+    o = primary_origin(g.cam, p, x, y, (int)(j % (uint32_t)g.spp));
+}
 
 __device__ __forceinline__ void load_ray(const LevelBufs& L, const Gen0& g, const pgrt_render_params& p, uint32_t j, float4& o, float4& d) {
     if (!g.on) { o = L.ray_o[j]; d = L.ray_d[j]; return; }
@@ -185,6 +207,7 @@ __device__ __forceinline__ void trace_queue(const DevScene& sc, const pgrt_rende
                 if (mine < n) {
                     float4 o, d;
                     load_ray(L, g0, p, mine, o, d);
+                    if (g0.on) L.ray_d[mine] = d;      // the shading kernels read it back instead of re-normalising three times
                     if (d.w >= 0.0f && sc.n_tris != 0) {
                         j = mine;
                         ray_ctx_init(r, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, FLT_MAX);
@@ -206,8 +229,11 @@ __device__ __forceinline__ void trace_queue(const DevScene& sc, const pgrt_rende
     if (COUNT) flush_trav_counts(my_nodes, my_tris, my_max, &cnt->lv_nodes[level], &cnt->lv_tris[level], &cnt->lv_max_nodes[level]);
 }
 
+#ifndef PGRT_TRACE_MIN_BLOCKS
+#define PGRT_TRACE_MIN_BLOCKS 6   // register cap of k_trace = 65536 / (128 * this)
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace(DevScene sc, pgrt_render_params p, Gen0 g0, LevelBufs L, int level, int refill, Counters* cnt) {
+__global__ void __launch_bounds__(128, PGRT_TRACE_MIN_BLOCKS) k_trace(DevScene sc, pgrt_render_params p, Gen0 g0, LevelBufs L, int level, int refill, Counters* cnt) {
     const uint32_t n = min(cnt->n_rays[level], L.cap);
     if (sc.node_layout == PGRT_LAYOUT_F32) trace_queue<RayCtxF, COUNT>(sc, p, g0, L, level, cnt, n, refill);
     else trace_queue<RayCtxQ, COUNT>(sc, p, g0, L, level, cnt, n, refill);
@@ -362,7 +388,7 @@ __device__ __forceinline__ float4 phong_eval(const DevScene& sc, const pgrt_rend
             if (p.shader_mode == 1) {
                 blue += i_d_b * m_d_b * ndl; green += i_d_g * m_d_g * ndl; red += i_d_r * m_d_r * ndl;
             } else {
-                const float spec = f_powf(dot3(camera_vector, l_r), mat.shininess);
+                const float spec = f_powf_whole(dot3(camera_vector, l_r), mat.shininess);
                 blue += (i_d_b * m_d_b * ndl + i_s_b * m_s_b * spec);
                 green += (i_d_g * m_d_g * ndl + i_s_g * m_s_g * spec);
                 red += (i_d_r * m_d_r * ndl + i_s_r * m_s_r * spec);
@@ -395,7 +421,7 @@ __global__ void __launch_bounds__(256) k_shade(DevScene sc, pgrt_render_params p
         bool is_phong = false, is_diel = false;
         if (i < n) {
             float4 o, d;
-            load_ray(L, g0, p, i, o, d);
+            load_ray_shade(L, g0, p, i, o, d);
             shade_classify(sc, p, level, o, d, L.hit[i], s);
             is_phong = s.kind == SK_PHONG; is_diel = s.kind == SK_DIEL;
             if (s.kind == SK_FINAL) L.color[i] = s.color;
@@ -453,7 +479,7 @@ __global__ void __launch_bounds__(128) k_phong(DevScene sc, pgrt_render_params p
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint32_t i = L.phong_list[k];
         float4 o, d;
-        load_ray(L, g0, p, i, o, d);
+        load_ray_shade(L, g0, p, i, o, d);
         const float4 h = L.hit[i];
         const HitFrame f = hit_frame(sc, o, d, h);
         L.color[i] = phong_eval<COUNT>(sc, p, o, d, f, my_shadow, acc);
