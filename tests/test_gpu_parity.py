@@ -416,6 +416,18 @@ def test_errors_are_reported_not_thrown(P):
         rt.render(dict(sampling_width=0))
     with pytest.raises(P.PgrtError):
         rt.render(dict(max_depth=64))
+    # maximum size: flat triangle ids are 29 bits; the call is refused before a single byte is read
+    import ctypes as C
+    dummy = np.zeros(18, np.float32)
+    rc = rt.lib.pgrt_add_mesh(rt.h, dummy.ctypes.data, dummy.ctypes.data, dummy.ctypes.data, 1 << 29, 0, None)
+    assert rc == 1 and b"2^29" in rt.lib.pgrt_last_error(rt.h)
+    # a mesh that names a material nobody set is reported at render time, not dereferenced
+    g = C.c_uint32()
+    assert rt.lib.pgrt_add_mesh(rt.h, dummy.ctypes.data, dummy.ctypes.data, dummy.ctypes.data, 2, 7, C.byref(g)) == 0
+    rt.commit()
+    with pytest.raises(P.PgrtError) as e2:
+        rt.render(dict())
+    assert "material" in str(e2.value)
 
 
 def test_two_ranks_p2p_and_nccl_gather_are_bit_identical():
