@@ -123,6 +123,7 @@ struct pgrt_context {
     DevBuf<uint4> flush_buf;          // pgrt_debug_flush_l2
     uint32_t* h_pin = nullptr;        // pinned scratch for small read-backs of the build
     size_t max_batch_samples = (size_t)1 << 23;
+    uint64_t batch_limit = 0;         // pixel slots per batch that last survived a queue overflow (0 = none yet); reset by pgrt_commit
     size_t min_level_cap = (size_t)1 << 18;
     double level_cap_factor = 0.5;   // queue capacity of the deeper levels per primary sample (x4 for the one pool of the dynamic scheduler); overflow = retry in smaller batches
     pgrt_level_stats level_stats[PGRT_MAX_LEVELS + 1] = {};
@@ -321,7 +322,7 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
     sync_all_slots(ctx);
     cudaStream_t st = ctx->stream;
     const uint32_t N = (uint32_t)ctx->h_tri_geom.size();
-    ctx->n_tris = N; ctx->px_valid = false;
+    ctx->n_tris = N; ctx->px_valid = false; ctx->batch_limit = 0;
     pgrt_build_stats bs = {}; bs.triangles = N;
     const uint32_t G = (uint32_t)ctx->h_geom_first.size();
     CUDA_TRY(ctx->d_geom_first.ensure(G)); CUDA_TRY(ctx->d_geom_material.ensure(G));
@@ -781,6 +782,7 @@ static int frame_begin(pgrt_context* ctx, int slot, const pgrt_render_params* p,
     const uint64_t total_slots = shard_slots(ctx);
     uint64_t batch_slots = std::max<uint64_t>(PGRT_TILE_PIXELS, ctx->max_batch_samples / SPP / PGRT_TILE_PIXELS * PGRT_TILE_PIXELS);
     S.batch_slots = std::min(batch_slots, total_slots);
+    if (ctx->batch_limit) S.batch_slots = std::min(S.batch_slots, ctx->batch_limit);   // do not overflow the same way every frame
     S.rs = pgrt_render_stats{};
     rc = enqueue_frame(ctx, S);
     if (rc) return rc;
@@ -807,6 +809,7 @@ static int frame_end(pgrt_context* ctx, int slot, pgrt_render_stats* stats) {
         if (rc) return rc;
     }
     pgrt_render_stats& rs = S.rs;
+    if (rs.overflow_retries) ctx->batch_limit = S.batch_slots;
     const Counters& hc = *S.h_counters;
     rs.rays_primary = hc.tot_primary; rs.rays_shadow = hc.tot_shadow; rs.rays_reflection = hc.tot_reflection; rs.rays_refraction = hc.tot_refraction;
     cudaEventElapsedTime(&rs.frame_ms, S.ev_frame0, S.ev_frame1);

@@ -17,6 +17,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <functional>
+#include <thread>
 
 namespace {
 
@@ -62,17 +65,20 @@ std::string second_token(const char* b, const char* e) {
     return std::string(t, b);
 }
 
-// "%*s %f %f %f" with scanf's partial-assignment behaviour: stops at the first field that does not parse
+// "%*s %f %f %f" with scanf's partial-assignment behaviour: stops at the first field that does not parse.
+// Parses in place (no per-line allocation: the workers of LoadOBJ would serialise on the allocator): the buffer is
+// NUL-terminated and a number never contains the '\n' that ends the line, so strtof cannot run past it.
 int scan_floats(const char* b, const char* e, float* dst[], int n) {
-    std::string tmp(b, e);
-    const char* s = tmp.c_str();
-    while (*s && isspace((unsigned char)*s)) ++s;
-    while (*s && !isspace((unsigned char)*s)) ++s;
+    const char* s = b;
+    while (s < e && isspace((unsigned char)*s)) ++s;
+    while (s < e && !isspace((unsigned char)*s)) ++s;
     int got = 0;
     for (; got < n; ++got) {
+        while (s < e && isspace((unsigned char)*s)) ++s;
+        if (s >= e) break;
         char* after = nullptr;
         const float v = strtof(s, &after);
-        if (after == s) break;
+        if (after == s || after > e) break;
         *dst[got] = v;
         s = after;
     }
@@ -168,39 +174,114 @@ int LoadMTL(const char* file_name, const char* path, std::vector<Material*>& mat
     return 0;
 }
 
+namespace {
+
+// What one worker extracts from its slice of the file (whole lines only).  Floats and face indices -- where the time
+// goes -- are parsed here, in parallel; everything that depends on file order is replayed sequentially afterwards.
+struct FaceRec { int idx[4][3]; int corners; };             // corners: 3, 4, or 0 = a line the loader skips
+struct Event { char type; uint32_t a, b; };                 // 'g' / 'u' / 'm': text[a, b) is the line; 'f': a = index into faces
+struct Slice {
+    std::vector<Vector3> vertices, normals; std::vector<Coord2f> tex_coords;
+    std::vector<FaceRec> faces; std::vector<Event> events;
+};
+
+void parse_slice(const std::string& text, size_t lo, size_t hi, bool flip_yz, Slice& out) {
+    const char* p = text.data() + lo; const char* end = text.data() + hi;
+    while (p < end) {
+        while (p < end && *p == '\n') ++p;
+        if (p >= end) break;
+        const char* b = p;
+        while (p < end && *p != '\n') ++p;
+        const char* e = p;
+        switch (*b) {
+        case 'v':
+            if (e - b >= 2) {
+                Vector3 v; float* q[3] = {&v.x, &v.y, &v.z};
+                if (b[1] == ' ' || b[1] == 'n') {
+                    if (flip_yz) { q[1] = &v.z; q[2] = &v.y; }
+                    scan_floats(b, e, q, 3);
+                    if (flip_yz) v.y *= -1;
+                    if (b[1] == 'n') { v.Normalize(); out.normals.push_back(v); } else out.vertices.push_back(v);
+                } else if (b[1] == 't') {
+                    Coord2f t{0.0f, 0.0f}; float w = 0; float* r[3] = {&t.u, &t.v, &w};
+                    scan_floats(b, e, r, 3);
+                    out.tex_coords.push_back(t);
+                }
+            }
+            break;
+        case 'g': case 'u': case 'm':
+            out.events.push_back(Event{*b, (uint32_t)(b - text.data()), (uint32_t)(e - text.data())});
+            break;
+        case 'f': {
+            FaceRec f; f.corners = 0;
+            const char *tb = b, *te = e;
+            trim(tb, te);
+            int spaces = 0;
+            for (const char* c = tb; c < te; ++c) spaces += (*c == ' ');
+            if (spaces == 3 || spaces == 4) {
+                bool ok = true;
+                const char* c = tb;
+                while (c < te && !isspace((unsigned char)*c)) ++c;      // the "f" token
+                for (int k = 0; k < spaces && ok; ++k) {
+                    while (c < te && isspace((unsigned char)*c)) ++c;
+                    const char* t = c;
+                    while (c < te && !isspace((unsigned char)*c)) ++c;
+                    ok = parse_corner(t, c, f.idx[k]);
+                }
+                if (ok) f.corners = spaces;
+            }
+            out.events.push_back(Event{'f', (uint32_t)out.faces.size(), 0});
+            out.faces.push_back(f);
+        } break;
+        default: break;
+        }
+    }
+}
+
+}  // namespace
+
 int LoadOBJ(const char* file_name, std::vector<Surface*>& surfaces, std::vector<Material*>& materials, const bool flip_yz,
             const Vector3 /*default_color: vertex colours are never read by the path*/, TextureCache* cache) {
     std::string text;
     if (!read_file(file_name, text)) return -1;
+    if (text.size() >= 0xFFFFFFFFull) { printf("File %s is larger than 4 GiB.\n", file_name); return -1; }
     std::string path;
     if (const char* slash = strrchr(file_name, '/')) path.assign(file_name, slash - file_name + 1);
 
-    // material libraries first (the reference's first pass): they do not depend on anything else in the file
-    {
-        Lines lines(text);
-        const char *b, *e;
-        while (lines.next(b, e))
-            if (*b == 'm') LoadMTL((path + second_token(b, e)).c_str(), path.c_str(), materials, cache);
+    // ---- parallel part: the file is cut at line ends into one slice per hardware thread
+    unsigned n_threads = std::thread::hardware_concurrency();
+    if (const char* e = getenv("PG1_LOADER_THREADS")) n_threads = (unsigned)atoi(e);
+    n_threads = std::max(1u, std::min(n_threads, 64u));
+    if (text.size() < (1u << 20)) n_threads = 1;
+    std::vector<size_t> cut(n_threads + 1, text.size());
+    cut[0] = 0;
+    for (unsigned t = 1; t < n_threads; ++t) {
+        size_t c = std::max(cut[t - 1], text.size() / n_threads * t);
+        while (c < text.size() && text[c] != '\n') ++c;
+        cut[t] = c;
     }
-    // one pass for coordinates and faces: OBJ indices are absolute, so a face may only refer to records that the
-    // reference's separate second pass would also have collected -- all of them.  Collect first, then build.
+    std::vector<Slice> slices(n_threads);
+    {
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < n_threads; ++t) pool.emplace_back(parse_slice, std::cref(text), cut[t], cut[t + 1], flip_yz, std::ref(slices[t]));
+        parse_slice(text, cut[0], cut[1], flip_yz, slices[0]);
+        for (auto& th : pool) th.join();
+    }
+
+    // ---- sequential part, in file order.  Material libraries first (the reference's first pass)
+    for (const Slice& sl : slices)
+        for (const Event& ev : sl.events)
+            if (ev.type == 'm') LoadMTL((path + second_token(text.data() + ev.a, text.data() + ev.b)).c_str(), path.c_str(), materials, cache);
+    // all coordinates of the file (OBJ indices are absolute: a face may name any record, as in the reference's second pass)
     std::vector<Vector3> vertices, normals; std::vector<Coord2f> tex_coords;
     {
-        Lines lines(text);
-        const char *b, *e;
-        while (lines.next(b, e)) {
-            if (*b != 'v' || e - b < 2) continue;
-            Vector3 v; float* p[3] = {&v.x, &v.y, &v.z};
-            if (b[1] == ' ' || b[1] == 'n') {
-                if (flip_yz) { p[1] = &v.z; p[2] = &v.y; }
-                scan_floats(b, e, p, 3);
-                if (flip_yz) v.y *= -1;
-                if (b[1] == 'n') { v.Normalize(); normals.push_back(v); } else vertices.push_back(v);
-            } else if (b[1] == 't') {
-                Coord2f t{0.0f, 0.0f}; float w = 0; float* q[3] = {&t.u, &t.v, &w};
-                scan_floats(b, e, q, 3);
-                tex_coords.push_back(t);
-            }
+        size_t nv = 0, nn = 0, nt = 0;
+        for (const Slice& sl : slices) { nv += sl.vertices.size(); nn += sl.normals.size(); nt += sl.tex_coords.size(); }
+        vertices.reserve(nv); normals.reserve(nn); tex_coords.reserve(nt);
+        for (const Slice& sl : slices) {
+            vertices.insert(vertices.end(), sl.vertices.begin(), sl.vertices.end());
+            normals.insert(normals.end(), sl.normals.begin(), sl.normals.end());
+            tex_coords.insert(tex_coords.end(), sl.tex_coords.begin(), sl.tex_coords.end());
         }
     }
     printf("%zu vertices, %zu normals and %zu texture coords.\n", vertices.size(), normals.size(), tex_coords.size());
@@ -216,37 +297,24 @@ int LoadOBJ(const char* file_name, std::vector<Surface*>& surfaces, std::vector<
         surfaces.push_back(s);
         ++no_surfaces;
     };
-    Lines lines(text);
-    const char *b, *e;
-    while (lines.next(b, e)) {
-        switch (*b) {
-        case 'g': flush(); group_name = second_token(b, e); break;
-        case 'u': material_name = second_token(b, e); break;
-        case 'f': {
-            trim(b, e);
-            int spaces = 0;
-            for (const char* c = b; c < e; ++c) spaces += (*c == ' ');
-            if (spaces != 3 && spaces != 4) break;
-            int idx[4][3]; bool ok = true;
-            const char* c = b;
-            while (c < e && !isspace((unsigned char)*c)) ++c;      // the "f" token
-            for (int k = 0; k < spaces && ok; ++k) {
-                while (c < e && isspace((unsigned char)*c)) ++c;
-                const char* t = c;
-                while (c < e && !isspace((unsigned char)*c)) ++c;
-                ok = parse_corner(t, c, idx[k]) && idx[k][0] >= 0 && (size_t)idx[k][0] < vertices.size() && idx[k][1] >= 0 &&
-                     (size_t)idx[k][1] < tex_coords.size() && idx[k][2] >= 0 && (size_t)idx[k][2] < normals.size();
+    for (const Slice& sl : slices)
+        for (const Event& ev : sl.events) {
+            if (ev.type == 'g') { flush(); group_name = second_token(text.data() + ev.a, text.data() + ev.b); }
+            else if (ev.type == 'u') material_name = second_token(text.data() + ev.a, text.data() + ev.b);
+            else if (ev.type == 'f') {
+                const FaceRec& f = sl.faces[ev.a];
+                bool ok = f.corners != 0;
+                for (int k = 0; k < f.corners && ok; ++k)
+                    ok = f.idx[k][0] >= 0 && (size_t)f.idx[k][0] < vertices.size() && f.idx[k][1] >= 0 && (size_t)f.idx[k][1] < tex_coords.size() &&
+                         f.idx[k][2] >= 0 && (size_t)f.idx[k][2] < normals.size();
+                if (!ok) continue;
+                const int order[6] = {0, 1, 2, 0, 2, 3};
+                for (int k = 0; k < (f.corners == 4 ? 6 : 3); ++k) {
+                    const int* i = f.idx[order[k]];
+                    current->push_corner(vertices[i[0]], normals[i[2]], tex_coords[i[1]]);
+                }
             }
-            if (!ok) break;
-            const int order[6] = {0, 1, 2, 0, 2, 3};
-            for (int k = 0; k < (spaces == 4 ? 6 : 3); ++k) {
-                const int* i = idx[order[k]];
-                current->push_corner(vertices[i[0]], normals[i[2]], tex_coords[i[1]]);
-            }
-        } break;
-        default: break;
         }
-    }
     flush();
     delete current;
     printf("%d group(s), %zu material(s)\n", no_surfaces, materials.size());

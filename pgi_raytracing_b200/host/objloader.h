@@ -1,6 +1,8 @@
 // objloader.h -- LoadOBJ / LoadMTL (pg1/objloader.h:19-20, pg1/objloader.cpp:53-507), same signatures and the same
-// observable behaviour, rebuilt as single-pass tokenisers that fill SoA surfaces (surface.h) instead of the
-// reference's three strtok passes over two copies of the file.
+// observable behaviour.  The reference makes three strtok passes over two copies of the file on one thread; here the
+// file is cut at line ends into one slice per hardware thread, floats and face indices are parsed in parallel, and only
+// what depends on file order (groups, usemtl, the corner copy into SoA surfaces, surface.h) is replayed sequentially.
+// PG1_LOADER_THREADS overrides the thread count.
 #pragma once
 #include <map>
 #include <string>

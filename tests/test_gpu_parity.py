@@ -347,6 +347,8 @@ def test_queue_overflow_falls_back_to_smaller_batches(P, cornell, monkeypatch, s
     p = dict(seed=2, scheduler=scheduler)
     img, st = rt.render(p)
     assert st["overflow_retries"] >= 1
+    img2, st2 = rt.render(p)                                   # the surviving batch size is remembered: no second overflow
+    assert st2["overflow_retries"] == 0 and st2["batches"] == st["batches"] and np.array_equal(img, img2, equal_nan=True)
     monkeypatch.delenv("PGRT_MIN_LEVEL_CAP"); monkeypatch.delenv("PGRT_LEVEL_CAP_FACTOR")
     ref, _ = P.raytracer_for(cornell).render(p)
     assert np.array_equal(img, ref, equal_nan=True)

@@ -316,3 +316,28 @@ def test_tutorial_2_fixture_through_the_cpp_texture(host):
     buf, w, h, pitch, bpp = load_image(host, p)
     assert (w, h, bpp) == (64, 32, 4)
     assert np.array_equal(buf, np.load(os.path.join(GOLDEN, "test4_bgra.npy")))
+
+
+def test_parallel_loader_equals_single_thread(host, tmp_path, monkeypatch):
+    """LoadOBJ cuts the file into one slice per thread; the result must not depend on the thread count (slices end at
+    line ends, faces keep file order, groups and usemtl are replayed sequentially)."""
+    sc = scenes.triangle_soup(12000, seed=3, resolution=(8, 8))
+    m = sc.meshes[0]
+    third = m.ntris // 3
+    sc.meshes = [scenes.Mesh("a", m.pos[:third], m.nrm[:third], m.uv[:third], 0), scenes.Mesh("b", m.pos[third:2 * third], m.nrm[third:2 * third], m.uv[third:2 * third], 0),
+                 scenes.Mesh("c", m.pos[2 * third:], m.nrm[2 * third:], m.uv[2 * third:], 0)]
+    path = str(tmp_path / "soup.obj")
+    scenes.write_obj(sc, path)
+    assert os.path.getsize(path) > (1 << 20)                  # large enough for the loader to go parallel
+    results = []
+    for threads in ("1", "3", "7"):
+        monkeypatch.setenv("PG1_LOADER_THREADS", threads)
+        h = host.pg1_load_obj(path.encode(), 0)
+        assert host.pg1_num_surfaces(h) == 3
+        results.append([(host.pg1_surface_name(h, i).decode(),) + scene_arrays(host, h, i) for i in range(3)])
+        host.pg1_free_scene(h)
+    for other in results[1:]:
+        for (n0, p0, q0, u0), (n1, p1, q1, u1) in zip(results[0], other):
+            assert n0 == n1 and np.array_equal(p0, p1) and np.array_equal(q0, q1) and np.array_equal(u0, u1)
+    for i, mesh in enumerate(sc.meshes):
+        assert np.array_equal(results[0][i][1], mesh.pos.reshape(-1, 9)) and np.array_equal(results[0][i][3], mesh.uv.reshape(-1, 6))
