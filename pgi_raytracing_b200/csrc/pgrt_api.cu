@@ -86,8 +86,11 @@ struct pgrt_context {
     uint64_t launches = 0;
 
     // host staging of the scene (what LoadScene hands over, pg1/raytracer.cpp:71-125)
-    std::vector<float> h_pos, h_nrm, h_uv;
-    std::vector<uint32_t> h_tri_geom, h_geom_first;
+    std::vector<uint32_t> h_geom_first;
+    uint32_t n_added = 0;             // triangles uploaded by pgrt_add_mesh since pgrt_clear_scene
+    // pgrt_add_mesh streams the caller's arrays to the device as they arrive: two pinned staging buffers, the copy of one
+    // chunk to pinned memory overlaps the DMA of the previous one; nothing of the geometry stays on the host
+    uint8_t* stage[2] = {nullptr, nullptr}; cudaEvent_t stage_done[2] = {nullptr, nullptr}; int stage_next = 0;
     std::vector<int32_t> h_geom_material;
     std::vector<pgrt_material> h_materials;
     std::vector<pgrt_light> h_lights;
@@ -209,6 +212,7 @@ extern "C" void pgrt_destroy(pgrt_context* ctx) {
     ctx->env.bytes.release();
     for (FrameSlot& S : ctx->slots) S.release();
     ctx->d_ids.release(); ctx->flush_buf.release();
+    for (int k = 0; k < 2; ++k) { if (ctx->stage[k]) cudaFreeHost(ctx->stage[k]); if (ctx->stage_done[k]) cudaEventDestroy(ctx->stage_done[k]); }
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     delete ctx;
 }
@@ -232,22 +236,72 @@ extern "C" void* pgrt_slot_stream(pgrt_context* ctx, int32_t slot) {
 // --------------------------------------------------------------------------------------------------- scene
 extern "C" int pgrt_clear_scene(pgrt_context* ctx) {
     CHECK_CTX(ctx);
-    ctx->h_pos.clear(); ctx->h_nrm.clear(); ctx->h_uv.clear(); ctx->h_tri_geom.clear(); ctx->h_geom_first.clear(); ctx->h_geom_material.clear();
-    ctx->n_tris = 0; ctx->committed = false; ctx->px_valid = false;
+    ctx->h_geom_first.clear(); ctx->h_geom_material.clear();
+    ctx->n_added = 0; ctx->n_tris = 0; ctx->committed = false; ctx->px_valid = false;
+    return PGRT_OK;
+}
+
+#define PGRT_STAGE_BYTES ((size_t)32 << 20)
+
+__global__ void __launch_bounds__(256) k_fill_u32(uint32_t* __restrict__ dst, uint32_t n, uint32_t v) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = v;
+}
+
+// grows a device array to `count` elements keeping the first `keep` (geometric growth; scene uploads only)
+template <typename T>
+static cudaError_t grow_keep(DevBuf<T>& b, size_t count, size_t keep, cudaStream_t st) {
+    if (count <= b.n) return cudaSuccess;
+    const size_t cap = std::max(count, b.n + b.n / 2);
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc((void**)&q, cap * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (keep) e = cudaMemcpyAsync(q, b.p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (b.p) cudaFree(b.p);
+    b.p = q; b.n = cap;
+    return e;
+}
+
+// host array -> device through the pinned ring
+static int upload_stream(pgrt_context* ctx, void* dst, const void* src, size_t bytes) {
+    cudaStream_t st = ctx->stream;
+    for (size_t off = 0; off < bytes; off += PGRT_STAGE_BYTES) {
+        const size_t n = std::min(PGRT_STAGE_BYTES, bytes - off);
+        const int k = ctx->stage_next; ctx->stage_next ^= 1;
+        if (!ctx->stage[k]) {
+            CUDA_TRY(cudaMallocHost((void**)&ctx->stage[k], PGRT_STAGE_BYTES));
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->stage_done[k], cudaEventDisableTiming));
+        } else CUDA_TRY(cudaEventSynchronize(ctx->stage_done[k]));
+        memcpy(ctx->stage[k], (const uint8_t*)src + off, n);
+        CUDA_TRY(cudaMemcpyAsync((uint8_t*)dst + off, ctx->stage[k], n, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaEventRecord(ctx->stage_done[k], st));
+    }
     return PGRT_OK;
 }
 
 extern "C" int pgrt_add_mesh(pgrt_context* ctx, const float* pos, const float* nrm, const float* uv, uint32_t T, int32_t material_id, uint32_t* geom_id) {
     CHECK_CTX(ctx);
     if (T && (!pos || !nrm || !uv)) return ctx->fail(PGRT_ERR_INVALID, "pgrt_add_mesh: null buffer");
-    if ((uint64_t)ctx->h_tri_geom.size() + T >= (1ull << 29)) return ctx->fail(PGRT_ERR_INVALID, "pgrt_add_mesh: more than 2^29 triangles");
+    if ((uint64_t)ctx->n_added + T >= (1ull << 29)) return ctx->fail(PGRT_ERR_INVALID, "pgrt_add_mesh: more than 2^29 triangles");
+    cudaSetDevice(ctx->device);
+    if (ctx->committed || ctx->n_added == 0) sync_all_slots(ctx);   // frames in flight still read the arrays that may move
     const uint32_t g = (uint32_t)ctx->h_geom_first.size();
-    ctx->h_geom_first.push_back((uint32_t)ctx->h_tri_geom.size());
+    const size_t first = ctx->n_added, total = first + T;
+    cudaStream_t st = ctx->stream;
+    if (T) {
+        CUDA_TRY(grow_keep(ctx->d_pos, 9 * total, 9 * first, st)); CUDA_TRY(grow_keep(ctx->d_nrm, 9 * total, 9 * first, st));
+        CUDA_TRY(grow_keep(ctx->d_uv, 6 * total, 6 * first, st)); CUDA_TRY(grow_keep(ctx->d_tri_geom, total, first, st));
+        int rc = upload_stream(ctx, ctx->d_pos.p + 9 * first, pos, 9 * (size_t)T * 4); if (rc) return rc;
+        rc = upload_stream(ctx, ctx->d_nrm.p + 9 * first, nrm, 9 * (size_t)T * 4); if (rc) return rc;
+        rc = upload_stream(ctx, ctx->d_uv.p + 6 * first, uv, 6 * (size_t)T * 4); if (rc) return rc;
+        k_fill_u32<<<div_up(T, 256), 256, 0, st>>>(ctx->d_tri_geom.p + first, T, g);
+        ctx->launches++;
+        LAUNCH_OK();
+    }
+    ctx->h_geom_first.push_back((uint32_t)first);
     ctx->h_geom_material.push_back(material_id);
-    ctx->h_pos.insert(ctx->h_pos.end(), pos, pos + 9 * (size_t)T);
-    ctx->h_nrm.insert(ctx->h_nrm.end(), nrm, nrm + 9 * (size_t)T);
-    ctx->h_uv.insert(ctx->h_uv.end(), uv, uv + 6 * (size_t)T);
-    ctx->h_tri_geom.insert(ctx->h_tri_geom.end(), T, g);
+    ctx->n_added = (uint32_t)total;
     if (geom_id) *geom_id = g;
     ctx->committed = false; ctx->px_valid = false;
     return PGRT_OK;
@@ -321,7 +375,7 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
     cudaSetDevice(ctx->device);
     sync_all_slots(ctx);
     cudaStream_t st = ctx->stream;
-    const uint32_t N = (uint32_t)ctx->h_tri_geom.size();
+    const uint32_t N = ctx->n_added;   // the geometry is on the device already (pgrt_add_mesh streams it)
     ctx->n_tris = N; ctx->px_valid = false; ctx->batch_limit = 0;
     pgrt_build_stats bs = {}; bs.triangles = N;
     const uint32_t G = (uint32_t)ctx->h_geom_first.size();
@@ -337,12 +391,6 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
         CUDA_TRY(cudaStreamSynchronize(st));
         return PGRT_OK;
     }
-    CUDA_TRY(ctx->d_pos.ensure(9 * (size_t)N)); CUDA_TRY(ctx->d_nrm.ensure(9 * (size_t)N)); CUDA_TRY(ctx->d_uv.ensure(6 * (size_t)N));
-    CUDA_TRY(ctx->d_tri_geom.ensure(N));
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_pos.p, ctx->h_pos.data(), 9 * (size_t)N * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_nrm.p, ctx->h_nrm.data(), 9 * (size_t)N * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_uv.p, ctx->h_uv.data(), 6 * (size_t)N * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_tri_geom.p, ctx->h_tri_geom.data(), (size_t)N * 4, cudaMemcpyHostToDevice, st));
     // node layout: un-quantised planes while the node array stays far below L2 capacity (the traversal is issue-bound
     // there and the decode is 30 % of a node visit), the 80-B quantised node otherwise; PGRT_NODE_LAYOUT=q8|f32 overrides
     int layout = ((double)N * 0.15 * PGRT_NODE_F4_F32 * 16.0 <= 48e6) ? PGRT_LAYOUT_F32 : PGRT_LAYOUT_Q8;
@@ -1153,6 +1201,6 @@ extern "C" int pgrt_last_level_stats(const pgrt_context* ctx, int32_t level, pgr
     *out = ctx->level_stats[level];
     return PGRT_OK;
 }
-extern "C" uint32_t pgrt_num_triangles(const pgrt_context* ctx) { return ctx ? (uint32_t)ctx->h_tri_geom.size() : 0; }
+extern "C" uint32_t pgrt_num_triangles(const pgrt_context* ctx) { return ctx ? ctx->n_added : 0; }
 extern "C" uint32_t pgrt_num_geometries(const pgrt_context* ctx) { return ctx ? (uint32_t)ctx->h_geom_first.size() : 0; }
 extern "C" uint64_t pgrt_kernel_launches(const pgrt_context* ctx) { return ctx ? ctx->launches : 0; }

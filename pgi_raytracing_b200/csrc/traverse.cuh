@@ -87,12 +87,19 @@ PG_HD uint32_t slab4f(float4 w, float4 nx, float4 ny, float4 nz, float4 fx, floa
 // (trace_closest8 / trace_closest8f: shadow rays, pgrt_intersect, k_secondary, the CPU emulation) and the persistent
 // k_trace, which swaps finished rays for new ones between rounds.
 struct RayCtxF {                       // PGRT_LAYOUT_F32
+    // loop shape: while-while (a lane keeps descending until it holds triangles) -- fewer passes through the triangle
+    // code per warp; right for the issue-bound, cache-resident scenes this layout is chosen for
+    static constexpr bool kWhileWhile = true;
     V3 O, D; float tnear, tfar;
     float idx, idy, idz, oodx, oody, oodz, pad_abs;
     int onx, ony, onz, ofx, ofy, ofz;  // float4 offsets of the near / far planes inside a node, by ray sign
     uint32_t octinv, sw1, sw2, sw4;    // delta-swap masks that move internal hit bits from 24 + s to 24 + (s ^ octinv)
 };
 struct RayCtxQ {                       // PGRT_LAYOUT_Q8
+    // loop shape: if-if (one node step, then its triangles, every round).  The quantised layout serves scenes whose
+    // nodes miss in L2: there while-while measured 40 % SLOWER (10 M soup: level 0 in 30.4 ms against 21.2 ms,
+    // profiles/r1_bisect_c5_loop_shape.txt) -- lanes that already hold triangles sit through other lanes' DRAM round trips
+    static constexpr bool kWhileWhile = false;
     V3 O, D; float tnear, tfar;
     float idx, idy, idz;
     bool negx, negy, negz;
@@ -177,8 +184,8 @@ PG_HD void trav_init(TravState& s, float tfar) {
     s.best.t = tfar; s.best.u = 0.0f; s.best.v = 0.0f; s.best.tri = PGRT_INVALID_ID;
 }
 
-// Up to `rounds` while-while rounds (a lane descends until it holds triangles to test or runs out of nodes, then tests
-// them); returns true once the ray is finished.
+// Up to `rounds` rounds; returns true once the ray is finished.  A round is: descend (while-while: until the lane holds
+// triangles to test or runs out of nodes; if-if: one node at most), then test the triangles it holds.
 template <class RC, bool COUNT>
 PG_HD bool trav_advance(const float4* __restrict__ nodes, const float4* __restrict__ tris, const RC& r, TravState& s, uint2* stack, TravCount& tc, int rounds) {
     for (int it = 0; it < rounds; ++it) {
@@ -200,6 +207,7 @@ PG_HD bool trav_advance(const float4* __restrict__ nodes, const float4* __restri
             s.ng.y = (hitmask & 0xFF000000u) | imask;
             s.tg.x = tri_base;
             s.tg.y = hitmask & 0x00FFFFFFu;
+            if (!RC::kWhileWhile) break;
         }
         while (s.tg.y) {
             const int bit = pg_bfind(s.tg.y);
