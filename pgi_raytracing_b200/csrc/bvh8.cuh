@@ -26,8 +26,8 @@
 //   f[3 + 2*p + h] = plane p (lo.x, lo.y, lo.z, hi.x, hi.y, hi.z) of slots 4h..4h+3, as floats.
 // It costs 3x the bytes and removes, per node visit, the 48 integer->float conversions (30 % of the instructions of a
 // visit, profiles/r1_ncu_bvh8_q8_k_trace_k_secondary.txt) and the per-slot variable shifts that assemble the hit mask
-// (another 20 %, profiles/r1_ncu_bvh8_f32_k_trace_k_shade.txt); pgrt_commit picks it while the node array stays far
-// below L2 capacity (the traversal is then issue-bound, not memory-bound) and the quantised one otherwise.
+// (another 20 %, profiles/r1_ncu_bvh8_f32_k_trace_k_shade.txt); pgrt_commit picks it while the node array fits L2 (even the
+// 10 M soup turned out issue-bound, not memory-bound: profiles/r1_ncu_c5_soup_k_trace_q8.txt) and the quantised one above.
 #pragma once
 #include "common.cuh"
 

@@ -145,7 +145,8 @@ struct DevScene {
     const pgrt_light* lights;
     int32_t n_lights;
     uint32_t n_tris;
-    int32_t node_layout;      // PGRT_LAYOUT_Q8 (80 B nodes) or PGRT_LAYOUT_F32 (208 B nodes), bvh8.cuh
+    int32_t node_layout;      // PGRT_LAYOUT_Q8 (80 B nodes) or PGRT_LAYOUT_F32 (240 B nodes), bvh8.cuh
+    int32_t loop_ww;          // traversal loop shape: 1 while-while, 0 if-if (traverse.cuh trav_advance)
 };
 
 #define CUDA_TRY(call)                                                                                  \

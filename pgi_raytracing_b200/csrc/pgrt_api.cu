@@ -106,7 +106,7 @@ struct pgrt_context {
     DevBuf<DevTexture> d_textures;
     DevBuf<float4> d_shade, d_tris, d_nodes;
     uint32_t n_tris = 0;
-    int node_layout = PGRT_LAYOUT_Q8;
+    int node_layout = PGRT_LAYOUT_Q8, loop_ww = 0;
     bool committed = false, tables_dirty = true;
     pgrt_build_stats last_build = {};
 
@@ -147,7 +147,7 @@ struct pgrt_context {
         s.nodes = d_nodes.p; s.tris = d_tris.p; s.shade = d_shade.p; s.geom_first = d_geom_first.p; s.geom_material = d_geom_material.p;
         s.materials = d_materials.p; s.textures = d_textures.p; s.n_textures = (int32_t)textures.size();
         s.env.data = env.set ? env.bytes.p : nullptr; s.env.width = env.w; s.env.height = env.h; s.env.pitch = env.pitch; s.env.bpp = env.bpp;
-        s.lights = d_lights.p; s.n_lights = (int32_t)h_lights.size(); s.n_tris = n_tris; s.node_layout = node_layout;
+        s.lights = d_lights.p; s.n_lights = (int32_t)h_lights.size(); s.n_tris = n_tris; s.node_layout = node_layout; s.loop_ww = loop_ww;
         return s;
     }
 };
@@ -391,12 +391,14 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
         CUDA_TRY(cudaStreamSynchronize(st));
         return PGRT_OK;
     }
-    // node layout: un-quantised planes while the node array stays far below L2 capacity (the traversal is issue-bound
-    // there and the decode is 30 % of a node visit), the 80-B quantised node otherwise; PGRT_NODE_LAYOUT=q8|f32 overrides
-    int layout = ((double)N * 0.15 * PGRT_NODE_F4_F32 * 16.0 <= 48e6) ? PGRT_LAYOUT_F32 : PGRT_LAYOUT_Q8;
+    // node layout: un-quantised planes while the node array fits L2 (the traversal is issue-bound there and the decode is
+    // 30 % of a node visit: C4 with 3.08 M triangles gains 8 %), the 80-B quantised node otherwise; PGRT_NODE_LAYOUT=q8|f32 overrides
+    int layout = ((double)N * 0.15 * PGRT_NODE_F4_F32 * 16.0 <= 128e6) ? PGRT_LAYOUT_F32 : PGRT_LAYOUT_Q8;   // about the size of L2
     if (const char* e = getenv("PGRT_NODE_LAYOUT")) layout = !strcmp(e, "f32") ? PGRT_LAYOUT_F32 : (!strcmp(e, "q8") ? PGRT_LAYOUT_Q8 : layout);
     const size_t node_f4 = layout == PGRT_LAYOUT_F32 ? PGRT_NODE_F4_F32 : PGRT_NODE_F4_Q8;
     ctx->node_layout = layout;
+    ctx->loop_ww = 0;   // loop shape (traverse.cuh): if-if wins on every workload measured (profiles/r1_matrix_layout_loopshape.txt); PGRT_LOOP=ww|ii overrides
+    if (const char* e = getenv("PGRT_LOOP")) ctx->loop_ww = !strcmp(e, "ww") ? 1 : (!strcmp(e, "ii") ? 0 : ctx->loop_ww);
     CUDA_TRY(ctx->d_shade.ensure(4 * (size_t)N)); CUDA_TRY(ctx->d_tris.ensure(3 * (size_t)N)); CUDA_TRY(ctx->d_nodes.ensure(node_f4 * (size_t)N));
 
     cudaEvent_t e0, e1, e2, e3, e4;

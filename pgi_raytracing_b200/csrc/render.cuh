@@ -210,7 +210,7 @@ __device__ __forceinline__ void trace_queue(const DevScene& sc, const pgrt_rende
                     if (g0.on) L.ray_d[mine] = d;      // the shading kernels read it back instead of re-normalising three times
                     if (d.w >= 0.0f && sc.n_tris != 0) {
                         j = mine;
-                        ray_ctx_init(r, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, FLT_MAX);
+                        ray_ctx_init(r, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, FLT_MAX, sc.loop_ww != 0);
                         trav_init(s, FLT_MAX);
                         tc.nodes = 0; tc.tris = 0;
                     } else {

@@ -87,27 +87,22 @@ PG_HD uint32_t slab4f(float4 w, float4 nx, float4 ny, float4 nz, float4 fx, floa
 // (trace_closest8 / trace_closest8f: shadow rays, pgrt_intersect, k_secondary, the CPU emulation) and the persistent
 // k_trace, which swaps finished rays for new ones between rounds.
 struct RayCtxF {                       // PGRT_LAYOUT_F32
-    // loop shape: while-while (a lane keeps descending until it holds triangles) -- fewer passes through the triangle
-    // code per warp; right for the issue-bound, cache-resident scenes this layout is chosen for
-    static constexpr bool kWhileWhile = true;
     V3 O, D; float tnear, tfar;
+    bool ww;                           // loop shape, see trav_advance
     float idx, idy, idz, oodx, oody, oodz, pad_abs;
     int onx, ony, onz, ofx, ofy, ofz;  // float4 offsets of the near / far planes inside a node, by ray sign
     uint32_t octinv, sw1, sw2, sw4;    // delta-swap masks that move internal hit bits from 24 + s to 24 + (s ^ octinv)
 };
 struct RayCtxQ {                       // PGRT_LAYOUT_Q8
-    // loop shape: if-if (one node step, then its triangles, every round).  The quantised layout serves scenes whose
-    // nodes miss in L2: there while-while measured 40 % SLOWER (10 M soup: level 0 in 30.4 ms against 21.2 ms,
-    // profiles/r1_bisect_c5_loop_shape.txt) -- lanes that already hold triangles sit through other lanes' DRAM round trips
-    static constexpr bool kWhileWhile = false;
     V3 O, D; float tnear, tfar;
+    bool ww;
     float idx, idy, idz;
     bool negx, negy, negz;
     uint32_t octinv, octinv4;
 };
 
-PG_HD void ray_ctx_init(RayCtxF& r, V3 O, V3 D, float tnear, float tfar) {
-    r.O = O; r.D = D; r.tnear = tnear; r.tfar = tfar;
+PG_HD void ray_ctx_init(RayCtxF& r, V3 O, V3 D, float tnear, float tfar, bool ww) {
+    r.O = O; r.D = D; r.tnear = tnear; r.tfar = tfar; r.ww = ww;
     const float ooeps = 8.271806e-25f;   // 2^-80
     r.idx = pg_rcp(fabsf(D.x) > ooeps ? D.x : copysignf(ooeps, D.x));
     r.idy = pg_rcp(fabsf(D.y) > ooeps ? D.y : copysignf(ooeps, D.y));
@@ -124,8 +119,8 @@ PG_HD void ray_ctx_init(RayCtxF& r, V3 O, V3 D, float tnear, float tfar) {
     r.sw1 = (r.octinv & 1u) ? 0x55000000u : 0u; r.sw2 = (r.octinv & 2u) ? 0x33000000u : 0u; r.sw4 = (r.octinv & 4u) ? 0x0F000000u : 0u;
 }
 
-PG_HD void ray_ctx_init(RayCtxQ& r, V3 O, V3 D, float tnear, float tfar) {
-    r.O = O; r.D = D; r.tnear = tnear; r.tfar = tfar;
+PG_HD void ray_ctx_init(RayCtxQ& r, V3 O, V3 D, float tnear, float tfar, bool ww) {
+    r.O = O; r.D = D; r.tnear = tnear; r.tfar = tfar; r.ww = ww;
     const float ooeps = 8.271806e-25f;
     r.idx = pg_rcp(fabsf(D.x) > ooeps ? D.x : copysignf(ooeps, D.x));
     r.idy = pg_rcp(fabsf(D.y) > ooeps ? D.y : copysignf(ooeps, D.y));
@@ -184,8 +179,11 @@ PG_HD void trav_init(TravState& s, float tfar) {
     s.best.t = tfar; s.best.u = 0.0f; s.best.v = 0.0f; s.best.tri = PGRT_INVALID_ID;
 }
 
-// Up to `rounds` rounds; returns true once the ray is finished.  A round is: descend (while-while: until the lane holds
-// triangles to test or runs out of nodes; if-if: one node at most), then test the triangles it holds.
+// Up to `rounds` rounds; returns true once the ray is finished.  A round is: descend (while-while, r.ww: until the lane
+// holds triangles to test or runs out of nodes; if-if: one node at most), then test the triangles it holds.
+// While-while enters the triangle code less often per warp, but lanes that hold triangles idle while the others keep
+// descending; measured with the persistent k_trace it loses on every workload (6 % on C2, 35 % on the 3 M-triangle
+// grove, 50 % on the 10 M soup: profiles/r1_matrix_layout_loopshape.txt), so if-if is the default and PGRT_LOOP=ww the knob.
 template <class RC, bool COUNT>
 PG_HD bool trav_advance(const float4* __restrict__ nodes, const float4* __restrict__ tris, const RC& r, TravState& s, uint2* stack, TravCount& tc, int rounds) {
     for (int it = 0; it < rounds; ++it) {
@@ -207,7 +205,7 @@ PG_HD bool trav_advance(const float4* __restrict__ nodes, const float4* __restri
             s.ng.y = (hitmask & 0xFF000000u) | imask;
             s.tg.x = tri_base;
             s.tg.y = hitmask & 0x00FFFFFFu;
-            if (!RC::kWhileWhile) break;
+            if (!r.ww) break;
         }
         while (s.tg.y) {
             const int bit = pg_bfind(s.tg.y);
@@ -221,12 +219,12 @@ PG_HD bool trav_advance(const float4* __restrict__ nodes, const float4* __restri
 
 template <class RC, bool COUNT>
 PG_HD HitRec trace_closest_rc(const float4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t n_tris, V3 O, V3 D, float tnear, float tfar,
-                              TravCount& tc) {
+                              TravCount& tc, bool ww) {
     TravState s;
     trav_init(s, tfar);
     if (n_tris == 0) return s.best;
     RC r;
-    ray_ctx_init(r, O, D, tnear, tfar);
+    ray_ctx_init(r, O, D, tnear, tfar, ww);
     uint2 stack[PGRT_STACK8];
     while (!trav_advance<RC, COUNT>(nodes, tris, r, s, stack, tc, 1 << 30)) {}
     return s.best;
@@ -234,21 +232,21 @@ PG_HD HitRec trace_closest_rc(const float4* __restrict__ nodes, const float4* __
 
 template <bool COUNT>
 PG_HD HitRec trace_closest8f(const float4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t n_tris, V3 O, V3 D,
-                             float tnear, float tfar, TravCount& tc) {
-    return trace_closest_rc<RayCtxF, COUNT>(nodes, tris, n_tris, O, D, tnear, tfar, tc);
+                             float tnear, float tfar, TravCount& tc, bool ww = true) {
+    return trace_closest_rc<RayCtxF, COUNT>(nodes, tris, n_tris, O, D, tnear, tfar, tc, ww);
 }
 
 template <bool COUNT>
 PG_HD HitRec trace_closest8(const float4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t n_tris, V3 O, V3 D,
-                            float tnear, float tfar, TravCount& tc) {
-    return trace_closest_rc<RayCtxQ, COUNT>(nodes, tris, n_tris, O, D, tnear, tfar, tc);
+                            float tnear, float tfar, TravCount& tc, bool ww = false) {
+    return trace_closest_rc<RayCtxQ, COUNT>(nodes, tris, n_tris, O, D, tnear, tfar, tc, ww);
 }
 
 #ifdef __CUDACC__
 template <bool COUNT>
 __device__ __forceinline__ HitRec trace_closest_t(const DevScene& sc, V3 O, V3 D, float tnear, float tfar, TravCount& tc) {
-    if (sc.node_layout == PGRT_LAYOUT_F32) return trace_closest8f<COUNT>(sc.nodes, sc.tris, sc.n_tris, O, D, tnear, tfar, tc);
-    return trace_closest8<COUNT>(sc.nodes, sc.tris, sc.n_tris, O, D, tnear, tfar, tc);
+    if (sc.node_layout == PGRT_LAYOUT_F32) return trace_closest8f<COUNT>(sc.nodes, sc.tris, sc.n_tris, O, D, tnear, tfar, tc, sc.loop_ww != 0);
+    return trace_closest8<COUNT>(sc.nodes, sc.tris, sc.n_tris, O, D, tnear, tfar, tc, sc.loop_ww != 0);
 }
 
 __device__ __forceinline__ HitRec trace_closest(const DevScene& sc, V3 O, V3 D, float tnear, float tfar) {

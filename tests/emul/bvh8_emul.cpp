@@ -167,12 +167,13 @@ void emul_trace(void* h, const float* rays, uint64_t n, float* out, uint32_t* st
         const V3 O = v3(r[0], r[1], r[2]), D = v3(r[4], r[5], r[6]);
         HitRec best;
         TravCount tc; tc.nodes = 0; tc.tris = 0;
-        if (brute) {
+        if (brute & 1) {
             best.t = r[7]; best.u = 0; best.v = 0; best.tri = PGRT_INVALID_ID;
             for (uint32_t k = 0; k < t->n; ++k) tri_test(t->tris.data(), k, O, D, r[3], r[7], best);
         } else {
-            best = t->layout == PGRT_LAYOUT_F32 ? trace_closest8f<true>(t->nodes.data(), t->tris.data(), t->n, O, D, r[3], r[7], tc)
-                                                : trace_closest8<true>(t->nodes.data(), t->tris.data(), t->n, O, D, r[3], r[7], tc);
+            const bool ww = (brute & 2) != 0;   // bit 1 of `brute` selects the while-while loop shape
+            best = t->layout == PGRT_LAYOUT_F32 ? trace_closest8f<true>(t->nodes.data(), t->tris.data(), t->n, O, D, r[3], r[7], tc, ww)
+                                                : trace_closest8<true>(t->nodes.data(), t->tris.data(), t->n, O, D, r[3], r[7], tc, ww);
         }
         out[4 * i] = best.t; out[4 * i + 1] = best.u; out[4 * i + 2] = best.v; memcpy(&out[4 * i + 3], &best.tri, 4);
         if (stats) { stats[2 * i] = tc.nodes; stats[2 * i + 1] = tc.tris; }

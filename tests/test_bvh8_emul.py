@@ -86,8 +86,10 @@ def test_wide_tree_structure_and_hits(emul, name, builder, layout):
         assert emul.emul_check(h) == 0                       # every triangle once, decoded boxes conservative, meta consistent
         assert emul.emul_depth(h) <= 32                      # PGRT_STACK8 = 40 entries
         rays = random_rays(pos, 1500 if pos.shape[0] > 100 else 600, seed=3)
-        a, st = trace(emul, h, rays, False); b, _ = trace(emul, h, rays, True)
+        a, st = trace(emul, h, rays, 0); b, _ = trace(emul, h, rays, 1)
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        c, st_ww = trace(emul, h, rays, 2)                   # while-while loop shape: same hits, same work
+        assert np.array_equal(c.view(np.uint32), b.view(np.uint32)) and st_ww[:, 0].sum() <= st[:, 0].sum() * 1.05 + 8
         hit = b.view(np.uint32)[:, 3] != 0xFFFFFFFF
         assert hit.mean() > 0.1
         if pos.shape[0] > 1000:                              # the tree prunes: far fewer triangle tests than brute force
