@@ -277,6 +277,7 @@ def run_ours(args):
         sr.begin(k, params, profile=1, before=l2_flush(k))
         st = sr.end(k)
         trace_ms += st["trace_ms"]; trace_launches += st["trace_launches"]; prof_rays += st["total"]; prof_frame_ms += st["frame_ms"]
+        prof_nodes = st.get("nodes_visited", 0); prof_tris = st.get("tris_tested", 0); prof_total = st["total"]
     lv = rt.level_stats()
     barrier()
 
@@ -334,6 +335,7 @@ def run_ours(args):
                 "kernel": "k_trace + k_phong + k_secondary (every closest-hit query of the frame)", "bytes_per_ray": b_ray,
                 "launch_ms_avg": trace_ms / max(trace_launches, 1), "launches_per_frame": trace_launches / max(n_prof, 1), "peak_kind": peak_kind,
                 "frame_ms_unpipelined": prof_frame_ms / max(n_prof, 1),
+                "nodes_per_ray": prof_nodes / max(prof_total, 1), "tris_per_ray": prof_tris / max(prof_total, 1),
                 "fp32": {"flop_per_ray": flop_per_ray(sc.ntris), "achieved_tflops": value * 1e6 * flop_per_ray(sc.ntris) / 1e12,
                          "peak_tflops": 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12,
                          "note": "SURVEY 8(d) contract figure F_ray = 192*D + 180 on the pipelined whole-frame rate; peak = 148 SM x 128 lanes x 2 x max SM clock"},

@@ -51,6 +51,26 @@ struct Bvh2View {
 
 struct Wide8 { int n; uint32_t ch[8]; };
 
+// PLOC nearest-neighbour preference.  Smaller merged area wins; equal areas are common (regular grids, instanced or
+// coincident geometry) and how they resolve shapes the tree (measured: profiles/r1_sweep_ploc_ties.txt):
+//   PLOC_TIES_LOWEST (default)  the lower index;
+//   PLOC_TIES_BUDDY             the nearer index, then the "buddy" i^1, so that a run of identical candidates pairs up
+//                               (2k, 2k+1) in one pass.  Slower trees on C2/C4, so it is only the fallback for a pass in
+//                               which the default rule merges fewer than 1/16 of the clusters: with thousands of coincident
+//                               triangles every cluster points at the same lowest index, one pair merges per pass and the
+//                               tree becomes a chain deeper than the traversal stack.
+#define PLOC_TIES_LOWEST 0
+#define PLOC_TIES_BUDDY 1
+struct PlocBest { float a; int j; int dist; bool buddy; };
+PG_HD void ploc_best_init(PlocBest& b) { b.a = 3.402823466e+38f; b.j = -1; b.dist = 0x7fffffff; b.buddy = false; }
+PG_HD void ploc_offer(PlocBest& b, float a, long i, long j, int ties) {
+    const int dist = (int)(j > i ? j - i : i - j);
+    const bool buddy = j == (i ^ 1L);
+    const bool take = a < b.a || (ties == PLOC_TIES_BUDDY && a == b.a && (dist < b.dist || (dist == b.dist && buddy && !b.buddy)));
+    if (take) { b.a = a; b.j = (int)j; b.dist = dist; b.buddy = buddy; }
+}
+PG_HD bool ploc_pass_stalled(uint32_t merges, uint32_t n) { return merges * 16u < n; }
+
 PG_HD float box_half_area(float4 lo, float4 hi) {
     const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
     return dx * dy + dy * dz + dz * dx;

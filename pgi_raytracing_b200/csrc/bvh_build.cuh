@@ -284,7 +284,7 @@ __device__ __forceinline__ float merged_half_area(const float* a_lo, const float
 }
 
 __global__ void __launch_bounds__(PLOC_THREADS) k_ploc_nn(const float4* __restrict__ b0, const float4* __restrict__ b1, const uint32_t* __restrict__ cid,
-                                                          uint32_t n, int* __restrict__ nn) {
+                                                          uint32_t n, int* __restrict__ nn, int ties) {
     __shared__ float sb[6][PLOC_THREADS + 2 * PLOC_R];
     const long first = (long)blockIdx.x * PLOC_THREADS - PLOC_R;
     for (int k = threadIdx.x; k < PLOC_THREADS + 2 * PLOC_R; k += PLOC_THREADS) {
@@ -300,16 +300,16 @@ __global__ void __launch_bounds__(PLOC_THREADS) k_ploc_nn(const float4* __restri
     if (i >= (long)n) return;
     const int me = threadIdx.x + PLOC_R;
     const float lo[3] = {sb[0][me], sb[1][me], sb[2][me]}, hi[3] = {sb[3][me], sb[4][me], sb[5][me]};
-    float best = FLT_MAX; int bj = -1;
+    PlocBest best; ploc_best_init(best);
 #pragma unroll 4
     for (int off = -PLOC_R; off <= PLOC_R; ++off) {
         const long j = i + off;
         if (off == 0 || j < 0 || j >= (long)n) continue;
         const int k = me + off;
         const float a = merged_half_area(lo, hi, sb[0][k], sb[1][k], sb[2][k], sb[3][k], sb[4][k], sb[5][k]);
-        if (a < best) { best = a; bj = (int)j; }   // ascending j, strict <: ties keep the lower index
+        ploc_offer(best, a, i, j, ties);
     }
-    nn[i] = bj;
+    nn[i] = best.j;
 }
 
 // flags of cluster i: bit 0 = survives into the next pass, bit 1 = creates a node (the lower index of a mutual pair)
@@ -395,7 +395,8 @@ __global__ void __launch_bounds__(PLOC_THREADS) k_ploc_apply(const int* __restri
 // the last passes (n <= PLOC_FINISH clusters) in one block, boxes and ids in shared memory
 #define PLOC_FINISH 512
 __global__ void __launch_bounds__(PLOC_FINISH) k_ploc_finish(const uint32_t* __restrict__ cid_in, uint32_t n, uint32_t next_node,
-                                                             float4* __restrict__ b0, float4* __restrict__ b1, uint32_t* __restrict__ count) {
+                                                             float4* __restrict__ b0, float4* __restrict__ b1, uint32_t* __restrict__ count,
+                                                             uint32_t* __restrict__ left_over, int ties) {
     __shared__ uint32_t s_cid[2][PLOC_FINISH], s_cnt[2][PLOC_FINISH];
     __shared__ float s_box[2][6][PLOC_FINISH];
     __shared__ int s_nn[PLOC_FINISH];
@@ -409,17 +410,18 @@ __global__ void __launch_bounds__(PLOC_FINISH) k_ploc_finish(const uint32_t* __r
         s_box[0][0][tid] = lo.x; s_box[0][1][tid] = lo.y; s_box[0][2][tid] = lo.z; s_box[0][3][tid] = hi.x; s_box[0][4][tid] = hi.y; s_box[0][5][tid] = hi.z;
     }
     __syncthreads();
+    int mode = ties;
     while (n > 1) {
         if ((uint32_t)tid < n) {
             const float lo[3] = {s_box[cur][0][tid], s_box[cur][1][tid], s_box[cur][2][tid]}, hi[3] = {s_box[cur][3][tid], s_box[cur][4][tid], s_box[cur][5][tid]};
-            float best = FLT_MAX; int bj = -1;
+            PlocBest best; ploc_best_init(best);
             for (int off = -PLOC_R; off <= PLOC_R; ++off) {
                 const int j = tid + off;
                 if (off == 0 || j < 0 || j >= (int)n) continue;
                 const float a = merged_half_area(lo, hi, s_box[cur][0][j], s_box[cur][1][j], s_box[cur][2][j], s_box[cur][3][j], s_box[cur][4][j], s_box[cur][5][j]);
-                if (a < best) { best = a; bj = j; }
+                ploc_offer(best, a, tid, j, mode);
             }
-            s_nn[tid] = bj;
+            s_nn[tid] = best.j;
         }
         __syncthreads();
         const uint32_t f = ploc_flags(s_nn, (uint32_t)tid, n);
@@ -428,6 +430,7 @@ __global__ void __launch_bounds__(PLOC_FINISH) k_ploc_finish(const uint32_t* __r
         __syncthreads();
         uint32_t pv = 0, pm = 0, tv = 0, tmg = 0;
         for (int w = 0; w < PLOC_FINISH / 32; ++w) { if (w < warp) { pv += wv[w]; pm += wm[w]; } tv += wv[w]; tmg += wm[w]; }
+        if (mode != PLOC_TIES_BUDDY && ploc_pass_stalled(tmg, n)) { mode = PLOC_TIES_BUDDY; __syncthreads(); continue; }   // redo this pass (see bvh8.cuh)
         if (f & 1u) {
             const uint32_t dst = pv + __popc(bv & ((1u << lane) - 1u));
             uint32_t node = s_cid[cur][tid], cnt = s_cnt[cur][tid];
@@ -451,8 +454,10 @@ __global__ void __launch_bounds__(PLOC_FINISH) k_ploc_finish(const uint32_t* __r
             for (int a = 0; a < 6; ++a) s_box[cur ^ 1][a][dst] = bx[a];
         }
         __syncthreads();
-        n = tv; next_node += tmg; cur ^= 1;
+        if (tmg == 0u) break;   // no mutual pair: only possible with non-finite boxes (NaN areas never compare); reported by the host
+        n = tv; next_node += tmg; cur ^= 1; mode = ties;
     }
+    if (tid == 0) *left_over = n;   // 1 = a single root remains
 }
 
 // the Karras tree (k_karras + k_refit) in the layout above: leaf k -> node k, internal j -> node N + j (root = N)

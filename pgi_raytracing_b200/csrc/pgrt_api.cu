@@ -408,6 +408,7 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
     DevBuf<float4> b0, b1; DevBuf<uint32_t> bcount, cid[2]; DevBuf<int> nn; DevBuf<uint2> bsums, items[2]; DevBuf<CollapseCounters> cc;
     DevBuf<int> ti[6]; DevBuf<float> tf[2];
     const uint32_t n_tiles = div_up(N, RS_TILE);
+    const int ploc_ties = getenv("PGRT_PLOC_TIES") ? atoi(getenv("PGRT_PLOC_TIES")) : PLOC_TIES_LOWEST;
     const bool use_lbvh = getenv("PGRT_BUILDER") && !strcmp(getenv("PGRT_BUILDER"), "lbvh");
     int rc = PGRT_OK;
     auto cleanup = [&]() {
@@ -467,18 +468,30 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
         uint32_t n = N, next = N; int c = 0;
         while (n > PLOC_FINISH) {
             const uint32_t nb = div_up(n, PLOC_THREADS);
-            k_ploc_nn<<<nb, PLOC_THREADS, 0, st>>>(b0.p, b1.p, cid[c].p, n, nn.p);
-            k_ploc_count<<<nb, PLOC_THREADS, 0, st>>>(nn.p, n, bsums.p);
-            k_ploc_scan<<<1, 1024, 0, st>>>(bsums.p, nb, bsums.p + nb);
+            uint32_t survivors = 0, merges = 0;
+            for (int mode = ploc_ties;;) {
+                k_ploc_nn<<<nb, PLOC_THREADS, 0, st>>>(b0.p, b1.p, cid[c].p, n, nn.p, mode);
+                k_ploc_count<<<nb, PLOC_THREADS, 0, st>>>(nn.p, n, bsums.p);
+                k_ploc_scan<<<1, 1024, 0, st>>>(bsums.p, nb, bsums.p + nb);
+                ctx->launches += 3;
+                BUILD_TRY(cudaMemcpyAsync(ctx->h_pin, bsums.p + nb, sizeof(uint2), cudaMemcpyDeviceToHost, st));
+                BUILD_TRY(cudaStreamSynchronize(st));
+                survivors = ctx->h_pin[0]; merges = ctx->h_pin[1];
+                if (mode == PLOC_TIES_BUDDY || !ploc_pass_stalled(merges, n)) break;
+                mode = PLOC_TIES_BUDDY;   // a run of ties pointed every cluster at the same neighbour: redo the pass pairing buddies (bvh8.cuh)
+            }
+            if (merges == 0 || survivors >= n) { rc = ctx->fail(PGRT_ERR_INVALID, "pgrt_commit: the triangles do not cluster (non-finite vertex coordinates?)"); cleanup(); return rc; }
             k_ploc_apply<<<nb, PLOC_THREADS, 0, st>>>(nn.p, cid[c].p, n, bsums.p, next, b0.p, b1.p, bcount.p, cid[c ^ 1].p);
-            ctx->launches += 4; passes++;
-            BUILD_TRY(cudaMemcpyAsync(ctx->h_pin, bsums.p + nb, sizeof(uint2), cudaMemcpyDeviceToHost, st));
-            BUILD_TRY(cudaStreamSynchronize(st));
-            const uint32_t survivors = ctx->h_pin[0], merges = ctx->h_pin[1];
-            if (merges == 0 || survivors >= n) { rc = ctx->fail(PGRT_ERR_CUDA, "pgrt_commit: PLOC pass made no progress"); cleanup(); return rc; }
+            ctx->launches += 1; passes++;
             n = survivors; next += merges; c ^= 1;
         }
-        if (n > 1) { k_ploc_finish<<<1, PLOC_FINISH, 0, st>>>(cid[c].p, n, next, b0.p, b1.p, bcount.p); ctx->launches += 1; }
+        if (n > 1) {
+            k_ploc_finish<<<1, PLOC_FINISH, 0, st>>>(cid[c].p, n, next, b0.p, b1.p, bcount.p, (uint32_t*)(bsums.p), ploc_ties);
+            ctx->launches += 1;
+            BUILD_TRY(cudaMemcpyAsync(ctx->h_pin, bsums.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            BUILD_TRY(cudaStreamSynchronize(st));
+            if (ctx->h_pin[0] != 1u) { rc = ctx->fail(PGRT_ERR_INVALID, "pgrt_commit: the triangles do not cluster (non-finite vertex coordinates?)"); cleanup(); return rc; }
+        }
         root2 = N >= 2 ? 2 * N - 2 : 0;
     }
     BUILD_TRY(cudaEventRecord(e3, st));

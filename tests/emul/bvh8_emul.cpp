@@ -91,18 +91,24 @@ void* emul_build(const float* pos, uint32_t n, int builder /*0 = PLOC, 1 = media
         for (uint32_t i = 0; i < n; ++i) cid[i] = i;
         uint32_t m = n;
         while (m > 1) {
-            for (uint32_t i = 0; i < m; ++i) {
-                float best = FLT_MAX; int bj = -1;
-                const float4 lo = t->b0[cid[i]], hi = t->b1[cid[i]];
-                for (int off = -PLOC_R; off <= PLOC_R; ++off) {
-                    const long j = (long)i + off;
-                    if (off == 0 || j < 0 || j >= (long)m) continue;
-                    const float4 l2 = t->b0[cid[j]], h2 = t->b1[cid[j]];
-                    const float dx = fmaxf(hi.x, h2.x) - fminf(lo.x, l2.x), dy = fmaxf(hi.y, h2.y) - fminf(lo.y, l2.y), dz = fmaxf(hi.z, h2.z) - fminf(lo.z, l2.z);
-                    const float a = dx * dy + dy * dz + dz * dx;
-                    if (a < best) { best = a; bj = (int)j; }
+            for (int mode = PLOC_TIES_LOWEST;;) {
+                for (uint32_t i = 0; i < m; ++i) {
+                    const float4 lo = t->b0[cid[i]], hi = t->b1[cid[i]];
+                    PlocBest best; ploc_best_init(best);
+                    for (int off = -PLOC_R; off <= PLOC_R; ++off) {
+                        const long j = (long)i + off;
+                        if (off == 0 || j < 0 || j >= (long)m) continue;
+                        const float4 l2 = t->b0[cid[j]], h2 = t->b1[cid[j]];
+                        const float dx = fmaxf(hi.x, h2.x) - fminf(lo.x, l2.x), dy = fmaxf(hi.y, h2.y) - fminf(lo.y, l2.y), dz = fmaxf(hi.z, h2.z) - fminf(lo.z, l2.z);
+                        const float a = dx * dy + dy * dz + dz * dx;
+                        ploc_offer(best, a, (long)i, j, mode);
+                    }
+                    nn[i] = best.j;
                 }
-                nn[i] = bj;
+                uint32_t merges = 0;
+                for (uint32_t i = 0; i < m; ++i) merges += nn[i] > (int)i && nn[nn[i]] == (int)i;
+                if (mode == PLOC_TIES_BUDDY || !ploc_pass_stalled(merges, m)) break;
+                mode = PLOC_TIES_BUDDY;
             }
             out.clear();
             for (uint32_t i = 0; i < m; ++i) {

@@ -111,6 +111,25 @@ def test_duplicates_and_degenerates(emul):
         _check_degenerates(emul, h, pos)
 
 
+def test_runs_of_ties_do_not_build_a_chain(emul):
+    """Thousands of coincident triangles, and a regular row of identical ones: every merge candidate has the same area.
+    The neighbour preference (nearer index, then the buddy i^1) must pair them up; picking the lowest index instead
+    merged one pair per pass and produced a tree thousands of levels deep (beyond the traversal stack)."""
+    one = np.array([[0, 0, 0, 4, 0, 0, 0, 4, 1]], np.float32)
+    row = np.repeat(one, 2500, axis=0); row[:, [0, 3, 6]] += np.arange(2500, dtype=np.float32)[:, None] * 8.0
+    for pos in (np.repeat(one, 3000, axis=0), row):
+        pos = np.ascontiguousarray(pos)
+        h = emul.emul_build(pos.ctypes.data, pos.shape[0], 0, 1)
+        try:
+            assert emul.emul_check(h) == 0
+            assert emul.emul_depth(h) <= 12, emul.emul_depth(h)
+            rays = random_rays(pos, 800, seed=6)
+            a, _ = trace(emul, h, rays, False); b, _ = trace(emul, h, rays, True)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        finally:
+            emul.emul_free(h)
+
+
 def _check_degenerates(emul, h, pos):
     try:
         assert emul.emul_check(h) == 0
