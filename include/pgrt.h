@@ -24,7 +24,7 @@ extern "C" {
 #define PGRT_ERR_NO_DEVICE 3    /* no usable GPU                                           */
 #define PGRT_ERR_OVERFLOW 4     /* secondary-ray queues overflowed even at the minimum batch */
 
-#define PGRT_MAX_INFLIGHT 8            /* frame slots of a context (pipelined frames)             */
+#define PGRT_MAX_INFLIGHT 16           /* frame slots of a context (pipelined frames)             */
 
 #define PGRT_INVALID_ID 0xFFFFFFFFu   /* = RTC_INVALID_GEOMETRY_ID, embree3/rtcore_common.h:45 */
 #define PGRT_IOR_AIR 1.000293f        /* material.h:15 */
@@ -179,6 +179,12 @@ int pgrt_frame_free(pgrt_context* ctx, void* device_ptr);
 int pgrt_frame_export(pgrt_context* ctx, void* device_ptr, uint8_t handle[64]);
 int pgrt_frame_import(pgrt_context* ctx, const uint8_t handle[64], void** device_ptr);
 int pgrt_frame_unmap(pgrt_context* ctx, void* device_ptr);
+/* host frames shared between the processes of one box: `host` is page-aligned host memory that every rank has mapped
+ * (a memfd / POSIX shared-memory mapping).  Registered with this context's device, *device_ptr is the address its
+ * kernels store through: passed as `frame_device` to pgrt_render_shard_to_frame_begin, every rank's resolve kernel writes
+ * its own tiles into the one host frame through its own PCIe link (zero-copy; no device-to-host copy on rank 0). */
+int pgrt_host_frame_register(pgrt_context* ctx, void* host, uint64_t bytes, void** device_ptr);
+int pgrt_host_frame_unregister(pgrt_context* ctx, void* host);
 int pgrt_enable_peer_access(pgrt_context* ctx, int32_t peer_device);   /* let this context's kernels store into memory of `peer_device` */
 int pgrt_render_shard_to_frame_begin(pgrt_context* ctx, const pgrt_render_params* p, void* frame_device, int32_t slot, int32_t profile);
 int pgrt_render_end(pgrt_context* ctx, int32_t slot, pgrt_render_stats* stats);

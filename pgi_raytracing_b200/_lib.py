@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 PGRT_OK, PGRT_ERR_INVALID, PGRT_ERR_CUDA, PGRT_ERR_NO_DEVICE, PGRT_ERR_OVERFLOW = 0, 1, 2, 3, 4
 INVALID_ID = 0xFFFFFFFF
-MAX_INFLIGHT = 8
+MAX_INFLIGHT = 16
 
 
 class Material(C.Structure):
@@ -79,6 +79,8 @@ SYMBOLS = {
     "pgrt_frame_export": (C.c_int, [_VP, _VP, C.c_char_p]),
     "pgrt_frame_import": (C.c_int, [_VP, C.c_char_p, C.POINTER(_VP)]),
     "pgrt_frame_unmap": (C.c_int, [_VP, _VP]),
+    "pgrt_host_frame_register": (C.c_int, [_VP, _VP, _U64, C.POINTER(_VP)]),
+    "pgrt_host_frame_unregister": (C.c_int, [_VP, _VP]),
     "pgrt_debug_flush_l2": (C.c_int, [_VP, _I32, _U64, _U32]),
     "pgrt_enable_peer_access": (C.c_int, [_VP, _I32]),
     "pgrt_render_shard_to_frame_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),

@@ -188,6 +188,15 @@ class Raytracer:
     def frame_unmap(self, ptr: int):
         self._check(self.lib.pgrt_frame_unmap(self.h, C.c_void_p(ptr)))
 
+    def host_frame_register(self, host_ptr: int, nbytes: int) -> int:
+        """Register page-aligned (shared) host memory with this rank's device; returns the address kernels store through."""
+        ptr = C.c_void_p()
+        self._check(self.lib.pgrt_host_frame_register(self.h, C.c_void_p(host_ptr), nbytes, C.byref(ptr)))
+        return int(ptr.value)
+
+    def host_frame_unregister(self, host_ptr: int):
+        self._check(self.lib.pgrt_host_frame_unregister(self.h, C.c_void_p(host_ptr)))
+
     def flush_l2(self, slot: int, nbytes: int = 160 << 20, value: int = 0):
         """Measurement helper (``pgrt_debug_flush_l2``): evict L2 on the slot's stream before a timed frame."""
         self._check(self.lib.pgrt_debug_flush_l2(self.h, slot, nbytes, value))

@@ -47,6 +47,7 @@ struct FrameSlot {
     std::vector<int> ev_class, ev_level;
     size_t ev_used = 0;
     cudaEvent_t ev_frame0 = nullptr, ev_frame1 = nullptr, ev_done = nullptr;
+    int secondary_grid = 0;           // CTAs of this frame's k_secondary (sized in frame_begin)
     // the frame in flight
     bool busy = false;
     pgrt_render_params params = {};
@@ -117,7 +118,7 @@ struct pgrt_context {
     // frame state: PGRT_MAX_INFLIGHT independent frame slots, each with its own stream, queues and counters, so the
     // latency-bound tail of one frame (k_secondary) and its device->host copy overlap the next frame's primary work
     FrameSlot slots[PGRT_MAX_INFLIGHT];
-    int secondary_grid = 0;
+    int secondary_per_sm_max = 0, secondary_per_sm_env = 0;   // occupancy bound of k_secondary; PGRT_SECONDARY_CTAS_PER_SM
     bool fuse_raygen = true;          // PGRT_FUSE_RAYGEN=0 restores the stored level-0 ray queue (k_raygen)
     bool use_graphs = true;           // PGRT_GRAPHS=0: every frame as individual launches
     int trace_refill = 32;            // k_trace claims new rays once this many lanes of a warp are idle (PGRT_TRACE_REFILL, 1..32); 32 = whole-warp chunks, the fastest for coherent primary rays (profiles/r1_sweep_trace_refill.txt)
@@ -698,8 +699,8 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
             tm.end();
             tm.begin(KC_TRACE, 1);
             const size_t smem = (size_t)4 * p->max_depth * (PGRT_WSTACK + 1) * sizeof(uint32_t);   // <= 33.3 KB at max_depth 32
-            if (count) k_secondary<true><<<ctx->secondary_grid, 128, smem, st>>>(sc, *p, S.levels[0], P, cnt);
-            else k_secondary<false><<<ctx->secondary_grid, 128, smem, st>>>(sc, *p, S.levels[0], P, cnt);
+            if (count) k_secondary<true><<<S.secondary_grid, 128, smem, st>>>(sc, *p, S.levels[0], P, cnt);
+            else k_secondary<false><<<S.secondary_grid, 128, smem, st>>>(sc, *p, S.levels[0], P, cnt);
             rs.launches++; rs.trace_launches++;
             tm.end();
         } else {
@@ -769,7 +770,7 @@ static uint64_t frame_key(pgrt_context* ctx, const FrameSlot& S) {
     h = fnv1a(S.levels, sizeof(LevelBufs) * (size_t)(S.n_levels + 1), h); h = fnv1a(&S.pool, sizeof S.pool, h);
     const void* extra[3] = {S.d_frame.p, S.d_counters.p, S.stream};
     h = fnv1a(extra, sizeof extra, h);
-    const int flags[5] = {S.dyn ? 1 : 0, ctx->fuse_raygen ? 1 : 0, ctx->secondary_grid, ctx->trace_refill, ctx->trace_ctas_per_sm};
+    const int flags[5] = {S.dyn ? 1 : 0, ctx->fuse_raygen ? 1 : 0, S.secondary_grid, ctx->trace_refill, ctx->trace_ctas_per_sm};
     return fnv1a(flags, sizeof flags, h) | 1ull;
 }
 
@@ -823,7 +824,7 @@ static int enqueue_frame(pgrt_context* ctx, FrameSlot& S) {
     return PGRT_OK;
 }
 
-static int frame_begin(pgrt_context* ctx, int slot, const pgrt_render_params* p, float4* dest, int dest_mode, float* host_dst, int profile) {
+static int frame_begin(pgrt_context* ctx, int slot, const pgrt_render_params* p, float4* dest, int dest_mode, float* host_dst, int profile, bool latency = false) {
     if (slot < 0 || slot >= PGRT_MAX_INFLIGHT) return ctx->fail(PGRT_ERR_INVALID, "render: slot out of range");
     FrameSlot& S = ctx->slots[slot];
     if (S.busy) return ctx->fail(PGRT_ERR_INVALID, "render: the slot still holds a frame in flight (call pgrt_render_end first)");
@@ -834,18 +835,25 @@ static int frame_begin(pgrt_context* ctx, int slot, const pgrt_render_params* p,
     const int SPP = p->sampling_width * p->sampling_width;
     S.n_levels = (dest_mode == 2) ? 1 : p->max_depth + 1;
     S.dyn = p->scheduler == 0 && dest_mode != 2 && S.n_levels > 1;
-    if (S.dyn && ctx->secondary_grid == 0) {
-        // the persistent kernel is latency-bound and runs beside other frames' kernels (sweep: profiles/r1_sweep_secondary.txt)
-        int per_sm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_secondary<false>, 128, 0));
-        int want = 4;
-        if (const char* e = getenv("PGRT_SECONDARY_CTAS_PER_SM")) want = std::max(1, atoi(e));
-        ctx->secondary_grid = ctx->sm_count * std::max(1, std::min(per_sm, want));
+    if (S.dyn && ctx->secondary_per_sm_max == 0) {
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->secondary_per_sm_max, k_secondary<false>, 128, 0));
+        ctx->secondary_per_sm_max = std::max(1, ctx->secondary_per_sm_max);
+        if (const char* e = getenv("PGRT_SECONDARY_CTAS_PER_SM")) ctx->secondary_per_sm_env = std::max(1, atoi(e));
     }
     const uint64_t total_slots = shard_slots(ctx);
     uint64_t batch_slots = std::max<uint64_t>(PGRT_TILE_PIXELS, ctx->max_batch_samples / SPP / PGRT_TILE_PIXELS * PGRT_TILE_PIXELS);
     S.batch_slots = std::min(batch_slots, total_slots);
     if (ctx->batch_limit) S.batch_slots = std::min(S.batch_slots, ctx->batch_limit);   // do not overflow the same way every frame
+    if (S.dyn) {
+        // The persistent secondary-ray kernel is latency-bound (dependent chains of up to max_depth traversals) and its
+        // CTAs hold their SM slots while they wait, so its grid decides how many frames can be resident at once.  A frame
+        // alone on the GPU (blocking call) wants 4 CTAs/SM; pipelined frames want the grid in proportion to the batch:
+        // 4/SM from 2 M primary samples up, 1/SM for a 0.3 M-sample frame or shard (profiles/r1_sweep_secondary.txt, r1_sweep_small_frames.txt).
+        const uint64_t samples = S.batch_slots * (uint64_t)SPP;
+        int want = latency ? 4 : (int)std::min<uint64_t>(4, std::max<uint64_t>(1, (samples + 262144) / 524288));
+        if (ctx->secondary_per_sm_env) want = ctx->secondary_per_sm_env;
+        S.secondary_grid = ctx->sm_count * std::min(ctx->secondary_per_sm_max, want);
+    }
     S.rs = pgrt_render_stats{};
     rc = enqueue_frame(ctx, S);
     if (rc) return rc;
@@ -895,7 +903,7 @@ static int frame_end(pgrt_context* ctx, int slot, pgrt_render_stats* stats) {
 }
 
 static int render_frame(pgrt_context* ctx, const pgrt_render_params* p, float4* dest, int dest_mode, float* host_dst, pgrt_render_stats* stats, int profile) {
-    int rc = frame_begin(ctx, 0, p, dest, dest_mode, host_dst, profile);
+    int rc = frame_begin(ctx, 0, p, dest, dest_mode, host_dst, profile, /*latency=*/true);
     if (rc) return rc;
     return frame_end(ctx, 0, stats);
 }
@@ -951,6 +959,22 @@ extern "C" int pgrt_frame_free(pgrt_context* ctx, void* device_ptr) {
     cudaSetDevice(ctx->device);
     sync_all_slots(ctx);
     CUDA_TRY(cudaFree(device_ptr));
+    return PGRT_OK;
+}
+extern "C" int pgrt_host_frame_register(pgrt_context* ctx, void* host, uint64_t bytes, void** device_ptr) {
+    CHECK_CTX(ctx);
+    if (!host || !bytes || !device_ptr || ((uintptr_t)host & 4095u)) return ctx->fail(PGRT_ERR_INVALID, "pgrt_host_frame_register: need a page-aligned host buffer");
+    cudaSetDevice(ctx->device);
+    CUDA_TRY(cudaHostRegister(host, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    cudaError_t e = cudaHostGetDevicePointer(device_ptr, host, 0);
+    if (e != cudaSuccess) { cudaHostUnregister(host); CUDA_TRY(e); }
+    return PGRT_OK;
+}
+extern "C" int pgrt_host_frame_unregister(pgrt_context* ctx, void* host) {
+    CHECK_CTX(ctx);
+    cudaSetDevice(ctx->device);
+    sync_all_slots(ctx);
+    CUDA_TRY(cudaHostUnregister(host));
     return PGRT_OK;
 }
 extern "C" int pgrt_frame_export(pgrt_context* ctx, void* device_ptr, uint8_t handle[64]) {

@@ -115,12 +115,61 @@ def share_frames(raytracer, n_frames: int, rank: int, device, group=None):
     return ptrs, views
 
 
+def share_host_frames(raytracer, n_frames: int, rank: int, device, group=None):
+    """``n_frames`` full frames in HOST memory shared by every rank: rank 0 creates a memfd, the others open it through
+    ``/proc/<pid>/fd``, every rank maps it and registers the mapping with its own device (``pgrt_host_frame_register``).
+    Each rank's resolve kernel then stores its tiles straight into the host frame through its own PCIe link, so a frame
+    that has to end in host memory needs no device-to-host copy on rank 0 (whose single link would carry all of it).
+    Returns (device-side pointers valid on this rank, rank-0 CPU torch views or None, keep-alive); (None, None, None)
+    when any rank cannot set it up."""
+    import ctypes
+    import mmap
+    import os
+    import torch
+    import torch.distributed as dist
+
+    stride = (raytracer.width * raytracer.height * 16 + 4095) // 4096 * 4096
+    total = stride * n_frames
+    ok, fd, mm, base, info = 1, -1, None, 0, [None]
+    try:
+        if rank == 0:
+            fd = os.memfd_create("pgrt_host_frames")
+            os.ftruncate(fd, total)
+            info = [(os.getpid(), fd)]
+    except Exception:
+        ok = 0
+    dist.broadcast_object_list(info, src=0, group=group)
+    dev_base = 0
+    try:
+        if info[0] is None:
+            ok = 0
+        else:
+            if rank != 0:
+                fd = os.open(f"/proc/{info[0][0]}/fd/{info[0][1]}", os.O_RDWR)
+            mm = mmap.mmap(fd, total)
+            base = ctypes.addressof(ctypes.c_char.from_buffer(mm))
+            dev_base = raytracer.host_frame_register(base, total)
+    except Exception:
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)     # also: everybody has opened the memfd before rank 0 may close it
+    if int(flag.item()) != 1:
+        return None, None, None
+    views = None
+    if rank == 0:
+        flat = torch.frombuffer(mm, dtype=torch.float32).view(n_frames, stride // 4)
+        views = [flat[i, : raytracer.height * raytracer.width * 4].view(raytracer.height, raytracer.width, 4) for i in range(n_frames)]
+    return [dev_base + i * stride for i in range(n_frames)], views, (mm, fd, base)
+
+
 class ShardedRenderer:
     """One rank of a tile-sharded render, ``depth`` frames in flight.
 
     mode "p2p" (default on GPUs when the frames can be peer-mapped): every rank's resolve kernel stores its tiles
     straight into rank 0's frame over NVLink (``pgrt_render_shard_to_frame_begin``); the only collective is a 4-byte
-    NCCL all-reduce per frame that serves as the completion barrier.  mode "nccl": compact per-rank tile buffers,
+    NCCL all-reduce per frame that serves as the completion barrier.  mode "host": the same, but the frames live in host
+    memory shared by all ranks (``share_host_frames``): every rank writes its tiles through its own PCIe link and
+    ``frames`` are CPU tensors on rank 0.  mode "nccl": compact per-rank tile buffers,
     ``gather`` to rank 0, un-tile kernel.  ``begin(k)`` enqueues frame k; ``end(k)`` collects this rank's stats;
     on rank 0, ``frames[k % depth]`` holds frame k once the communication stream has passed ``ready[k % depth]``."""
 
@@ -141,7 +190,12 @@ class ShardedRenderer:
             self.mode = "p2p" if self.frame_ptrs is not None else "nccl"
             if self.mode == "p2p":
                 self.frames = views
-        if self.mode != "p2p" and rank == 0:
+        if self.mode == "host":
+            self.frame_ptrs, views, self._host_keep = share_host_frames(raytracer, depth, rank, device)
+            if self.frame_ptrs is None:
+                raise RuntimeError("ShardedRenderer: cannot set up frames in shared host memory")
+            self.frames = views
+        if self.mode not in ("p2p", "host") and rank == 0:
             self.frames = [torch.zeros((raytracer.height, raytracer.width, 4), dtype=torch.float32, device=device) for _ in range(depth)]
         if self.mode == "nccl":
             self.shards = [torch.zeros((self.n_slots, 4), dtype=torch.float32, device=device) for _ in range(depth)]
@@ -152,6 +206,23 @@ class ShardedRenderer:
         self.ready = [None] * depth          # event on the communication stream: frame of this slot complete on rank 0
         self.history = {}                    # step -> ready event (kept for the last `depth` steps)
         torch.cuda.synchronize(device)
+
+    def close(self):
+        """Release the shared host frames of mode "host" (device frames go with the context)."""
+        keep = getattr(self, "_host_keep", None)
+        if keep is not None:
+            import os
+            import torch
+            torch.cuda.synchronize(self.device)
+            mm, fd, base = keep
+            self.rt.host_frame_unregister(base)
+            self.frames = None
+            self._host_keep = None
+            try:
+                mm.close()
+            except BufferError:      # a caller still holds a view of a frame: the mapping goes when that does
+                pass
+            os.close(fd)
 
     @property
     def frame(self):
@@ -178,7 +249,7 @@ class ShardedRenderer:
             self.rt.render_begin(s, params, device_ptr=self.frames[s].data_ptr(), profile=profile)
             t.append(time.perf_counter())
             self.rt.stream_wait_slot(s, comm.cuda_stream)
-        elif self.mode == "p2p":
+        elif self.mode in ("p2p", "host"):
             self.rt.render_begin(s, params, frame_ptr=self.frame_ptrs[s], profile=profile)
             t.append(time.perf_counter())
             self.rt.stream_wait_slot(s, comm.cuda_stream)

@@ -443,7 +443,32 @@ def test_two_ranks_p2p_and_nccl_gather_are_bit_identical():
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", "29531", os.path.join(root, "tools", "p2p_check.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "p2p: 2 ranks" in out.stdout and "mode used = p2p" in out.stdout and "nccl: 2 ranks" in out.stdout
+    assert "p2p: 2 ranks" in out.stdout and "mode used = p2p" in out.stdout and "nccl: 2 ranks" in out.stdout and "host: 2 ranks" in out.stdout
+
+
+def test_tiles_stored_straight_into_registered_host_memory(P, cornell):
+    """pgrt_host_frame_register: the resolve kernel writes through the mapping of a page-aligned host buffer (what the
+    ranks of a box share in mode "host" of dist.ShardedRenderer); the frame must equal the ordinary host render."""
+    import ctypes, mmap
+    rt = P.raytracer_for(cornell)
+    params = dict(sampling_width=2, seed=4)
+    ref, st = rt.render(params)
+    nbytes = (rt.width * rt.height * 16 + 4095) // 4096 * 4096
+    mm = mmap.mmap(-1, nbytes)
+    base = ctypes.addressof(ctypes.c_char.from_buffer(mm))
+    dev_ptr = rt.host_frame_register(base, nbytes)
+    try:
+        rt.set_shard(0, 1)
+        for slot in (0, 1):                      # two frames in flight into the same host frame (same pixels)
+            rt.render_begin(slot, params, frame_ptr=dev_ptr)
+        tot = [rt.render_end(slot)["total"] for slot in (0, 1)]
+        got = np.frombuffer(mm, dtype=np.float32, count=rt.width * rt.height * 4).reshape(rt.height, rt.width, 4).copy()
+    finally:
+        rt.host_frame_unregister(base)
+    assert tot == [st["total"], st["total"]]
+    assert np.array_equal(got, ref, equal_nan=True)
+    with pytest.raises(P.PgrtError):
+        rt.host_frame_register(base + 8, 4096)   # not page-aligned
 
 
 def test_dof_converges_to_the_same_mean_for_different_seeds(P, oracle_mod, cornell):
