@@ -846,13 +846,16 @@ static int frame_begin(pgrt_context* ctx, int slot, const pgrt_render_params* p,
     if (ctx->batch_limit) S.batch_slots = std::min(S.batch_slots, ctx->batch_limit);   // do not overflow the same way every frame
     if (S.dyn) {
         // The persistent secondary-ray kernel is latency-bound (dependent chains of up to max_depth traversals) and its
-        // CTAs hold their SM slots while they wait, so its grid decides how many frames can be resident at once.  A frame
-        // alone on the GPU (blocking call) wants 4 CTAs/SM; pipelined frames want the grid in proportion to the batch:
-        // 4/SM from 2 M primary samples up, 1/SM for a 0.3 M-sample frame or shard (profiles/r1_sweep_secondary.txt, r1_sweep_small_frames.txt).
+        // CTAs hold registers and warp slots while they wait, so its grid decides how many frames can be resident at
+        // once.  A frame alone on the GPU (blocking call) wants 4 CTAs/SM for latency.  Pipelined frames want a small
+        // grid in proportion to the batch - fuller warps, more frames side by side: one CTA per 7 000 primary samples,
+        // at most 2/SM (C2: 296 CTAs, +4 % over 592; C1: 44 CTAs, +9 % over 148; profiles/r1_sweep_small_frames.txt).
         const uint64_t samples = S.batch_slots * (uint64_t)SPP;
-        int want = latency ? 4 : (int)std::min<uint64_t>(4, std::max<uint64_t>(1, (samples + 262144) / 524288));
-        if (ctx->secondary_per_sm_env) want = ctx->secondary_per_sm_env;
-        S.secondary_grid = ctx->sm_count * std::min(ctx->secondary_per_sm_max, want);
+        const int cap = ctx->sm_count * ctx->secondary_per_sm_max;
+        int grid = latency ? ctx->sm_count * 4 : (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 2, std::max<uint64_t>(32, samples / 7000));
+        if (ctx->secondary_per_sm_env) grid = ctx->sm_count * ctx->secondary_per_sm_env;
+        if (const char* e = getenv("PGRT_SECONDARY_CTAS")) grid = std::max(1, atoi(e));
+        S.secondary_grid = std::min(grid, cap);
     }
     S.rs = pgrt_render_stats{};
     rc = enqueue_frame(ctx, S);
@@ -1012,7 +1015,9 @@ extern "C" int pgrt_debug_flush_l2(pgrt_context* ctx, int32_t slot, uint64_t byt
     if (slot < 0 || slot >= PGRT_MAX_INFLIGHT || bytes < 16) return ctx->fail(PGRT_ERR_INVALID, "pgrt_debug_flush_l2: bad arguments");
     cudaSetDevice(ctx->device);
     if (ctx->flush_buf.n < bytes / 16) { sync_all_slots(ctx); CUDA_TRY(ctx->flush_buf.ensure(bytes / 16)); }
-    k_l2_flush<<<ctx->sm_count * 8, 256, 0, ctx->slots[slot].stream>>>(ctx->flush_buf.p, bytes / 16, value);
+    // a grid that leaves room on every SM: the fill runs beside the other frames' kernels instead of displacing them
+    static const int flush_ctas = getenv("PGRT_FLUSH_CTAS_PER_SM") ? std::max(1, atoi(getenv("PGRT_FLUSH_CTAS_PER_SM"))) : 2;
+    k_l2_flush<<<ctx->sm_count * flush_ctas, 256, 0, ctx->slots[slot].stream>>>(ctx->flush_buf.p, bytes / 16, value);
     ctx->launches++;
     LAUNCH_OK();
     return PGRT_OK;
