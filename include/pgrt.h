@@ -190,6 +190,10 @@ int pgrt_render_shard_to_frame_begin(pgrt_context* ctx, const pgrt_render_params
 int pgrt_render_end(pgrt_context* ctx, int32_t slot, pgrt_render_stats* stats);
 void* pgrt_slot_stream(pgrt_context* ctx, int32_t slot);                          /* cudaStream_t of a slot (slot 0 = pgrt_set_stream's) */
 int pgrt_stream_wait_slot(pgrt_context* ctx, int32_t slot, void* cuda_stream);    /* make `cuda_stream` wait for the slot's frame        */
+/* cross-frame accumulation (the step after the path; the reference's Producer re-renders from scratch every iteration,
+ * simpleguidx11.cpp:95-118): n_frames finished frames with seeds p->seed, p->seed + 1, ... are summed on the device in
+ * frame order (float) and divided by n_frames; rgba_host as pgrt_render.  stats = totals over the frames. */
+int pgrt_render_accumulate(pgrt_context* ctx, const pgrt_render_params* p, int32_t n_frames, float* rgba_host, pgrt_render_stats* stats);
 /* single-pixel hook with the signature of SimpleGuiDX11::get_pixel (simpleguidx11.h:27): serves pixel (x,y) of
  * the frame rendered by the last pgrt_render* call (re-renders when the camera, scene or params changed). */
 int pgrt_get_pixel(pgrt_context* ctx, const pgrt_render_params* p, int32_t x, int32_t y, float rgba[4]);

@@ -74,6 +74,7 @@ SYMBOLS = {
     "pgrt_render_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),
     "pgrt_render_device_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),
     "pgrt_render_shard_device_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),
+    "pgrt_render_accumulate": (C.c_int, [_VP, C.POINTER(RenderParams), C.c_int32, _VP, C.POINTER(RenderStats)]),
     "pgrt_frame_alloc": (C.c_int, [_VP, _U64, C.POINTER(_VP)]),
     "pgrt_frame_free": (C.c_int, [_VP, _VP]),
     "pgrt_frame_export": (C.c_int, [_VP, _VP, C.c_char_p]),

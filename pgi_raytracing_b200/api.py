@@ -135,6 +135,17 @@ class Raytracer:
         self._check(self.lib.pgrt_render(self.h, C.byref(p), _ptr(out), C.byref(rs), int(profile)))
         return out, self._stats(rs)
 
+    def render_accumulate(self, n_frames: int, params=None, out: np.ndarray | None = None):
+        """Mean of ``n_frames`` finished frames with seeds seed, seed+1, ... (``pgrt_render_accumulate``; summed on the
+        device in frame order).  The progressive loop the reference lacks (it re-renders from scratch each iteration)."""
+        p = self._params(params)
+        if out is None:
+            out = np.empty((self.height, self.width, 4), np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == self.width * self.height * 4
+        rs = L.RenderStats()
+        self._check(self.lib.pgrt_render_accumulate(self.h, C.byref(p), int(n_frames), _ptr(out), C.byref(rs)))
+        return out, self._stats(rs)
+
     def render_device(self, device_ptr: int, params=None, profile: bool = False) -> dict:
         p = self._params(params); rs = L.RenderStats()
         self._check(self.lib.pgrt_render_device(self.h, C.byref(p), C.c_void_p(device_ptr), C.byref(rs), int(profile)))

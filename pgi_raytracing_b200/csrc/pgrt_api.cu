@@ -125,6 +125,7 @@ struct pgrt_context {
     int trace_ctas_per_sm = 6;        // persistent k_trace grid (PGRT_TRACE_CTAS_PER_SM)
     DevBuf<uint32_t> d_ids;
     DevBuf<uint4> flush_buf;          // pgrt_debug_flush_l2
+    DevBuf<float4> acc_sum, acc_frames[4]; cudaEvent_t acc_event = nullptr;   // pgrt_render_accumulate
     uint32_t* h_pin = nullptr;        // pinned scratch for small read-backs of the build
     size_t max_batch_samples = (size_t)1 << 23;
     uint64_t batch_limit = 0;         // pixel slots per batch that last survived a queue overflow (0 = none yet); reset by pgrt_commit
@@ -213,6 +214,7 @@ extern "C" void pgrt_destroy(pgrt_context* ctx) {
     ctx->env.bytes.release();
     for (FrameSlot& S : ctx->slots) S.release();
     ctx->d_ids.release(); ctx->flush_buf.release();
+    ctx->acc_sum.release(); for (auto& b : ctx->acc_frames) b.release(); if (ctx->acc_event) cudaEventDestroy(ctx->acc_event);
     for (int k = 0; k < 2; ++k) { if (ctx->stage[k]) cudaFreeHost(ctx->stage[k]); if (ctx->stage_done[k]) cudaEventDestroy(ctx->stage_done[k]); }
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     delete ctx;
@@ -923,6 +925,79 @@ extern "C" int pgrt_render(pgrt_context* ctx, const pgrt_render_params* p, float
     if (!rgba_host) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render: null destination");
     if (ctx->shard.n_ranks != 1) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render: context is sharded; use pgrt_render_shard_device");
     return render_frame(ctx, p, nullptr, 0, rgba_host, stats, profile);
+}
+
+// ---- cross-frame accumulation (the reference's Producer re-renders from scratch every iteration,
+// simpleguidx11.cpp:95-118; here n finished frames with seeds seed, seed+1, ... are averaged on the device)
+__global__ void __launch_bounds__(256) k_accumulate(float4* __restrict__ acc, const float4* __restrict__ frame, size_t n, int first) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 f = frame[i];
+    if (first) { acc[i] = f; return; }
+    const float4 a = acc[i];
+    acc[i] = make_float4(a.x + f.x, a.y + f.y, a.z + f.z, a.w + f.w);   // in frame order: the sum is reproducible
+}
+__global__ void __launch_bounds__(256) k_accumulate_finish(float4* __restrict__ acc, size_t n, float count) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = acc[i];
+    acc[i] = make_float4(a.x / count, a.y / count, a.z / count, a.w / count);
+}
+extern "C" int pgrt_render_accumulate(pgrt_context* ctx, const pgrt_render_params* p, int32_t n_frames, float* rgba_host, pgrt_render_stats* stats) {
+    CHECK_CTX(ctx);
+    if (!p || !rgba_host || n_frames < 1) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_accumulate: bad arguments");
+    if (ctx->shard.n_ranks != 1) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_accumulate: context is sharded");
+    int rc = validate_frame(ctx, p);
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    const size_t n = (size_t)ctx->cam.width * ctx->cam.height;
+    const int D = std::min<int>(4, n_frames);
+    sync_all_slots(ctx);
+    CUDA_TRY(ctx->acc_sum.ensure(n));
+    for (int s = 0; s < D; ++s) CUDA_TRY(ctx->acc_frames[s].ensure(n));
+    if (!ctx->acc_event) CUDA_TRY(cudaEventCreateWithFlags(&ctx->acc_event, cudaEventDisableTiming));
+    const unsigned blocks = (unsigned)div_up(n, 256);
+    for (int attempt = 0;; ++attempt) {
+        pgrt_render_stats total = {}, rs;
+        bool overflowed = false;
+        auto collect = [&](int slot) -> int {
+            int r = frame_end(ctx, slot, &rs);
+            if (r) return r;
+            overflowed |= rs.overflow_retries != 0;
+            total.rays_primary += rs.rays_primary; total.rays_shadow += rs.rays_shadow; total.rays_reflection += rs.rays_reflection;
+            total.rays_refraction += rs.rays_refraction; total.launches += rs.launches + 1; total.batches += rs.batches; total.frame_ms += rs.frame_ms;
+            total.trace_launches += rs.trace_launches;
+            return PGRT_OK;
+        };
+        for (int i = 0; i < n_frames; ++i) {
+            const int slot = i % D;
+            if (i >= D && (rc = collect(slot))) return rc;
+            pgrt_render_params pi = *p;
+            pi.seed = p->seed + (uint32_t)i;
+            if ((rc = frame_begin(ctx, slot, &pi, ctx->acc_frames[slot].p, 0, nullptr, 0))) return rc;
+            cudaStream_t st = ctx->slots[slot].stream;
+            if (i > 0) CUDA_TRY(cudaStreamWaitEvent(st, ctx->acc_event, 0));
+            k_accumulate<<<blocks, 256, 0, st>>>(ctx->acc_sum.p, ctx->acc_frames[slot].p, n, i == 0);
+            LAUNCH_OK();
+            CUDA_TRY(cudaEventRecord(ctx->acc_event, st));
+            ctx->launches++;
+        }
+        for (int i = std::max(0, n_frames - D); i < n_frames; ++i)
+            if ((rc = collect(i % D))) return rc;
+        // a queue overflow re-renders a frame AFTER its first version was summed: start again (the smaller batch is remembered)
+        if (overflowed && attempt == 0) continue;
+        if (overflowed) return ctx->fail(PGRT_ERR_OVERFLOW, "pgrt_render_accumulate: secondary-ray queues keep overflowing; raise PGRT_MIN_LEVEL_CAP");
+        cudaStream_t st = ctx->slots[0].stream;
+        CUDA_TRY(cudaStreamWaitEvent(st, ctx->acc_event, 0));
+        k_accumulate_finish<<<blocks, 256, 0, st>>>(ctx->acc_sum.p, n, (float)n_frames);
+        LAUNCH_OK();
+        ctx->launches++;
+        CUDA_TRY(cudaMemcpyAsync(rgba_host, ctx->acc_sum.p, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        ctx->px_valid = false;
+        if (stats) *stats = total;
+        return PGRT_OK;
+    }
 }
 
 // ---- pipelined frames

@@ -545,3 +545,67 @@ bool WritePFM(const char* file_name, const float* rgba, int width, int height) {
     fclose(f);
     return true;
 }
+
+// ---- PNG out (headless presentation): 8-bit RGB, filter 0, zlib "stored" blocks (valid, uncompressed)
+static uint32_t crc32_update(uint32_t crc, const uint8_t* p, size_t n) {
+    static uint32_t table[256]; static bool ready = false;
+    if (!ready) {
+        for (uint32_t i = 0; i < 256; ++i) { uint32_t c = i; for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1; table[i] = c; }
+        ready = true;
+    }
+    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xFFu] ^ (crc >> 8);
+    return crc;
+}
+static void put_be32(std::vector<uint8_t>& v, uint32_t x) { v.push_back(uint8_t(x >> 24)); v.push_back(uint8_t(x >> 16)); v.push_back(uint8_t(x >> 8)); v.push_back(uint8_t(x)); }
+static bool write_chunk(FILE* f, const char type[4], const std::vector<uint8_t>& data) {
+    std::vector<uint8_t> head; put_be32(head, (uint32_t)data.size());
+    uint32_t crc = crc32_update(0xFFFFFFFFu, (const uint8_t*)type, 4);
+    crc = crc32_update(crc, data.data(), data.size()) ^ 0xFFFFFFFFu;
+    std::vector<uint8_t> tail; put_be32(tail, crc);
+    return fwrite(head.data(), 1, 4, f) == 4 && fwrite(type, 1, 4, f) == 4 && fwrite(data.data(), 1, data.size(), f) == data.size() && fwrite(tail.data(), 1, 4, f) == 4;
+}
+
+bool WritePNG(const char* file_name, const float* rgba, int width, int height) {
+    if (width <= 0 || height <= 0) return false;
+    FILE* f = fopen(file_name, "wb");
+    if (!f) return false;
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    bool ok = fwrite(sig, 1, 8, f) == 8;
+    std::vector<uint8_t> ihdr; put_be32(ihdr, (uint32_t)width); put_be32(ihdr, (uint32_t)height);
+    ihdr.push_back(8); ihdr.push_back(2); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);   // 8 bit, RGB, deflate, adaptive filters, no interlace
+    ok = ok && write_chunk(f, "IHDR", ihdr);
+    const size_t row_bytes = 1 + (size_t)width * 3;
+    std::vector<uint8_t> raw(row_bytes * (size_t)height);
+    for (int y = 0; y < height; ++y) {
+        uint8_t* row = &raw[row_bytes * (size_t)y];
+        row[0] = 0;                                                                                // filter type None
+        for (int x = 0; x < width; ++x) for (int c = 0; c < 3; ++c) row[1 + 3 * x + c] = to8(rgba[((size_t)y * width + x) * 4 + c]);
+    }
+    uint32_t a = 1, b = 0;                                                                         // Adler-32 of the raw stream
+    for (size_t i = 0; i < raw.size();) {
+        const size_t n = std::min<size_t>(5552, raw.size() - i);
+        for (size_t k = 0; k < n; ++k) { a += raw[i + k]; b += a; }
+        a %= 65521u; b %= 65521u; i += n;
+    }
+    std::vector<uint8_t> z; z.reserve(raw.size() + raw.size() / 65535 * 5 + 16);
+    z.push_back(0x78); z.push_back(0x01);
+    for (size_t i = 0; i < raw.size();) {
+        const size_t n = std::min<size_t>(65535, raw.size() - i);
+        z.push_back(i + n == raw.size() ? 1 : 0);                                                  // BFINAL, BTYPE = 00 (stored)
+        z.push_back(uint8_t(n)); z.push_back(uint8_t(n >> 8)); z.push_back(uint8_t(~n)); z.push_back(uint8_t((~n) >> 8));
+        z.insert(z.end(), raw.begin() + (ptrdiff_t)i, raw.begin() + (ptrdiff_t)(i + n));
+        i += n;
+    }
+    put_be32(z, (b << 16) | a);
+    ok = ok && write_chunk(f, "IDAT", z) && write_chunk(f, "IEND", {});
+    fclose(f);
+    return ok;
+}
+
+bool WriteImageFile(const char* file_name, const float* rgba, int width, int height) {
+    const std::string n(file_name);
+    auto ends = [&](const char* e) { const size_t l = strlen(e); return n.size() >= l && strcasecmp(n.c_str() + n.size() - l, e) == 0; };
+    if (ends(".png")) return WritePNG(file_name, rgba, width, height);
+    if (ends(".pfm")) return WritePFM(file_name, rgba, width, height);
+    return WritePPM(file_name, rgba, width, height);
+}

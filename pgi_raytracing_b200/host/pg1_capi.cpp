@@ -72,6 +72,7 @@ void pg1_image_info(void* h, int* out4) { const RawImage* im = (RawImage*)h; out
 void pg1_image_bytes(void* h, unsigned char* dst) { const RawImage* im = (RawImage*)h; memcpy(dst, im->bytes.data(), im->bytes.size()); }
 void pg1_free_image(void* h) { delete (RawImage*)h; }
 int pg1_write_ppm(const char* file_name, const float* rgba, int w, int h) { return WritePPM(file_name, rgba, w, h) ? 0 : -1; }
+int pg1_write_image(const char* file_name, const float* rgba, int w, int h) { return WriteImageFile(file_name, rgba, w, h) ? 0 : -1; }
 
 // ---- camera (host copy)
 void pg1_camera_ray(int w, int h, float fov_y, const float* from, const float* at, float x, float y, int lens, float focal, float r1, float r2, float* out9) {

@@ -3,7 +3,7 @@
 // Producer loop become `--frames N` iterations and an image file.
 //
 //   pg1_b200 [obj] [background] [--width W --height H] [--frames N] [--spp-width S] [--aperture A] [--focal F] [--depth D]
-//            [--gamma G] [--seed K] [--no-jitter] [--device N] [--out frame.ppm] [--pfm frame.pfm]
+//            [--gamma G] [--seed K] [--no-jitter] [--device N] [--accumulate N] [--out frame.ppm|.png|.pfm] [--pfm frame.pfm]
 // Defaults = the reference's hard-coded values: ../../../data/6887_allied_avenger.obj, ../../../data/spherical_map_lakeside.jpg,
 // 640x480, fov_y 42.185 deg, eye (-140,-175,80) -> (0,0,40), 3x3 jittered samples, thin lens f=200 a=5, depth 7, gamma 0.5.
 #include <chrono>
@@ -17,7 +17,7 @@
 namespace {
 struct Options {
     std::string obj = "../../../data/6887_allied_avenger.obj", bg = "../../../data/spherical_map_lakeside.jpg";
-    int width = 640, height = 480, frames = 3, spp = 3, depth = 7, device = 0;
+    int width = 640, height = 480, frames = 3, spp = 3, depth = 7, device = 0, accumulate = 0;
     float aperture = 5.0f, focal = 200.0f, gamma = 0.5f;
     unsigned seed = 1; bool jitter = true;
     std::string out = "frame.ppm", pfm;
@@ -44,7 +44,13 @@ int raytrace_loop(const std::string object_file_name, const std::string backgrou
                st.frame_ms, rays, (unsigned long long)st.rays_primary, (unsigned long long)st.rays_shadow, (unsigned long long)st.rays_reflection,
                (unsigned long long)st.rays_refraction, rays / (ms * 1e3));
     }
-    if (!g_opt.out.empty() && !WritePPM(g_opt.out.c_str(), frame.data(), g_opt.width, g_opt.height)) printf("cannot write %s\n", g_opt.out.c_str());
+    if (g_opt.accumulate > 0) {                // progressive: the mean of N iterations with consecutive seeds
+        pgrt_render_stats st;
+        raytracer.RenderAccumulated(g_opt.accumulate, frame.data(), &st);
+        printf("accumulated %d frames: %.3f ms device, %llu rays\n", g_opt.accumulate, st.frame_ms,
+               (unsigned long long)(st.rays_primary + st.rays_shadow + st.rays_reflection + st.rays_refraction));
+    }
+    if (!g_opt.out.empty() && !WriteImageFile(g_opt.out.c_str(), frame.data(), g_opt.width, g_opt.height)) printf("cannot write %s\n", g_opt.out.c_str());
     if (!g_opt.pfm.empty()) WritePFM(g_opt.pfm.c_str(), frame.data(), g_opt.width, g_opt.height);
     return EXIT_SUCCESS;
 }
@@ -67,6 +73,7 @@ int main(int argc, char** argv) {
         else if (a == "--seed") g_opt.seed = (unsigned)strtoul(val(), nullptr, 10);
         else if (a == "--no-jitter") g_opt.jitter = false;
         else if (a == "--device") g_opt.device = atoi(val());
+        else if (a == "--accumulate") g_opt.accumulate = atoi(val());
         else if (a == "--out") g_opt.out = val();
         else if (a == "--pfm") g_opt.pfm = val();
         else if (positional == 0) { g_opt.obj = a; positional++; }

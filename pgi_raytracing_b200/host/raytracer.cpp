@@ -109,6 +109,11 @@ void Raytracer::RenderFrame(float* rgba, pgrt_render_stats* stats) {
     check(pgrt_render(ctx_, &p, rgba, stats, 0));
 }
 
+void Raytracer::RenderAccumulated(int n_frames, float* rgba, pgrt_render_stats* stats) {
+    const pgrt_render_params p = params();
+    check(pgrt_render_accumulate(ctx_, &p, n_frames, rgba, stats));
+}
+
 Color4f Raytracer::get_pixel(const int x, const int y, const float /*t: ignored, as in the reference*/) {
     const pgrt_render_params p = params();
     float px[4];

@@ -45,6 +45,8 @@ public:
 
     // one Producer iteration into a caller-owned frame of width*height*4 floats (row 0 = top, a = 1)
     void RenderFrame(float* rgba, pgrt_render_stats* stats = nullptr);
+    // progressive loop: the mean of n_frames Producer iterations with seeds seed, seed+1, ... (the reference starts over every iteration)
+    void RenderAccumulated(int n_frames, float* rgba, pgrt_render_stats* stats = nullptr);
     // rtcIntersect1 on caller-owned RTCRayHit-compatible records
     void Intersect(pgrt_rayhit* rayhits, size_t n);
 

@@ -593,3 +593,37 @@ def test_non_finite_vertices_are_an_error_not_a_hang(P):
         return
     img, st = rt.render(dict(sampling_width=1, jitter=0, aperture=0.0))   # if the build went through, frames must still come back
     assert st["primary"] == 32 * 24
+
+
+def test_cross_frame_accumulation(P, oracle_mod, cornell):
+    """pgrt_render_accumulate: n finished frames, seeds s, s+1, ..., summed on the device in frame order and
+    divided by n.  (1) bit-exact against the same float sum of the library's own single frames; (2) against the oracle's
+    frames of the same seeds within the image bars; (3) the ray count is the sum; (4) more frames = closer to a reference
+    of many samples."""
+    rt = P.raytracer_for(cornell); o = oracle_mod.Oracle(cornell)
+    base = dict(sampling_width=2, seed=11)
+    n = 6                                            # more frames than the 4 slots it keeps in flight
+    singles, rays = [], 0
+    for i in range(n):
+        img, st = rt.render(dict(base, seed=11 + i)); singles.append(img.copy()); rays += st["total"]
+    acc = singles[0].copy()
+    for f in singles[1:]:
+        acc = acc + f
+    expect = acc / np.float32(n)
+    got, st = rt.render_accumulate(n, base)
+    assert np.array_equal(got, expect, equal_nan=True)
+    assert st["total"] == rays
+    ref = None
+    for i in range(n):
+        f = o.render(oracle_mod.make_params(sampling_width=2, seed=11 + i))[0]
+        ref = f.copy() if ref is None else ref + f
+    ok, psnr = image_bars(P, ref / np.float32(n), got)
+    assert ok >= 0.995 and psnr >= 45.0, (ok, psnr)
+    # convergence: against 12x12 samples of another seed the 6-frame mean beats a single frame
+    many, _ = rt.render(dict(sampling_width=12, seed=1234))
+    err = lambda a: float(np.mean((P.to_srgb8(a).astype(float) - P.to_srgb8(many).astype(float)) ** 2))
+    assert err(got) < 0.6 * err(singles[0])
+    one, st1 = rt.render_accumulate(1, base)
+    assert np.array_equal(one, singles[0], equal_nan=True)
+    with pytest.raises(P.PgrtError):
+        rt.render_accumulate(0, base)

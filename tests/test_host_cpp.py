@@ -32,7 +32,7 @@ def host():
         ("pg1_surface_triangles", C.c_int, [VP, C.c_int]), ("pg1_surface_name", C.c_char_p, [VP, C.c_int]), ("pg1_surface_material", C.c_int, [VP, C.c_int]),
         ("pg1_surface_data", None, [VP, C.c_int, VP, VP, VP]), ("pg1_material", C.c_char_p, [VP, C.c_int, VP]),
         ("pg1_load_image", VP, [C.c_char_p]), ("pg1_image_info", None, [VP, VP]), ("pg1_image_bytes", None, [VP, VP]), ("pg1_free_image", None, [VP]),
-        ("pg1_write_ppm", C.c_int, [C.c_char_p, VP, C.c_int, C.c_int]),
+        ("pg1_write_ppm", C.c_int, [C.c_char_p, VP, C.c_int, C.c_int]), ("pg1_write_image", C.c_int, [C.c_char_p, VP, C.c_int, C.c_int]),
         ("pg1_camera_ray", None, [C.c_int, C.c_int, C.c_float, VP, VP, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, VP]),
         ("pg1_raytracer_create", VP, [C.c_int, C.c_int, C.c_float, VP, VP, C.c_char_p]), ("pg1_raytracer_destroy", None, [VP]),
         ("pg1_raytracer_load_scene", C.c_int, [VP, C.c_char_p, C.c_char_p]),
@@ -341,3 +341,28 @@ def test_parallel_loader_equals_single_thread(host, tmp_path, monkeypatch):
             assert n0 == n1 and np.array_equal(p0, p1) and np.array_equal(q0, q1) and np.array_equal(u0, u1)
     for i, mesh in enumerate(sc.meshes):
         assert np.array_equal(results[0][i][1], mesh.pos.reshape(-1, 9)) and np.array_equal(results[0][i][3], mesh.uv.reshape(-1, 6))
+
+
+@pytest.mark.parametrize("size", [(37, 21), (640, 480), (1, 1)])
+def test_png_writer(host, tmp_path, size):
+    """WritePNG (headless presentation): a valid PNG (PIL reads it; CRCs and Adler-32 are checked there) with
+    the 8-bit quantisation of the D3D11 back buffer (round(clamp(c,0,1)*255), NaN -> 0); larger than one 64 KiB stored block
+    at 640x480; and our own decoder reads it back to the same bytes."""
+    from PIL import Image
+    w, h = size
+    rng = np.random.default_rng(w * h)
+    rgba = rng.uniform(-0.2, 1.2, (h, w, 4)).astype(np.float32)
+    rgba[0, 0, 0] = np.nan; rgba[-1, -1, 1] = np.inf
+    p = str(tmp_path / "frame.png")
+    assert host.pg1_write_image(p.encode(), rgba.ctypes.data, w, h) == 0
+    c = rgba[..., :3].copy(); c[np.isnan(c)] = 0.0
+    want = np.floor(np.clip(c, 0.0, 1.0) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
+    im = Image.open(p); im.load()
+    assert im.mode == "RGB" and im.size == (w, h)
+    assert np.array_equal(np.asarray(im), want)
+    buf, ww, hh, pitch, bpp = load_image(host, p)
+    assert (ww, hh, bpp) == (w, h, 3)
+    assert np.array_equal(buf[:, :3 * w].reshape(h, w, 3)[..., ::-1], want)
+    ppm = str(tmp_path / "frame.ppm")
+    assert host.pg1_write_image(ppm.encode(), rgba.ctypes.data, w, h) == 0          # by extension
+    assert np.array_equal(np.asarray(Image.open(ppm)), want)
