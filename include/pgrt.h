@@ -60,7 +60,10 @@ typedef struct pgrt_render_params {
     uint32_t seed;            /* counter-based RNG seed (replaces the clock-seeded mt19937, raytracer.cpp:407) */
     int32_t camera_mode;      /* 0 thin lens generate_ray(x,y,f,a) PinHoleCamera.cpp:65-105; 1 pinhole :31-63 */
     int32_t shader_mode;      /* 0 Whitted (trace as shipped); 1 Lambert (diffuse addend of :377 only);
-                                 2 normal shader (the commented block raytracer.cpp:274-280)                 */
+                                 2 normal shader (the commented block raytracer.cpp:274-280);
+                                 3 path tracing (README.md:21 "To do"; no reference counterpart): dielectrics as in 0, every other
+                                   hit = its Phong value + albedo x the radiance of one cosine-weighted bounce (the environment
+                                   map lights the scene); converge with pgrt_render_accumulate.  Bounces count as reflection rays. */
     int32_t scheduler;        /* 0 dynamic: one persistent kernel owns every ray of level >= 1 (default);
                                  1 level-synchronous wavefront (one queue per recursion level).  Same image, bit for bit. */
     int32_t shadow_mode;      /* 0 is_illuminated as shipped (shadow rays that leave the light towards the hit POSITION,

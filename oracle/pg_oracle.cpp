@@ -75,7 +75,8 @@ struct orc_params {
     float gamma_level;       // raytracer.cpp:450  (0.5)
     uint32_t seed;
     int32_t camera_mode;     // 0 thin lens PinHoleCamera.cpp:65-105, 1 pinhole :31-63
-    int32_t shader_mode;     // 0 Whitted (trace as shipped), 1 Lambert (diffuse term only), 2 normal shader (:274-280)
+    int32_t shader_mode;     // 0 Whitted (trace as shipped), 1 Lambert (diffuse term only), 2 normal shader (:274-280),
+                             // 3 path tracing (README.md:21 to-do; spec in include/pgrt.h and path_bounce_direction below)
     int32_t reserved[7];
 };
 struct orc_stats {
@@ -501,6 +502,25 @@ struct Tracer {
         return r;
     }
 
+    // Diffuse bounce of shader_mode 3: normalize(n + q), q uniform on the unit sphere by rejection from the cube; keyed by
+    // the bits of the hit point, the level and the frame seed (the same spec as shading.cuh, restated).
+    static V3 path_bounce_direction(V3 n, V3 hitp, uint32_t seed, int level) {
+        auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+        uint32_t k = mix32(seed ^ (0x9E3779B9u * (uint32_t)(level + 1)));
+        k = mix32(k ^ bits(hitp.x)); k = mix32(k ^ bits(hitp.y)); k = mix32(k ^ bits(hitp.z));
+        V3 q = n;
+        for (uint32_t t = 0; t < 16u; ++t) {
+            const float x = 2.0f * ((float)(mix32(k + 0x85EBCA6Bu * (3u * t + 1u)) >> 8) * (1.0f / 16777216.0f)) - 1.0f;
+            const float y = 2.0f * ((float)(mix32(k + 0x85EBCA6Bu * (3u * t + 2u)) >> 8) * (1.0f / 16777216.0f)) - 1.0f;
+            const float z = 2.0f * ((float)(mix32(k + 0x85EBCA6Bu * (3u * t + 3u)) >> 8) * (1.0f / 16777216.0f)) - 1.0f;
+            const V3 c = v3(x, y, z);
+            const float l2 = dot(c, c);
+            if (l2 <= 1.0f && l2 > 1e-6f) { q = normalize(c); break; }
+        }
+        const V3 d = v3(n.x + q.x, n.y + q.y, n.z + q.z);
+        return dot(d, d) > 1e-8f ? normalize(d) : n;
+    }
+
     Color4 trace(const Ray& ray, int level, Hit* first_hit = nullptr) {                 // :237-394
         const Hit h = get_ray_hit(ray);
         if (first_hit) *first_hit = h;
@@ -519,7 +539,7 @@ struct Tracer {
             }
             if (level >= p.max_depth) { Color4 k = {0, 0, 0, 1}; return k; }            // :282-283
             const V3 v = -direction_vector;
-            if (material.type == 4 && p.shader_mode == 0) {                             // :294-323
+            if (material.type == 4 && (p.shader_mode == 0 || p.shader_mode == 3)) {     // :294-323
                 const Ray reflection_ray = get_reflection_ray(direction_vector, normal_vector, hit_vector, n1);
                 n_refl++;
                 const Color4 reflection_color = trace(reflection_ray, level + 1);
@@ -570,6 +590,15 @@ struct Tracer {
                         red += (i_d_r * m_d_r * ndl + i_s_r * m_s_r * spec);
                     }
                 }
+            }
+            if (p.shader_mode == 3) {
+                // path tracing (no reference counterpart): the Phong value above + albedo x one cosine-weighted bounce
+                const V3 bd = path_bounce_direction(normal_vector, hit_vector, p.seed, level);
+                const Ray bounce = {hit_vector.x, hit_vector.y, hit_vector.z, 0.01f, bd.x, bd.y, bd.z, ray.time, FLT_MAX};
+                n_refl++;
+                const Color4 c = trace(bounce, level + 1);
+                Color4 o = {blue + m_d_b * c.r, green + m_d_g * c.g, red + m_d_r * c.b, 1.0f};
+                return o;
             }
             Color4 o = {blue, green, red, 1.0f};                                        // :385
             return o;

@@ -666,6 +666,7 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
     const bool dyn = S.dyn;
     FrameTimer tm{&S, (profile & 1) != 0};
     const bool count = (profile & 2) != 0;
+    const bool path = p->shader_mode == 3;   // path-tracing instantiations of k_shade / k_secondary / k_combine
     pgrt_render_stats& rs = S.rs;
     S.ev_used = 0; rs.launches = 0; rs.trace_launches = 0; rs.batches = 0;
     Counters* cnt = S.d_counters.p;
@@ -692,7 +693,9 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
             rs.launches++; rs.trace_launches++;
             tm.end();
             tm.begin(KC_SHADE, 0);
-            k_shade<<<shade_grid, 256, 0, st>>>(sc, *p, g0, 0, S.levels[0], Ln, P, 1, cnt); rs.launches++;
+            if (path) k_shade<true><<<shade_grid, 256, 0, st>>>(sc, *p, g0, 0, S.levels[0], Ln, P, 1, cnt);
+            else k_shade<false><<<shade_grid, 256, 0, st>>>(sc, *p, g0, 0, S.levels[0], Ln, P, 1, cnt);
+            rs.launches++;
             tm.end();
             tm.begin(KC_TRACE, 0);
             if (count) k_phong<true><<<phong_grid, 128, 0, st>>>(sc, *p, g0, 0, S.levels[0], cnt);
@@ -701,8 +704,13 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
             tm.end();
             tm.begin(KC_TRACE, 1);
             const size_t smem = (size_t)4 * p->max_depth * (PGRT_WSTACK + 1) * sizeof(uint32_t);   // <= 33.3 KB at max_depth 32
-            if (count) k_secondary<true><<<S.secondary_grid, 128, smem, st>>>(sc, *p, S.levels[0], P, cnt);
-            else k_secondary<false><<<S.secondary_grid, 128, smem, st>>>(sc, *p, S.levels[0], P, cnt);
+            if (path) {
+                if (count) k_secondary<true, true><<<S.secondary_grid, 128, smem, st>>>(sc, *p, S.levels[0], P, cnt);
+                else k_secondary<false, true><<<S.secondary_grid, 128, smem, st>>>(sc, *p, S.levels[0], P, cnt);
+            } else {
+                if (count) k_secondary<true, false><<<S.secondary_grid, 128, smem, st>>>(sc, *p, S.levels[0], P, cnt);
+                else k_secondary<false, false><<<S.secondary_grid, 128, smem, st>>>(sc, *p, S.levels[0], P, cnt);
+            }
             rs.launches++; rs.trace_launches++;
             tm.end();
         } else {
@@ -714,7 +722,9 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
                 tm.end();
                 if (dest_mode == 2) break;
                 tm.begin(KC_SHADE, l);
-                k_shade<<<shade_grid, 256, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], S.levels[l + 1], S.pool, 0, cnt); rs.launches++;
+                if (path) k_shade<true><<<shade_grid, 256, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], S.levels[l + 1], S.pool, 0, cnt);
+                else k_shade<false><<<shade_grid, 256, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], S.levels[l + 1], S.pool, 0, cnt);
+                rs.launches++;
                 tm.end();
                 tm.begin(KC_TRACE, l);   // Phong = shading preamble + one inline shadow traversal per light
                 if (count) k_phong<true><<<phong_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], cnt);
@@ -728,7 +738,11 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
             k_primary_ids<<<div_up(n_slots, 256), 256, 0, st>>>(sc, ctx->cam, ctx->shard, (uint32_t)slot0, n_slots, SPP, S.levels[0].hit, geom, prim); rs.launches++;
         } else {
             tm.begin(KC_SHADE);
-            if (!dyn) for (int l = n_levels - 2; l >= 0; --l) { k_combine<<<shade_grid, 256, 0, st>>>(l, S.levels[l], S.levels[l + 1], cnt); rs.launches++; }
+            if (!dyn) for (int l = n_levels - 2; l >= 0; --l) {
+                if (path) k_combine<true><<<shade_grid, 256, 0, st>>>(l, S.levels[l], S.levels[l + 1], cnt);
+                else k_combine<false><<<shade_grid, 256, 0, st>>>(l, S.levels[l], S.levels[l + 1], cnt);
+                rs.launches++;
+            }
             k_resolve<<<div_up(n_slots, 256), 256, 0, st>>>(ctx->cam, *p, ctx->shard, (uint32_t)slot0, n_slots, S.levels[0].color, S.host_dst ? S.d_frame.p : dest, dest_mode == 1); rs.launches++;
             tm.end();
         }
@@ -838,7 +852,7 @@ static int frame_begin(pgrt_context* ctx, int slot, const pgrt_render_params* p,
     S.n_levels = (dest_mode == 2) ? 1 : p->max_depth + 1;
     S.dyn = p->scheduler == 0 && dest_mode != 2 && S.n_levels > 1;
     if (S.dyn && ctx->secondary_per_sm_max == 0) {
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->secondary_per_sm_max, k_secondary<false>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->secondary_per_sm_max, k_secondary<false, false>, 128, 0));
         ctx->secondary_per_sm_max = std::max(1, ctx->secondary_per_sm_max);
         if (const char* e = getenv("PGRT_SECONDARY_CTAS_PER_SM")) ctx->secondary_per_sm_env = std::max(1, atoi(e));
     }

@@ -277,16 +277,28 @@ __device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool pred, in
 }
 
 // ---- K8 (per ray): classification of one (ray, hit) pair = the head of trace() (raytracer.cpp:247-323, :390-393)
-enum ShadeKind { SK_FINAL = 0, SK_PHONG = 1, SK_DIEL = 2 };
+enum ShadeKind { SK_FINAL = 0, SK_PHONG = 1, SK_DIEL = 2, SK_PATH = 3 };   // SK_PATH: Phong value + one diffuse bounce (shader_mode 3)
 struct ShadeOut {
     int kind;
     float4 color;           // SK_FINAL: the value trace() returns
     HitFrame f;             // SK_PHONG / SK_DIEL
     RayRec refl, refr;      // SK_DIEL
-    float4 att;             // SK_DIEL: attenuation rgb, R
+    float4 att;             // SK_DIEL: attenuation rgb, R;  SK_PATH: diffuse albedo in output channel order, w = -1 (marks the node)
     bool has_refr;          // SK_DIEL: the refraction ray exists (no total internal reflection)
 };
 
+// m_d of the Phong sum (raytracer.cpp:338-348): Kd with the x<->z naming swap, or the texel of the diffuse map
+__device__ __forceinline__ void diffuse_albedo(const DevScene& sc, const pgrt_material& mat, const HitFrame& f, float& m_d_r, float& m_d_g, float& m_d_b) {
+    if (mat.diffuse_tex < 0 || mat.diffuse_tex >= sc.n_textures) {         // :338-341
+        m_d_r = mat.diffuse[2]; m_d_g = mat.diffuse[1]; m_d_b = mat.diffuse[0];
+    } else {                                                                // :343-348
+        const Col3 texel = tex_get_texel(sc.textures[mat.diffuse_tex], f.tu, 1.0f - f.tv);
+        m_d_r = texel.r; m_d_g = texel.g; m_d_b = texel.b;
+    }
+}
+
+// PATH: compiled with the path-tracing branch (shader_mode 3).  The default instantiation carries none of it.
+template <bool PATH>
 __device__ __forceinline__ void shade_classify(const DevScene& sc, const pgrt_render_params& p, int level, float4 o, float4 d, float4 h, ShadeOut& s) {
     s.kind = SK_FINAL; s.has_refr = false;
     s.color = make_float4(0.f, 0.f, 0.f, 1.f);
@@ -305,7 +317,7 @@ __device__ __forceinline__ void shade_classify(const DevScene& sc, const pgrt_re
         s.color = make_float4((s.f.n.x + 1) / 2, (s.f.n.y + 1) / 2, (s.f.n.z + 1) / 2, 1.0f);
     } else if (level >= p.max_depth) {                                  // :282-283
         s.color = make_float4(0.f, 0.f, 0.f, 1.f);
-    } else if (mat.type == 4 && p.shader_mode == 0) {                   // :294-323
+    } else if (mat.type == 4 && (p.shader_mode == 0 || (PATH && p.shader_mode == 3))) {   // :294-323
         float n1, n2;
         if (d.w == PGRT_IOR_AIR) { n1 = PGRT_IOR_AIR; n2 = mat.ior; } else { n1 = mat.ior; n2 = PGRT_IOR_AIR; }   // :261-267
         s.kind = SK_DIEL;
@@ -323,6 +335,15 @@ __device__ __forceinline__ void shade_classify(const DevScene& sc, const pgrt_re
             const double q1 = (double)(1 - cos1), q2 = q1 * q1;
             s.att.w = (float)((double)(alpha * alpha + (1 - (alpha * alpha))) * (q2 * q2 * q1));
         }
+    } else if (PATH && p.shader_mode == 3) {
+        // path tracing: the Phong value of this hit plus albedo x the radiance of ONE cosine-weighted bounce; handled as
+        // a node with a single child whose combine is linear (combine_node, att.w < 0)
+        s.kind = SK_PATH;
+        float m_d_r, m_d_g, m_d_b;
+        diffuse_albedo(sc, mat, s.f, m_d_r, m_d_g, m_d_b);
+        s.att = make_float4(m_d_b, m_d_g, m_d_r, -1.0f);                // phong_eval returns {blue, green, red}
+        s.refl.o = s.f.hitp; s.refl.tnear = 0.01f; s.refl.time = d.w;   // stays in the medium it came through
+        s.refl.d = path_bounce_direction(s.f.n, s.f.hitp, p.seed, level);
     } else {
         s.kind = SK_PHONG;
     }
@@ -338,12 +359,7 @@ __device__ __forceinline__ float4 phong_eval(const DevScene& sc, const pgrt_rend
     const pgrt_material& mat = sc.materials[sc.geom_material[f.geom]];
     float blue = 0, green = 0, red = 0;
     float m_d_r, m_d_g, m_d_b;
-    if (mat.diffuse_tex < 0 || mat.diffuse_tex >= sc.n_textures) {         // :338-341
-        m_d_r = mat.diffuse[2]; m_d_g = mat.diffuse[1]; m_d_b = mat.diffuse[0];
-    } else {                                                                // :343-348
-        const Col3 texel = tex_get_texel(sc.textures[mat.diffuse_tex], f.tu, 1.0f - f.tv);
-        m_d_r = texel.r; m_d_g = texel.g; m_d_b = texel.b;
-    }
+    diffuse_albedo(sc, mat, f, m_d_r, m_d_g, m_d_b);
     for (int li = 0; li < sc.n_lights; ++li) {                              // :351
         const pgrt_light& light = sc.lights[li];
         const V3 lp = v3(light.position[0], light.position[1], light.position[2]);
@@ -399,7 +415,10 @@ __device__ __forceinline__ float4 phong_eval(const DevScene& sc, const pgrt_rend
 }
 
 // ---- K10 (per node): value of a dielectric node from its children (raytracer.cpp:318-321)
-__device__ __forceinline__ float4 combine_node(float4 att, float4 a, bool has_b, float4 b) {
+//      `own`: what the node's colour slot held before (SK_PATH keeps its Phong value there; unused otherwise)
+template <bool PATH>
+__device__ __forceinline__ float4 combine_node(float4 att, float4 a, bool has_b, float4 b, float4 own) {
+    if (PATH && att.w < 0.0f) return make_float4(own.x + att.x * a.x, own.y + att.y * a.y, own.z + att.z * a.z, 1.0f);   // SK_PATH
     if (has_b) {
         Col4 c0, c1; c0.r = a.x; c0.g = a.y; c0.b = a.z; c0.a = a.w; c1.r = b.x; c1.g = b.y; c1.b = b.z; c1.a = b.w;
         const Col4 c = mix_srgb(c0, c1, att.w);
@@ -410,6 +429,7 @@ __device__ __forceinline__ float4 combine_node(float4 att, float4 a, bool has_b,
 
 // ---- K8 (kernel): one level of the wavefront.  With `dyn` set (level 0 of the dynamic scheduler) the children go
 //      to the ray pool (Ln aliases its ray arrays) together with their parent link, and are published at once.
+template <bool PATH>
 __global__ void __launch_bounds__(256) k_shade(DevScene sc, pgrt_render_params p, Gen0 g0, int level, LevelBufs L, LevelBufs Ln, RayPool P, int dyn, Counters* cnt) {
     const uint32_t n = min(cnt->n_rays[level], L.cap);
     const int lane = threadIdx.x & 31;
@@ -422,8 +442,8 @@ __global__ void __launch_bounds__(256) k_shade(DevScene sc, pgrt_render_params p
         if (i < n) {
             float4 o, d;
             load_ray_shade(L, g0, p, i, o, d);
-            shade_classify(sc, p, level, o, d, L.hit[i], s);
-            is_phong = s.kind == SK_PHONG; is_diel = s.kind == SK_DIEL;
+            shade_classify<PATH>(sc, p, level, o, d, L.hit[i], s);
+            is_phong = s.kind == SK_PHONG || (PATH && s.kind == SK_PATH); is_diel = s.kind == SK_DIEL || (PATH && s.kind == SK_PATH);
             if (s.kind == SK_FINAL) L.color[i] = s.color;
         }
         const bool has_refr = is_diel && s.has_refr;
@@ -458,7 +478,7 @@ __global__ void __launch_bounds__(256) k_shade(DevScene sc, pgrt_render_params p
                 if (dyn) {            // reserved slots inside the pool are claimed by k_secondary: mark them dead
                     if (rl < Ln.cap) Ln.ray_d[rl] = make_float4(0.f, 0.f, 0.f, -1.0f);
                     if (has_refr && rr < Ln.cap) Ln.ray_d[rr] = make_float4(0.f, 0.f, 0.f, -1.0f);
-                    L.color[i] = make_float4(0.f, 0.f, 0.f, 1.f);
+                    L.color[i] = make_float4(0.f, 0.f, 0.f, 1.f);     // (SK_PATH: k_phong overwrites it; the frame is redone anyway)
                 }
             }
             L.dn_att[i] = s.att;
@@ -490,6 +510,7 @@ __global__ void __launch_bounds__(128) k_phong(DevScene sc, pgrt_render_params p
 }
 
 // ---- K10 (kernel): post-order combine of one level's dielectric nodes (level-synchronous scheduler)
+template <bool PATH>
 __global__ void __launch_bounds__(256) k_combine(int level, LevelBufs L, LevelBufs Ln, const Counters* __restrict__ cnt) {
     const uint32_t n = cnt->n_diel[level];
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -499,7 +520,9 @@ __global__ void __launch_bounds__(256) k_combine(int level, LevelBufs L, LevelBu
         float4 out = make_float4(0.f, 0.f, 0.f, 1.f);
         if (ch.x != PGRT_INVALID_ID) {
             const bool has_b = ch.y != PGRT_INVALID_ID;
-            out = combine_node(att, Ln.color[ch.x], has_b, has_b ? Ln.color[ch.y] : make_float4(0.f, 0.f, 0.f, 0.f));
+            out = combine_node<PATH>(att, Ln.color[ch.x], has_b, has_b ? Ln.color[ch.y] : make_float4(0.f, 0.f, 0.f, 0.f), L.color[i]);
+        } else if (PATH && att.w < 0.0f) {
+            out = L.color[i];             // SK_PATH whose bounce did not fit the queue (overflow: the frame is redone)
         }
         L.color[i] = out;
     }
@@ -516,7 +539,7 @@ __global__ void __launch_bounds__(256) k_combine(int level, LevelBufs L, LevelBu
 #define PGRT_SEC_MIN_BLOCKS 4     // register cap of k_secondary = 65536 / (128 * this)
 #endif
 
-template <bool COUNT>
+template <bool COUNT, bool PATH>
 __global__ void __launch_bounds__(128, PGRT_SEC_MIN_BLOCKS) k_secondary(DevScene sc, pgrt_render_params p, LevelBufs L0, RayPool P, Counters* cnt) {
     extern __shared__ uint32_t pgrt_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -576,13 +599,14 @@ __global__ void __launch_bounds__(128, PGRT_SEC_MIN_BLOCKS) k_secondary(DevScene
                 atomicAdd(&cnt->lv_nodes[level], (unsigned long long)tc.nodes);
                 atomicAdd(&cnt->lv_tris[level], (unsigned long long)tc.tris); atomicMax(&cnt->lv_max_nodes[level], tc.nodes);
             }
-            shade_classify(sc, p, level, o, d, make_float4(hr.t, hr.u, hr.v, __uint_as_float(hr.tri)), s);
+            shade_classify<PATH>(sc, p, level, o, d, make_float4(hr.t, hr.u, hr.v, __uint_as_float(hr.tri)), s);
             if (s.kind == SK_FINAL) { col = s.color; final_ = true; }
-            else if (s.kind == SK_PHONG) {
+            else if (s.kind == SK_PHONG || (PATH && s.kind == SK_PATH)) {
                 const unsigned long long sh0 = my_shadow;
                 TravAcc a1; a1.nodes = 0; a1.tris = 0; a1.mx = 0;
                 col = phong_eval<COUNT>(sc, p, o, d, s.f, my_shadow, a1);
-                final_ = true;
+                final_ = !PATH || s.kind == SK_PHONG;
+                if (PATH && !final_) __stcg(&P.color[i], col);          // SK_PATH: the node's own value waits in its colour slot for the bounce
                 if (my_shadow != sh0) atomicAdd(&cnt->lv_shadow[level], my_shadow - sh0);
                 if (COUNT) {
                     atomicAdd(&cnt->lv_sh_nodes[level], a1.nodes); atomicAdd(&cnt->lv_sh_tris[level], a1.tris);
@@ -592,7 +616,7 @@ __global__ void __launch_bounds__(128, PGRT_SEC_MIN_BLOCKS) k_secondary(DevScene
         }
 
         // ---- dielectric hits: two pool records for the children (all 32 lanes take part in the aggregated atomics)
-        const bool is_diel = live && s.kind == SK_DIEL;
+        const bool is_diel = live && (s.kind == SK_DIEL || (PATH && s.kind == SK_PATH));
         bool has_refr = is_diel && s.has_refr;
         const uint32_t rl = warp_append(&cnt->q_tail, is_diel, lane);
         const uint32_t rr = warp_append(&cnt->q_tail, has_refr, lane);
@@ -655,7 +679,8 @@ __global__ void __launch_bounds__(128, PGRT_SEC_MIN_BLOCKS) k_secondary(DevScene
                 const uint2 ch = par_l0 ? __ldcg(&L0.dn_child[par]) : __ldcg(&P.child[par]);
                 const float4 att = par_l0 ? __ldcg(&L0.dn_att[par]) : __ldcg(&P.att[par]);
                 const bool has_b = ch.y != PGRT_INVALID_ID;
-                c = combine_node(att, __ldcg(&P.color[ch.x]), has_b, has_b ? __ldcg(&P.color[ch.y]) : make_float4(0.f, 0.f, 0.f, 0.f));
+                const float4 own = PATH && att.w < 0.0f ? (par_l0 ? __ldcg(&L0.color[par]) : __ldcg(&P.color[par])) : make_float4(0.f, 0.f, 0.f, 0.f);
+                c = combine_node<PATH>(att, __ldcg(&P.color[ch.x]), has_b, has_b ? __ldcg(&P.color[ch.y]) : make_float4(0.f, 0.f, 0.f, 0.f), own);
                 if (par_l0) { L0.color[par] = c; break; }
                 node = par; nlk = __ldcg(&P.link[par]);
             }

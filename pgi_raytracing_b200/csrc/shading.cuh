@@ -128,6 +128,26 @@ __device__ __forceinline__ float rng_u01(uint32_t seed, uint32_t pixel, uint32_t
 }
 __device__ __forceinline__ float rng_uniform(float a, float b, float u) { return (b - a) * u + a; }
 
+// ---- diffuse bounce of the path-tracing mode (shader_mode 3; README.md:21 "To do: path tracing", no reference code).
+// Cosine-weighted direction = normalize(n + q), q uniform on the unit sphere, found by rejection from the cube: only
+// +, *, /, sqrt, so the oracle reproduces it bit for bit.  The random numbers are keyed by the BITS of the hit point, the
+// level and the frame seed: a ray carries no sample id below level 0, and the hit point is deterministic.
+__device__ __forceinline__ V3 path_bounce_direction(V3 n, V3 hitp, uint32_t seed, int level) {
+    uint32_t k = mix32(seed ^ (0x9E3779B9u * (uint32_t)(level + 1)));
+    k = mix32(k ^ __float_as_uint(hitp.x)); k = mix32(k ^ __float_as_uint(hitp.y)); k = mix32(k ^ __float_as_uint(hitp.z));
+    V3 q = n;
+    for (uint32_t t = 0; t < 16u; ++t) {
+        const float x = 2.0f * ((float)(mix32(k + 0x85EBCA6Bu * (3u * t + 1u)) >> 8) * (1.0f / 16777216.0f)) - 1.0f;
+        const float y = 2.0f * ((float)(mix32(k + 0x85EBCA6Bu * (3u * t + 2u)) >> 8) * (1.0f / 16777216.0f)) - 1.0f;
+        const float z = 2.0f * ((float)(mix32(k + 0x85EBCA6Bu * (3u * t + 3u)) >> 8) * (1.0f / 16777216.0f)) - 1.0f;
+        const V3 c = v3(x, y, z);
+        const float l2 = dot3(c, c);
+        if (l2 <= 1.0f && l2 > 1e-6f) { q = normalize3(c); break; }
+    }
+    const V3 d = v3(n.x + q.x, n.y + q.y, n.z + q.z);
+    return dot3(d, d) > 1e-8f ? normalize3(d) : n;
+}
+
 // ---- PinHoleCamera::generate_ray, both overloads (PinHoleCamera.cpp:31-63, :65-105)
 __device__ __forceinline__ RayRec camera_ray_pinhole(const DevCamera& c, const float x_i, const float y_i) {
     V3 d = normalize3(v3(x_i - (float)(c.width / 2), (float)(c.height / 2) - y_i, -c.f_y));

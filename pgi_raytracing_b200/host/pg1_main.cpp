@@ -3,7 +3,8 @@
 // Producer loop become `--frames N` iterations and an image file.
 //
 //   pg1_b200 [obj] [background] [--width W --height H] [--frames N] [--spp-width S] [--aperture A] [--focal F] [--depth D]
-//            [--gamma G] [--seed K] [--no-jitter] [--device N] [--accumulate N] [--out frame.ppm|.png|.pfm] [--pfm frame.pfm]
+//            [--gamma G] [--seed K] [--no-jitter] [--device N] [--accumulate N] [--path-tracing] [--hard-shadows]
+//            [--out frame.ppm|.png|.pfm] [--pfm frame.pfm]
 // Defaults = the reference's hard-coded values: ../../../data/6887_allied_avenger.obj, ../../../data/spherical_map_lakeside.jpg,
 // 640x480, fov_y 42.185 deg, eye (-140,-175,80) -> (0,0,40), 3x3 jittered samples, thin lens f=200 a=5, depth 7, gamma 0.5.
 #include <chrono>
@@ -19,7 +20,7 @@ struct Options {
     std::string obj = "../../../data/6887_allied_avenger.obj", bg = "../../../data/spherical_map_lakeside.jpg";
     int width = 640, height = 480, frames = 3, spp = 3, depth = 7, device = 0, accumulate = 0;
     float aperture = 5.0f, focal = 200.0f, gamma = 0.5f;
-    unsigned seed = 1; bool jitter = true;
+    unsigned seed = 1; bool jitter = true, path_tracing = false, hard_shadows = false;
     std::string out = "frame.ppm", pfm;
 } g_opt;
 }  // namespace
@@ -29,6 +30,7 @@ int raytrace_loop(const std::string object_file_name, const std::string backgrou
     Raytracer raytracer(g_opt.width, g_opt.height, deg2rad(42.185f), Vector3(-140, -175, 80), Vector3(0, 0, 40), cfg.c_str());
     raytracer.sampling_width = g_opt.spp; raytracer.aperture = g_opt.aperture; raytracer.focal_distance = g_opt.focal;
     raytracer.max_depth = g_opt.depth; raytracer.gamma_level = g_opt.gamma; raytracer.seed = g_opt.seed; raytracer.jitter = g_opt.jitter;
+    raytracer.path_tracing = g_opt.path_tracing; raytracer.hard_shadows = g_opt.hard_shadows;
     raytracer.LoadScene(object_file_name, background_file_name);
     const pgrt_build_stats& bs = raytracer.build_stats();
     printf("Surfaces = %zu\nMaterials = %zu\n", raytracer.no_surfaces(), raytracer.no_materials());   // pg1/raytracer.cpp:456-457
@@ -74,6 +76,8 @@ int main(int argc, char** argv) {
         else if (a == "--no-jitter") g_opt.jitter = false;
         else if (a == "--device") g_opt.device = atoi(val());
         else if (a == "--accumulate") g_opt.accumulate = atoi(val());
+        else if (a == "--path-tracing") g_opt.path_tracing = true;
+        else if (a == "--hard-shadows") g_opt.hard_shadows = true;
         else if (a == "--out") g_opt.out = val();
         else if (a == "--pfm") g_opt.pfm = val();
         else if (positional == 0) { g_opt.obj = a; positional++; }

@@ -101,6 +101,8 @@ pgrt_render_params Raytracer::params() const {
     pgrt_default_params(&p);
     p.sampling_width = sampling_width; p.jitter = jitter ? 1 : 0; p.focal_distance = focal_distance; p.aperture = aperture;
     p.max_depth = max_depth; p.gamma_level = gamma_level; p.seed = seed;
+    p.shadow_mode = hard_shadows ? 1 : 0;
+    if (path_tracing) p.shader_mode = 3;
     return p;
 }
 

@@ -31,6 +31,9 @@ public:
     int max_depth = 7;                   // :282
     unsigned int seed = 1;               // replaces the clock seed of :407
     bool jitter = true;
+    // the README's to-do list (README.md:20-21), off by default: hard shadows (hit point -> light) and path tracing
+    bool hard_shadows = false;
+    bool path_tracing = false;           // shader_mode 3 of pgrt.h; converge with RenderAccumulated
 
     int InitDeviceAndScene(const char* config);      // config: "device=N" selects the CUDA ordinal; Embree keys are ignored
     int ReleaseDeviceAndScene();
