@@ -277,6 +277,14 @@ __device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool pred, in
 }
 
 // ---- K8 (per ray): classification of one (ray, hit) pair = the head of trace() (raytracer.cpp:247-323, :390-393)
+#ifndef PGRT_SHADE_MIN_BLOCKS
+#define PGRT_SHADE_MIN_BLOCKS 6   // register cap of k_shade = 65536 / (256 * this) = 40.  With many frames in flight what a kernel
+                                  // leaves free matters more than its own speed: fewer registers = more CTAs of OTHER frames' kernels
+                                  // resident beside it (profiles/r1_sweep_register_caps_pipelined.txt: C2 6.69 -> 7.22 Grays/s)
+#endif
+#ifndef PGRT_PHONG_MIN_BLOCKS
+#define PGRT_PHONG_MIN_BLOCKS 8   // register cap of k_phong = 65536 / (128 * this) = 64
+#endif
 enum ShadeKind { SK_FINAL = 0, SK_PHONG = 1, SK_DIEL = 2, SK_PATH = 3 };   // SK_PATH: Phong value + one diffuse bounce (shader_mode 3)
 struct ShadeOut {
     int kind;
@@ -430,7 +438,7 @@ __device__ __forceinline__ float4 combine_node(float4 att, float4 a, bool has_b,
 // ---- K8 (kernel): one level of the wavefront.  With `dyn` set (level 0 of the dynamic scheduler) the children go
 //      to the ray pool (Ln aliases its ray arrays) together with their parent link, and are published at once.
 template <bool PATH>
-__global__ void __launch_bounds__(256) k_shade(DevScene sc, pgrt_render_params p, Gen0 g0, int level, LevelBufs L, LevelBufs Ln, RayPool P, int dyn, Counters* cnt) {
+__global__ void __launch_bounds__(256, PGRT_SHADE_MIN_BLOCKS) k_shade(DevScene sc, pgrt_render_params p, Gen0 g0, int level, LevelBufs L, LevelBufs Ln, RayPool P, int dyn, Counters* cnt) {
     const uint32_t n = min(cnt->n_rays[level], L.cap);
     const int lane = threadIdx.x & 31;
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -491,7 +499,7 @@ __global__ void __launch_bounds__(256) k_shade(DevScene sc, pgrt_render_params p
 
 // ---- K8b/K9 (kernel)
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_phong(DevScene sc, pgrt_render_params p, Gen0 g0, int level, LevelBufs L, Counters* cnt) {
+__global__ void __launch_bounds__(128, PGRT_PHONG_MIN_BLOCKS) k_phong(DevScene sc, pgrt_render_params p, Gen0 g0, int level, LevelBufs L, Counters* cnt) {
     const uint32_t n = cnt->n_phong[level];
     if (level == 0 && blockIdx.x == 0 && threadIdx.x == 0) cnt->q_l1 = cnt->q_tail;   // dynamic scheduler: the level-1 rays are complete
     unsigned long long my_shadow = 0;
@@ -536,7 +544,7 @@ __global__ void __launch_bounds__(256) k_combine(int level, LevelBufs L, LevelBu
 // No warp ever waits for another one: there is no queue to poll and nothing to time out.
 #define PGRT_WSTACK 64
 #ifndef PGRT_SEC_MIN_BLOCKS
-#define PGRT_SEC_MIN_BLOCKS 4     // register cap of k_secondary = 65536 / (128 * this)
+#define PGRT_SEC_MIN_BLOCKS 6     // register cap of k_secondary = 65536 / (128 * this) = 80 (was 128: no gain alone, +2.6 % pipelined)
 #endif
 
 template <bool COUNT, bool PATH>
