@@ -7,13 +7,17 @@
 A "step" is one frame = one pass of the hot path (pg1/simpleguidx11.cpp:95-118) over every pixel of the frame.
 Workload (N=1 default) = BASELINE.json configs[1]: avenger (stand-in mesh, the reference's OBJ is absent) 1920x1080,
 Whitted, depth cut-off 10, 1 spp un-jittered.  For N>1 the same frame is cut into 32x8 tiles dealt round-robin to
-the ranks (strong scaling: total work fixed) and gathered to rank 0 over NCCL every step.
+the ranks (strong scaling: total work fixed); every rank's resolve kernel stores its tiles straight into rank 0's frame over
+NVLink (fallback: NCCL gather), a 4-byte NCCL all-reduce per step is the completion barrier.
 
 value  : rays/s of K whole frames, scene resident in HBM, device time between two CUDA events around all K steps; the
-         Producer loop renders frames forever (pg1/simpleguidx11.cpp:95-125), so up to --inflight frames (default 4) are
-         in flight per GPU (own stream each, pgrt_render*_begin / pgrt_render_end); L2 is flushed before every step.
+         Producer loop renders frames forever (pg1/simpleguidx11.cpp:95-125), so --inflight frames (default 8; 16 for
+         frames or shards below 1 M primary samples) are in flight per GPU (own stream each, pgrt_render*_begin /
+         pgrt_render_end); L2 is flushed before every step on that step's stream (a fill of 1.125 x L2).
 e2e    : the same metric through the host-buffer C-ABI call every step (pgrt_set_camera + pgrt_render_begin into pinned
-         host memory + pgrt_render_end), wall clock.
+         host memory + pgrt_render_end), wall clock.  N>1: the frames live in host memory shared by all ranks and every
+         rank's tiles cross its own PCIe link (dist.ShardedRenderer mode "host").
+clocks : SM clock and throttle reasons sampled through NVML every 2 ms inside the timed region.
 --impl reference : the CPU restatement of the reference's loop (oracle/; the reference itself cannot be built here)
                    on all host cores, same config, same metric.
 """
