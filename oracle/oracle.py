@@ -52,6 +52,8 @@ def _lib():
     build()
     lib = C.CDLL(_LIB_PATH)
     lib.orc_create.restype = C.c_void_p
+    lib.orc_path_bounce.restype = None
+    lib.orc_path_bounce.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.c_void_p]
     lib.orc_rng_u01.restype = C.c_float
     lib.orc_rng_u01.argtypes = [C.c_uint32] * 4
     lib.orc_num_triangles.restype = C.c_uint32
@@ -199,6 +201,13 @@ class Oracle:
         rc = self.lib.orc_interpolate(self.h, _p(geom), _p(prim), _p(u), _p(v), C.c_uint64(geom.shape[0]), int(slot), _p(out))
         if rc:
             raise RuntimeError("orc_interpolate: id out of range")
+        return out
+
+    def path_bounce(self, normal, hits: np.ndarray, seed: int, level: int) -> np.ndarray:
+        """Directions of the diffuse bounce of shader_mode 3 at the given hit points (one normal for all)."""
+        n = np.ascontiguousarray(np.asarray(normal, np.float32)); h = np.ascontiguousarray(np.asarray(hits, np.float32).reshape(-1, 3))
+        out = np.zeros_like(h)
+        self.lib.orc_path_bounce(_p(n), _p(h), C.c_uint64(h.shape[0]), int(seed), int(level), _p(out))
         return out
 
     def rng_u01(self, seed, pixel, sample, dim) -> float:

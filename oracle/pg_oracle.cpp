@@ -833,6 +833,13 @@ int orc_interpolate(void* h, const uint32_t* geom, const uint32_t* prim, const f
     return 0;
 }
 float orc_rng_u01(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t dim) { return rng_u01(seed, pixel, sample, dim); }
+// n directions of the diffuse bounce (shader_mode 3) for normal nrm at hit points hit[3*i..]: out[3*i..]
+void orc_path_bounce(const float* nrm, const float* hit, uint64_t n, uint32_t seed, int32_t level, float* out) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const V3 d = Tracer::path_bounce_direction(v3(nrm[0], nrm[1], nrm[2]), v3(hit[3 * i], hit[3 * i + 1], hit[3 * i + 2]), seed, level);
+        out[3 * i] = d.x; out[3 * i + 1] = d.y; out[3 * i + 2] = d.z;
+    }
+}
 int orc_max_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -279,3 +279,33 @@ def test_path_tracing_mode_of_the_oracle_is_deterministic_and_adds_light(oracle_
     assert np.array_equal(a, a2, equal_nan=True) and not np.array_equal(a, c, equal_nan=True)
     assert sa["primary"] == sb["primary"] and sa["refraction"] > 0 and sa["reflection"] > sb["reflection"]
     assert np.nanmean(a[..., :3]) > np.nanmean(b[..., :3])
+
+
+def test_path_bounce_is_cosine_weighted(tri_oracle):
+    """The bounce of shader_mode 3: unit vectors in the hemisphere of n, density proportional to cos(theta) -- E[cos] = 2/3,
+    E[cos^2] = 1/2, azimuth uniform -- and a function of (hit point bits, level, seed) only."""
+    rng = np.random.default_rng(5)
+    hits = rng.uniform(-100, 100, (200_000, 3)).astype(np.float32)
+    n = np.array([0.0, 0.6, 0.8], np.float32)
+    d = tri_oracle.path_bounce(n, hits, seed=7, level=2)
+    assert np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=2e-6)
+    c = d @ n
+    assert c.min() >= -1e-6
+    assert abs(c.mean() - 2.0 / 3.0) < 3e-3 and abs((c * c).mean() - 0.5) < 3e-3
+    t = np.cross(n, [1.0, 0.0, 0.0]); t /= np.linalg.norm(t); b = np.cross(n, t)
+    phi = np.arctan2(d @ b, d @ t)
+    hist, _ = np.histogram(phi, bins=16, range=(-np.pi, np.pi))
+    assert np.abs(hist / hist.mean() - 1.0).max() < 0.04
+    assert np.array_equal(d, tri_oracle.path_bounce(n, hits, seed=7, level=2))
+    assert not np.array_equal(d, tri_oracle.path_bounce(n, hits, seed=8, level=2))
+    assert not np.array_equal(d, tri_oracle.path_bounce(n, hits, seed=7, level=3))
+
+
+def test_bench_clock_sampler_degrades_without_a_gpu():
+    """bench.py's sampler must never take the run down: without NVML / nvidia-smi it reports that and nothing else."""
+    import importlib, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    bench = importlib.import_module("bench")
+    s = bench.ClockSampler(0); s.start()
+    out = s.stop()
+    assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"}
