@@ -192,9 +192,18 @@ def run_reference(args):
     # bounded sample: a centred horizontal band of the frame sized to keep each step around a second
     S = p["sampling_width"] ** 2
     rows = H if W * H * S <= 4_000_000 else max(8, int(4_000_000 / (W * S)) // 8 * 8)
+    pr = make_params(**p)
+    # ... and the whole run around a minute and a half whatever the host: one untimed calibration step, then the band
+    # shrinks if (warmup + steps) of it would take longer
+    y0 = (H - rows) // 2
+    t0 = time.perf_counter()
+    orc.render(pr, want_ids=False, threads=0, region=(0, y0, W, y0 + rows))
+    t_step = time.perf_counter() - t0
+    budget = 90.0
+    if t_step * (args.steps + args.warmup) > budget:
+        rows = max(8, int(rows * budget / (t_step * (args.steps + args.warmup))) // 8 * 8)
     y0 = (H - rows) // 2
     region = (0, y0, W, y0 + rows)
-    pr = make_params(**p)
     for _ in range(args.warmup):
         orc.render(pr, want_ids=False, threads=0, region=region)
     t0 = time.perf_counter(); rays = 0
