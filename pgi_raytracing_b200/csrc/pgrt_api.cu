@@ -643,10 +643,13 @@ static int validate_frame(pgrt_context* ctx, const pgrt_render_params* p) {
 static int prepare_frame(pgrt_context* ctx, FrameSlot& S) {
     const int SPP = S.params.sampling_width * S.params.sampling_width;
     const size_t cap0 = (size_t)S.batch_slots * SPP;
-    const size_t capn = std::max<size_t>(ctx->min_level_cap, (size_t)(ctx->level_cap_factor * (double)cap0));
+    // deeper levels: Whitted spawns rays at dielectric hits only (a fraction of the samples); the path-tracing mode spawns
+    // one at every hit of every level, so its queues are sized for a full level each
+    const bool path = S.params.shader_mode == 3;
+    const size_t capn = std::max<size_t>(ctx->min_level_cap, (size_t)((path ? std::max(1.0, ctx->level_cap_factor) : ctx->level_cap_factor) * (double)cap0));
     int rc = ensure_levels(ctx, S, S.dyn ? 1 : S.n_levels, cap0, capn);
     if (rc) return rc;
-    if (S.dyn) { rc = ensure_pool(ctx, S, capn * (size_t)std::min(S.n_levels - 1, 4)); if (rc) return rc; }   // one pool replaces the per-level queues
+    if (S.dyn) { rc = ensure_pool(ctx, S, capn * (size_t)std::min(S.n_levels - 1, path ? 8 : 4)); if (rc) return rc; }   // one pool replaces the per-level queues
     if (S.host_dst) CUDA_TRY(S.d_frame.ensure((size_t)ctx->cam.width * ctx->cam.height));
     return PGRT_OK;
 }

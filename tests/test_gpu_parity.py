@@ -641,6 +641,7 @@ def test_path_tracing_mode_matches_the_oracle(P, oracle_mod, cornell, scheduler)
     ok, psnr = image_bars(P, ref, img)
     assert ok >= 0.995 and psnr >= 45.0, (ok, psnr)
     assert st["total"] == rst["total"] and st["reflection"] == rst["reflection"] and st["shadow"] == rst["shadow"]
+    assert st["overflow_retries"] == 0            # queues are sized for one bounce per hit and level
     whitted, wst = rt.render(dict(kw, shader_mode=0, scheduler=scheduler))
     assert st["reflection"] > 2 * wst["reflection"]                       # every diffuse hit bounces
     assert P.to_srgb8(img).astype(int).sum() > P.to_srgb8(whitted).astype(int).sum()   # the environment lights the scene
