@@ -217,6 +217,9 @@ int pgrt_untile_on_stream(pgrt_context* ctx, const void* gathered_device, int32_
 /* ---- rtcIntersect1 over a batch (raytracer.cpp:130-148; semantics emb/doc/README.md:6331-6415):
  *      closest hit in (tnear, tfar]; on hit writes tfar, u, v, Ng, primID, geomID; a miss leaves the record
  *      untouched.  Host array of n RTCRayHit-compatible records. */
+/* Ray directions: a component whose magnitude is below 2^-80 is treated as 2^-80 of the same sign when the reciprocal
+ * is formed (Embree clamps in the same way, at a larger threshold); a direction ALL of whose components are that small is outside
+ * the supported domain. */
 int pgrt_intersect(pgrt_context* ctx, pgrt_rayhit* rayhits_host, uint64_t n);
 /* rtcInterpolate0 (raytracer.cpp:252, :344): slot 0 -> 3 floats (normal), slot 1 -> 2 floats (uv), per query */
 int pgrt_interpolate(pgrt_context* ctx, const uint32_t* geom_id, const uint32_t* prim_id, const float* u, const float* v,

@@ -43,7 +43,7 @@ __device__ __forceinline__ V3 tri_ng(const float* __restrict__ pos, uint32_t id)
 struct TravCount { uint32_t nodes, tris; };   // instrumented renders only (profile bit 1)
 
 PG_HD uint32_t slab4(uint32_t meta4, uint32_t nx4, uint32_t ny4, uint32_t nz4, uint32_t fx4, uint32_t fy4, uint32_t fz4,
-                     float sx, float sy, float sz, float ax, float ay, float az, float tnear, float far_pad, uint32_t octinv4) {
+                     float sx, float sy, float sz, float ax, float ay, float az, float tnear, float far_pad, float pad_abs, uint32_t octinv4) {
     // four children at once: meta bytes -> (bit index, child bits); inner children are re-indexed by the ray octant
     const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
     const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xFFu;
@@ -58,7 +58,7 @@ PG_HD uint32_t slab4(uint32_t meta4, uint32_t nx4, uint32_t ny4, uint32_t nz4, u
         const float tz0 = pg_fma((float)((nz4 >> sh) & 0xFFu), sz, az), tz1 = pg_fma((float)((fz4 >> sh) & 0xFFu), sz, az);
         const float tmin = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, tnear));
         const float tmax = fminf(fminf(tx1, ty1), fminf(tz1, far_pad));
-        if (tmin <= tmax * 1.0000005f) hitmask |= ((child_bits4 >> sh) & 0xFFu) << ((bit_index4 >> sh) & 0xFFu);
+        if (tmin <= pg_fma(tmax, 1.0000005f, pad_abs)) hitmask |= ((child_bits4 >> sh) & 0xFFu) << ((bit_index4 >> sh) & 0xFFu);
     }
     return hitmask;
 }
@@ -96,7 +96,7 @@ struct RayCtxF {                       // PGRT_LAYOUT_F32
 struct RayCtxQ {                       // PGRT_LAYOUT_Q8
     V3 O, D; float tnear, tfar;
     bool ww;
-    float idx, idy, idz;
+    float idx, idy, idz, pad_abs;
     bool negx, negy, negz;
     uint32_t octinv, octinv4;
 };
@@ -125,6 +125,9 @@ PG_HD void ray_ctx_init(RayCtxQ& r, V3 O, V3 D, float tnear, float tfar, bool ww
     r.idx = pg_rcp(fabsf(D.x) > ooeps ? D.x : copysignf(ooeps, D.x));
     r.idy = pg_rcp(fabsf(D.y) > ooeps ? D.y : copysignf(ooeps, D.y));
     r.idz = pg_rcp(fabsf(D.z) > ooeps ? D.z : copysignf(ooeps, D.z));
+    // (origin - O) * idir carries the rounding of O, 2^-24 |O|, times |idir|: an ABSOLUTE error on t that a relative pad does
+    // not cover when the ray is nearly parallel to an axis (found by fuzzing axis-aligned sheets hit on their border)
+    r.pad_abs = 2.3841858e-7f * fmaxf(fmaxf(fabsf(O.x * r.idx), fabsf(O.y * r.idy)), fabsf(O.z * r.idz));   // 2^-22 * max |O * idir|
     r.negx = r.idx < 0.0f; r.negy = r.idy < 0.0f; r.negz = r.idz < 0.0f;
     r.octinv = (r.negx ? 0u : 4u) | (r.negy ? 0u : 2u) | (r.negz ? 0u : 1u);
     r.octinv4 = r.octinv * 0x01010101u;
@@ -155,14 +158,14 @@ PG_HD uint32_t node_visit(const float4* __restrict__ nodes, uint32_t ni, const R
     const uint32_t eb = pg_f2u(n0.w);
     const float sx = pg_u2f((eb & 0xFFu) << 23) * r.idx, sy = pg_u2f(((eb >> 8) & 0xFFu) << 23) * r.idy, sz = pg_u2f(((eb >> 16) & 0xFFu) << 23) * r.idz;
     const float ax = (n0.x - r.O.x) * r.idx, ay = (n0.y - r.O.y) * r.idy, az = (n0.z - r.O.z) * r.idz;
-    const float far_pad = best_t * 1.0000005f;
+    const float far_pad = pg_fma(best_t, 1.0000005f, r.pad_abs);
     const uint32_t lox0 = pg_f2u(n2.x), lox1 = pg_f2u(n2.y), loy0 = pg_f2u(n2.z), loy1 = pg_f2u(n2.w);
     const uint32_t loz0 = pg_f2u(n3.x), loz1 = pg_f2u(n3.y), hix0 = pg_f2u(n3.z), hix1 = pg_f2u(n3.w);
     const uint32_t hiy0 = pg_f2u(n4.x), hiy1 = pg_f2u(n4.y), hiz0 = pg_f2u(n4.z), hiz1 = pg_f2u(n4.w);
     uint32_t hitmask = slab4(pg_f2u(n1.z), r.negx ? hix0 : lox0, r.negy ? hiy0 : loy0, r.negz ? hiz0 : loz0, r.negx ? lox0 : hix0, r.negy ? loy0 : hiy0,
-                             r.negz ? loz0 : hiz0, sx, sy, sz, ax, ay, az, r.tnear, far_pad, r.octinv4);
+                             r.negz ? loz0 : hiz0, sx, sy, sz, ax, ay, az, r.tnear, far_pad, r.pad_abs, r.octinv4);
     hitmask |= slab4(pg_f2u(n1.w), r.negx ? hix1 : lox1, r.negy ? hiy1 : loy1, r.negz ? hiz1 : loz1, r.negx ? lox1 : hix1, r.negy ? loy1 : hiy1,
-                     r.negz ? loz1 : hiz1, sx, sy, sz, ax, ay, az, r.tnear, far_pad, r.octinv4);
+                     r.negz ? loz1 : hiz1, sx, sy, sz, ax, ay, az, r.tnear, far_pad, r.pad_abs, r.octinv4);
     child_base = pg_f2u(n1.x); tri_base = pg_f2u(n1.y); imask = eb >> 24;
     return hitmask;
 }

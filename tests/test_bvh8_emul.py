@@ -149,3 +149,69 @@ def test_ploc_tree_is_better_than_median_split(emul):
         assert emul.emul_sah(h0) < emul.emul_sah(h1)
     finally:
         emul.emul_free(h0); emul.emul_free(h1)
+
+
+# ------------------------------------------------------------------------------------------------ fuzzing
+FMAX = np.finfo(np.float32).max
+def _fuzz_scene(rng, kind, n):
+    if kind == 0:   # uniform soup
+        c = rng.uniform(-100, 100, (n, 1, 3)); p = c + rng.uniform(-3, 3, (n, 3, 3))
+    elif kind == 1: # axis-aligned grid sheets (flat boxes), exact integer coordinates
+        g = int(np.sqrt(n / 2)) + 1
+        xs, ys = np.meshgrid(np.arange(g), np.arange(g))
+        a = np.stack([xs, ys, np.zeros_like(xs)], -1).reshape(-1, 3).astype(float)
+        t1 = np.stack([a, a + [1, 0, 0], a + [1, 1, 0]], 1); t2 = np.stack([a, a + [1, 1, 0], a + [0, 1, 0]], 1)
+        p = np.concatenate([t1, t2])[:n]
+        if rng.random() < 0.5: p = p[..., [2, 0, 1]]
+    elif kind == 2: # huge + tiny mix, far from origin
+        c = rng.uniform(-1, 1, (n, 1, 3)) * 10.0 ** rng.uniform(-2, 4, (n, 1, 1)) + 5000.0
+        p = c + rng.normal(size=(n, 3, 3)) * 10.0 ** rng.uniform(-3, 2, (n, 1, 1))
+    elif kind == 3: # many duplicates + degenerate
+        base = rng.uniform(-10, 10, (max(n // 8, 1), 3, 3))
+        p = base[rng.integers(0, base.shape[0], n)]
+        deg = rng.random(n) < 0.1; p[deg, 2] = p[deg, 1]
+    else:           # long thin slivers along a diagonal
+        t = rng.uniform(0, 1, (n, 1, 1)); c = t * np.array([100.0, 100.0, 100.0])
+        p = c + rng.normal(size=(n, 3, 3)) * np.array([20.0, 0.01, 0.01])
+    return np.ascontiguousarray(p.reshape(n, 9).astype(np.float32))
+def _fuzz_rays(rng, pos, m):
+    P = pos.reshape(-1, 3); lo, hi = P.min(0), P.max(0); ext = np.maximum(hi - lo, 1e-3)
+    org = rng.uniform(lo - ext, hi + ext, (m, 3)); tri = pos[rng.integers(0, pos.shape[0], m)].reshape(m, 3, 3)
+    w = rng.dirichlet((1, 1, 1), m)[:, :, None]; tgt = (tri * w).sum(1)
+    edge = rng.random(m) < 0.2; tgt[edge] = tri[edge, 0] * 0.5 + tri[edge, 1] * 0.5     # aim at edges
+    vert = rng.random(m) < 0.1; tgt[vert] = tri[vert, 2]                                 # and vertices
+    d = (tgt - org) * rng.uniform(0.01, 5, (m, 1))
+    ax = rng.random(m) < 0.15; k = rng.integers(0, 3, m); d[ax, k[ax]] = 0.0            # zero components
+    ax2 = rng.random(m) < 0.05; d[ax2] = 0; d[ax2, k[ax2]] = rng.choice([-1.0, 1.0], ax2.sum())
+    inside = rng.random(m) < 0.2; org[inside] = tgt[inside]; d[inside] = rng.normal(size=(inside.sum(), 3))
+    rays = np.zeros((m, 8), np.float32); rays[:, :3] = org; rays[:, 4:7] = d
+    rays[:, 3] = rng.choice([0.0, 1e-3, 0.01], m); rays[:, 7] = FMAX
+    b = rng.random(m) < 0.2; rays[b, 7] = rng.uniform(0.1, 2.0, b.sum())
+    neg = rng.random(m) < 0.02; rays[neg, 3] = 5.0; rays[neg, 7] = 1.0                   # empty interval
+    tiny = rng.random(m) < 0.03; rays[tiny, 4:7] *= 1e-12                                # near-denormal directions
+    return rays
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_fuzzed_scenes_and_rays_match_brute_force(emul, block):
+    """Pathological geometry (axis-aligned sheets on an integer grid, 1e-2..1e4 size mixes far from the origin, duplicates,
+    slivers) x pathological rays (aimed at edges and vertices, zero components, axis-parallel, origins on the surface, empty
+    intervals, 1e-12-scaled directions): both layouts, both builders, both loop shapes against brute force, bit for bit.
+    This is how the missing absolute pad of the quantised layout was found (hits on the border of axis-aligned sheets by
+    rays nearly parallel to an axis).  Directions whose components are ALL below 2^-80 are outside the supported domain
+    (the reciprocal is clamped there, as Embree clamps at 1e-18)."""
+    for seed in range(10 * block, 10 * block + 10):
+        rng = np.random.default_rng(seed)
+        kind = seed % 5; n = int(rng.choice([1, 2, 3, 7, 33, 200, 1500]))
+        pos = _fuzz_scene(rng, kind, n); rays = _fuzz_rays(rng, pos, 400)
+        for layout in (0, 1):
+            for builder in (0, 1):
+                h = emul.emul_build(pos.ctypes.data, pos.shape[0], builder, layout)
+                try:
+                    assert emul.emul_check(h) == 0 and emul.emul_depth(h) <= 38
+                    b, _ = trace(emul, h, rays, 1)
+                    for ww in (0, 2):
+                        a, _ = trace(emul, h, rays, ww)
+                        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (seed, kind, n, layout, builder, ww)
+                finally:
+                    emul.emul_free(h)
