@@ -43,7 +43,8 @@ __device__ __forceinline__ V3 tri_ng(const float* __restrict__ pos, uint32_t id)
 struct TravCount { uint32_t nodes, tris; };   // instrumented renders only (profile bit 1)
 
 PG_HD uint32_t slab4(uint32_t meta4, uint32_t nx4, uint32_t ny4, uint32_t nz4, uint32_t fx4, uint32_t fy4, uint32_t fz4,
-                     float sx, float sy, float sz, float ax, float ay, float az, float tnear, float far_pad, float pad_abs, uint32_t octinv4) {
+                     float sx, float sy, float sz, float axn, float ayn, float azn, float axf, float ayf, float azf, float tnear, float far_pad,
+                     uint32_t octinv4) {
     // four children at once: meta bytes -> (bit index, child bits); inner children are re-indexed by the ray octant
     const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
     const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xFFu;
@@ -53,31 +54,31 @@ PG_HD uint32_t slab4(uint32_t meta4, uint32_t nx4, uint32_t ny4, uint32_t nz4, u
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int sh = 8 * j;
-        const float tx0 = pg_fma((float)((nx4 >> sh) & 0xFFu), sx, ax), tx1 = pg_fma((float)((fx4 >> sh) & 0xFFu), sx, ax);
-        const float ty0 = pg_fma((float)((ny4 >> sh) & 0xFFu), sy, ay), ty1 = pg_fma((float)((fy4 >> sh) & 0xFFu), sy, ay);
-        const float tz0 = pg_fma((float)((nz4 >> sh) & 0xFFu), sz, az), tz1 = pg_fma((float)((fz4 >> sh) & 0xFFu), sz, az);
+        const float tx0 = pg_fma((float)((nx4 >> sh) & 0xFFu), sx, axn), tx1 = pg_fma((float)((fx4 >> sh) & 0xFFu), sx, axf);
+        const float ty0 = pg_fma((float)((ny4 >> sh) & 0xFFu), sy, ayn), ty1 = pg_fma((float)((fy4 >> sh) & 0xFFu), sy, ayf);
+        const float tz0 = pg_fma((float)((nz4 >> sh) & 0xFFu), sz, azn), tz1 = pg_fma((float)((fz4 >> sh) & 0xFFu), sz, azf);
         const float tmin = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, tnear));
         const float tmax = fminf(fminf(tx1, ty1), fminf(tz1, far_pad));
-        if (tmin <= pg_fma(tmax, 1.0000005f, pad_abs)) hitmask |= ((child_bits4 >> sh) & 0xFFu) << ((bit_index4 >> sh) & 0xFFu);
+        if (tmin <= tmax * 1.0000005f) hitmask |= ((child_bits4 >> sh) & 0xFFu) << ((bit_index4 >> sh) & 0xFFu);
     }
     return hitmask;
 }
 
 // F32 layout: slab tests on float planes, four slots per call; a hit ORs the slot's pre-shifted word into the mask
 PG_HD uint32_t slab4f(float4 w, float4 nx, float4 ny, float4 nz, float4 fx, float4 fy, float4 fz, float idx, float idy, float idz,
-                      float oodx, float oody, float oodz, float tnear, float far_pad, float pad_abs) {
+                      float nxo, float nyo, float nzo, float fxo, float fyo, float fzo, float tnear, float far_pad) {
     const float nxs[4] = {nx.x, nx.y, nx.z, nx.w}, nys[4] = {ny.x, ny.y, ny.z, ny.w}, nzs[4] = {nz.x, nz.y, nz.z, nz.w};
     const float fxs[4] = {fx.x, fx.y, fx.z, fx.w}, fys[4] = {fy.x, fy.y, fy.z, fy.w}, fzs[4] = {fz.x, fz.y, fz.z, fz.w};
     const uint32_t ws[4] = {pg_f2u(w.x), pg_f2u(w.y), pg_f2u(w.z), pg_f2u(w.w)};
     uint32_t hitmask = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float tx0 = pg_fma(nxs[j], idx, -oodx), tx1 = pg_fma(fxs[j], idx, -oodx);
-        const float ty0 = pg_fma(nys[j], idy, -oody), ty1 = pg_fma(fys[j], idy, -oody);
-        const float tz0 = pg_fma(nzs[j], idz, -oodz), tz1 = pg_fma(fzs[j], idz, -oodz);
+        const float tx0 = pg_fma(nxs[j], idx, nxo), tx1 = pg_fma(fxs[j], idx, fxo);
+        const float ty0 = pg_fma(nys[j], idy, nyo), ty1 = pg_fma(fys[j], idy, fyo);
+        const float tz0 = pg_fma(nzs[j], idz, nzo), tz1 = pg_fma(fzs[j], idz, fzo);
         const float tmin = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, tnear));
         const float tmax = fminf(fminf(tx1, ty1), fminf(tz1, far_pad));
-        if (tmin <= pg_fma(tmax, 1.0000005f, pad_abs)) hitmask |= ws[j];
+        if (tmin <= tmax * 1.0000005f) hitmask |= ws[j];
     }
     return hitmask;
 }
@@ -89,17 +90,30 @@ PG_HD uint32_t slab4f(float4 w, float4 nx, float4 ny, float4 nz, float4 fx, floa
 struct RayCtxF {                       // PGRT_LAYOUT_F32
     V3 O, D; float tnear, tfar;
     bool ww;                           // loop shape, see trav_advance
-    float idx, idy, idz, oodx, oody, oodz, pad_abs;
+    float idx, idy, idz;
+    float nxo, nyo, nzo, fxo, fyo, fzo; // -O * idir per axis, lowered (near planes) / raised (far planes) by that axis' rounding pad
+    float pad_far;                      // absolute slack of the comparison with the best hit so far (see ray_far_pad)
     int onx, ony, onz, ofx, ofy, ofz;  // float4 offsets of the near / far planes inside a node, by ray sign
     uint32_t octinv, sw1, sw2, sw4;    // delta-swap masks that move internal hit bits from 24 + s to 24 + (s ^ octinv)
 };
 struct RayCtxQ {                       // PGRT_LAYOUT_Q8
     V3 O, D; float tnear, tfar;
     bool ww;
-    float idx, idy, idz, pad_abs;
+    float idx, idy, idz;
+    float pox, poy, poz;               // 2^-22 |O * idir| per axis: the rounding of O seen through that axis' reciprocal
+    float pad_far;                     // absolute slack of the comparison with the best hit so far (see ray_far_pad)
     bool negx, negy, negz;
     uint32_t octinv, octinv4;
 };
+
+// The best hit's t comes from tri_test, whose own rounding starts with O - v0: an error of 2^-24 max|O| in position, i.e. about
+// that over |D| in t.  A box that the hit lies on the border of (a triangle hit at the corner of its own box; the lower-id
+// twin of a duplicated triangle) must still pass "entry <= best t", so that comparison gets an absolute slack of
+// 2^-21 max|O_i| * min|1/D_i| besides the relative one -- small for every ray, unlike the per-axis slab pads, which grow without
+// bound for a ray parallel to an axis and would switch off the culling by distance if they were used here.
+PG_HD float ray_far_pad(V3 O, float idx, float idy, float idz) {
+    return 4.7683716e-7f * fmaxf(fmaxf(fabsf(O.x), fabsf(O.y)), fabsf(O.z)) * fminf(fminf(fabsf(idx), fabsf(idy)), fabsf(idz));
+}
 
 PG_HD void ray_ctx_init(RayCtxF& r, V3 O, V3 D, float tnear, float tfar, bool ww) {
     r.O = O; r.D = D; r.tnear = tnear; r.tfar = tfar; r.ww = ww;
@@ -107,10 +121,15 @@ PG_HD void ray_ctx_init(RayCtxF& r, V3 O, V3 D, float tnear, float tfar, bool ww
     r.idx = pg_rcp(fabsf(D.x) > ooeps ? D.x : copysignf(ooeps, D.x));
     r.idy = pg_rcp(fabsf(D.y) > ooeps ? D.y : copysignf(ooeps, D.y));
     r.idz = pg_rcp(fabsf(D.z) > ooeps ? D.z : copysignf(ooeps, D.z));
-    r.oodx = O.x * r.idx; r.oody = O.y * r.idy; r.oodz = O.z * r.idz;
     // plane * idir - O * idir cancels when the origin is far from the box compared with t: the rounding of O * idir
-    // (2^-24 of its magnitude) is an ABSOLUTE error on t, so the culling bounds carry an absolute pad as well
-    r.pad_abs = 2.3841858e-7f * fmaxf(fmaxf(fabsf(r.oodx), fabsf(r.oody)), fabsf(r.oodz));   // 2^-22 * max |O * idir|
+    // (2^-24 of its magnitude) is an ABSOLUTE error on that axis' t.  Each axis carries its own pad, folded into the
+    // constant of its FMA: a pad taken as the maximum over the axes lets a ray that is nearly parallel to one axis
+    // (huge |O * idir| there) through every box that only the OTHER axes can reject (C5: 16 -> 38 ms per frame).
+    const float oodx = O.x * r.idx, oody = O.y * r.idy, oodz = O.z * r.idz;
+    const float px = 2.3841858e-7f * fabsf(oodx), py = 2.3841858e-7f * fabsf(oody), pz = 2.3841858e-7f * fabsf(oodz);   // 2^-22 |O * idir|
+    r.nxo = -oodx - px; r.nyo = -oody - py; r.nzo = -oodz - pz;
+    r.fxo = -oodx + px; r.fyo = -oody + py; r.fzo = -oodz + pz;
+    r.pad_far = ray_far_pad(O, r.idx, r.idy, r.idz);
     const bool negx = r.idx < 0.0f, negy = r.idy < 0.0f, negz = r.idz < 0.0f;
     r.octinv = (negx ? 0u : 4u) | (negy ? 0u : 2u) | (negz ? 0u : 1u);
     // plane p of half h sits at float4 3 + 2*p + h
@@ -125,9 +144,11 @@ PG_HD void ray_ctx_init(RayCtxQ& r, V3 O, V3 D, float tnear, float tfar, bool ww
     r.idx = pg_rcp(fabsf(D.x) > ooeps ? D.x : copysignf(ooeps, D.x));
     r.idy = pg_rcp(fabsf(D.y) > ooeps ? D.y : copysignf(ooeps, D.y));
     r.idz = pg_rcp(fabsf(D.z) > ooeps ? D.z : copysignf(ooeps, D.z));
-    // (origin - O) * idir carries the rounding of O, 2^-24 |O|, times |idir|: an ABSOLUTE error on t that a relative pad does
-    // not cover when the ray is nearly parallel to an axis (found by fuzzing axis-aligned sheets hit on their border)
-    r.pad_abs = 2.3841858e-7f * fmaxf(fmaxf(fabsf(O.x * r.idx), fabsf(O.y * r.idy)), fabsf(O.z * r.idz));   // 2^-22 * max |O * idir|
+    // (origin - O) * idir carries the rounding of the subtraction, 2^-24 max(|origin|, |O|), times |idir|: an ABSOLUTE error on
+    // that axis' t which a relative pad does not cover when the ray is nearly parallel to the axis (found by fuzzing
+    // axis-aligned sheets hit on their border).  Per axis, never the maximum over the axes (see RayCtxF).
+    r.pox = 2.3841858e-7f * fabsf(O.x * r.idx); r.poy = 2.3841858e-7f * fabsf(O.y * r.idy); r.poz = 2.3841858e-7f * fabsf(O.z * r.idz);
+    r.pad_far = ray_far_pad(O, r.idx, r.idy, r.idz);
     r.negx = r.idx < 0.0f; r.negy = r.idy < 0.0f; r.negz = r.idz < 0.0f;
     r.octinv = (r.negx ? 0u : 4u) | (r.negy ? 0u : 2u) | (r.negz ? 0u : 1u);
     r.octinv4 = r.octinv * 0x01010101u;
@@ -140,9 +161,9 @@ PG_HD uint32_t node_visit(const float4* __restrict__ nodes, uint32_t ni, const R
     const float4 f0 = pg_ldg4(nd), w0 = pg_ldg4(nd + 1), w1 = pg_ldg4(nd + 2);
     const float4 nx0 = pg_ldg4(nd + r.onx), ny0 = pg_ldg4(nd + r.ony), nz0 = pg_ldg4(nd + r.onz), fx0 = pg_ldg4(nd + r.ofx), fy0 = pg_ldg4(nd + r.ofy), fz0 = pg_ldg4(nd + r.ofz);
     const float4 nx1 = pg_ldg4(nd + r.onx + 1), ny1 = pg_ldg4(nd + r.ony + 1), nz1 = pg_ldg4(nd + r.onz + 1), fx1 = pg_ldg4(nd + r.ofx + 1), fy1 = pg_ldg4(nd + r.ofy + 1), fz1 = pg_ldg4(nd + r.ofz + 1);
-    const float far_pad = pg_fma(best_t, 1.0000005f, r.pad_abs);
-    uint32_t hitmask = slab4f(w0, nx0, ny0, nz0, fx0, fy0, fz0, r.idx, r.idy, r.idz, r.oodx, r.oody, r.oodz, r.tnear, far_pad, r.pad_abs);
-    hitmask |= slab4f(w1, nx1, ny1, nz1, fx1, fy1, fz1, r.idx, r.idy, r.idz, r.oodx, r.oody, r.oodz, r.tnear, far_pad, r.pad_abs);
+    const float far_pad = pg_fma(best_t, 1.0000005f, r.pad_far);
+    uint32_t hitmask = slab4f(w0, nx0, ny0, nz0, fx0, fy0, fz0, r.idx, r.idy, r.idz, r.nxo, r.nyo, r.nzo, r.fxo, r.fyo, r.fzo, r.tnear, far_pad);
+    hitmask |= slab4f(w1, nx1, ny1, nz1, fx1, fy1, fz1, r.idx, r.idy, r.idz, r.nxo, r.nyo, r.nzo, r.fxo, r.fyo, r.fzo, r.tnear, far_pad);
     uint32_t x;
     x = ((hitmask >> 1) ^ hitmask) & r.sw1; hitmask ^= x ^ (x << 1);
     x = ((hitmask >> 2) ^ hitmask) & r.sw2; hitmask ^= x ^ (x << 2);
@@ -158,14 +179,17 @@ PG_HD uint32_t node_visit(const float4* __restrict__ nodes, uint32_t ni, const R
     const uint32_t eb = pg_f2u(n0.w);
     const float sx = pg_u2f((eb & 0xFFu) << 23) * r.idx, sy = pg_u2f(((eb >> 8) & 0xFFu) << 23) * r.idy, sz = pg_u2f(((eb >> 16) & 0xFFu) << 23) * r.idz;
     const float ax = (n0.x - r.O.x) * r.idx, ay = (n0.y - r.O.y) * r.idy, az = (n0.z - r.O.z) * r.idz;
-    const float far_pad = pg_fma(best_t, 1.0000005f, r.pad_abs);
+    // |origin * idir| <= |O * idir| + |a|: pad = 2^-22 of both
+    const float pdx = pg_fma(2.3841858e-7f, fabsf(ax), r.pox), pdy = pg_fma(2.3841858e-7f, fabsf(ay), r.poy), pdz = pg_fma(2.3841858e-7f, fabsf(az), r.poz);
+    const float axn = ax - pdx, ayn = ay - pdy, azn = az - pdz, axf = ax + pdx, ayf = ay + pdy, azf = az + pdz;
+    const float far_pad = pg_fma(best_t, 1.0000005f, r.pad_far);
     const uint32_t lox0 = pg_f2u(n2.x), lox1 = pg_f2u(n2.y), loy0 = pg_f2u(n2.z), loy1 = pg_f2u(n2.w);
     const uint32_t loz0 = pg_f2u(n3.x), loz1 = pg_f2u(n3.y), hix0 = pg_f2u(n3.z), hix1 = pg_f2u(n3.w);
     const uint32_t hiy0 = pg_f2u(n4.x), hiy1 = pg_f2u(n4.y), hiz0 = pg_f2u(n4.z), hiz1 = pg_f2u(n4.w);
     uint32_t hitmask = slab4(pg_f2u(n1.z), r.negx ? hix0 : lox0, r.negy ? hiy0 : loy0, r.negz ? hiz0 : loz0, r.negx ? lox0 : hix0, r.negy ? loy0 : hiy0,
-                             r.negz ? loz0 : hiz0, sx, sy, sz, ax, ay, az, r.tnear, far_pad, r.pad_abs, r.octinv4);
+                             r.negz ? loz0 : hiz0, sx, sy, sz, axn, ayn, azn, axf, ayf, azf, r.tnear, far_pad, r.octinv4);
     hitmask |= slab4(pg_f2u(n1.w), r.negx ? hix1 : lox1, r.negy ? hiy1 : loy1, r.negz ? hiz1 : loz1, r.negx ? lox1 : hix1, r.negy ? loy1 : hiy1,
-                     r.negz ? loz1 : hiz1, sx, sy, sz, ax, ay, az, r.tnear, far_pad, r.pad_abs, r.octinv4);
+                     r.negz ? loz1 : hiz1, sx, sy, sz, axn, ayn, azn, axf, ayf, azf, r.tnear, far_pad, r.octinv4);
     child_base = pg_f2u(n1.x); tri_base = pg_f2u(n1.y); imask = eb >> 24;
     return hitmask;
 }
