@@ -433,15 +433,32 @@ bool DecodeJpeg(const uint8_t* d, size_t size, RawImage& out, std::string* error
             }
             const bool h2v2 = comp[0].h == 2 && comp[0].v == 2 && comp[1].h == 1 && comp[1].v == 1 && comp[2].h == 1 && comp[2].v == 1;
             const bool h1v1 = comp[0].h == 1 && comp[0].v == 1 && comp[1].h == 1 && comp[1].v == 1 && comp[2].h == 1 && comp[2].v == 1;
-            if (!h2v2 && !h1v1) return fail(error, "unsupported chroma sub-sampling (only 4:4:4 and 4:2:0)");
+            const bool h2v1 = comp[0].h == 2 && comp[0].v == 1 && comp[1].h == 1 && comp[1].v == 1 && comp[2].h == 1 && comp[2].v == 1;
+            if (!h2v2 && !h1v1 && !h2v1) return fail(error, "unsupported chroma sub-sampling (only 4:4:4, 4:2:2 and 4:2:0)");
             std::vector<uint8_t> up[2];
             const int cw = (width + 1) / 2, chh = (height + 1) / 2;     // down-sampled size actually carrying image data
-            if (h2v2) {
+            // libjpeg picks the triangle ("fancy") filters only when the down-sampled row has more than two samples
+            // (jdsample.c, jinit_upsampler); narrower images get plain replication
+            const bool fancy = cw > 2;
+            if (h2v2 || h2v1) {
                 for (int c = 0; c < 2; ++c) {
                     const Component& C = comp[1 + c];
                     up[c].assign((size_t)width * height + 2 * width + 4, 0);
                     std::vector<int> colsum(cw);
-                    for (int y = 0; y < height; ++y) {
+                    for (int y = 0; y < height && (!fancy || h2v1); ++y) {
+                        const uint8_t* a = &C.plane[(size_t)(h2v1 ? y : y >> 1) * C.stride];
+                        uint8_t* o = &up[c][(size_t)y * width];
+                        for (int x = 0; x < cw; ++x) {
+                            int e0 = a[x], e1 = a[x];                                       // replication
+                            if (fancy) {                                                      // h2v1_fancy_upsample
+                                e0 = x == 0 ? a[x] : (3 * a[x] + a[x - 1] + 1) >> 2;
+                                e1 = x + 1 == cw ? a[x] : (3 * a[x] + a[x + 1] + 2) >> 2;
+                            }
+                            if (2 * x < width) o[2 * x] = (uint8_t)e0;
+                            if (2 * x + 1 < width) o[2 * x + 1] = (uint8_t)e1;
+                        }
+                    }
+                    for (int y = 0; y < height && fancy && h2v2; ++y) {
                         const int r = y >> 1;
                         int rn = (y & 1) ? r + 1 : r - 1;                 // nearer neighbour row; edges replicate
                         rn = rn < 0 ? 0 : (rn >= chh ? chh - 1 : rn);
@@ -460,8 +477,8 @@ bool DecodeJpeg(const uint8_t* d, size_t size, RawImage& out, std::string* error
             }
             for (int y = 0; y < height; ++y) {
                 const uint8_t* Y = &comp[0].plane[(size_t)y * comp[0].stride];
-                const uint8_t* Cb = h2v2 ? &up[0][(size_t)y * width] : &comp[1].plane[(size_t)y * comp[1].stride];
-                const uint8_t* Cr = h2v2 ? &up[1][(size_t)y * width] : &comp[2].plane[(size_t)y * comp[2].stride];
+                const uint8_t* Cb = !h1v1 ? &up[0][(size_t)y * width] : &comp[1].plane[(size_t)y * comp[1].stride];
+                const uint8_t* Cr = !h1v1 ? &up[1][(size_t)y * width] : &comp[2].plane[(size_t)y * comp[2].stride];
                 uint8_t* o = &out.bytes[(size_t)y * out.pitch];
                 for (int x = 0; x < width; ++x) {
                     const int yy = Y[x], cb = Cb[x] - 128, cr = Cr[x] - 128;

@@ -1,6 +1,6 @@
 // image_io.h -- image decode / encode for the host surface.  Replaces what the reference gets from FreeImage 3.18.0
 // (pg1/texture.cpp:15-50; the library is not vendored): baseline JPEG (every .jpg under the reference's data/ is
-// SOF0, 4:2:0 or 4:4:4, one with restart intervals), 8-bit non-interlaced PNG (tutorial_2's data/test4.png), binary PPM and
+// SOF0, 4:2:0 or 4:4:4, one with restart intervals; 4:2:2 is decoded as well), 8-bit non-interlaced PNG (tutorial_2's data/test4.png), binary PPM and
 // 24/32-bit BMP in; PPM, PFM and PNG out (the headless counterpart of the D3D11 presentation).
 // Decoded images are returned the way Texture keeps them: top-down rows, B,G,R(,A) byte order, rows padded to 4 bytes
 // (FreeImage_GetPitch).

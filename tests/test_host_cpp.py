@@ -366,3 +366,30 @@ def test_png_writer(host, tmp_path, size):
     ppm = str(tmp_path / "frame.ppm")
     assert host.pg1_write_image(ppm.encode(), rgba.ctypes.data, w, h) == 0          # by extension
     assert np.array_equal(np.asarray(Image.open(ppm)), want)
+
+
+def test_jpeg_decoder_fuzz_against_libjpeg(host, tmp_path):
+    """Random small JPEGs -- sizes 1..90, quality 1..100, 4:4:4 / 4:2:2 / 4:2:0, optimised Huffman tables, restart intervals,
+    greyscale -- decoded bit-exactly as libjpeg-turbo does (through PIL).  Found by this fuzz: libjpeg switches from the
+    triangle filter to plain replication when the down-sampled row has two samples or fewer (images up to 4 pixels wide)."""
+    from PIL import Image
+    rng = np.random.default_rng(11)
+    sizes = [(w, h) for w in (1, 2, 3, 4, 5) for h in (1, 2, 3, 9)] + [(int(rng.integers(1, 90)), int(rng.integers(1, 90))) for _ in range(60)]
+    for k, (w, h) in enumerate(sizes):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if k % 2 else _test_picture(w, h, k)
+        grey = k % 7 == 3
+        kw = dict(quality=int(rng.integers(1, 101)), optimize=bool(k % 3 == 0))
+        if not grey:
+            kw["subsampling"] = int(rng.choice([0, 1, 2]))
+        if k % 5 == 1:
+            kw["restart_marker_blocks"] = int(rng.choice([1, 2, 5]))
+        p = str(tmp_path / f"f{k}.jpg")
+        im = Image.fromarray(img[..., 0], "L") if grey else Image.fromarray(img)
+        try:
+            im.save(p, "JPEG", **kw)
+        except TypeError:                      # an older Pillow without restart_marker_blocks
+            kw.pop("restart_marker_blocks", None); im.save(p, "JPEG", **kw)
+        ref = np.asarray(Image.open(p).convert("RGB"))
+        buf, ww, hh, pitch, bpp = load_image(host, p)
+        assert (ww, hh, bpp) == (w, h, 3), (k, w, h, kw)
+        assert np.array_equal(buf[:, :3 * w].reshape(h, w, 3)[..., ::-1], ref), (k, w, h, kw, grey)
