@@ -277,6 +277,13 @@ def test_pg1_b200_executable(tmp_path, cornell):
     assert f"Surfaces = {len(sc.meshes)}" in out.stdout and "Mrays/s" in out.stdout
     img = np.asarray(Image.open(str(tmp_path / "frame.ppm")))
     assert img.shape == (64, 96, 3) and img.std() > 5
+    # the progressive loop and the README to-dos: 4 accumulated frames of the path-tracing mode with hard shadows, as a PNG
+    out = subprocess.run([exe, str(tmp_path / "scene.obj"), str(tmp_path / "env.ppm"), "--width", "96", "--height", "64", "--frames", "1", "--depth", "4",
+                          "--accumulate", "4", "--path-tracing", "--hard-shadows", "--out", str(tmp_path / "acc.png")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "accumulated 4 frames" in out.stdout
+    acc = np.asarray(Image.open(str(tmp_path / "acc.png")))
+    assert acc.shape == (64, 96, 3) and acc.std() > 5 and not np.array_equal(acc, img)
 
 
 @pytest.mark.parametrize("mode,size,level", [("RGBA", (64, 32), 9), ("RGB", (37, 21), 6), ("L", (50, 7), 1), ("LA", (9, 40), 9), ("P", (33, 33), 9), ("RGB", (300, 200), 0)])
