@@ -400,3 +400,47 @@ def test_jpeg_decoder_fuzz_against_libjpeg(host, tmp_path):
         buf, ww, hh, pitch, bpp = load_image(host, p)
         assert (ww, hh, bpp) == (w, h, 3), (k, w, h, kw)
         assert np.array_equal(buf[:, :3 * w].reshape(h, w, 3)[..., ::-1], ref), (k, w, h, kw, grey)
+
+
+def test_loader_float_scan_equals_strtof_and_crlf(host, tmp_path):
+    """The loader's in-place float scan against glibc strtof (what the reference's sscanf("%f") does): integers, fixed and
+    scientific notation, leading '.', trailing '.', 30-digit midpoints between adjacent floats -- bit for bit; a malformed
+    token stops the line as sscanf does (the remaining components keep 0).  The same file with CRLF line ends loads identically."""
+    import re
+    libc = C.CDLL("libc.so.6"); libc.strtof.restype = C.c_float; libc.strtof.argtypes = [C.c_char_p, C.c_void_p]
+    rng = np.random.default_rng(8)
+
+    def tok():
+        k = int(rng.integers(0, 8)); sign = str(rng.choice(["", "-", "+"], p=[0.6, 0.3, 0.1]))
+        if k == 0: return sign + str(int(rng.integers(0, 10 ** int(rng.integers(1, 12)))))
+        if k == 1: return sign + f"{rng.uniform(0, 1e3):.{int(rng.integers(0, 12))}f}"
+        if k == 2: return sign + f"{rng.uniform(0, 1):.{int(rng.integers(1, 25))}f}"
+        if k == 3: return sign + f"{rng.uniform(1, 10):.{int(rng.integers(0, 10))}f}e{int(rng.integers(-45, 39))}"
+        if k == 4: return sign + f"{rng.uniform(1, 10):.{int(rng.integers(0, 17))}g}E{int(rng.integers(-10, 10)):+d}"
+        if k == 5: return sign + "." + str(int(rng.integers(0, 10 ** 9)))
+        if k == 6: return sign + str(int(rng.integers(0, 10 ** 6))) + "."
+        f = np.float32(rng.uniform(1e-3, 1e3)); g = np.nextafter(f, np.float32(np.inf))
+        return sign + f"{(float(f) + float(g)) / 2:.30f}"
+
+    n = 6000
+    def valid_tok():
+        while True:
+            t = tok()
+            if re.fullmatch(r"[+-]?(\d+\.?\d*|\.\d+)([eE][+-]?\d+)?", t):
+                return t
+
+    strs = [[valid_tok() for _ in range(3)] for _ in range(n)]
+    strs[7] = ["1.5", "--2", "3"]                                   # malformed: sscanf stops here
+    body = "".join("v " + " ".join(s) + "\n" for s in strs) + "vn 0 0 1\nvt 0 0\ng a\n" + "".join(f"f {i + 1}/1/1 {i + 2}/1/1 {i + 3}/1/1\n" for i in range(0, n - 2, 3))
+    want = np.array([[libc.strtof(t.encode(), None) for t in s] for s in strs], np.float32)
+    want[7] = [1.5, 0.0, 0.0]
+    for name, text in (("lf.obj", body), ("crlf.obj", body.replace("\n", "\r\n"))):
+        p = tmp_path / name
+        p.write_bytes(text.encode())
+        h = host.pg1_load_obj(str(p).encode(), 0)
+        try:
+            assert host.pg1_num_surfaces(h) == 1 and host.pg1_surface_name(h, 0).decode() == "a"
+            pos, _, _ = scene_arrays(host, h, 0)
+            assert np.array_equal(pos.reshape(-1, 3).view(np.uint32), want[: pos.size // 3].view(np.uint32)), name
+        finally:
+            host.pg1_free_scene(h)
