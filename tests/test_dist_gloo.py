@@ -46,3 +46,57 @@ def test_gather_and_untile_world2(wh):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+class _HostOnlyRaytracer:
+    """Stands in for api.Raytracer where share_host_frames needs it: on a CPU box 'registering' a host mapping with the
+    device is the identity (the kernels of a real rank store through the device alias of the same pages)."""
+    def __init__(self, w, h):
+        self.width, self.height, self.registered = w, h, []
+
+    def host_frame_register(self, host_ptr, nbytes):
+        self.registered.append((host_ptr, nbytes))
+        return host_ptr
+
+    def host_frame_unregister(self, host_ptr):
+        self.registered = [r for r in self.registered if r[0] != host_ptr]
+
+
+def _host_frames_worker(rank, world, port, w, h, q):
+    import ctypes
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rt = _HostOnlyRaytracer(w, h)
+    n_frames = 3
+    ptrs, views, keep = D.share_host_frames(rt, n_frames, rank, torch.device("cpu"))
+    assert ptrs is not None and len(ptrs) == n_frames and ptrs[0] % 4096 == 0 and (ptrs[1] - ptrs[0]) % 4096 == 0
+    assert (views is not None) == (rank == 0)
+    # every rank writes "its tiles" of every frame through its own mapping of the one memfd: rank r fills rows r, r+world, ...
+    for f in range(n_frames):
+        row = np.ctypeslib.as_array((ctypes.c_float * (w * h * 4)).from_address(ptrs[f])).reshape(h, w, 4)
+        row[rank::world] = 100.0 * f + rank + 1
+    dist.barrier()
+    if rank == 0:
+        ok = True
+        for f in range(n_frames):
+            got = views[f].numpy()
+            for r in range(world):
+                ok &= bool(np.all(got[r::world] == 100.0 * f + r + 1))
+        q.put(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shared_host_frames_world2():
+    """dist.share_host_frames (mode "host" of ShardedRenderer): rank 0 creates a memfd, rank 1 opens it through
+    /proc/<pid>/fd, both map it; what each rank writes through its mapping is what rank 0 reads from its CPU views."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_host_frames_worker, args=(r, 2, port, 70, 21, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
