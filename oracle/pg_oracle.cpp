@@ -214,16 +214,24 @@ static Hit intersect_brute(const Scene& s, const Ray& r) {
 
 static inline bool box_test(const BNode& n, const Ray& r, const float inv[3], float tbest, float& tentry) {
     const float o[3] = {r.ox, r.oy, r.oz};
-    float t0 = r.tnear, t1 = tbest;
+    // The box test only culls: it must never reject a triangle that tri_test accepts.  (plane - o) * inv carries the rounding
+    // of the subtraction seen through inv -- an ABSOLUTE error on t of about 2^-24 max(|plane|, |o|) |inv| -- so every axis is
+    // widened by 2^-22 (|o * inv| + |t|), and the best hit so far (whose t has tri_test's own rounding of o - v0) gets a
+    // slack of 2^-21 max|o| min|inv|.  Found by fuzzing axis-aligned sheets hit on their border (tools/fuzz_emul.py scenes).
+    const float omax = std::max(std::fabs(o[0]), std::max(std::fabs(o[1]), std::fabs(o[2])));
+    const float imin = std::min(std::fabs(inv[0]), std::min(std::fabs(inv[1]), std::fabs(inv[2])));
+    float t0 = r.tnear, t1 = tbest * 1.0000005f + 4.7683716e-7f * omax * imin;
     for (int a = 0; a < 3; ++a) {
         float ta = (n.lo[a] - o[a]) * inv[a], tb = (n.hi[a] - o[a]) * inv[a];
         if (ta > tb) std::swap(ta, tb);
-        // NaN (0*inf) compares false on both and leaves the interval untouched: conservative
+        const float po = 2.3841858e-7f * std::fabs(o[a] * inv[a]);
+        ta -= po + 2.3841858e-7f * std::fabs(ta); tb += po + 2.3841858e-7f * std::fabs(tb);
+        // NaN (0*inf, inf-inf) compares false on both and leaves the interval untouched: conservative
         if (ta > t0) t0 = ta;
         if (tb < t1) t1 = tb;
     }
     tentry = t0;
-    return t0 <= t1 * 1.0000005f + 1e-30f;   // padded: never culls a triangle tri_test accepts
+    return t0 <= t1 * 1.0000005f + 1e-30f;
 }
 
 static Hit intersect_bvh(const Scene& s, const Ray& r) {

@@ -309,3 +309,63 @@ def test_bench_clock_sampler_degrades_without_a_gpu():
     s = bench.ClockSampler(0); s.start()
     out = s.stop()
     assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+# ------------------------------------------------------------------------------------------------ the oracle's own BVH
+FMAX = np.finfo(np.float32).max
+def _fuzz_scene(rng, kind, n):
+    if kind == 0:   # uniform soup
+        c = rng.uniform(-100, 100, (n, 1, 3)); p = c + rng.uniform(-3, 3, (n, 3, 3))
+    elif kind == 1: # axis-aligned grid sheets (flat boxes), exact integer coordinates
+        g = int(np.sqrt(n / 2)) + 1
+        xs, ys = np.meshgrid(np.arange(g), np.arange(g))
+        a = np.stack([xs, ys, np.zeros_like(xs)], -1).reshape(-1, 3).astype(float)
+        t1 = np.stack([a, a + [1, 0, 0], a + [1, 1, 0]], 1); t2 = np.stack([a, a + [1, 1, 0], a + [0, 1, 0]], 1)
+        p = np.concatenate([t1, t2])[:n]
+        if rng.random() < 0.5: p = p[..., [2, 0, 1]]
+    elif kind == 2: # huge + tiny mix, far from origin
+        c = rng.uniform(-1, 1, (n, 1, 3)) * 10.0 ** rng.uniform(-2, 4, (n, 1, 1)) + 5000.0
+        p = c + rng.normal(size=(n, 3, 3)) * 10.0 ** rng.uniform(-3, 2, (n, 1, 1))
+    elif kind == 3: # many duplicates + degenerate
+        base = rng.uniform(-10, 10, (max(n // 8, 1), 3, 3))
+        p = base[rng.integers(0, base.shape[0], n)]
+        deg = rng.random(n) < 0.1; p[deg, 2] = p[deg, 1]
+    else:           # long thin slivers along a diagonal
+        t = rng.uniform(0, 1, (n, 1, 1)); c = t * np.array([100.0, 100.0, 100.0])
+        p = c + rng.normal(size=(n, 3, 3)) * np.array([20.0, 0.01, 0.01])
+    return np.ascontiguousarray(p.reshape(n, 9).astype(np.float32))
+def _fuzz_rays(rng, pos, m):
+    P = pos.reshape(-1, 3); lo, hi = P.min(0), P.max(0); ext = np.maximum(hi - lo, 1e-3)
+    org = rng.uniform(lo - ext, hi + ext, (m, 3)); tri = pos[rng.integers(0, pos.shape[0], m)].reshape(m, 3, 3)
+    w = rng.dirichlet((1, 1, 1), m)[:, :, None]; tgt = (tri * w).sum(1)
+    edge = rng.random(m) < 0.2; tgt[edge] = tri[edge, 0] * 0.5 + tri[edge, 1] * 0.5     # aim at edges
+    vert = rng.random(m) < 0.1; tgt[vert] = tri[vert, 2]                                 # and vertices
+    d = (tgt - org) * rng.uniform(0.01, 5, (m, 1))
+    ax = rng.random(m) < 0.15; k = rng.integers(0, 3, m); d[ax, k[ax]] = 0.0            # zero components
+    ax2 = rng.random(m) < 0.05; d[ax2] = 0; d[ax2, k[ax2]] = rng.choice([-1.0, 1.0], ax2.sum())
+    inside = rng.random(m) < 0.2; org[inside] = tgt[inside]; d[inside] = rng.normal(size=(inside.sum(), 3))
+    rays = np.zeros((m, 8), np.float32); rays[:, :3] = org; rays[:, 4:7] = d
+    rays[:, 3] = rng.choice([0.0, 1e-3, 0.01], m); rays[:, 7] = FMAX
+    b = rng.random(m) < 0.2; rays[b, 7] = rng.uniform(0.1, 2.0, b.sum())
+    neg = rng.random(m) < 0.02; rays[neg, 3] = 5.0; rays[neg, 7] = 1.0                   # empty interval
+    tiny = rng.random(m) < 0.03; rays[tiny, 4:7] *= 1e-12                                # near-denormal directions
+    return rays
+
+
+
+def test_oracle_bvh_equals_oracle_brute_force_on_fuzzed_input(oracle_mod):
+    """The checker checked: the oracle's BVH traversal (what its renders use) against its brute-force loop on pathological
+    scenes and rays (axis-aligned sheets hit on their border, slivers, duplicates, axis-parallel rays ...).  Its box test
+    once culled a handful of border hits in 150 000 rays; it now carries the same per-axis pads as the CUDA path."""
+    for seed in range(0, 30):
+        rng = np.random.default_rng(seed)
+        kind = seed % 5; n = int(rng.choice([1, 2, 3, 7, 33, 200, 1500]))
+        pos = _fuzz_scene(rng, kind, n); rays = _fuzz_rays(rng, pos, 400)
+        nrm = np.tile(np.array([0, 0, 1], np.float32), (n, 3, 1)); uv = np.zeros((n, 3, 2), np.float32)
+        sc = scenes.Scene("fuzz", [scenes.Mesh("m", pos.reshape(n, 3, 3), nrm, uv, 0)], [scenes.Material("m")], camera=scenes.Camera(8, 8))
+        o = oracle_mod.Oracle(sc)
+        rh = oracle_mod.make_rayhits(rays[:, :3], rays[:, 4:7])
+        rh["tnear"] = rays[:, 3]; rh["tfar"] = rays[:, 7]
+        a = o.intersect(rh, brute=False); b = o.intersect(rh, brute=True)
+        for f in ("tfar", "u", "v", "geomID", "primID"):
+            assert np.array_equal(a[f], b[f]), (seed, kind, n, f)
