@@ -19,7 +19,11 @@
 #include <cstring>
 #include <algorithm>
 #include <functional>
+#include <chrono>
 #include <thread>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace {
 
@@ -33,6 +37,54 @@ bool read_file(const char* file_name, std::string& out) {
     const size_t got = out.empty() ? 0 : fread(&out[0], 1, out.size(), f);
     fclose(f);
     out.resize(got);
+    return true;
+}
+
+// The OBJ text: malloc'ed (not value-initialised: the reading threads touch its pages first, in parallel), NUL-terminated
+struct TextBuf {
+    char* p = nullptr; size_t n = 0;
+    TextBuf() = default;
+    TextBuf(const TextBuf&) = delete;
+    TextBuf& operator=(const TextBuf&) = delete;
+    ~TextBuf() { free(p); }
+    const char* data() const { return p; }
+    size_t size() const { return n; }
+    char operator[](size_t i) const { return p[i]; }
+};
+
+// Every thread preads its own part of the file: page faults of the fresh buffer and the copy out of the page cache scale.
+bool read_file_parallel(const char* file_name, TextBuf& out, unsigned n_threads) {
+    const int fd = open(file_name, O_RDONLY);
+    if (fd < 0) { printf("File %s not found.\n", file_name); return false; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 0) { close(fd); return false; }
+    const size_t n = (size_t)st.st_size;
+    out.p = (char*)malloc(n + 1);
+    if (!out.p) { close(fd); return false; }
+    out.n = n; out.p[n] = 0;
+    if (n < (size_t)(8u << 20)) n_threads = 1;
+    std::vector<std::thread> pool;
+    std::vector<size_t> got_to(n_threads, 0);
+    const size_t chunk = (n + n_threads - 1) / n_threads;
+    auto work = [&](unsigned t) {
+        size_t off = std::min(n, chunk * t);
+        const size_t end = std::min(n, off + chunk);
+        while (off < end) {
+            const ssize_t got = pread(fd, out.p + off, end - off, (off_t)off);
+            if (got <= 0) break;
+            off += (size_t)got;
+        }
+        got_to[t] = off;
+    };
+    for (unsigned t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    close(fd);
+    for (unsigned t = 0; t < n_threads; ++t)
+        if (got_to[t] != std::min(n, chunk * t + chunk)) {          // the file shrank under us: keep what is contiguous
+            out.n = got_to[t]; out.p[out.n] = 0;
+            break;
+        }
     return true;
 }
 
@@ -68,6 +120,78 @@ std::string second_token(const char* b, const char* e) {
 // "%*s %f %f %f" with scanf's partial-assignment behaviour: stops at the first field that does not parse.
 // Parses in place (no per-line allocation: the workers of LoadOBJ would serialise on the allocator): the buffer is
 // NUL-terminated and a number never contains the '\n' that ends the line, so strtof cannot run past it.
+// strtof for the common case, about 8x faster than glibc's: up to 19 significant digits with |decimal exponent| <= 22 give
+// m * 10^E (or m / 10^-E) as ONE correctly rounded double operation (m <= 2^53 and 10^|E| are exact doubles); the cast to
+// float then rounds a second time, which can only go wrong when that double sits exactly on the midpoint of two floats
+// (low 29 mantissa bits == 0x10000000): those, sub-normal / overflowing values, hex floats, inf / nan and longer digit
+// strings return false and go through strtof.  Result: bit-identical to strtof (tests/test_host_cpp.py fuzzes it).
+inline bool fast_strtof(const char* s, const char* e, const char*& after, float& out) {
+    static const double P10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+    const char* p = s;
+    bool neg = false;
+    if (p < e && (*p == '-' || *p == '+')) { neg = *p == '-'; ++p; }
+    if (p >= e || !((*p >= '0' && *p <= '9') || *p == '.')) return false;
+    if (*p == '0' && p + 1 < e && (p[1] == 'x' || p[1] == 'X')) return false;
+    uint64_t m = 0; int nd = 0, dec = 0; bool any = false;
+    for (; p < e && *p >= '0' && *p <= '9'; ++p) {
+        any = true;
+        if (nd >= 19) return false;
+        m = m * 10 + (uint64_t)(*p - '0');
+        if (m) ++nd;
+    }
+    if (p < e && *p == '.') {
+        ++p;
+        for (; p < e && *p >= '0' && *p <= '9'; ++p) {
+            any = true;
+            if (nd >= 19) return false;
+            m = m * 10 + (uint64_t)(*p - '0');
+            if (m) ++nd;
+            --dec;
+        }
+    }
+    if (!any) return false;
+    if (p < e && (*p == 'e' || *p == 'E')) {
+        const char* q = p + 1;
+        bool eneg = false;
+        if (q < e && (*q == '-' || *q == '+')) { eneg = *q == '-'; ++q; }
+        if (q < e && *q >= '0' && *q <= '9') {
+            int ex = 0;
+            for (; q < e && *q >= '0' && *q <= '9'; ++q) if (ex < 100000) ex = ex * 10 + (*q - '0');
+            dec += eneg ? -ex : ex;
+            p = q;
+        }                                   // "1e" / "1e+": strtof stops before the 'e'
+    }
+    if (m == 0) { out = neg ? -0.0f : 0.0f; after = p; return true; }
+    if (m <= (1ull << 53) && dec >= -22 && dec <= 22) {
+        double d = (double)m;
+        d = dec < 0 ? d / P10[-dec] : d * P10[dec];
+        if (!(d > 1.2e-37 && d < 3.0e38)) return false;
+        uint64_t bits; memcpy(&bits, &d, sizeof bits);
+        if ((bits & 0x1FFFFFFFull) == 0x10000000ull) return false;
+        out = (float)(neg ? -d : d);
+        after = p;
+        return true;
+    }
+#if defined(__x86_64__) && defined(__GNUC__)
+    // 16-19 digits (a float printed as a double's repr): the same argument one precision up.  The x87 long double has a 64-bit
+    // significand, so any 19-digit m and 10^|E| up to 10^27 are exact and m * 10^E is one correctly rounded operation; the
+    // cast to float is ambiguous only on a float midpoint (low 40 significand bits == 0x8000000000).
+    if (dec >= -27 && dec <= 27) {
+        static const long double P10L[28] = {1e0L, 1e1L, 1e2L, 1e3L, 1e4L, 1e5L, 1e6L, 1e7L, 1e8L, 1e9L, 1e10L, 1e11L, 1e12L, 1e13L, 1e14L, 1e15L, 1e16L,
+                                             1e17L, 1e18L, 1e19L, 1e20L, 1e21L, 1e22L, 1e23L, 1e24L, 1e25L, 1e26L, 1e27L};
+        long double d = (long double)m;
+        d = dec < 0 ? d / P10L[-dec] : d * P10L[dec];
+        if (!(d > 1.2e-37L && d < 3.0e38L)) return false;
+        uint64_t sig; memcpy(&sig, &d, sizeof sig);          // little endian: the 64-bit significand comes first
+        if ((sig & 0xFFFFFFFFFFull) == 0x8000000000ull) return false;
+        out = (float)(neg ? -d : d);
+        after = p;
+        return true;
+    }
+#endif
+    return false;
+}
+
 int scan_floats(const char* b, const char* e, float* dst[], int n) {
     const char* s = b;
     while (s < e && isspace((unsigned char)*s)) ++s;
@@ -76,8 +200,10 @@ int scan_floats(const char* b, const char* e, float* dst[], int n) {
     for (; got < n; ++got) {
         while (s < e && isspace((unsigned char)*s)) ++s;
         if (s >= e) break;
+        const char* fast_after = nullptr; float v;
+        if (fast_strtof(s, e, fast_after, v)) { *dst[got] = v; s = fast_after; continue; }
         char* after = nullptr;
-        const float v = strtof(s, &after);
+        v = strtof(s, &after);
         if (after == s || after > e) break;
         *dst[got] = v;
         s = after;
@@ -185,7 +311,7 @@ struct Slice {
     std::vector<FaceRec> faces; std::vector<Event> events;
 };
 
-void parse_slice(const std::string& text, size_t lo, size_t hi, bool flip_yz, Slice& out) {
+void parse_slice(const TextBuf& text, size_t lo, size_t hi, bool flip_yz, Slice& out) {
     const char* p = text.data() + lo; const char* end = text.data() + hi;
     while (p < end) {
         while (p < end && *p == '\n') ++p;
@@ -242,16 +368,21 @@ void parse_slice(const std::string& text, size_t lo, size_t hi, bool flip_yz, Sl
 
 int LoadOBJ(const char* file_name, std::vector<Surface*>& surfaces, std::vector<Material*>& materials, const bool flip_yz,
             const Vector3 /*default_color: vertex colours are never read by the path*/, TextureCache* cache) {
-    std::string text;
-    if (!read_file(file_name, text)) return -1;
+    const bool timing = getenv("PG1_LOADER_TIMING") != nullptr;
+    auto now = []() { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t_start = now();
+    unsigned n_threads = std::thread::hardware_concurrency();
+    if (const char* e = getenv("PG1_LOADER_THREADS")) n_threads = (unsigned)atoi(e);
+    n_threads = std::max(1u, std::min(n_threads, 64u));
+    TextBuf text;
+    if (!read_file_parallel(file_name, text, n_threads)) return -1;
     if (text.size() >= 0xFFFFFFFFull) { printf("File %s is larger than 4 GiB.\n", file_name); return -1; }
+    const auto t_read = now();
     std::string path;
     if (const char* slash = strrchr(file_name, '/')) path.assign(file_name, slash - file_name + 1);
 
     // ---- parallel part: the file is cut at line ends into one slice per hardware thread
-    unsigned n_threads = std::thread::hardware_concurrency();
-    if (const char* e = getenv("PG1_LOADER_THREADS")) n_threads = (unsigned)atoi(e);
-    n_threads = std::max(1u, std::min(n_threads, 64u));
     if (text.size() < (1u << 20)) n_threads = 1;
     std::vector<size_t> cut(n_threads + 1, text.size());
     cut[0] = 0;
@@ -268,6 +399,7 @@ int LoadOBJ(const char* file_name, std::vector<Surface*>& surfaces, std::vector<
         for (auto& th : pool) th.join();
     }
 
+    const auto t_parse = now();
     // ---- sequential part, in file order.  Material libraries first (the reference's first pass)
     for (const Slice& sl : slices)
         for (const Event& ev : sl.events)
@@ -285,6 +417,7 @@ int LoadOBJ(const char* file_name, std::vector<Surface*>& surfaces, std::vector<
         }
     }
     printf("%zu vertices, %zu normals and %zu texture coords.\n", vertices.size(), normals.size(), tex_coords.size());
+    const auto t_concat = now();
 
     int no_surfaces = 0;
     std::string group_name, material_name;
@@ -318,5 +451,7 @@ int LoadOBJ(const char* file_name, std::vector<Surface*>& surfaces, std::vector<
     flush();
     delete current;
     printf("%d group(s), %zu material(s)\n", no_surfaces, materials.size());
+    if (timing) printf("LoadOBJ: read %.1f ms, parse (%u threads) %.1f ms, materials + concatenate %.1f ms, surfaces %.1f ms\n", ms(t_start, t_read), n_threads,
+                       ms(t_read, t_parse), ms(t_parse, t_concat), ms(t_concat, now()));
     return no_surfaces;
 }

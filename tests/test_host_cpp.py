@@ -403,15 +403,18 @@ def test_jpeg_decoder_fuzz_against_libjpeg(host, tmp_path):
 
 
 def test_loader_float_scan_equals_strtof_and_crlf(host, tmp_path):
-    """The loader's in-place float scan against glibc strtof (what the reference's sscanf("%f") does): integers, fixed and
-    scientific notation, leading '.', trailing '.', 30-digit midpoints between adjacent floats -- bit for bit; a malformed
+    """The loader's in-place float scan (its own two-tier exact fast path, strtof behind it) against glibc strtof (what the
+    reference's sscanf("%f") does): integers, fixed and scientific notation, leading '.', trailing '.', 16-19 digit
+    mantissas, reprs of float32 values, 30-digit midpoints between adjacent floats -- bit for bit; a malformed
     token stops the line as sscanf does (the remaining components keep 0).  The same file with CRLF line ends loads identically."""
     import re
     libc = C.CDLL("libc.so.6"); libc.strtof.restype = C.c_float; libc.strtof.argtypes = [C.c_char_p, C.c_void_p]
     rng = np.random.default_rng(8)
 
     def tok():
-        k = int(rng.integers(0, 8)); sign = str(rng.choice(["", "-", "+"], p=[0.6, 0.3, 0.1]))
+        k = int(rng.integers(0, 10)); sign = str(rng.choice(["", "-", "+"], p=[0.6, 0.3, 0.1]))
+        if k == 8: return repr(float(np.float32(rng.uniform(-100, 100) * 10.0 ** int(rng.integers(-6, 6)))))      # 16-17 digits: the x87 tier
+        if k == 9: return sign + (str(int(rng.integers(10 ** 8, 10 ** 9))) + str(int(rng.integers(10 ** 9, 10 ** 10))))[: int(rng.integers(16, 20))] + "e-" + str(int(rng.integers(0, 28)))
         if k == 0: return sign + str(int(rng.integers(0, 10 ** int(rng.integers(1, 12)))))
         if k == 1: return sign + f"{rng.uniform(0, 1e3):.{int(rng.integers(0, 12))}f}"
         if k == 2: return sign + f"{rng.uniform(0, 1):.{int(rng.integers(1, 25))}f}"
