@@ -419,16 +419,28 @@ int LoadOBJ(const char* file_name, std::vector<Surface*>& surfaces, std::vector<
     printf("%zu vertices, %zu normals and %zu texture coords.\n", vertices.size(), normals.size(), tex_coords.size());
     const auto t_concat = now();
 
+    // Surfaces.  The walk over the events is sequential (group / material names and the "last usemtl before the next g wins"
+    // rule depend on file order) but only counts: every valid face gets its surface and its triangle offset there.  The
+    // corners -- where the bytes are -- are then copied by all threads.
+    struct Job { const FaceRec* face; uint32_t surface, first_triangle; };
+    std::vector<Job> jobs;
+    {
+        size_t n_faces = 0;
+        for (const Slice& sl : slices) n_faces += sl.faces.size();
+        jobs.reserve(n_faces);
+    }
     int no_surfaces = 0;
+    const size_t first_new = surfaces.size();
     std::string group_name, material_name;
-    Surface* current = new Surface();
+    uint32_t pending = 0;                        // triangles of the group being read
     auto flush = [&]() {
-        if (current->no_triangles() == 0) return;
-        Surface* s = new Surface(group_name, 0);
-        s->positions.swap(current->positions); s->normals.swap(current->normals); s->tex_coords.swap(current->tex_coords);
-        for (Material* m : materials) if (m->get_name() == material_name) { s->set_material(m); break; }
-        surfaces.push_back(s);
+        if (pending == 0) return;
+        Surface* sf = new Surface(group_name, 0);
+        sf->positions.resize(9 * (size_t)pending); sf->normals.resize(9 * (size_t)pending); sf->tex_coords.resize(6 * (size_t)pending);
+        for (Material* m : materials) if (m->get_name() == material_name) { sf->set_material(m); break; }
+        surfaces.push_back(sf);
         ++no_surfaces;
+        pending = 0;
     };
     for (const Slice& sl : slices)
         for (const Event& ev : sl.events) {
@@ -441,15 +453,35 @@ int LoadOBJ(const char* file_name, std::vector<Surface*>& surfaces, std::vector<
                     ok = f.idx[k][0] >= 0 && (size_t)f.idx[k][0] < vertices.size() && f.idx[k][1] >= 0 && (size_t)f.idx[k][1] < tex_coords.size() &&
                          f.idx[k][2] >= 0 && (size_t)f.idx[k][2] < normals.size();
                 if (!ok) continue;
-                const int order[6] = {0, 1, 2, 0, 2, 3};
-                for (int k = 0; k < (f.corners == 4 ? 6 : 3); ++k) {
-                    const int* i = f.idx[order[k]];
-                    current->push_corner(vertices[i[0]], normals[i[2]], tex_coords[i[1]]);
-                }
+                jobs.push_back(Job{&f, (uint32_t)(first_new + (size_t)no_surfaces), pending});
+                pending += f.corners == 4 ? 2u : 1u;
             }
         }
     flush();
-    delete current;
+    {
+        auto fill = [&](size_t lo, size_t hi) {
+            const int order[6] = {0, 1, 2, 0, 2, 3};
+            for (size_t j = lo; j < hi; ++j) {
+                const Job& job = jobs[j];
+                Surface* sf = surfaces[job.surface];
+                const int n_corners = job.face->corners == 4 ? 6 : 3;
+                for (int k = 0; k < n_corners; ++k) {
+                    const int* i = job.face->idx[order[k]];
+                    const size_t c = 3 * (size_t)job.first_triangle + (size_t)k;
+                    const Vector3& pv = vertices[i[0]]; const Vector3& nv = normals[i[2]]; const Coord2f& tv = tex_coords[i[1]];
+                    sf->positions[3 * c] = pv.x; sf->positions[3 * c + 1] = pv.y; sf->positions[3 * c + 2] = pv.z;
+                    sf->normals[3 * c] = nv.x; sf->normals[3 * c + 1] = nv.y; sf->normals[3 * c + 2] = nv.z;
+                    sf->tex_coords[2 * c] = tv.u; sf->tex_coords[2 * c + 1] = tv.v;
+                }
+            }
+        };
+        const unsigned n_fill = jobs.size() < (1u << 16) ? 1u : n_threads;
+        std::vector<std::thread> pool;
+        const size_t per = (jobs.size() + n_fill - 1) / n_fill;
+        for (unsigned t = 1; t < n_fill; ++t) pool.emplace_back(fill, std::min(jobs.size(), per * t), std::min(jobs.size(), per * t + per));
+        fill(0, std::min(jobs.size(), per));
+        for (auto& th : pool) th.join();
+    }
     printf("%d group(s), %zu material(s)\n", no_surfaces, materials.size());
     if (timing) printf("LoadOBJ: read %.1f ms, parse (%u threads) %.1f ms, materials + concatenate %.1f ms, surfaces %.1f ms\n", ms(t_start, t_read), n_threads,
                        ms(t_read, t_parse), ms(t_parse, t_concat), ms(t_concat, now()));
