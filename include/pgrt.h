@@ -83,7 +83,7 @@ typedef struct pgrt_build_stats {
     float collapse_ms;        /* collapse to the wide layout + triangle re-layout                */
     uint32_t depth;           /* levels of the wide tree                                         */
     uint32_t ploc_passes;     /* multi-block PLOC passes (the last <= 512 clusters finish in one block) */
-    uint32_t node_bytes;      /* 80 = quantised planes, 208 = float planes (chosen by scene size; PGRT_NODE_LAYOUT=q8|f32) */
+    uint32_t node_bytes;      /* 80 = quantised planes, 240 = float planes (chosen by scene size; PGRT_NODE_LAYOUT=q8|f32) */
     uint32_t reserved[2];
 } pgrt_build_stats;
 

@@ -78,7 +78,7 @@ CASES = {
 
 @pytest.mark.parametrize("name", list(CASES))
 @pytest.mark.parametrize("builder", [0, 1])
-@pytest.mark.parametrize("layout", [0, 1])          # 0 = 80-B quantised nodes, 1 = 208-B float planes
+@pytest.mark.parametrize("layout", [0, 1])          # 0 = 80-B quantised nodes, 1 = 240-B float planes
 def test_wide_tree_structure_and_hits(emul, name, builder, layout):
     pos = scene_pos(CASES[name]())
     h = emul.emul_build(pos.ctypes.data, pos.shape[0], builder, layout)
