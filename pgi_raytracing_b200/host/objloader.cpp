@@ -279,7 +279,18 @@ int LoadMTL(const char* file_name, const char* path, std::vector<Material*>& mat
         float* v3s[3] = {&material->specular.x, &material->specular.y, &material->specular.z};
         float* v3e[3] = {&material->emission.x, &material->emission.y, &material->emission.z};
         if (starts_with(b, e, "Ka")) scan_floats(b, e, v3a, 3);
-        if (starts_with(b, e, "shader")) { float t = 0; float* p[1] = {&t}; if (scan_floats(b, e, p, 1) == 1) material->type = (int)t; }
+        if (starts_with(b, e, "shader")) {                                  // "%*s %d": sign and digits only ("4.7" and "4e1" read as 4)
+            const char* s = b;
+            while (s < e && !isspace((unsigned char)*s)) ++s;
+            while (s < e && isspace((unsigned char)*s)) ++s;
+            bool neg = false;
+            if (s < e && (*s == '-' || *s == '+')) { neg = *s == '-'; ++s; }
+            if (s < e && *s >= '0' && *s <= '9') {
+                long v = 0;
+                for (; s < e && *s >= '0' && *s <= '9'; ++s) if (v < 0x7fffffff) v = v * 10 + (*s - '0');
+                material->type = (int)(neg ? -v : v);
+            }
+        }
         if (starts_with(b, e, "Ni")) { float* p[1] = {&material->ior}; scan_floats(b, e, p, 1); }
         if (starts_with(b, e, "Tf")) scan_floats(b, e, v3t, 3);
         if (starts_with(b, e, "Kd")) scan_floats(b, e, v3d, 3);

@@ -162,7 +162,7 @@ def test_mtl_parse_matches_the_reference_fixture(host, tmp_path):
 
 def test_loader_quirks(host, tmp_path):
     obj = tmp_path / "q.obj"
-    (tmp_path / "q.mtl").write_text("newmtl a\nKd 1 0 0\nshader 4\nnewmtl b\n  Kd 0 1 0\nnewmtl a\nKd 0 0 1\nKdx 9 9 9\n# Kd 5 5 5\nnewmtl c\nNs 7\n")
+    (tmp_path / "q.mtl").write_text("newmtl a\nKd 1 0 0\nshader 4e1\nnewmtl b\n  Kd 0 1 0\nnewmtl a\nKd 0 0 1\nKdx 9 9 9\n# Kd 5 5 5\nnewmtl c\nNs 7\n  newmtl d\nshader x\nshader 3.9\n")
     obj.write_text("\n".join([
         "mtllib q.mtl", "v 0 0 0", "v 1 0 0", "v 1 1 0", "v 0 1 0", "vn 0 0 2", "vt 0.25 0.75 0", "vt 1 1",
         "f 1/1/1 2/1/1 3/2/1",                    # before any g: surface named ""
@@ -186,7 +186,8 @@ def test_loader_quirks(host, tmp_path):
         assert pos.reshape(2, 3, 3)[1].tolist() == [[0, 0, 0], [1, 1, 0], [0, 1, 0]]
         assert np.allclose(nrm.reshape(-1, 3), [0, 0, 1]) and uv.reshape(2, 3, 2)[1].tolist() == [[0.25, 0.75], [0.25, 0.75], [1, 1]]
         name, v = material(host, h, 0)
-        assert v[3:6].tolist() == [1, 0, 0] and int(v[14]) == 4
+        assert v[3:6].tolist() == [1, 0, 0] and int(v[14]) == 4         # "shader 4e1" is read with %d
+        assert int(material(host, h, 2)[1][14]) == 3                    # an indented "newmtl" starts nothing; "shader x" keeps, "shader 3.9" reads 3
     finally:
         host.pg1_free_scene(h)
     h = host.pg1_load_obj(str(tmp_path / "absent.obj").encode(), 0)
