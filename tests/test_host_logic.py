@@ -112,3 +112,26 @@ def test_byte_over_255_identity():
     e = (b.astype(np.float64) - q.astype(np.float64) * 255.0).astype(np.float32)
     q2 = (q.astype(np.float64) + e.astype(np.float64) * np.float64(r)).astype(np.float32)
     assert np.array_equal(q2, ref) and np.count_nonzero(q != ref) > 50
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys, the
+    BASELINE.json metric and unit, `impl: reference`, a cpu_baseline describing the run and an e2e object without copies."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c1", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    with open(os.path.join(root, "BASELINE.json")) as f:
+        base = json.load(f)
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+              "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["unit"] == "Mrays/s" and line["value"] > 0 and "workload" in line["config"]
+    if isinstance(base.get("unit"), str):
+        assert line["unit"] == base["unit"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
