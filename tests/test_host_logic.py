@@ -135,3 +135,18 @@ def test_bench_reference_arm_prints_the_contract_line():
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_and_smoke_fail_loudly_without_a_gpu():
+    """No silent CPU path: on a box without CUDA `bench.py` (our arm) exits non-zero with a message, and smoke() raises."""
+    import os, subprocess, sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this box has a GPU")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+    sys.path.insert(0, root)
+    import __graft_entry__ as g
+    with pytest.raises(Exception):
+        g.smoke()
