@@ -448,3 +448,18 @@ def test_loader_float_scan_equals_strtof_and_crlf(host, tmp_path):
             assert np.array_equal(pos.reshape(-1, 3).view(np.uint32), want[: pos.size // 3].view(np.uint32)), name
         finally:
             host.pg1_free_scene(h)
+
+
+def test_loader_flip_yz(host, tmp_path):
+    """flip_yz (pg1/objloader.cpp:311-316, :327-333): "x y z" is read as (x, -z, y) for positions and normals (normals are
+    normalised afterwards); texture coordinates are untouched."""
+    p = tmp_path / "f.obj"
+    p.write_text("v 1 2 3\nv 4 5 6\nv 7 8 10\nvn 0 3 4\nvt 0.25 0.5\ng a\nf 1/1/1 2/1/1 3/1/1\n")
+    for flip, want_pos, want_n in ((0, [1, 2, 3, 4, 5, 6, 7, 8, 10], [0, 0.6, 0.8]), (1, [1, -3, 2, 4, -6, 5, 7, -10, 8], [0, -0.8, 0.6])):
+        h = host.pg1_load_obj(str(p).encode(), flip)
+        try:
+            pos, nrm, uv = scene_arrays(host, h, 0)
+            assert pos.reshape(-1).tolist() == [float(x) for x in want_pos]
+            assert np.allclose(nrm.reshape(3, 3), want_n, atol=1e-7) and uv.reshape(3, 2).tolist() == [[0.25, 0.5]] * 3
+        finally:
+            host.pg1_free_scene(h)
