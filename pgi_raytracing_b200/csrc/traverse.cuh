@@ -111,6 +111,9 @@ struct RayCtxQ {                       // PGRT_LAYOUT_Q8
 // twin of a duplicated triangle) must still pass "entry <= best t", so that comparison gets an absolute slack of
 // 2^-21 max|O_i| * min|1/D_i| besides the relative one -- small for every ray, unlike the per-axis slab pads, which grow without
 // bound for a ray parallel to an axis and would switch off the culling by distance if they were used here.
+#ifndef PGRT_FAR_REL
+#define PGRT_FAR_REL 1.0000005f
+#endif
 PG_HD float ray_far_pad(V3 O, float idx, float idy, float idz) {
     return 4.7683716e-7f * fmaxf(fmaxf(fabsf(O.x), fabsf(O.y)), fabsf(O.z)) * fminf(fminf(fabsf(idx), fabsf(idy)), fabsf(idz));
 }
@@ -161,7 +164,7 @@ PG_HD uint32_t node_visit(const float4* __restrict__ nodes, uint32_t ni, const R
     const float4 f0 = pg_ldg4(nd), w0 = pg_ldg4(nd + 1), w1 = pg_ldg4(nd + 2);
     const float4 nx0 = pg_ldg4(nd + r.onx), ny0 = pg_ldg4(nd + r.ony), nz0 = pg_ldg4(nd + r.onz), fx0 = pg_ldg4(nd + r.ofx), fy0 = pg_ldg4(nd + r.ofy), fz0 = pg_ldg4(nd + r.ofz);
     const float4 nx1 = pg_ldg4(nd + r.onx + 1), ny1 = pg_ldg4(nd + r.ony + 1), nz1 = pg_ldg4(nd + r.onz + 1), fx1 = pg_ldg4(nd + r.ofx + 1), fy1 = pg_ldg4(nd + r.ofy + 1), fz1 = pg_ldg4(nd + r.ofz + 1);
-    const float far_pad = pg_fma(best_t, 1.0000005f, r.pad_far);
+    const float far_pad = pg_fma(best_t, PGRT_FAR_REL, r.pad_far);
     uint32_t hitmask = slab4f(w0, nx0, ny0, nz0, fx0, fy0, fz0, r.idx, r.idy, r.idz, r.nxo, r.nyo, r.nzo, r.fxo, r.fyo, r.fzo, r.tnear, far_pad);
     hitmask |= slab4f(w1, nx1, ny1, nz1, fx1, fy1, fz1, r.idx, r.idy, r.idz, r.nxo, r.nyo, r.nzo, r.fxo, r.fyo, r.fzo, r.tnear, far_pad);
     uint32_t x;
@@ -182,7 +185,7 @@ PG_HD uint32_t node_visit(const float4* __restrict__ nodes, uint32_t ni, const R
     // |origin * idir| <= |O * idir| + |a|: pad = 2^-22 of both
     const float pdx = pg_fma(2.3841858e-7f, fabsf(ax), r.pox), pdy = pg_fma(2.3841858e-7f, fabsf(ay), r.poy), pdz = pg_fma(2.3841858e-7f, fabsf(az), r.poz);
     const float axn = ax - pdx, ayn = ay - pdy, azn = az - pdz, axf = ax + pdx, ayf = ay + pdy, azf = az + pdz;
-    const float far_pad = pg_fma(best_t, 1.0000005f, r.pad_far);
+    const float far_pad = pg_fma(best_t, PGRT_FAR_REL, r.pad_far);
     const uint32_t lox0 = pg_f2u(n2.x), lox1 = pg_f2u(n2.y), loy0 = pg_f2u(n2.z), loy1 = pg_f2u(n2.w);
     const uint32_t loz0 = pg_f2u(n3.x), loz1 = pg_f2u(n3.y), hix0 = pg_f2u(n3.z), hix1 = pg_f2u(n3.w);
     const uint32_t hiy0 = pg_f2u(n4.x), hiy1 = pg_f2u(n4.y), hiz0 = pg_f2u(n4.z), hiz1 = pg_f2u(n4.w);
