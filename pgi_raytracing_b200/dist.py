@@ -154,6 +154,16 @@ def share_host_frames(raytracer, n_frames: int, rank: int, device, group=None):
     flag = torch.tensor([ok], dtype=torch.int32, device=device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)     # also: everybody has opened the memfd before rank 0 may close it
     if int(flag.item()) != 1:
+        # some rank could not map or register the frames: undo what this one did and let the caller fall back
+        if dev_base:
+            try:
+                raytracer.host_frame_unregister(base)
+            except Exception:
+                pass
+        if mm is not None:
+            mm.close()
+        if fd >= 0:
+            os.close(fd)
         return None, None, None
     views = None
     if rank == 0:
