@@ -100,3 +100,35 @@ def test_shared_host_frames_world2():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+class _FailingRaytracer(_HostOnlyRaytracer):
+    def host_frame_register(self, host_ptr, nbytes):
+        raise RuntimeError("cudaHostRegister failed (simulated)")
+
+
+def _host_frames_failure_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rt = _FailingRaytracer(64, 16) if rank == 1 else _HostOnlyRaytracer(64, 16)
+    fds_before = len(os.listdir("/proc/self/fd"))
+    out = D.share_host_frames(rt, 2, rank, torch.device("cpu"))
+    q.put((rank, out == (None, None, None), len(os.listdir("/proc/self/fd")) <= fds_before, len(rt.registered)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shared_host_frames_fall_back_together_when_one_rank_fails():
+    """One rank cannot register the mapping: EVERY rank gets (None, None, None) (the caller then takes the NVLink / NCCL
+    path) and the rank that succeeded has unregistered its mapping and closed its descriptor."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_host_frames_failure_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=5) for _ in range(2))
+    assert got == [(0, True, True, 0), (1, True, True, 0)], got
