@@ -150,3 +150,24 @@ def test_bench_and_smoke_fail_loudly_without_a_gpu():
     import __graft_entry__ as g
     with pytest.raises(Exception):
         g.smoke()
+
+
+def test_tiling_properties_for_arbitrary_sizes():
+    """Property test (hypothesis): for any frame size and rank count the shards partition the frame, have the same padded
+    length on every rank, and tile -> gather order -> untile is the identity."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(w=st.integers(1, 300), h=st.integers(1, 200), n=st.integers(1, 9), seed=st.integers(0, 2 ** 31 - 1))
+    def prop(w, h, n, seed):
+        seen = np.zeros((h, w), np.int32)
+        for r in range(n):
+            x, y, valid = D.slot_pixels(w, h, r, n)
+            assert x.shape[0] == D.shard_pixels(w, h, n) and x.shape[0] % 256 == 0
+            np.add.at(seen, (y[valid], x[valid]), 1)
+        assert np.all(seen == 1)
+        frame = np.random.default_rng(seed).random((h, w, 4)).astype(np.float32)
+        g = np.concatenate([D.tile_numpy(frame, r, n) for r in range(n)])
+        assert np.array_equal(D.untile_numpy(g, w, h, n), frame)
+
+    prop()
