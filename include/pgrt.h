@@ -64,7 +64,7 @@ typedef struct pgrt_render_params {
                                  3 path tracing (README.md:21 "To do"; no reference counterpart): dielectrics as in 0, every other
                                    hit = its Phong value + albedo x the radiance of one cosine-weighted bounce (the environment
                                    map lights the scene); converge with pgrt_render_accumulate.  Bounces count as reflection rays. */
-    int32_t scheduler;        /* 0 dynamic: one persistent kernel owns every ray of level >= 1 (default);
+    int32_t scheduler;        /* 0 fused: one persistent kernel runs trace() for every sample, secondary rays in a shared pool (default);
                                  1 level-synchronous wavefront (one queue per recursion level).  Same image, bit for bit. */
     int32_t shadow_mode;      /* 0 is_illuminated as shipped (shadow rays that leave the light towards the hit POSITION,
                                  raytracer.cpp:150-176, LightSource.cpp:11-32: the parity contract); 1 the hard shadows of the
@@ -162,6 +162,10 @@ void pgrt_default_params(pgrt_render_params* p);
  *      bit 1 runs the instrumented traversal that counts nodes / triangles per query (slower; same image). */
 int pgrt_render(pgrt_context* ctx, const pgrt_render_params* p, float* rgba_host, pgrt_render_stats* stats, int32_t profile);
 int pgrt_render_device(pgrt_context* ctx, const pgrt_render_params* p, void* rgba_device, pgrt_render_stats* stats, int32_t profile);
+/* the same frame as R8G8B8A8_UNORM, the format the reference's swap chain presents (simpleguidx11.cpp:229; the float texture is
+ * converted on the way to the back buffer, :290): byte = round(clamp(c,0,1)*255), NaN -> 0; pixel (x,y) at (y*width+x)*4, a = 255.
+ * A quarter of the bytes of the float frame when the frame has to reach host memory. */
+int pgrt_render_rgba8(pgrt_context* ctx, const pgrt_render_params* p, uint8_t* rgba8_host, pgrt_render_stats* stats, int32_t profile);
 /* ---- pipelined frames.  Producer renders frames forever (simpleguidx11.cpp:95-125); a context can keep up to
  *      PGRT_MAX_INFLIGHT of them in flight, each in its own slot (own CUDA stream, queues and counters), so that the
  *      latency-bound tail of one frame and its device->host copy overlap the next frame's primary rays.
@@ -190,9 +194,21 @@ int pgrt_host_frame_register(pgrt_context* ctx, void* host, uint64_t bytes, void
 int pgrt_host_frame_unregister(pgrt_context* ctx, void* host);
 int pgrt_enable_peer_access(pgrt_context* ctx, int32_t peer_device);   /* let this context's kernels store into memory of `peer_device` */
 int pgrt_render_shard_to_frame_begin(pgrt_context* ctx, const pgrt_render_params* p, void* frame_device, int32_t slot, int32_t profile);
+int pgrt_render_rgba8_begin(pgrt_context* ctx, const pgrt_render_params* p, uint8_t* rgba8_host, int32_t slot, int32_t profile);   /* pgrt_render_rgba8, pipelined */
+int pgrt_render_shard_to_frame_rgba8_begin(pgrt_context* ctx, const pgrt_render_params* p, void* frame_rgba8_device, int32_t slot, int32_t profile);
 int pgrt_render_end(pgrt_context* ctx, int32_t slot, pgrt_render_stats* stats);
 void* pgrt_slot_stream(pgrt_context* ctx, int32_t slot);                          /* cudaStream_t of a slot (slot 0 = pgrt_set_stream's) */
-int pgrt_stream_wait_slot(pgrt_context* ctx, int32_t slot, void* cuda_stream);    /* make `cuda_stream` wait for the slot's frame        */
+/* make `cuda_stream` wait for the frames begun on the slot so far.  The wait is on the slot's completion count, which only a
+ * frame that finished WITHOUT a secondary-ray queue overflow advances: a consumer ordered here is never released by an attempt
+ * that pgrt_render_end is still going to repeat with larger queues. */
+int pgrt_stream_wait_slot(pgrt_context* ctx, int32_t slot, void* cuda_stream);
+/* completion flags between the processes of one box, replacing a per-frame collective: the frames begun on `slot` from now on
+ * store `value` in *flag_device (own memory, a peer-mapped word, registered host memory) when they finish without a queue
+ * overflow; pgrt_stream_wait_value32 makes a stream wait until *flag_device >= value (cuStreamWaitValue32),
+ * pgrt_stream_write_value32 stores a value in stream order (the "frame consumed" signal in the other direction). */
+int pgrt_slot_signal(pgrt_context* ctx, int32_t slot, void* flag_device, uint32_t value);
+int pgrt_stream_wait_value32(pgrt_context* ctx, void* cuda_stream, void* flag_device, uint32_t value);
+int pgrt_stream_write_value32(pgrt_context* ctx, void* cuda_stream, void* flag_device, uint32_t value);
 /* cross-frame accumulation (the step after the path; the reference's Producer re-renders from scratch every iteration,
  * simpleguidx11.cpp:95-118): n_frames finished frames with seeds p->seed, p->seed + 1, ... are summed on the device in
  * frame order (float) and divided by n_frames; rgba_host as pgrt_render.  stats = totals over the frames. */

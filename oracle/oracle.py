@@ -34,7 +34,7 @@ class OrcLight(C.Structure):
 class OrcParams(C.Structure):
     _fields_ = [("sampling_width", C.c_int32), ("jitter", C.c_int32), ("focal_distance", C.c_float), ("aperture", C.c_float),
                 ("max_depth", C.c_int32), ("gamma_level", C.c_float), ("seed", C.c_uint32), ("camera_mode", C.c_int32),
-                ("shader_mode", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("shader_mode", C.c_int32), ("shadow_mode", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 class OrcStats(C.Structure):
@@ -66,10 +66,10 @@ def _p(a, t=C.c_void_p):
 
 
 def make_params(sampling_width=3, jitter=1, focal_distance=200.0, aperture=5.0, max_depth=7, gamma_level=0.5, seed=1,
-                camera_mode=0, shader_mode=0) -> dict:
+                camera_mode=0, shader_mode=0, shadow_mode=0) -> dict:
     """Defaults = the values hard-coded in the reference (pg1/raytracer.cpp:398-400,282,450)."""
     return dict(sampling_width=sampling_width, jitter=jitter, focal_distance=focal_distance, aperture=aperture, max_depth=max_depth,
-                gamma_level=gamma_level, seed=seed, camera_mode=camera_mode, shader_mode=shader_mode)
+                gamma_level=gamma_level, seed=seed, camera_mode=camera_mode, shader_mode=shader_mode, shadow_mode=shadow_mode)
 
 
 class Oracle:
@@ -157,6 +157,26 @@ class Oracle:
         if rc:
             raise RuntimeError(f"orc_intersect failed: {rc}")
         return rh
+
+    def trace(self, params: dict, rays9: np.ndarray, level: int = 0, brute=False, threads=0) -> np.ndarray:
+        """``Raytracer::trace(ray, level)`` on caller-supplied rays [n, 9] = (org, tnear, dir, time, tfar) -> Color4f [n, 4]."""
+        rays9 = np.ascontiguousarray(rays9, np.float32); out = np.zeros((rays9.shape[0], 4), np.float32)
+        q = self._params(params)
+        rc = self.lib.orc_trace(self.h, C.byref(q), _p(rays9), C.c_uint64(rays9.shape[0]), int(level), _p(out), int(brute), int(threads))
+        if rc:
+            raise RuntimeError(f"orc_trace failed: {rc}")
+        return out
+
+    def is_illuminated(self, params: dict, light, hit, normal, brute=False) -> np.ndarray:
+        """``Raytracer::is_illuminated(light, hit_position, normal)`` per query -> bool [n]."""
+        hit = np.ascontiguousarray(np.asarray(hit, np.float32).reshape(-1, 3)); n = hit.shape[0]
+        light = np.ascontiguousarray(np.broadcast_to(np.asarray(light, np.float32).reshape(-1, 3), (n, 3)))
+        normal = np.ascontiguousarray(np.broadcast_to(np.asarray(normal, np.float32).reshape(-1, 3), (n, 3)))
+        out = np.zeros(n, np.int32); q = self._params(params)
+        rc = self.lib.orc_is_illuminated(self.h, C.byref(q), _p(light), _p(hit), _p(normal), C.c_uint64(n), _p(out), int(brute))
+        if rc:
+            raise RuntimeError(f"orc_is_illuminated failed: {rc}")
+        return out.astype(bool)
 
     def primary_rays(self, params: dict) -> np.ndarray:
         w = params["sampling_width"]

@@ -77,7 +77,9 @@ struct orc_params {
     int32_t camera_mode;     // 0 thin lens PinHoleCamera.cpp:65-105, 1 pinhole :31-63
     int32_t shader_mode;     // 0 Whitted (trace as shipped), 1 Lambert (diffuse term only), 2 normal shader (:274-280),
                              // 3 path tracing (README.md:21 to-do; spec in include/pgrt.h and path_bounce_direction below)
-    int32_t reserved[7];
+    int32_t shadow_mode;     // 0 is_illuminated as shipped (:150-176); 1 hard shadows (README.md:20 to-do; spec in include/pgrt.h):
+                             // hit point -> light, in units of that segment, t in (1e-3, 1]; the closest occluder decides
+    int32_t reserved[6];
 };
 struct orc_stats {
     uint64_t rays_primary, rays_shadow, rays_reflection, rays_refraction;
@@ -483,6 +485,16 @@ struct Tracer {
 
     bool is_illuminated(const orc_light& light, V3 hit_position, V3 normal) {           // :150-176
         const V3 lp = v3(light.position[0], light.position[1], light.position[2]);
+        if (p.shadow_mode == 1) {
+            // README "To do: hard shadows" (README.md:20), non-default, no reference code: the ray the reference meant to cast
+            const V3 to_light = v3(lp.x - hit_position.x, lp.y - hit_position.y, lp.z - hit_position.z);
+            if (dot(normal, to_light) < 0) return false;
+            Ray r = {hit_position.x, hit_position.y, hit_position.z, 1e-3f, to_light.x, to_light.y, to_light.z, 0.0f, 1.0f};
+            n_shadow++;
+            const Hit h = get_ray_hit(r);
+            if (h.tri != ORC_INVALID_ID) return material_of(h.tri).type == 4;
+            return true;
+        }
         if (dot(normal, lp) < 0) return false;
         // LightSource::GenerateRay, LightSource.cpp:11-32: dir = the hit POSITION (sic), not hit - light
         Ray r = {lp.x, lp.y, lp.z, 0.01f, hit_position.x, hit_position.y, hit_position.z, 0.0f,
@@ -768,6 +780,39 @@ int orc_render_region(void* h, const orc_params* p, int x0, int y0, int x1, int 
 int orc_render(void* h, const orc_params* p, float* rgba, uint32_t* geom, uint32_t* prim, orc_stats* stats, int brute, int threads) {
     Scene& s = *(Scene*)h;
     return orc_render_region(h, p, 0, 0, s.cam.width, s.cam.height, rgba, geom, prim, stats, brute, threads);
+}
+
+// Raytracer::trace (raytracer.cpp:237-394) on caller-supplied rays: in = 9 floats per ray (org, tnear, dir, time, tfar), out = Color4f
+int orc_trace(void* h, const orc_params* p, const float* rays9, uint64_t n, int level, float* out4, int brute, int threads) {
+    Scene& s = *(Scene*)h;
+    if (!s.committed && !brute) return 1;
+    (void)threads;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel for schedule(dynamic, 64)
+#endif
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+        FtzGuard g;
+        Tracer tr(s, *p, brute != 0);
+        const float* q = rays9 + 9 * i;
+        const Ray r = {q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8]};
+        const Color4 c = tr.trace(r, level);
+        out4[4 * i] = c.r; out4[4 * i + 1] = c.g; out4[4 * i + 2] = c.b; out4[4 * i + 3] = c.a;
+    }
+    return 0;
+}
+// Raytracer::is_illuminated (raytracer.cpp:150-176): light position, hit position, normal per query -> 0 / 1
+int orc_is_illuminated(void* h, const orc_params* p, const float* light3, const float* hit3, const float* nrm3, uint64_t n, int32_t* out, int brute) {
+    Scene& s = *(Scene*)h;
+    if (!s.committed && !brute) return 1;
+    FtzGuard g;
+    Tracer tr(s, *p, brute != 0);
+    for (uint64_t i = 0; i < n; ++i) {
+        orc_light l = {};
+        l.position[0] = light3[3 * i]; l.position[1] = light3[3 * i + 1]; l.position[2] = light3[3 * i + 2];
+        out[i] = tr.is_illuminated(l, v3(hit3[3 * i], hit3[3 * i + 1], hit3[3 * i + 2]), v3(nrm3[3 * i], nrm3[3 * i + 1], nrm3[3 * i + 2])) ? 1 : 0;
+    }
+    return 0;
 }
 
 // ---- per-function entry points (unit parity of each App. A quirk)

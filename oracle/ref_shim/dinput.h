@@ -1,0 +1,2 @@
+// dinput.h (shim): empty on purpose, see stdafx.h
+#pragma once

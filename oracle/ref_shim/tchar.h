@@ -1,0 +1,2 @@
+// tchar.h (shim): empty on purpose, see stdafx.h
+#pragma once

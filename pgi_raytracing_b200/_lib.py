@@ -85,6 +85,12 @@ SYMBOLS = {
     "pgrt_debug_flush_l2": (C.c_int, [_VP, _I32, _U64, _U32]),
     "pgrt_enable_peer_access": (C.c_int, [_VP, _I32]),
     "pgrt_render_shard_to_frame_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),
+    "pgrt_render_rgba8": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, C.POINTER(RenderStats), _I32]),
+    "pgrt_render_rgba8_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),
+    "pgrt_render_shard_to_frame_rgba8_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),
+    "pgrt_slot_signal": (C.c_int, [_VP, _I32, _VP, _U32]),
+    "pgrt_stream_wait_value32": (C.c_int, [_VP, _VP, _VP, _U32]),
+    "pgrt_stream_write_value32": (C.c_int, [_VP, _VP, _VP, _U32]),
     "pgrt_render_end": (C.c_int, [_VP, _I32, C.POINTER(RenderStats)]),
     "pgrt_slot_stream": (_VP, [_VP, _I32]),
     "pgrt_stream_wait_slot": (C.c_int, [_VP, _I32, _VP]),

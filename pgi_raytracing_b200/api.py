@@ -121,7 +121,8 @@ class Raytracer:
         d = dict(primary=rs.rays_primary, shadow=rs.rays_shadow, reflection=rs.rays_reflection, refraction=rs.rays_refraction,
                  frame_ms=rs.frame_ms, trace_ms=rs.trace_ms, shade_ms=rs.shade_ms, trace_launches=rs.trace_launches,
                  launches=rs.launches, batches=rs.batches, overflow_retries=rs.overflow_retries,
-                 nodes_visited=rs.nodes_visited, tris_tested=rs.tris_tested, max_nodes_per_ray=rs.max_nodes_per_ray)
+                 nodes_visited=rs.nodes_visited, tris_tested=rs.tris_tested, max_nodes_per_ray=rs.max_nodes_per_ray,
+                 pool_peak=rs.reserved[0])
         d["total"] = d["primary"] + d["shadow"] + d["reflection"] + d["refraction"]
         return d
 
@@ -133,6 +134,17 @@ class Raytracer:
         assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == self.width * self.height * 4
         rs = L.RenderStats()
         self._check(self.lib.pgrt_render(self.h, C.byref(p), _ptr(out), C.byref(rs), int(profile)))
+        return out, self._stats(rs)
+
+    def render_rgba8(self, params=None, out: np.ndarray | None = None, profile: bool = False):
+        """The same frame as R8G8B8A8_UNORM [H,W,4] uint8 (``pgrt_render_rgba8``): what the reference's swap chain shows
+        (pg1/simpleguidx11.cpp:229,290)."""
+        p = self._params(params)
+        if out is None:
+            out = np.empty((self.height, self.width, 4), np.uint8)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.size == self.width * self.height * 4
+        rs = L.RenderStats()
+        self._check(self.lib.pgrt_render_rgba8(self.h, C.byref(p), _ptr(out), C.byref(rs), int(profile)))
         return out, self._stats(rs)
 
     def render_accumulate(self, n_frames: int, params=None, out: np.ndarray | None = None):
@@ -158,11 +170,16 @@ class Raytracer:
 
     # ---- pipelined frames (pgrt_render*_begin / pgrt_render_end): up to MAX_INFLIGHT frames in flight
     def render_begin(self, slot: int, params=None, *, host_ptr: int = 0, device_ptr: int = 0, shard_ptr: int = 0, frame_ptr: int = 0,
-                     profile: int = 0):
+                     profile: int = 0, rgba8: bool = False):
         """Enqueue one frame in ``slot`` and return without waiting for the GPU.  Exactly one destination
-        (``frame_ptr``: sharded context, tiles stored at their final place of a possibly peer-mapped full frame)."""
+        (``frame_ptr``: sharded context, tiles stored at their final place of a possibly peer-mapped full frame).
+        ``rgba8``: the destination (``host_ptr`` or ``frame_ptr``) is an R8G8B8A8_UNORM frame."""
         p = self._params(params)
-        if frame_ptr:
+        if rgba8 and frame_ptr:
+            rc = self.lib.pgrt_render_shard_to_frame_rgba8_begin(self.h, C.byref(p), C.c_void_p(frame_ptr), slot, int(profile))
+        elif rgba8:
+            rc = self.lib.pgrt_render_rgba8_begin(self.h, C.byref(p), C.c_void_p(host_ptr), slot, int(profile))
+        elif frame_ptr:
             rc = self.lib.pgrt_render_shard_to_frame_begin(self.h, C.byref(p), C.c_void_p(frame_ptr), slot, int(profile))
         elif host_ptr:
             rc = self.lib.pgrt_render_begin(self.h, C.byref(p), C.c_void_p(host_ptr), slot, int(profile))
@@ -220,6 +237,16 @@ class Raytracer:
 
     def stream_wait_slot(self, slot: int, cuda_stream_ptr: int):
         self._check(self.lib.pgrt_stream_wait_slot(self.h, slot, C.c_void_p(cuda_stream_ptr)))
+
+    def slot_signal(self, slot: int, flag_ptr: int, value: int):
+        """Frames begun on ``slot`` from now on store ``value`` in ``*flag_ptr`` when they finish (``pgrt_slot_signal``)."""
+        self._check(self.lib.pgrt_slot_signal(self.h, slot, C.c_void_p(flag_ptr), value))
+
+    def stream_wait_value32(self, cuda_stream_ptr: int, flag_ptr: int, value: int):
+        self._check(self.lib.pgrt_stream_wait_value32(self.h, C.c_void_p(cuda_stream_ptr), C.c_void_p(flag_ptr), value))
+
+    def stream_write_value32(self, cuda_stream_ptr: int, flag_ptr: int, value: int):
+        self._check(self.lib.pgrt_stream_write_value32(self.h, C.c_void_p(cuda_stream_ptr), C.c_void_p(flag_ptr), value))
 
     def get_pixel(self, x: int, y: int, t: float = 0.0, params=None):
         """``Color4f get_pixel(x, y, t)`` (pg1/raytracer.cpp:396-437); ``t`` is ignored, as in the reference."""

@@ -38,8 +38,8 @@ struct FrameSlot {
     DevBuf<uint2> lv_child[PGRT_MAX_LEVELS + 1];
     DevBuf<uint32_t> lv_list[PGRT_MAX_LEVELS + 1][2];
     DevBuf<uint32_t> l0_pending;
-    RayPool pool = {};                // every ray of level >= 1 (dynamic scheduler)
-    DevBuf<float4> pool_f4[4]; DevBuf<uint2> pool_u2[2]; DevBuf<uint32_t> pool_u32[1];
+    RayPool pool = {};                // every ray of level >= 1 (fused scheduler)
+    DevBuf<float4> pool_f4[4]; DevBuf<uint2> pool_u2[1]; DevBuf<uint4> pool_u4[1]; DevBuf<uint32_t> pool_u32[1];
     DevBuf<Counters> d_counters;
     DevBuf<float4> d_frame;           // device frame behind a host destination
     Counters* h_counters = nullptr;   // pinned
@@ -47,12 +47,14 @@ struct FrameSlot {
     std::vector<int> ev_class, ev_level;
     size_t ev_used = 0;
     cudaEvent_t ev_frame0 = nullptr, ev_frame1 = nullptr, ev_done = nullptr;
-    int secondary_grid = 0;           // CTAs of this frame's k_secondary (sized in frame_begin)
+    int frame_grid = 0;               // CTAs of this frame's k_frame (sized in frame_begin)
     // the frame in flight
     bool busy = false;
     pgrt_render_params params = {};
-    float4* dest = nullptr; int dest_mode = 0; float* host_dst = nullptr; int profile = 0;
-    uint64_t batch_slots = 0; int n_levels = 0; bool dyn = false;
+    void* dest = nullptr; int dest_mode = 0; int fmt = 0; void* host_dst = nullptr; int profile = 0;   // fmt: 0 float4, 1 R8G8B8A8_UNORM
+    uint32_t* sig_flag = nullptr; uint32_t sig_value = 0;   // external completion flag (pgrt_slot_signal)
+    uint32_t seq_expected = 0;        // frames begun on this slot = value of Counters::done_seq once the last of them has finished
+    uint64_t batch_slots = 0; int n_levels = 0; bool fused = false;
     pgrt_render_stats rs = {};
     // the frame as a CUDA graph (re-used while nothing it depends on changes)
     cudaGraphExec_t gexec = nullptr; uint64_t gkey = 0, gseen = 0; uint32_t g_launches = 0, g_trace_launches = 0, g_batches = 0;
@@ -64,7 +66,7 @@ struct FrameSlot {
             lv_child[l].release(); lv_list[l][0].release(); lv_list[l][1].release();
         }
         l0_pending.release();
-        for (auto& b : pool_f4) b.release(); for (auto& b : pool_u2) b.release(); for (auto& b : pool_u32) b.release();
+        for (auto& b : pool_f4) b.release(); for (auto& b : pool_u2) b.release(); for (auto& b : pool_u4) b.release(); for (auto& b : pool_u32) b.release();
         d_counters.release(); d_frame.release();
         for (auto e : ev_pool) cudaEventDestroy(e);
         ev_pool.clear();
@@ -118,7 +120,11 @@ struct pgrt_context {
     // frame state: PGRT_MAX_INFLIGHT independent frame slots, each with its own stream, queues and counters, so the
     // latency-bound tail of one frame (k_secondary) and its device->host copy overlap the next frame's primary work
     FrameSlot slots[PGRT_MAX_INFLIGHT];
-    int secondary_per_sm_max = 0, secondary_per_sm_env = 0;   // occupancy bound of k_secondary; PGRT_SECONDARY_CTAS_PER_SM
+    int frame_per_sm_max = 0, frame_per_sm_env = 0;   // occupancy bound of k_frame; PGRT_FRAME_CTAS_PER_SM
+    int min_claim = 32;               // k_frame takes pool records ahead of primary rays once this many wait (PGRT_MIN_CLAIM, 1..32)
+    double pool_scale = 1.0;          // grown after a pool overflow; never shrinks before the next pgrt_commit
+    // driver entry points for stream memory operations (completion flags without a collective); null = not available
+    void* fn_wait32 = nullptr; void* fn_write32 = nullptr;
     bool fuse_raygen = true;          // PGRT_FUSE_RAYGEN=0 restores the stored level-0 ray queue (k_raygen)
     bool use_graphs = true;           // PGRT_GRAPHS=0: every frame as individual launches
     int trace_refill = 32;            // k_trace claims new rays once this many lanes of a warp are idle (PGRT_TRACE_REFILL, 1..32); 32 = whole-warp chunks, the fastest for coherent primary rays (profiles/r1_sweep_trace_refill.txt)
@@ -180,6 +186,7 @@ extern "C" int pgrt_create(pgrt_context** out, int device) {
         ok = ok && cudaEventCreate(&S.ev_frame0) == cudaSuccess && cudaEventCreate(&S.ev_frame1) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaMallocHost((void**)&S.h_counters, sizeof(Counters)) == cudaSuccess && S.d_counters.ensure(1) == cudaSuccess;
+        ok = ok && cudaMemset(S.d_counters.p, 0, sizeof(Counters)) == cudaSuccess;
         if (!ok) { pgrt_destroy(ctx); return PGRT_ERR_CUDA; }
     }
     ctx->stream = ctx->slots[0].stream;
@@ -188,6 +195,13 @@ extern "C" int pgrt_create(pgrt_context** out, int device) {
     if (const char* e = getenv("PGRT_GRAPHS")) ctx->use_graphs = atoi(e) != 0;
     if (const char* e = getenv("PGRT_TRACE_REFILL")) ctx->trace_refill = std::min(32, std::max(1, atoi(e)));
     if (const char* e = getenv("PGRT_TRACE_CTAS_PER_SM")) ctx->trace_ctas_per_sm = std::min(16, std::max(1, atoi(e)));
+    if (const char* e = getenv("PGRT_MIN_CLAIM")) ctx->min_claim = std::min(32, std::max(1, atoi(e)));
+    {   // cuStreamWaitValue32 / cuStreamWriteValue32 through the runtime (no link-time dependency on libcuda)
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &ctx->fn_wait32, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) ctx->fn_wait32 = nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &ctx->fn_write32, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) ctx->fn_write32 = nullptr;
+        cudaGetLastError();
+    }
     if (const char* e = getenv("PGRT_MAX_BATCH_SAMPLES")) ctx->max_batch_samples = std::max<size_t>(256, strtoull(e, nullptr, 10));
     if (const char* e = getenv("PGRT_MIN_LEVEL_CAP")) ctx->min_level_cap = std::max<size_t>(64, strtoull(e, nullptr, 10));
     if (const char* e = getenv("PGRT_LEVEL_CAP_FACTOR")) ctx->level_cap_factor = std::max(0.01, atof(e));
@@ -379,7 +393,7 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
     sync_all_slots(ctx);
     cudaStream_t st = ctx->stream;
     const uint32_t N = ctx->n_added;   // the geometry is on the device already (pgrt_add_mesh streams it)
-    ctx->n_tris = N; ctx->px_valid = false; ctx->batch_limit = 0;
+    ctx->n_tris = N; ctx->px_valid = false; ctx->batch_limit = 0; ctx->pool_scale = 1.0;
     pgrt_build_stats bs = {}; bs.triangles = N;
     const uint32_t G = (uint32_t)ctx->h_geom_first.size();
     CUDA_TRY(ctx->d_geom_first.ensure(G)); CUDA_TRY(ctx->d_geom_material.ensure(G));
@@ -588,18 +602,25 @@ static int ensure_pool(pgrt_context* ctx, FrameSlot& S, size_t cap) {
     for (auto& b : S.pool_f4) CUDA_TRY(b.ensure(cap));
     for (auto& b : S.pool_u2) CUDA_TRY(b.ensure(cap));
     for (auto& b : S.pool_u32) CUDA_TRY(b.ensure(cap));
+    if (cap > S.pool_u4[0].n) {
+        // the link array carries the publication words: fresh memory must not look like a record of a recent batch
+        CUDA_TRY(S.pool_u4[0].ensure(cap));
+        CUDA_TRY(cudaMemsetAsync(S.pool_u4[0].p, 0, S.pool_u4[0].n * sizeof(uint4), S.stream));
+    }
     RayPool& P = S.pool;
     P.ray_o = S.pool_f4[0].p; P.ray_d = S.pool_f4[1].p; P.color = S.pool_f4[2].p; P.att = S.pool_f4[3].p;
-    P.child = S.pool_u2[0].p; P.link = S.pool_u2[1].p; P.pending = S.pool_u32[0].p;
-    P.cap = (uint32_t)cap;
+    P.child = S.pool_u2[0].p; P.link = S.pool_u4[0].p; P.pending = S.pool_u32[0].p;
+    P.cap = (uint32_t)std::min<size_t>(cap, 0xFFFFFFF0u);
     return PGRT_OK;
 }
 
-static int ensure_levels(pgrt_context* ctx, FrameSlot& S, int n_levels, size_t cap0, size_t capn) {
+static int ensure_levels(pgrt_context* ctx, FrameSlot& S, int n_levels, size_t cap0, size_t capn, bool fused) {
     for (int l = 0; l <= n_levels; ++l) {   // one spare level so k_shade always has a (never written) "next"
         const size_t cap = l == 0 ? cap0 : (l == n_levels ? 1 : capn);
-        for (int k = 0; k < 5; ++k) CUDA_TRY(S.lv_f4[l][k].ensure(cap));
-        CUDA_TRY(S.lv_child[l].ensure(cap)); CUDA_TRY(S.lv_list[l][0].ensure(cap)); CUDA_TRY(S.lv_list[l][1].ensure(cap));
+        // the fused scheduler keeps rays and hits in registers: level 0 holds colours and dielectric nodes only
+        for (int k = 0; k < 5; ++k) if (!fused || k >= 3) CUDA_TRY(S.lv_f4[l][k].ensure(cap));
+        CUDA_TRY(S.lv_child[l].ensure(cap));
+        if (!fused) { CUDA_TRY(S.lv_list[l][0].ensure(cap)); CUDA_TRY(S.lv_list[l][1].ensure(cap)); }
         LevelBufs& L = S.levels[l];
         L.ray_o = S.lv_f4[l][0].p; L.ray_d = S.lv_f4[l][1].p; L.hit = S.lv_f4[l][2].p; L.color = S.lv_f4[l][3].p; L.dn_att = S.lv_f4[l][4].p;
         L.dn_child = S.lv_child[l].p; L.phong_list = S.lv_list[l][0].p; L.diel_list = S.lv_list[l][1].p;
@@ -637,20 +658,20 @@ static int validate_frame(pgrt_context* ctx, const pgrt_render_params* p) {
     return upload_tables(ctx);
 }
 
-// Enqueues one frame on the slot's stream: every launch, the read-back of the counters and (host destinations) of the
-// frame itself.  Nothing here waits for the GPU once the slot's buffers exist.
-// dest_mode: 0 = full frame (W*H float4), 1 = compact shard buffer, 2 = ids only (geom/prim in d_ids)
+// dest_mode: 0 = full frame (W*H pixels), 1 = compact shard buffer, 2 = ids only (geom/prim in d_ids);  fmt: 0 float4, 1 RGBA8
+static size_t pixel_bytes(const FrameSlot& S) { return S.fmt == 1 ? 4 : 16; }
+
 static int prepare_frame(pgrt_context* ctx, FrameSlot& S) {
     const int SPP = S.params.sampling_width * S.params.sampling_width;
     const size_t cap0 = (size_t)S.batch_slots * SPP;
     // deeper levels: Whitted spawns rays at dielectric hits only (a fraction of the samples); the path-tracing mode spawns
-    // one at every hit of every level, so its queues are sized for a full level each
+    // one at every hit of every level, so its queues are sized for a full level each.  pool_scale grows after an overflow.
     const bool path = S.params.shader_mode == 3;
-    const size_t capn = std::max<size_t>(ctx->min_level_cap, (size_t)((path ? std::max(1.0, ctx->level_cap_factor) : ctx->level_cap_factor) * (double)cap0));
-    int rc = ensure_levels(ctx, S, S.dyn ? 1 : S.n_levels, cap0, capn);
+    const size_t capn = std::max<size_t>(ctx->min_level_cap, (size_t)((path ? std::max(1.0, ctx->level_cap_factor) : ctx->level_cap_factor) * ctx->pool_scale * (double)cap0));
+    int rc = ensure_levels(ctx, S, S.fused ? 1 : S.n_levels, cap0, capn, S.fused);
     if (rc) return rc;
-    if (S.dyn) { rc = ensure_pool(ctx, S, capn * (size_t)std::min(S.n_levels - 1, path ? 8 : 4)); if (rc) return rc; }   // one pool replaces the per-level queues
-    if (S.host_dst) CUDA_TRY(S.d_frame.ensure((size_t)ctx->cam.width * ctx->cam.height));
+    if (S.fused) { rc = ensure_pool(ctx, S, capn * (size_t)std::min(S.n_levels - 1, path ? 8 : 4)); if (rc) return rc; }   // one pool replaces the per-level queues
+    if (S.host_dst) CUDA_TRY(S.d_frame.ensure(((size_t)ctx->cam.width * ctx->cam.height * pixel_bytes(S) + 15) / 16));
     return PGRT_OK;
 }
 
@@ -659,64 +680,48 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
     cudaStream_t st = S.stream;
     const pgrt_render_params* p = &S.params;
     const int dest_mode = S.dest_mode, profile = S.profile;
-    float4* dest = S.dest;
     const int SPP = p->sampling_width * p->sampling_width;
     const int n_levels = S.n_levels;
     const uint64_t total_slots = shard_slots(ctx);
     const uint64_t batch_slots = S.batch_slots;
     const DevScene sc = ctx->dev_scene();
     const unsigned trace_grid = ctx->sm_count * ctx->trace_ctas_per_sm, phong_grid = ctx->sm_count * 16, shade_grid = ctx->sm_count * 8;
-    const bool dyn = S.dyn;
+    const bool fused = S.fused;
     FrameTimer tm{&S, (profile & 1) != 0};
     const bool count = (profile & 2) != 0;
-    const bool path = p->shader_mode == 3;   // path-tracing instantiations of k_shade / k_secondary / k_combine
+    const bool path = p->shader_mode == 3;   // path-tracing instantiations of k_shade / k_frame / k_combine
     pgrt_render_stats& rs = S.rs;
     S.ev_used = 0; rs.launches = 0; rs.trace_launches = 0; rs.batches = 0;
     Counters* cnt = S.d_counters.p;
-    k_frame_begin<<<1, 64, 0, st>>>(cnt); rs.launches++;
+    FrameOut fo = {};
+    void* out = S.host_dst ? (void*)S.d_frame.p : S.dest;
+    if (S.fmt == 1) fo.rgba8 = (uint32_t*)out; else fo.rgba = (float4*)out;
+    fo.compact = dest_mode == 1; fo.direct = (fused && SPP == 1) ? 1 : 0;
     for (uint64_t slot0 = 0; slot0 < total_slots; slot0 += batch_slots) {
         const uint32_t n_slots = (uint32_t)std::min<uint64_t>(batch_slots, total_slots - slot0);
         const uint32_t n0 = n_slots * (uint32_t)SPP;
+        const bool first = slot0 == 0, last = slot0 + batch_slots >= total_slots;
         rs.batches++;
-        k_batch_begin<<<1, 64, 0, st>>>(cnt, n0); rs.launches++;
-        Gen0 g0; g0.cam = ctx->cam; g0.sh = ctx->shard; g0.slot0 = (uint32_t)slot0; g0.n_slots = n_slots; g0.spp = SPP; g0.on = ctx->fuse_raygen ? 1 : 0;
+        k_batch_begin<<<1, 64, 0, st>>>(cnt, n0, first ? 1 : 0); rs.launches++;
+        Gen0 g0; g0.cam = ctx->cam; g0.sh = ctx->shard; g0.slot0 = (uint32_t)slot0; g0.n_slots = n_slots; g0.spp = SPP; g0.on = (fused || ctx->fuse_raygen) ? 1 : 0;
         Gen0 gN = g0; gN.on = 0;
-        if (!g0.on) {
-            tm.begin(KC_SHADE);
-            k_raygen<<<div_up(n0, 256), 256, 0, st>>>(ctx->cam, *p, ctx->shard, (uint32_t)slot0, n_slots, S.levels[0], cnt); rs.launches++;
-            tm.end();
-        }
-        if (dyn) {
-            // level 0 as a wavefront (coherent primary rays), every deeper level inside the persistent kernel
-            const RayPool P = S.pool;
-            LevelBufs Ln = {}; Ln.ray_o = P.ray_o; Ln.ray_d = P.ray_d; Ln.cap = P.cap;
+        if (fused) {
             tm.begin(KC_TRACE, 0);
-            if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], 0, ctx->trace_refill, cnt);
-            else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], 0, ctx->trace_refill, cnt);
-            rs.launches++; rs.trace_launches++;
-            tm.end();
-            tm.begin(KC_SHADE, 0);
-            if (path) k_shade<true><<<shade_grid, 256, 0, st>>>(sc, *p, g0, 0, S.levels[0], Ln, P, 1, cnt);
-            else k_shade<false><<<shade_grid, 256, 0, st>>>(sc, *p, g0, 0, S.levels[0], Ln, P, 1, cnt);
-            rs.launches++;
-            tm.end();
-            tm.begin(KC_TRACE, 0);
-            if (count) k_phong<true><<<phong_grid, 128, 0, st>>>(sc, *p, g0, 0, S.levels[0], cnt);
-            else k_phong<false><<<phong_grid, 128, 0, st>>>(sc, *p, g0, 0, S.levels[0], cnt);
-            rs.launches++; rs.trace_launches++;
-            tm.end();
-            tm.begin(KC_TRACE, 1);
-            const size_t smem = (size_t)4 * p->max_depth * (PGRT_WSTACK + 1) * sizeof(uint32_t);   // <= 33.3 KB at max_depth 32
             if (path) {
-                if (count) k_secondary<true, true><<<S.secondary_grid, 128, smem, st>>>(sc, *p, S.levels[0], P, cnt);
-                else k_secondary<false, true><<<S.secondary_grid, 128, smem, st>>>(sc, *p, S.levels[0], P, cnt);
+                if (count) k_frame<true, true><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, cnt);
+                else k_frame<false, true><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, cnt);
             } else {
-                if (count) k_secondary<true, false><<<S.secondary_grid, 128, smem, st>>>(sc, *p, S.levels[0], P, cnt);
-                else k_secondary<false, false><<<S.secondary_grid, 128, smem, st>>>(sc, *p, S.levels[0], P, cnt);
+                if (count) k_frame<true, false><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, cnt);
+                else k_frame<false, false><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, cnt);
             }
             rs.launches++; rs.trace_launches++;
             tm.end();
         } else {
+            if (!g0.on) {
+                tm.begin(KC_SHADE);
+                k_raygen<<<div_up(n0, 256), 256, 0, st>>>(ctx->cam, *p, ctx->shard, (uint32_t)slot0, n_slots, S.levels[0], cnt); rs.launches++;
+                tm.end();
+            }
             for (int l = 0; l < n_levels; ++l) {
                 tm.begin(KC_TRACE, l);
                 if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, S.levels[l], l, ctx->trace_refill, cnt);
@@ -725,8 +730,8 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
                 tm.end();
                 if (dest_mode == 2) break;
                 tm.begin(KC_SHADE, l);
-                if (path) k_shade<true><<<shade_grid, 256, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], S.levels[l + 1], S.pool, 0, cnt);
-                else k_shade<false><<<shade_grid, 256, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], S.levels[l + 1], S.pool, 0, cnt);
+                if (path) k_shade<true><<<shade_grid, 256, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], S.levels[l + 1], cnt);
+                else k_shade<false><<<shade_grid, 256, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], S.levels[l + 1], cnt);
                 rs.launches++;
                 tm.end();
                 tm.begin(KC_TRACE, l);   // Phong = shading preamble + one inline shadow traversal per light
@@ -739,14 +744,14 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
         if (dest_mode == 2) {
             uint32_t* geom = ctx->d_ids.p; uint32_t* prim = geom + (size_t)ctx->cam.width * ctx->cam.height;
             k_primary_ids<<<div_up(n_slots, 256), 256, 0, st>>>(sc, ctx->cam, ctx->shard, (uint32_t)slot0, n_slots, SPP, S.levels[0].hit, geom, prim); rs.launches++;
-        } else {
+        } else if (!fo.direct) {
             tm.begin(KC_SHADE);
-            if (!dyn) for (int l = n_levels - 2; l >= 0; --l) {
+            if (!fused) for (int l = n_levels - 2; l >= 0; --l) {
                 if (path) k_combine<true><<<shade_grid, 256, 0, st>>>(l, S.levels[l], S.levels[l + 1], cnt);
                 else k_combine<false><<<shade_grid, 256, 0, st>>>(l, S.levels[l], S.levels[l + 1], cnt);
                 rs.launches++;
             }
-            k_resolve<<<div_up(n_slots, 256), 256, 0, st>>>(ctx->cam, *p, ctx->shard, (uint32_t)slot0, n_slots, S.levels[0].color, S.host_dst ? S.d_frame.p : dest, dest_mode == 1); rs.launches++;
+            k_resolve<<<div_up(n_slots, 256), 256, 0, st>>>(ctx->cam, *p, ctx->shard, (uint32_t)slot0, n_slots, S.levels[0].color, fo); rs.launches++;
             tm.end();
         }
         unsigned long long valid_px;
@@ -762,11 +767,11 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
             }
             valid_px = v * SPP;
         }
-        k_batch_end<<<1, 64, 0, st>>>(cnt, valid_px, dyn ? 1 : 0); rs.launches++;
+        k_batch_end<<<1, 64, 0, st>>>(cnt, valid_px, fused ? 1 : 0, last ? 1 : 0, S.sig_flag); rs.launches++;
     }
     CUDA_TRY(cudaMemcpyAsync(S.h_counters, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     if (S.host_dst)   // the memcpy of simpleguidx11.cpp:121-124; overlaps the next frame when the destination is pinned
-        CUDA_TRY(cudaMemcpyAsync(S.host_dst, S.d_frame.p, (size_t)ctx->cam.width * ctx->cam.height * sizeof(float4), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(S.host_dst, S.d_frame.p, (size_t)ctx->cam.width * ctx->cam.height * pixel_bytes(S), cudaMemcpyDeviceToHost, st));
     LAUNCH_OK();
     return PGRT_OK;
 }
@@ -778,7 +783,7 @@ static uint64_t fnv1a(const void* data, size_t n, uint64_t h = 14695981039346656
 }
 
 // Everything the recorded launches depend on: a frame whose key equals the slot's cached one is re-submitted as ONE
-// cudaGraphLaunch instead of ~8 launches + copies (55 -> ~10 us of host time per frame; it matters once a GPU's share of
+// cudaGraphLaunch instead of its launches + copies (55 -> ~10 us of host time per frame; it matters once a GPU's share of
 // the frame is tens of microseconds, i.e. with many GPUs on a small frame).
 static uint64_t frame_key(pgrt_context* ctx, const FrameSlot& S) {
     const DevScene sc = ctx->dev_scene();
@@ -787,9 +792,9 @@ static uint64_t frame_key(pgrt_context* ctx, const FrameSlot& S) {
     h = fnv1a(&S.dest, sizeof S.dest, h); h = fnv1a(&S.host_dst, sizeof S.host_dst, h); h = fnv1a(&S.dest_mode, sizeof S.dest_mode, h);
     h = fnv1a(&S.batch_slots, sizeof S.batch_slots, h); h = fnv1a(&S.n_levels, sizeof S.n_levels, h);
     h = fnv1a(S.levels, sizeof(LevelBufs) * (size_t)(S.n_levels + 1), h); h = fnv1a(&S.pool, sizeof S.pool, h);
-    const void* extra[3] = {S.d_frame.p, S.d_counters.p, S.stream};
+    const void* extra[4] = {S.d_frame.p, S.d_counters.p, S.stream, S.sig_flag};
     h = fnv1a(extra, sizeof extra, h);
-    const int flags[5] = {S.dyn ? 1 : 0, ctx->fuse_raygen ? 1 : 0, S.secondary_grid, ctx->trace_refill, ctx->trace_ctas_per_sm};
+    const int flags[7] = {S.fused ? 1 : 0, ctx->fuse_raygen ? 1 : 0, S.frame_grid, ctx->trace_refill, ctx->trace_ctas_per_sm, S.fmt, ctx->min_claim};
     return fnv1a(flags, sizeof flags, h) | 1ull;
 }
 
@@ -799,12 +804,22 @@ static bool host_ptr_is_pinned(const void* p) {
     return a.type == cudaMemoryTypeHost;
 }
 
+typedef int (*pgrt_cu_memop32)(cudaStream_t, unsigned long long, uint32_t, unsigned int);   // CUresult cuStream{Wait,Write}Value32(CUstream, CUdeviceptr, cuuint32_t, unsigned)
+
+// stores `value` in a device-visible word, in stream order
+static int stream_write32(pgrt_context* ctx, cudaStream_t st, void* addr, uint32_t value) {
+    if (ctx->fn_write32 && ((pgrt_cu_memop32)ctx->fn_write32)(st, (unsigned long long)(uintptr_t)addr, value, 0u) == 0) return PGRT_OK;
+    CUDA_TRY(cudaMemcpyAsync(addr, &value, sizeof value, cudaMemcpyHostToDevice, st));   // pageable source: staged before the call returns
+    return PGRT_OK;
+}
+
 // Enqueues one frame on the slot's stream: every launch, the read-back of the counters and (host destinations) of the
 // frame itself.  Nothing here waits for the GPU once the slot's buffers exist.
 static int enqueue_frame(pgrt_context* ctx, FrameSlot& S) {
     int rc = prepare_frame(ctx, S);
     if (rc) return rc;
     cudaStream_t st = S.stream;
+    if (S.sig_flag) { rc = stream_write32(ctx, st, &S.d_counters.p->sig_value, S.sig_value); if (rc) return rc; }   // outside the graph: it changes every frame
     CUDA_TRY(cudaEventRecord(S.ev_frame0, st));
     bool submitted = false;
     const bool graphable = ctx->use_graphs && S.profile == 0 && S.dest_mode != 2 && (!S.host_dst || host_ptr_is_pinned(S.host_dst));
@@ -843,43 +858,39 @@ static int enqueue_frame(pgrt_context* ctx, FrameSlot& S) {
     return PGRT_OK;
 }
 
-static int frame_begin(pgrt_context* ctx, int slot, const pgrt_render_params* p, float4* dest, int dest_mode, float* host_dst, int profile, bool latency = false) {
+static int frame_begin(pgrt_context* ctx, int slot, const pgrt_render_params* p, void* dest, int dest_mode, void* host_dst, int profile, int fmt = 0) {
     if (slot < 0 || slot >= PGRT_MAX_INFLIGHT) return ctx->fail(PGRT_ERR_INVALID, "render: slot out of range");
     FrameSlot& S = ctx->slots[slot];
     if (S.busy) return ctx->fail(PGRT_ERR_INVALID, "render: the slot still holds a frame in flight (call pgrt_render_end first)");
     int rc = validate_frame(ctx, p);
     if (rc) return rc;
     cudaSetDevice(ctx->device);
-    S.params = *p; S.dest = dest; S.dest_mode = dest_mode; S.host_dst = host_dst; S.profile = profile;
+    S.params = *p; S.dest = dest; S.dest_mode = dest_mode; S.host_dst = host_dst; S.profile = profile; S.fmt = fmt;
     const int SPP = p->sampling_width * p->sampling_width;
     S.n_levels = (dest_mode == 2) ? 1 : p->max_depth + 1;
-    S.dyn = p->scheduler == 0 && dest_mode != 2 && S.n_levels > 1;
-    if (S.dyn && ctx->secondary_per_sm_max == 0) {
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->secondary_per_sm_max, k_secondary<false, false>, 128, 0));
-        ctx->secondary_per_sm_max = std::max(1, ctx->secondary_per_sm_max);
-        if (const char* e = getenv("PGRT_SECONDARY_CTAS_PER_SM")) ctx->secondary_per_sm_env = std::max(1, atoi(e));
+    S.fused = p->scheduler == 0 && dest_mode != 2;
+    if (S.fused && ctx->frame_per_sm_max == 0) {
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->frame_per_sm_max, k_frame<false, false>, 128, 0));
+        ctx->frame_per_sm_max = std::max(1, ctx->frame_per_sm_max);
+        if (const char* e = getenv("PGRT_FRAME_CTAS_PER_SM")) ctx->frame_per_sm_env = std::max(1, atoi(e));
     }
     const uint64_t total_slots = shard_slots(ctx);
     uint64_t batch_slots = std::max<uint64_t>(PGRT_TILE_PIXELS, ctx->max_batch_samples / SPP / PGRT_TILE_PIXELS * PGRT_TILE_PIXELS);
     S.batch_slots = std::min(batch_slots, total_slots);
     if (ctx->batch_limit) S.batch_slots = std::min(S.batch_slots, ctx->batch_limit);   // do not overflow the same way every frame
-    if (S.dyn) {
-        // The persistent secondary-ray kernel is latency-bound (dependent chains of up to max_depth traversals) and its
-        // CTAs hold registers and warp slots while they wait, so its grid decides how many frames can be resident at
-        // once.  A frame alone on the GPU (blocking call) wants 4 CTAs/SM for latency.  Pipelined frames want a small
-        // grid in proportion to the batch - fuller warps, more frames side by side: one CTA per 7 000 primary samples,
-        // at most 2/SM (C2: 296 CTAs, +4 % over 592; C1: 44 CTAs, +9 % over 148; profiles/r1_sweep_small_frames.txt).
+    if (S.fused) {
+        // A persistent grid: as many CTAs as fit (register-bound) for a large batch; a small batch (a shard of a frame, a
+        // 640x480 frame) takes one CTA per four 32-ray chunks per warp, so that the frames in flight behind it find room
         const uint64_t samples = S.batch_slots * (uint64_t)SPP;
-        const int cap = ctx->sm_count * ctx->secondary_per_sm_max;
-        int grid = latency ? ctx->sm_count * 4 : (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 2, std::max<uint64_t>(32, samples / 7000));
-        if (ctx->secondary_per_sm_env) grid = ctx->sm_count * ctx->secondary_per_sm_env;
-        if (const char* e = getenv("PGRT_SECONDARY_CTAS")) grid = std::max(1, atoi(e));
-        S.secondary_grid = std::min(grid, cap);
+        const int per_sm = ctx->frame_per_sm_env ? std::min(ctx->frame_per_sm_env, ctx->frame_per_sm_max) : ctx->frame_per_sm_max;
+        int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * per_sm, std::max<uint64_t>(1, (samples + 511) / 512));
+        if (const char* e = getenv("PGRT_FRAME_CTAS")) grid = std::max(1, atoi(e));
+        S.frame_grid = grid;
     }
     S.rs = pgrt_render_stats{};
     rc = enqueue_frame(ctx, S);
     if (rc) return rc;
-    S.busy = true;
+    S.busy = true; S.seq_expected++;
     return PGRT_OK;
 }
 
@@ -891,18 +902,23 @@ static int frame_end(pgrt_context* ctx, int slot, pgrt_render_stats* stats) {
     S.busy = false;
     for (;;) {
         CUDA_TRY(cudaStreamSynchronize(S.stream));
-        if (S.h_counters->watchdog) return ctx->fail(PGRT_ERR_CUDA, "render: internal error in the persistent secondary-ray kernel (mini-stack bound violated)");
         if (!S.h_counters->overflow) break;
-        // a secondary-ray queue overflowed: render the frame again in smaller batches (rare; sizes are generous)
+        // A secondary-ray queue overflowed (rare; sizes are generous): the attempt did not signal completion (k_batch_end), so
+        // no consumer ordered behind this slot has been released.  Render the frame again with four times the capacity -
+        // remembered until the next commit - or, once that would take more than a few GB per slot, in smaller batches.
         const uint32_t retries = S.rs.overflow_retries + 1;
-        if (S.batch_slots <= PGRT_TILE_PIXELS) return ctx->fail(PGRT_ERR_OVERFLOW, "render: secondary-ray queues overflow at the minimum batch; raise PGRT_MIN_LEVEL_CAP");
-        S.batch_slots = std::max<uint64_t>(PGRT_TILE_PIXELS, S.batch_slots / 2 / PGRT_TILE_PIXELS * PGRT_TILE_PIXELS);
+        const size_t pool_bytes = S.fused ? S.pool_f4[0].n * 100 : (size_t)S.n_levels * S.lv_f4[1][0].n * 100;
+        if (pool_bytes <= ((size_t)2 << 30)) ctx->pool_scale *= 4.0;
+        else {
+            if (S.batch_slots <= PGRT_TILE_PIXELS) { S.seq_expected = S.h_counters->done_seq; return ctx->fail(PGRT_ERR_OVERFLOW, "render: secondary-ray queues overflow at the minimum batch; raise PGRT_MIN_LEVEL_CAP"); }
+            S.batch_slots = std::max<uint64_t>(PGRT_TILE_PIXELS, S.batch_slots / 2 / PGRT_TILE_PIXELS * PGRT_TILE_PIXELS);
+            ctx->batch_limit = S.batch_slots;
+        }
         S.rs = pgrt_render_stats{}; S.rs.overflow_retries = retries;
         int rc = enqueue_frame(ctx, S);
-        if (rc) return rc;
+        if (rc) { S.seq_expected = S.h_counters->done_seq; return rc; }
     }
     pgrt_render_stats& rs = S.rs;
-    if (rs.overflow_retries) ctx->batch_limit = S.batch_slots;
     const Counters& hc = *S.h_counters;
     rs.rays_primary = hc.tot_primary; rs.rays_shadow = hc.tot_shadow; rs.rays_reflection = hc.tot_reflection; rs.rays_refraction = hc.tot_refraction;
     cudaEventElapsedTime(&rs.frame_ms, S.ev_frame0, S.ev_frame1);
@@ -920,12 +936,13 @@ static int frame_end(pgrt_context* ctx, int slot, pgrt_render_stats* stats) {
         pgrt_level_stats& ls = ctx->level_stats[S.ev_level[k / 2]];
         if (S.ev_class[k / 2] == KC_TRACE) { rs.trace_ms += ms; ls.trace_ms += ms; } else { rs.shade_ms += ms; ls.shade_ms += ms; }
     }
+    rs.reserved[0] = hc.q_peak;   // pool records of the largest batch (introspection; sizes PGRT_LEVEL_CAP_FACTOR)
     if (stats) *stats = rs;
     return PGRT_OK;
 }
 
-static int render_frame(pgrt_context* ctx, const pgrt_render_params* p, float4* dest, int dest_mode, float* host_dst, pgrt_render_stats* stats, int profile) {
-    int rc = frame_begin(ctx, 0, p, dest, dest_mode, host_dst, profile, /*latency=*/true);
+static int render_frame(pgrt_context* ctx, const pgrt_render_params* p, void* dest, int dest_mode, void* host_dst, pgrt_render_stats* stats, int profile, int fmt = 0) {
+    int rc = frame_begin(ctx, 0, p, dest, dest_mode, host_dst, profile, fmt);
     if (rc) return rc;
     return frame_end(ctx, 0, stats);
 }
@@ -934,7 +951,7 @@ extern "C" int pgrt_render_device(pgrt_context* ctx, const pgrt_render_params* p
     CHECK_CTX(ctx);
     if (!rgba_device) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_device: null destination");
     if (ctx->shard.n_ranks != 1) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_device: context is sharded; use pgrt_render_shard_device");
-    return render_frame(ctx, p, (float4*)rgba_device, 0, nullptr, stats, profile);
+    return render_frame(ctx, p, rgba_device, 0, nullptr, stats, profile);
 }
 
 extern "C" int pgrt_render(pgrt_context* ctx, const pgrt_render_params* p, float* rgba_host, pgrt_render_stats* stats, int32_t profile) {
@@ -942,6 +959,15 @@ extern "C" int pgrt_render(pgrt_context* ctx, const pgrt_render_params* p, float
     if (!rgba_host) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render: null destination");
     if (ctx->shard.n_ranks != 1) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render: context is sharded; use pgrt_render_shard_device");
     return render_frame(ctx, p, nullptr, 0, rgba_host, stats, profile);
+}
+
+// 8-bit frames: the resolve writes R8G8B8A8_UNORM, the format the reference presents (simpleguidx11.cpp:229,290), so a frame
+// that must end in host memory crosses PCIe as W*H*4 bytes instead of W*H*16
+extern "C" int pgrt_render_rgba8(pgrt_context* ctx, const pgrt_render_params* p, uint8_t* rgba8_host, pgrt_render_stats* stats, int32_t profile) {
+    CHECK_CTX(ctx);
+    if (!rgba8_host) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_rgba8: null destination");
+    if (ctx->shard.n_ranks != 1) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_rgba8: context is sharded; use pgrt_render_shard_to_frame_rgba8_begin");
+    return render_frame(ctx, p, nullptr, 0, rgba8_host, stats, profile, 1);
 }
 
 // ---- cross-frame accumulation (the reference's Producer re-renders from scratch every iteration,
@@ -1028,17 +1054,54 @@ extern "C" int pgrt_render_device_begin(pgrt_context* ctx, const pgrt_render_par
     CHECK_CTX(ctx);
     if (!rgba_device) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_device_begin: null destination");
     if (ctx->shard.n_ranks != 1) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_device_begin: context is sharded; use pgrt_render_shard_device_begin");
-    return frame_begin(ctx, slot, p, (float4*)rgba_device, 0, nullptr, profile);
+    return frame_begin(ctx, slot, p, rgba_device, 0, nullptr, profile);
 }
 extern "C" int pgrt_render_shard_device_begin(pgrt_context* ctx, const pgrt_render_params* p, void* shard_rgba_device, int32_t slot, int32_t profile) {
     CHECK_CTX(ctx);
     if (!shard_rgba_device) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_shard_device_begin: null destination");
-    return frame_begin(ctx, slot, p, (float4*)shard_rgba_device, 1, nullptr, profile);
+    return frame_begin(ctx, slot, p, shard_rgba_device, 1, nullptr, profile);
 }
 extern "C" int pgrt_render_shard_to_frame_begin(pgrt_context* ctx, const pgrt_render_params* p, void* frame_device, int32_t slot, int32_t profile) {
     CHECK_CTX(ctx);
     if (!frame_device) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_shard_to_frame_begin: null destination");
-    return frame_begin(ctx, slot, p, (float4*)frame_device, 0, nullptr, profile);   // full-frame addressing, this rank's tiles only
+    return frame_begin(ctx, slot, p, frame_device, 0, nullptr, profile);   // full-frame addressing, this rank's tiles only
+}
+extern "C" int pgrt_render_rgba8_begin(pgrt_context* ctx, const pgrt_render_params* p, uint8_t* rgba8_host, int32_t slot, int32_t profile) {
+    CHECK_CTX(ctx);
+    if (!rgba8_host) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_rgba8_begin: null destination");
+    if (ctx->shard.n_ranks != 1) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_rgba8_begin: context is sharded; use pgrt_render_shard_to_frame_rgba8_begin");
+    return frame_begin(ctx, slot, p, nullptr, 0, rgba8_host, profile, 1);
+}
+extern "C" int pgrt_render_shard_to_frame_rgba8_begin(pgrt_context* ctx, const pgrt_render_params* p, void* frame_rgba8_device, int32_t slot, int32_t profile) {
+    CHECK_CTX(ctx);
+    if (!frame_rgba8_device) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_shard_to_frame_rgba8_begin: null destination");
+    return frame_begin(ctx, slot, p, frame_rgba8_device, 0, nullptr, profile, 1);
+}
+// ---- completion flags (no collective): the next frames begun on `slot` store `value` in *flag once they have finished
+// without a queue overflow (k_batch_end).  `flag` is any word the device can write: its own memory, a peer-mapped frame
+// header (CUDA IPC), registered host memory.  NULL switches the signal off.
+extern "C" int pgrt_slot_signal(pgrt_context* ctx, int32_t slot, void* flag_device, uint32_t value) {
+    CHECK_CTX(ctx);
+    if (slot < 0 || slot >= PGRT_MAX_INFLIGHT) return ctx->fail(PGRT_ERR_INVALID, "pgrt_slot_signal: slot out of range");
+    if (ctx->slots[slot].busy) return ctx->fail(PGRT_ERR_INVALID, "pgrt_slot_signal: the slot holds a frame in flight");
+    ctx->slots[slot].sig_flag = (uint32_t*)flag_device; ctx->slots[slot].sig_value = value;
+    return PGRT_OK;
+}
+// make `cuda_stream` wait until *flag >= value (cuStreamWaitValue32, GEQ) / store value in *flag in stream order
+extern "C" int pgrt_stream_wait_value32(pgrt_context* ctx, void* cuda_stream, void* flag_device, uint32_t value) {
+    CHECK_CTX(ctx);
+    if (!flag_device) return ctx->fail(PGRT_ERR_INVALID, "pgrt_stream_wait_value32: null flag");
+    if (!ctx->fn_wait32) return ctx->fail(PGRT_ERR_CUDA, "pgrt_stream_wait_value32: the driver does not export cuStreamWaitValue32");
+    cudaSetDevice(ctx->device);
+    const int rc = ((pgrt_cu_memop32)ctx->fn_wait32)((cudaStream_t)cuda_stream, (unsigned long long)(uintptr_t)flag_device, value, 0x1u /* CU_STREAM_WAIT_VALUE_GEQ */);
+    if (rc != 0) return ctx->fail(PGRT_ERR_CUDA, "pgrt_stream_wait_value32: cuStreamWaitValue32 failed with CUresult " + std::to_string(rc));
+    return PGRT_OK;
+}
+extern "C" int pgrt_stream_write_value32(pgrt_context* ctx, void* cuda_stream, void* flag_device, uint32_t value) {
+    CHECK_CTX(ctx);
+    if (!flag_device) return ctx->fail(PGRT_ERR_INVALID, "pgrt_stream_write_value32: null flag");
+    cudaSetDevice(ctx->device);
+    return stream_write32(ctx, (cudaStream_t)cuda_stream, flag_device, value);
 }
 // ---- frames shared between the processes of one box (one process per GPU): CUDA IPC over NVLink
 extern "C" int pgrt_frame_alloc(pgrt_context* ctx, uint64_t bytes, void** device_ptr) {
@@ -1135,7 +1198,12 @@ extern "C" int pgrt_stream_wait_slot(pgrt_context* ctx, int32_t slot, void* cuda
     CHECK_CTX(ctx);
     if (slot < 0 || slot >= PGRT_MAX_INFLIGHT) return ctx->fail(PGRT_ERR_INVALID, "pgrt_stream_wait_slot: slot out of range");
     cudaSetDevice(ctx->device);
-    CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)cuda_stream, ctx->slots[slot].ev_done, 0));
+    FrameSlot& S = ctx->slots[slot];
+    // The slot's completion count only moves for a frame that finished WITHOUT a queue overflow: a consumer ordered here is
+    // not released by an attempt whose retry (pgrt_render_end) is still to come.  Without stream memory operations the
+    // event of the last enqueue is all there is; then a frame is only known to be good once pgrt_render_end has returned.
+    if (ctx->fn_wait32 && ((pgrt_cu_memop32)ctx->fn_wait32)((cudaStream_t)cuda_stream, (unsigned long long)(uintptr_t)&S.d_counters.p->done_seq, S.seq_expected, 0x1u) == 0) return PGRT_OK;
+    CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)cuda_stream, S.ev_done, 0));
     return PGRT_OK;
 }
 
@@ -1171,7 +1239,7 @@ extern "C" int pgrt_primary_ids(pgrt_context* ctx, const pgrt_render_params* p, 
 extern "C" int pgrt_render_shard_device(pgrt_context* ctx, const pgrt_render_params* p, void* shard_rgba_device, pgrt_render_stats* stats, int32_t profile) {
     CHECK_CTX(ctx);
     if (!shard_rgba_device) return ctx->fail(PGRT_ERR_INVALID, "pgrt_render_shard_device: null destination");
-    return render_frame(ctx, p, (float4*)shard_rgba_device, 1, nullptr, stats, profile);
+    return render_frame(ctx, p, shard_rgba_device, 1, nullptr, stats, profile);
 }
 
 static int untile_on(pgrt_context* ctx, const void* gathered_device, int32_t n_ranks, void* rgba_device, cudaStream_t st);

@@ -1,24 +1,27 @@
-// render.cuh -- wavefront form of Raytracer::get_pixel / trace (pg1/raytracer.cpp:237-437).
+// render.cuh -- GPU form of Raytracer::get_pixel / trace (pg1/raytracer.cpp:237-437).
 //
 // The reference recurses: trace(ray, level) calls itself for the reflection and the refraction ray of every
 // dielectric hit and combines the two results with the NON-linear mix_srgb (raytracer.cpp:318-319), so no
-// linear path throughput exists.  Here every recursion level is a queue:
+// linear path throughput exists: every dielectric hit is a node that waits for its children.
 //
-//   forward,  level = 0 .. max_depth :  k_trace -> k_shade -> k_phong
-//       k_shade classifies each (ray, hit): miss -> env texel; depth cut-off -> black; dielectric -> pushes its
-//       reflection / refraction rays on the level+1 queue (warp-aggregated atomics) and records (attenuation, R,
-//       child slots); everything else -> Phong list.  k_phong evaluates the Phong sum with the shadow query inline.
-//   backward, level = max_depth-1 .. 0 : k_combine resolves each dielectric node from its two children (post-order).
-//   k_resolve averages the samples of a pixel in sx-major order and applies gamma (raytracer.cpp:421-446).
+// Two schedulers (pgrt_render_params.scheduler), bit-identical in every output:
 //
-// Two schedulers drive levels >= 1 (pgrt_render_params.scheduler), bit-identical in every output:
-//   1  level-synchronous: the three forward kernels per level, then k_combine per level (as described above).
-//   0  dynamic (default): ONE persistent kernel, k_secondary, owns every ray of level >= 1.  Warps claim rays from a
-//      single pool in allocation order, trace + shade them in place, append the reflection / refraction rays of
-//      dielectric hits to the same pool (consumable at once by any idle warp), and resolve the non-linear combine
-//      by continuation: a finished node decrements its parent's pending count and the last child to arrive
-//      evaluates mix_srgb for the parent and keeps climbing.  No per-level barrier exists, so the few long
-//      traversals of a level no longer serialise the frame (profiles/r1_level_stats_bvh2_lbvh.txt).
+//   0  fused (default): ONE persistent kernel per batch, k_frame, runs the whole of trace() for every sample.
+//      A warp claims either 32 primary rays (regenerated from the slot index: coherent 8x4 pixel blocks) or up to 32
+//      records of the frame's ray pool, runs the closest-hit query, classifies the hit, evaluates Phong with its
+//      shadow query inline, and for a dielectric hit appends the reflection / refraction rays to the pool, where ANY
+//      warp of the grid may claim them at once (records are published with a per-record epoch word, claimed in
+//      allocation order with one compare-and-swap per warp).  The non-linear combine is resolved by continuation: a
+//      finished node decrements its parent's pending count, and the last child to arrive evaluates mix_srgb for the
+//      parent and keeps climbing.  With one sample per pixel the warp that finishes a pixel applies gamma and stores it
+//      in the frame, so neither hits, directions nor colours of level 0 ever travel through HBM.  No warp waits for
+//      another one except for the few hundred nanoseconds between a record's allocation and its publication; a warp
+//      leaves when no primary ray is left and the pool is empty (rays still in flight belong to warps that will look
+//      again after pushing their children), so there is no polling and no time-out.
+//   1  level-synchronous wavefront, one queue per recursion level (the cross-check of scheduler 0):
+//        forward,  level = 0 .. max_depth :  k_trace -> k_shade -> k_phong
+//        backward, level = max_depth-1 .. 0 : k_combine resolves each dielectric node from its two children (post-order)
+//        k_resolve averages the samples of a pixel in sx-major order and applies gamma (raytracer.cpp:421-446).
 //
 // Pixel order: 32x8 tiles dealt round-robin to ranks; inside a tile 8x4 blocks so a warp's primary rays are coherent.
 #pragma once
@@ -39,18 +42,27 @@ struct LevelBufs {
     uint32_t cap;
 };
 
-// Pool of every ray of level >= 1 (dynamic scheduler).  A record is written once, by the warp that shaded its parent
-// (the same warp traces it later); values that cross warps (colours, pending counts) go through ld.cg / st.cg and
-// atomics only: L1 is not coherent between SMs and a 32-B sector holds two neighbouring records.
+// Pool of every ray of level >= 1 (fused scheduler).  A record is written once, by the warp that shaded its parent, and
+// may be traced by any warp; everything that crosses warps (records, colours, pending counts) goes through ld.cg / st.cg,
+// fences and atomics only: L1 is not coherent between SMs and a 32-B sector holds two neighbouring records.
 struct RayPool {
     float4* ray_o;          // org.xyz, tnear
     float4* ray_d;          // dir.xyz, time; time < 0 marks a reserved-but-unused slot
     float4* color;          // value trace() returns for this node
     float4* att;            // dielectric nodes: attenuation rgb, R
     uint2* child;           // dielectric nodes: pool slots of the reflection / refraction child
-    uint2* link;            // x = parent record, y = level | child bit << 8 | (parent is a level-0 record) << 9
+    uint4* link;            // x = parent record, y = level | child bit << 8 | (parent is a level-0 record) << 9,
+                            // z = epoch of the batch that wrote the record: stored LAST, it publishes the record
     uint32_t* pending;      // dielectric nodes: children not yet resolved
     uint32_t cap;
+};
+
+// Where the resolved pixels of a frame go (K11)
+struct FrameOut {
+    float4* rgba;           // float frame in the layout of tex_data_ (simpleguidx11.cpp:108-114) or compact shard buffer; may be null
+    uint32_t* rgba8;        // R8G8B8A8_UNORM frame, the format the reference displays (simpleguidx11.cpp:229), or null
+    int32_t compact;        // 1: addressed by shard slot, 0: by y * W + x
+    int32_t direct;         // 1 (one sample per pixel): k_frame resolves the pixel itself; 0: samples go through L0.color and k_resolve
 };
 
 struct Counters {
@@ -58,8 +70,8 @@ struct Counters {
     uint32_t n_phong[PGRT_MAX_LEVELS + 1];
     uint32_t n_diel[PGRT_MAX_LEVELS + 1];
     uint32_t overflow;
-    uint32_t watchdog;      // dynamic scheduler: a bounded wait expired (never expected; reported as an error)
-    uint32_t pad0;
+    uint32_t watchdog;      // (unused by the fused scheduler: nothing in it waits with a bound)
+    uint32_t q_peak;        // most pool records any batch of this frame allocated (sizes the pool of the next frames)
     unsigned long long shadow, reflection, refraction;          // this batch
     unsigned long long tot_shadow, tot_reflection, tot_refraction, tot_primary;   // this frame
     // per-level frame totals; the traversal columns are filled by instrumented renders only (profile bit 1)
@@ -67,8 +79,10 @@ struct Counters {
     unsigned long long lv_nodes[PGRT_MAX_LEVELS + 1], lv_tris[PGRT_MAX_LEVELS + 1];
     unsigned long long lv_sh_nodes[PGRT_MAX_LEVELS + 1], lv_sh_tris[PGRT_MAX_LEVELS + 1];
     uint32_t lv_max_nodes[PGRT_MAX_LEVELS + 1], lv_sh_max_nodes[PGRT_MAX_LEVELS + 1];
-    // dynamic scheduler: pool records allocated / level-1 records (frozen before k_secondary) / level-1 records claimed
-    uint32_t q_tail, q_l1, q_head, pad1;
+    // fused scheduler: pool records allocated / claimed; epoch = batches begun on this slot (publication word of the records);
+    // done_seq = frames finished without a queue overflow (the completion flag of the slot, see k_batch_end)
+    uint32_t q_tail, q_head, epoch, done_seq;
+    uint32_t sig_value, pad2[3];   // what a finished frame stores in the slot's external completion flag (pgrt_slot_signal)
     uint32_t trace_next[PGRT_MAX_LEVELS + 1];   // k_trace: rays of the level's queue claimed so far
 };
 
@@ -435,10 +449,9 @@ __device__ __forceinline__ float4 combine_node(float4 att, float4 a, bool has_b,
     return make_float4(a.x * att.x, a.y * att.y, a.z * att.z, 1.0f);
 }
 
-// ---- K8 (kernel): one level of the wavefront.  With `dyn` set (level 0 of the dynamic scheduler) the children go
-//      to the ray pool (Ln aliases its ray arrays) together with their parent link, and are published at once.
+// ---- K8 (kernel): one level of the wavefront (level-synchronous scheduler)
 template <bool PATH>
-__global__ void __launch_bounds__(256, PGRT_SHADE_MIN_BLOCKS) k_shade(DevScene sc, pgrt_render_params p, Gen0 g0, int level, LevelBufs L, LevelBufs Ln, RayPool P, int dyn, Counters* cnt) {
+__global__ void __launch_bounds__(256, PGRT_SHADE_MIN_BLOCKS) k_shade(DevScene sc, pgrt_render_params p, Gen0 g0, int level, LevelBufs L, LevelBufs Ln, Counters* cnt) {
     const uint32_t n = min(cnt->n_rays[level], L.cap);
     const int lane = threadIdx.x & 31;
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -458,9 +471,8 @@ __global__ void __launch_bounds__(256, PGRT_SHADE_MIN_BLOCKS) k_shade(DevScene s
         const uint32_t pslot = warp_append(&cnt->n_phong[level], is_phong, lane);
         if (is_phong) L.phong_list[pslot] = i;
         const uint32_t dslot = warp_append(&cnt->n_diel[level], is_diel, lane);
-        uint32_t* next_count = dyn ? &cnt->q_tail : &cnt->n_rays[level + 1];
-        const uint32_t rl = warp_append(next_count, is_diel, lane);
-        const uint32_t rr = warp_append(next_count, has_refr, lane);
+        const uint32_t rl = warp_append(&cnt->n_rays[level + 1], is_diel, lane);
+        const uint32_t rr = warp_append(&cnt->n_rays[level + 1], has_refr, lane);
         if (is_diel) {
             L.diel_list[dslot] = i;
             uint2 ch = make_uint2(PGRT_INVALID_ID, PGRT_INVALID_ID);
@@ -475,19 +487,8 @@ __global__ void __launch_bounds__(256, PGRT_SHADE_MIN_BLOCKS) k_shade(DevScene s
                     Ln.ray_d[rr] = make_float4(s.refr.d.x, s.refr.d.y, s.refr.d.z, s.refr.time);
                     my_refr++;
                 }
-                if (dyn) {
-                    const uint32_t meta = (uint32_t)(level + 1) | (1u << 9);
-                    P.link[rl] = make_uint2(i, meta);
-                    if (has_refr) P.link[rr] = make_uint2(i, meta | (1u << 8));
-                    L.pending[i] = has_refr ? 2u : 1u;
-                }
             } else {
-                cnt->overflow = 1u;   // the frame is re-rendered in smaller batches
-                if (dyn) {            // reserved slots inside the pool are claimed by k_secondary: mark them dead
-                    if (rl < Ln.cap) Ln.ray_d[rl] = make_float4(0.f, 0.f, 0.f, -1.0f);
-                    if (has_refr && rr < Ln.cap) Ln.ray_d[rr] = make_float4(0.f, 0.f, 0.f, -1.0f);
-                    L.color[i] = make_float4(0.f, 0.f, 0.f, 1.f);     // (SK_PATH: k_phong overwrites it; the frame is redone anyway)
-                }
+                cnt->overflow = 1u;   // the frame is re-rendered with larger queues
             }
             L.dn_att[i] = s.att;
             L.dn_child[i] = ch;
@@ -501,7 +502,6 @@ __global__ void __launch_bounds__(256, PGRT_SHADE_MIN_BLOCKS) k_shade(DevScene s
 template <bool COUNT>
 __global__ void __launch_bounds__(128, PGRT_PHONG_MIN_BLOCKS) k_phong(DevScene sc, pgrt_render_params p, Gen0 g0, int level, LevelBufs L, Counters* cnt) {
     const uint32_t n = cnt->n_phong[level];
-    if (level == 0 && blockIdx.x == 0 && threadIdx.x == 0) cnt->q_l1 = cnt->q_tail;   // dynamic scheduler: the level-1 rays are complete
     unsigned long long my_shadow = 0;
     TravAcc acc; acc.nodes = 0; acc.tris = 0; acc.mx = 0;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -536,64 +536,98 @@ __global__ void __launch_bounds__(256) k_combine(int level, LevelBufs L, LevelBu
     }
 }
 
-// ---- dynamic scheduler: every ray of level >= 1 in one persistent kernel (see the file header)
-// Each warp claims a share of the level-1 rays with one atomicAdd and then owns their whole sub-trees: children go to
-// the warp's own per-level mini-stacks in shared memory and are popped deepest level first, 32 at a time.
-// Popping deepest-first means a level receives children only in an iteration that has just drained it, so no level
-// ever holds more than 64 entries (2 children x 32 lanes): PGRT_WSTACK per level is exact, not a guess.
-// No warp ever waits for another one: there is no queue to poll and nothing to time out.
-#define PGRT_WSTACK 64
-#ifndef PGRT_SEC_MIN_BLOCKS
-#define PGRT_SEC_MIN_BLOCKS 6     // register cap of k_secondary = 65536 / (128 * this) = 80 (was 128: no gain alone, +2.6 % pipelined)
+// ---- K11 (per pixel): mean over the samples + gamma (raytracer.cpp:421-446), and the 8-bit form the reference displays
+__device__ __forceinline__ float4 resolve_value(float fr, float fg, float fb, int S, float gamma_level) {
+    Col4 in; in.r = fb / S; in.g = fg / S; in.b = fr / S; in.a = 1.0f;       // :431 (swap in)
+    const Col4 g = gamma_correct(in, gamma_level);
+    return make_float4(g.r, g.g, g.b, g.a);
+}
+// float -> R8G8B8A8_UNORM as D3D11 converts when the float texture reaches the back buffer (simpleguidx11.cpp:229,290):
+// NaN -> 0, clamp to [0,1], scale by 255, round to nearest
+__device__ __forceinline__ uint32_t unorm8(float c) {
+    c = (c != c) ? 0.0f : fminf(fmaxf(c, 0.0f), 1.0f);
+    return (uint32_t)floorf(c * 255.0f + 0.5f);
+}
+__device__ __forceinline__ uint32_t pack_rgba8(float4 c) { return unorm8(c.x) | (unorm8(c.y) << 8) | (unorm8(c.z) << 16) | (unorm8(c.w) << 24); }
+__device__ __forceinline__ void store_pixel(const FrameOut& fo, size_t idx, float4 c) {
+    if (fo.rgba) fo.rgba[idx] = c;
+    if (fo.rgba8) fo.rgba8[idx] = pack_rgba8(c);
+}
+
+// closest hit as its own function: one copy of the traversal loop per node layout whatever the number of call sites,
+// and the register allocation of that loop is not mixed with the shading code around it
+template <bool COUNT>
+__device__ __noinline__ HitRec trace_dev(const DevScene& sc, V3 O, V3 D, float tnear, float tfar, TravCount& tc) {
+    return trace_closest_t<COUNT>(sc, O, D, tnear, tfar, tc);
+}
+
+// ---- fused scheduler: the whole of trace() for every sample of a batch in one persistent kernel (see the file header)
+#ifndef PGRT_FRAME_MIN_BLOCKS
+#define PGRT_FRAME_MIN_BLOCKS 5     // register cap of k_frame = 65536 / (128 * this)
 #endif
 
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+// a load the compiler can neither hoist out of a spin loop nor drop with the loop (a loop without side effects may be assumed to end)
+__device__ __forceinline__ uint4 ld_volatile_u4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 template <bool COUNT, bool PATH>
-__global__ void __launch_bounds__(128, PGRT_SEC_MIN_BLOCKS) k_secondary(DevScene sc, pgrt_render_params p, LevelBufs L0, RayPool P, Counters* cnt) {
-    extern __shared__ uint32_t pgrt_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_lv = p.max_depth;                                   // rays exist at levels 1 .. max_depth
-    uint32_t* stk = pgrt_smem + (size_t)warp * n_lv * (PGRT_WSTACK + 1);   // [n_lv][PGRT_WSTACK] slots, then [n_lv] counts
-    uint32_t* lvc = stk + (size_t)n_lv * PGRT_WSTACK;
-    for (int l = lane; l < n_lv; l += 32) lvc[l] = 0;
-    __syncwarp();
-    const uint32_t n_l1 = min(cnt->q_l1, P.cap);
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    // the phase is latency-bound (few rays, dependent chains): spread the level-1 rays over all warps, so a warp
-    // runs as few lanes as possible (less divergence, and an iteration lasts as long as its slowest lane)
-    const uint32_t share = min(32u, max(1u, (n_l1 + n_warps - 1u) / n_warps));
-    unsigned long long my_shadow = 0, my_refl = 0, my_refr = 0;
-    int top = 0;                                                    // deepest non-empty level, 0 = none
+__global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(DevScene sc, pgrt_render_params p, Gen0 g0, LevelBufs L0, RayPool P, FrameOut fo,
+                                                                       int min_claim, Counters* cnt) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t n0 = g0.n_slots * (uint32_t)g0.spp;             // primary samples of this batch
+    const uint32_t epoch = cnt->epoch;
+    unsigned long long my_shadow = 0, my_refl = 0, my_refr = 0, my_shadow0 = 0;
+    unsigned long long my_nodes0 = 0, my_tris0 = 0; uint32_t my_max0 = 0;   // COUNT: level-0 traversal statistics
+    bool more_primary = true;
     for (;;) {
-        if (top == 0) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&cnt->q_head, share);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= n_l1) break;
-            const uint32_t n = min(share, n_l1 - base);
-            if ((uint32_t)lane < n) stk[lane] = base + (uint32_t)lane;
-            if (lane == 0) lvc[0] = n;
-            __syncwarp();
-            top = 1;
-        }
-        // ---- pop up to 32 records, deepest level first
-        uint32_t i = PGRT_INVALID_ID; int level = 0;
-        {
-            uint32_t taken = 0;
-            for (int l = top; l >= 1 && taken < 32u; --l) {
-                const uint32_t c = lvc[l - 1];
-                const uint32_t take = min(c, 32u - taken);
-                if ((uint32_t)lane >= taken && (uint32_t)lane < taken + take) { i = stk[(size_t)(l - 1) * PGRT_WSTACK + c - 1u - ((uint32_t)lane - taken)]; level = l; }
-                __syncwarp();
-                if (lane == 0) lvc[l - 1] = c - take;
-                taken += take;
+        // ---- claim: pool records first once a warp's worth is waiting (their chains are the critical path of the
+        //      frame), else a chunk of primary rays; once those are gone, whatever the pool holds
+        uint32_t base = 0, n = 0; int mode = 0;     // 1 = pool records, 2 = primary rays, 3 = lost a race: look again
+        if (lane == 0) {
+            const uint32_t tail = min(ld_volatile_u32(&cnt->q_tail), P.cap), head = ld_volatile_u32(&cnt->q_head);
+            const uint32_t avail = tail > head ? tail - head : 0u;
+            if (avail >= (more_primary ? (uint32_t)min_claim : 1u)) {
+                n = min(avail, 32u);
+                if (atomicCAS(&cnt->q_head, head, head + n) == head) { base = head; mode = 1; }
+                else if (!more_primary) mode = 3;
             }
-            __syncwarp();
+            if (mode == 0 && more_primary) {
+                base = atomicAdd(&cnt->trace_next[0], 32u);
+                if (base < n0) { mode = 2; n = min(32u, n0 - base); } else mode = 3;
+            }
         }
-        const bool usable = i != PGRT_INVALID_ID;
+        mode = __shfl_sync(0xffffffffu, mode, 0); base = __shfl_sync(0xffffffffu, base, 0); n = __shfl_sync(0xffffffffu, n, 0);
+        if (mode == 0) break;
+        if (mode == 3) { more_primary = false; continue; }
+        const bool l0 = mode == 2;
+
+        // ---- this lane's ray
+        uint32_t i = PGRT_INVALID_ID; int level = 0;
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(0.f, 0.f, 0.f, -1.0f);
         uint2 lk = make_uint2(0u, 0u);
-        if (usable) { o = __ldcg(&P.ray_o[i]); d = __ldcg(&P.ray_d[i]); lk = __ldcg(&P.link[i]); }
-        const bool live = usable && d.w >= 0.0f;
+        int px = 0, py = 0; bool px_valid = false;
+        if ((uint32_t)lane < n) {
+            i = base + (uint32_t)lane;
+            if (l0) {
+                const uint32_t slot = g0.slot0 + i / (uint32_t)g0.spp;
+                px_valid = slot_to_pixel(g0.sh, g0.cam.width, g0.cam.height, slot, px, py);
+                if (px_valid) {
+                    const RayRec r = primary_ray(g0.cam, p, px, py, (int)(i % (uint32_t)g0.spp));
+                    o = make_float4(r.o.x, r.o.y, r.o.z, r.tnear); d = make_float4(r.d.x, r.d.y, r.d.z, r.time);
+                }
+            } else {
+                uint4 l4;
+                do { l4 = ld_volatile_u4(&P.link[i]); } while (l4.z != epoch);   // allocated before it was written: wait for the publication
+                __threadfence();
+                o = __ldcg(&P.ray_o[i]); d = __ldcg(&P.ray_d[i]);
+                lk = make_uint2(l4.x, l4.y); level = (int)(l4.y & 0xFFu);
+            }
+        }
+        const bool live = i != PGRT_INVALID_ID && d.w >= 0.0f;
 
         // ---- trace() for this ray: closest hit, classification, Phong (with its shadow query)
         ShadeOut s; s.kind = SK_FINAL; s.has_refr = false;
@@ -601,11 +635,14 @@ __global__ void __launch_bounds__(128, PGRT_SEC_MIN_BLOCKS) k_secondary(DevScene
         float4 col = make_float4(0.f, 0.f, 0.f, 1.f);
         if (live) {
             TravCount tc; tc.nodes = 0; tc.tris = 0;
-            const HitRec hr = trace_closest_t<COUNT>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, FLT_MAX, tc);
-            atomicAdd(&cnt->lv_rays[level], 1ull);
+            const HitRec hr = trace_dev<COUNT>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, FLT_MAX, tc);
+            if (!l0) atomicAdd(&cnt->lv_rays[level], 1ull);
             if (COUNT) {
-                atomicAdd(&cnt->lv_nodes[level], (unsigned long long)tc.nodes);
-                atomicAdd(&cnt->lv_tris[level], (unsigned long long)tc.tris); atomicMax(&cnt->lv_max_nodes[level], tc.nodes);
+                if (l0) { my_nodes0 += tc.nodes; my_tris0 += tc.tris; my_max0 = max(my_max0, tc.nodes); }
+                else {
+                    atomicAdd(&cnt->lv_nodes[level], (unsigned long long)tc.nodes);
+                    atomicAdd(&cnt->lv_tris[level], (unsigned long long)tc.tris); atomicMax(&cnt->lv_max_nodes[level], tc.nodes);
+                }
             }
             shade_classify<PATH>(sc, p, level, o, d, make_float4(hr.t, hr.u, hr.v, __uint_as_float(hr.tri)), s);
             if (s.kind == SK_FINAL) { col = s.color; final_ = true; }
@@ -614,13 +651,18 @@ __global__ void __launch_bounds__(128, PGRT_SEC_MIN_BLOCKS) k_secondary(DevScene
                 TravAcc a1; a1.nodes = 0; a1.tris = 0; a1.mx = 0;
                 col = phong_eval<COUNT>(sc, p, o, d, s.f, my_shadow, a1);
                 final_ = !PATH || s.kind == SK_PHONG;
-                if (PATH && !final_) __stcg(&P.color[i], col);          // SK_PATH: the node's own value waits in its colour slot for the bounce
-                if (my_shadow != sh0) atomicAdd(&cnt->lv_shadow[level], my_shadow - sh0);
+                if (PATH && !final_) {                                   // SK_PATH: the node's own value waits in its colour slot for the bounce
+                    if (l0) __stcg(&L0.color[i], col); else __stcg(&P.color[i], col);
+                }
+                if (l0) my_shadow0 += my_shadow - sh0;
+                else if (my_shadow != sh0) atomicAdd(&cnt->lv_shadow[level], my_shadow - sh0);
                 if (COUNT) {
                     atomicAdd(&cnt->lv_sh_nodes[level], a1.nodes); atomicAdd(&cnt->lv_sh_tris[level], a1.tris);
                     atomicMax(&cnt->lv_sh_max_nodes[level], a1.mx);
                 }
             }
+        } else if (i != PGRT_INVALID_ID && l0) {
+            final_ = true;                                               // unused slot of a partial tile: black, as the wavefront leaves it
         }
 
         // ---- dielectric hits: two pool records for the children (all 32 lanes take part in the aggregated atomics)
@@ -628,54 +670,43 @@ __global__ void __launch_bounds__(128, PGRT_SEC_MIN_BLOCKS) k_secondary(DevScene
         bool has_refr = is_diel && s.has_refr;
         const uint32_t rl = warp_append(&cnt->q_tail, is_diel, lane);
         const uint32_t rr = warp_append(&cnt->q_tail, has_refr, lane);
-        bool push = false;
         if (is_diel) {
             if (rl < P.cap && (!has_refr || rr < P.cap)) {
-                const uint32_t meta = (uint32_t)(level + 1);
+                const uint32_t meta = (uint32_t)(level + 1) | (l0 ? (1u << 9) : 0u);
+                // the node first (its children may finish, and climb, on another SM before this warp moves on) ...
+                if (l0) { __stcg(&L0.dn_att[i], s.att); __stcg(&L0.dn_child[i], make_uint2(rl, has_refr ? rr : PGRT_INVALID_ID)); __stcg(&L0.pending[i], has_refr ? 2u : 1u); }
+                else { __stcg(&P.att[i], s.att); __stcg(&P.child[i], make_uint2(rl, has_refr ? rr : PGRT_INVALID_ID)); __stcg(&P.pending[i], has_refr ? 2u : 1u); }
                 __stcg(&P.ray_o[rl], make_float4(s.refl.o.x, s.refl.o.y, s.refl.o.z, s.refl.tnear));
                 __stcg(&P.ray_d[rl], make_float4(s.refl.d.x, s.refl.d.y, s.refl.d.z, s.refl.time));
-                __stcg(&P.link[rl], make_uint2(i, meta));
                 my_refl++;
                 if (has_refr) {
                     __stcg(&P.ray_o[rr], make_float4(s.refr.o.x, s.refr.o.y, s.refr.o.z, s.refr.tnear));
                     __stcg(&P.ray_d[rr], make_float4(s.refr.d.x, s.refr.d.y, s.refr.d.z, s.refr.time));
-                    __stcg(&P.link[rr], make_uint2(i, meta | (1u << 8)));
                     my_refr++;
                 }
-                __stcg(&P.att[i], s.att);
-                __stcg(&P.child[i], make_uint2(rl, has_refr ? rr : PGRT_INVALID_ID));
-                __stcg(&P.pending[i], has_refr ? 2u : 1u);
-                push = true;
+                __threadfence();
+                // ... then the publication words
+                __stcg(&P.link[rl], make_uint4(i, meta, epoch, 0u));
+                if (has_refr) __stcg(&P.link[rr], make_uint4(i, meta | (1u << 8), epoch, 0u));
             } else {
-                cnt->overflow = 1u;   // black; the frame is re-rendered in smaller batches
-                final_ = true; has_refr = false;
+                cnt->overflow = 1u;   // black; the frame is re-rendered with a larger pool
+                // a reserved record inside the pool will be claimed by somebody: publish it as dead
+                if (rl < P.cap) { __stcg(&P.ray_d[rl], make_float4(0.f, 0.f, 0.f, -1.0f)); __threadfence(); __stcg(&P.link[rl], make_uint4(0u, 0u, epoch, 0u)); }
+                if (has_refr && rr < P.cap) { __stcg(&P.ray_d[rr], make_float4(0.f, 0.f, 0.f, -1.0f)); __threadfence(); __stcg(&P.link[rr], make_uint4(0u, 0u, epoch, 0u)); }
+                final_ = true; col = make_float4(0.f, 0.f, 0.f, 1.f);
             }
         }
-        // ---- push the children on the mini-stack of their level (lanes grouped by level with match_any)
-        int new_top = top;
-        #pragma unroll
-        for (int kind = 0; kind < 2; ++kind) {
-            const bool need = push && (kind == 0 || has_refr);
-            const int clevel = need ? level + 1 : 0;
-            const unsigned grp = __match_any_sync(0xffffffffu, clevel);
-            uint32_t basec = 0;
-            if (need) {
-                basec = lvc[clevel - 1];
-                const uint32_t pos = basec + (uint32_t)__popc(grp & ((1u << lane) - 1u));
-                if (pos < PGRT_WSTACK) stk[(size_t)(clevel - 1) * PGRT_WSTACK + pos] = kind == 0 ? rl : rr;
-                else cnt->watchdog = 2u;   // cannot happen (see the bound above); never write out of bounds
-            }
-            __syncwarp();
-            if (need && lane == __ffs(grp) - 1) lvc[clevel - 1] = min(basec + (uint32_t)__popc(grp), (uint32_t)PGRT_WSTACK);
-            __syncwarp();
-            new_top = max(new_top, clevel);
-        }
-        for (int o2 = 16; o2 > 0; o2 >>= 1) new_top = max(new_top, __shfl_xor_sync(0xffffffffu, new_top, o2));
-        top = new_top;
-        while (top > 0 && lvc[top - 1] == 0u) --top;
 
+        // ---- a finished level-0 sample is a pixel (one sample per pixel) or one addend of k_resolve
+        if (final_ && l0) {
+            if (fo.direct) {
+                const uint32_t slot = g0.slot0 + i;
+                if (px_valid) store_pixel(fo, fo.compact ? (size_t)slot : (size_t)py * g0.cam.width + px, resolve_value(0.0f + col.x, 0.0f + col.y, 0.0f + col.z, 1, p.gamma_level));
+                else if (fo.compact) store_pixel(fo, (size_t)slot, make_float4(0.f, 0.f, 0.f, 0.f));
+            } else L0.color[i] = col;
+        }
         // ---- continuation: hand the value to the parent; the last child to arrive evaluates the parent and climbs on
-        if (final_) {
+        if (final_ && !l0) {
             uint32_t node = i; uint2 nlk = lk; float4 c = col;
             for (;;) {
                 __stcg(&P.color[node], c);
@@ -689,37 +720,47 @@ __global__ void __launch_bounds__(128, PGRT_SEC_MIN_BLOCKS) k_secondary(DevScene
                 const bool has_b = ch.y != PGRT_INVALID_ID;
                 const float4 own = PATH && att.w < 0.0f ? (par_l0 ? __ldcg(&L0.color[par]) : __ldcg(&P.color[par])) : make_float4(0.f, 0.f, 0.f, 0.f);
                 c = combine_node<PATH>(att, __ldcg(&P.color[ch.x]), has_b, has_b ? __ldcg(&P.color[ch.y]) : make_float4(0.f, 0.f, 0.f, 0.f), own);
-                if (par_l0) { L0.color[par] = c; break; }
-                node = par; nlk = __ldcg(&P.link[par]);
+                if (par_l0) {
+                    if (fo.direct) {
+                        int x, y;
+                        const uint32_t slot = g0.slot0 + par;
+                        slot_to_pixel(g0.sh, g0.cam.width, g0.cam.height, slot, x, y);
+                        store_pixel(fo, fo.compact ? (size_t)slot : (size_t)y * g0.cam.width + x, resolve_value(0.0f + c.x, 0.0f + c.y, 0.0f + c.z, 1, p.gamma_level));
+                    } else L0.color[par] = c;
+                    break;
+                }
+                const uint4 l4 = __ldcg(&P.link[par]);
+                node = par; nlk = make_uint2(l4.x, l4.y);
             }
         }
         __syncwarp();
     }
     for (int o = 16; o > 0; o >>= 1) {
         my_shadow += __shfl_xor_sync(0xffffffffu, my_shadow, o); my_refl += __shfl_xor_sync(0xffffffffu, my_refl, o); my_refr += __shfl_xor_sync(0xffffffffu, my_refr, o);
+        my_shadow0 += __shfl_xor_sync(0xffffffffu, my_shadow0, o);
     }
     if (lane == 0) {
         if (my_shadow) atomicAdd(&cnt->shadow, my_shadow);
+        if (my_shadow0) atomicAdd(&cnt->lv_shadow[0], my_shadow0);
         if (my_refl) atomicAdd(&cnt->reflection, my_refl);
         if (my_refr) atomicAdd(&cnt->refraction, my_refr);
     }
+    if (COUNT) flush_trav_counts(my_nodes0, my_tris0, my_max0, &cnt->lv_nodes[0], &cnt->lv_tris[0], &cnt->lv_max_nodes[0]);
 }
 
 // ---- K11: sample resolve (raytracer.cpp:421-436) + gamma (:439-446); full-frame or compact-shard destination
 __global__ void __launch_bounds__(256) k_resolve(DevCamera cam, pgrt_render_params p, ShardInfo sh, uint32_t slot0, uint32_t n_slots,
-                                                 const float4* __restrict__ color0, float4* __restrict__ out, int compact) {
+                                                 const float4* __restrict__ color0, FrameOut fo) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_slots) return;
     const uint32_t slot = slot0 + s;
     int x, y;
     const bool valid = slot_to_pixel(sh, cam.width, cam.height, slot, x, y);
-    if (!valid) { if (compact) out[slot] = make_float4(0.f, 0.f, 0.f, 0.f); return; }
+    if (!valid) { if (fo.compact) store_pixel(fo, slot, make_float4(0.f, 0.f, 0.f, 0.f)); return; }
     const int S = p.sampling_width * p.sampling_width;
     float fr = 0.0f, fg = 0.0f, fb = 0.0f;
     for (int k = 0; k < S; ++k) { const float4 c = color0[(size_t)s * S + k]; fr += c.x; fg += c.y; fb += c.z; }
-    Col4 in; in.r = fb / S; in.g = fg / S; in.b = fr / S; in.a = 1.0f;
-    const Col4 g = gamma_correct(in, p.gamma_level);
-    out[compact ? (size_t)slot : (size_t)y * cam.width + x] = make_float4(g.r, g.g, g.b, g.a);
+    store_pixel(fo, fo.compact ? (size_t)slot : (size_t)y * cam.width + x, resolve_value(fr, fg, fb, S, p.gamma_level));
 }
 
 // compact per-rank shard buffers (rank-major) -> full frame (simpleguidx11.cpp:108-114 layout)
@@ -745,22 +786,36 @@ __global__ void __launch_bounds__(256) k_primary_ids(DevScene sc, DevCamera cam,
     geom[(size_t)y * cam.width + x] = g; prim[(size_t)y * cam.width + x] = pr;
 }
 
-__global__ void k_batch_begin(Counters* c, uint32_t n0) {
-    const int t = threadIdx.x;
-    if (t <= PGRT_MAX_LEVELS) { c->n_rays[t] = t == 0 ? n0 : 0u; c->n_phong[t] = 0; c->n_diel[t] = 0; c->trace_next[t] = 0; }
-    if (t == 0) { c->shadow = 0; c->reflection = 0; c->refraction = 0; c->q_head = 0; c->q_l1 = 0; c->q_tail = 0; }
-}
-__global__ void k_batch_end(Counters* c, unsigned long long primary, int dyn) {
-    if (!dyn && threadIdx.x <= PGRT_MAX_LEVELS && threadIdx.x > 0) c->lv_rays[threadIdx.x] += c->n_rays[threadIdx.x];
-    if (threadIdx.x == 0) { c->lv_rays[0] += primary; c->tot_shadow += c->shadow; c->tot_reflection += c->reflection; c->tot_refraction += c->refraction; c->tot_primary += primary; }
-}
-__global__ void k_frame_begin(Counters* c) {
+// frame / batch bookkeeping.  `first`: first batch of a frame (resets the frame totals).
+__global__ void k_batch_begin(Counters* c, uint32_t n0, int first) {
     const int t = threadIdx.x;
     if (t <= PGRT_MAX_LEVELS) {
-        c->lv_rays[t] = 0; c->lv_shadow[t] = 0; c->lv_nodes[t] = 0; c->lv_tris[t] = 0; c->lv_sh_nodes[t] = 0; c->lv_sh_tris[t] = 0;
-        c->lv_max_nodes[t] = 0; c->lv_sh_max_nodes[t] = 0;
+        c->n_rays[t] = t == 0 ? n0 : 0u; c->n_phong[t] = 0; c->n_diel[t] = 0; c->trace_next[t] = 0;
+        if (first) {
+            c->lv_rays[t] = 0; c->lv_shadow[t] = 0; c->lv_nodes[t] = 0; c->lv_tris[t] = 0; c->lv_sh_nodes[t] = 0; c->lv_sh_tris[t] = 0;
+            c->lv_max_nodes[t] = 0; c->lv_sh_max_nodes[t] = 0;
+        }
     }
-    if (threadIdx.x == 0) { c->overflow = 0; c->watchdog = 0; c->tot_shadow = 0; c->tot_reflection = 0; c->tot_refraction = 0; c->tot_primary = 0; }
+    if (t == 0) {
+        c->shadow = 0; c->reflection = 0; c->refraction = 0; c->q_head = 0; c->q_tail = 0;
+        c->epoch += 1u;      // the pool's publication word: records of earlier batches (and frames) read as "not yet written"
+        if (first) { c->overflow = 0; c->watchdog = 0; c->tot_shadow = 0; c->tot_reflection = 0; c->tot_refraction = 0; c->tot_primary = 0; c->q_peak = 0; }
+    }
+}
+// `last`: last batch of the frame.  A frame that finished without a queue overflow bumps the slot's completion count (what
+// pgrt_stream_wait_slot waits for) and stores the caller's tag in `done_flag` (host-visible or peer memory, pgrt_slot_signal:
+// what dist.ShardedRenderer waits for); an overflowed attempt does neither, so nobody is released before the retry has
+// rendered the frame.
+__global__ void k_batch_end(Counters* c, unsigned long long primary, int fused, int last, uint32_t* done_flag) {
+    if (!fused && threadIdx.x <= PGRT_MAX_LEVELS && threadIdx.x > 0) c->lv_rays[threadIdx.x] += c->n_rays[threadIdx.x];
+    if (threadIdx.x == 0) {
+        c->lv_rays[0] += primary; c->tot_shadow += c->shadow; c->tot_reflection += c->reflection; c->tot_refraction += c->refraction; c->tot_primary += primary;
+        c->q_peak = max(c->q_peak, c->q_tail);
+        if (last && !c->overflow) {
+            c->done_seq += 1u;
+            if (done_flag) { __threadfence_system(); *(volatile uint32_t*)done_flag = c->sig_value; }
+        }
+    }
 }
 
 // ---- batch rtcIntersect1 over RTCRayHit-compatible records (device copies)

@@ -322,7 +322,7 @@ def test_pipelined_frames_equal_synchronous_frames(P, avenger):
 
 
 def test_schedulers_agree_bit_for_bit(P, cornell, avenger):
-    """The persistent dynamic scheduler (continuation-passing combine, no level barrier) and the level-synchronous
+    """The fused persistent kernel (shared ray pool, continuation-passing combine, no level barrier) and the level-synchronous
     wavefront evaluate the same tree with the same arithmetic: frames and ray counts must be identical."""
     sc, rt, o = avenger
     cases = [(P.raytracer_for(cornell), dict(seed=5)), (P.raytracer_for(cornell), dict(seed=5, max_depth=1)),
@@ -340,18 +340,52 @@ def test_schedulers_agree_bit_for_bit(P, cornell, avenger):
 
 
 @pytest.mark.parametrize("scheduler", [0, 1])
-def test_queue_overflow_falls_back_to_smaller_batches(P, cornell, monkeypatch, scheduler):
-    # the dynamic scheduler keeps ONE pool (4 x cap) for all levels; the worst 32x8 tile of this frame needs 8385 records
+def test_queue_overflow_is_retried_with_larger_queues(P, cornell, monkeypatch, scheduler):
+    # the fused scheduler keeps ONE pool (4 x cap) for all levels; this frame needs far more than 4 x 2500 records
     monkeypatch.setenv("PGRT_MIN_LEVEL_CAP", "2500" if scheduler == 0 else "2048"); monkeypatch.setenv("PGRT_LEVEL_CAP_FACTOR", "0.05")
     rt = P.raytracer_for(cornell)
     p = dict(seed=2, scheduler=scheduler)
     img, st = rt.render(p)
     assert st["overflow_retries"] >= 1
-    img2, st2 = rt.render(p)                                   # the surviving batch size is remembered: no second overflow
-    assert st2["overflow_retries"] == 0 and st2["batches"] == st["batches"] and np.array_equal(img, img2, equal_nan=True)
+    img2, st2 = rt.render(p)                                   # the capacity that survived is remembered: no second overflow
+    assert st2["overflow_retries"] == 0 and np.array_equal(img, img2, equal_nan=True)
     monkeypatch.delenv("PGRT_MIN_LEVEL_CAP"); monkeypatch.delenv("PGRT_LEVEL_CAP_FACTOR")
     ref, _ = P.raytracer_for(cornell).render(p)
     assert np.array_equal(img, ref, equal_nan=True)
+
+
+def test_overflowed_attempt_does_not_release_stream_consumers(P, cornell, monkeypatch):
+    """a consumer ordered behind a slot with pgrt_stream_wait_slot must not see the frame of an attempt whose
+    queues overflowed (black dielectric nodes); it is released by the retry that pgrt_render_end runs."""
+    import torch
+    monkeypatch.setenv("PGRT_MIN_LEVEL_CAP", "2500"); monkeypatch.setenv("PGRT_LEVEL_CAP_FACTOR", "0.05")
+    rt = P.raytracer_for(cornell)
+    p = dict(seed=2)
+    dev = torch.zeros((rt.height, rt.width, 4), dtype=torch.float32, device="cuda")
+    copy = torch.zeros_like(dev)
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    rt.render_begin(1, p, device_ptr=dev.data_ptr())
+    rt.stream_wait_slot(1, side.cuda_stream)
+    with torch.cuda.stream(side):
+        copy.copy_(dev, non_blocking=True)
+    st = rt.render_end(1)
+    assert st["overflow_retries"] >= 1
+    torch.cuda.synchronize()
+    monkeypatch.delenv("PGRT_MIN_LEVEL_CAP"); monkeypatch.delenv("PGRT_LEVEL_CAP_FACTOR")
+    ref, _ = P.raytracer_for(cornell).render(p)
+    assert np.array_equal(copy.cpu().numpy(), ref, equal_nan=True)
+
+
+def test_rgba8_frame_is_the_quantised_float_frame(P, cornell, avenger):
+    """pgrt_render_rgba8 = round(clamp(c,0,1)*255), NaN -> 0 of the float frame (what D3D11 presents, simpleguidx11.cpp:229,290)."""
+    sc, rt, o = avenger
+    for r, p in ((P.raytracer_for(cornell), dict(seed=4)), (rt, dict(sampling_width=1, jitter=0, aperture=0.0, max_depth=10)),
+                 (rt, dict(sampling_width=2, seed=3, scheduler=1))):
+        f, sf = r.render(p)
+        q, sq = r.render_rgba8(p)
+        assert np.array_equal(q[..., :3], P.to_srgb8(f)) and np.all(q[..., 3] == 255)
+        assert sf["total"] == sq["total"]
 
 
 def test_sharded_render_is_bit_identical_to_single_gpu(P, avenger):
