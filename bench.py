@@ -7,16 +7,19 @@
 A "step" is one frame = one pass of the hot path (pg1/simpleguidx11.cpp:95-118) over every pixel of the frame.
 Workload (N=1 default) = BASELINE.json configs[1]: avenger (stand-in mesh, the reference's OBJ is absent) 1920x1080,
 Whitted, depth cut-off 10, 1 spp un-jittered.  For N>1 the same frame is cut into 32x8 tiles dealt round-robin to
-the ranks (strong scaling: total work fixed); every rank's resolve kernel stores its tiles straight into rank 0's frame over
-NVLink (fallback: NCCL gather), a 4-byte NCCL all-reduce per step is the completion barrier.
+the ranks (strong scaling: total work fixed); every rank's frame kernel stores its tiles straight into rank 0's frame over
+NVLink (fallback: NCCL gather); completion is one flag per rank and slot in shared host memory, waited for with stream
+memory operations (no collective per step).
 
-value  : rays/s of K whole frames, scene resident in HBM, device time between two CUDA events around all K steps; the
-         Producer loop renders frames forever (pg1/simpleguidx11.cpp:95-125), so --inflight frames (default 8; 16 for
-         frames or shards below 1 M primary samples) are in flight per GPU (own stream each, pgrt_render*_begin /
-         pgrt_render_end); L2 is flushed before every step on that step's stream (a fill of 1.125 x L2).
+value  : rays/s of K whole frames, scene resident in HBM: the Producer loop renders frames forever
+         (pg1/simpleguidx11.cpp:95-125), so the run is one continuous pipeline (--inflight frames in flight per GPU, own
+         stream each, pgrt_render*_begin / pgrt_render_end; L2 flushed before every step on that step's stream, a fill of
+         1.125 x L2) cut into consecutive windows of exactly K steps; a CUDA event on the consumer stream closes every
+         window, the slowest rank counts per window, and the MEDIAN window is reported (the first one fills the pipeline).
+         Enough windows run to cover --min-seconds (1 s) of device time, with the clocks sampled throughout.
 e2e    : the same metric through the host-buffer C-ABI call every step (pgrt_set_camera + pgrt_render_begin into pinned
-         host memory + pgrt_render_end), wall clock.  N>1: the frames live in host memory shared by all ranks and every
-         rank's tiles cross its own PCIe link (dist.ShardedRenderer mode "host").
+         host memory + pgrt_render_end), wall clock, float frame (e2e) and 8-bit frame (e2e_rgba8).  N>1: the frames live
+         in host memory shared by all ranks and every rank's tiles cross its own PCIe link (dist.ShardedRenderer mode "host").
 clocks : SM clock and throttle reasons sampled through NVML every 2 ms inside the timed region.
 --impl reference : the CPU restatement of the reference's loop (oracle/; the reference itself cannot be built here)
                    on all host cores, same config, same metric.
@@ -38,10 +41,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "Mrays/s (prim+secondary), avenger Whitted 1080p"
-# dram__bytes_read.sum + dram__bytes_write.sum of one C2 frame's traversal launches, from the committed ncu --set full capture
-# (profiles/r1_ncu_bvh8_f32w_k_trace_k_secondary.txt: k_trace 7.82 MB + 0.43 MB, k_secondary 10.87 MB + 0.02 MB; k_phong is negligible).
-# The algorithmic figure for the same launches is 2.84 M rays x 720 B = 2.05 GB: the working set lives in L1/L2, not in HBM.
-NCU_TRAFFIC_BYTES = int(7.819264e6 + 428544 + 10.873856e6 + 17920)
 UNIT = "Mrays/s"
 
 
@@ -179,6 +178,15 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
+def host_threads() -> int:
+    """Threads the CPU arm may use: the cores this process may run on, whatever OMP_NUM_THREADS says (torch.distributed.run
+    exports OMP_NUM_THREADS=1 to every rank, which would otherwise turn the all-cores baseline into a one-core one)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args):
     """CPU arm: the oracle restatement of the reference loop on all host cores (rank 0 only)."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -187,7 +195,7 @@ def run_reference(args):
 
     sc, p, desc = workload(args.workload)
     orc = Oracle(sc)
-    cores = orc.max_threads()
+    cores = host_threads()
     W, H = sc.camera.width, sc.camera.height
     # bounded sample: a centred horizontal band of the frame sized to keep each step around a second
     S = p["sampling_width"] ** 2
@@ -197,7 +205,7 @@ def run_reference(args):
     # shrinks if (warmup + steps) of it would take longer
     y0 = (H - rows) // 2
     t0 = time.perf_counter()
-    orc.render(pr, want_ids=False, threads=0, region=(0, y0, W, y0 + rows))
+    orc.render(pr, want_ids=False, threads=cores, region=(0, y0, W, y0 + rows))
     t_step = time.perf_counter() - t0
     budget = 90.0
     if t_step * (args.steps + args.warmup) > budget:
@@ -205,18 +213,19 @@ def run_reference(args):
     y0 = (H - rows) // 2
     region = (0, y0, W, y0 + rows)
     for _ in range(args.warmup):
-        orc.render(pr, want_ids=False, threads=0, region=region)
+        orc.render(pr, want_ids=False, threads=cores, region=region)
     t0 = time.perf_counter(); rays = 0
     for _ in range(args.steps):
-        _, _, _, st = orc.render(pr, want_ids=False, threads=0, region=region)
+        _, _, _, st = orc.render(pr, want_ids=False, threads=cores, region=region)
         rays += st["total"]
     dt = time.perf_counter() - t0
     v = rays / dt / 1e6
-    sample = f"rows {y0}..{y0 + rows} of {H} ({rows * W} px x {S} spp) per step, all host threads"
+    sample = f"rows {y0}..{y0 + rows} of {H} ({rows * W} px x {S} spp) per step, {cores} host threads"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "note": "CPU restatement of the reference loop (oracle/): the Windows/D3D11/Embree reference cannot be built here"},
+        "config": {"workload": desc, "note": "CPU restatement of the reference loop (oracle/pg_oracle.cpp) with its own SAH BVH in place of Embree (binary not vendored); "
+                                             "bit-identical to the reference's own pg1/*.cpp object code above the rtcIntersect1 boundary (oracle/_ref, tests/test_oracle_vs_ref.py)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -227,17 +236,17 @@ def cpu_baseline(sc, p, budget_s=12.0):
     from oracle.oracle import Oracle, make_params
 
     orc = Oracle(sc)
-    cores = orc.max_threads()
+    cores = host_threads()
     W, H = sc.camera.width, sc.camera.height
     S = p["sampling_width"] ** 2
     rows = H if W * H * S <= 4_000_000 else max(8, int(4_000_000 / (W * S)) // 8 * 8)
     y0 = (H - rows) // 2
     region = (0, y0, W, y0 + rows)
     pr = make_params(**p)
-    orc.render(pr, want_ids=False, threads=0, region=region)
+    orc.render(pr, want_ids=False, threads=cores, region=region)
     t0 = time.perf_counter(); rays = 0; n = 0
     while True:
-        _, _, _, st = orc.render(pr, want_ids=False, threads=0, region=region)
+        _, _, _, st = orc.render(pr, want_ids=False, threads=cores, region=region)
         rays += st["total"]; n += 1
         if time.perf_counter() - t0 > budget_s or n >= 1000:
             break
@@ -248,7 +257,24 @@ def cpu_baseline(sc, p, budget_s=12.0):
     _, _, _, st1 = orc.render(pr, want_ids=False, threads=1, region=band)
     dt1 = time.perf_counter() - t1
     return {"value": rays / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} x rows {y0}..{y0 + rows} of {H} at {W} px x {S} spp, all {cores} host threads; single-thread {st1['total'] / dt1 / 1e6:.3f} Mrays/s on 8 rows"}
+            "sample": f"{n} x rows {y0}..{y0 + rows} of {H} at {W} px x {S} spp, {cores} host threads; single-thread {st1['total'] / dt1 / 1e6:.3f} Mrays/s on 8 rows"}
+
+
+def ncu_traffic(workload_name: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed summary of the
+    `ncu --set full` capture of this build (profiles/r2_ncu_traffic.json, written by tools/ncu_summary.py); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(workload_name)
+    except Exception:
+        return None
+
+
+def frame_hash(t) -> str:
+    """NaN-safe content hash of a frame tensor (the bit patterns, not the values: NaN pixels of negative Phong sums count)."""
+    import hashlib
+    return hashlib.sha256(t.contiguous().cpu().numpy().tobytes()).hexdigest()[:16]
 
 
 def run_ours(args):
@@ -272,9 +298,10 @@ def run_ours(args):
     sc, p, desc = workload(args.workload)
     rt = raytracer_for(sc, device=local)
     params = default_params(**p)
-    # frames in flight: a frame (or shard) of < 1 M primary samples is latency-bound and wants a deeper pipeline
+    # frames in flight: the Producer loop renders frames forever (pg1/simpleguidx11.cpp:95-125); a frame whose secondary-ray
+    # chains are still running leaves most of the GPU to the next one
     shard_samples = sc.camera.width * sc.camera.height * p.get("sampling_width", 1) ** 2 / world
-    auto_depth = 8 if shard_samples >= 1e6 else 16
+    auto_depth = 4 if shard_samples >= 1e6 else 8
     depth = max(1, min(args.inflight if args.inflight > 0 else auto_depth, 16))
     K, W = args.steps, max(args.warmup, 3)
     sr = ShardedRenderer(rt, rank, world, dev, depth=depth)
@@ -292,147 +319,222 @@ def run_ours(args):
 
     host_issue = [0.0, 0]
 
-    def run_frames(n, timed):
-        """n frames, `depth` in flight; every frame is preceded by an L2 flush on its own stream.  Returns (device ms, rays)."""
+    def run_windows(renderer, n_windows, k_per_window):
+        """n_windows x k_per_window frames as ONE continuous pipeline (`depth` in flight, every frame preceded by an L2 flush on
+        its own stream), bracketed by barrier + synchronize; a CUDA event on the consumer stream marks the completion of the
+        last frame of every window.  Returns (device ms per window, rays of this rank, host seconds between the brackets)."""
         comm = torch.cuda.current_stream()
-        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(n_windows + 1)]
+        n = n_windows * k_per_window
         barrier()
-        t0.record(comm)
-        for s in sr.slot_streams:
-            s.wait_event(t0)
+        h_start = time.perf_counter()
+        marks[0].record(comm)
+        for s in renderer.slot_streams:
+            s.wait_event(marks[0])
         rays = 0
         for k in range(n):
             if k >= depth:
-                rays += sr.end(k - depth)["total"]
+                rays += renderer.end(k - depth)["total"]
             h0 = time.perf_counter()
-            sr.begin(k, params, before=l2_flush(k))
+            renderer.begin(k, params, before=l2_flush(k))      # leaves the consumer stream waiting for frame k
             host_issue[0] += time.perf_counter() - h0; host_issue[1] += 1
+            if (k + 1) % k_per_window == 0:
+                marks[(k + 1) // k_per_window].record(comm)
         for k in range(max(0, n - depth), n):
-            rays += sr.end(k)["total"]
-        for s in sr.slot_streams:
-            comm.wait_stream(s)
-        t1.record(comm)
+            rays += renderer.end(k)["total"]
         barrier()
-        return t0.elapsed_time(t1), rays
+        h_stop = time.perf_counter()
+        return [marks[i].elapsed_time(marks[i + 1]) for i in range(n_windows)], rays, h_stop - h_start
 
-    run_frames(max(W, 2 * depth), False)   # every slot allocates its queues on first use: keep that out of the timed region
+    # warm-up: every slot allocates its queues and captures its frame graph on first use; also the estimate that sizes the run
+    win, _, _ = run_windows(sr, 2, max(W, 2 * depth))
+    est_ms = max(win[1] / max(W, 2 * depth), 1e-3)
+    R = int(min(200, max(5, math.ceil(args.min_seconds * 1e3 / (K * est_ms)))))    # windows of exactly K steps, >= min_seconds in total
     host_issue[0] = 0.0; host_issue[1] = 0
     sr.host_s, sr.host_n = [0.0, 0.0, 0.0, 0.0], 0
     sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(dev), "uuid", None)); sampler.start()
     launches0 = rt.kernel_launches()
-    total_ms, rays = run_frames(K, True)
+    win, rays, timed_s = run_windows(sr, R, K)
     launches = rt.kernel_launches() - launches0
     host_parts = [x / max(sr.host_n, 1) * 1e6 for x in sr.host_s]
     clocks = sampler.stop()
-    step_ms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    wt = torch.tensor(win, dtype=torch.float64, device=dev)
     tot = torch.tensor([float(rays), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(wt, op=dist.ReduceOp.MAX)          # every window: the slowest rank's device time
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    total_ms = float(step_ms.item()); total_rays = float(tot[0].item())
-    value = total_rays / (total_ms * 1e-3) / 1e6
+    win = [float(x) for x in wt.tolist()]
+    rays_per_frame = float(tot[0].item()) / (R * K)
+    steady = sorted(win[1:])                               # the first window also fills the pipeline
+    window_ms = steady[len(steady) // 2]
+    ms_per_step = window_ms / K
+    value = rays_per_frame / (ms_per_step * 1e-3) / 1e6
 
-    # roofline of the dominant kernels: the same frames one at a time with every launch bracketed by CUDA events on its stream
-    trace_ms = 0.0; trace_launches = 0; prof_rays = 0; lv = None; prof_frame_ms = 0.0
-    n_prof = min(K, 10)
+    # the frame the other ranks helped to render must be the frame one GPU renders (rank 0, untimed)
+    frame_equal = None
+    if world > 1:
+        barrier()
+        sr.begin(0, params); sr.end(0)
+        torch.cuda.current_stream().synchronize()
+        barrier()
+        if rank == 0:
+            h_sharded = frame_hash(sr.frames[0])
+            rt.set_shard(0, 1)
+            solo = torch.zeros((rt.height, rt.width, 4), dtype=torch.float32, device=dev)
+            torch.cuda.synchronize()
+            rt.render_device(solo.data_ptr(), params)
+            torch.cuda.synchronize()
+            frame_equal = bool(h_sharded == frame_hash(solo))
+            rt.set_shard(rank, world)
+        barrier()
+
+    # roofline of the dominant kernel: the same frames one at a time, the frame kernel bracketed by CUDA events on its stream
+    trace_ms = 0.0; trace_launches = 0; prof_rays = 0; prof_frame_ms = 0.0
+    n_prof = 10
     for k in range(n_prof):
         sr.begin(k, params, profile=1, before=l2_flush(k))
         st = sr.end(k)
         trace_ms += st["trace_ms"]; trace_launches += st["trace_launches"]; prof_rays += st["total"]; prof_frame_ms += st["frame_ms"]
-    lv = rt.level_stats()
+    sr.begin(0, params, profile=3); st_count = sr.end(0)      # instrumented traversal: nodes fetched / triangles tested per ray
     barrier()
+    l2 = rt.l2_bandwidth() if rank == 0 else None
 
-    # e2e: the host-buffer C-ABI call every step (camera re-sent, frame copied back to pinned host memory), `depth` in flight
+    # e2e: the host-buffer C-ABI call every step (camera re-sent, frame in pinned host memory when the step ends), `depth` in flight
     c = sc.camera
+    e2e_extra = {}
     if world == 1:
-        hosts = [torch.empty((rt.height, rt.width, 4), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        def e2e_run(rgba8):
+            if rgba8:
+                hosts = [torch.empty((rt.height, rt.width, 4), dtype=torch.uint8).pin_memory() for _ in range(depth)]
+            else:
+                hosts = [torch.empty((rt.height, rt.width, 4), dtype=torch.float32).pin_memory() for _ in range(depth)]
 
-        def e2e_frames(n):
-            e_rays = 0
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for k in range(n):
-                if k >= depth:
-                    e_rays += rt.render_end((k - depth) % depth)["total"]
-                rt.flush_l2(k % depth, FLUSH_BYTES, k & 0xFF)
-                rt.set_camera(c.width, c.height, c.fov_y, c.view_from, c.view_at)
-                rt.render_begin(k % depth, params, host_ptr=hosts[k % depth].data_ptr())
-            for k in range(max(0, n - depth), n):
-                e_rays += rt.render_end(k % depth)["total"]
-            torch.cuda.synchronize()
-            return time.perf_counter() - t0, e_rays
+            def frames(n):
+                e_rays = 0
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for k in range(n):
+                    if k >= depth:
+                        e_rays += rt.render_end((k - depth) % depth)["total"]
+                    rt.flush_l2(k % depth, FLUSH_BYTES, k & 0xFF)
+                    rt.set_camera(c.width, c.height, c.fov_y, c.view_from, c.view_at)
+                    rt.render_begin(k % depth, params, host_ptr=hosts[k % depth].data_ptr(), rgba8=rgba8)
+                for k in range(max(0, n - depth), n):
+                    e_rays += rt.render_end(k % depth)["total"]
+                torch.cuda.synchronize()
+                return time.perf_counter() - t0, e_rays
+
+            frames(2 * depth)
+            t, r = frames(R * K)
+            return {"value": r / t / 1e6, "unit": UNIT, "h2d_bytes_per_step": 4 * (2 + 1 + 3 + 3) + 64,
+                    "d2h_bytes_per_step": rt.width * rt.height * (4 if rgba8 else 16), "ms_per_step": t / (R * K) * 1e3,
+                    "frame": "R8G8B8A8_UNORM (what the reference presents, pg1/simpleguidx11.cpp:229)" if rgba8 else "float RGBA (the reference's tex_data_, pg1/simpleguidx11.cpp:108-114)",
+                    "frame_hash": frame_hash(hosts[(R * K - 1) % depth])}
 
         rt.set_shard(0, 1)
-        e2e_frames(2 * depth)
-        t_e2e, e_rays = e2e_frames(K)
-        e2e = {"value": e_rays / t_e2e / 1e6, "unit": UNIT, "h2d_bytes_per_step": 4 * (2 + 1 + 3 + 3) + 64,
-               "d2h_bytes_per_step": rt.width * rt.height * 16, "ms_per_step": t_e2e / K * 1e3}
+        e2e = e2e_run(False)
+        e2e_extra["e2e_rgba8"] = e2e_run(True)
     else:
-        # multi-GPU e2e: rank 0 additionally copies the gathered frame to pinned host memory every step
-        # The frames live in host memory shared by all ranks (memfd registered with every device): each rank's resolve
-        # kernel stores its tiles through its own PCIe link.  Fallback: rank 0 copies the NVLink-gathered frame out.
-        try:
-            sr_e = ShardedRenderer(rt, rank, world, dev, depth=depth, mode="host")
-        except RuntimeError:
-            sr_e = sr
-        host = torch.empty((rt.height, rt.width, 4), dtype=torch.float32).pin_memory() if rank == 0 and sr_e is sr else None
+        # The frames live in host memory shared by all ranks (memfd registered with every device): each rank's frame kernel
+        # stores its tiles through its own PCIe link.  Fallback: rank 0 copies the NVLink-gathered frame out.
+        def e2e_run(rgba8):
+            try:
+                sr_e = ShardedRenderer(rt, rank, world, dev, depth=depth, mode="host", rgba8=rgba8)
+            except (RuntimeError, ValueError):
+                if rgba8:
+                    return None
+                sr_e = sr
+            host = torch.empty((rt.height, rt.width, 4), dtype=torch.float32).pin_memory() if rank == 0 and sr_e is sr else None
 
-        def e2e_frames(n):
-            barrier()
-            t0 = time.perf_counter(); rays = 0
-            for k in range(n):
-                if k >= depth:
-                    rays += sr_e.end(k - depth)["total"]
-                sr_e.begin(k, params, before=l2_flush(k))
-                if host is not None:
-                    host.copy_(sr.frames[k % depth], non_blocking=True)   # on the communication stream, after that frame's barrier
-            for k in range(max(0, n - depth), n):
-                rays += sr_e.end(k)["total"]
-            barrier()
-            return t0, rays
+            def frames(n):
+                barrier()
+                t0 = time.perf_counter(); rays = 0
+                for k in range(n):
+                    if k >= depth:
+                        rays += sr_e.end(k - depth)["total"]
+                    sr_e.begin(k, params, before=l2_flush(k))
+                    if host is not None:
+                        host.copy_(sr.frames[k % depth], non_blocking=True)   # on the consumer stream, behind that frame's completion
+                for k in range(max(0, n - depth), n):
+                    rays += sr_e.end(k)["total"]
+                barrier()
+                return time.perf_counter() - t0, rays
 
-        if sr_e is not sr:
-            e2e_frames(2 * depth)       # new destinations: let every slot re-capture its frame graph outside the timed region
-        t0, e_rays = e2e_frames(K)
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        er = torch.tensor([float(e_rays)], dtype=torch.float64, device=dev)
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX); dist.all_reduce(er, op=dist.ReduceOp.SUM)
-        e2e = {"value": float(er.item()) / float(dt.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 4 * (2 + 1 + 3 + 3) + 64,
-               "d2h_bytes_per_step": rt.width * rt.height * 16, "ms_per_step": float(dt.item()) / K * 1e3,
-               "path": "frames in shared host memory, every rank stores its tiles through its own PCIe link" if sr_e is not sr
-                       else "NVLink gather to rank 0, device-to-host copy on rank 0"}
-        if sr_e is not sr:
-            if rank == 0:
-                e2e["checksum"] = float(sr_e.frames[(K - 1) % depth].double().sum().item())   # the host frame is read, not just written
-            sr_e.close()
+            frames(2 * depth)           # new destinations: let every slot re-capture its frame graph outside the timed region
+            t, e_rays = frames(R * K)
+            dt = torch.tensor([t], dtype=torch.float64, device=dev); er = torch.tensor([float(e_rays)], dtype=torch.float64, device=dev)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX); dist.all_reduce(er, op=dist.ReduceOp.SUM)
+            out = {"value": float(er.item()) / float(dt.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 4 * (2 + 1 + 3 + 3) + 64,
+                   "d2h_bytes_per_step": rt.width * rt.height * (4 if rgba8 else 16), "ms_per_step": float(dt.item()) / (R * K) * 1e3,
+                   "frame": "R8G8B8A8_UNORM" if rgba8 else "float RGBA", "completion": sr_e.completion,
+                   "path": "frames in shared host memory, every rank stores its tiles through its own PCIe link" if sr_e is not sr
+                           else "NVLink gather to rank 0, device-to-host copy on rank 0"}
+            if sr_e is not sr:
+                if rank == 0:
+                    out["frame_hash"] = frame_hash(sr_e.frames[(R * K - 1) % depth])   # the host frame is read, not just written
+                sr_e.close()
+            return out
+
+        e2e = e2e_run(False)
+        r8 = e2e_run(True)
+        if r8 is not None:
+            e2e_extra["e2e_rgba8"] = r8
+
+    # the other configurations BASELINE.json names for scaling (C3, C5), one short measurement each at the same N
+    extra = {}
+    if args.extra and args.workload == "c2":
+        for name, frames_n in (("c3", 6), ("c5", 6)):
+            try:
+                extra[name] = run_extra(name, frames_n, rank, world, local, dev, barrier)
+            except Exception as e:      # never lose the headline line to an extra
+                extra[name] = {"error": str(e)[:200]}
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         b_ray = algorithmic_bytes_per_ray(sc.ntris)
         achieved = prof_rays * b_ray / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None
+        frame_bytes = rt.width * rt.height * 16
+        scene_bytes = sc.ntris * 48 + rt.build_stats["nodes"] * rt.build_stats["node_bytes"]
+        traffic = ncu_traffic(args.workload)
+        node_bytes = rt.build_stats["node_bytes"]
+        req_bytes = st_count["nodes_visited"] * node_bytes + st_count["tris_tested"] * 48       # what the traversal asks L1/L2 for, per frame
+        k_ms = trace_ms / max(trace_launches, 1)
         roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (achieved / peaks["hbm_gbs"]) if achieved else None,
-                "traffic": NCU_TRAFFIC_BYTES if args.workload == "c2" else None,
-                "kernel": "k_trace + k_phong + k_secondary (every closest-hit query of the frame)", "bytes_per_ray": b_ray,
-                "launch_ms_avg": trace_ms / max(trace_launches, 1), "launches_per_frame": trace_launches / max(n_prof, 1), "peak_kind": peak_kind,
+                "traffic": traffic.get("k_frame_dram_bytes") if traffic else None,
+                "kernel": "k_frame (the whole of trace() for every sample: closest hit, shading, shadow and secondary rays, resolve)", "bytes_per_ray": b_ray,
+                "launch_ms_avg": k_ms, "launches_per_frame": trace_launches / max(n_prof, 1), "peak_kind": peak_kind,
                 "frame_ms_unpipelined": prof_frame_ms / max(n_prof, 1),
-                "achieved_pipelined": value * 1e6 * b_ray / 1e9, "frac_pipelined": value * 1e6 * b_ray / 1e9 / peaks["hbm_gbs"],
-                "fp32": {"flop_per_ray": flop_per_ray(sc.ntris), "achieved_tflops": value * 1e6 * flop_per_ray(sc.ntris) / 1e12,
+                "achieved_pipelined": value / world * 1e6 * b_ray / 1e9, "frac_pipelined": value / world * 1e6 * b_ray / 1e9 / peaks["hbm_gbs"],
+                "algorithmic_min_frame_bytes": frame_bytes + scene_bytes,
+                "whole_frame_dram_bytes": traffic.get("frame_dram_bytes") if traffic else None,
+                "traversal": {"nodes_per_ray": st_count["nodes_visited"] / max(st_count["total"], 1), "tris_per_ray": st_count["tris_tested"] / max(st_count["total"], 1),
+                              "requested_bytes_per_frame": req_bytes, "requested_gbs": req_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None},
+                "l2": {"peak_gbs": l2, "requested_frac_of_l2_peak": (req_bytes / (k_ms * 1e-3) / 1e9 / l2) if (l2 and k_ms > 0) else None,
+                       "note": "peak = measured read bandwidth of a 32 MiB L2-resident buffer from all SMs (pgrt_debug_l2_bandwidth); requested = node and triangle "
+                               "bytes the traversal loads per frame (instrumented run) over the frame kernel's time: the working set is L1/L2-resident, so this, "
+                               "not HBM, is the memory roof that applies"},
+                "fp32": {"flop_per_ray": flop_per_ray(sc.ntris), "achieved_tflops": value / world * 1e6 * flop_per_ray(sc.ntris) / 1e12,
                          "peak_tflops": 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12,
-                         "note": "SURVEY 8(d) contract figure F_ray = 192*D + 180 on the pipelined whole-frame rate; peak = 148 SM x 128 lanes x 2 x max SM clock"},
-                "level0_trace_ms": lv[0]["trace_ms"] if lv else None, "secondary_ms": lv[1]["trace_ms"] if lv and len(lv) > 1 else None,
-                "note": "algorithmic bytes = SURVEY 8(d) contract figure (720 B/ray at this size) x rays of rank 0, over the summed device time of the "
-                        "traversal launches measured one frame at a time (CUDA events on the launching stream, L2 flushed before each frame); the "
-                        "working set is L2-resident and the kernels are issue-/latency-bound, see DESIGN.md 3.3.  achieved_pipelined = the same "
-                        "bytes over the timed, pipelined whole-frame rate (`value`): frames overlap, so it exceeds the one-at-a-time figure"}
+                         "note": "SURVEY 8(d) contract figure F_ray = 192*D + 180 on the per-GPU pipelined rate; peak = 148 SM x 128 lanes x 2 x max SM clock"},
+                "note": "achieved = SURVEY 8(d) contract bytes (720 B/ray at this size) x rays of rank 0 over the frame kernel's own time, one frame at a time "
+                        "(CUDA events on the launching stream, L2 flushed before each frame); *_pipelined = the same bytes over the per-GPU share of `value`"}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-               "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-               "data": "synthetic", "config": {"workload": desc, "triangles": sc.ntris, "rays_per_frame": total_rays / K,
-                                                "parallelism": f"tiles32x8/rr x{world}", "frames_in_flight": depth, "gather": sr.mode,
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic", "config": {"workload": desc, "triangles": sc.ntris, "rays_per_frame": rays_per_frame,
+                                                "parallelism": f"tiles32x8/rr x{world}", "frames_in_flight": depth, "gather": sr.mode, "completion": sr.completion,
+                                                "timing": f"median of {R - 1} consecutive windows of {K} steps each in one continuous pipeline (a first window fills it), "
+                                                          f"CUDA events on the consumer stream, max over ranks per window; {timed_s:.2f} s between the barriers",
+                                                "windows_ms_per_step": {"first": win[0] / K, "min": steady[0] / K, "median": ms_per_step, "max": steady[-1] / K},
                                                 "host_issue_us_per_step": host_issue[0] / max(host_issue[1], 1) * 1e6,
-                                                "host_issue_parts_us": dict(zip(("flush", "render_begin", "barrier", "event"), host_parts)),
+                                                "host_issue_parts_us": dict(zip(("flush", "render_begin", "completion", "event"), host_parts)),
                                                 "l2": f"flushed before every timed step on that step's stream ({FLUSH_BYTES >> 20} MiB fill = 1.125 x L2)",
                                                 "bvh": rt.build_stats},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(tot[1].item()), "roofline": roof}
+        out.update(e2e_extra)
+        if frame_equal is not None:
+            out["frame_equal_to_1gpu"] = frame_equal
+        if extra:
+            out["config"]["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(sc, p)
         print(json.dumps(out))
@@ -440,15 +542,64 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_extra(name, n_frames, rank, world, local, dev, barrier):
+    """A short measurement of another BASELINE.json configuration at the same N (own context; one continuous pipeline of
+    n_frames frames after as many warm-up frames).  Returns rank 0's summary."""
+    import torch
+    import torch.distributed as dist
+
+    from pgi_raytracing_b200 import raytracer_for, default_params
+    from pgi_raytracing_b200.dist import ShardedRenderer
+
+    sc, p, desc = workload(name)
+    rt = raytracer_for(sc, device=local)
+    params = default_params(**p)
+    depth = 2
+    sr = ShardedRenderer(rt, rank, world, dev, depth=depth)
+
+    def frames(n):
+        comm = torch.cuda.current_stream()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(comm)
+        for s in sr.slot_streams:
+            s.wait_event(e0)
+        rays = 0
+        for k in range(n):
+            if k >= depth:
+                rays += sr.end(k - depth)["total"]
+            sr.begin(k, params)
+        for k in range(max(0, n - depth), n):
+            rays += sr.end(k)["total"]
+        e1.record(comm)
+        barrier()
+        return e0.elapsed_time(e1), rays
+
+    frames(depth + 1)
+    ms, rays = frames(n_frames)
+    t = torch.tensor([ms, float(rays)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, rays = float(mx[0].item()), float(t[1].item())
+    out = {"workload": desc, "value": rays / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_frame": ms / n_frames, "frames": n_frames, "frames_in_flight": depth,
+           "triangles": sc.ntris, "build_ms": rt.build_stats["build_ms"], "node_bytes": rt.build_stats["node_bytes"], "completion": sr.completion,
+           "l2": "not flushed between frames (inputs per frame exceed L2 for c5; c3 writes 530 M samples per frame)"}
+    sr.close()
+    rt.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=0, help="frames in flight per GPU (1 = one frame at a time; 0 = 8, or 16 when a frame or shard has fewer than 1 M primary samples)")
+    ap.add_argument("--no-extra", dest="extra", action="store_false", help="skip the short C3 / C5 measurements appended to config.extra")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="the timed windows of --steps frames are repeated until they cover this much device time")
+    ap.add_argument("--inflight", type=int, default=0, help="frames in flight per GPU (1 = one frame at a time; 0 = 4, or 8 when a frame or shard has fewer than 1 M primary samples)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

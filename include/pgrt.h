@@ -102,7 +102,8 @@ typedef struct pgrt_render_stats {
     uint32_t batches;         /* sample batches the frame was cut into                           */
     uint32_t overflow_retries;
     uint32_t max_nodes_per_ray;   /* worst single query (profile & 2 renders only)             */
-    uint32_t reserved[4];
+    uint32_t reserved[4];     /* [0] pool records of the largest batch; fused scheduler, last batch: [1] frame kernel first warp in ..
+                                 last warp out (us), [2] .. until the primary rays ran out (us)   */
 } pgrt_render_stats;
 
 /* One recursion level of trace() (raytracer.cpp:237, `level`) in the last rendered frame. */
@@ -124,6 +125,14 @@ typedef struct pgrt_rayhit {
     float Ng_x, Ng_y, Ng_z, u, v;
     uint32_t primID, geomID, instID;
 } pgrt_rayhit;
+
+/* Layout-compatible with RTCRay (embree3/rtcore_ray.h:11-27), 48 bytes. */
+typedef struct pgrt_ray {
+    float org_x, org_y, org_z, tnear;
+    float dir_x, dir_y, dir_z, time;   /* time carries the IOR of the medium the ray travels in (raytracer.cpp:200,228,416) */
+    float tfar;
+    uint32_t mask, id, flags;
+} pgrt_ray;
 
 /* ---- lifetime: replaces Raytracer::InitDeviceAndScene / ReleaseDeviceAndScene (raytracer.cpp:26-46),
  *      i.e. rtcNewDevice + rtcNewScene / rtcReleaseScene + rtcReleaseDevice.  `device` = CUDA ordinal. */
@@ -241,7 +250,17 @@ int pgrt_intersect(pgrt_context* ctx, pgrt_rayhit* rayhits_host, uint64_t n);
 int pgrt_interpolate(pgrt_context* ctx, const uint32_t* geom_id, const uint32_t* prim_id, const float* u, const float* v,
                      uint64_t n, int32_t slot, float* out_host);
 
-/* ---- device implementations of the path's leaf functions, exposed for per-function parity tests */
+/* ---- the two public query methods of the class (raytracer.h:31, :34) over batches.
+ *      pgrt_trace: Color4f Raytracer::trace(RTCRay ray, int level) (raytracer.cpp:237-394) for n caller-supplied rays, all at
+ *      recursion level `level`; rgba_host receives n x 4 floats.  Only shader_mode, max_depth, shadow_mode and seed of p apply.
+ *      pgrt_is_illuminated: bool Raytracer::is_illuminated(LightSource, Vector3 hit_position, Vector3 normal) (:150-176) for n
+ *      (light position, hit position, normal) triples of 3 floats each; lit_host receives 0 / 1. */
+int pgrt_trace(pgrt_context* ctx, const pgrt_render_params* p, const pgrt_ray* rays_host, uint64_t n, int32_t level, float* rgba_host);
+int pgrt_is_illuminated(pgrt_context* ctx, const pgrt_render_params* p, const float* light_pos3, const float* hit_pos3, const float* normal3,
+                        uint64_t n, int32_t* lit_host);
+
+/* ---- TESTING: device implementations of the path's leaf functions, exposed for per-function parity tests (not part of the
+ *      drop-in surface; a binding may ignore everything from here to "introspection") */
 int pgrt_eval_mix_srgb(pgrt_context* ctx, const float* c0, const float* c1, const float* alpha, uint64_t n, float* out);  /* utils.cpp:238-241 */
 int pgrt_eval_texture(pgrt_context* ctx, int32_t tex_id, const float* uv, uint64_t n, float* out3);  /* Texture::get_texel texture.cpp:77-130; id -1 = env texture */
 int pgrt_eval_envmap(pgrt_context* ctx, const float* dirs, uint64_t n, float* out4);                 /* SphericalMap::get_texel SphericalMap.cpp:17-29 */
@@ -249,9 +268,12 @@ int pgrt_eval_gamma(pgrt_context* ctx, const float* in4, float gamma_level, uint
 int pgrt_eval_primary_rays(pgrt_context* ctx, const pgrt_render_params* p, float* out9);             /* get_pixel :405-416 + generate_ray; 9 floats/ray */
 int pgrt_eval_secondary_rays(pgrt_context* ctx, const float* in11, uint64_t n, int32_t refraction, float* out9);  /* raytracer.cpp:178-235 */
 
-/* ---- measurement helper: stream `bytes` of writes through a scratch buffer on the slot's stream (evicts the 126 MB L2
+/* ---- TESTING / measurement helper: stream `bytes` of writes through a scratch buffer on the slot's stream (evicts the 126 MB L2
  *      when bytes exceeds it); benchmarks call it before every timed frame */
 int pgrt_debug_flush_l2(pgrt_context* ctx, int32_t slot, uint64_t bytes, uint32_t value);
+/* read bandwidth (GB/s) of a `bytes`-sized buffer that stays L2-resident, from all SMs with L1 bypassed, `iters` passes:
+ * the memory roof that applies while a scene's nodes and triangles fit L2 */
+int pgrt_debug_l2_bandwidth(pgrt_context* ctx, uint64_t bytes, int32_t iters, float* gb_per_s);
 
 /* ---- introspection */
 uint32_t pgrt_num_triangles(const pgrt_context* ctx);

@@ -7,17 +7,23 @@
 // legs may load this library; the CUDA product never links, imports or calls it.
 //
 // PINNING STATUS
-//   * pinned against the only known answers the reference holds for this path:
-//       T1  tutorials.cpp:39-41,67-69,87-97  (one triangle, one ray: t=2,u=.05,v=.0667,
-//           normal (0,0,1), uv (0.050,0.933))
+//   * pinned to the reference's OWN object code above the Embree boundary: oracle/ref.mk compiles the unmodified pg1/*.cpp
+//     (raytracer, PinHoleCamera, LightSource, SphericalMap, texture, utils, vector3, matrix3x3, material, objloader, tutorials, ...)
+//     into oracle/_ref/libpg_ref.so over stub Embree / FreeImage / window layers, and tests/test_oracle_vs_ref.py holds this file
+//     to it BIT FOR BIT: Raytracer::trace at levels 0..7 on 12 000 rays per scene, whole un-jittered frames, is_illuminated,
+//     both ray makers, both camera overloads, mix_srgb, gamma, Texture::get_texel, SphericalMap::get_texel, LoadOBJ / LoadMTL,
+//     and the reference's own tutorial_1 / tutorial_2 print-outs; the shipped (clock-seeded) get_pixel as a converged mean.
+//   * and to the known answers the reference holds for this path:
+//       T1  tutorials.cpp:39-41,67-69,87-97  (one triangle, one ray: t=2,u=.05,v=.0667, normal (0,0,1), uv (0.050,0.933))
 //       T2  tutorials.cpp:173-175 + data/test4.png (texel (r=1.000,g=0.000,b=0.500))
 //       MTL data/6887_allied_avenger.mtl (5 materials, Ks parses to (1.0,0.8,0.8))
-//   * PARITY UNPINNED at the Embree boundary: the intersection arithmetic lives in
-//     Intel Embree 3.11.0 (embree3.lib, not vendored, emb/include/embree3/rtcore_config.h:6-10);
-//     no reference test pins rtcIntersect1 results.  Its published algorithm
-//     (Moeller-Trumbore as formulated in Embree's TriangleM intersector: C=v0-O, R=C x D,
-//     den=Ng.D, U=R.e2, V=R.e1, T=Ng.C, sign-folded, tnear < t <= tfar, no culling) is
-//     restated here with IEEE division in place of Embree's rcp+Newton step.
+//   * PARITY UNPINNED only at the Embree boundary itself: the intersection arithmetic lives in Intel Embree 3.11.0
+//     (embree3.lib, not vendored, emb/include/embree3/rtcore_config.h:6-10); no reference test pins rtcIntersect1 results, and
+//     the stub of oracle/_ref calls THIS file's intersector.  Embree's published algorithm (Moeller-Trumbore as formulated in
+//     its TriangleM intersector: C=v0-O, R=C x D, den=Ng.D, U=R.e2, V=R.e1, T=Ng.C, sign-folded, tnear < t <= tfar, no
+//     culling) is restated here with IEEE division in place of Embree's rcp+Newton step.
+//   * The one place the reference has no defined behaviour: Texture::get_pixel reads out of bounds for u >= 1 or outside
+//     [0,1] (texture.cpp:56-62, tiled UVs); this file clamps the texel index, and so does the CUDA path.
 //
 // ARITHMETIC CONVENTIONS (the CUDA path states the same ones independently)
 //   * FP32 everywhere the reference uses float; double only where the reference promotes

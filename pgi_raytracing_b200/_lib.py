@@ -83,6 +83,7 @@ SYMBOLS = {
     "pgrt_host_frame_register": (C.c_int, [_VP, _VP, _U64, C.POINTER(_VP)]),
     "pgrt_host_frame_unregister": (C.c_int, [_VP, _VP]),
     "pgrt_debug_flush_l2": (C.c_int, [_VP, _I32, _U64, _U32]),
+    "pgrt_debug_l2_bandwidth": (C.c_int, [_VP, _U64, _I32, C.POINTER(_F)]),
     "pgrt_enable_peer_access": (C.c_int, [_VP, _I32]),
     "pgrt_render_shard_to_frame_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),
     "pgrt_render_rgba8": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, C.POINTER(RenderStats), _I32]),
@@ -103,6 +104,8 @@ SYMBOLS = {
     "pgrt_untile_on_stream": (C.c_int, [_VP, _VP, _I32, _VP, _VP]),
     "pgrt_intersect": (C.c_int, [_VP, _VP, _U64]),
     "pgrt_interpolate": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _U64, _I32, _VP]),
+    "pgrt_trace": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _U64, _I32, _VP]),
+    "pgrt_is_illuminated": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _VP, _VP, _U64, _VP]),
     "pgrt_eval_mix_srgb": (C.c_int, [_VP, _VP, _VP, _VP, _U64, _VP]),
     "pgrt_eval_texture": (C.c_int, [_VP, _I32, _VP, _U64, _VP]),
     "pgrt_eval_envmap": (C.c_int, [_VP, _VP, _U64, _VP]),

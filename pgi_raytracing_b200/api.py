@@ -122,7 +122,7 @@ class Raytracer:
                  frame_ms=rs.frame_ms, trace_ms=rs.trace_ms, shade_ms=rs.shade_ms, trace_launches=rs.trace_launches,
                  launches=rs.launches, batches=rs.batches, overflow_retries=rs.overflow_retries,
                  nodes_visited=rs.nodes_visited, tris_tested=rs.tris_tested, max_nodes_per_ray=rs.max_nodes_per_ray,
-                 pool_peak=rs.reserved[0])
+                 pool_peak=rs.reserved[0], kernel_us=rs.reserved[1], primary_phase_us=rs.reserved[2])
         d["total"] = d["primary"] + d["shadow"] + d["reflection"] + d["refraction"]
         return d
 
@@ -229,6 +229,12 @@ class Raytracer:
         """Measurement helper (``pgrt_debug_flush_l2``): evict L2 on the slot's stream before a timed frame."""
         self._check(self.lib.pgrt_debug_flush_l2(self.h, slot, nbytes, value))
 
+    def l2_bandwidth(self, nbytes: int = 32 << 20, iters: int = 50) -> float:
+        """Measurement helper (``pgrt_debug_l2_bandwidth``): GB/s of an L2-resident buffer read from all SMs, L1 bypassed."""
+        g = C.c_float()
+        self._check(self.lib.pgrt_debug_l2_bandwidth(self.h, nbytes, iters, C.byref(g)))
+        return float(g.value)
+
     def enable_peer_access(self, peer_device: int):
         self._check(self.lib.pgrt_enable_peer_access(self.h, peer_device))
 
@@ -292,6 +298,26 @@ class Raytracer:
         out = np.empty((geom.shape[0], 3 if slot == 0 else 2), np.float32)
         self._check(self.lib.pgrt_interpolate(self.h, _ptr(geom), _ptr(prim), _ptr(u), _ptr(v), geom.shape[0], slot, _ptr(out)))
         return out
+
+    # ---- the two public query methods of the class (pg1/raytracer.h:31, :34)
+    def trace(self, rays9, level: int = 0, params=None) -> np.ndarray:
+        """``Color4f trace(RTCRay ray, int level)`` over a batch: rays9 [n, 9] = (org, tnear, dir, time, tfar) -> [n, 4]."""
+        p = self._params(params)
+        rays9 = np.ascontiguousarray(rays9, np.float32)
+        rays = np.zeros((rays9.shape[0], 12), np.float32); rays[:, :9] = rays9      # RTCRay: mask, id, flags = 0
+        out = np.empty((rays9.shape[0], 4), np.float32)
+        self._check(self.lib.pgrt_trace(self.h, C.byref(p), _ptr(rays), rays.shape[0], int(level), _ptr(out)))
+        return out
+
+    def is_illuminated(self, light, hit, normal, params=None) -> np.ndarray:
+        """``bool is_illuminated(LightSource light, Vector3 hit_position, Vector3 normal)`` over a batch -> bool [n]."""
+        p = self._params(params)
+        hit = np.ascontiguousarray(np.asarray(hit, np.float32).reshape(-1, 3)); n = hit.shape[0]
+        light = np.ascontiguousarray(np.broadcast_to(np.asarray(light, np.float32).reshape(-1, 3), (n, 3)))
+        normal = np.ascontiguousarray(np.broadcast_to(np.asarray(normal, np.float32).reshape(-1, 3), (n, 3)))
+        out = np.empty(n, np.int32)
+        self._check(self.lib.pgrt_is_illuminated(self.h, C.byref(p), _ptr(light), _ptr(hit), _ptr(normal), n, _ptr(out)))
+        return out.astype(bool)
 
     # ---- device leaf functions (per-function parity)
     def mix_srgb(self, c0, c1, alpha):

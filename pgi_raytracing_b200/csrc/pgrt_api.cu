@@ -6,18 +6,33 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <mutex>
 #include "common.cuh"
 #include "bvh_build.cuh"
 #include "render.cuh"
 
 namespace {
 
+// cudaFree synchronises the whole device.  A buffer that grows while frames are in flight (a queue-overflow retry inside
+// pgrt_render_end, the first frame of another slot) must not do that: a consumer stream may be parked on a completion flag
+// (pgrt_stream_wait_slot, dist.ShardedRenderer) that only the work we are about to enqueue will set, and the free would wait
+// for that stream for ever.  Outgrown buffers go to a graveyard that is emptied where everything is synchronised anyway
+// (pgrt_commit, pgrt_destroy).
+std::mutex g_graveyard_lock;
+std::vector<void*> g_graveyard;
+void deferred_free(void* p) { std::lock_guard<std::mutex> g(g_graveyard_lock); g_graveyard.push_back(p); }
+void drain_graveyard() {
+    std::vector<void*> v;
+    { std::lock_guard<std::mutex> g(g_graveyard_lock); v.swap(g_graveyard); }
+    for (void* p : v) cudaFree(p);
+}
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr; size_t n = 0;
     cudaError_t ensure(size_t count) {
         if (count <= n) return cudaSuccess;
-        if (p) cudaFree(p);
+        if (p) deferred_free(p);
         p = nullptr; n = 0;
         cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
         if (e == cudaSuccess) n = count;
@@ -47,7 +62,7 @@ struct FrameSlot {
     std::vector<int> ev_class, ev_level;
     size_t ev_used = 0;
     cudaEvent_t ev_frame0 = nullptr, ev_frame1 = nullptr, ev_done = nullptr;
-    int frame_grid = 0;               // CTAs of this frame's k_frame (sized in frame_begin)
+    int frame_grid = 0, keep_ctas = 0; // CTAs of this frame's k_frame, and how many of them stay until the batch is done (sized in frame_begin)
     // the frame in flight
     bool busy = false;
     pgrt_render_params params = {};
@@ -122,6 +137,8 @@ struct pgrt_context {
     FrameSlot slots[PGRT_MAX_INFLIGHT];
     int frame_per_sm_max = 0, frame_per_sm_env = 0;   // occupancy bound of k_frame; PGRT_FRAME_CTAS_PER_SM
     int min_claim = 32;               // k_frame takes pool records ahead of primary rays once this many wait (PGRT_MIN_CLAIM, 1..32)
+    int keep_per_sm = 1;              // CTAs per SM of k_frame that stay until the batch is done (PGRT_KEEP_CTAS_PER_SM)
+    int claim_patience = 4;           // polls after which an idle warp of k_frame halves the number of pool records it waits for (PGRT_CLAIM_PATIENCE)
     double pool_scale = 1.0;          // grown after a pool overflow; never shrinks before the next pgrt_commit
     // driver entry points for stream memory operations (completion flags without a collective); null = not available
     void* fn_wait32 = nullptr; void* fn_write32 = nullptr;
@@ -196,6 +213,8 @@ extern "C" int pgrt_create(pgrt_context** out, int device) {
     if (const char* e = getenv("PGRT_TRACE_REFILL")) ctx->trace_refill = std::min(32, std::max(1, atoi(e)));
     if (const char* e = getenv("PGRT_TRACE_CTAS_PER_SM")) ctx->trace_ctas_per_sm = std::min(16, std::max(1, atoi(e)));
     if (const char* e = getenv("PGRT_MIN_CLAIM")) ctx->min_claim = std::min(32, std::max(1, atoi(e)));
+    if (const char* e = getenv("PGRT_KEEP_CTAS_PER_SM")) ctx->keep_per_sm = std::min(32, std::max(1, atoi(e)));
+    if (const char* e = getenv("PGRT_CLAIM_PATIENCE")) ctx->claim_patience = std::min(1 << 20, std::max(1, atoi(e)));
     {   // cuStreamWaitValue32 / cuStreamWriteValue32 through the runtime (no link-time dependency on libcuda)
         cudaDriverEntryPointQueryResult qr;
         if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &ctx->fn_wait32, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) ctx->fn_wait32 = nullptr;
@@ -231,6 +250,7 @@ extern "C" void pgrt_destroy(pgrt_context* ctx) {
     ctx->acc_sum.release(); for (auto& b : ctx->acc_frames) b.release(); if (ctx->acc_event) cudaEventDestroy(ctx->acc_event);
     for (int k = 0; k < 2; ++k) { if (ctx->stage[k]) cudaFreeHost(ctx->stage[k]); if (ctx->stage_done[k]) cudaEventDestroy(ctx->stage_done[k]); }
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    drain_graveyard();
     delete ctx;
 }
 
@@ -391,6 +411,7 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
     CHECK_CTX(ctx);
     cudaSetDevice(ctx->device);
     sync_all_slots(ctx);
+    drain_graveyard();
     cudaStream_t st = ctx->stream;
     const uint32_t N = ctx->n_added;   // the geometry is on the device already (pgrt_add_mesh streams it)
     ctx->n_tris = N; ctx->px_valid = false; ctx->batch_limit = 0; ctx->pool_scale = 1.0;
@@ -708,11 +729,11 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
         if (fused) {
             tm.begin(KC_TRACE, 0);
             if (path) {
-                if (count) k_frame<true, true><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, cnt);
-                else k_frame<false, true><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, cnt);
+                if (count) k_frame<true, true><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, cnt);
+                else k_frame<false, true><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, cnt);
             } else {
-                if (count) k_frame<true, false><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, cnt);
-                else k_frame<false, false><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, cnt);
+                if (count) k_frame<true, false><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, cnt);
+                else k_frame<false, false><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, cnt);
             }
             rs.launches++; rs.trace_launches++;
             tm.end();
@@ -794,7 +815,7 @@ static uint64_t frame_key(pgrt_context* ctx, const FrameSlot& S) {
     h = fnv1a(S.levels, sizeof(LevelBufs) * (size_t)(S.n_levels + 1), h); h = fnv1a(&S.pool, sizeof S.pool, h);
     const void* extra[4] = {S.d_frame.p, S.d_counters.p, S.stream, S.sig_flag};
     h = fnv1a(extra, sizeof extra, h);
-    const int flags[7] = {S.fused ? 1 : 0, ctx->fuse_raygen ? 1 : 0, S.frame_grid, ctx->trace_refill, ctx->trace_ctas_per_sm, S.fmt, ctx->min_claim};
+    const int flags[9] = {S.fused ? 1 : 0, ctx->fuse_raygen ? 1 : 0, S.frame_grid, ctx->trace_refill, ctx->trace_ctas_per_sm, S.fmt, ctx->min_claim, S.keep_ctas, ctx->claim_patience};
     return fnv1a(flags, sizeof flags, h) | 1ull;
 }
 
@@ -886,6 +907,9 @@ static int frame_begin(pgrt_context* ctx, int slot, const pgrt_render_params* p,
         int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * per_sm, std::max<uint64_t>(1, (samples + 511) / 512));
         if (const char* e = getenv("PGRT_FRAME_CTAS")) grid = std::max(1, atoi(e));
         S.frame_grid = grid;
+        // one CTA per SM stays for the dependent chains of the secondary rays (4 warps x 148 SMs take 19 k rays at a time: more
+        // than any level of a Whitted frame holds at once); the rest leave when they run dry, so the next frame's kernel finds room
+        S.keep_ctas = std::min(grid, ctx->sm_count * ctx->keep_per_sm);
     }
     S.rs = pgrt_render_stats{};
     rc = enqueue_frame(ctx, S);
@@ -902,6 +926,7 @@ static int frame_end(pgrt_context* ctx, int slot, pgrt_render_stats* stats) {
     S.busy = false;
     for (;;) {
         CUDA_TRY(cudaStreamSynchronize(S.stream));
+        if (S.h_counters->watchdog) { S.seq_expected = S.h_counters->done_seq; return ctx->fail(PGRT_ERR_CUDA, "render: internal error in the frame kernel (a bounded wait expired; the frame is incomplete)"); }
         if (!S.h_counters->overflow) break;
         // A secondary-ray queue overflowed (rare; sizes are generous): the attempt did not signal completion (k_batch_end), so
         // no consumer ordered behind this slot has been released.  Render the frame again with four times the capacity -
@@ -937,6 +962,10 @@ static int frame_end(pgrt_context* ctx, int slot, pgrt_render_stats* stats) {
         if (S.ev_class[k / 2] == KC_TRACE) { rs.trace_ms += ms; ls.trace_ms += ms; } else { rs.shade_ms += ms; ls.shade_ms += ms; }
     }
     rs.reserved[0] = hc.q_peak;   // pool records of the largest batch (introspection; sizes PGRT_LEVEL_CAP_FACTOR)
+    if (S.fused && hc.t_last > hc.t_first && hc.t_first != ~0ull) {   // phases of the (last batch's) frame kernel, microseconds
+        rs.reserved[1] = (uint32_t)((hc.t_last - hc.t_first) / 1000ull);
+        rs.reserved[2] = hc.t_primary_done > hc.t_first ? (uint32_t)((hc.t_primary_done - hc.t_first) / 1000ull) : 0u;
+    }
     if (stats) *stats = rs;
     return PGRT_OK;
 }
@@ -1000,6 +1029,11 @@ extern "C" int pgrt_render_accumulate(pgrt_context* ctx, const pgrt_render_param
     for (int s = 0; s < D; ++s) CUDA_TRY(ctx->acc_frames[s].ensure(n));
     if (!ctx->acc_event) CUDA_TRY(cudaEventCreateWithFlags(&ctx->acc_event, cudaEventDisableTiming));
     const unsigned blocks = (unsigned)div_up(n, 256);
+    // whatever way this function is left, no slot it started stays marked busy (later renders use slot 0 .. 3)
+    struct SlotGuard {
+        pgrt_context* c; int d; bool armed = true;
+        ~SlotGuard() { if (!armed) return; sync_all_slots(c); for (int s = 0; s < d; ++s) c->slots[s].busy = false; }
+    } guard{ctx, D};
     for (int attempt = 0;; ++attempt) {
         pgrt_render_stats total = {}, rs;
         bool overflowed = false;
@@ -1093,7 +1127,7 @@ extern "C" int pgrt_stream_wait_value32(pgrt_context* ctx, void* cuda_stream, vo
     if (!flag_device) return ctx->fail(PGRT_ERR_INVALID, "pgrt_stream_wait_value32: null flag");
     if (!ctx->fn_wait32) return ctx->fail(PGRT_ERR_CUDA, "pgrt_stream_wait_value32: the driver does not export cuStreamWaitValue32");
     cudaSetDevice(ctx->device);
-    const int rc = ((pgrt_cu_memop32)ctx->fn_wait32)((cudaStream_t)cuda_stream, (unsigned long long)(uintptr_t)flag_device, value, 0x1u /* CU_STREAM_WAIT_VALUE_GEQ */);
+    const int rc = ((pgrt_cu_memop32)ctx->fn_wait32)((cudaStream_t)cuda_stream, (unsigned long long)(uintptr_t)flag_device, value, 0x0u /* CU_STREAM_WAIT_VALUE_GEQ */);
     if (rc != 0) return ctx->fail(PGRT_ERR_CUDA, "pgrt_stream_wait_value32: cuStreamWaitValue32 failed with CUresult " + std::to_string(rc));
     return PGRT_OK;
 }
@@ -1178,6 +1212,45 @@ extern "C" int pgrt_debug_flush_l2(pgrt_context* ctx, int32_t slot, uint64_t byt
     return PGRT_OK;
 }
 
+// measurement helper: read bandwidth of an L2-resident buffer from all SMs (the memory roof of scenes whose nodes and
+// triangles fit L2).  ld.global.cg: the loads bypass L1, so every byte crosses the L2 -> SM fabric.
+__global__ void __launch_bounds__(256) k_l2_read(const uint4* __restrict__ buf, size_t n, int iters, uint32_t* __restrict__ sink) {
+    uint32_t acc = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    for (int it = 0; it < iters; ++it)
+        for (size_t i = i0; i + 3 * stride < n; i += 4 * stride) {     // four independent 16-byte loads in flight per thread
+            const uint4 a = __ldcg(buf + i), b = __ldcg(buf + i + stride), c = __ldcg(buf + i + 2 * stride), d = __ldcg(buf + i + 3 * stride);
+            acc += a.x ^ b.y ^ c.z ^ d.w;
+        }
+    if (acc == 0x9E3779B9u) *sink = acc;      // keeps the loads alive; practically never true
+}
+extern "C" int pgrt_debug_l2_bandwidth(pgrt_context* ctx, uint64_t bytes, int32_t iters, float* gb_per_s) {
+    CHECK_CTX(ctx);
+    if (!gb_per_s || bytes < (1u << 20) || iters < 1) return ctx->fail(PGRT_ERR_INVALID, "pgrt_debug_l2_bandwidth: bad arguments");
+    cudaSetDevice(ctx->device);
+    sync_all_slots(ctx);
+    const size_t n = bytes / 16;
+    CUDA_TRY(ctx->flush_buf.ensure(n + 1));
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(cudaMemsetAsync(ctx->flush_buf.p, 1, n * 16, st));
+    const int grid = ctx->sm_count * 8;
+    const size_t per_iter = (n / ((size_t)grid * 256 * 4)) * ((size_t)grid * 256 * 4);     // elements one pass really reads
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    k_l2_read<<<grid, 256, 0, st>>>(ctx->flush_buf.p, n, 2, (uint32_t*)(ctx->flush_buf.p + n));      // warm: the buffer becomes L2-resident
+    cudaEventRecord(e0, st);
+    k_l2_read<<<grid, 256, 0, st>>>(ctx->flush_buf.p, n, iters, (uint32_t*)(ctx->flush_buf.p + n));
+    cudaEventRecord(e1, st);
+    ctx->launches += 2;
+    cudaError_t e = cudaStreamSynchronize(st);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CUDA_TRY(e);
+    *gb_per_s = ms > 0.f ? (float)((double)per_iter * 16.0 * iters / (ms * 1e-3) / 1e9) : 0.f;
+    return PGRT_OK;
+}
+
 extern "C" int pgrt_enable_peer_access(pgrt_context* ctx, int32_t peer_device) {
     CHECK_CTX(ctx);
     cudaSetDevice(ctx->device);
@@ -1202,7 +1275,7 @@ extern "C" int pgrt_stream_wait_slot(pgrt_context* ctx, int32_t slot, void* cuda
     // The slot's completion count only moves for a frame that finished WITHOUT a queue overflow: a consumer ordered here is
     // not released by an attempt whose retry (pgrt_render_end) is still to come.  Without stream memory operations the
     // event of the last enqueue is all there is; then a frame is only known to be good once pgrt_render_end has returned.
-    if (ctx->fn_wait32 && ((pgrt_cu_memop32)ctx->fn_wait32)((cudaStream_t)cuda_stream, (unsigned long long)(uintptr_t)&S.d_counters.p->done_seq, S.seq_expected, 0x1u) == 0) return PGRT_OK;
+    if (ctx->fn_wait32 && ((pgrt_cu_memop32)ctx->fn_wait32)((cudaStream_t)cuda_stream, (unsigned long long)(uintptr_t)&S.d_counters.p->done_seq, S.seq_expected, 0x0u /* GEQ */) == 0) return PGRT_OK;
     CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)cuda_stream, S.ev_done, 0));
     return PGRT_OK;
 }
@@ -1326,6 +1399,51 @@ extern "C" int pgrt_interpolate(pgrt_context* ctx, const uint32_t* geom, const u
     if (!dg || !dp || !du || !dv || !dout) return ctx->fail(PGRT_ERR_CUDA, "pgrt_interpolate: allocation failed");
     k_interpolate<<<div_up(n, 256), 256, 0, ctx->stream>>>(ctx->dev_scene(), (uint32_t*)dg, (uint32_t*)dp, (float*)du, (float*)dv, n, slot, (float*)dout);
     EVAL_FINISH(dout, out, n * w * 4);
+}
+
+// Raytracer::trace / Raytracer::is_illuminated over batches (the two public query methods of the class, raytracer.h:31,34)
+extern "C" int pgrt_trace(pgrt_context* ctx, const pgrt_render_params* p, const pgrt_ray* rays, uint64_t n, int32_t level, float* rgba) {
+    CHECK_CTX(ctx);
+    if (n == 0) return PGRT_OK;
+    if (!p || !rays || !rgba || level < 0) return ctx->fail(PGRT_ERR_INVALID, "pgrt_trace: bad arguments");
+    if (!ctx->committed) return ctx->fail(PGRT_ERR_INVALID, "pgrt_trace: scene not committed");
+    if (p->max_depth < 0 || p->max_depth >= PGRT_MAX_LEVELS) return ctx->fail(PGRT_ERR_INVALID, "pgrt_trace: max_depth out of range [0,32]");
+    if (p->shadow_mode != 0 && p->shadow_mode != 1) return ctx->fail(PGRT_ERR_INVALID, "pgrt_trace: shadow_mode must be 0 or 1");
+    int rc = upload_tables(ctx); if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    static_assert(sizeof(pgrt_ray) == 48, "RTCRay layout");
+    const uint64_t chunk = std::min<uint64_t>(n, 1u << 17);   // one explicit recursion stack per ray in flight
+    Scratch s;
+    void* d_rays = s.up(nullptr, chunk * sizeof(pgrt_ray), ctx->stream); void* d_out = s.up(nullptr, chunk * 16, ctx->stream);
+    void* d_stk = s.up(nullptr, chunk * (PGRT_MAX_LEVELS + 1) * sizeof(TraceFrame), ctx->stream);
+    if (!d_rays || !d_out || !d_stk) return ctx->fail(PGRT_ERR_CUDA, "pgrt_trace: allocation failed");
+    const DevScene sc = ctx->dev_scene();
+    for (uint64_t i0 = 0; i0 < n; i0 += chunk) {
+        const uint64_t m = std::min(chunk, n - i0);
+        CUDA_TRY(cudaMemcpyAsync(d_rays, rays + i0, m * sizeof(pgrt_ray), cudaMemcpyHostToDevice, ctx->stream));
+        if (p->shader_mode == 3) k_trace_rays<true><<<div_up(m, 128), 128, 0, ctx->stream>>>(sc, *p, (const pgrt_ray*)d_rays, m, level, (float4*)d_out, (TraceFrame*)d_stk, ctx->slots[0].d_counters.p);
+        else k_trace_rays<false><<<div_up(m, 128), 128, 0, ctx->stream>>>(sc, *p, (const pgrt_ray*)d_rays, m, level, (float4*)d_out, (TraceFrame*)d_stk, ctx->slots[0].d_counters.p);
+        ctx->launches++;
+        LAUNCH_OK();
+        CUDA_TRY(cudaMemcpyAsync(rgba + 4 * i0, d_out, m * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return PGRT_OK;
+}
+
+extern "C" int pgrt_is_illuminated(pgrt_context* ctx, const pgrt_render_params* p, const float* light, const float* hit, const float* nrm, uint64_t n, int32_t* lit) {
+    CHECK_CTX(ctx);
+    if (n == 0) return PGRT_OK;
+    if (!p || !light || !hit || !nrm || !lit) return ctx->fail(PGRT_ERR_INVALID, "pgrt_is_illuminated: bad arguments");
+    if (!ctx->committed) return ctx->fail(PGRT_ERR_INVALID, "pgrt_is_illuminated: scene not committed");
+    if (p->shadow_mode != 0 && p->shadow_mode != 1) return ctx->fail(PGRT_ERR_INVALID, "pgrt_is_illuminated: shadow_mode must be 0 or 1");
+    int rc = upload_tables(ctx); if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    Scratch s;
+    void* dl = s.up(light, n * 12, ctx->stream); void* dh = s.up(hit, n * 12, ctx->stream); void* dn = s.up(nrm, n * 12, ctx->stream); void* o = s.up(nullptr, n * 4, ctx->stream);
+    if (!dl || !dh || !dn || !o) return ctx->fail(PGRT_ERR_CUDA, "pgrt_is_illuminated: allocation failed");
+    k_is_illuminated<<<div_up(n, 128), 128, 0, ctx->stream>>>(ctx->dev_scene(), *p, (const float*)dl, (const float*)dh, (const float*)dn, n, (int32_t*)o);
+    EVAL_FINISH(o, lit, n * 4);
 }
 
 extern "C" int pgrt_eval_mix_srgb(pgrt_context* ctx, const float* c0, const float* c1, const float* alpha, uint64_t n, float* out) {

@@ -81,8 +81,14 @@ struct Counters {
     uint32_t lv_max_nodes[PGRT_MAX_LEVELS + 1], lv_sh_max_nodes[PGRT_MAX_LEVELS + 1];
     // fused scheduler: pool records allocated / claimed; epoch = batches begun on this slot (publication word of the records);
     // done_seq = frames finished without a queue overflow (the completion flag of the slot, see k_batch_end)
-    uint32_t q_tail, q_head, epoch, done_seq;
-    uint32_t sig_value, pad2[3];   // what a finished frame stores in the slot's external completion flag (pgrt_slot_signal)
+    // The three words a warp of k_frame looks at before every claim sit in one aligned 16-byte group (one volatile load):
+    // outstanding = primary chunks + published pool records not yet fully processed (0 = batch done)
+    alignas(16) uint32_t q_tail;
+    uint32_t q_head, outstanding, epoch;
+    uint32_t done_seq;
+    uint32_t sig_value;     // what a finished frame stores in the slot's external completion flag (pgrt_slot_signal)
+    uint32_t pad2[2];
+    unsigned long long t_first, t_primary_done, t_last;   // fused scheduler: %globaltimer marks (ns): first warp in, primary rays exhausted, last warp out
     uint32_t trace_next[PGRT_MAX_LEVELS + 1];   // k_trace: rays of the level's queue claimed so far
 };
 
@@ -375,6 +381,55 @@ __device__ __forceinline__ void shade_classify(const DevScene& sc, const pgrt_re
 //      LightSource::GenerateRay LightSource.cpp:11-32)
 struct TravAcc { unsigned long long nodes, tris; uint32_t mx; };
 
+// closest hit as its own function: one copy of the traversal loop per node layout whatever the number of call sites,
+// and the register allocation of that loop is not mixed with the shading code around it
+#ifdef PGRT_TRACE_INLINE
+#define PGRT_TRACE_DEV_ATTR __forceinline__
+#else
+#define PGRT_TRACE_DEV_ATTR __noinline__
+#endif
+template <bool COUNT>
+__device__ PGRT_TRACE_DEV_ATTR HitRec trace_dev(const DevScene& sc, V3 O, V3 D, float tnear, float tfar, TravCount& tc) {
+    return trace_closest_t<COUNT>(sc, O, D, tnear, tfar, tc);
+}
+
+
+// Raytracer::is_illuminated (raytracer.cpp:150-176) with LightSource::GenerateRay (LightSource.cpp:11-32)
+template <bool COUNT>
+__device__ __forceinline__ bool is_illuminated_dev(const DevScene& sc, const pgrt_render_params& p, V3 lp, V3 hitp, V3 n, unsigned long long& my_shadow, TravAcc& acc) {
+    bool lit = false;
+    if (p.shadow_mode == 1) {
+        // README "To do: hard shadows" (README.md:20), behind a non-default flag: the ray the reference meant to
+        // cast -- from the hit point towards the light, in units of that segment -- with the same rule that the
+        // closest occluder decides and a dielectric one does not shadow.  Not part of the parity contract.
+        const V3 to_light = v3(lp.x - hitp.x, lp.y - hitp.y, lp.z - hitp.z);
+        if (!(dot3(n, to_light) < 0)) {
+            my_shadow++;
+            TravCount tc; tc.nodes = 0; tc.tris = 0;
+            const HitRec sh = trace_dev<COUNT>(sc, hitp, to_light, 1e-3f, 1.0f, tc);
+            if (COUNT) { acc.nodes += tc.nodes; acc.tris += tc.tris; acc.mx = max(acc.mx, tc.nodes); }
+            if (sh.tri == PGRT_INVALID_ID) lit = true;
+            else {
+                const uint32_t g = __float_as_uint(__ldg(sc.shade + 4 * (size_t)sh.tri + 3).w);
+                lit = sc.materials[sc.geom_material[g]].type == 4;
+            }
+        }
+    } else if (!(dot3(n, lp) < 0)) {                                        // :155
+        // the shadow ray leaves the light with the hit POSITION as its direction (sic, LightSource.cpp:18-20)
+        const float tfar = l2norm3(v3(lp.x - hitp.x, lp.y - hitp.y, lp.z - hitp.z));
+        my_shadow++;
+        TravCount tc; tc.nodes = 0; tc.tris = 0;
+        const HitRec sh = trace_dev<COUNT>(sc, lp, hitp, 0.01f, tfar, tc);
+        if (COUNT) { acc.nodes += tc.nodes; acc.tris += tc.tris; acc.mx = max(acc.mx, tc.nodes); }
+        if (sh.tri == PGRT_INVALID_ID) lit = true;
+        else {                                                              // :166-172: a dielectric occluder does not shadow
+            const uint32_t g = __float_as_uint(__ldg(sc.shade + 4 * (size_t)sh.tri + 3).w);
+            lit = sc.materials[sc.geom_material[g]].type == 4;
+        }
+    }
+    return lit;
+}
+
 template <bool COUNT>
 __device__ __forceinline__ float4 phong_eval(const DevScene& sc, const pgrt_render_params& p, float4 o, float4 d, const HitFrame& f,
                                              unsigned long long& my_shadow, TravAcc& acc) {
@@ -385,36 +440,7 @@ __device__ __forceinline__ float4 phong_eval(const DevScene& sc, const pgrt_rend
     for (int li = 0; li < sc.n_lights; ++li) {                              // :351
         const pgrt_light& light = sc.lights[li];
         const V3 lp = v3(light.position[0], light.position[1], light.position[2]);
-        bool lit = false;
-        if (p.shadow_mode == 1) {
-            // README "To do: hard shadows" (README.md:20), behind a non-default flag: the ray the reference meant to
-            // cast -- from the hit point towards the light, in units of that segment -- with the same rule that the
-            // closest occluder decides and a dielectric one does not shadow.  Not part of the parity contract.
-            const V3 to_light = v3(lp.x - f.hitp.x, lp.y - f.hitp.y, lp.z - f.hitp.z);
-            if (!(dot3(f.n, to_light) < 0)) {
-                my_shadow++;
-                TravCount tc; tc.nodes = 0; tc.tris = 0;
-                const HitRec sh = trace_closest_t<COUNT>(sc, f.hitp, to_light, 1e-3f, 1.0f, tc);
-                if (COUNT) { acc.nodes += tc.nodes; acc.tris += tc.tris; acc.mx = max(acc.mx, tc.nodes); }
-                if (sh.tri == PGRT_INVALID_ID) lit = true;
-                else {
-                    const uint32_t g = __float_as_uint(__ldg(sc.shade + 4 * (size_t)sh.tri + 3).w);
-                    lit = sc.materials[sc.geom_material[g]].type == 4;
-                }
-            }
-        } else if (!(dot3(f.n, lp) < 0)) {                                  // :155
-            // the shadow ray leaves the light with the hit POSITION as its direction (sic, LightSource.cpp:18-20)
-            const float tfar = l2norm3(v3(lp.x - f.hitp.x, lp.y - f.hitp.y, lp.z - f.hitp.z));
-            my_shadow++;
-            TravCount tc; tc.nodes = 0; tc.tris = 0;
-            const HitRec sh = trace_closest_t<COUNT>(sc, lp, f.hitp, 0.01f, tfar, tc);
-            if (COUNT) { acc.nodes += tc.nodes; acc.tris += tc.tris; acc.mx = max(acc.mx, tc.nodes); }
-            if (sh.tri == PGRT_INVALID_ID) lit = true;
-            else {                                                          // :166-172: a dielectric occluder does not shadow
-                const uint32_t g = __float_as_uint(__ldg(sc.shade + 4 * (size_t)sh.tri + 3).w);
-                lit = sc.materials[sc.geom_material[g]].type == 4;
-            }
-        }
+        const bool lit = is_illuminated_dev<COUNT>(sc, p, lp, f.hitp, f.n, my_shadow, acc);
         if (lit) {
             const V3 light_vector = normalize3(v3(lp.x - f.hitp.x, lp.y - f.hitp.y, lp.z - f.hitp.z));
             const V3 camera_vector = normalize3(v3(o.x - d.x, o.y - d.y, o.z - d.z));   // :360 (sic)
@@ -554,13 +580,6 @@ __device__ __forceinline__ void store_pixel(const FrameOut& fo, size_t idx, floa
     if (fo.rgba8) fo.rgba8[idx] = pack_rgba8(c);
 }
 
-// closest hit as its own function: one copy of the traversal loop per node layout whatever the number of call sites,
-// and the register allocation of that loop is not mixed with the shading code around it
-template <bool COUNT>
-__device__ __noinline__ HitRec trace_dev(const DevScene& sc, V3 O, V3 D, float tnear, float tfar, TravCount& tc) {
-    return trace_closest_t<COUNT>(sc, O, D, tnear, tfar, tc);
-}
-
 // ---- fused scheduler: the whole of trace() for every sample of a batch in one persistent kernel (see the file header)
 #ifndef PGRT_FRAME_MIN_BLOCKS
 #define PGRT_FRAME_MIN_BLOCKS 5     // register cap of k_frame = 65536 / (128 * this)
@@ -574,35 +593,75 @@ __device__ __forceinline__ uint4 ld_volatile_u4(const uint4* p) {
     return v;
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
+// keep_ctas: CTAs 0 .. keep_ctas-1 stay until the batch is done (they poll for work while rays are outstanding); the others
+// leave as soon as they find neither a primary chunk nor a pool record, which frees their SM slots for the next frame's kernel
+// while this frame's dependent chains (up to max_depth traversals in a row) are still running.
 template <bool COUNT, bool PATH>
 __global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(DevScene sc, pgrt_render_params p, Gen0 g0, LevelBufs L0, RayPool P, FrameOut fo,
-                                                                       int min_claim, Counters* cnt) {
+                                                                       int min_claim, int patience, int keep_ctas, Counters* cnt) {
     const int lane = threadIdx.x & 31;
     const uint32_t n0 = g0.n_slots * (uint32_t)g0.spp;             // primary samples of this batch
     const uint32_t epoch = cnt->epoch;
+    const bool keeper = (int)blockIdx.x < keep_ctas;
     unsigned long long my_shadow = 0, my_refl = 0, my_refr = 0, my_shadow0 = 0;
     unsigned long long my_nodes0 = 0, my_tris0 = 0; uint32_t my_max0 = 0;   // COUNT: level-0 traversal statistics
     bool more_primary = true;
+    // Pool records are handed out by TICKET: atomicAdd(q_head, 32) never fails, so no warp ever retries against the others (a
+    // compare-and-swap here makes hundreds of idle warps fight for one word and lets ONE of them win 32 rays per round).  A
+    // ticket may run ahead of q_tail: its holder then waits for exactly its own records to be published -- each lane polls its
+    // own record's publication word, 32 distinct addresses -- so idle warps queue up for the rays that are still to be
+    // produced, in allocation order, and the children of a finished ray are picked up within a poll interval.
+    uint32_t tk_base = 0, tk_mask = 0;          // the held ticket: records tk_base + lane, for the lanes of tk_mask that are still to be processed
+    uint32_t wait_polls = 0;                    // polls since the held ticket last made progress
+    if (lane == 0) atomicMin(&cnt->t_first, global_timer_ns());
     for (;;) {
-        // ---- claim: pool records first once a warp's worth is waiting (their chains are the critical path of the
-        //      frame), else a chunk of primary rays; once those are gone, whatever the pool holds
-        uint32_t base = 0, n = 0; int mode = 0;     // 1 = pool records, 2 = primary rays, 3 = lost a race: look again
-        if (lane == 0) {
-            const uint32_t tail = min(ld_volatile_u32(&cnt->q_tail), P.cap), head = ld_volatile_u32(&cnt->q_head);
-            const uint32_t avail = tail > head ? tail - head : 0u;
-            if (avail >= (more_primary ? (uint32_t)min_claim : 1u)) {
-                n = min(avail, 32u);
-                if (atomicCAS(&cnt->q_head, head, head + n) == head) { base = head; mode = 1; }
-                else if (!more_primary) mode = 3;
-            }
-            if (mode == 0 && more_primary) {
-                base = atomicAdd(&cnt->trace_next[0], 32u);
-                if (base < n0) { mode = 2; n = min(32u, n0 - base); } else mode = 3;
-            }
+        uint32_t base = 0, n = 0, take = 0; int mode = 0;     // mode 1 = pool records (lanes of `take`), 2 = primary rays
+        uint4 l4 = make_uint4(0u, 0u, 0u, 0u);
+        // ---- a held ticket first: which of its records have been published?
+        if (tk_mask) {
+            const uint32_t rec = tk_base + (uint32_t)lane;
+            const bool mine = (tk_mask >> lane) & 1u;
+            bool ready = false;
+            if (mine && rec < P.cap) { l4 = ld_volatile_u4(&P.link[rec]); ready = l4.z == epoch; }
+            tk_mask &= ~__ballot_sync(0xffffffffu, mine && rec >= P.cap);          // beyond the pool: such a record never comes
+            const uint32_t ready_mask = __ballot_sync(0xffffffffu, ready);
+            // all of it, or -- once the rest has been waited for long enough -- what there is
+            if (ready_mask && (ready_mask == tk_mask || wait_polls >= (uint32_t)patience)) { mode = 1; take = ready_mask; }
         }
-        mode = __shfl_sync(0xffffffffu, mode, 0); base = __shfl_sync(0xffffffffu, base, 0); n = __shfl_sync(0xffffffffu, n, 0);
-        if (mode == 0) break;
-        if (mode == 3) { more_primary = false; continue; }
+        // ---- else new work: a full ticket's worth of waiting records, or a chunk of primary rays
+        if (mode == 0 && (more_primary || tk_mask == 0u)) {
+            int m = 0;      // 2 primary chunk, 5 took a ticket, 6 nothing left anywhere, 7 primaries just ran out
+            if (lane == 0) {
+                const uint4 q = ld_volatile_u4(reinterpret_cast<const uint4*>(&cnt->q_tail));     // q_tail, q_head, outstanding, epoch
+                const int avail = (int)(min(q.x, P.cap) - q.y);                                  // negative: tickets already run ahead of the records
+                if (tk_mask == 0u && ((more_primary && avail >= min_claim) || (!more_primary && q.z != 0u && (keeper || avail > 0)))) {
+                    base = atomicAdd(&cnt->q_head, 32u); m = 5;
+                } else if (more_primary) {
+                    base = atomicAdd(&cnt->trace_next[0], 32u);
+                    if (base < n0) { m = 2; n = min(32u, n0 - base); }
+                    else { m = 7; atomicMax(&cnt->t_primary_done, global_timer_ns()); }
+                } else if (q.z == 0u || tk_mask == 0u) m = 6;       // the batch is done, or this warp may leave (not a keeper, nothing waiting)
+            }
+            m = __shfl_sync(0xffffffffu, m, 0); base = __shfl_sync(0xffffffffu, base, 0); n = __shfl_sync(0xffffffffu, n, 0);
+            if (m == 5) { tk_base = base; tk_mask = 0xffffffffu; wait_polls = 0; continue; }
+            if (m == 7) { more_primary = false; continue; }
+            if (m == 6) break;
+            if (m == 2) mode = 2;
+        }
+        if (mode == 0) {
+            // holding a ticket whose records are not there yet, nothing else to do: wait (bounded), unless the batch is over
+            if ((wait_polls & 3u) == 0u) {                                 // (the waiters all read this one word: not at every poll)
+                uint32_t out = 1u;
+                if (lane == 0) out = ld_volatile_u32(&cnt->outstanding);
+                out = __shfl_sync(0xffffffffu, out, 0);
+                if (out == 0u) break;                                      // nothing is in flight any more: the rest of the ticket never comes
+            }
+            if (++wait_polls > (1u << 23)) { if (lane == 0) cnt->watchdog = 1u; break; }   // seconds of waiting: never expected; reported, not hung
+            __nanosleep(200u + 25u * min(wait_polls, 32u));
+            continue;
+        }
         const bool l0 = mode == 2;
 
         // ---- this lane's ray
@@ -610,19 +669,23 @@ __global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(DevScene s
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(0.f, 0.f, 0.f, -1.0f);
         uint2 lk = make_uint2(0u, 0u);
         int px = 0, py = 0; bool px_valid = false;
-        if ((uint32_t)lane < n) {
-            i = base + (uint32_t)lane;
-            if (l0) {
+        if (l0) {
+            if ((uint32_t)lane < n) {
+                i = base + (uint32_t)lane;
                 const uint32_t slot = g0.slot0 + i / (uint32_t)g0.spp;
                 px_valid = slot_to_pixel(g0.sh, g0.cam.width, g0.cam.height, slot, px, py);
                 if (px_valid) {
                     const RayRec r = primary_ray(g0.cam, p, px, py, (int)(i % (uint32_t)g0.spp));
                     o = make_float4(r.o.x, r.o.y, r.o.z, r.tnear); d = make_float4(r.d.x, r.d.y, r.d.z, r.time);
                 }
-            } else {
-                uint4 l4;
-                do { l4 = ld_volatile_u4(&P.link[i]); } while (l4.z != epoch);   // allocated before it was written: wait for the publication
-                __threadfence();
+            }
+            if (tk_mask) wait_polls++;                                     // time passes for a ticket that waits meanwhile
+        } else {
+            n = (uint32_t)__popc(take);
+            tk_mask &= ~take; wait_polls = 0;
+            if ((take >> lane) & 1u) {
+                i = tk_base + (uint32_t)lane;
+                __threadfence();                                           // the publication word was seen: now the record itself
                 o = __ldcg(&P.ray_o[i]); d = __ldcg(&P.ray_d[i]);
                 lk = make_uint2(l4.x, l4.y); level = (int)(l4.y & 0xFFu);
             }
@@ -670,6 +733,8 @@ __global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(DevScene s
         bool has_refr = is_diel && s.has_refr;
         const uint32_t rl = warp_append(&cnt->q_tail, is_diel, lane);
         const uint32_t rr = warp_append(&cnt->q_tail, has_refr, lane);
+        // records inside the pool will be claimed by somebody, alive or dead: they are outstanding from here on
+        const int published = (is_diel && rl < P.cap ? 1 : 0) + (has_refr && rr < P.cap ? 1 : 0);
         if (is_diel) {
             if (rl < P.cap && (!has_refr || rr < P.cap)) {
                 const uint32_t meta = (uint32_t)(level + 1) | (l0 ? (1u << 9) : 0u);
@@ -733,8 +798,16 @@ __global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(DevScene s
                 node = par; nlk = make_uint2(l4.x, l4.y);
             }
         }
+        // ---- retire what this iteration processed (one primary chunk, or n pool records) and account for the children
+        {
+            int delta = published;
+            for (int o2 = 16; o2 > 0; o2 >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o2);
+            delta -= l0 ? 1 : (int)n;
+            if (lane == 0 && delta != 0) atomicAdd(&cnt->outstanding, (uint32_t)delta);
+        }
         __syncwarp();
     }
+    if (lane == 0) atomicMax(&cnt->t_last, global_timer_ns());
     for (int o = 16; o > 0; o >>= 1) {
         my_shadow += __shfl_xor_sync(0xffffffffu, my_shadow, o); my_refl += __shfl_xor_sync(0xffffffffu, my_refl, o); my_refr += __shfl_xor_sync(0xffffffffu, my_refr, o);
         my_shadow0 += __shfl_xor_sync(0xffffffffu, my_shadow0, o);
@@ -798,6 +871,8 @@ __global__ void k_batch_begin(Counters* c, uint32_t n0, int first) {
     }
     if (t == 0) {
         c->shadow = 0; c->reflection = 0; c->refraction = 0; c->q_head = 0; c->q_tail = 0;
+        c->outstanding = (n0 + 31u) / 32u;      // primary chunks; pool records join as they are published (k_frame)
+        if (first) { c->t_first = ~0ull; c->t_primary_done = 0ull; c->t_last = 0ull; }
         c->epoch += 1u;      // the pool's publication word: records of earlier batches (and frames) read as "not yet written"
         if (first) { c->overflow = 0; c->watchdog = 0; c->tot_shadow = 0; c->tot_reflection = 0; c->tot_refraction = 0; c->tot_primary = 0; c->q_peak = 0; }
     }
@@ -816,6 +891,78 @@ __global__ void k_batch_end(Counters* c, unsigned long long primary, int fused, 
             if (done_flag) { __threadfence_system(); *(volatile uint32_t*)done_flag = c->sig_value; }
         }
     }
+}
+
+// ---- Raytracer::trace(RTCRay, level) on caller-supplied rays (raytracer.h:31): one thread walks one ray's whole tree
+//      depth-first with an explicit stack, in the reference's own order (reflection, then refraction, then the combine).
+//      A third evaluation order of the same node functions, besides the two frame schedulers; not a frame path.
+struct TraceFrame { float4 att; float4 other; RayRec refr; int stage; };   // other: value of the reflection child, or the node's own value (SK_PATH)
+template <bool PATH>
+__global__ void __launch_bounds__(128) k_trace_rays(DevScene sc, pgrt_render_params p, const pgrt_ray* __restrict__ rays, uint64_t n, int level0, float4* __restrict__ out,
+                                                    TraceFrame* __restrict__ stacks, Counters* cnt) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TraceFrame* stk = stacks + i * (uint64_t)(PGRT_MAX_LEVELS + 1);
+    unsigned long long my_shadow = 0, my_refl = 0, my_refr = 0;
+    TravAcc acc; acc.nodes = 0; acc.tris = 0; acc.mx = 0;
+    const pgrt_ray q = rays[i];
+    float4 o = make_float4(q.org_x, q.org_y, q.org_z, q.tnear), d = make_float4(q.dir_x, q.dir_y, q.dir_z, q.time);
+    float tfar = q.tfar;
+    int sp = 0, level = level0;
+    float4 v = make_float4(0.f, 0.f, 0.f, 1.f);
+    for (;;) {
+        // ---- descend: evaluate the node of the current ray
+        bool have_value;
+        {
+            TravCount tc;
+            const HitRec hr = trace_dev<false>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, tfar, tc);
+            ShadeOut s;
+            shade_classify<PATH>(sc, p, level, o, d, make_float4(hr.t, hr.u, hr.v, __uint_as_float(hr.tri)), s);
+            float4 own = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s.kind == SK_PHONG || (PATH && s.kind == SK_PATH)) own = phong_eval<false>(sc, p, o, d, s.f, my_shadow, acc);
+            if (s.kind == SK_FINAL) { v = s.color; have_value = true; }
+            else if (s.kind == SK_PHONG) { v = own; have_value = true; }
+            else {
+                TraceFrame& f = stk[sp++];
+                f.att = s.att; f.refr = s.refr; f.other = own;
+                f.stage = (PATH && s.kind == SK_PATH) ? 2 : (s.has_refr ? 0 : 1);   // 0: refraction still to come, 1 / 2: one child only
+                o = make_float4(s.refl.o.x, s.refl.o.y, s.refl.o.z, s.refl.tnear); d = make_float4(s.refl.d.x, s.refl.d.y, s.refl.d.z, s.refl.time);
+                tfar = FLT_MAX; level++; my_refl++;
+                have_value = false;
+            }
+        }
+        // ---- climb: hand the value to the parents that are complete
+        bool done = false;
+        while (have_value) {
+            if (sp == 0) { done = true; break; }
+            TraceFrame& f = stk[sp - 1];
+            if (f.stage == 0) {                       // that was the reflection child: now the refraction ray (raytracer.cpp:308-311)
+                f.other = v; f.stage = 3;
+                o = make_float4(f.refr.o.x, f.refr.o.y, f.refr.o.z, f.refr.tnear); d = make_float4(f.refr.d.x, f.refr.d.y, f.refr.d.z, f.refr.time);
+                tfar = FLT_MAX; my_refr++;            // level stays: both children live one level below the node
+                have_value = false;
+            } else {
+                if (f.stage == 3) v = combine_node<PATH>(f.att, f.other, true, v, make_float4(0.f, 0.f, 0.f, 0.f));
+                else v = combine_node<PATH>(f.att, v, false, make_float4(0.f, 0.f, 0.f, 0.f), f.other);
+                --sp; --level;
+            }
+        }
+        if (done) break;
+    }
+    out[i] = v;
+    if (my_shadow) atomicAdd(&cnt->shadow, my_shadow);
+    if (my_refl) atomicAdd(&cnt->reflection, my_refl);
+    if (my_refr) atomicAdd(&cnt->refraction, my_refr);
+}
+
+// Raytracer::is_illuminated (raytracer.h:34) over a batch of (light position, hit position, normal)
+__global__ void __launch_bounds__(128) k_is_illuminated(DevScene sc, pgrt_render_params p, const float* __restrict__ light, const float* __restrict__ hit,
+                                                        const float* __restrict__ nrm, uint64_t n, int32_t* __restrict__ out) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long sh = 0; TravAcc acc; acc.nodes = 0; acc.tris = 0; acc.mx = 0;
+    out[i] = is_illuminated_dev<false>(sc, p, v3(light[3 * i], light[3 * i + 1], light[3 * i + 2]), v3(hit[3 * i], hit[3 * i + 1], hit[3 * i + 2]),
+                                       v3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]), sh, acc) ? 1 : 0;
 }
 
 // ---- batch rtcIntersect1 over RTCRayHit-compatible records (device copies)

@@ -2,8 +2,11 @@
 
 The reference renders every pixel on one thread (pg1/simpleguidx11.cpp:102-118); pixels are independent, so the
 frame is cut into 32x8-pixel tiles dealt round-robin to ranks (load balance: sky tiles are cheap, canopy tiles are
-not) and the only exchange is the gather of the per-rank compact tile buffers into rank 0, followed by the un-tile
-kernel.  The same tile arithmetic is restated here in numpy so the host logic is testable on CPU (gloo).
+not).  Every rank's frame kernel stores its tiles at their final place of rank 0's frame (peer-mapped device memory
+over NVLink, or host memory shared by all ranks); completion travels as one 32-bit flag per rank and frame slot in a
+page of shared host memory (``FlagProtocol``), waited for with stream memory operations: no collective runs per frame.
+Fallback: compact per-rank tile buffers, NCCL ``gather``, un-tile kernel.  The tile arithmetic and the flag protocol
+are plain Python / numpy so the host logic is testable on CPU (gloo).
 """
 from __future__ import annotations
 
@@ -115,26 +118,22 @@ def share_frames(raytracer, n_frames: int, rank: int, device, group=None):
     return ptrs, views
 
 
-def share_host_frames(raytracer, n_frames: int, rank: int, device, group=None):
-    """``n_frames`` full frames in HOST memory shared by every rank: rank 0 creates a memfd, the others open it through
-    ``/proc/<pid>/fd``, every rank maps it and registers the mapping with its own device (``pgrt_host_frame_register``).
-    Each rank's resolve kernel then stores its tiles straight into the host frame through its own PCIe link, so a frame
-    that has to end in host memory needs no device-to-host copy on rank 0 (whose single link would carry all of it).
-    Returns (device-side pointers valid on this rank, rank-0 CPU torch views or None, keep-alive); (None, None, None)
-    when any rank cannot set it up."""
+def share_host_region(raytracer, nbytes: int, rank: int, device, group=None, name: str = "pgrt_host_region"):
+    """``nbytes`` (a multiple of 4096) of HOST memory shared by every rank of the box: rank 0 creates a memfd, the others open it
+    through ``/proc/<pid>/fd``, every rank maps it and registers the mapping with its own device
+    (``pgrt_host_frame_register``).  Returns (device-side base address valid on this rank, the mmap, keep-alive tuple);
+    (None, None, None) on EVERY rank when any rank cannot set it up (nothing stays mapped or registered then)."""
     import ctypes
     import mmap
     import os
     import torch
     import torch.distributed as dist
 
-    stride = (raytracer.width * raytracer.height * 16 + 4095) // 4096 * 4096
-    total = stride * n_frames
     ok, fd, mm, base, info = 1, -1, None, 0, [None]
     try:
         if rank == 0:
-            fd = os.memfd_create("pgrt_host_frames")
-            os.ftruncate(fd, total)
+            fd = os.memfd_create(name)
+            os.ftruncate(fd, nbytes)
             info = [(os.getpid(), fd)]
     except Exception:
         ok = 0
@@ -146,15 +145,15 @@ def share_host_frames(raytracer, n_frames: int, rank: int, device, group=None):
         else:
             if rank != 0:
                 fd = os.open(f"/proc/{info[0][0]}/fd/{info[0][1]}", os.O_RDWR)
-            mm = mmap.mmap(fd, total)
+            mm = mmap.mmap(fd, nbytes)
             base = ctypes.addressof(ctypes.c_char.from_buffer(mm))
-            dev_base = raytracer.host_frame_register(base, total)
+            dev_base = raytracer.host_frame_register(base, nbytes)
     except Exception:
         ok = 0
     flag = torch.tensor([ok], dtype=torch.int32, device=device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)     # also: everybody has opened the memfd before rank 0 may close it
     if int(flag.item()) != 1:
-        # some rank could not map or register the frames: undo what this one did and let the caller fall back
+        # some rank could not map or register the region: undo what this one did and let the caller fall back
         if dev_base:
             try:
                 raytracer.host_frame_unregister(base)
@@ -165,25 +164,106 @@ def share_host_frames(raytracer, n_frames: int, rank: int, device, group=None):
         if fd >= 0:
             os.close(fd)
         return None, None, None
+    return dev_base, mm, (mm, fd, base)
+
+
+def release_host_region(raytracer, keep) -> None:
+    import os
+    mm, fd, base = keep
+    raytracer.host_frame_unregister(base)
+    try:
+        mm.close()
+    except BufferError:      # a caller still holds a view: the mapping goes when that does
+        pass
+    os.close(fd)
+
+
+def share_host_frames(raytracer, n_frames: int, rank: int, device, group=None, bytes_per_pixel: int = 16):
+    """``n_frames`` full frames in HOST memory shared by every rank (``share_host_region``).  Each rank's frame kernel then
+    stores its tiles straight into the host frame through its own PCIe link, so a frame that has to end in host memory needs
+    no device-to-host copy on rank 0 (whose single link would carry all of it).  ``bytes_per_pixel`` 16 = float RGBA, 4 = RGBA8.
+    Returns (device-side pointers valid on this rank, rank-0 CPU torch views or None, keep-alive); (None, None, None)
+    when any rank cannot set it up."""
+    import torch
+
+    stride = (raytracer.width * raytracer.height * bytes_per_pixel + 4095) // 4096 * 4096
+    dev_base, mm, keep = share_host_region(raytracer, stride * n_frames, rank, device, group, "pgrt_host_frames")
+    if dev_base is None:
+        return None, None, None
     views = None
     if rank == 0:
-        flat = torch.frombuffer(mm, dtype=torch.float32).view(n_frames, stride // 4)
-        views = [flat[i, : raytracer.height * raytracer.width * 4].view(raytracer.height, raytracer.width, 4) for i in range(n_frames)]
-    return [dev_base + i * stride for i in range(n_frames)], views, (mm, fd, base)
+        if bytes_per_pixel == 16:
+            flat = torch.frombuffer(mm, dtype=torch.float32).view(n_frames, stride // 4)
+            views = [flat[i, : raytracer.height * raytracer.width * 4].view(raytracer.height, raytracer.width, 4) for i in range(n_frames)]
+        else:
+            flat = torch.frombuffer(mm, dtype=torch.uint8).view(n_frames, stride)
+            views = [flat[i, : raytracer.height * raytracer.width * 4].view(raytracer.height, raytracer.width, 4) for i in range(n_frames)]
+    return [dev_base + i * stride for i in range(n_frames)], views, keep
+
+
+class FlagProtocol:
+    """Completion flags of a tile-sharded frame pipeline, ``depth`` frame slots, ``world`` ranks, in one page of shared memory:
+    ``done[slot][rank]`` (stored by the last kernel of that rank's frame once its tiles of the slot's frame are in place) and
+    ``consumed[slot]`` (stored by rank 0 behind whatever consumed the slot's frame).  The n-th frame rendered into a slot
+    carries tag n in both (words start at 0; every wait is "word >= tag").  Every rank calls ``next_frame`` for the same
+    slots in the same order, so all ranks agree on the tags without talking to each other.  No CUDA here:
+    ``ShardedRenderer`` turns the answers into stream memory operations (``pgrt_slot_signal`` /
+    ``pgrt_stream_wait_value32`` / ``pgrt_stream_write_value32``), tests/test_dist_gloo.py into host stores and polls."""
+
+    def __init__(self, depth: int, world: int):
+        self.depth, self.world = depth, world
+        self.nbytes = (4 * (depth * world + depth) + 4095) // 4096 * 4096
+        self.count = [0] * depth       # frames begun per slot = tag of the slot's latest frame
+        self.last_slot = None
+
+    def done_offset(self, slot: int, rank: int) -> int:
+        return 4 * (slot * self.world + rank)
+
+    def consumed_offset(self, slot: int) -> int:
+        return 4 * (self.depth * self.world + slot)
+
+    def next_frame(self, slot: int, rank: int) -> dict:
+        """The memory operations around the next frame rendered into ``slot``, each an (offset, value) pair:
+        ``mark_consumed``: rank 0 stores it on the consumer stream FIRST -- everything enqueued there since the previous
+        ``next_frame`` has had the previous frame (None for the very first frame);
+        ``before``: every rank's slot stream waits for these before the frame may overwrite the slot;
+        ``signal``: what this rank's frame stores when its tiles are in place;
+        ``done``: what rank 0's consumer stream waits for (all ranks' tiles of this frame are in place)."""
+        ops = {"mark_consumed": None, "before": []}
+        if self.last_slot is not None:
+            ops["mark_consumed"] = (self.consumed_offset(self.last_slot), self.count[self.last_slot])
+        if self.count[slot] > 0:
+            ops["before"].append((self.consumed_offset(slot), self.count[slot]))
+        self.count[slot] = (self.count[slot] + 1) & 0xFFFFFFFF
+        tag = self.count[slot]
+        ops["signal"] = (self.done_offset(slot, rank), tag)
+        ops["done"] = [(self.done_offset(slot, r), tag) for r in range(self.world)]
+        self.last_slot = slot
+        return ops
 
 
 class ShardedRenderer:
     """One rank of a tile-sharded render, ``depth`` frames in flight.
 
-    mode "p2p" (default on GPUs when the frames can be peer-mapped): every rank's resolve kernel stores its tiles
-    straight into rank 0's frame over NVLink (``pgrt_render_shard_to_frame_begin``); the only collective is a 4-byte
-    NCCL all-reduce per frame that serves as the completion barrier.  mode "host": the same, but the frames live in host
-    memory shared by all ranks (``share_host_frames``): every rank writes its tiles through its own PCIe link and
-    ``frames`` are CPU tensors on rank 0.  mode "nccl": compact per-rank tile buffers,
-    ``gather`` to rank 0, un-tile kernel.  ``begin(k)`` enqueues frame k; ``end(k)`` collects this rank's stats;
-    on rank 0, ``frames[k % depth]`` holds frame k once the communication stream has passed ``ready[k % depth]``."""
+    mode "p2p" (default on GPUs when the frames can be peer-mapped): every rank's frame kernel stores its tiles straight
+    into rank 0's frame over NVLink (``pgrt_render_shard_to_frame_begin``).  mode "host": the same, but the frames live in
+    host memory shared by all ranks (``share_host_frames``): every rank writes its tiles through its own PCIe link and
+    ``frames`` are CPU tensors on rank 0 (``rgba8=True``: R8G8B8A8_UNORM frames, a quarter of the bytes).
+    Completion in both: ``FlagProtocol`` -- the last kernel of a rank's frame stores the frame's tag in that rank's word of a
+    shared host page (only if no secondary-ray queue overflowed: a retried frame signals when the retry is done), rank 0's
+    consumer stream waits for all ``world`` words, and stores the slot's "consumed" word behind whatever consumed the frame,
+    which every rank's slot stream waits for before it overwrites the slot.  No collective runs per frame; when the driver
+    lacks stream memory operations a 4-byte NCCL all-reduce per frame takes the flags' place.
+    mode "nccl": compact per-rank tile buffers, ``gather`` to rank 0, un-tile kernel.
 
-    def __init__(self, raytracer, rank: int, world: int, device, depth: int = 1, mode: str = "auto"):
+    ``begin(k)`` enqueues a frame into slot k % depth (every rank makes the same calls in the same order); ``end(k)`` collects
+    this rank's stats (after a queue overflow it re-renders the frame, and only then is the frame signalled complete).  On
+    rank 0, ``frames[k % depth]`` holds the frame for work enqueued on the current stream after ``begin(k)`` returned and before
+    the next ``begin`` is called: that next call is what marks the frame as consumed (with ``depth`` = 1 it is also what lets
+    every rank start the next frame).
+    Mode "local" (one rank) orders nothing for the caller beyond ``stream_wait_slot``: sync before reusing a frame."""
+
+    def __init__(self, raytracer, rank: int, world: int, device, depth: int = 1, mode: str = "auto", rgba8: bool = False, flags: bool = True):
         import torch
 
         self.rt, self.rank, self.world, self.device, self.depth = raytracer, rank, world, device, depth
@@ -192,7 +272,11 @@ class ShardedRenderer:
         self.slot_streams = [torch.cuda.ExternalStream(raytracer.slot_stream(i), device=device) for i in range(depth)]
         self.frames = None
         self.mode = "local" if world == 1 else mode
+        self.rgba8 = bool(rgba8)
+        if self.rgba8 and self.mode not in ("host", "local"):
+            raise ValueError("ShardedRenderer: rgba8 frames are implemented for mode 'host' (and one rank)")
         self.frame_ptrs = None
+        self._host_keep = None; self._ctl_keep = None; self._owned_frames = []
         if self.mode in ("auto", "p2p"):
             self.frame_ptrs, views = share_frames(raytracer, depth, rank, device)
             if self.frame_ptrs is None and self.mode == "p2p":
@@ -200,16 +284,38 @@ class ShardedRenderer:
             self.mode = "p2p" if self.frame_ptrs is not None else "nccl"
             if self.mode == "p2p":
                 self.frames = views
+                self._owned_frames = list(self.frame_ptrs)
         if self.mode == "host":
-            self.frame_ptrs, views, self._host_keep = share_host_frames(raytracer, depth, rank, device)
+            self.frame_ptrs, views, self._host_keep = share_host_frames(raytracer, depth, rank, device, bytes_per_pixel=4 if self.rgba8 else 16)
             if self.frame_ptrs is None:
                 raise RuntimeError("ShardedRenderer: cannot set up frames in shared host memory")
             self.frames = views
         if self.mode not in ("p2p", "host") and rank == 0:
-            self.frames = [torch.zeros((raytracer.height, raytracer.width, 4), dtype=torch.float32, device=device) for _ in range(depth)]
+            self.frames = [torch.zeros((raytracer.height, raytracer.width, 4), dtype=torch.uint8 if self.rgba8 else torch.float32, device=device) for _ in range(depth)]
         if self.mode == "nccl":
             self.shards = [torch.zeros((self.n_slots, 4), dtype=torch.float32, device=device) for _ in range(depth)]
             self.gathered = [torch.empty((world, self.n_slots, 4), dtype=torch.float32, device=device) if rank == 0 else None for _ in range(depth)]
+        # completion flags in a page of shared host memory (all ranks or none)
+        self.proto, self.ctl_dev, self.ctl = None, 0, None
+        if self.mode in ("p2p", "host") and flags:
+            proto = FlagProtocol(depth, world)
+            dev_base, mm, keep = share_host_region(raytracer, proto.nbytes, rank, device, name="pgrt_flags")
+            ok = 0
+            if dev_base is not None:
+                try:      # the driver must offer stream memory operations on every rank
+                    raytracer.stream_wait_value32(torch.cuda.current_stream(device).cuda_stream, dev_base, 0)
+                    ok = 1
+                except Exception:
+                    ok = 0
+                import torch.distributed as dist
+                t = torch.tensor([ok], dtype=torch.int32, device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                ok = int(t.item())
+                if ok:
+                    self.proto, self.ctl_dev, self._ctl_keep = proto, dev_base, keep
+                    self.ctl = np.frombuffer(mm, dtype=np.uint32)
+                else:
+                    release_host_region(raytracer, keep)
         self.token = torch.zeros(1, dtype=torch.float32, device=device)
         self._events = [torch.cuda.Event() for _ in range(4 * depth + 8)]   # recycled: an event is dead 2*depth+2 steps later
         self.host_s, self.host_n = [0.0, 0.0, 0.0, 0.0], 0                 # host time per part of begin() (bench reports it)
@@ -217,22 +323,38 @@ class ShardedRenderer:
         self.history = {}                    # step -> ready event (kept for the last `depth` steps)
         torch.cuda.synchronize(device)
 
+    @property
+    def completion(self) -> str:
+        if self.mode in ("local", "nccl"):
+            return self.mode
+        return "flags" if self.proto is not None else "nccl-allreduce"
+
     def close(self):
-        """Release the shared host frames of mode "host" (device frames go with the context)."""
-        keep = getattr(self, "_host_keep", None)
-        if keep is not None:
-            import os
-            import torch
-            torch.cuda.synchronize(self.device)
-            mm, fd, base = keep
-            self.rt.host_frame_unregister(base)
-            self.frames = None
-            self._host_keep = None
+        """Release what this renderer shared between the ranks: host frames, the flag page, peer-mapped device frames."""
+        import torch
+        torch.cuda.synchronize(self.device)
+        for s in range(self.depth):
             try:
-                mm.close()
-            except BufferError:      # a caller still holds a view of a frame: the mapping goes when that does
+                self.rt.slot_signal(s, 0, 0)
+            except Exception:
                 pass
-            os.close(fd)
+        self.ctl = None
+        if self._ctl_keep is not None:
+            release_host_region(self.rt, self._ctl_keep); self._ctl_keep = None; self.proto = None
+        if self._host_keep is not None:
+            self.frames = None
+            release_host_region(self.rt, self._host_keep); self._host_keep = None
+        if self._owned_frames:
+            import torch.distributed as dist
+            self.frames = None
+            if self.rank != 0:
+                for p in self._owned_frames:
+                    self.rt.frame_unmap(p)
+            dist.barrier()                  # nobody holds a mapping any more
+            if self.rank == 0:
+                for p in self._owned_frames:
+                    self.rt.frame_free(p)
+            self._owned_frames = []
 
     @property
     def frame(self):
@@ -247,23 +369,41 @@ class ShardedRenderer:
         t = [time.perf_counter()]
         s = k % self.depth
         comm = torch.cuda.current_stream(self.device)
-        # the slot's destination is free once what consumed its last frame has run: that work sits on rank 0's
-        # communication stream before the barrier of the NEXT step, so waiting for that barrier (here, on every rank) suffices
-        prev = self.history.get(k - self.depth + 1 if self.depth > 1 else k - 1)
-        if prev is not None and k >= self.depth and self.mode != "local":
-            self.slot_streams[s].wait_event(prev)
+        ops = None
+        if self.proto is not None:
+            ops = self.proto.next_frame(s, self.rank)
+            if self.rank == 0 and ops["mark_consumed"] is not None:   # everything enqueued on the consumer stream since the last begin() has had that frame
+                off, val = ops["mark_consumed"]
+                self.rt.stream_write_value32(comm.cuda_stream, self.ctl_dev + off, val)
+            for off, val in ops["before"]:
+                self.rt.stream_wait_value32(self.slot_streams[s].cuda_stream, self.ctl_dev + off, val)
+        elif self.mode != "local":
+            # the slot's destination is free once what consumed its last frame has run: that work sits on rank 0's
+            # communication stream before the barrier of the NEXT step, so waiting for that barrier (here, on every rank) suffices
+            prev = self.history.get(k - self.depth + 1 if self.depth > 1 else k - 1)
+            if prev is not None and k >= self.depth:
+                self.slot_streams[s].wait_event(prev)
         if before is not None:
             before(self.slot_streams[s])
         t.append(time.perf_counter())
         if self.mode == "local":
+            if self.rgba8:
+                raise ValueError("ShardedRenderer: one rank renders rgba8 frames through Raytracer.render_begin(host_ptr=..., rgba8=True)")
             self.rt.render_begin(s, params, device_ptr=self.frames[s].data_ptr(), profile=profile)
             t.append(time.perf_counter())
             self.rt.stream_wait_slot(s, comm.cuda_stream)
         elif self.mode in ("p2p", "host"):
-            self.rt.render_begin(s, params, frame_ptr=self.frame_ptrs[s], profile=profile)
+            if ops is not None:
+                self.rt.slot_signal(s, self.ctl_dev + ops["signal"][0], ops["signal"][1])
+            self.rt.render_begin(s, params, frame_ptr=self.frame_ptrs[s], profile=profile, rgba8=self.rgba8)
             t.append(time.perf_counter())
-            self.rt.stream_wait_slot(s, comm.cuda_stream)
-            dist.all_reduce(self.token)          # completion barrier: 4 bytes; the pixels travelled inside the resolve kernel
+            if ops is not None:
+                if self.rank == 0:
+                    for off, val in ops["done"]:
+                        self.rt.stream_wait_value32(comm.cuda_stream, self.ctl_dev + off, val)
+            else:
+                self.rt.stream_wait_slot(s, comm.cuda_stream)
+                dist.all_reduce(self.token)          # completion barrier: 4 bytes; the pixels travelled inside the frame kernel
         else:
             self.rt.render_begin(s, params, shard_ptr=self.shards[s].data_ptr(), profile=profile)
             t.append(time.perf_counter())
@@ -280,7 +420,7 @@ class ShardedRenderer:
         self.history[k] = ev
         self.history.pop(k - 2 * self.depth - 2, None)
         t.append(time.perf_counter())
-        for i in range(4):                       # host seconds spent in: wait+before, render_begin, barrier/gather, event
+        for i in range(4):                       # host seconds spent in: wait+before, render_begin, completion, event
             self.host_s[i] += t[i + 1] - t[i]
         self.host_n += 1
 

@@ -38,11 +38,12 @@ struct Huff {
     int mincode[17], maxcode[18], valptr[17];
     uint16_t look[512];      // 9-bit lookahead: (length << 8) | symbol, 0 = longer code
     bool present = false;
-    void build() {
+    bool build() {      // false: the code lengths do not describe a prefix code (more codes of a length than that length has room for)
         int code = 0, k = 0;
         for (int l = 1; l <= 16; ++l) {
             valptr[l] = k; mincode[l] = code;
             code += bits[l]; k += bits[l];
+            if (code > (1 << l)) { present = false; return false; }
             maxcode[l] = bits[l] ? code - 1 : -1;
             code <<= 1;
         }
@@ -57,6 +58,7 @@ struct Huff {
             code <<= 1;
         }
         present = true;
+        return true;
     }
 };
 
@@ -337,42 +339,58 @@ bool DecodeJpeg(const uint8_t* d, size_t size, RawImage& out, std::string* error
         const size_t len = ((size_t)d[i + 2] << 8) | d[i + 3];
         if (len < 2 || i + 2 + len > size) return fail(error, "truncated JPEG segment");
         const uint8_t* s = d + i + 4; const uint8_t* se = d + i + 2 + len;
+        // every field below comes from the file: nothing is read past the end of its segment (se), no table or component
+        // index is used before it has been range-checked
         if (m == 0xDB) {
             while (s < se) {
                 const int pq = *s >> 4, tq = *s & 15; ++s;
-                if (tq > 3) return fail(error, "bad quantisation table id");
+                if (tq > 3 || pq > 1) return fail(error, "bad quantisation table id");
+                if (s + (pq ? 128 : 64) > se) return fail(error, "truncated quantisation table");
                 for (int k = 0; k < 64; ++k) { qt[tq][ZIGZAG[k]] = pq ? (uint16_t)((s[0] << 8) | s[1]) : s[0]; s += pq ? 2 : 1; }
                 have_qt[tq] = true;
             }
         } else if (m == 0xC4) {
             while (s < se) {
                 const int tc = *s >> 4, th = *s & 15; ++s;
-                if (th > 3) return fail(error, "bad Huffman table id");
+                if (th > 3 || tc > 1) return fail(error, "bad Huffman table id");
+                if (s + 16 > se) return fail(error, "truncated Huffman table");
                 Huff& h = tc ? ac[th] : dc[th];
                 int total = 0;
                 for (int l = 1; l <= 16; ++l) { h.bits[l] = *s++; total += h.bits[l]; }
                 if (total > 256 || s + total > se) return fail(error, "bad Huffman table");
                 memcpy(h.vals, s, total); s += total;
-                h.build();
+                if (!h.build()) return fail(error, "bad Huffman table (over-subscribed code lengths)");
             }
         } else if (m == 0xC0 || m == 0xC1) {
+            if (se - s < 6) return fail(error, "truncated frame header");
             if (s[0] != 8) return fail(error, "only 8-bit JPEG is supported");
             height = (s[1] << 8) | s[2]; width = (s[3] << 8) | s[4]; ncomp = s[5];
             if ((ncomp != 1 && ncomp != 3) || width <= 0 || height <= 0) return fail(error, "unsupported JPEG component count");
-            for (int c = 0; c < ncomp; ++c) { comp[c].id = s[6 + 3 * c]; comp[c].h = s[7 + 3 * c] >> 4; comp[c].v = s[7 + 3 * c] & 15; comp[c].tq = s[8 + 3 * c]; }
+            if ((size_t)width * (size_t)height > ((size_t)1 << 28)) return fail(error, "JPEG frame too large");
+            if (se - s < 6 + 3 * ncomp) return fail(error, "truncated frame header");
+            for (int c = 0; c < ncomp; ++c) {
+                comp[c].id = s[6 + 3 * c]; comp[c].h = s[7 + 3 * c] >> 4; comp[c].v = s[7 + 3 * c] & 15; comp[c].tq = s[8 + 3 * c];
+                comp[c].td = comp[c].ta = -1;
+                if (comp[c].h < 1 || comp[c].h > 4 || comp[c].v < 1 || comp[c].v > 4 || comp[c].tq > 3) return fail(error, "bad JPEG component parameters");
+            }
             sof = true;
         } else if (m == 0xC2 || (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC)) {
             return fail(error, "only baseline (SOF0) JPEG is supported");
         } else if (m == 0xDD) {
+            if (se - s < 2) return fail(error, "truncated restart interval");
             restart = (s[0] << 8) | s[1];
         } else if (m == 0xDA) {
             if (!sof) return fail(error, "SOS before SOF");
+            if (se - s < 1) return fail(error, "truncated scan header");
             const int ns = s[0];
             if (ns != ncomp) return fail(error, "non-interleaved scans are not supported");
+            if (se - s < 1 + 2 * ns + 3) return fail(error, "truncated scan header");
             for (int k = 0; k < ns; ++k) {
                 const int id = s[1 + 2 * k];
                 for (int c = 0; c < ncomp; ++c) if (comp[c].id == id) { comp[c].td = s[2 + 2 * k] >> 4; comp[c].ta = s[2 + 2 * k] & 15; }
             }
+            for (int c = 0; c < ncomp; ++c)
+                if (comp[c].td < 0 || comp[c].td > 3 || comp[c].ta < 0 || comp[c].ta > 3) return fail(error, "bad Huffman table selector in the scan header");
             // ---- entropy-coded data
             int hmax = 1, vmax = 1;
             for (int c = 0; c < ncomp; ++c) { hmax = comp[c].h > hmax ? comp[c].h : hmax; vmax = comp[c].v > vmax ? comp[c].v : vmax; }
@@ -402,6 +420,7 @@ bool DecodeJpeg(const uint8_t* d, size_t size, RawImage& out, std::string* error
                             for (int bx = 0; bx < C.h; ++bx) {
                                 memset(coef, 0, sizeof coef);
                                 const int t = decode_symbol(br, dc[C.td]);
+                                if (t > 11) return fail(error, "bad DC difference category");      // 8-bit baseline: 0..11; a crafted table could name up to 255
                                 const int diff = t ? extend(br.get(t), t) : 0;
                                 C.pred += diff;
                                 coef[0] = C.pred * qt[C.tq][0];

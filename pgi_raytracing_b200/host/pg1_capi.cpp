@@ -107,6 +107,20 @@ int pg1_raytracer_get_pixel(void* h, int x, int y, float* rgba) {
     try { const Color4f c = ((Raytracer*)h)->get_pixel(x, y); rgba[0] = c.r; rgba[1] = c.g; rgba[2] = c.b; rgba[3] = c.a; return 0; }
     catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
+int pg1_raytracer_trace(void* h, const float* rays12, unsigned long long n, int level, float* rgba) {
+    try {
+        if (n == 1) { const Color4f c = ((Raytracer*)h)->trace(*reinterpret_cast<const RTCRay*>(rays12), level); rgba[0] = c.r; rgba[1] = c.g; rgba[2] = c.b; rgba[3] = c.a; }
+        else ((Raytracer*)h)->TraceRays(reinterpret_cast<const RTCRay*>(rays12), (size_t)n, level, rgba);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+int pg1_raytracer_is_illuminated(void* h, const float* light3, const float* hit3, const float* nrm3) {
+    try {
+        const Vector3 one(1, 1, 1);
+        return ((Raytracer*)h)->is_illuminated(LightSource(Vector3(light3[0], light3[1], light3[2]), one, one, one), Vector3(hit3[0], hit3[1], hit3[2]),
+                                               Vector3(nrm3[0], nrm3[1], nrm3[2])) ? 1 : 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
 int pg1_raytracer_counts(void* h, int* out2) { out2[0] = (int)((Raytracer*)h)->no_surfaces(); out2[1] = (int)((Raytracer*)h)->no_materials(); return 0; }
 
 }  // extern "C"

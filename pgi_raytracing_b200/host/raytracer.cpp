@@ -8,7 +8,8 @@ Raytracer::Raytracer(const int width, const int height, const float fov_y, const
     : camera_(width, height, fov_y, view_from, view_at) {
     if (InitDeviceAndScene(config) != 0) throw std::runtime_error("Raytracer: no CUDA device (the render loop has no CPU fallback)");
     const float from[3] = {view_from.x, view_from.y, view_from.z}, at[3] = {view_at.x, view_at.y, view_at.z};
-    check(pgrt_set_camera(ctx_, width, height, fov_y, from, at));
+    try { check(pgrt_set_camera(ctx_, width, height, fov_y, from, at)); }
+    catch (...) { ReleaseDeviceAndScene(); throw; }      // the destructor does not run for a constructor that throws
 }
 
 Raytracer::~Raytracer() {
@@ -151,3 +152,26 @@ RTCRay Raytracer::get_reflection_ray(Vector3 direction, Vector3 normal, Vector3 
 }
 
 void Raytracer::Intersect(pgrt_rayhit* rayhits, size_t n) { check(pgrt_intersect(ctx_, rayhits, n)); }
+
+// Raytracer::trace (pg1/raytracer.cpp:237-394): the recursion runs on the device (pgrt_trace), in the reference's own order
+void Raytracer::TraceRays(const RTCRay* rays, size_t n, int level, float* rgba) {
+    static_assert(sizeof(RTCRay) == sizeof(pgrt_ray), "RTCRay layout");
+    const pgrt_render_params p = params();
+    check(pgrt_trace(ctx_, &p, reinterpret_cast<const pgrt_ray*>(rays), n, level, rgba));
+}
+
+Color4f Raytracer::trace(RTCRay ray, int level) {
+    float px[4];
+    TraceRays(&ray, 1, level, px);
+    return Color4f{px[0], px[1], px[2], px[3]};
+}
+
+// Raytracer::is_illuminated (pg1/raytracer.cpp:150-176)
+bool Raytracer::is_illuminated(LightSource light, Vector3 hit_position, Vector3 normal) {
+    const pgrt_render_params p = params();
+    const float l[3] = {light.position_.x, light.position_.y, light.position_.z}, h[3] = {hit_position.x, hit_position.y, hit_position.z},
+                n[3] = {normal.x, normal.y, normal.z};
+    int32_t lit = 0;
+    check(pgrt_is_illuminated(ctx_, &p, l, h, n, 1, &lit));
+    return lit != 0;
+}

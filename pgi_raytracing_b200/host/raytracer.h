@@ -41,8 +41,10 @@ public:
     // same, from surfaces already in memory (what LoadScene does after LoadOBJ, pg1/raytracer.cpp:66-127)
     void LoadSurfaces(const std::vector<Surface*>& surfaces, const std::vector<Material*>& materials, const Texture* background);
 
+    Color4f trace(RTCRay ray, int level);                                                 // pg1/raytracer.h:31 (one ray; TraceRays for batches)
     Color4f get_pixel(const int x, const int y, const float t = 0.0f);
     Color4f gamma(Color4f input);
+    bool is_illuminated(LightSource light, Vector3 hit_position, Vector3 normal);        // pg1/raytracer.h:34
     RTCRay get_refraction_ray(Vector3 direction, Vector3 normal, float iorFrom, float iorTo, Vector3 hit_point);
     RTCRay get_reflection_ray(Vector3 direction, Vector3 normal, Vector3 hit_point, float ior);
 
@@ -52,6 +54,8 @@ public:
     void RenderAccumulated(int n_frames, float* rgba, pgrt_render_stats* stats = nullptr);
     // rtcIntersect1 on caller-owned RTCRayHit-compatible records
     void Intersect(pgrt_rayhit* rayhits, size_t n);
+    // trace() over a batch of caller-owned rays, all at recursion level `level`; rgba = n x 4 floats
+    void TraceRays(const RTCRay* rays, size_t n, int level, float* rgba);
 
     int width() const { return camera_.width(); }
     int height() const { return camera_.height(); }

@@ -43,7 +43,7 @@ void tri_box(const float* p, float lo[3], float hi[3]) {
 
 extern "C" {
 
-void* emul_build(const float* pos, uint32_t n, int builder /*0 = PLOC, 1 = median split*/, int layout /*PGRT_LAYOUT_Q8 / _F32*/) {
+void* emul_build(const float* pos, uint32_t n, int builder /*0 = PLOC, 1 = median split, 2 = binned SAH*/, int layout /*PGRT_LAYOUT_Q8 / _F32*/) {
     Tree* t = new Tree();
     t->layout = layout;
     const size_t node_f4 = layout == PGRT_LAYOUT_F32 ? PGRT_NODE_F4_F32 : PGRT_NODE_F4_Q8;
@@ -120,6 +120,57 @@ void* emul_build(const float* pos, uint32_t n, int builder /*0 = PLOC, 1 = media
             cid = out; m = (uint32_t)cid.size();
         }
         t->root = cid[0];
+    } else if (builder == 2) {
+        // Binned SAH, top-down: the family of builder behind rtcCommitScene's default MEDIUM quality (pg1/raytracer.cpp:127,
+        // emb/doc/README.md:2126-2127) and the "refined by binned SAH" of the north star.  16 bins over the centroid bounds of
+        // every axis, cost = area(L) * n(L) + area(R) * n(R), split down to single triangles (the collapse forms the leaves);
+        // a range the bins cannot separate is cut at its median.  Here only as the yardstick the PLOC tree is measured against.
+        const int NB = 16;
+        std::vector<uint32_t> order(n);
+        for (uint32_t i = 0; i < n; ++i) order[i] = i;
+        auto cen = [&](uint32_t k, int a) { const float4 lo = t->b0[k], hi = t->b1[k]; return a == 0 ? 0.5f * (lo.x + hi.x) : (a == 1 ? 0.5f * (lo.y + hi.y) : 0.5f * (lo.z + hi.z)); };
+        struct Box { float lo[3], hi[3]; void reset() { for (int a = 0; a < 3; ++a) { lo[a] = FLT_MAX; hi[a] = -FLT_MAX; } }
+                     void grow(const float4& l, const float4& h) { lo[0] = fminf(lo[0], l.x); lo[1] = fminf(lo[1], l.y); lo[2] = fminf(lo[2], l.z); hi[0] = fmaxf(hi[0], h.x); hi[1] = fmaxf(hi[1], h.y); hi[2] = fmaxf(hi[2], h.z); }
+                     void grow(const Box& b) { for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], b.lo[a]); hi[a] = fmaxf(hi[a], b.hi[a]); } }
+                     float area() const { const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2]; return dx < 0 ? 0.0f : dx * dy + dy * dz + dz * dx; } };
+        std::function<uint32_t(uint32_t, uint32_t)> rec = [&](uint32_t lo, uint32_t hi) -> uint32_t {
+            if (hi - lo == 1) return order[lo];
+            float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            for (uint32_t i = lo; i < hi; ++i) for (int a = 0; a < 3; ++a) { const float c = cen(order[i], a); clo[a] = fminf(clo[a], c); chi[a] = fmaxf(chi[a], c); }
+            float best = FLT_MAX; int best_axis = -1, best_bin = 0;
+            for (int a = 0; a < 3; ++a) {
+                const float ext = chi[a] - clo[a];
+                if (!(ext > 0.0f)) continue;
+                Box bb[NB]; uint32_t bn[NB];
+                for (int b = 0; b < NB; ++b) { bb[b].reset(); bn[b] = 0; }
+                const float scale = NB / ext;
+                for (uint32_t i = lo; i < hi; ++i) {
+                    int b = (int)((cen(order[i], a) - clo[a]) * scale); b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+                    bb[b].grow(t->b0[order[i]], t->b1[order[i]]); bn[b]++;
+                }
+                float ra[NB]; uint32_t rn[NB]; Box acc; acc.reset(); uint32_t cnt = 0;
+                for (int b = NB - 1; b > 0; --b) { acc.grow(bb[b]); cnt += bn[b]; ra[b] = acc.area(); rn[b] = cnt; }
+                acc.reset(); cnt = 0;
+                for (int b = 0; b < NB - 1; ++b) {
+                    acc.grow(bb[b]); cnt += bn[b];
+                    if (cnt == 0 || rn[b + 1] == 0) continue;
+                    const float cost = acc.area() * cnt + ra[b + 1] * rn[b + 1];
+                    if (cost < best) { best = cost; best_axis = a; best_bin = b; }
+                }
+            }
+            uint32_t mid = (lo + hi) / 2;
+            if (best_axis >= 0) {
+                const float scale = NB / (chi[best_axis] - clo[best_axis]);
+                auto it = std::partition(order.begin() + lo, order.begin() + hi, [&](uint32_t k) {
+                    int b = (int)((cen(k, best_axis) - clo[best_axis]) * scale); b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+                    return b <= best_bin; });
+                const uint32_t m2 = (uint32_t)(it - order.begin());
+                if (m2 > lo && m2 < hi) mid = m2;
+            }
+            const uint32_t a = rec(lo, mid), b = rec(mid, hi);
+            return merge(a, b);
+        };
+        t->root = rec(0, n);
     } else {
         // median split over the Morton order (any binary tree must give the same hits)
         struct Job { uint32_t lo, hi; };

@@ -132,3 +132,79 @@ def test_shared_host_frames_fall_back_together_when_one_rank_fails():
         assert p.exitcode == 0
     got = sorted(q.get(timeout=5) for _ in range(2))
     assert got == [(0, True, True, 0), (1, True, True, 0)], got
+
+
+def _flag_pipeline_worker(rank, world, port, depth, n_frames, q):
+    """The flag protocol of dist.ShardedRenderer with host stores and polls in place of stream memory operations: every
+    rank 'renders' its rows of a shared frame, rank 0 consumes the frame and releases the slot."""
+    import ctypes
+    import time
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w, h = 16, 8
+    rt = _HostOnlyRaytracer(w, h)
+    proto = D.FlagProtocol(depth, world)
+    ctl_base, ctl_mm, ctl_keep = D.share_host_region(rt, proto.nbytes, rank, torch.device("cpu"), name="flags_test")
+    ptrs, views, keep = D.share_host_frames(rt, depth, rank, torch.device("cpu"))
+    ctl = np.frombuffer(ctl_mm, dtype=np.uint32)
+    assert ctl_base is not None and (ctl == 0).all()
+    frames = [np.ctypeslib.as_array((ctypes.c_float * (w * h * 4)).from_address(p)).reshape(h, w, 4) for p in ptrs]
+    rng = np.random.default_rng(rank)
+
+    def wait(off, val):
+        t0 = time.time()
+        while ctl[off // 4] < val:
+            assert time.time() - t0 < 60, "flag wait timed out"
+            time.sleep(0)
+    ok, consumed_log = True, []
+    for k in range(n_frames):
+        s = k % depth
+        ops = proto.next_frame(s, rank)
+        if rank == 0 and ops["mark_consumed"] is not None:
+            off, val = ops["mark_consumed"]; ctl[off // 4] = val
+        for off, val in ops["before"]:
+            wait(off, val)                          # the slot's previous frame has been consumed by rank 0
+        if rng.random() < 0.5:
+            time.sleep(0.002 * rng.random())        # ranks drift against each other
+        frames[s][rank::world] = float(k + 1)       # "render": this rank's rows of frame k
+        off, val = ops["signal"]; ctl[off // 4] = val
+        if rank == 0:
+            for off, val in ops["done"]:
+                wait(off, val)
+            ok &= bool((frames[s] == float(k + 1)).all())     # every rank's rows hold frame k: nobody ran ahead into this slot
+            consumed_log.append(k)
+    if rank == 0:
+        q.put((ok, consumed_log == list(range(n_frames)), [int(x) for x in proto.count]))
+    dist.barrier()
+    D.release_host_region(rt, ctl_keep)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("depth", [1, 3])
+def test_flag_protocol_world2(depth):
+    """FlagProtocol at world size 2: tags agree without communication, no rank overwrites a slot before rank 0 has consumed
+    it (depth 1: strict alternation), rank 0 never sees a frame before both ranks' rows are in place."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    n_frames = 40
+    procs = [ctx.Process(target=_flag_pipeline_worker, args=(r, 2, port, depth, n_frames, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    ok, in_order, counts = q.get(timeout=5)
+    assert ok and in_order and sum(counts) == n_frames
+
+
+def test_flag_protocol_offsets_and_tags():
+    p = D.FlagProtocol(3, 4)
+    assert p.nbytes == 4096 and len({p.done_offset(s, r) for s in range(3) for r in range(4)} | {p.consumed_offset(s) for s in range(3)}) == 15
+    a = p.next_frame(0, 2)
+    assert a["mark_consumed"] is None and a["before"] == [] and a["signal"] == (p.done_offset(0, 2), 1) and len(a["done"]) == 4
+    b = p.next_frame(1, 2)
+    assert b["mark_consumed"] == (p.consumed_offset(0), 1) and b["before"] == []
+    p.next_frame(2, 2)
+    c = p.next_frame(0, 2)
+    assert c["mark_consumed"] == (p.consumed_offset(2), 1) and c["before"] == [(p.consumed_offset(0), 1)] and c["signal"][1] == 2

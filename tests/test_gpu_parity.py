@@ -696,3 +696,148 @@ def test_path_tracing_converges_and_covers_textures_and_glass(P, oracle_mod, ave
     many, _ = rt.render_accumulate(16, dict(kw, seed=1000))
     err = lambda a: float(np.mean((np.clip(np.nan_to_num(a[..., :3]), 0, 1) - np.clip(np.nan_to_num(many[..., :3]), 0, 1)) ** 2))
     assert err(acc8) < 0.5 * err(one), (err(acc8), err(one))
+
+
+# ------------------------------------------------------------------------------------------------ the class's query methods
+@pytest.mark.parametrize("which", ["cornell", "avenger"])
+def test_trace_on_caller_rays_matches_the_oracle(P, oracle_mod, cornell_pair, avenger, which):
+    """pgrt_trace = Raytracer::trace(RTCRay, level) (pg1/raytracer.h:31, raytracer.cpp:237-394) on caller-supplied rays at
+    levels 0..7: camera rays, rays from inside the scene, rays that start inside glass.  Tolerance: the colours agree to
+    5e-4 absolute = 1/8 of an 8-bit step and are bit-equal on >= 95 % of the rays: atan2 / asin / pow / exp of CUDA and glibc
+    differ in the last place, one ulp of the environment map's u is 2.4e-4 texels of a 4000-pixel map, and mix_srgb chains
+    double pows through the steep start of the sRGB curve.  The device recursion and the frame kernel give the same colour bit for bit."""
+    rt, o = cornell_pair if which == "cornell" else avenger[1:]
+    pd = dict(sampling_width=1, jitter=0, aperture=0.0)
+    p = oracle_mod.make_params(**pd)
+    rng = np.random.default_rng(31)
+    prim = o.primary_rays(p)
+    n = 20000
+    rays = np.zeros((n, 9), np.float32)
+    rays[:, 0:3] = rng.uniform(-60, 60, (n, 3)); rays[:, 2] = rng.uniform(2, 70, n)
+    rays[:, 4:7] = rng.normal(size=(n, 3)); rays[:, 3] = 0.01; rays[:, 8] = np.finfo(np.float32).max
+    rays[:, 7] = np.where(rng.random(n) < 0.7, np.float32(1.000293), 1.5)
+    allrays = np.concatenate([prim[rng.integers(0, prim.shape[0], n)], rays])
+    for level in (0, 1, 3, 6, 7):
+        a, b = rt.trace(allrays, level, pd), o.trace(p, allrays, level)
+        eq = ((a == b) | (np.isnan(a) & np.isnan(b))).all(axis=-1)
+        assert eq.mean() >= 0.95 and np.nanmax(np.abs(a - b)) <= 5e-4, (which, level, eq.mean(), np.nanmax(np.abs(a - b)))
+    # level 0 on the frame's own primary rays = the frame before the resolve (one sample per pixel, gamma 0.5 = identity up to rounding)
+    img, _ = rt.render(pd)
+    t = rt.trace(prim, 0, pd).reshape(rt.height, rt.width, 4)
+    lin = np.sqrt(t[..., [2, 1, 0]]) ** 2        # the resolve swaps into gamma and back (raytracer.cpp:431-446)
+    ok = np.isfinite(lin).all(axis=-1)
+    assert np.array_equal(lin[ok][:, [2, 1, 0]], img[..., :3][ok])
+
+
+def test_is_illuminated_matches_the_oracle(P, oracle_mod, cornell_pair, cornell):
+    """pgrt_is_illuminated = Raytracer::is_illuminated (pg1/raytracer.h:34, raytracer.cpp:150-176) as shipped, and the
+    README's hard shadows (shadow_mode 1) against the oracle's statement of the same spec: exact agreement."""
+    rt, o = cornell_pair
+    rng = np.random.default_rng(32)
+    n = 50000
+    hit = rng.uniform(-80, 80, (n, 3)).astype(np.float32); hit[:, 2] = rng.uniform(0, 60, n)
+    nrm = rng.normal(size=(n, 3)).astype(np.float32)
+    for light in (cornell.lights[0].position, (5.0, -60.0, 35.0)):
+        for mode in (0, 1):
+            a = rt.is_illuminated(light, hit, nrm, dict(shadow_mode=mode))
+            b = o.is_illuminated(oracle_mod.make_params(shadow_mode=mode), light, hit, nrm)
+            assert np.array_equal(a, b), (light, mode, (a != b).sum())
+            assert 0.05 < a.mean() < 0.95
+
+
+def test_hard_shadows_match_the_oracle(P, oracle_mod, cornell_pair, avenger):
+    """shadow_mode = 1 (README.md:20 to-do, non-default): whole frames against the oracle's statement of the same rule."""
+    for (rt, o), pd in ((cornell_pair, dict(seed=8, shadow_mode=1)), (avenger[1:], dict(sampling_width=1, jitter=0, aperture=0.0, shadow_mode=1))):
+        ref, g0, p0, st0 = o.render(oracle_mod.make_params(**pd))
+        img, st = rt.render(pd)
+        ok, psnr = image_bars(P, ref, img)
+        assert ok >= 0.995 and psnr >= 45.0, (ok, psnr)
+        for k in ("primary", "shadow", "reflection", "refraction"):
+            assert abs(st[k] - st0[k]) <= 1e-3 * max(st0[k], 1), (k, st[k], st0[k])
+        plain, _ = rt.render(dict(pd, shadow_mode=0))
+        assert (P.to_srgb8(img).astype(int).sum(-1) < P.to_srgb8(plain).astype(int).sum(-1) - 6).mean() > 0.005    # shadows did appear
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE.json configs at full size
+def test_C2_full_frame_against_the_oracle(P, oracle_mod, avenger):
+    """Config C2 (BASELINE.json configs[1]): avenger stand-in 1920x1080, Whitted, depth 10, 1 spp -- the whole frame against the
+    oracle (all host threads), at the north-star bars: ids >= 99.9 %, <= 2 LSB on >= 99.5 %, PSNR >= 45 dB, ray counts 0.1 %."""
+    sc, rt, o = avenger
+    cam = sc.camera
+    rt.set_camera(1920, 1080, cam.fov_y, cam.view_from, cam.view_at); o.set_camera(1920, 1080, cam.fov_y, cam.view_from, cam.view_at)
+    try:
+        pd = dict(sampling_width=1, jitter=0, aperture=0.0, max_depth=10)
+        ref, g0, p0, st0 = o.render(oracle_mod.make_params(**pd))
+        img, st = rt.render(pd)
+        g1, p1 = rt.primary_ids(pd)
+        assert np.mean((g0 == g1) & (p0 == p1)) >= 0.999
+        ok, psnr = image_bars(P, ref, img)
+        assert ok >= 0.995 and psnr >= 45.0, (ok, psnr)
+        for k in ("primary", "shadow", "reflection", "refraction"):
+            assert abs(st[k] - st0[k]) <= 1e-3 * max(st0[k], 1), (k, st[k], st0[k])
+        q, _ = rt.render_rgba8(pd)
+        assert np.array_equal(q[..., :3], P.to_srgb8(img))
+    finally:
+        rt.set_camera(640, 480, cam.fov_y, cam.view_from, cam.view_at); o.set_camera(640, 480, cam.fov_y, cam.view_from, cam.view_at)
+
+
+def test_C4_palm_grove_against_the_oracle(P, oracle_mod):
+    """Config C4 (stand-in for PalmTrees): procedural palm grove, 1920x1080, Lambert + spherical env map, 1 spp -- thin fronds
+    stress the builder; the frame against the oracle at the north-star bars."""
+    sc = scenes.palm_grove(n_palms=150)
+    rt = P.raytracer_for(sc); o = oracle_mod.Oracle(sc)
+    assert sc.ntris > 500_000 and (rt.width, rt.height) == (1920, 1080)
+    pd = dict(sampling_width=1, jitter=0, aperture=0.0, max_depth=7, shader_mode=1)
+    ref, g0, p0, st0 = o.render(oracle_mod.make_params(**pd))
+    img, st = rt.render(pd)
+    g1, p1 = rt.primary_ids(pd)
+    assert np.mean((g0 == g1) & (p0 == p1)) >= 0.999
+    ok, psnr = image_bars(P, ref, img)
+    assert ok >= 0.995 and psnr >= 45.0, (ok, psnr)
+    for k in ("primary", "shadow", "reflection", "refraction"):
+        assert abs(st[k] - st0[k]) <= 1e-3 * max(st0[k], 1), (k, st[k], st0[k])
+    assert (g0 != INVALID).mean() > 0.2
+
+
+def test_C5_soup_one_million_triangles_through_quantised_nodes(P, oracle_mod, monkeypatch):
+    """Config C5 scaled to what the oracle builds in seconds: 1 M-triangle soup through the 80-B quantised nodes (forced, as
+    the 10 M soup selects them), Lambert, 2x2 jittered samples on a 480x270 frame: ids, image bars and ray counts."""
+    sc = scenes.triangle_soup(1_000_000, seed=1, resolution=(480, 270))
+    monkeypatch.setenv("PGRT_NODE_LAYOUT", "q8")
+    rt = P.raytracer_for(sc)
+    monkeypatch.delenv("PGRT_NODE_LAYOUT")
+    assert rt.build_stats["node_bytes"] == 80
+    o = oracle_mod.Oracle(sc)
+    pd = dict(sampling_width=2, jitter=1, aperture=0.0, max_depth=7, seed=1, shader_mode=1)
+    ref, g0, p0, st0 = o.render(oracle_mod.make_params(**pd))
+    img, st = rt.render(pd)
+    g1, p1 = rt.primary_ids(pd)
+    assert np.mean((g0 == g1) & (p0 == p1)) >= 0.999
+    ok, psnr = image_bars(P, ref, img)
+    assert ok >= 0.995 and psnr >= 45.0, (ok, psnr)
+    for k in ("primary", "shadow"):
+        assert abs(st[k] - st0[k]) <= 1e-3 * max(st0[k], 1), (k, st[k], st0[k])
+
+
+def test_C3_dof_64spp_converges_to_the_high_spp_oracle(P, oracle_mod, avenger):
+    """Config C3 in the wording of SURVEY 8(d): thin lens f = 200, a = 5, 8x8 stratified samples, compared as a converged mean:
+    the 64-spp GPU frame of a 640x360 view against a 32x32 = 1024-spp oracle frame of a crop of it (different sample sets,
+    so the bar is statistical: PSNR of the 8-bit crop >= 30 dB and mean difference below half an LSB), plus the exact ray count."""
+    sc, rt, o = avenger
+    cam = sc.camera
+    rt.set_camera(640, 360, cam.fov_y, cam.view_from, cam.view_at); o.set_camera(640, 360, cam.fov_y, cam.view_from, cam.view_at)
+    try:
+        pd = dict(sampling_width=8, jitter=1, aperture=5.0, focal_distance=200.0, max_depth=7, seed=1)
+        img, st = rt.render(pd)
+        assert st["primary"] == 640 * 360 * 64
+        x0, y0, x1, y1 = 260, 130, 420, 230
+        ref = o.render(oracle_mod.make_params(**dict(pd, sampling_width=32, seed=5)), want_ids=False, region=(x0, y0, x1, y1))[0][y0:y1, x0:x1]
+        a, b = P.to_srgb8(np.nan_to_num(img[y0:y1, x0:x1])).astype(float), P.to_srgb8(np.nan_to_num(ref)).astype(float)
+        mse = np.mean((a - b) ** 2)
+        assert 10 * np.log10(255.0 ** 2 / max(mse, 1e-9)) >= 30.0 and abs(a.mean() - b.mean()) < 0.5, (mse, a.mean(), b.mean())
+        # the same 64 samples on both sides: the ordinary bars
+        ref64, _, _, st0 = o.render(oracle_mod.make_params(**pd), want_ids=False, region=(x0, y0, x1, y1))
+        ok, psnr = image_bars(P, ref64[y0:y1, x0:x1], img[y0:y1, x0:x1])
+        assert ok >= 0.995 and psnr >= 45.0, (ok, psnr)
+    finally:
+        rt.set_camera(640, 480, cam.fov_y, cam.view_from, cam.view_at); o.set_camera(640, 480, cam.fov_y, cam.view_from, cam.view_at)

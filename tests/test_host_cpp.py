@@ -403,6 +403,64 @@ def test_jpeg_decoder_fuzz_against_libjpeg(host, tmp_path):
         assert np.array_equal(buf[:, :3 * w].reshape(h, w, 3)[..., ::-1], ref), (k, w, h, kw, grey)
 
 
+_MALFORMED_FUZZ = r"""
+import ctypes as C, sys, numpy as np
+lib = C.CDLL(sys.argv[1]); lib.pg1_load_image.restype = C.c_void_p; lib.pg1_load_image.argtypes = [C.c_char_p]
+lib.pg1_free_image.argtypes = [C.c_void_p]; lib.pg1_image_info.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+seeds = [open(p, "rb").read() for p in sys.argv[3:]]
+rng = np.random.default_rng(5)
+out = sys.argv[2]
+ok = bad = 0
+for it in range(4000):
+    d = bytearray(seeds[it % len(seeds)])
+    hdr = min(len(d) - 4, 700)                   # markers, tables, frame and scan headers live here
+    mode = it % 5
+    if mode == 0:
+        for _ in range(int(rng.integers(1, 6))): d[int(rng.integers(2, hdr))] = int(rng.integers(0, 256))
+    elif mode == 1:
+        d = d[: int(rng.integers(2, len(d)))]    # truncated anywhere
+    elif mode == 2:
+        i = int(rng.integers(2, hdr)); d[i:i + 2] = bytes([0xFF, int(rng.choice([0xC0, 0xC4, 0xDA, 0xDB, 0xDD]))])   # a marker where none belongs
+    elif mode == 3:
+        i = int(rng.integers(2, hdr)); d[i] = 0xFF; d[i + 1] = int(rng.integers(0xC0, 0xE0)); d[i + 2] = 0; d[i + 3] = int(rng.integers(0, 20))   # segment with a tiny length
+    else:
+        for _ in range(40): d[int(rng.integers(2, len(d)))] = int(rng.integers(0, 256))              # noise in the entropy-coded data too
+    open(out, "wb").write(bytes(d))
+    h = lib.pg1_load_image(out.encode())
+    if h:
+        info = (C.c_int * 4)(); lib.pg1_image_info(h, info)
+        assert 0 < info[0] <= 65535 and 0 < info[1] <= 65535 and info[3] in (3, 4)
+        lib.pg1_free_image(h); ok += 1
+    else:
+        bad += 1
+print(ok, bad)
+"""
+
+
+def test_malformed_jpeg_files_are_rejected_not_trusted(host, tmp_path):
+    """header fields come from the file.  4000 mutated / truncated JPEGs (bytes flipped in the marker segments,
+    markers and short segment lengths planted, files cut anywhere, noise in the entropy-coded data) must each end in an
+    error or an image -- in a child process, so that an out-of-bounds access fails this test instead of ending the run."""
+    import subprocess
+    import sys
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    seeds = []
+    for k, (sub, q, grey) in enumerate([(0, 90, False), (2, 50, False), (1, 75, False), (0, 30, True)]):
+        p = str(tmp_path / f"seed{k}.jpg")
+        img = _test_picture(33 + 7 * k, 21 + 5 * k, k)
+        kw = dict(quality=q, optimize=bool(k % 2))
+        if grey:
+            Image.fromarray(img[..., 0], "L").save(p, "JPEG", **kw)
+        else:
+            Image.fromarray(img).save(p, "JPEG", subsampling=sub, **kw)
+        seeds.append(p)
+    r = subprocess.run([sys.executable, "-c", _MALFORMED_FUZZ, HOST_LIB, str(tmp_path / "m.jpg")] + seeds, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    ok, bad = (int(x) for x in r.stdout.split())
+    assert ok + bad == 4000 and bad > 500 and ok > 100, (ok, bad)
+
+
 def test_loader_float_scan_equals_strtof_and_crlf(host, tmp_path):
     """The loader's in-place float scan (its own two-tier exact fast path, strtof behind it) against glibc strtof (what the
     reference's sscanf("%f") does): integers, fixed and scientific notation, leading '.', trailing '.', 16-19 digit

@@ -11,12 +11,15 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="c2")
 ap.add_argument("--frames", type=int, default=3)
 ap.add_argument("--stats", default="")
+ap.add_argument("--params", default="", help="JSON object of render-parameter overrides, e.g. '{\"shader_mode\": 1}'")
 a = ap.parse_args()
 sc, p, desc = bench.workload(a.workload)
+if a.params:
+    p.update(json.loads(a.params)); desc += " " + a.params
 rt = raytracer_for(sc)
 for _ in range(a.frames):
     img, st = rt.render(p)
-print(desc, {k: st[k] for k in ("primary", "shadow", "reflection", "refraction", "total", "frame_ms", "launches")})
+print(desc, {k: st[k] for k in ("primary", "shadow", "reflection", "refraction", "total", "frame_ms", "launches", "kernel_us", "primary_phase_us")})
 if a.stats:
     img, st1 = rt.render(p, profile=1)
     lv_t = rt.level_stats()
