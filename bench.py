@@ -301,7 +301,7 @@ def run_ours(args):
     # frames in flight: the Producer loop renders frames forever (pg1/simpleguidx11.cpp:95-125); a frame whose secondary-ray
     # chains are still running leaves most of the GPU to the next one
     shard_samples = sc.camera.width * sc.camera.height * p.get("sampling_width", 1) ** 2 / world
-    auto_depth = 4 if shard_samples >= 1e6 else 8
+    auto_depth = 4 if shard_samples >= 2e6 else (8 if shard_samples >= 5e5 else 16)
     depth = max(1, min(args.inflight if args.inflight > 0 else auto_depth, 16))
     K, W = args.steps, max(args.warmup, 3)
     sr = ShardedRenderer(rt, rank, world, dev, depth=depth)
@@ -348,7 +348,10 @@ def run_ours(args):
 
     # warm-up: every slot allocates its queues and captures its frame graph on first use; also the estimate that sizes the run
     win, _, _ = run_windows(sr, 2, max(W, 2 * depth))
-    est_ms = max(win[1] / max(W, 2 * depth), 1e-3)
+    est = torch.tensor([max(win[1] / max(W, 2 * depth), 1e-3)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)      # every rank must run the same number of frames: one estimate for all
+    est_ms = float(est.item())
     R = int(min(200, max(5, math.ceil(args.min_seconds * 1e3 / (K * est_ms)))))    # windows of exactly K steps, >= min_seconds in total
     host_issue[0] = 0.0; host_issue[1] = 0
     sr.host_s, sr.host_n = [0.0, 0.0, 0.0, 0.0], 0
@@ -599,8 +602,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", dest="extra", action="store_false", help="skip the short C3 / C5 measurements appended to config.extra")
     ap.add_argument("--min-seconds", type=float, default=1.0, help="the timed windows of --steps frames are repeated until they cover this much device time")
-    ap.add_argument("--inflight", type=int, default=0, help="frames in flight per GPU (1 = one frame at a time; 0 = 4, or 8 when a frame or shard has fewer than 1 M primary samples)")
+    ap.add_argument("--inflight", type=int, default=0, help="frames in flight per GPU (1 = one frame at a time; 0 = 4 for a frame or shard of 2 M primary samples or more, 8 down to 0.5 M, 16 below)")
+    ap.add_argument("--watchdog", type=float, default=900.0, help="seconds after which a run that has not finished dumps every thread's stack and exits (a hang must not sit on a GPU box)")
     args = ap.parse_args()
+    import faulthandler
+    faulthandler.enable()
+    if args.watchdog > 0:
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:

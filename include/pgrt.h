@@ -103,7 +103,7 @@ typedef struct pgrt_render_stats {
     uint32_t overflow_retries;
     uint32_t max_nodes_per_ray;   /* worst single query (profile & 2 renders only)             */
     uint32_t reserved[4];     /* [0] pool records of the largest batch; fused scheduler, last batch: [1] frame kernel first warp in ..
-                                 last warp out (us), [2] .. until the primary rays ran out (us)   */
+                                 last warp out (us), [2] .. until the primary rays ran out (us), [3] warp iterations spent on secondary rays */
 } pgrt_render_stats;
 
 /* One recursion level of trace() (raytracer.cpp:237, `level`) in the last rendered frame. */

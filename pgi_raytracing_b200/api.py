@@ -122,7 +122,7 @@ class Raytracer:
                  frame_ms=rs.frame_ms, trace_ms=rs.trace_ms, shade_ms=rs.shade_ms, trace_launches=rs.trace_launches,
                  launches=rs.launches, batches=rs.batches, overflow_retries=rs.overflow_retries,
                  nodes_visited=rs.nodes_visited, tris_tested=rs.tris_tested, max_nodes_per_ray=rs.max_nodes_per_ray,
-                 pool_peak=rs.reserved[0], kernel_us=rs.reserved[1], primary_phase_us=rs.reserved[2])
+                 pool_peak=rs.reserved[0], kernel_us=rs.reserved[1], primary_phase_us=rs.reserved[2], pool_iters=rs.reserved[3])
         d["total"] = d["primary"] + d["shadow"] + d["reflection"] + d["refraction"]
         return d
 

@@ -137,7 +137,8 @@ struct pgrt_context {
     FrameSlot slots[PGRT_MAX_INFLIGHT];
     int frame_per_sm_max = 0, frame_per_sm_env = 0;   // occupancy bound of k_frame; PGRT_FRAME_CTAS_PER_SM
     int min_claim = 32;               // k_frame takes pool records ahead of primary rays once this many wait (PGRT_MIN_CLAIM, 1..32)
-    int keep_per_sm = 1;              // CTAs per SM of k_frame that stay until the batch is done (PGRT_KEEP_CTAS_PER_SM)
+    int keep_ctas = 8;                // CTAs of k_frame that stay until the batch is done (PGRT_KEEP_CTAS)
+    int pool_policy = 0;              // how k_frame takes secondary rays while primary rays last: 0 not at all, 1 full batches by compare-and-swap, 2 tickets (PGRT_POOL_POLICY)
     int claim_patience = 4;           // polls after which an idle warp of k_frame halves the number of pool records it waits for (PGRT_CLAIM_PATIENCE)
     double pool_scale = 1.0;          // grown after a pool overflow; never shrinks before the next pgrt_commit
     // driver entry points for stream memory operations (completion flags without a collective); null = not available
@@ -213,7 +214,8 @@ extern "C" int pgrt_create(pgrt_context** out, int device) {
     if (const char* e = getenv("PGRT_TRACE_REFILL")) ctx->trace_refill = std::min(32, std::max(1, atoi(e)));
     if (const char* e = getenv("PGRT_TRACE_CTAS_PER_SM")) ctx->trace_ctas_per_sm = std::min(16, std::max(1, atoi(e)));
     if (const char* e = getenv("PGRT_MIN_CLAIM")) ctx->min_claim = std::min(32, std::max(1, atoi(e)));
-    if (const char* e = getenv("PGRT_KEEP_CTAS_PER_SM")) ctx->keep_per_sm = std::min(32, std::max(1, atoi(e)));
+    if (const char* e = getenv("PGRT_KEEP_CTAS")) ctx->keep_ctas = std::min(1 << 16, std::max(1, atoi(e)));
+    if (const char* e = getenv("PGRT_POOL_POLICY")) ctx->pool_policy = std::min(2, std::max(0, atoi(e)));
     if (const char* e = getenv("PGRT_CLAIM_PATIENCE")) ctx->claim_patience = std::min(1 << 20, std::max(1, atoi(e)));
     {   // cuStreamWaitValue32 / cuStreamWriteValue32 through the runtime (no link-time dependency on libcuda)
         cudaDriverEntryPointQueryResult qr;
@@ -729,11 +731,11 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
         if (fused) {
             tm.begin(KC_TRACE, 0);
             if (path) {
-                if (count) k_frame<true, true><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, cnt);
-                else k_frame<false, true><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, cnt);
+                if (count) k_frame<true, true><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, ctx->pool_policy, cnt);
+                else k_frame<false, true><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, ctx->pool_policy, cnt);
             } else {
-                if (count) k_frame<true, false><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, cnt);
-                else k_frame<false, false><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, cnt);
+                if (count) k_frame<true, false><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, ctx->pool_policy, cnt);
+                else k_frame<false, false><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, ctx->pool_policy, cnt);
             }
             rs.launches++; rs.trace_launches++;
             tm.end();
@@ -815,7 +817,7 @@ static uint64_t frame_key(pgrt_context* ctx, const FrameSlot& S) {
     h = fnv1a(S.levels, sizeof(LevelBufs) * (size_t)(S.n_levels + 1), h); h = fnv1a(&S.pool, sizeof S.pool, h);
     const void* extra[4] = {S.d_frame.p, S.d_counters.p, S.stream, S.sig_flag};
     h = fnv1a(extra, sizeof extra, h);
-    const int flags[9] = {S.fused ? 1 : 0, ctx->fuse_raygen ? 1 : 0, S.frame_grid, ctx->trace_refill, ctx->trace_ctas_per_sm, S.fmt, ctx->min_claim, S.keep_ctas, ctx->claim_patience};
+    const int flags[10] = {S.fused ? 1 : 0, ctx->fuse_raygen ? 1 : 0, S.frame_grid, ctx->trace_refill, ctx->trace_ctas_per_sm, S.fmt, ctx->min_claim, S.keep_ctas, ctx->claim_patience, ctx->pool_policy};
     return fnv1a(flags, sizeof flags, h) | 1ull;
 }
 
@@ -907,9 +909,11 @@ static int frame_begin(pgrt_context* ctx, int slot, const pgrt_render_params* p,
         int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * per_sm, std::max<uint64_t>(1, (samples + 511) / 512));
         if (const char* e = getenv("PGRT_FRAME_CTAS")) grid = std::max(1, atoi(e));
         S.frame_grid = grid;
-        // one CTA per SM stays for the dependent chains of the secondary rays (4 warps x 148 SMs take 19 k rays at a time: more
-        // than any level of a Whitted frame holds at once); the rest leave when they run dry, so the next frame's kernel finds room
-        S.keep_ctas = std::min(grid, ctx->sm_count * ctx->keep_per_sm);
+        // A few CTAs stay for the dependent chains of the secondary rays; the rest leave when they run dry, so the next frame's
+        // kernel finds room.  The end of a frame is a latency chain (max_depth traversals in a row), not a throughput problem: 4 or
+        // 148 keepers give the same single-frame time (1.1 ms on C2), but every keeper holds an SM slot the following frames
+        // cannot use: 8 keepers 0.486 ms per pipelined frame, 148 keepers 0.587 (profiles/r2_sweep_kframe_keepers.txt).
+        S.keep_ctas = std::min(grid, ctx->keep_ctas);
     }
     S.rs = pgrt_render_stats{};
     rc = enqueue_frame(ctx, S);
@@ -953,6 +957,10 @@ static int frame_end(pgrt_context* ctx, int slot, pgrt_render_stats* stats) {
         ls = pgrt_level_stats{};
         ls.rays = hc.lv_rays[l]; ls.shadow_rays = hc.lv_shadow[l]; ls.nodes = hc.lv_nodes[l]; ls.tris = hc.lv_tris[l];
         ls.shadow_nodes = hc.lv_sh_nodes[l]; ls.shadow_tris = hc.lv_sh_tris[l]; ls.max_nodes = hc.lv_max_nodes[l]; ls.shadow_max_nodes = hc.lv_sh_max_nodes[l];
+        if (S.fused && l >= 1 && hc.lv_t_last[l] > hc.t_first && hc.lv_t_first[l] != ~0ull) {
+            // fused scheduler: when the level's first ray was taken up / its last ray finished, in ms after the kernel's first warp
+            ls.shade_ms = (float)((double)(hc.lv_t_first[l] - hc.t_first) * 1e-6); ls.trace_ms = (float)((double)(hc.lv_t_last[l] - hc.t_first) * 1e-6);
+        }
         rs.nodes_visited += ls.nodes + ls.shadow_nodes; rs.tris_tested += ls.tris + ls.shadow_tris;
         rs.max_nodes_per_ray = std::max(rs.max_nodes_per_ray, std::max(ls.max_nodes, ls.shadow_max_nodes));
     }
@@ -966,6 +974,7 @@ static int frame_end(pgrt_context* ctx, int slot, pgrt_render_stats* stats) {
         rs.reserved[1] = (uint32_t)((hc.t_last - hc.t_first) / 1000ull);
         rs.reserved[2] = hc.t_primary_done > hc.t_first ? (uint32_t)((hc.t_primary_done - hc.t_first) / 1000ull) : 0u;
     }
+    rs.reserved[3] = hc.pool_iters;
     if (stats) *stats = rs;
     return PGRT_OK;
 }

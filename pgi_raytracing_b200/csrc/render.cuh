@@ -87,8 +87,10 @@ struct Counters {
     uint32_t q_head, outstanding, epoch;
     uint32_t done_seq;
     uint32_t sig_value;     // what a finished frame stores in the slot's external completion flag (pgrt_slot_signal)
-    uint32_t pad2[2];
+    uint32_t pool_iters;    // fused scheduler: warp iterations spent on pool records (rays of level >= 1 / this = lanes per iteration)
+    uint32_t pad2[1];
     unsigned long long t_first, t_primary_done, t_last;   // fused scheduler: %globaltimer marks (ns): first warp in, primary rays exhausted, last warp out
+    unsigned long long lv_t_first[PGRT_MAX_LEVELS + 1], lv_t_last[PGRT_MAX_LEVELS + 1];   // ... and per level: first ray taken up, last ray finished
     uint32_t trace_next[PGRT_MAX_LEVELS + 1];   // k_trace: rays of the level's queue claimed so far
 };
 
@@ -325,6 +327,31 @@ __device__ __forceinline__ void diffuse_albedo(const DevScene& sc, const pgrt_ma
     }
 }
 
+// The bulky double-precision leaves (environment look-up: atan2 / asin in double; dielectric set-up: three exp, one pow; the
+// sRGB mix: six pow).  As real functions (-DPGRT_COLD_NOINLINE) they would keep the register count and the instruction-cache
+// footprint of the kernels down, but measured on C2 the calls cost more than they save (0.59 vs 0.64 ms per pipelined frame,
+// profiles/r2_sweep_kframe_builds.txt): inlined by default.
+#ifdef PGRT_COLD_NOINLINE
+#define PGRT_COLD __noinline__
+#else
+#define PGRT_COLD __forceinline__
+#endif
+__device__ PGRT_COLD float4 env_color(const DevTexture* env, float x, float y, float z) {
+    const Col4 c = env_get_texel(*env, x, y, z);
+    return make_float4(c.r, c.g, c.b, c.a);
+}
+__device__ PGRT_COLD float4 diel_attenuation(float kx, float ky, float kz, float t, float n1, float n2, float cos1, bool with_r) {
+    float4 att;
+    att.x = f_expf(-(1 - kx) * t); att.y = f_expf(-(1 - ky) * t); att.z = f_expf(-(1 - kz) * t); att.w = 0.0f;   // raytracer.cpp:303-305
+    if (with_r) {
+        const float alpha = (n1 - n2) / (n1 + n2);
+        // :316  pow(1 - cos1, 5) in double: five exact-ish products (<= 2 ulp of a double, invisible after the cast to float)
+        const double q1 = (double)(1 - cos1), q2 = q1 * q1;
+        att.w = (float)((double)(alpha * alpha + (1 - (alpha * alpha))) * (q2 * q2 * q1));
+    }
+    return att;
+}
+
 // PATH: compiled with the path-tracing branch (shader_mode 3).  The default instantiation carries none of it.
 template <bool PATH>
 __device__ __forceinline__ void shade_classify(const DevScene& sc, const pgrt_render_params& p, int level, float4 o, float4 d, float4 h, ShadeOut& s) {
@@ -335,8 +362,7 @@ __device__ __forceinline__ void shade_classify(const DevScene& sc, const pgrt_re
     if (d.w < 0.0f) return;                                             // unused slot of a partial tile / dead pool slot
     if (tri == PGRT_INVALID_ID) {                                       // :390-393
         const V3 dirn = normalize3(v3(d.x, d.y, d.z));
-        const Col4 c = env_get_texel(sc.env, dirn.x, dirn.y, dirn.z);
-        s.color = make_float4(c.r, c.g, c.b, c.a);
+        s.color = env_color(&sc.env, dirn.x, dirn.y, dirn.z);
         return;
     }
     s.f = hit_frame(sc, o, d, h);
@@ -350,19 +376,10 @@ __device__ __forceinline__ void shade_classify(const DevScene& sc, const pgrt_re
         if (d.w == PGRT_IOR_AIR) { n1 = PGRT_IOR_AIR; n2 = mat.ior; } else { n1 = mat.ior; n2 = PGRT_IOR_AIR; }   // :261-267
         s.kind = SK_DIEL;
         s.refl = make_reflection_ray(s.f.dirn, s.f.n, s.f.hitp, n1);
-        s.att.x = f_expf(-(1 - mat.diffuse[0]) * h.x);
-        s.att.y = f_expf(-(1 - mat.diffuse[1]) * h.x);
-        s.att.z = f_expf(-(1 - mat.diffuse[2]) * h.x);
         s.refr = make_refraction_ray(s.f.dirn, s.f.n, n1, n2, s.f.hitp);
         s.has_refr = (s.refr.d.x == s.refr.d.x);                        // :309
-        if (s.has_refr) {
-            const V3 v = -s.f.dirn;
-            const float cos1 = fabsf(dot3(s.f.n, v));
-            const float alpha = (n1 - n2) / (n1 + n2);
-            // :316  pow(1 - cos1, 5) in double: five exact-ish products (<= 2 ulp of a double, invisible after the cast to float)
-            const double q1 = (double)(1 - cos1), q2 = q1 * q1;
-            s.att.w = (float)((double)(alpha * alpha + (1 - (alpha * alpha))) * (q2 * q2 * q1));
-        }
+        const V3 v = -s.f.dirn;
+        s.att = diel_attenuation(mat.diffuse[0], mat.diffuse[1], mat.diffuse[2], h.x, n1, n2, fabsf(dot3(s.f.n, v)), s.has_refr);
     } else if (PATH && p.shader_mode == 3) {
         // path tracing: the Phong value of this hit plus albedo x the radiance of ONE cosine-weighted bounce; handled as
         // a node with a single child whose combine is linear (combine_node, att.w < 0)
@@ -465,7 +482,7 @@ __device__ __forceinline__ float4 phong_eval(const DevScene& sc, const pgrt_rend
 // ---- K10 (per node): value of a dielectric node from its children (raytracer.cpp:318-321)
 //      `own`: what the node's colour slot held before (SK_PATH keeps its Phong value there; unused otherwise)
 template <bool PATH>
-__device__ __forceinline__ float4 combine_node(float4 att, float4 a, bool has_b, float4 b, float4 own) {
+__device__ PGRT_COLD float4 combine_node(float4 att, float4 a, bool has_b, float4 b, float4 own) {
     if (PATH && att.w < 0.0f) return make_float4(own.x + att.x * a.x, own.y + att.y * a.y, own.z + att.z * a.z, 1.0f);   // SK_PATH
     if (has_b) {
         Col4 c0, c1; c0.r = a.x; c0.g = a.y; c0.b = a.z; c0.a = a.w; c1.r = b.x; c1.g = b.y; c1.b = b.z; c1.a = b.w;
@@ -599,8 +616,13 @@ __device__ __forceinline__ unsigned long long global_timer_ns() { unsigned long 
 // leave as soon as they find neither a primary chunk nor a pool record, which frees their SM slots for the next frame's kernel
 // while this frame's dependent chains (up to max_depth traversals in a row) are still running.
 template <bool COUNT, bool PATH>
-__global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(DevScene sc, pgrt_render_params p, Gen0 g0, LevelBufs L0, RayPool P, FrameOut fo,
-                                                                       int min_claim, int patience, int keep_ctas, Counters* cnt) {
+#ifdef PGRT_GRID_CONST
+#define PGRT_GC const __grid_constant__
+#else
+#define PGRT_GC
+#endif
+__global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(PGRT_GC DevScene sc, PGRT_GC pgrt_render_params p, PGRT_GC Gen0 g0, LevelBufs L0, RayPool P, FrameOut fo,
+                                                                       int min_claim, int patience, int keep_ctas, int policy, Counters* cnt) {
     const int lane = threadIdx.x & 31;
     const uint32_t n0 = g0.n_slots * (uint32_t)g0.spp;             // primary samples of this batch
     const uint32_t epoch = cnt->epoch;
@@ -608,6 +630,11 @@ __global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(DevScene s
     unsigned long long my_shadow = 0, my_refl = 0, my_refr = 0, my_shadow0 = 0;
     unsigned long long my_nodes0 = 0, my_tris0 = 0; uint32_t my_max0 = 0;   // COUNT: level-0 traversal statistics
     bool more_primary = true;
+#ifdef PGRT_NO_PREFETCH
+#define PGRT_PF_ON 0
+#else
+#define PGRT_PF_ON 1
+#endif
     // Pool records are handed out by TICKET: atomicAdd(q_head, 32) never fails, so no warp ever retries against the others (a
     // compare-and-swap here makes hundreds of idle warps fight for one word and lets ONE of them win 32 rays per round).  A
     // ticket may run ahead of q_tail: its holder then waits for exactly its own records to be published -- each lane polls its
@@ -615,7 +642,12 @@ __global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(DevScene s
     // produced, in allocation order, and the children of a finished ray are picked up within a poll interval.
     uint32_t tk_base = 0, tk_mask = 0;          // the held ticket: records tk_base + lane, for the lanes of tk_mask that are still to be processed
     uint32_t wait_polls = 0;                    // polls since the held ticket last made progress
-    if (lane == 0) atomicMin(&cnt->t_first, global_timer_ns());
+    uint32_t pf_base = 0xFFFFFFFFu; uint4 pf_q = make_uint4(0u, 0u, 0u, 0u);   // lane 0: the next primary chunk and a snapshot of the queue words
+    if (lane == 0) {
+        atomicMin(&cnt->t_first, global_timer_ns());
+        pf_base = atomicAdd(&cnt->trace_next[0], 32u);
+        pf_q = ld_volatile_u4(reinterpret_cast<const uint4*>(&cnt->q_tail));
+    }
     for (;;) {
         uint32_t base = 0, n = 0, take = 0; int mode = 0;     // mode 1 = pool records (lanes of `take`), 2 = primary rays
         uint4 l4 = make_uint4(0u, 0u, 0u, 0u);
@@ -628,27 +660,55 @@ __global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(DevScene s
             tk_mask &= ~__ballot_sync(0xffffffffu, mine && rec >= P.cap);          // beyond the pool: such a record never comes
             const uint32_t ready_mask = __ballot_sync(0xffffffffu, ready);
             // all of it, or -- once the rest has been waited for long enough -- what there is
-            if (ready_mask && (ready_mask == tk_mask || wait_polls >= (uint32_t)patience)) { mode = 1; take = ready_mask; }
+            if (ready_mask && (ready_mask == tk_mask || wait_polls >= (uint32_t)(more_primary ? 4 * patience : patience))) { mode = 1; take = ready_mask; }
         }
-        // ---- else new work: a full ticket's worth of waiting records, or a chunk of primary rays
+        // ---- else new work: a full ticket's worth of waiting records, or a chunk of primary rays.  While primary rays last, the
+        //      queue words and the next chunk were fetched when the previous chunk STARTED (pf_q, pf_base: lane 0), so neither
+        //      round trip to L2 is waited for here; a snapshot that is one chunk old only makes a ticket run ahead or come late.
         if (mode == 0 && (more_primary || tk_mask == 0u)) {
             int m = 0;      // 2 primary chunk, 5 took a ticket, 6 nothing left anywhere, 7 primaries just ran out
             if (lane == 0) {
-                const uint4 q = ld_volatile_u4(reinterpret_cast<const uint4*>(&cnt->q_tail));     // q_tail, q_head, outstanding, epoch
-                const int avail = (int)(min(q.x, P.cap) - q.y);                                  // negative: tickets already run ahead of the records
-                if (tk_mask == 0u && ((more_primary && avail >= min_claim) || (!more_primary && q.z != 0u && (keeper || avail > 0)))) {
-                    base = atomicAdd(&cnt->q_head, 32u); m = 5;
-                } else if (more_primary) {
-                    base = atomicAdd(&cnt->trace_next[0], 32u);
-                    if (base < n0) { m = 2; n = min(32u, n0 - base); }
-                    else { m = 7; atomicMax(&cnt->t_primary_done, global_timer_ns()); }
-                } else if (q.z == 0u || tk_mask == 0u) m = 6;       // the batch is done, or this warp may leave (not a keeper, nothing waiting)
+                if (more_primary) {
+                    // While primary rays last, `policy` (PGRT_POOL_POLICY) says whether a warp looks at the pool at all.  0 (default): no
+                    // -- the secondary rays wait until the primary rays of their frame are gone and are then worked off with full
+                    // warps, beside the NEXT frame's primary rays when frames are pipelined: C2 0.461 ms per frame.  2: by ticket,
+                    // like the idle warps later -- the chains advance all through the primary phase, but every traversal of
+                    // incoherent rays holds a warp slot five to six times as long as a primary chunk: 0.592 ms.  1: a full batch
+                    // that exists right now, by one compare-and-swap on a fresh read (no retry): 0.481 ms.
+                    // (profiles/r2_sweep_kframe_policy.txt; the single frame takes 1.06 - 1.12 ms with all three.)
+                    if (tk_mask == 0u && policy != 0 && (int)(min(pf_q.x, P.cap) - pf_q.y) >= min_claim) {
+                        if (policy == 2) { base = atomicAdd(&cnt->q_head, 32u); m = 5; }
+                        else {      // policy 1: only a full batch that exists right now, by one compare-and-swap on a fresh read
+                            const uint4 q = ld_volatile_u4(reinterpret_cast<const uint4*>(&cnt->q_tail));
+                            if ((int)(min(q.x, P.cap) - q.y) >= 32 && atomicCAS(&cnt->q_head, q.y, q.y + 32u) == q.y) { base = q.y; m = 5; }
+                            pf_q = q;
+                        }
+                    }
+                    if (m == 0) {
+                        base = pf_base;
+                        if (base < n0) { m = 2; n = min(32u, n0 - base); }
+                        else { m = 7; atomicMax(&cnt->t_primary_done, global_timer_ns()); }
+                    }
+                } else {
+                    // Afterwards idle warps queue up by ticket (see above): atomicAdd never fails, whoever is first in line gets the
+                    // next records that are produced.
+                    const uint4 q = ld_volatile_u4(reinterpret_cast<const uint4*>(&cnt->q_tail));
+                    const int avail = (int)(min(q.x, P.cap) - q.y);                              // negative: tickets already run ahead of the records
+                    if (tk_mask == 0u && q.z != 0u && (keeper || avail > 0)) { base = atomicAdd(&cnt->q_head, 32u); m = 5; }
+                    else if (q.z == 0u || tk_mask == 0u) m = 6;     // the batch is done, or this warp may leave (not a keeper, nothing waiting)
+                }
             }
             m = __shfl_sync(0xffffffffu, m, 0); base = __shfl_sync(0xffffffffu, base, 0); n = __shfl_sync(0xffffffffu, n, 0);
             if (m == 5) { tk_base = base; tk_mask = 0xffffffffu; wait_polls = 0; continue; }
             if (m == 7) { more_primary = false; continue; }
             if (m == 6) break;
-            if (m == 2) mode = 2;
+            if (m == 2) {
+                mode = 2;
+                if (lane == 0) {      // for the NEXT iteration; the answers arrive while this chunk is traced
+                    pf_base = atomicAdd(&cnt->trace_next[0], 32u);
+                    pf_q = ld_volatile_u4(reinterpret_cast<const uint4*>(&cnt->q_tail));
+                }
+            }
         }
         if (mode == 0) {
             // holding a ticket whose records are not there yet, nothing else to do: wait (bounded), unless the batch is over
@@ -683,6 +743,8 @@ __global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(DevScene s
         } else {
             n = (uint32_t)__popc(take);
             tk_mask &= ~take; wait_polls = 0;
+            if (lane == 0) { atomicAdd(&cnt->pool_iters, 1u); if (more_primary) pf_q = ld_volatile_u4(reinterpret_cast<const uint4*>(&cnt->q_tail)); }
+            if (COUNT && ((take >> lane) & 1u)) atomicMin(&cnt->lv_t_first[l4.y & 0xFFu], global_timer_ns());
             if ((take >> lane) & 1u) {
                 i = tk_base + (uint32_t)lane;
                 __threadfence();                                           // the publication word was seen: now the record itself
@@ -696,10 +758,10 @@ __global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(DevScene s
         ShadeOut s; s.kind = SK_FINAL; s.has_refr = false;
         bool final_ = false;
         float4 col = make_float4(0.f, 0.f, 0.f, 1.f);
+        uint32_t lane_shadow = 0;                                        // shadow queries this lane's ray issued (levels >= 1: counted per level)
         if (live) {
             TravCount tc; tc.nodes = 0; tc.tris = 0;
             const HitRec hr = trace_dev<COUNT>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, FLT_MAX, tc);
-            if (!l0) atomicAdd(&cnt->lv_rays[level], 1ull);
             if (COUNT) {
                 if (l0) { my_nodes0 += tc.nodes; my_tris0 += tc.tris; my_max0 = max(my_max0, tc.nodes); }
                 else {
@@ -718,7 +780,7 @@ __global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(DevScene s
                     if (l0) __stcg(&L0.color[i], col); else __stcg(&P.color[i], col);
                 }
                 if (l0) my_shadow0 += my_shadow - sh0;
-                else if (my_shadow != sh0) atomicAdd(&cnt->lv_shadow[level], my_shadow - sh0);
+                else lane_shadow = (uint32_t)(my_shadow - sh0);
                 if (COUNT) {
                     atomicAdd(&cnt->lv_sh_nodes[level], a1.nodes); atomicAdd(&cnt->lv_sh_tris[level], a1.tris);
                     atomicMax(&cnt->lv_sh_max_nodes[level], a1.mx);
@@ -798,6 +860,19 @@ __global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(DevScene s
                 node = par; nlk = make_uint2(l4.x, l4.y);
             }
         }
+        if (COUNT && !l0 && i != PGRT_INVALID_ID) atomicMax(&cnt->lv_t_last[level], global_timer_ns());
+        if (!l0) {
+            // per-level ray counts of the frame: one pair of atomics per warp and level (a warp's records are mostly of one level),
+            // not one per ray -- a hundred thousand same-address atomics per frame are a queue of their own in L2
+            const int lv = live ? level : -1;
+            const unsigned grp = __match_any_sync(0xffffffffu, lv);
+            uint32_t tot = 0;                                            // shadow queries of the group (every lane walks its own group's members)
+            for (int src = 0; src < 32; ++src) { const uint32_t v = __shfl_sync(0xffffffffu, lane_shadow, src); if ((grp >> src) & 1u) tot += v; }
+            if (lv >= 0 && lane == __ffs(grp) - 1) {
+                atomicAdd(&cnt->lv_rays[lv], (unsigned long long)__popc(grp));
+                if (tot) atomicAdd(&cnt->lv_shadow[lv], (unsigned long long)tot);
+            }
+        }
         // ---- retire what this iteration processed (one primary chunk, or n pool records) and account for the children
         {
             int delta = published;
@@ -872,7 +947,10 @@ __global__ void k_batch_begin(Counters* c, uint32_t n0, int first) {
     if (t == 0) {
         c->shadow = 0; c->reflection = 0; c->refraction = 0; c->q_head = 0; c->q_tail = 0;
         c->outstanding = (n0 + 31u) / 32u;      // primary chunks; pool records join as they are published (k_frame)
-        if (first) { c->t_first = ~0ull; c->t_primary_done = 0ull; c->t_last = 0ull; }
+        if (first) { c->t_first = ~0ull; c->t_primary_done = 0ull; c->t_last = 0ull; c->pool_iters = 0u; }
+    }
+    if (first && t <= PGRT_MAX_LEVELS) { c->lv_t_first[t] = ~0ull; c->lv_t_last[t] = 0ull; }
+    if (t == 0) {
         c->epoch += 1u;      // the pool's publication word: records of earlier batches (and frames) read as "not yet written"
         if (first) { c->overflow = 0; c->watchdog = 0; c->tot_shadow = 0; c->tot_reflection = 0; c->tot_refraction = 0; c->tot_primary = 0; c->q_peak = 0; }
     }

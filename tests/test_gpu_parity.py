@@ -467,8 +467,10 @@ def test_errors_are_reported_not_thrown(P):
 
 
 def test_two_ranks_p2p_and_nccl_gather_are_bit_identical():
-    """One process per GPU: the peer-mapped direct-write path (resolve kernel stores into rank 0's frame over NVLink,
-    4-byte NCCL all-reduce as the barrier) and the NCCL gather path against a single-GPU render (tools/p2p_check.py).
+    """One process per GPU (tools/p2p_check.py): the peer-mapped direct-write path (frame kernel stores into rank 0's frame over
+    NVLink) with completion by flags in shared host memory and by the NCCL all-reduce fallback, the NCCL gather path, the
+    shared-host-frame path in float and 8-bit, and a run whose ray pools overflow (retried frames must not be seen early) --
+    all against a single-GPU render, bit for bit, including what a consumer ordered right behind begin() copies.
     Needs two GPUs; the single-GPU box of the round-end run skips it."""
     import subprocess, sys, torch
     if torch.cuda.device_count() < 2:
@@ -478,6 +480,8 @@ def test_two_ranks_p2p_and_nccl_gather_are_bit_identical():
                           "--master-port", "29531", os.path.join(root, "tools", "p2p_check.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "p2p: 2 ranks" in out.stdout and "mode used = p2p" in out.stdout and "nccl: 2 ranks" in out.stdout and "host: 2 ranks" in out.stdout
+    assert "completion = flags" in out.stdout and "completion = nccl-allreduce" in out.stdout      # both completion protocols ran
+    assert "host rgba8: 2 ranks" in out.stdout and "p2p squeezed-pool: 2 ranks" in out.stdout
 
 
 def test_tiles_stored_straight_into_registered_host_memory(P, cornell):

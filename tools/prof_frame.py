@@ -20,6 +20,9 @@ rt = raytracer_for(sc)
 for _ in range(a.frames):
     img, st = rt.render(p)
 print(desc, {k: st[k] for k in ("primary", "shadow", "reflection", "refraction", "total", "frame_ms", "launches", "kernel_us", "primary_phase_us")})
+rt.render(p, profile=3)
+lv_t = rt.level_stats()
+print("level timeline (ms after the frame kernel's first warp): " + "  ".join(f"L{l}:{x['shade_ms']:.3f}-{x['trace_ms']:.3f}" for l, x in enumerate(lv_t) if l >= 1 and x["rays"]))
 if a.stats:
     img, st1 = rt.render(p, profile=1)
     lv_t = rt.level_stats()

@@ -8,9 +8,12 @@ from pgi_raytracing_b200 import raytracer_for, default_params
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="c2"); ap.add_argument("--frames", type=int, default=200); ap.add_argument("--depth", type=int, default=4)
-ap.add_argument("--tag", default="")
+ap.add_argument("--tag", default=""); ap.add_argument("--params", default="")
 a = ap.parse_args()
 sc, p, desc = bench.workload(a.workload)
+if a.params:
+    import json
+    p.update(json.loads(a.params))
 rt = raytracer_for(sc)
 params = default_params(**p)
 dev = torch.zeros((rt.height, rt.width, 4), dtype=torch.float32, device="cuda")
@@ -18,7 +21,7 @@ torch.cuda.synchronize()
 lat = []
 for _ in range(6):
     st = rt.render_device(dev.data_ptr(), params, profile=True)
-    lat.append((st["frame_ms"], st["kernel_us"], st["primary_phase_us"]))
+    lat.append((st["frame_ms"], st["kernel_us"], st["primary_phase_us"], st["pool_iters"], st["reflection"] + st["refraction"]))
 lat = sorted(lat)[len(lat) // 2]
 frames = [torch.zeros((rt.height, rt.width, 4), dtype=torch.float32, device="cuda") for _ in range(a.depth)]
 torch.cuda.synchronize()
@@ -35,6 +38,6 @@ def run(n):
     return time.perf_counter() - t0, rays
 run(3 * a.depth)
 t, rays = run(a.frames)
-print(f"{a.tag or os.environ.get('PGRT_LIB', 'default')} keep={os.environ.get('PGRT_KEEP_CTAS_PER_SM', '1')} claim={os.environ.get('PGRT_MIN_CLAIM', '32')} "
-      f"ctas={os.environ.get('PGRT_FRAME_CTAS_PER_SM', 'max')} | blocking frame {lat[0]:.3f} ms (kernel {lat[1]} us, primaries done at {lat[2]} us) | "
+print(f"{a.tag or os.environ.get('PGRT_LIB', 'default')} keep={os.environ.get('PGRT_KEEP_CTAS', '8')} policy={os.environ.get('PGRT_POOL_POLICY', '1')} claim={os.environ.get('PGRT_MIN_CLAIM', '32')} "
+      f"ctas={os.environ.get('PGRT_FRAME_CTAS_PER_SM', 'max')} | blocking frame {lat[0]:.3f} ms (kernel {lat[1]} us, primaries done at {lat[2]} us, {lat[4]} secondary rays in {lat[3]} warp iterations) | "
       f"pipelined x{a.depth}: {t / a.frames * 1e3:.3f} ms/frame = {rays / t / 1e6:.0f} Mrays/s", flush=True)
