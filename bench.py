@@ -302,7 +302,7 @@ def run_ours(args):
     # chains are still running leaves most of the GPU to the next one
     shard_samples = sc.camera.width * sc.camera.height * p.get("sampling_width", 1) ** 2 / world
     auto_depth = 4 if shard_samples >= 2e6 else (8 if shard_samples >= 5e5 else 16)
-    depth = max(1, min(args.inflight if args.inflight > 0 else auto_depth, 16))
+    depth = max(1, min(args.inflight if args.inflight > 0 else auto_depth, 32))
     K, W = args.steps, max(args.warmup, 3)
     sr = ShardedRenderer(rt, rank, world, dev, depth=depth)
     FLUSH_BYTES = int(torch.cuda.get_device_properties(dev).L2_cache_size * 1.125) // 4096 * 4096   # a fill 12.5 % larger than L2

@@ -24,7 +24,7 @@ extern "C" {
 #define PGRT_ERR_NO_DEVICE 3    /* no usable GPU                                           */
 #define PGRT_ERR_OVERFLOW 4     /* secondary-ray queues overflowed even at the minimum batch */
 
-#define PGRT_MAX_INFLIGHT 16           /* frame slots of a context (pipelined frames)             */
+#define PGRT_MAX_INFLIGHT 32           /* frame slots of a context (pipelined frames)             */
 
 #define PGRT_INVALID_ID 0xFFFFFFFFu   /* = RTC_INVALID_GEOMETRY_ID, embree3/rtcore_common.h:45 */
 #define PGRT_IOR_AIR 1.000293f        /* material.h:15 */
@@ -216,6 +216,9 @@ int pgrt_stream_wait_slot(pgrt_context* ctx, int32_t slot, void* cuda_stream);
  * overflow; pgrt_stream_wait_value32 makes a stream wait until *flag_device >= value (cuStreamWaitValue32),
  * pgrt_stream_write_value32 stores a value in stream order (the "frame consumed" signal in the other direction). */
 int pgrt_slot_signal(pgrt_context* ctx, int32_t slot, void* flag_device, uint32_t value);
+/* the same with a counter shared by all ranks: a finished frame adds 1 to *counter_device (system-scope atomic; the counter may live on
+ * another GPU behind NVLink), so the consumer waits once per frame for n_ranks * frames instead of once per rank */
+int pgrt_slot_signal_add(pgrt_context* ctx, int32_t slot, void* counter_device);
 int pgrt_stream_wait_value32(pgrt_context* ctx, void* cuda_stream, void* flag_device, uint32_t value);
 int pgrt_stream_write_value32(pgrt_context* ctx, void* cuda_stream, void* flag_device, uint32_t value);
 /* cross-frame accumulation (the step after the path; the reference's Producer re-renders from scratch every iteration,

@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 PGRT_OK, PGRT_ERR_INVALID, PGRT_ERR_CUDA, PGRT_ERR_NO_DEVICE, PGRT_ERR_OVERFLOW = 0, 1, 2, 3, 4
 INVALID_ID = 0xFFFFFFFF
-MAX_INFLIGHT = 16
+MAX_INFLIGHT = 32
 
 
 class Material(C.Structure):
@@ -90,6 +90,7 @@ SYMBOLS = {
     "pgrt_render_rgba8_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),
     "pgrt_render_shard_to_frame_rgba8_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),
     "pgrt_slot_signal": (C.c_int, [_VP, _I32, _VP, _U32]),
+    "pgrt_slot_signal_add": (C.c_int, [_VP, _I32, _VP]),
     "pgrt_stream_wait_value32": (C.c_int, [_VP, _VP, _VP, _U32]),
     "pgrt_stream_write_value32": (C.c_int, [_VP, _VP, _VP, _U32]),
     "pgrt_render_end": (C.c_int, [_VP, _I32, C.POINTER(RenderStats)]),

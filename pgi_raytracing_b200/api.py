@@ -248,6 +248,10 @@ class Raytracer:
         """Frames begun on ``slot`` from now on store ``value`` in ``*flag_ptr`` when they finish (``pgrt_slot_signal``)."""
         self._check(self.lib.pgrt_slot_signal(self.h, slot, C.c_void_p(flag_ptr), value))
 
+    def slot_signal_add(self, slot: int, counter_ptr: int):
+        """Frames begun on ``slot`` from now on add 1 to ``*counter_ptr`` when they finish (``pgrt_slot_signal_add``)."""
+        self._check(self.lib.pgrt_slot_signal_add(self.h, slot, C.c_void_p(counter_ptr)))
+
     def stream_wait_value32(self, cuda_stream_ptr: int, flag_ptr: int, value: int):
         self._check(self.lib.pgrt_stream_wait_value32(self.h, C.c_void_p(cuda_stream_ptr), C.c_void_p(flag_ptr), value))
 

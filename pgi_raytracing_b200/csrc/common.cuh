@@ -147,6 +147,7 @@ struct DevScene {
     uint32_t n_tris;
     int32_t node_layout;      // PGRT_LAYOUT_Q8 (80 B nodes) or PGRT_LAYOUT_F32 (240 B nodes), bvh8.cuh
     int32_t loop_ww;          // traversal loop shape: 1 while-while, 0 if-if (traverse.cuh trav_advance)
+    float bb_lo[3], bb_hi[3]; // bounds of the whole scene (the root of the binary tree): rays that miss them skip the traversal
 };
 
 #define CUDA_TRY(call)                                                                                  \

@@ -67,7 +67,7 @@ struct FrameSlot {
     bool busy = false;
     pgrt_render_params params = {};
     void* dest = nullptr; int dest_mode = 0; int fmt = 0; void* host_dst = nullptr; int profile = 0;   // fmt: 0 float4, 1 R8G8B8A8_UNORM
-    uint32_t* sig_flag = nullptr; uint32_t sig_value = 0;   // external completion flag (pgrt_slot_signal)
+    uint32_t* sig_flag = nullptr; uint32_t sig_value = 0; bool sig_add = false;   // external completion flag (pgrt_slot_signal / pgrt_slot_signal_add)
     uint32_t seq_expected = 0;        // frames begun on this slot = value of Counters::done_seq once the last of them has finished
     uint64_t batch_slots = 0; int n_levels = 0; bool fused = false;
     pgrt_render_stats rs = {};
@@ -124,6 +124,7 @@ struct pgrt_context {
     DevBuf<DevTexture> d_textures;
     DevBuf<float4> d_shade, d_tris, d_nodes;
     uint32_t n_tris = 0;
+    float bb_lo[3] = {0.f, 0.f, 0.f}, bb_hi[3] = {0.f, 0.f, 0.f};     // scene bounds (root of the binary tree), set by pgrt_commit
     int node_layout = PGRT_LAYOUT_Q8, loop_ww = 0;
     bool committed = false, tables_dirty = true;
     pgrt_build_stats last_build = {};
@@ -174,6 +175,7 @@ struct pgrt_context {
         s.materials = d_materials.p; s.textures = d_textures.p; s.n_textures = (int32_t)textures.size();
         s.env.data = env.set ? env.bytes.p : nullptr; s.env.width = env.w; s.env.height = env.h; s.env.pitch = env.pitch; s.env.bpp = env.bpp;
         s.lights = d_lights.p; s.n_lights = (int32_t)h_lights.size(); s.n_tris = n_tris; s.node_layout = node_layout; s.loop_ww = loop_ww;
+        for (int a = 0; a < 3; ++a) { s.bb_lo[a] = bb_lo[a]; s.bb_hi[a] = bb_hi[a]; }
         return s;
     }
 };
@@ -563,6 +565,8 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
     BUILD_TRY(cudaStreamSynchronize(st));
     if (hcc.tris != N) { rc = ctx->fail(PGRT_ERR_CUDA, "pgrt_commit: collapse emitted a wrong number of triangles"); cleanup(); return rc; }
     if (depth + 2 > PGRT_STACK8) { rc = ctx->fail(PGRT_ERR_INVALID, "pgrt_commit: the tree is deeper than the traversal stack (degenerate input)"); cleanup(); return rc; }
+    ctx->bb_lo[0] = rb[0].x; ctx->bb_lo[1] = rb[0].y; ctx->bb_lo[2] = rb[0].z; ctx->bb_hi[0] = rb[1].x; ctx->bb_hi[1] = rb[1].y; ctx->bb_hi[2] = rb[1].z;
+    if (getenv("PGRT_NO_SCENE_BOX")) for (int a = 0; a < 3; ++a) { ctx->bb_lo[a] = -FLT_MAX; ctx->bb_hi[a] = FLT_MAX; }   // A/B: the test never culls
     const float ra = box_half_area(rb[0], rb[1]);
     bs.nodes = hcc.nodes; bs.sah_cost = ra > 0.0f ? hcc.sah / ra : (float)N;
     bs.depth = depth; bs.ploc_passes = passes; bs.node_bytes = (uint32_t)(node_f4 * 16);
@@ -790,7 +794,7 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
             }
             valid_px = v * SPP;
         }
-        k_batch_end<<<1, 64, 0, st>>>(cnt, valid_px, fused ? 1 : 0, last ? 1 : 0, S.sig_flag); rs.launches++;
+        k_batch_end<<<1, 64, 0, st>>>(cnt, valid_px, fused ? 1 : 0, last ? 1 : 0, S.sig_flag, S.sig_add ? 1 : 0); rs.launches++;
     }
     CUDA_TRY(cudaMemcpyAsync(S.h_counters, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     if (S.host_dst)   // the memcpy of simpleguidx11.cpp:121-124; overlaps the next frame when the destination is pinned
@@ -815,7 +819,7 @@ static uint64_t frame_key(pgrt_context* ctx, const FrameSlot& S) {
     h = fnv1a(&S.dest, sizeof S.dest, h); h = fnv1a(&S.host_dst, sizeof S.host_dst, h); h = fnv1a(&S.dest_mode, sizeof S.dest_mode, h);
     h = fnv1a(&S.batch_slots, sizeof S.batch_slots, h); h = fnv1a(&S.n_levels, sizeof S.n_levels, h);
     h = fnv1a(S.levels, sizeof(LevelBufs) * (size_t)(S.n_levels + 1), h); h = fnv1a(&S.pool, sizeof S.pool, h);
-    const void* extra[4] = {S.d_frame.p, S.d_counters.p, S.stream, S.sig_flag};
+    const void* extra[5] = {S.d_frame.p, S.d_counters.p, S.stream, S.sig_flag, S.sig_add ? (const void*)1 : nullptr};
     h = fnv1a(extra, sizeof extra, h);
     const int flags[10] = {S.fused ? 1 : 0, ctx->fuse_raygen ? 1 : 0, S.frame_grid, ctx->trace_refill, ctx->trace_ctas_per_sm, S.fmt, ctx->min_claim, S.keep_ctas, ctx->claim_patience, ctx->pool_policy};
     return fnv1a(flags, sizeof flags, h) | 1ull;
@@ -842,7 +846,7 @@ static int enqueue_frame(pgrt_context* ctx, FrameSlot& S) {
     int rc = prepare_frame(ctx, S);
     if (rc) return rc;
     cudaStream_t st = S.stream;
-    if (S.sig_flag) { rc = stream_write32(ctx, st, &S.d_counters.p->sig_value, S.sig_value); if (rc) return rc; }   // outside the graph: it changes every frame
+    if (S.sig_flag && !S.sig_add) { rc = stream_write32(ctx, st, &S.d_counters.p->sig_value, S.sig_value); if (rc) return rc; }   // outside the graph: it changes every frame
     CUDA_TRY(cudaEventRecord(S.ev_frame0, st));
     bool submitted = false;
     const bool graphable = ctx->use_graphs && S.profile == 0 && S.dest_mode != 2 && (!S.host_dst || host_ptr_is_pinned(S.host_dst));
@@ -930,7 +934,15 @@ static int frame_end(pgrt_context* ctx, int slot, pgrt_render_stats* stats) {
     S.busy = false;
     for (;;) {
         CUDA_TRY(cudaStreamSynchronize(S.stream));
-        if (S.h_counters->watchdog) { S.seq_expected = S.h_counters->done_seq; return ctx->fail(PGRT_ERR_CUDA, "render: internal error in the frame kernel (a bounded wait expired; the frame is incomplete)"); }
+        if (S.h_counters->watchdog) {
+            S.seq_expected = S.h_counters->done_seq;
+            const uint32_t* w = S.h_counters->wd_info;
+            char buf[384];
+            snprintf(buf, sizeof buf, "render: internal error in the frame kernel (a bounded wait expired; the frame is incomplete): ticket base %u mask %08x, q_tail %u q_head %u "
+                     "outstanding %u, block %u more_primary %u, primary chunks claimed up to %u of %llu, pool cap %u, grid %d keepers %d", w[0], w[1], w[2], w[3], w[4], w[5] & 0x7fffffffu,
+                     w[5] >> 31, w[6], (unsigned long long)S.batch_slots * S.params.sampling_width * S.params.sampling_width, w[7], S.frame_grid, S.keep_ctas);
+            return ctx->fail(PGRT_ERR_CUDA, buf);
+        }
         if (!S.h_counters->overflow) break;
         // A secondary-ray queue overflowed (rare; sizes are generous): the attempt did not signal completion (k_batch_end), so
         // no consumer ordered behind this slot has been released.  Render the frame again with four times the capacity -
@@ -1127,7 +1139,16 @@ extern "C" int pgrt_slot_signal(pgrt_context* ctx, int32_t slot, void* flag_devi
     CHECK_CTX(ctx);
     if (slot < 0 || slot >= PGRT_MAX_INFLIGHT) return ctx->fail(PGRT_ERR_INVALID, "pgrt_slot_signal: slot out of range");
     if (ctx->slots[slot].busy) return ctx->fail(PGRT_ERR_INVALID, "pgrt_slot_signal: the slot holds a frame in flight");
-    ctx->slots[slot].sig_flag = (uint32_t*)flag_device; ctx->slots[slot].sig_value = value;
+    ctx->slots[slot].sig_flag = (uint32_t*)flag_device; ctx->slots[slot].sig_value = value; ctx->slots[slot].sig_add = false;
+    return PGRT_OK;
+}
+// the same with a COUNTER shared by all ranks: a finished frame adds 1 to *counter_device (system-scope atomic; the counter may live
+// on another GPU behind NVLink), so that one pgrt_stream_wait_value32 on n_ranks * frames covers every rank
+extern "C" int pgrt_slot_signal_add(pgrt_context* ctx, int32_t slot, void* counter_device) {
+    CHECK_CTX(ctx);
+    if (slot < 0 || slot >= PGRT_MAX_INFLIGHT) return ctx->fail(PGRT_ERR_INVALID, "pgrt_slot_signal_add: slot out of range");
+    if (ctx->slots[slot].busy) return ctx->fail(PGRT_ERR_INVALID, "pgrt_slot_signal_add: the slot holds a frame in flight");
+    ctx->slots[slot].sig_flag = (uint32_t*)counter_device; ctx->slots[slot].sig_value = 0; ctx->slots[slot].sig_add = counter_device != nullptr;
     return PGRT_OK;
 }
 // make `cuda_stream` wait until *flag >= value (cuStreamWaitValue32, GEQ) / store value in *flag in stream order

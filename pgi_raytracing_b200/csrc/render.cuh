@@ -10,14 +10,15 @@
 //      A warp claims either 32 primary rays (regenerated from the slot index: coherent 8x4 pixel blocks) or up to 32
 //      records of the frame's ray pool, runs the closest-hit query, classifies the hit, evaluates Phong with its
 //      shadow query inline, and for a dielectric hit appends the reflection / refraction rays to the pool, where ANY
-//      warp of the grid may claim them at once (records are published with a per-record epoch word, claimed in
-//      allocation order with one compare-and-swap per warp).  The non-linear combine is resolved by continuation: a
-//      finished node decrements its parent's pending count, and the last child to arrive evaluates mix_srgb for the
-//      parent and keeps climbing.  With one sample per pixel the warp that finishes a pixel applies gamma and stores it
-//      in the frame, so neither hits, directions nor colours of level 0 ever travel through HBM.  No warp waits for
-//      another one except for the few hundred nanoseconds between a record's allocation and its publication; a warp
-//      leaves when no primary ray is left and the pool is empty (rays still in flight belong to warps that will look
-//      again after pushing their children), so there is no polling and no time-out.
+//      warp of the grid may trace them: records are handed out by ticket (atomicAdd on q_head, 32 records per ticket, never
+//      a retry), published with a per-record epoch word, and a ticket may run ahead of the records -- its holder polls its
+//      own 32 publication words.  The non-linear combine is resolved by continuation: a finished node decrements its
+//      parent's pending count, and the last child to arrive evaluates mix_srgb for the parent and keeps climbing.  With one
+//      sample per pixel the warp that finishes a pixel applies gamma and stores it in the frame, so neither hits,
+//      directions nor colours of level 0 ever travel through HBM.  `outstanding` counts primary chunks + published records
+//      not yet retired (children are added BEFORE they are published, so it is 0 only when the batch is done).  The first
+//      keep_ctas CTAs stay and poll until it is 0; the others leave when they find neither a primary chunk nor a record,
+//      which frees their SM slots for the next frame's kernel.  Every wait is bounded (Counters::watchdog reports, never hangs).
 //   1  level-synchronous wavefront, one queue per recursion level (the cross-check of scheduler 0):
 //        forward,  level = 0 .. max_depth :  k_trace -> k_shade -> k_phong
 //        backward, level = max_depth-1 .. 0 : k_combine resolves each dielectric node from its two children (post-order)
@@ -70,7 +71,7 @@ struct Counters {
     uint32_t n_phong[PGRT_MAX_LEVELS + 1];
     uint32_t n_diel[PGRT_MAX_LEVELS + 1];
     uint32_t overflow;
-    uint32_t watchdog;      // (unused by the fused scheduler: nothing in it waits with a bound)
+    uint32_t watchdog;      // fused scheduler: a bounded wait expired (internal error; wd_info says what the warp saw)
     uint32_t q_peak;        // most pool records any batch of this frame allocated (sizes the pool of the next frames)
     unsigned long long shadow, reflection, refraction;          // this batch
     unsigned long long tot_shadow, tot_reflection, tot_refraction, tot_primary;   // this frame
@@ -89,6 +90,7 @@ struct Counters {
     uint32_t sig_value;     // what a finished frame stores in the slot's external completion flag (pgrt_slot_signal)
     uint32_t pool_iters;    // fused scheduler: warp iterations spent on pool records (rays of level >= 1 / this = lanes per iteration)
     uint32_t pad2[1];
+    uint32_t wd_info[8];    // what the first warp whose bounded wait expired saw (diagnostics of the watchdog)
     unsigned long long t_first, t_primary_done, t_last;   // fused scheduler: %globaltimer marks (ns): first warp in, primary rays exhausted, last warp out
     unsigned long long lv_t_first[PGRT_MAX_LEVELS + 1], lv_t_last[PGRT_MAX_LEVELS + 1];   // ... and per level: first ray taken up, last ray finished
     uint32_t trace_next[PGRT_MAX_LEVELS + 1];   // k_trace: rays of the level's queue claimed so far
@@ -230,7 +232,7 @@ __device__ __forceinline__ void trace_queue(const DevScene& sc, const pgrt_rende
                     float4 o, d;
                     load_ray(L, g0, p, mine, o, d);
                     if (g0.on) L.ray_d[mine] = d;      // the shading kernels read it back instead of re-normalising three times
-                    if (d.w >= 0.0f && sc.n_tris != 0) {
+                    if (d.w >= 0.0f && sc.n_tris != 0 && !ray_misses_box(sc.bb_lo, sc.bb_hi, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, FLT_MAX)) {
                         j = mine;
                         ray_ctx_init(r, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, FLT_MAX, sc.loop_ww != 0);
                         trav_init(s, FLT_MAX);
@@ -406,8 +408,18 @@ struct TravAcc { unsigned long long nodes, tris; uint32_t mx; };
 #define PGRT_TRACE_DEV_ATTR __noinline__
 #endif
 template <bool COUNT>
-__device__ PGRT_TRACE_DEV_ATTR HitRec trace_dev(const DevScene& sc, V3 O, V3 D, float tnear, float tfar, TravCount& tc) {
+__device__ PGRT_TRACE_DEV_ATTR HitRec trace_dev_walk(const DevScene& sc, V3 O, V3 D, float tnear, float tfar, TravCount& tc) {
     return trace_closest_t<COUNT>(sc, O, D, tnear, tfar, tc);
+}
+// the query every kernel of this file issues: the scene-box test inline (traverse.cuh), the walk only for rays that pass it
+template <bool COUNT>
+__device__ __forceinline__ HitRec trace_dev(const DevScene& sc, V3 O, V3 D, float tnear, float tfar, TravCount& tc) {
+    if (ray_misses_box(sc.bb_lo, sc.bb_hi, O, D, tnear, tfar)) {
+        HitRec miss; miss.t = tfar; miss.u = 0.0f; miss.v = 0.0f; miss.tri = PGRT_INVALID_ID;
+        tc.nodes = 0; tc.tris = 0;
+        return miss;
+    }
+    return trace_dev_walk<COUNT>(sc, O, D, tnear, tfar, tc);
 }
 
 
@@ -718,7 +730,14 @@ __global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(PGRT_GC De
                 out = __shfl_sync(0xffffffffu, out, 0);
                 if (out == 0u) break;                                      // nothing is in flight any more: the rest of the ticket never comes
             }
-            if (++wait_polls > (1u << 23)) { if (lane == 0) cnt->watchdog = 1u; break; }   // seconds of waiting: never expected; reported, not hung
+            if (++wait_polls > (1u << 23)) {                               // seconds of waiting: never expected; reported, not hung
+                if (lane == 0 && atomicExch(&cnt->watchdog, 1u) == 0u) {
+                    const uint4 q = ld_volatile_u4(reinterpret_cast<const uint4*>(&cnt->q_tail));
+                    cnt->wd_info[0] = tk_base; cnt->wd_info[1] = tk_mask; cnt->wd_info[2] = q.x; cnt->wd_info[3] = q.y; cnt->wd_info[4] = q.z;
+                    cnt->wd_info[5] = blockIdx.x | (more_primary ? 0x80000000u : 0u); cnt->wd_info[6] = ld_volatile_u32(&cnt->trace_next[0]); cnt->wd_info[7] = P.cap;
+                }
+                break;
+            }
             __nanosleep(200u + 25u * min(wait_polls, 32u));
             continue;
         }
@@ -797,6 +816,18 @@ __global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(PGRT_GC De
         const uint32_t rr = warp_append(&cnt->q_tail, has_refr, lane);
         // records inside the pool will be claimed by somebody, alive or dead: they are outstanding from here on
         const int published = (is_diel && rl < P.cap ? 1 : 0) + (has_refr && rr < P.cap ? 1 : 0);
+        // `outstanding` must never read 0 while work exists: the children are counted BEFORE their publication words are stored
+        // (counted afterwards, a fast claimer could retire them first, the word would pass through 0 and a waiting keeper would
+        // walk away from its ticket -- the records allocated into that ticket later were then never traced and the batch hung).
+        // What this iteration retires (one primary chunk, or n pool records) leaves in the same atomic: nothing but this warp's
+        // own stores is left of it, and those are ordered before the next kernel by the end of this one.
+        int pub_w = published;
+        for (int o2 = 16; o2 > 0; o2 >>= 1) pub_w += __shfl_xor_sync(0xffffffffu, pub_w, o2);
+        const int retired = l0 ? 1 : (int)n;
+        if (pub_w > 0) {
+            if (lane == 0) { if (pub_w != retired) atomicAdd(&cnt->outstanding, (uint32_t)(pub_w - retired)); __threadfence(); }
+            __syncwarp();
+        }
         if (is_diel) {
             if (rl < P.cap && (!has_refr || rr < P.cap)) {
                 const uint32_t meta = (uint32_t)(level + 1) | (l0 ? (1u << 9) : 0u);
@@ -873,13 +904,8 @@ __global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(PGRT_GC De
                 if (tot) atomicAdd(&cnt->lv_shadow[lv], (unsigned long long)tot);
             }
         }
-        // ---- retire what this iteration processed (one primary chunk, or n pool records) and account for the children
-        {
-            int delta = published;
-            for (int o2 = 16; o2 > 0; o2 >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o2);
-            delta -= l0 ? 1 : (int)n;
-            if (lane == 0 && delta != 0) atomicAdd(&cnt->outstanding, (uint32_t)delta);
-        }
+        // ---- retire what this iteration processed (one primary chunk, or n pool records), unless that left with the children above
+        if (pub_w == 0 && lane == 0) atomicAdd(&cnt->outstanding, (uint32_t)(-retired));
         __syncwarp();
     }
     if (lane == 0) atomicMax(&cnt->t_last, global_timer_ns());
@@ -956,17 +982,19 @@ __global__ void k_batch_begin(Counters* c, uint32_t n0, int first) {
     }
 }
 // `last`: last batch of the frame.  A frame that finished without a queue overflow bumps the slot's completion count (what
-// pgrt_stream_wait_slot waits for) and stores the caller's tag in `done_flag` (host-visible or peer memory, pgrt_slot_signal:
-// what dist.ShardedRenderer waits for); an overflowed attempt does neither, so nobody is released before the retry has
-// rendered the frame.
-__global__ void k_batch_end(Counters* c, unsigned long long primary, int fused, int last, uint32_t* done_flag) {
+// pgrt_stream_wait_slot waits for) and stores the caller's tag in `done_flag` -- or adds 1 to it -- (host-visible or peer
+// memory, pgrt_slot_signal / pgrt_slot_signal_add: what dist.ShardedRenderer waits for); an overflowed attempt does neither,
+// so nobody is released before the retry has rendered the frame.
+__global__ void k_batch_end(Counters* c, unsigned long long primary, int fused, int last, uint32_t* done_flag, int flag_add) {
     if (!fused && threadIdx.x <= PGRT_MAX_LEVELS && threadIdx.x > 0) c->lv_rays[threadIdx.x] += c->n_rays[threadIdx.x];
     if (threadIdx.x == 0) {
         c->lv_rays[0] += primary; c->tot_shadow += c->shadow; c->tot_reflection += c->reflection; c->tot_refraction += c->refraction; c->tot_primary += primary;
         c->q_peak = max(c->q_peak, c->q_tail);
         if (last && !c->overflow) {
             c->done_seq += 1u;
-            if (done_flag) { __threadfence_system(); *(volatile uint32_t*)done_flag = c->sig_value; }
+            // flag_add: the flag is a counter shared by all ranks (one system-scope atomic over NVLink), so that the consumer
+            // needs ONE stream wait per frame instead of one per rank
+            if (done_flag) { __threadfence_system(); if (flag_add) atomicAdd_system(done_flag, 1u); else *(volatile uint32_t*)done_flag = c->sig_value; }
         }
     }
 }

@@ -272,6 +272,25 @@ PG_HD HitRec trace_closest8(const float4* __restrict__ nodes, const float4* __re
     return trace_closest_rc<RayCtxQ, COUNT>(nodes, tris, n_tris, O, D, tnear, tfar, tc, ww);
 }
 
+// A ray that cannot reach the scene's bounding box needs no traversal: the shadow rays of the reference leave the light with
+// the hit POSITION as their direction (LightSource.cpp:18-20) and nearly all of them point away from the scene, and so do
+// camera rays that see only sky.  One slab test with generous absolute pads (2^-21 of every term that was rounded, four times
+// what the node tests carry): like every box test of the traversal it only culls -- a hit is still decided by tri_test alone,
+// and a ray that passes here walks the tree as before.
+PG_HD bool ray_misses_box(const float* lo, const float* hi, V3 O, V3 D, float tnear, float tfar) {
+    const float ooeps = 8.271806e-25f;   // 2^-80, as in ray_ctx_init
+    const float o[3] = {O.x, O.y, O.z}, d[3] = {D.x, D.y, D.z};
+    float t0 = tnear, t1 = tfar;
+    for (int a = 0; a < 3; ++a) {
+        const float id = pg_rcp(fabsf(d[a]) > ooeps ? d[a] : copysignf(ooeps, d[a]));
+        const float oi = o[a] * id, p0 = lo[a] * id, p1 = hi[a] * id;
+        const float pad = 4.7683716e-7f * (fabsf(oi) + fabsf(p0) + fabsf(p1));
+        const float a0 = p0 - oi, a1 = p1 - oi;
+        t0 = fmaxf(t0, fminf(a0, a1) - pad); t1 = fminf(t1, fmaxf(a0, a1) + pad);
+    }
+    return !(t0 <= t1);      // (NaN anywhere: not a provable miss)
+}
+
 #ifdef __CUDACC__
 template <bool COUNT>
 __device__ __forceinline__ HitRec trace_closest_t(const DevScene& sc, V3 O, V3 D, float tnear, float tfar, TravCount& tc) {

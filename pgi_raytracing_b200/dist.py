@@ -84,14 +84,16 @@ class _DevicePtr:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2, "strides": None}
 
 
-def share_frames(raytracer, n_frames: int, rank: int, device, group=None):
-    """``n_frames`` full frames in rank 0's memory, mapped into every rank (``pgrt_frame_alloc / _export / _import``:
-    CUDA IPC, opened from each rank's own device, so its resolve kernel stores into them over NVLink).
+def share_frames(raytracer, n_frames: int, rank: int, device, group=None, nbytes: int | None = None):
+    """``n_frames`` full frames (or buffers of ``nbytes``) in rank 0's memory, zeroed, mapped into every rank
+    (``pgrt_frame_alloc / _export / _import``: CUDA IPC, opened from each rank's own device, so its kernels reach them over NVLink).
     Returns (pointers valid on this rank, rank-0 torch views or None); (None, None) when any rank cannot map them."""
     import torch
     import torch.distributed as dist
 
-    nbytes = raytracer.width * raytracer.height * 16
+    as_frames = nbytes is None
+    if nbytes is None:
+        nbytes = raytracer.width * raytracer.height * 16
     ok, ptrs, handles = 1, None, [None]
     try:
         if rank == 0:
@@ -113,7 +115,7 @@ def share_frames(raytracer, n_frames: int, rank: int, device, group=None):
     if int(flag.item()) != 1:
         return None, None
     views = None
-    if rank == 0:
+    if rank == 0 and as_frames:
         views = [torch.as_tensor(_DevicePtr(p, (raytracer.height, raytracer.width, 4)), device=device) for p in ptrs]
     return ptrs, views
 
@@ -228,7 +230,8 @@ class FlagProtocol:
         ``next_frame`` has had the previous frame (None for the very first frame);
         ``before``: every rank's slot stream waits for these before the frame may overwrite the slot;
         ``signal``: what this rank's frame stores when its tiles are in place;
-        ``done``: what rank 0's consumer stream waits for (all ranks' tiles of this frame are in place)."""
+        ``done``: what rank 0's consumer stream waits for (all ranks' tiles of this frame are in place);
+        ``done_count``: the same as ONE wait, when every rank adds 1 to a counter of the slot instead of storing its own word."""
         ops = {"mark_consumed": None, "before": []}
         if self.last_slot is not None:
             ops["mark_consumed"] = (self.consumed_offset(self.last_slot), self.count[self.last_slot])
@@ -238,6 +241,8 @@ class FlagProtocol:
         tag = self.count[slot]
         ops["signal"] = (self.done_offset(slot, rank), tag)
         ops["done"] = [(self.done_offset(slot, r), tag) for r in range(self.world)]
+        # with ONE counter per slot that every rank's finished frame adds 1 to: byte offset of the counter, value to wait for
+        ops["done_count"] = (4 * slot, (tag * self.world) & 0xFFFFFFFF)
         self.last_slot = slot
         return ops
 
@@ -263,7 +268,8 @@ class ShardedRenderer:
     every rank start the next frame).
     Mode "local" (one rank) orders nothing for the caller beyond ``stream_wait_slot``: sync before reusing a frame."""
 
-    def __init__(self, raytracer, rank: int, world: int, device, depth: int = 1, mode: str = "auto", rgba8: bool = False, flags: bool = True):
+    def __init__(self, raytracer, rank: int, world: int, device, depth: int = 1, mode: str = "auto", rgba8: bool = False, flags: bool = True,
+                 counters: bool = True):
         import torch
 
         self.rt, self.rank, self.world, self.device, self.depth = raytracer, rank, world, device, depth
@@ -295,8 +301,10 @@ class ShardedRenderer:
         if self.mode == "nccl":
             self.shards = [torch.zeros((self.n_slots, 4), dtype=torch.float32, device=device) for _ in range(depth)]
             self.gathered = [torch.empty((world, self.n_slots, 4), dtype=torch.float32, device=device) if rank == 0 else None for _ in range(depth)]
-        # completion flags in a page of shared host memory (all ranks or none)
-        self.proto, self.ctl_dev, self.ctl = None, 0, None
+        # completion flags in a page of shared host memory (all ranks or none); on top of that, when rank 0's memory can be
+        # peer-mapped, one "frames done" counter per slot THERE: every rank's finished frame adds 1 to it over NVLink, and rank 0's
+        # consumer stream needs one wait per frame on its own memory instead of one wait per rank on host memory
+        self.proto, self.ctl_dev, self.ctl, self.cnt_ptr = None, 0, None, 0
         if self.mode in ("p2p", "host") and flags:
             proto = FlagProtocol(depth, world)
             dev_base, mm, keep = share_host_region(raytracer, proto.nbytes, rank, device, name="pgrt_flags")
@@ -314,6 +322,10 @@ class ShardedRenderer:
                 if ok:
                     self.proto, self.ctl_dev, self._ctl_keep = proto, dev_base, keep
                     self.ctl = np.frombuffer(mm, dtype=np.uint32)
+                    if counters:
+                        ptrs, _ = share_frames(raytracer, 1, rank, device, nbytes=4096)
+                        if ptrs is not None:
+                            self.cnt_ptr = ptrs[0]; self._owned_frames.append(ptrs[0])
                 else:
                     release_host_region(raytracer, keep)
         self.token = torch.zeros(1, dtype=torch.float32, device=device)
@@ -327,7 +339,9 @@ class ShardedRenderer:
     def completion(self) -> str:
         if self.mode in ("local", "nccl"):
             return self.mode
-        return "flags" if self.proto is not None else "nccl-allreduce"
+        if self.proto is None:
+            return "nccl-allreduce"
+        return "flags+counter" if self.cnt_ptr else "flags"
 
     def close(self):
         """Release what this renderer shared between the ranks: host frames, the flag page, peer-mapped device frames."""
@@ -394,13 +408,19 @@ class ShardedRenderer:
             self.rt.stream_wait_slot(s, comm.cuda_stream)
         elif self.mode in ("p2p", "host"):
             if ops is not None:
-                self.rt.slot_signal(s, self.ctl_dev + ops["signal"][0], ops["signal"][1])
+                if self.cnt_ptr:
+                    self.rt.slot_signal_add(s, self.cnt_ptr + ops["done_count"][0])
+                else:
+                    self.rt.slot_signal(s, self.ctl_dev + ops["signal"][0], ops["signal"][1])
             self.rt.render_begin(s, params, frame_ptr=self.frame_ptrs[s], profile=profile, rgba8=self.rgba8)
             t.append(time.perf_counter())
             if ops is not None:
                 if self.rank == 0:
-                    for off, val in ops["done"]:
-                        self.rt.stream_wait_value32(comm.cuda_stream, self.ctl_dev + off, val)
+                    if self.cnt_ptr:
+                        self.rt.stream_wait_value32(comm.cuda_stream, self.cnt_ptr + ops["done_count"][0], ops["done_count"][1])
+                    else:
+                        for off, val in ops["done"]:
+                            self.rt.stream_wait_value32(comm.cuda_stream, self.ctl_dev + off, val)
             else:
                 self.rt.stream_wait_slot(s, comm.cuda_stream)
                 dist.all_reduce(self.token)          # completion barrier: 4 bytes; the pixels travelled inside the frame kernel

@@ -17,8 +17,9 @@ rt = raytracer_for(sc, device=local)
 ref, st_ref = rt.render(p)                       # every rank renders the whole frame alone first
 out = {}
 # (mode, completion by flags in shared host memory?, 8-bit frames?, squeeze the ray pool so that frames overflow and are re-rendered?)
-cases = [("p2p", True, False, False), ("p2p", False, False, False), ("nccl", True, False, False), ("host", True, False, False), ("host", True, True, False),
-         ("p2p", True, False, True)]
+# flags: True = flags + one counter per slot in rank 0's memory (default), "words" = one flag word per rank in host memory, False = NCCL all-reduce
+cases = [("p2p", True, False, False), ("p2p", "words", False, False), ("p2p", False, False, False), ("nccl", True, False, False), ("host", True, False, False),
+         ("host", True, True, False), ("p2p", True, False, True), ("host", "words", False, True)]
 for mode, flags, rgba8, squeeze in cases:
     if squeeze:      # every rank's first frames overflow their queues: the retry, not the overflowed attempt, must be what rank 0 sees
         os.environ["PGRT_MIN_LEVEL_CAP"] = "3000"; os.environ["PGRT_LEVEL_CAP_FACTOR"] = "0.002"
@@ -26,7 +27,7 @@ for mode, flags, rgba8, squeeze in cases:
         del os.environ["PGRT_MIN_LEVEL_CAP"]; del os.environ["PGRT_LEVEL_CAP_FACTOR"]
     else:
         rt2 = rt
-    sr = ShardedRenderer(rt2, rank, world, dev, depth=3, mode=mode, flags=flags, rgba8=rgba8)
+    sr = ShardedRenderer(rt2, rank, world, dev, depth=3, mode=mode, flags=bool(flags), rgba8=rgba8, counters=flags is True)
     rays = 0; retries = 0
     snap = []                                     # rank 0: a copy of every frame, enqueued on the consumer stream right behind begin()
     for k in range(7):                            # more frames than slots: buffers are reused
