@@ -37,6 +37,10 @@ import time
 
 import numpy as np
 
+# one hardware channel per frame-slot stream (the driver's default of 8 makes waiting streams hold back their channel-mates);
+# must be in the environment before the CUDA context exists
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 

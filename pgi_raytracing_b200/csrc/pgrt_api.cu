@@ -193,6 +193,9 @@ extern "C" void pgrt_destroy(pgrt_context* ctx);
 extern "C" int pgrt_create(pgrt_context** out, int device) {
     if (!out) return PGRT_ERR_INVALID;
     *out = nullptr;
+    // one hardware channel per frame-slot stream: with the default of 8, streams share channels and one that waits (completion
+    // flags, events) holds back its channel-mates.  Read when the CUDA context is created: a no-op if the process has one already.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return PGRT_ERR_NO_DEVICE;
     pgrt_context* ctx = new pgrt_context();

@@ -10,6 +10,8 @@ are plain Python / numpy so the host logic is testable on CPU (gloo).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 TILE_W, TILE_H = 32, 8
@@ -329,11 +331,27 @@ class ShardedRenderer:
                 else:
                     release_host_region(raytracer, keep)
         self.token = torch.zeros(1, dtype=torch.float32, device=device)
+        self._probe = set(os.environ.get("PGRT_DIST_PROBE", "").split(","))     # measurement only (tools/scale_probe.py): parts of the protocol left out
         self._events = [torch.cuda.Event() for _ in range(4 * depth + 8)]   # recycled: an event is dead 2*depth+2 steps later
         self.host_s, self.host_n = [0.0, 0.0, 0.0, 0.0], 0                 # host time per part of begin() (bench reports it)
         self.ready = [None] * depth          # event on the communication stream: frame of this slot complete on rank 0
         self.history = {}                    # step -> ready event (kept for the last `depth` steps)
         torch.cuda.synchronize(device)
+
+    def _host_sees(self, off: int, val: int, spin_s: float = 150e-6) -> bool:
+        """Has the flag word at byte ``off`` reached ``val`` (cyclic >=, the comparison of cuStreamWaitValue32)?  Polls for at most ``spin_s``."""
+        import time
+        w = self.ctl
+        i = off // 4
+        t_end = None
+        while True:
+            if ((int(w[i]) - val) & 0xFFFFFFFF) < 0x80000000:
+                return True
+            now = time.perf_counter()
+            if t_end is None:
+                t_end = now + spin_s
+            elif now >= t_end:
+                return False
 
     @property
     def completion(self) -> str:
@@ -386,11 +404,17 @@ class ShardedRenderer:
         ops = None
         if self.proto is not None:
             ops = self.proto.next_frame(s, self.rank)
-            if self.rank == 0 and ops["mark_consumed"] is not None:   # everything enqueued on the consumer stream since the last begin() has had that frame
+            if self.rank == 0 and ops["mark_consumed"] is not None and "nomark" not in self._probe:   # everything enqueued on the consumer stream since the last begin() has had that frame
                 off, val = ops["mark_consumed"]
                 self.rt.stream_write_value32(comm.cuda_stream, self.ctl_dev + off, val)
-            for off, val in ops["before"]:
-                self.rt.stream_wait_value32(self.slot_streams[s].cuda_stream, self.ctl_dev + off, val)
+            for off, val in ([] if "nobefore" in self._probe else ops["before"]):
+                # The host looks first (the word is in host memory; it is usually set within microseconds of end(k - depth)
+                # returning): a stream wait that is NOT yet satisfied parks the hardware channel of the slot's stream, and
+                # with it every other stream the driver mapped to that channel -- 0.29 -> 0.38 ms per frame at two GPUs
+                # with the default 8 channels (profiles/r2_scale_probe_n2.txt).  Only a consumer that really lags gets
+                # the stream wait, so begin() still never blocks for longer than `spin_s`.
+                if "nospin" in self._probe or not self._host_sees(off, val):
+                    self.rt.stream_wait_value32(self.slot_streams[s].cuda_stream, self.ctl_dev + off, val)
         elif self.mode != "local":
             # the slot's destination is free once what consumed its last frame has run: that work sits on rank 0's
             # communication stream before the barrier of the NEXT step, so waiting for that barrier (here, on every rank) suffices
@@ -407,14 +431,18 @@ class ShardedRenderer:
             t.append(time.perf_counter())
             self.rt.stream_wait_slot(s, comm.cuda_stream)
         elif self.mode in ("p2p", "host"):
-            if ops is not None:
+            if ops is not None and "nosignal" in self._probe:
+                self.rt.slot_signal(s, 0, 0)
+            elif ops is not None:
                 if self.cnt_ptr:
                     self.rt.slot_signal_add(s, self.cnt_ptr + ops["done_count"][0])
                 else:
                     self.rt.slot_signal(s, self.ctl_dev + ops["signal"][0], ops["signal"][1])
             self.rt.render_begin(s, params, frame_ptr=self.frame_ptrs[s], profile=profile, rgba8=self.rgba8)
             t.append(time.perf_counter())
-            if ops is not None:
+            if ops is not None and "nosignal" in self._probe:
+                self.rt.stream_wait_slot(s, comm.cuda_stream)
+            elif ops is not None:
                 if self.rank == 0:
                     if self.cnt_ptr:
                         self.rt.stream_wait_value32(comm.cuda_stream, self.cnt_ptr + ops["done_count"][0], ops["done_count"][1])
