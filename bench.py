@@ -305,7 +305,7 @@ def run_ours(args):
     # frames in flight: the Producer loop renders frames forever (pg1/simpleguidx11.cpp:95-125); a frame whose secondary-ray
     # chains are still running leaves most of the GPU to the next one
     shard_samples = sc.camera.width * sc.camera.height * p.get("sampling_width", 1) ** 2 / world
-    auto_depth = 4 if shard_samples >= 2e6 else (8 if shard_samples >= 5e5 else 16)
+    auto_depth = 16 if shard_samples >= 4e5 else 32     # profiles/r2_scale_probe_n8.txt, r2_sweep_shard_depth.txt, r2_sched_by_shard.txt
     depth = max(1, min(args.inflight if args.inflight > 0 else auto_depth, 32))
     K, W = args.steps, max(args.warmup, 3)
     sr = ShardedRenderer(rt, rank, world, dev, depth=depth)
@@ -507,13 +507,15 @@ def run_ours(args):
         req_bytes = st_count["nodes_visited"] * node_bytes + st_count["tris_tested"] * 48       # what the traversal asks L1/L2 for, per frame
         k_ms = trace_ms / max(trace_launches, 1)
         roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (achieved / peaks["hbm_gbs"]) if achieved else None,
-                "traffic": traffic.get("k_frame_dram_bytes") if traffic else None,
-                "kernel": "k_frame (the whole of trace() for every sample: closest hit, shading, shadow and secondary rays, resolve)", "bytes_per_ray": b_ray,
+                "traffic": (traffic.get("k_frame_dram_bytes" if trace_launches == n_prof else "hybrid_trace_kernels_dram_bytes") if traffic else None),
+                "kernel": ("k_frame (the whole of trace() for every sample: closest hit, shading, shadow and secondary rays, resolve)" if trace_launches == n_prof else
+                           "k_trace + k_phong + k_frame (hybrid scheduler: closest-hit and shadow queries of level 0 as wavefront kernels, every ray of level >= 1 through the pool)"),
+                "scheduler": "fused" if trace_launches == n_prof else "hybrid", "bytes_per_ray": b_ray,
                 "launch_ms_avg": k_ms, "launches_per_frame": trace_launches / max(n_prof, 1), "peak_kind": peak_kind,
                 "frame_ms_unpipelined": prof_frame_ms / max(n_prof, 1),
                 "achieved_pipelined": value / world * 1e6 * b_ray / 1e9, "frac_pipelined": value / world * 1e6 * b_ray / 1e9 / peaks["hbm_gbs"],
                 "algorithmic_min_frame_bytes": frame_bytes + scene_bytes,
-                "whole_frame_dram_bytes": traffic.get("frame_dram_bytes") if traffic else None,
+                "whole_frame_dram_bytes": (traffic.get("frame_dram_bytes" if trace_launches == n_prof else "hybrid_frame_dram_bytes") if traffic else None),
                 "traversal": {"nodes_per_ray": st_count["nodes_visited"] / max(st_count["total"], 1), "tris_per_ray": st_count["tris_tested"] / max(st_count["total"], 1),
                               "requested_bytes_per_frame": req_bytes, "requested_gbs": req_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None},
                 "l2": {"peak_gbs": l2, "requested_frac_of_l2_peak": (req_bytes / (k_ms * 1e-3) / 1e9 / l2) if (l2 and k_ms > 0) else None,
@@ -523,7 +525,7 @@ def run_ours(args):
                 "fp32": {"flop_per_ray": flop_per_ray(sc.ntris), "achieved_tflops": value / world * 1e6 * flop_per_ray(sc.ntris) / 1e12,
                          "peak_tflops": 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12,
                          "note": "SURVEY 8(d) contract figure F_ray = 192*D + 180 on the per-GPU pipelined rate; peak = 148 SM x 128 lanes x 2 x max SM clock"},
-                "note": "achieved = SURVEY 8(d) contract bytes (720 B/ray at this size) x rays of rank 0 over the frame kernel's own time, one frame at a time "
+                "note": "achieved = SURVEY 8(d) contract bytes (720 B/ray at this size) x rays of rank 0 over the traversal kernels' own time (fused scheduler: k_frame; hybrid: k_trace + k_phong + k_frame, summed), one frame at a time "
                         "(CUDA events on the launching stream, L2 flushed before each frame); *_pipelined = the same bytes over the per-GPU share of `value`"}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -606,7 +608,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", dest="extra", action="store_false", help="skip the short C3 / C5 measurements appended to config.extra")
     ap.add_argument("--min-seconds", type=float, default=1.0, help="the timed windows of --steps frames are repeated until they cover this much device time")
-    ap.add_argument("--inflight", type=int, default=0, help="frames in flight per GPU (1 = one frame at a time; 0 = 4 for a frame or shard of 2 M primary samples or more, 8 down to 0.5 M, 16 below)")
+    ap.add_argument("--inflight", type=int, default=0, help="frames in flight per GPU (1 = one frame at a time; 0 = 16 for a frame or shard of 0.4 M primary samples or more, 32 below)")
     ap.add_argument("--watchdog", type=float, default=900.0, help="seconds after which a run that has not finished dumps every thread's stack and exits (a hang must not sit on a GPU box)")
     args = ap.parse_args()
     import faulthandler

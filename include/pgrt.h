@@ -64,8 +64,12 @@ typedef struct pgrt_render_params {
                                  3 path tracing (README.md:21 "To do"; no reference counterpart): dielectrics as in 0, every other
                                    hit = its Phong value + albedo x the radiance of one cosine-weighted bounce (the environment
                                    map lights the scene); converge with pgrt_render_accumulate.  Bounces count as reflection rays. */
-    int32_t scheduler;        /* 0 fused: one persistent kernel runs trace() for every sample, secondary rays in a shared pool (default);
-                                 1 level-synchronous wavefront (one queue per recursion level).  Same image, bit for bit. */
+    int32_t scheduler;        /* 0 fused: one persistent kernel runs trace() for every sample, secondary rays in a shared pool;
+                                 1 level-synchronous wavefront (one queue per recursion level);
+                                 2 hybrid: level 0 as three lean wavefront kernels, every ray of level >= 1 through the pool;
+                                 3 automatic (what pgrt_default_params sets): hybrid for batches of PGRT_AUTO_HYBRID_MIN
+                                   (400 000) samples or more, fused below -- the faster one on either side.
+                                 Same image, bit for bit, whichever runs. */
     int32_t shadow_mode;      /* 0 is_illuminated as shipped (shadow rays that leave the light towards the hit POSITION,
                                  raytracer.cpp:150-176, LightSource.cpp:11-32: the parity contract); 1 the hard shadows of the
                                  README's to-do list (README.md:20): hit point -> light.  Non-default, no reference counterpart. */
@@ -277,6 +281,9 @@ int pgrt_debug_flush_l2(pgrt_context* ctx, int32_t slot, uint64_t bytes, uint32_
 /* read bandwidth (GB/s) of a `bytes`-sized buffer that stays L2-resident, from all SMs with L1 bypassed, `iters` passes:
  * the memory roof that applies while a scene's nodes and triangles fit L2 */
 int pgrt_debug_l2_bandwidth(pgrt_context* ctx, uint64_t bytes, int32_t iters, float* gb_per_s);
+/* builds with -DPGRT_FRAME_TIMING only (zeros otherwise): SM cycles the warps of the slot's last frame kernel spent on
+ * [0] primary chunks, [1] pool records (secondary rays), [2] resident in total; [3] = warps that ran */
+int pgrt_debug_frame_cycles(pgrt_context* ctx, int32_t slot, uint64_t out[4]);
 
 /* ---- introspection */
 uint32_t pgrt_num_triangles(const pgrt_context* ctx);

@@ -84,6 +84,7 @@ SYMBOLS = {
     "pgrt_host_frame_unregister": (C.c_int, [_VP, _VP]),
     "pgrt_debug_flush_l2": (C.c_int, [_VP, _I32, _U64, _U32]),
     "pgrt_debug_l2_bandwidth": (C.c_int, [_VP, _U64, _I32, C.POINTER(_F)]),
+    "pgrt_debug_frame_cycles": (C.c_int, [_VP, _I32, C.POINTER(_U64)]),
     "pgrt_enable_peer_access": (C.c_int, [_VP, _I32]),
     "pgrt_render_shard_to_frame_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _I32, _I32]),
     "pgrt_render_rgba8": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, C.POINTER(RenderStats), _I32]),

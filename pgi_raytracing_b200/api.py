@@ -229,6 +229,12 @@ class Raytracer:
         """Measurement helper (``pgrt_debug_flush_l2``): evict L2 on the slot's stream before a timed frame."""
         self._check(self.lib.pgrt_debug_flush_l2(self.h, slot, nbytes, value))
 
+    def frame_cycles(self, slot: int = 0):
+        """``pgrt_debug_frame_cycles`` (library built with -DPGRT_FRAME_TIMING): warp cycles on primary chunks, on pool records, resident; warps."""
+        out = (C.c_uint64 * 4)()
+        self._check(self.lib.pgrt_debug_frame_cycles(self.h, slot, out))
+        return [int(x) for x in out]
+
     def l2_bandwidth(self, nbytes: int = 32 << 20, iters: int = 50) -> float:
         """Measurement helper (``pgrt_debug_l2_bandwidth``): GB/s of an L2-resident buffer read from all SMs, L1 bypassed."""
         g = C.c_float()

@@ -105,10 +105,12 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restri
     hist[(size_t)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];   // digit-major for the scan
 }
 
-// exclusive scan of `n` uint32 in place, single block (n = 256 * n_tiles, a few 1e5 at most)
-__global__ void __launch_bounds__(1024) k_rs_scan(uint32_t* __restrict__ data, uint32_t n) {
+// exclusive scan of every digit's row of the histogram (n_tiles counts, digit-major) in place, one block per digit; the row's
+// total goes to totals[digit].  (One block over all 256 * n_tiles counts took 290 us per pass at 10 M keys: 2.3 of the 13 ms build.)
+__global__ void __launch_bounds__(1024) k_rs_scan_rows(uint32_t* __restrict__ hist, uint32_t n, uint32_t* __restrict__ totals) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
+    uint32_t* data = hist + (size_t)blockIdx.x * n;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     const uint32_t per_iter = 1024 * 4;
@@ -137,13 +139,28 @@ __global__ void __launch_bounds__(1024) k_rs_scan(uint32_t* __restrict__ data, u
         if (threadIdx.x == 1023) carry = excl;
         __syncthreads();
     }
+    if (threadIdx.x == 0) totals[blockIdx.x] = carry;
 }
 
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                            uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
-                                                           const uint32_t* __restrict__ hist_scanned, uint32_t n_tiles) {
+                                                           const uint32_t* __restrict__ hist_scanned, const uint32_t* __restrict__ totals, uint32_t n_tiles) {
     __shared__ uint32_t cnt[RS_WARPS][256];
+    __shared__ uint32_t dsum[RS_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // where digit d starts in the output: exclusive prefix of the digit totals (RS_THREADS = 256 = one thread per digit)
+    uint32_t dbase;
+    {
+        const uint32_t t = totals[threadIdx.x];
+        uint32_t incl = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        if (lane == 31) dsum[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0;
+        for (int w = 0; w < warp; ++w) before += dsum[w];
+        dbase = before + incl - t;
+    }
     for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_THREADS) (&cnt[0][0])[k] = 0;
     __syncthreads();
     const uint32_t wbase = blockIdx.x * RS_TILE + warp * (32 * RS_ITEMS);
@@ -166,7 +183,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
     __syncthreads();
     {   // exclusive prefix over warps per digit, folded with the tile's global base
         const uint32_t d = threadIdx.x;
-        uint32_t run = hist_scanned[(size_t)d * n_tiles + blockIdx.x];
+        uint32_t run = dbase + hist_scanned[(size_t)d * n_tiles + blockIdx.x];
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) { const uint32_t c = cnt[w][d]; cnt[w][d] = run; run += c; }
     }

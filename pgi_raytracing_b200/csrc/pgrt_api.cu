@@ -69,7 +69,7 @@ struct FrameSlot {
     void* dest = nullptr; int dest_mode = 0; int fmt = 0; void* host_dst = nullptr; int profile = 0;   // fmt: 0 float4, 1 R8G8B8A8_UNORM
     uint32_t* sig_flag = nullptr; uint32_t sig_value = 0; bool sig_add = false;   // external completion flag (pgrt_slot_signal / pgrt_slot_signal_add)
     uint32_t seq_expected = 0;        // frames begun on this slot = value of Counters::done_seq once the last of them has finished
-    uint64_t batch_slots = 0; int n_levels = 0; bool fused = false;
+    uint64_t batch_slots = 0; int n_levels = 0; bool fused = false, hybrid = false;   // hybrid: level 0 as wavefront kernels, levels >= 1 through the pool (k_frame)
     pgrt_render_stats rs = {};
     // the frame as a CUDA graph (re-used while nothing it depends on changes)
     cudaGraphExec_t gexec = nullptr; uint64_t gkey = 0, gseen = 0; uint32_t g_launches = 0, g_trace_launches = 0, g_batches = 0;
@@ -154,6 +154,7 @@ struct pgrt_context {
     uint32_t* h_pin = nullptr;        // pinned scratch for small read-backs of the build
     size_t max_batch_samples = (size_t)1 << 23;
     uint64_t batch_limit = 0;         // pixel slots per batch that last survived a queue overflow (0 = none yet); reset by pgrt_commit
+    size_t auto_hybrid_min = 400000;  // scheduler 3: batches of this many samples or more run the hybrid scheduler (PGRT_AUTO_HYBRID_MIN)
     size_t min_level_cap = (size_t)1 << 18;
     double level_cap_factor = 0.5;   // queue capacity of the deeper levels per primary sample (x4 for the one pool of the dynamic scheduler); overflow = retry in smaller batches
     pgrt_level_stats level_stats[PGRT_MAX_LEVELS + 1] = {};
@@ -229,6 +230,7 @@ extern "C" int pgrt_create(pgrt_context** out, int device) {
         cudaGetLastError();
     }
     if (const char* e = getenv("PGRT_MAX_BATCH_SAMPLES")) ctx->max_batch_samples = std::max<size_t>(256, strtoull(e, nullptr, 10));
+    if (const char* e = getenv("PGRT_AUTO_HYBRID_MIN")) ctx->auto_hybrid_min = (size_t)strtoull(e, nullptr, 10);
     if (const char* e = getenv("PGRT_MIN_LEVEL_CAP")) ctx->min_level_cap = std::max<size_t>(64, strtoull(e, nullptr, 10));
     if (const char* e = getenv("PGRT_LEVEL_CAP_FACTOR")) ctx->level_cap_factor = std::max(0.01, atof(e));
     *out = ctx;
@@ -464,7 +466,7 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
     };
 #define BUILD_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = ctx->fail_cuda(e__, #call, __FILE__, __LINE__); cleanup(); return rc; } } while (0)
     BUILD_TRY(keys[0].ensure(N)); BUILD_TRY(keys[1].ensure(N)); BUILD_TRY(vals[0].ensure(N)); BUILD_TRY(vals[1].ensure(N));
-    BUILD_TRY(hist.ensure(256 * (size_t)n_tiles)); BUILD_TRY(sb.ensure(1));
+    BUILD_TRY(hist.ensure(256 * (size_t)n_tiles + 256)); BUILD_TRY(sb.ensure(1));
     BUILD_TRY(b0.ensure(2 * (size_t)N)); BUILD_TRY(b1.ensure(2 * (size_t)N)); BUILD_TRY(bcount.ensure(2 * (size_t)N));
     BUILD_TRY(items[0].ensure(N)); BUILD_TRY(items[1].ensure(N)); BUILD_TRY(cc.ensure(1));
     if (use_lbvh) {
@@ -488,8 +490,8 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
     for (int pass = 0; pass < 8; ++pass) {
         const int shift = pass * 8;
         k_rs_hist<<<n_tiles, RS_THREADS, 0, st>>>(keys[cur].p, N, shift, hist.p, n_tiles);
-        k_rs_scan<<<1, 1024, 0, st>>>(hist.p, 256 * n_tiles);
-        k_rs_scatter<<<n_tiles, RS_THREADS, 0, st>>>(keys[cur].p, vals[cur].p, keys[cur ^ 1].p, vals[cur ^ 1].p, N, shift, hist.p, n_tiles);
+        k_rs_scan_rows<<<256, 1024, 0, st>>>(hist.p, n_tiles, hist.p + 256 * (size_t)n_tiles);
+        k_rs_scatter<<<n_tiles, RS_THREADS, 0, st>>>(keys[cur].p, vals[cur].p, keys[cur ^ 1].p, vals[cur ^ 1].p, N, shift, hist.p, hist.p + 256 * (size_t)n_tiles, n_tiles);
         cur ^= 1; ctx->launches += 3;
     }
     BUILD_TRY(cudaEventRecord(e2, st));
@@ -581,6 +583,24 @@ extern "C" int pgrt_commit(pgrt_context* ctx, pgrt_build_stats* stats) {
     cleanup();
     ctx->committed = true; ctx->last_build = bs;
     if (stats) *stats = bs;
+    // PGRT_L2_PERSIST=1 (measurement, off by default): an access-policy window that marks the node array as persisting in L2
+    // on every slot stream (the frame kernels are captured with it), so that streaming traffic -- the frame, the bench's L2
+    // flush -- does not evict the tree.  profiles/r2_l2_persist.txt says what it buys.
+    if (const char* e = getenv("PGRT_L2_PERSIST")) {
+        cudaDeviceProp prop;
+        if (atoi(e) != 0 && cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+            const size_t bytes = (size_t)bs.nodes * node_f4 * 16;
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, bytes + (bytes >> 2)));
+            cudaStreamAttrValue v = {};
+            v.accessPolicyWindow.base_ptr = ctx->d_nodes.p;
+            v.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+            v.accessPolicyWindow.hitRatio = 1.0f;
+            v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            for (FrameSlot& S : ctx->slots) { cudaStreamSetAttribute(S.stream, cudaStreamAttributeAccessPolicyWindow, &v); S.gkey = 0; }
+            cudaGetLastError();
+        }
+    }
     return PGRT_OK;
 }
 
@@ -611,7 +631,7 @@ extern "C" void pgrt_default_params(pgrt_render_params* p) {
     if (!p) return;
     memset(p, 0, sizeof *p);
     p->sampling_width = 3; p->jitter = 1; p->focal_distance = 200.0f; p->aperture = 5.0f; p->max_depth = 7; p->gamma_level = 0.5f;
-    p->seed = 1; p->camera_mode = 0; p->shader_mode = 0;
+    p->seed = 1; p->camera_mode = 0; p->shader_mode = 0; p->scheduler = 3;
 }
 
 extern "C" int pgrt_set_shard(pgrt_context* ctx, int32_t rank, int32_t n_ranks) {
@@ -683,7 +703,7 @@ static int validate_frame(pgrt_context* ctx, const pgrt_render_params* p) {
     if (!ctx->cam_set) return ctx->fail(PGRT_ERR_INVALID, "render: pgrt_set_camera has not been called");
     if (p->sampling_width < 1 || p->sampling_width > 64) return ctx->fail(PGRT_ERR_INVALID, "render: sampling_width out of range [1,64]");
     if (p->max_depth < 0 || p->max_depth >= PGRT_MAX_LEVELS) return ctx->fail(PGRT_ERR_INVALID, "render: max_depth out of range [0,32]");
-    if (p->scheduler != 0 && p->scheduler != 1) return ctx->fail(PGRT_ERR_INVALID, "render: scheduler must be 0 (dynamic) or 1 (level-synchronous)");
+    if (p->scheduler < 0 || p->scheduler > 3) return ctx->fail(PGRT_ERR_INVALID, "render: scheduler must be 0 (fused), 1 (level-synchronous), 2 (hybrid) or 3 (automatic)");
     if (p->shadow_mode != 0 && p->shadow_mode != 1) return ctx->fail(PGRT_ERR_INVALID, "render: shadow_mode must be 0 (as shipped) or 1 (hit point -> light)");
     return upload_tables(ctx);
 }
@@ -698,9 +718,9 @@ static int prepare_frame(pgrt_context* ctx, FrameSlot& S) {
     // one at every hit of every level, so its queues are sized for a full level each.  pool_scale grows after an overflow.
     const bool path = S.params.shader_mode == 3;
     const size_t capn = std::max<size_t>(ctx->min_level_cap, (size_t)((path ? std::max(1.0, ctx->level_cap_factor) : ctx->level_cap_factor) * ctx->pool_scale * (double)cap0));
-    int rc = ensure_levels(ctx, S, S.fused ? 1 : S.n_levels, cap0, capn, S.fused);
+    int rc = ensure_levels(ctx, S, (S.fused || S.hybrid) ? 1 : S.n_levels, cap0, capn, S.fused);
     if (rc) return rc;
-    if (S.fused) { rc = ensure_pool(ctx, S, capn * (size_t)std::min(S.n_levels - 1, path ? 8 : 4)); if (rc) return rc; }   // one pool replaces the per-level queues
+    if (S.fused || S.hybrid) { rc = ensure_pool(ctx, S, capn * (size_t)std::min(S.n_levels - 1, path ? 8 : 4)); if (rc) return rc; }   // one pool replaces the per-level queues
     if (S.host_dst) CUDA_TRY(S.d_frame.ensure(((size_t)ctx->cam.width * ctx->cam.height * pixel_bytes(S) + 15) / 16));
     return PGRT_OK;
 }
@@ -716,7 +736,7 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
     const uint64_t batch_slots = S.batch_slots;
     const DevScene sc = ctx->dev_scene();
     const unsigned trace_grid = ctx->sm_count * ctx->trace_ctas_per_sm, phong_grid = ctx->sm_count * 16, shade_grid = ctx->sm_count * 8;
-    const bool fused = S.fused;
+    const bool fused = S.fused, hybrid = S.hybrid;
     FrameTimer tm{&S, (profile & 1) != 0};
     const bool count = (profile & 2) != 0;
     const bool path = p->shader_mode == 3;   // path-tracing instantiations of k_shade / k_frame / k_combine
@@ -732,17 +752,17 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
         const uint32_t n0 = n_slots * (uint32_t)SPP;
         const bool first = slot0 == 0, last = slot0 + batch_slots >= total_slots;
         rs.batches++;
-        k_batch_begin<<<1, 64, 0, st>>>(cnt, n0, first ? 1 : 0); rs.launches++;
+        k_batch_begin<<<1, 64, 0, st>>>(cnt, n0, first ? 1 : 0, hybrid ? 1 : 0); rs.launches++;
         Gen0 g0; g0.cam = ctx->cam; g0.sh = ctx->shard; g0.slot0 = (uint32_t)slot0; g0.n_slots = n_slots; g0.spp = SPP; g0.on = (fused || ctx->fuse_raygen) ? 1 : 0;
         Gen0 gN = g0; gN.on = 0;
         if (fused) {
             tm.begin(KC_TRACE, 0);
             if (path) {
-                if (count) k_frame<true, true><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, ctx->pool_policy, cnt);
-                else k_frame<false, true><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, ctx->pool_policy, cnt);
+                if (count) k_frame<true, true><<<S.frame_grid, PGRT_FRAME_THREADS, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, ctx->pool_policy, cnt);
+                else k_frame<false, true><<<S.frame_grid, PGRT_FRAME_THREADS, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, ctx->pool_policy, cnt);
             } else {
-                if (count) k_frame<true, false><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, ctx->pool_policy, cnt);
-                else k_frame<false, false><<<S.frame_grid, 128, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, ctx->pool_policy, cnt);
+                if (count) k_frame<true, false><<<S.frame_grid, PGRT_FRAME_THREADS, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, ctx->pool_policy, cnt);
+                else k_frame<false, false><<<S.frame_grid, PGRT_FRAME_THREADS, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, ctx->pool_policy, cnt);
             }
             rs.launches++; rs.trace_launches++;
             tm.end();
@@ -752,7 +772,7 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
                 k_raygen<<<div_up(n0, 256), 256, 0, st>>>(ctx->cam, *p, ctx->shard, (uint32_t)slot0, n_slots, S.levels[0], cnt); rs.launches++;
                 tm.end();
             }
-            for (int l = 0; l < n_levels; ++l) {
+            for (int l = 0; l < (hybrid ? 1 : n_levels); ++l) {
                 tm.begin(KC_TRACE, l);
                 if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, S.levels[l], l, ctx->trace_refill, cnt);
                 else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, S.levels[l], l, ctx->trace_refill, cnt);
@@ -760,13 +780,30 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
                 tm.end();
                 if (dest_mode == 2) break;
                 tm.begin(KC_SHADE, l);
-                if (path) k_shade<true><<<shade_grid, 256, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], S.levels[l + 1], cnt);
-                else k_shade<false><<<shade_grid, 256, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], S.levels[l + 1], cnt);
+                if (hybrid) {
+                    if (path) k_shade<true, true><<<shade_grid, 256, 0, st>>>(sc, *p, g0, l, S.levels[l], S.levels[l + 1], S.pool, cnt);
+                    else k_shade<false, true><<<shade_grid, 256, 0, st>>>(sc, *p, g0, l, S.levels[l], S.levels[l + 1], S.pool, cnt);
+                }
+                else if (path) k_shade<true, false><<<shade_grid, 256, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], S.levels[l + 1], S.pool, cnt);
+                else k_shade<false, false><<<shade_grid, 256, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], S.levels[l + 1], S.pool, cnt);
                 rs.launches++;
                 tm.end();
                 tm.begin(KC_TRACE, l);   // Phong = shading preamble + one inline shadow traversal per light
                 if (count) k_phong<true><<<phong_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], cnt);
                 else k_phong<false><<<phong_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], cnt);
+                rs.launches++; rs.trace_launches++;
+                tm.end();
+            }
+            if (hybrid && p->max_depth >= 1) {
+                // every ray of level >= 1: the pool half of k_frame (its claim of primary chunks finds trace_next[0] used up by k_trace above)
+                tm.begin(KC_TRACE, 1);
+                if (path) {
+                    if (count) k_frame<true, true><<<S.frame_grid, PGRT_FRAME_THREADS, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, ctx->pool_policy, cnt);
+                    else k_frame<false, true><<<S.frame_grid, PGRT_FRAME_THREADS, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, ctx->pool_policy, cnt);
+                } else {
+                    if (count) k_frame<true, false><<<S.frame_grid, PGRT_FRAME_THREADS, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, ctx->pool_policy, cnt);
+                    else k_frame<false, false><<<S.frame_grid, PGRT_FRAME_THREADS, 0, st>>>(sc, *p, g0, S.levels[0], S.pool, fo, ctx->min_claim, ctx->claim_patience, S.keep_ctas, ctx->pool_policy, cnt);
+                }
                 rs.launches++; rs.trace_launches++;
                 tm.end();
             }
@@ -776,7 +813,7 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
             k_primary_ids<<<div_up(n_slots, 256), 256, 0, st>>>(sc, ctx->cam, ctx->shard, (uint32_t)slot0, n_slots, SPP, S.levels[0].hit, geom, prim); rs.launches++;
         } else if (!fo.direct) {
             tm.begin(KC_SHADE);
-            if (!fused) for (int l = n_levels - 2; l >= 0; --l) {
+            if (!fused && !hybrid) for (int l = n_levels - 2; l >= 0; --l) {
                 if (path) k_combine<true><<<shade_grid, 256, 0, st>>>(l, S.levels[l], S.levels[l + 1], cnt);
                 else k_combine<false><<<shade_grid, 256, 0, st>>>(l, S.levels[l], S.levels[l + 1], cnt);
                 rs.launches++;
@@ -797,7 +834,7 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
             }
             valid_px = v * SPP;
         }
-        k_batch_end<<<1, 64, 0, st>>>(cnt, valid_px, fused ? 1 : 0, last ? 1 : 0, S.sig_flag, S.sig_add ? 1 : 0); rs.launches++;
+        k_batch_end<<<1, 64, 0, st>>>(cnt, valid_px, (fused || hybrid) ? 1 : 0, last ? 1 : 0, S.sig_flag, S.sig_add ? 1 : 0); rs.launches++;
     }
     CUDA_TRY(cudaMemcpyAsync(S.h_counters, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     if (S.host_dst)   // the memcpy of simpleguidx11.cpp:121-124; overlaps the next frame when the destination is pinned
@@ -824,7 +861,7 @@ static uint64_t frame_key(pgrt_context* ctx, const FrameSlot& S) {
     h = fnv1a(S.levels, sizeof(LevelBufs) * (size_t)(S.n_levels + 1), h); h = fnv1a(&S.pool, sizeof S.pool, h);
     const void* extra[5] = {S.d_frame.p, S.d_counters.p, S.stream, S.sig_flag, S.sig_add ? (const void*)1 : nullptr};
     h = fnv1a(extra, sizeof extra, h);
-    const int flags[10] = {S.fused ? 1 : 0, ctx->fuse_raygen ? 1 : 0, S.frame_grid, ctx->trace_refill, ctx->trace_ctas_per_sm, S.fmt, ctx->min_claim, S.keep_ctas, ctx->claim_patience, ctx->pool_policy};
+    const int flags[10] = {(S.fused ? 1 : 0) | (S.hybrid ? 2 : 0), ctx->fuse_raygen ? 1 : 0, S.frame_grid, ctx->trace_refill, ctx->trace_ctas_per_sm, S.fmt, ctx->min_claim, S.keep_ctas, ctx->claim_patience, ctx->pool_policy};
     return fnv1a(flags, sizeof flags, h) | 1ull;
 }
 
@@ -898,9 +935,20 @@ static int frame_begin(pgrt_context* ctx, int slot, const pgrt_render_params* p,
     S.params = *p; S.dest = dest; S.dest_mode = dest_mode; S.host_dst = host_dst; S.profile = profile; S.fmt = fmt;
     const int SPP = p->sampling_width * p->sampling_width;
     S.n_levels = (dest_mode == 2) ? 1 : p->max_depth + 1;
-    S.fused = p->scheduler == 0 && dest_mode != 2;
-    if (S.fused && ctx->frame_per_sm_max == 0) {
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->frame_per_sm_max, k_frame<false, false>, 128, 0));
+    {
+        // scheduler 3 = automatic: the hybrid pays three more launches and the level-0 queues' round trip through L2 for lean,
+        // refilled level-0 kernels -- faster from about 400 k samples per batch (C2: whole frame 0.40 against 0.54 ms, a quarter
+        // of it 0.161 against 0.175, an eighth 0.117 against 0.106: profiles/r2_sched_by_shard.txt)
+        int sched = p->scheduler;
+        if (sched == 3) {
+            const uint64_t bs = std::min<uint64_t>(shard_slots(ctx), std::max<uint64_t>(PGRT_TILE_PIXELS, ctx->max_batch_samples / SPP / PGRT_TILE_PIXELS * PGRT_TILE_PIXELS));
+            sched = bs * (uint64_t)SPP >= ctx->auto_hybrid_min ? 2 : 0;
+        }
+        S.fused = sched == 0 && dest_mode != 2;
+        S.hybrid = sched == 2 && dest_mode != 2;
+    }
+    if ((S.fused || S.hybrid) && ctx->frame_per_sm_max == 0) {
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->frame_per_sm_max, k_frame<false, false>, PGRT_FRAME_THREADS, 0));
         ctx->frame_per_sm_max = std::max(1, ctx->frame_per_sm_max);
         if (const char* e = getenv("PGRT_FRAME_CTAS_PER_SM")) ctx->frame_per_sm_env = std::max(1, atoi(e));
     }
@@ -908,19 +956,19 @@ static int frame_begin(pgrt_context* ctx, int slot, const pgrt_render_params* p,
     uint64_t batch_slots = std::max<uint64_t>(PGRT_TILE_PIXELS, ctx->max_batch_samples / SPP / PGRT_TILE_PIXELS * PGRT_TILE_PIXELS);
     S.batch_slots = std::min(batch_slots, total_slots);
     if (ctx->batch_limit) S.batch_slots = std::min(S.batch_slots, ctx->batch_limit);   // do not overflow the same way every frame
-    if (S.fused) {
+    if (S.fused || S.hybrid) {
         // A persistent grid: as many CTAs as fit (register-bound) for a large batch; a small batch (a shard of a frame, a
         // 640x480 frame) takes one CTA per four 32-ray chunks per warp, so that the frames in flight behind it find room
         const uint64_t samples = S.batch_slots * (uint64_t)SPP;
         const int per_sm = ctx->frame_per_sm_env ? std::min(ctx->frame_per_sm_env, ctx->frame_per_sm_max) : ctx->frame_per_sm_max;
-        int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * per_sm, std::max<uint64_t>(1, (samples + 511) / 512));
+        int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * per_sm, std::max<uint64_t>(1, (samples + 4 * PGRT_FRAME_THREADS - 1) / (4 * PGRT_FRAME_THREADS)));
         if (const char* e = getenv("PGRT_FRAME_CTAS")) grid = std::max(1, atoi(e));
         S.frame_grid = grid;
         // A few CTAs stay for the dependent chains of the secondary rays; the rest leave when they run dry, so the next frame's
         // kernel finds room.  The end of a frame is a latency chain (max_depth traversals in a row), not a throughput problem: 4 or
         // 148 keepers give the same single-frame time (1.1 ms on C2), but every keeper holds an SM slot the following frames
         // cannot use: 8 keepers 0.486 ms per pipelined frame, 148 keepers 0.587 (profiles/r2_sweep_kframe_keepers.txt).
-        S.keep_ctas = std::min(grid, ctx->keep_ctas);
+        S.keep_ctas = std::min(grid, ctx->keep_ctas * (128 / PGRT_FRAME_THREADS));      // (PGRT_KEEP_CTAS counts CTAs of 128 threads)
     }
     S.rs = pgrt_render_stats{};
     rc = enqueue_frame(ctx, S);
@@ -951,7 +999,7 @@ static int frame_end(pgrt_context* ctx, int slot, pgrt_render_stats* stats) {
         // no consumer ordered behind this slot has been released.  Render the frame again with four times the capacity -
         // remembered until the next commit - or, once that would take more than a few GB per slot, in smaller batches.
         const uint32_t retries = S.rs.overflow_retries + 1;
-        const size_t pool_bytes = S.fused ? S.pool_f4[0].n * 100 : (size_t)S.n_levels * S.lv_f4[1][0].n * 100;
+        const size_t pool_bytes = (S.fused || S.hybrid) ? S.pool_f4[0].n * 100 : (size_t)S.n_levels * S.lv_f4[1][0].n * 100;
         if (pool_bytes <= ((size_t)2 << 30)) ctx->pool_scale *= 4.0;
         else {
             if (S.batch_slots <= PGRT_TILE_PIXELS) { S.seq_expected = S.h_counters->done_seq; return ctx->fail(PGRT_ERR_OVERFLOW, "render: secondary-ray queues overflow at the minimum batch; raise PGRT_MIN_LEVEL_CAP"); }
@@ -1242,6 +1290,14 @@ extern "C" int pgrt_debug_flush_l2(pgrt_context* ctx, int32_t slot, uint64_t byt
     k_l2_flush<<<ctx->sm_count * flush_ctas, 256, 0, ctx->slots[slot].stream>>>(ctx->flush_buf.p, bytes / 16, value);
     ctx->launches++;
     LAUNCH_OK();
+    return PGRT_OK;
+}
+
+extern "C" int pgrt_debug_frame_cycles(pgrt_context* ctx, int32_t slot, uint64_t out[4]) {
+    CHECK_CTX(ctx);
+    if (slot < 0 || slot >= PGRT_MAX_INFLIGHT || !out) return ctx->fail(PGRT_ERR_INVALID, "pgrt_debug_frame_cycles: bad arguments");
+    if (ctx->slots[slot].busy) return ctx->fail(PGRT_ERR_INVALID, "pgrt_debug_frame_cycles: the slot holds a frame in flight");
+    for (int i = 0; i < 4; ++i) out[i] = ctx->slots[slot].h_counters->warp_cycles[i];
     return PGRT_OK;
 }
 

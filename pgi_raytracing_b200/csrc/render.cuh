@@ -91,6 +91,7 @@ struct Counters {
     uint32_t pool_iters;    // fused scheduler: warp iterations spent on pool records (rays of level >= 1 / this = lanes per iteration)
     uint32_t pad2[1];
     uint32_t wd_info[8];    // what the first warp whose bounded wait expired saw (diagnostics of the watchdog)
+    unsigned long long warp_cycles[4];   // builds with -DPGRT_FRAME_TIMING only: SM cycles the frame kernel's warps spent on primary chunks, on pool records, resident in total; [3] warps
     unsigned long long t_first, t_primary_done, t_last;   // fused scheduler: %globaltimer marks (ns): first warp in, primary rays exhausted, last warp out
     unsigned long long lv_t_first[PGRT_MAX_LEVELS + 1], lv_t_last[PGRT_MAX_LEVELS + 1];   // ... and per level: first ray taken up, last ray finished
     uint32_t trace_next[PGRT_MAX_LEVELS + 1];   // k_trace: rays of the level's queue claimed so far
@@ -505,9 +506,13 @@ __device__ PGRT_COLD float4 combine_node(float4 att, float4 a, bool has_b, float
 }
 
 // ---- K8 (kernel): one level of the wavefront (level-synchronous scheduler)
-template <bool PATH>
-__global__ void __launch_bounds__(256, PGRT_SHADE_MIN_BLOCKS) k_shade(DevScene sc, pgrt_render_params p, Gen0 g0, int level, LevelBufs L, LevelBufs Ln, Counters* cnt) {
+// POOL (hybrid scheduler, level 0 only): the children of a dielectric hit do not go to the next level's queue but to the frame's
+// ray pool, as records of k_frame's own format (published by their epoch word, counted in `outstanding`), and the node waits
+// in L for the continuation: the k_frame launched behind this kernel finds all of level 1 ready and runs the rest of trace().
+template <bool PATH, bool POOL>
+__global__ void __launch_bounds__(256, PGRT_SHADE_MIN_BLOCKS) k_shade(DevScene sc, pgrt_render_params p, Gen0 g0, int level, LevelBufs L, LevelBufs Ln, RayPool P, Counters* cnt) {
     const uint32_t n = min(cnt->n_rays[level], L.cap);
+    const uint32_t epoch = POOL ? cnt->epoch : 0u;
     const int lane = threadIdx.x & 31;
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     unsigned long long my_refl = 0, my_refr = 0;
@@ -525,6 +530,35 @@ __global__ void __launch_bounds__(256, PGRT_SHADE_MIN_BLOCKS) k_shade(DevScene s
         const bool has_refr = is_diel && s.has_refr;
         const uint32_t pslot = warp_append(&cnt->n_phong[level], is_phong, lane);
         if (is_phong) L.phong_list[pslot] = i;
+        if (POOL) {
+            const uint32_t rl = warp_append(&cnt->q_tail, is_diel, lane);
+            const uint32_t rr = warp_append(&cnt->q_tail, has_refr, lane);
+            int pub_w = (is_diel && rl < P.cap ? 1 : 0) + (has_refr && rr < P.cap ? 1 : 0);
+            for (int o2 = 16; o2 > 0; o2 >>= 1) pub_w += __shfl_xor_sync(0xffffffffu, pub_w, o2);
+            if (pub_w > 0 && lane == 0) atomicAdd(&cnt->outstanding, (uint32_t)pub_w);
+            if (is_diel) {
+                if (rl < P.cap && (!has_refr || rr < P.cap)) {
+                    const uint32_t meta = (uint32_t)(level + 1) | (1u << 9);
+                    L.dn_att[i] = s.att; L.dn_child[i] = make_uint2(rl, has_refr ? rr : PGRT_INVALID_ID); L.pending[i] = has_refr ? 2u : 1u;
+                    P.ray_o[rl] = make_float4(s.refl.o.x, s.refl.o.y, s.refl.o.z, s.refl.tnear);
+                    P.ray_d[rl] = make_float4(s.refl.d.x, s.refl.d.y, s.refl.d.z, s.refl.time);
+                    P.link[rl] = make_uint4(i, meta, epoch, 0u);
+                    my_refl++;
+                    if (has_refr) {
+                        P.ray_o[rr] = make_float4(s.refr.o.x, s.refr.o.y, s.refr.o.z, s.refr.tnear);
+                        P.ray_d[rr] = make_float4(s.refr.d.x, s.refr.d.y, s.refr.d.z, s.refr.time);
+                        P.link[rr] = make_uint4(i, meta | (1u << 8), epoch, 0u);
+                        my_refr++;
+                    }
+                } else {
+                    cnt->overflow = 1u;   // black; the frame is re-rendered with a larger pool.  A reserved record inside the pool is published as dead
+                    if (rl < P.cap) { P.ray_d[rl] = make_float4(0.f, 0.f, 0.f, -1.0f); P.link[rl] = make_uint4(0u, 0u, epoch, 0u); }
+                    if (has_refr && rr < P.cap) { P.ray_d[rr] = make_float4(0.f, 0.f, 0.f, -1.0f); P.link[rr] = make_uint4(0u, 0u, epoch, 0u); }
+                    L.color[i] = make_float4(0.f, 0.f, 0.f, 1.f);
+                }
+            }
+            continue;
+        }
         const uint32_t dslot = warp_append(&cnt->n_diel[level], is_diel, lane);
         const uint32_t rl = warp_append(&cnt->n_rays[level + 1], is_diel, lane);
         const uint32_t rr = warp_append(&cnt->n_rays[level + 1], has_refr, lane);
@@ -610,8 +644,11 @@ __device__ __forceinline__ void store_pixel(const FrameOut& fo, size_t idx, floa
 }
 
 // ---- fused scheduler: the whole of trace() for every sample of a batch in one persistent kernel (see the file header)
+#ifndef PGRT_FRAME_THREADS
+#define PGRT_FRAME_THREADS 128      // threads per CTA of k_frame (warps work on their own: the CTA is only the unit that holds an SM slot)
+#endif
 #ifndef PGRT_FRAME_MIN_BLOCKS
-#define PGRT_FRAME_MIN_BLOCKS 5     // register cap of k_frame = 65536 / (128 * this)
+#define PGRT_FRAME_MIN_BLOCKS (5 * 128 / PGRT_FRAME_THREADS)     // register cap of k_frame = 65536 / (threads * this)
 #endif
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *(const volatile uint32_t*)p; }
@@ -633,7 +670,7 @@ template <bool COUNT, bool PATH>
 #else
 #define PGRT_GC
 #endif
-__global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(PGRT_GC DevScene sc, PGRT_GC pgrt_render_params p, PGRT_GC Gen0 g0, LevelBufs L0, RayPool P, FrameOut fo,
+__global__ void __launch_bounds__(PGRT_FRAME_THREADS, PGRT_FRAME_MIN_BLOCKS) k_frame(PGRT_GC DevScene sc, PGRT_GC pgrt_render_params p, PGRT_GC Gen0 g0, LevelBufs L0, RayPool P, FrameOut fo,
                                                                        int min_claim, int patience, int keep_ctas, int policy, Counters* cnt) {
     const int lane = threadIdx.x & 31;
     const uint32_t n0 = g0.n_slots * (uint32_t)g0.spp;             // primary samples of this batch
@@ -642,6 +679,9 @@ __global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(PGRT_GC De
     unsigned long long my_shadow = 0, my_refl = 0, my_refr = 0, my_shadow0 = 0;
     unsigned long long my_nodes0 = 0, my_tris0 = 0; uint32_t my_max0 = 0;   // COUNT: level-0 traversal statistics
     bool more_primary = true;
+#ifdef PGRT_FRAME_TIMING
+    const long long tm_enter = clock64(); long long tm_prim = 0, tm_sec = 0;
+#endif
 #ifdef PGRT_NO_PREFETCH
 #define PGRT_PF_ON 0
 #else
@@ -742,6 +782,9 @@ __global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(PGRT_GC De
             continue;
         }
         const bool l0 = mode == 2;
+#ifdef PGRT_FRAME_TIMING
+        const long long tm_0 = clock64();
+#endif
 
         // ---- this lane's ray
         uint32_t i = PGRT_INVALID_ID; int level = 0;
@@ -907,7 +950,16 @@ __global__ void __launch_bounds__(128, PGRT_FRAME_MIN_BLOCKS) k_frame(PGRT_GC De
         // ---- retire what this iteration processed (one primary chunk, or n pool records), unless that left with the children above
         if (pub_w == 0 && lane == 0) atomicAdd(&cnt->outstanding, (uint32_t)(-retired));
         __syncwarp();
+#ifdef PGRT_FRAME_TIMING
+        if (l0) tm_prim += clock64() - tm_0; else tm_sec += clock64() - tm_0;
+#endif
     }
+#ifdef PGRT_FRAME_TIMING
+    if (lane == 0) {
+        atomicAdd(&cnt->warp_cycles[0], (unsigned long long)tm_prim); atomicAdd(&cnt->warp_cycles[1], (unsigned long long)tm_sec);
+        atomicAdd(&cnt->warp_cycles[2], (unsigned long long)(clock64() - tm_enter)); atomicAdd(&cnt->warp_cycles[3], 1ull);
+    }
+#endif
     if (lane == 0) atomicMax(&cnt->t_last, global_timer_ns());
     for (int o = 16; o > 0; o >>= 1) {
         my_shadow += __shfl_xor_sync(0xffffffffu, my_shadow, o); my_refl += __shfl_xor_sync(0xffffffffu, my_refl, o); my_refr += __shfl_xor_sync(0xffffffffu, my_refr, o);
@@ -961,7 +1013,7 @@ __global__ void __launch_bounds__(256) k_primary_ids(DevScene sc, DevCamera cam,
 }
 
 // frame / batch bookkeeping.  `first`: first batch of a frame (resets the frame totals).
-__global__ void k_batch_begin(Counters* c, uint32_t n0, int first) {
+__global__ void k_batch_begin(Counters* c, uint32_t n0, int first, int pool_only) {
     const int t = threadIdx.x;
     if (t <= PGRT_MAX_LEVELS) {
         c->n_rays[t] = t == 0 ? n0 : 0u; c->n_phong[t] = 0; c->n_diel[t] = 0; c->trace_next[t] = 0;
@@ -972,13 +1024,13 @@ __global__ void k_batch_begin(Counters* c, uint32_t n0, int first) {
     }
     if (t == 0) {
         c->shadow = 0; c->reflection = 0; c->refraction = 0; c->q_head = 0; c->q_tail = 0;
-        c->outstanding = (n0 + 31u) / 32u;      // primary chunks; pool records join as they are published (k_frame)
+        c->outstanding = pool_only ? 0u : (n0 + 31u) / 32u;      // primary chunks (none when level 0 runs as wavefront kernels); pool records join as they are published
         if (first) { c->t_first = ~0ull; c->t_primary_done = 0ull; c->t_last = 0ull; c->pool_iters = 0u; }
     }
     if (first && t <= PGRT_MAX_LEVELS) { c->lv_t_first[t] = ~0ull; c->lv_t_last[t] = 0ull; }
     if (t == 0) {
         c->epoch += 1u;      // the pool's publication word: records of earlier batches (and frames) read as "not yet written"
-        if (first) { c->overflow = 0; c->watchdog = 0; c->tot_shadow = 0; c->tot_reflection = 0; c->tot_refraction = 0; c->tot_primary = 0; c->q_peak = 0; }
+        if (first) { c->warp_cycles[0] = 0; c->warp_cycles[1] = 0; c->warp_cycles[2] = 0; c->warp_cycles[3] = 0; c->overflow = 0; c->watchdog = 0; c->tot_shadow = 0; c->tot_reflection = 0; c->tot_refraction = 0; c->tot_primary = 0; c->q_peak = 0; }
     }
 }
 // `last`: last batch of the frame.  A frame that finished without a queue overflow bumps the slot's completion count (what

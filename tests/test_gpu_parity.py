@@ -329,20 +329,26 @@ def test_schedulers_agree_bit_for_bit(P, cornell, avenger):
              (rt, dict(sampling_width=1, jitter=0, aperture=0.0, max_depth=10)), (rt, dict(sampling_width=2, seed=9, max_depth=4))]
     for r, p in cases:
         a, sa = r.render(dict(p, scheduler=0)); b, sb = r.render(dict(p, scheduler=1))
+        h, sh = r.render(dict(p, scheduler=2))       # hybrid: level 0 as wavefront kernels, levels >= 1 through the pool
         assert np.array_equal(a, b, equal_nan=True), p
+        assert np.array_equal(a, h, equal_nan=True), p
         for k in ("primary", "shadow", "reflection", "refraction"):
-            assert sa[k] == sb[k], (k, p)
+            assert sa[k] == sb[k] == sh[k], (k, p)
         assert sa["launches"] < sb["launches"] or p.get("max_depth") == 1
+        assert sa["launches"] < sh["launches"] <= 7
     la = rt.render(dict(cases[2][1], scheduler=0), profile=3)[1]; lv0 = rt.level_stats()
     lb = rt.render(dict(cases[2][1], scheduler=1), profile=3)[1]; lv1 = rt.level_stats()
+    lh = rt.render(dict(cases[2][1], scheduler=2), profile=3)[1]; lv2 = rt.level_stats()
     assert [x["rays"] for x in lv0] == [x["rays"] for x in lv1] and [x["shadow_rays"] for x in lv0] == [x["shadow_rays"] for x in lv1]
+    assert [x["rays"] for x in lv0] == [x["rays"] for x in lv2] and [x["shadow_rays"] for x in lv0] == [x["shadow_rays"] for x in lv2]
     assert (la["nodes_visited"], la["tris_tested"]) == (lb["nodes_visited"], lb["tris_tested"]) and la["nodes_visited"] > 0
+    assert (la["nodes_visited"], la["tris_tested"]) == (lh["nodes_visited"], lh["tris_tested"])
 
 
-@pytest.mark.parametrize("scheduler", [0, 1])
+@pytest.mark.parametrize("scheduler", [0, 1, 2])
 def test_queue_overflow_is_retried_with_larger_queues(P, cornell, monkeypatch, scheduler):
     # the fused scheduler keeps ONE pool (4 x cap) for all levels; this frame needs far more than 4 x 2500 records
-    monkeypatch.setenv("PGRT_MIN_LEVEL_CAP", "2500" if scheduler == 0 else "2048"); monkeypatch.setenv("PGRT_LEVEL_CAP_FACTOR", "0.05")
+    monkeypatch.setenv("PGRT_MIN_LEVEL_CAP", "2500" if scheduler != 1 else "2048"); monkeypatch.setenv("PGRT_LEVEL_CAP_FACTOR", "0.05")
     rt = P.raytracer_for(cornell)
     p = dict(seed=2, scheduler=scheduler)
     img, st = rt.render(p)
@@ -428,6 +434,11 @@ def test_full_size_1080p_properties(P, avenger):
         a, sa = rt.render(p); b, sb = rt.render(p)
         assert np.array_equal(a, b, equal_nan=True) and sa["total"] == sb["total"]
         assert sa["primary"] == 1920 * 1080 and sa["refraction"] <= sa["reflection"]
+        assert sa["launches"] == 7                    # the automatic choice at this size: the hybrid scheduler (pgrt.h)
+        for sched, launches in ((0, 3), (2, 7)):      # ... and the same frame from the fused and the explicit hybrid scheduler
+            c, sc_ = rt.render(dict(p, scheduler=sched))
+            assert np.array_equal(a, c, equal_nan=True) and sc_["launches"] == launches
+            assert all(sa[k] == sc_[k] for k in ("primary", "shadow", "reflection", "refraction"))
         s7 = rt.render(dict(p, max_depth=7))[1]
         assert s7["reflection"] <= sa["reflection"] and s7["primary"] == sa["primary"]
         assert np.all(a[..., 3] == 1.0)
@@ -669,7 +680,7 @@ def test_cross_frame_accumulation(P, oracle_mod, cornell):
         rt.render_accumulate(0, base)
 
 
-@pytest.mark.parametrize("scheduler", [0, 1])
+@pytest.mark.parametrize("scheduler", [0, 1, 2])
 def test_path_tracing_mode_matches_the_oracle(P, oracle_mod, cornell, scheduler):
     """shader_mode = 3 (README.md:21 'To do: path tracing'; no reference counterpart, so the spec is include/pgrt.h and the
     oracle restates it): every non-dielectric hit = its Phong value + albedo x one cosine-weighted bounce.  The bounce

@@ -38,6 +38,13 @@ def run(n):
     return time.perf_counter() - t0, rays
 run(3 * a.depth)
 t, rays = run(a.frames)
+cyc = [0, 0, 0, 0]
+for sl in range(a.depth):
+    c = rt.frame_cycles(sl)
+    cyc = [x + y for x, y in zip(cyc, c)]
+if cyc[3]:
+    print(f"   warp time per frame (pipelined, mean of the last {a.depth} frames): primary {cyc[0] / a.depth / 1.965e3:.0f} us-warp, secondary {cyc[1] / a.depth / 1.965e3:.0f}, "
+          f"resident {cyc[2] / a.depth / 1.965e3:.0f} ({cyc[3] / a.depth:.0f} warps): {100 * cyc[0] / cyc[2]:.1f} % / {100 * cyc[1] / cyc[2]:.1f} % / other {100 * (cyc[2] - cyc[0] - cyc[1]) / cyc[2]:.1f} %", flush=True)
 print(f"{a.tag or os.environ.get('PGRT_LIB', 'default')} keep={os.environ.get('PGRT_KEEP_CTAS', '8')} policy={os.environ.get('PGRT_POOL_POLICY', '1')} claim={os.environ.get('PGRT_MIN_CLAIM', '32')} "
       f"ctas={os.environ.get('PGRT_FRAME_CTAS_PER_SM', 'max')} | blocking frame {lat[0]:.3f} ms (kernel {lat[1]} us, primaries done at {lat[2]} us, {lat[4]} secondary rays in {lat[3]} warp iterations) | "
       f"pipelined x{a.depth}: {t / a.frames * 1e3:.3f} ms/frame = {rays / t / 1e6:.0f} Mrays/s", flush=True)

@@ -9,9 +9,12 @@ from pgi_raytracing_b200 import raytracer_for, default_params
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--ranks", type=int, default=8); ap.add_argument("--depth", type=int, default=16); ap.add_argument("--frames", type=int, default=400)
-ap.add_argument("--flush", type=int, default=1); ap.add_argument("--tag", default=""); ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--flush", type=int, default=1); ap.add_argument("--tag", default=""); ap.add_argument("--reps", type=int, default=1); ap.add_argument("--params", default="")
 a = ap.parse_args()
 sc, p, desc = bench.workload("c2")
+if a.params:
+    import json
+    p.update(json.loads(a.params))
 rt = raytracer_for(sc)
 params = default_params(**p)
 rt.set_shard(0, a.ranks)
@@ -37,5 +40,5 @@ def run(n):
 run(3 * a.depth)
 for rep in range(a.reps):
     t, rays, host = run(a.frames)
-    print(f"{a.tag} shard 1/{a.ranks} depth {a.depth} flush {a.flush} keep={os.environ.get('PGRT_KEEP_CTAS', '8')} ctas={os.environ.get('PGRT_FRAME_CTAS', 'auto')}: "
+    print(f"{a.tag} {a.params} shard 1/{a.ranks} depth {a.depth} flush {a.flush} keep={os.environ.get('PGRT_KEEP_CTAS', '8')} ctas={os.environ.get('PGRT_FRAME_CTAS', 'auto')}: "
           f"{t / a.frames * 1e3:.4f} ms/frame, {rays / t / 1e6:.0f} Mrays/s of this rank's rays (x{a.ranks} = {rays / t / 1e6 * a.ranks:.0f}), host {host * 1e6:.1f} us/frame", flush=True)

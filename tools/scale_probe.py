@@ -14,13 +14,16 @@ from pgi_raytracing_b200.dist import ShardedRenderer, share_frames
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--depth", default="16"); ap.add_argument("--frames", type=int, default=600); ap.add_argument("--flush", default="1")
-ap.add_argument("--variants", default="solo,p2p-nosync,counter,words,allreduce"); ap.add_argument("--workload", default="c2")
+ap.add_argument("--variants", default="solo,p2p-nosync,counter,words,allreduce"); ap.add_argument("--workload", default="c2"); ap.add_argument("--params", default="", help="JSON overrides of the render parameters")
 a = ap.parse_args()
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 sc, p, desc = bench.workload(a.workload)
+if a.params:
+    import json
+    p.update(json.loads(a.params))
 rt = raytracer_for(sc, device=local)
 params = default_params(**p)
 FLUSH = int(torch.cuda.get_device_properties(dev).L2_cache_size * 1.125) // 4096 * 4096
@@ -116,7 +119,7 @@ for depth in [int(x) for x in a.depth.split(",")]:
                 completion = sr.completion
                 sr.close()
             if rank == 0:
-                print(f"N={world} depth {depth} flush {flush} {variant:11s} ({completion}): {ms:.4f} ms/frame device, {wall:.4f} wall, {rays / ms / 1e3:.0f} Mrays/s", flush=True)
+                print(f"{a.params} N={world} depth {depth} flush {flush} {variant:11s} ({completion}): {ms:.4f} ms/frame device, {wall:.4f} wall, {rays / ms / 1e3:.0f} Mrays/s", flush=True)
             barrier()
 if world > 1:
     dist.destroy_process_group()
