@@ -138,7 +138,7 @@ struct pgrt_context {
     FrameSlot slots[PGRT_MAX_INFLIGHT];
     int frame_per_sm_max = 0, frame_per_sm_env = 0;   // occupancy bound of k_frame; PGRT_FRAME_CTAS_PER_SM
     int min_claim = 32;               // k_frame takes pool records ahead of primary rays once this many wait (PGRT_MIN_CLAIM, 1..32)
-    int keep_ctas = 8;                // CTAs of k_frame that stay until the batch is done (PGRT_KEEP_CTAS)
+    int keep_ctas = 2;                // CTAs of k_frame that stay until the batch is done (PGRT_KEEP_CTAS)
     int pool_policy = 0;              // how k_frame takes secondary rays while primary rays last: 0 not at all, 1 full batches by compare-and-swap, 2 tickets (PGRT_POOL_POLICY)
     int claim_patience = 4;           // polls after which an idle warp of k_frame halves the number of pool records it waits for (PGRT_CLAIM_PATIENCE)
     double pool_scale = 1.0;          // grown after a pool overflow; never shrinks before the next pgrt_commit
@@ -746,7 +746,8 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
     FrameOut fo = {};
     void* out = S.host_dst ? (void*)S.d_frame.p : S.dest;
     if (S.fmt == 1) fo.rgba8 = (uint32_t*)out; else fo.rgba = (float4*)out;
-    fo.compact = dest_mode == 1; fo.direct = (fused && SPP == 1) ? 1 : 0;
+    fo.compact = dest_mode == 1; fo.direct = ((fused || (hybrid && !path)) && SPP == 1) ? 1 : 0;   // (path tracing keeps a node's own value in its colour slot)
+    FrameOut fo_q = fo; fo_q.direct = 0;                                                            // level-synchronous kernels: samples go through the colour queue
     for (uint64_t slot0 = 0; slot0 < total_slots; slot0 += batch_slots) {
         const uint32_t n_slots = (uint32_t)std::min<uint64_t>(batch_slots, total_slots - slot0);
         const uint32_t n0 = n_slots * (uint32_t)SPP;
@@ -781,16 +782,16 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
                 if (dest_mode == 2) break;
                 tm.begin(KC_SHADE, l);
                 if (hybrid) {
-                    if (path) k_shade<true, true><<<shade_grid, 256, 0, st>>>(sc, *p, g0, l, S.levels[l], S.levels[l + 1], S.pool, cnt);
-                    else k_shade<false, true><<<shade_grid, 256, 0, st>>>(sc, *p, g0, l, S.levels[l], S.levels[l + 1], S.pool, cnt);
+                    if (path) k_shade<true, true><<<shade_grid, 256, 0, st>>>(sc, *p, g0, l, S.levels[l], S.levels[l + 1], S.pool, fo, cnt);
+                    else k_shade<false, true><<<shade_grid, 256, 0, st>>>(sc, *p, g0, l, S.levels[l], S.levels[l + 1], S.pool, fo, cnt);
                 }
-                else if (path) k_shade<true, false><<<shade_grid, 256, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], S.levels[l + 1], S.pool, cnt);
-                else k_shade<false, false><<<shade_grid, 256, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], S.levels[l + 1], S.pool, cnt);
+                else if (path) k_shade<true, false><<<shade_grid, 256, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], S.levels[l + 1], S.pool, fo_q, cnt);
+                else k_shade<false, false><<<shade_grid, 256, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], S.levels[l + 1], S.pool, fo_q, cnt);
                 rs.launches++;
                 tm.end();
                 tm.begin(KC_TRACE, l);   // Phong = shading preamble + one inline shadow traversal per light
-                if (count) k_phong<true><<<phong_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], cnt);
-                else k_phong<false><<<phong_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], cnt);
+                if (count) k_phong<true><<<phong_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], hybrid ? fo : fo_q, cnt);
+                else k_phong<false><<<phong_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, l, S.levels[l], hybrid ? fo : fo_q, cnt);
                 rs.launches++; rs.trace_launches++;
                 tm.end();
             }

@@ -505,12 +505,39 @@ __device__ PGRT_COLD float4 combine_node(float4 att, float4 a, bool has_b, float
     return make_float4(a.x * att.x, a.y * att.y, a.z * att.z, 1.0f);
 }
 
+// ---- K11 (per pixel): mean over the samples + gamma (raytracer.cpp:421-446), and the 8-bit form the reference displays
+__device__ __forceinline__ float4 resolve_value(float fr, float fg, float fb, int S, float gamma_level) {
+    Col4 in; in.r = fb / S; in.g = fg / S; in.b = fr / S; in.a = 1.0f;       // :431 (swap in)
+    const Col4 g = gamma_correct(in, gamma_level);
+    return make_float4(g.r, g.g, g.b, g.a);
+}
+// float -> R8G8B8A8_UNORM as D3D11 converts when the float texture reaches the back buffer (simpleguidx11.cpp:229,290):
+// NaN -> 0, clamp to [0,1], scale by 255, round to nearest
+__device__ __forceinline__ uint32_t unorm8(float c) {
+    c = (c != c) ? 0.0f : fminf(fmaxf(c, 0.0f), 1.0f);
+    return (uint32_t)floorf(c * 255.0f + 0.5f);
+}
+__device__ __forceinline__ uint32_t pack_rgba8(float4 c) { return unorm8(c.x) | (unorm8(c.y) << 8) | (unorm8(c.z) << 16) | (unorm8(c.w) << 24); }
+__device__ __forceinline__ void store_pixel(const FrameOut& fo, size_t idx, float4 c) {
+    if (fo.rgba) fo.rgba[idx] = c;
+    if (fo.rgba8) fo.rgba8[idx] = pack_rgba8(c);
+}
+
+// a finished level-0 sample IS the pixel when there is one sample per pixel: gamma and the store at its final place
+__device__ __forceinline__ void store_sample_as_pixel(const FrameOut& fo, const Gen0& g0, const pgrt_render_params& p, uint32_t i, float4 col) {
+    int x, y;
+    const uint32_t slot = g0.slot0 + i;
+    if (slot_to_pixel(g0.sh, g0.cam.width, g0.cam.height, slot, x, y))
+        store_pixel(fo, fo.compact ? (size_t)slot : (size_t)y * g0.cam.width + x, resolve_value(0.0f + col.x, 0.0f + col.y, 0.0f + col.z, 1, p.gamma_level));
+    else if (fo.compact) store_pixel(fo, (size_t)slot, make_float4(0.f, 0.f, 0.f, 0.f));
+}
+
 // ---- K8 (kernel): one level of the wavefront (level-synchronous scheduler)
 // POOL (hybrid scheduler, level 0 only): the children of a dielectric hit do not go to the next level's queue but to the frame's
 // ray pool, as records of k_frame's own format (published by their epoch word, counted in `outstanding`), and the node waits
 // in L for the continuation: the k_frame launched behind this kernel finds all of level 1 ready and runs the rest of trace().
 template <bool PATH, bool POOL>
-__global__ void __launch_bounds__(256, PGRT_SHADE_MIN_BLOCKS) k_shade(DevScene sc, pgrt_render_params p, Gen0 g0, int level, LevelBufs L, LevelBufs Ln, RayPool P, Counters* cnt) {
+__global__ void __launch_bounds__(256, PGRT_SHADE_MIN_BLOCKS) k_shade(DevScene sc, pgrt_render_params p, Gen0 g0, int level, LevelBufs L, LevelBufs Ln, RayPool P, FrameOut fo, Counters* cnt) {
     const uint32_t n = min(cnt->n_rays[level], L.cap);
     const uint32_t epoch = POOL ? cnt->epoch : 0u;
     const int lane = threadIdx.x & 31;
@@ -525,7 +552,8 @@ __global__ void __launch_bounds__(256, PGRT_SHADE_MIN_BLOCKS) k_shade(DevScene s
             load_ray_shade(L, g0, p, i, o, d);
             shade_classify<PATH>(sc, p, level, o, d, L.hit[i], s);
             is_phong = s.kind == SK_PHONG || (PATH && s.kind == SK_PATH); is_diel = s.kind == SK_DIEL || (PATH && s.kind == SK_PATH);
-            if (s.kind == SK_FINAL) L.color[i] = s.color;
+            // (POOL with one sample per pixel, fo.direct: a finished sample goes straight to the frame, no colour queue, no k_resolve)
+            if (s.kind == SK_FINAL) { if (POOL && fo.direct) store_sample_as_pixel(fo, g0, p, i, s.color); else L.color[i] = s.color; }
         }
         const bool has_refr = is_diel && s.has_refr;
         const uint32_t pslot = warp_append(&cnt->n_phong[level], is_phong, lane);
@@ -554,7 +582,7 @@ __global__ void __launch_bounds__(256, PGRT_SHADE_MIN_BLOCKS) k_shade(DevScene s
                     cnt->overflow = 1u;   // black; the frame is re-rendered with a larger pool.  A reserved record inside the pool is published as dead
                     if (rl < P.cap) { P.ray_d[rl] = make_float4(0.f, 0.f, 0.f, -1.0f); P.link[rl] = make_uint4(0u, 0u, epoch, 0u); }
                     if (has_refr && rr < P.cap) { P.ray_d[rr] = make_float4(0.f, 0.f, 0.f, -1.0f); P.link[rr] = make_uint4(0u, 0u, epoch, 0u); }
-                    L.color[i] = make_float4(0.f, 0.f, 0.f, 1.f);
+                    if (fo.direct) store_sample_as_pixel(fo, g0, p, i, make_float4(0.f, 0.f, 0.f, 1.f)); else L.color[i] = make_float4(0.f, 0.f, 0.f, 1.f);
                 }
             }
             continue;
@@ -589,7 +617,7 @@ __global__ void __launch_bounds__(256, PGRT_SHADE_MIN_BLOCKS) k_shade(DevScene s
 
 // ---- K8b/K9 (kernel)
 template <bool COUNT>
-__global__ void __launch_bounds__(128, PGRT_PHONG_MIN_BLOCKS) k_phong(DevScene sc, pgrt_render_params p, Gen0 g0, int level, LevelBufs L, Counters* cnt) {
+__global__ void __launch_bounds__(128, PGRT_PHONG_MIN_BLOCKS) k_phong(DevScene sc, pgrt_render_params p, Gen0 g0, int level, LevelBufs L, FrameOut fo, Counters* cnt) {
     const uint32_t n = cnt->n_phong[level];
     unsigned long long my_shadow = 0;
     TravAcc acc; acc.nodes = 0; acc.tris = 0; acc.mx = 0;
@@ -599,7 +627,8 @@ __global__ void __launch_bounds__(128, PGRT_PHONG_MIN_BLOCKS) k_phong(DevScene s
         load_ray_shade(L, g0, p, i, o, d);
         const float4 h = L.hit[i];
         const HitFrame f = hit_frame(sc, o, d, h);
-        L.color[i] = phong_eval<COUNT>(sc, p, o, d, f, my_shadow, acc);
+        const float4 col = phong_eval<COUNT>(sc, p, o, d, f, my_shadow, acc);
+        if (fo.direct) store_sample_as_pixel(fo, g0, p, i, col); else L.color[i] = col;     // fo.direct: hybrid scheduler, one sample per pixel
     }
     for (int o = 16; o > 0; o >>= 1) my_shadow += __shfl_xor_sync(0xffffffffu, my_shadow, o);
     if ((threadIdx.x & 31) == 0 && my_shadow) { atomicAdd(&cnt->shadow, my_shadow); atomicAdd(&cnt->lv_shadow[level], my_shadow); }
@@ -623,24 +652,6 @@ __global__ void __launch_bounds__(256) k_combine(int level, LevelBufs L, LevelBu
         }
         L.color[i] = out;
     }
-}
-
-// ---- K11 (per pixel): mean over the samples + gamma (raytracer.cpp:421-446), and the 8-bit form the reference displays
-__device__ __forceinline__ float4 resolve_value(float fr, float fg, float fb, int S, float gamma_level) {
-    Col4 in; in.r = fb / S; in.g = fg / S; in.b = fr / S; in.a = 1.0f;       // :431 (swap in)
-    const Col4 g = gamma_correct(in, gamma_level);
-    return make_float4(g.r, g.g, g.b, g.a);
-}
-// float -> R8G8B8A8_UNORM as D3D11 converts when the float texture reaches the back buffer (simpleguidx11.cpp:229,290):
-// NaN -> 0, clamp to [0,1], scale by 255, round to nearest
-__device__ __forceinline__ uint32_t unorm8(float c) {
-    c = (c != c) ? 0.0f : fminf(fmaxf(c, 0.0f), 1.0f);
-    return (uint32_t)floorf(c * 255.0f + 0.5f);
-}
-__device__ __forceinline__ uint32_t pack_rgba8(float4 c) { return unorm8(c.x) | (unorm8(c.y) << 8) | (unorm8(c.z) << 16) | (unorm8(c.w) << 24); }
-__device__ __forceinline__ void store_pixel(const FrameOut& fo, size_t idx, float4 c) {
-    if (fo.rgba) fo.rgba[idx] = c;
-    if (fo.rgba8) fo.rgba8[idx] = pack_rgba8(c);
 }
 
 // ---- fused scheduler: the whole of trace() for every sample of a batch in one persistent kernel (see the file header)

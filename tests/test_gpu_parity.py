@@ -434,8 +434,8 @@ def test_full_size_1080p_properties(P, avenger):
         a, sa = rt.render(p); b, sb = rt.render(p)
         assert np.array_equal(a, b, equal_nan=True) and sa["total"] == sb["total"]
         assert sa["primary"] == 1920 * 1080 and sa["refraction"] <= sa["reflection"]
-        assert sa["launches"] == 7                    # the automatic choice at this size: the hybrid scheduler (pgrt.h)
-        for sched, launches in ((0, 3), (2, 7)):      # ... and the same frame from the fused and the explicit hybrid scheduler
+        assert sa["launches"] == 6                    # the automatic choice at this size: the hybrid scheduler (pgrt.h); one sample per pixel: no k_resolve
+        for sched, launches in ((0, 3), (2, 6)):      # ... and the same frame from the fused and the explicit hybrid scheduler
             c, sc_ = rt.render(dict(p, scheduler=sched))
             assert np.array_equal(a, c, equal_nan=True) and sc_["launches"] == launches
             assert all(sa[k] == sc_[k] for k in ("primary", "shadow", "reflection", "refraction"))
