@@ -7,9 +7,10 @@
 A "step" is one frame = one pass of the hot path (pg1/simpleguidx11.cpp:95-118) over every pixel of the frame.
 Workload (N=1 default) = BASELINE.json configs[1]: avenger (stand-in mesh, the reference's OBJ is absent) 1920x1080,
 Whitted, depth cut-off 10, 1 spp un-jittered.  For N>1 the same frame is cut into 32x8 tiles dealt round-robin to
-the ranks (strong scaling: total work fixed); every rank's frame kernel stores its tiles straight into rank 0's frame over
-NVLink (fallback: NCCL gather); completion is one flag per rank and slot in shared host memory, waited for with stream
-memory operations (no collective per step).
+the ranks (strong scaling: total work fixed); every rank's kernels store its tiles straight into rank 0's frame over
+NVLink (fallback: NCCL gather); completion is one counter per slot in rank 0's memory that every rank's finished frame adds 1
+to, waited for with a stream memory operation (no collective per step).  The library picks the scheduler by the size of a
+rank's share (pgrt.h, scheduler 3): hybrid from 400 k samples, the fused frame kernel below (8 GPUs).
 
 value  : rays/s of K whole frames, scene resident in HBM: the Producer loop renders frames forever
          (pg1/simpleguidx11.cpp:95-125), so the run is one continuous pipeline (--inflight frames in flight per GPU, own
@@ -533,7 +534,7 @@ def run_ours(args):
                                                 "parallelism": f"tiles32x8/rr x{world}", "frames_in_flight": depth, "gather": sr.mode, "completion": sr.completion,
                                                 "timing": f"median of {R - 1} consecutive windows of {K} steps each in one continuous pipeline (a first window fills it), "
                                                           f"CUDA events on the consumer stream, max over ranks per window; {timed_s:.2f} s between the barriers",
-                                                "windows_ms_per_step": {"first": win[0] / K, "min": steady[0] / K, "median": ms_per_step, "max": steady[-1] / K},
+                                                "windows_ms_per_step": {"first": win[0] / K, "min": steady[0] / K, "median": ms_per_step, "mean": sum(steady) / len(steady) / K, "max": steady[-1] / K},
                                                 "host_issue_us_per_step": host_issue[0] / max(host_issue[1], 1) * 1e6,
                                                 "host_issue_parts_us": dict(zip(("flush", "render_begin", "completion", "event"), host_parts)),
                                                 "l2": f"flushed before every timed step on that step's stream ({FLUSH_BYTES >> 20} MiB fill = 1.125 x L2)",

@@ -1,0 +1,17 @@
+#!/bin/bash
+# round 2, session 2, two GPUs: bit-identity of every gather path with the automatic scheduler, then the bench line
+mkdir -p gpurun_out
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 tools/p2p_check.py > gpurun_out/r2s2_p2p_n2b.log 2>&1
+grep -E "ranks|Error|error|assert" gpurun_out/r2s2_p2p_n2b.log | tail -12
+PGRT_AUTO_HYBRID_MIN=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/p2p_check.py > gpurun_out/r2s2_p2p_n2c.log 2>&1
+echo "-- the same with the hybrid scheduler forced (PGRT_AUTO_HYBRID_MIN=1)"; grep -E "ranks|Error|error|assert" gpurun_out/r2s2_p2p_n2c.log | tail -12
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29532 bench.py --gpus 2 --steps 20 --warmup 5 --watchdog 240 > gpurun_out/r2s2_bench_n2.log 2>&1
+python - <<PY
+import json
+try:
+    j=json.loads([l for l in open("gpurun_out/r2s2_bench_n2.log").read().strip().splitlines() if l.startswith("{")][-1])
+    print("N=2", round(j["value"]), "Mrays/s", round(j["ms_per_step"],4), "ms/step", "inflight", j["config"]["frames_in_flight"], "e2e", round(j["e2e"]["value"]), "e2e8", round(j.get("e2e_rgba8",{}).get("value",0)), j["config"]["completion"], j["config"]["windows_ms_per_step"], "equal1gpu", j.get("frame_equal_to_1gpu"), "host_us", round(j["config"]["host_issue_us_per_step"],1), j["roofline"]["scheduler"])
+    print(json.dumps(j["config"].get("extra"))[:600])
+except Exception as e:
+    print("N=2 failed", e); print(open("gpurun_out/r2s2_bench_n2.log").read()[-3000:])
+PY
