@@ -171,3 +171,19 @@ def test_tiling_properties_for_arbitrary_sizes():
         assert np.array_equal(D.untile_numpy(g, w, h, n), frame)
 
     prop()
+
+
+def test_host_side_look_at_a_flag_word_compares_like_the_stream_wait():
+    """dist.ShardedRenderer looks at the "consumed" word from the host before it falls back to cuStreamWaitValue32 (an
+    unsatisfied stream wait parks its hardware channel): same cyclic >= comparison, bounded spin, no CUDA involved."""
+    import time
+    sr = object.__new__(D.ShardedRenderer)
+    sr.ctl = np.zeros(8, np.uint32)
+    sr.ctl[2] = 5
+    assert sr._host_sees(8, 5) and sr._host_sees(8, 3)
+    t0 = time.perf_counter()
+    assert not sr._host_sees(8, 6, spin_s=2e-3)                      # not reached: gives up after the spin, does not block
+    assert 1e-3 < time.perf_counter() - t0 < 0.5
+    sr.ctl[2] = 3                                                    # tags wrap at 2^32: 3 is "after" 0xFFFFFFFE
+    assert sr._host_sees(8, 0xFFFFFFFE) and not sr._host_sees(8, 8, spin_s=1e-4)
+    assert os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS") == "32"     # set by the package before any CUDA context exists (its default here)
