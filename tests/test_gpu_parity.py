@@ -360,6 +360,19 @@ def test_queue_overflow_is_retried_with_larger_queues(P, cornell, monkeypatch, s
     assert np.array_equal(img, ref, equal_nan=True)
 
 
+def test_queue_overflow_with_direct_pixel_stores(P, cornell, monkeypatch):
+    """One sample per pixel: the hybrid's shading kernels and the fused kernel store finished pixels straight into the frame;
+    an attempt whose pool overflowed has stored black for the nodes that did not fit, and the retry must overwrite all of it."""
+    p = dict(seed=2, sampling_width=1, jitter=0, aperture=0.0)
+    ref, st_ref = P.raytracer_for(cornell).render(dict(p, scheduler=1))
+    monkeypatch.setenv("PGRT_MIN_LEVEL_CAP", "100"); monkeypatch.setenv("PGRT_LEVEL_CAP_FACTOR", "0.01")
+    for sched in (0, 2):
+        rt = P.raytracer_for(cornell)
+        img, st = rt.render(dict(p, scheduler=sched))
+        assert st["overflow_retries"] >= 1, sched
+        assert np.array_equal(img, ref, equal_nan=True) and st["total"] == st_ref["total"], sched
+
+
 def test_overflowed_attempt_does_not_release_stream_consumers(P, cornell, monkeypatch):
     """a consumer ordered behind a slot with pgrt_stream_wait_slot must not see the frame of an attempt whose
     queues overflowed (black dielectric nodes); it is released by the retry that pgrt_render_end runs."""
