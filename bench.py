@@ -16,7 +16,8 @@ value  : rays/s of K whole frames, scene resident in HBM: the Producer loop rend
          (pg1/simpleguidx11.cpp:95-125), so the run is one continuous pipeline (--inflight frames in flight per GPU, own
          stream each, pgrt_render*_begin / pgrt_render_end; L2 flushed before every step on that step's stream, a fill of
          1.125 x L2) cut into consecutive windows of exactly K steps; a CUDA event on the consumer stream closes every
-         window, the slowest rank counts per window, and the MEDIAN window is reported (the first one fills the pipeline).
+         window, the slowest rank counts per window, and the MEAN of the windows between the first (which fills the pipeline) and the last
+         (which drains it) is reported: frames complete in bursts of --inflight, windows alternate between two values, a median would be arbitrary.
          Enough windows run to cover --min-seconds (1 s) of device time, with the clocks sampled throughout.
 e2e    : the same metric through the host-buffer C-ABI call every step (pgrt_set_camera + pgrt_render_begin into pinned
          host memory + pgrt_render_end), wall clock, float frame (e2e) and 8-bit frame (e2e_rgba8).  N>1: the frames live
@@ -373,8 +374,13 @@ def run_ours(args):
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     win = [float(x) for x in wt.tolist()]
     rays_per_frame = float(tot[0].item()) / (R * K)
-    steady = sorted(win[1:])                               # the first window also fills the pipeline
-    window_ms = steady[len(steady) // 2]
+    # The first window also fills the pipeline; the others are averaged: frames complete in bursts of `depth` (the GPU works
+    # through the frames in flight breadth-first), so windows of K = 20 frames alternate between two values (C2, one GPU: 0.305
+    # and 0.451 ms per frame, profiles/r2_bench_windows.txt) and their MEDIAN is arbitrary (0.315 in one run, 0.395 in the
+    # next); the mean = device time of all steady windows / their frames is what repeats (0.3787, 0.3783).
+    # (the last window, which sees the pipeline drain with nothing new competing, is left out like the first)
+    steady = sorted(win[1:-1] if len(win) >= 4 else win[1:])
+    window_ms = sum(steady) / len(steady)
     ms_per_step = window_ms / K
     value = rays_per_frame / (ms_per_step * 1e-3) / 1e6
 
@@ -532,9 +538,10 @@ def run_ours(args):
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "config": {"workload": desc, "triangles": sc.ntris, "rays_per_frame": rays_per_frame,
                                                 "parallelism": f"tiles32x8/rr x{world}", "frames_in_flight": depth, "gather": sr.mode, "completion": sr.completion,
-                                                "timing": f"median of {R - 1} consecutive windows of {K} steps each in one continuous pipeline (a first window fills it), "
+                                                "timing": f"mean of {len(steady)} consecutive windows of {K} steps each in one continuous pipeline (the first window, which fills it, and the last, which drains it, are left out; frames complete in bursts of frames_in_flight, so single windows alternate between two values and the median is printed only for reference), "
                                                           f"CUDA events on the consumer stream, max over ranks per window; {timed_s:.2f} s between the barriers",
-                                                "windows_ms_per_step": {"first": win[0] / K, "min": steady[0] / K, "median": ms_per_step, "mean": sum(steady) / len(steady) / K, "max": steady[-1] / K},
+                                                "windows_ms_per_step": {"first": win[0] / K, "min": steady[0] / K, "median": steady[len(steady) // 2] / K, "mean": ms_per_step, "max": steady[-1] / K,
+                                                                        "in_order": [round(x / K, 4) for x in win]},
                                                 "host_issue_us_per_step": host_issue[0] / max(host_issue[1], 1) * 1e6,
                                                 "host_issue_parts_us": dict(zip(("flush", "render_begin", "completion", "event"), host_parts)),
                                                 "l2": f"flushed before every timed step on that step's stream ({FLUSH_BYTES >> 20} MiB fill = 1.125 x L2)",
