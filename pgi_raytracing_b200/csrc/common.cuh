@@ -101,6 +101,13 @@ PG_HD float4 pg_ldg4(const float4* p) {
     return *p;
 #endif
 }
+#if defined(__CUDACC__)
+__device__ __forceinline__ float4 pg_lds4(uint32_t saddr) {      // 16-byte load from a shared-memory address (cvta'd)
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+#endif
 // Embree 3 vec3 forms on FMA hardware (restated): dot = madd(x,x,madd(y,y,z*z)), cross = msub(..)
 PG_HD float e_dot(V3 a, V3 b) { return pg_fma(a.x, b.x, pg_fma(a.y, b.y, a.z * b.z)); }
 PG_HD V3 e_cross(V3 a, V3 b) {

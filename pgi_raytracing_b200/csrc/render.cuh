@@ -206,10 +206,16 @@ __device__ __forceinline__ void load_ray(const LevelBufs& L, const Gen0& g, cons
 // lanes (ballot + one atomicAdd per warp), so a few long traversals do not keep 31 lanes idle until they end.
 // refill = 32 degenerates to "a fresh 32-ray chunk when the whole warp is done".
 #define PGRT_TRACE_ROUNDS 2
+__device__ __forceinline__ void set_top(RayCtxF& r, uint32_t top) {
+#ifdef PGRT_SMEM_TOP
+    r.top = top;
+#endif
+}
+__device__ __forceinline__ void set_top(RayCtxQ&, uint32_t) {}
 
 template <class RC, bool COUNT>
 __device__ __forceinline__ void trace_queue(const DevScene& sc, const pgrt_render_params& p, const Gen0& g0, const LevelBufs& L, int level, Counters* cnt,
-                                            uint32_t n, int refill) {
+                                            uint32_t n, int refill, uint32_t top = 0u) {
     const int lane = threadIdx.x & 31;
     uint32_t* next = &cnt->trace_next[level];
     uint2 stack[PGRT_STACK8];
@@ -236,6 +242,7 @@ __device__ __forceinline__ void trace_queue(const DevScene& sc, const pgrt_rende
                     if (d.w >= 0.0f && sc.n_tris != 0 && !ray_misses_box(sc.bb_lo, sc.bb_hi, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, FLT_MAX)) {
                         j = mine;
                         ray_ctx_init(r, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, FLT_MAX, sc.loop_ww != 0);
+                        set_top(r, top);
                         trav_init(s, FLT_MAX);
                         tc.nodes = 0; tc.tris = 0;
                     } else {
@@ -260,7 +267,17 @@ __device__ __forceinline__ void trace_queue(const DevScene& sc, const pgrt_rende
 template <bool COUNT>
 __global__ void __launch_bounds__(128, PGRT_TRACE_MIN_BLOCKS) k_trace(DevScene sc, pgrt_render_params p, Gen0 g0, LevelBufs L, int level, int refill, Counters* cnt) {
     const uint32_t n = min(cnt->n_rays[level], L.cap);
-    if (sc.node_layout == PGRT_LAYOUT_F32) trace_queue<RayCtxF, COUNT>(sc, p, g0, L, level, cnt, n, refill);
+    uint32_t top = 0u;
+#ifdef PGRT_SMEM_TOP
+    // measurement build: the first PGRT_SMEM_TOP nodes (the root and what follows it) staged in shared memory
+    __shared__ float4 s_top[PGRT_SMEM_TOP * PGRT_NODE_F4_F32];
+    if (sc.node_layout == PGRT_LAYOUT_F32 && sc.n_tris >= 64u) {
+        for (int k = threadIdx.x; k < PGRT_SMEM_TOP * PGRT_NODE_F4_F32; k += blockDim.x) s_top[k] = sc.nodes[k];
+        __syncthreads();
+        top = (uint32_t)__cvta_generic_to_shared(s_top);
+    }
+#endif
+    if (sc.node_layout == PGRT_LAYOUT_F32) trace_queue<RayCtxF, COUNT>(sc, p, g0, L, level, cnt, n, refill, top);
     else trace_queue<RayCtxQ, COUNT>(sc, p, g0, L, level, cnt, n, refill);
 }
 

@@ -95,6 +95,9 @@ struct RayCtxF {                       // PGRT_LAYOUT_F32
     float pad_far;                      // absolute slack of the comparison with the best hit so far (see ray_far_pad)
     int onx, ony, onz, ofx, ofy, ofz;  // float4 offsets of the near / far planes inside a node, by ray sign
     uint32_t octinv, sw1, sw2, sw4;    // delta-swap masks that move internal hit bits from 24 + s to 24 + (s ^ octinv)
+#ifdef PGRT_SMEM_TOP
+    uint32_t top;                      // builds with -DPGRT_SMEM_TOP=n (measurement): shared-memory address of a copy of nodes 0 .. n-1, 0 = none
+#endif
 };
 struct RayCtxQ {                       // PGRT_LAYOUT_Q8
     V3 O, D; float tnear, tfar;
@@ -139,6 +142,9 @@ PG_HD void ray_ctx_init(RayCtxF& r, V3 O, V3 D, float tnear, float tfar, bool ww
     r.onx = 3 + 2 * (negx ? 3 : 0); r.ony = 3 + 2 * (negy ? 4 : 1); r.onz = 3 + 2 * (negz ? 5 : 2);
     r.ofx = 3 + 2 * (negx ? 0 : 3); r.ofy = 3 + 2 * (negy ? 1 : 4); r.ofz = 3 + 2 * (negz ? 2 : 5);
     r.sw1 = (r.octinv & 1u) ? 0x55000000u : 0u; r.sw2 = (r.octinv & 2u) ? 0x33000000u : 0u; r.sw4 = (r.octinv & 4u) ? 0x0F000000u : 0u;
+#ifdef PGRT_SMEM_TOP
+    r.top = 0u;
+#endif
 }
 
 PG_HD void ray_ctx_init(RayCtxQ& r, V3 O, V3 D, float tnear, float tfar, bool ww) {
@@ -161,9 +167,23 @@ PG_HD void ray_ctx_init(RayCtxQ& r, V3 O, V3 D, float tnear, float tfar, bool ww
 PG_HD uint32_t node_visit(const float4* __restrict__ nodes, uint32_t ni, const RayCtxF& r, float best_t, uint32_t& child_base, uint32_t& tri_base,
                           uint32_t& imask) {
     const float4* __restrict__ nd = nodes + PGRT_NODE_F4_F32 * (size_t)ni;
-    const float4 f0 = pg_ldg4(nd), w0 = pg_ldg4(nd + 1), w1 = pg_ldg4(nd + 2);
-    const float4 nx0 = pg_ldg4(nd + r.onx), ny0 = pg_ldg4(nd + r.ony), nz0 = pg_ldg4(nd + r.onz), fx0 = pg_ldg4(nd + r.ofx), fy0 = pg_ldg4(nd + r.ofy), fz0 = pg_ldg4(nd + r.ofz);
-    const float4 nx1 = pg_ldg4(nd + r.onx + 1), ny1 = pg_ldg4(nd + r.ony + 1), nz1 = pg_ldg4(nd + r.onz + 1), fx1 = pg_ldg4(nd + r.ofx + 1), fy1 = pg_ldg4(nd + r.ofy + 1), fz1 = pg_ldg4(nd + r.ofz + 1);
+    float4 f0, w0, w1, nx0, ny0, nz0, fx0, fy0, fz0, nx1, ny1, nz1, fx1, fy1, fz1;
+#if defined(PGRT_SMEM_TOP) && defined(__CUDA_ARCH__)
+    // the root and the nodes right behind it (the collapse numbers nodes level by level) from a copy in shared memory
+    if (r.top != 0u && ni < (uint32_t)PGRT_SMEM_TOP) {
+        const uint32_t a = r.top + 16u * (uint32_t)PGRT_NODE_F4_F32 * ni;
+        f0 = pg_lds4(a); w0 = pg_lds4(a + 16u); w1 = pg_lds4(a + 32u);
+        nx0 = pg_lds4(a + 16u * r.onx); ny0 = pg_lds4(a + 16u * r.ony); nz0 = pg_lds4(a + 16u * r.onz);
+        fx0 = pg_lds4(a + 16u * r.ofx); fy0 = pg_lds4(a + 16u * r.ofy); fz0 = pg_lds4(a + 16u * r.ofz);
+        nx1 = pg_lds4(a + 16u * r.onx + 16u); ny1 = pg_lds4(a + 16u * r.ony + 16u); nz1 = pg_lds4(a + 16u * r.onz + 16u);
+        fx1 = pg_lds4(a + 16u * r.ofx + 16u); fy1 = pg_lds4(a + 16u * r.ofy + 16u); fz1 = pg_lds4(a + 16u * r.ofz + 16u);
+    } else
+#endif
+    {
+        f0 = pg_ldg4(nd); w0 = pg_ldg4(nd + 1); w1 = pg_ldg4(nd + 2);
+        nx0 = pg_ldg4(nd + r.onx); ny0 = pg_ldg4(nd + r.ony); nz0 = pg_ldg4(nd + r.onz); fx0 = pg_ldg4(nd + r.ofx); fy0 = pg_ldg4(nd + r.ofy); fz0 = pg_ldg4(nd + r.ofz);
+        nx1 = pg_ldg4(nd + r.onx + 1); ny1 = pg_ldg4(nd + r.ony + 1); nz1 = pg_ldg4(nd + r.onz + 1); fx1 = pg_ldg4(nd + r.ofx + 1); fy1 = pg_ldg4(nd + r.ofy + 1); fz1 = pg_ldg4(nd + r.ofz + 1);
+    }
     const float far_pad = pg_fma(best_t, PGRT_FAR_REL, r.pad_far);
     uint32_t hitmask = slab4f(w0, nx0, ny0, nz0, fx0, fy0, fz0, r.idx, r.idy, r.idz, r.nxo, r.nyo, r.nzo, r.fxo, r.fyo, r.fzo, r.tnear, far_pad);
     hitmask |= slab4f(w1, nx1, ny1, nz1, fx1, fy1, fz1, r.idx, r.idy, r.idz, r.nxo, r.nyo, r.nzo, r.fxo, r.fyo, r.fzo, r.tnear, far_pad);
