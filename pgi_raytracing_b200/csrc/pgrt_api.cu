@@ -148,6 +148,7 @@ struct pgrt_context {
     bool use_graphs = true;           // PGRT_GRAPHS=0: every frame as individual launches
     int trace_refill = 32;            // k_trace claims new rays once this many lanes of a warp are idle (PGRT_TRACE_REFILL, 1..32); 32 = whole-warp chunks, the fastest for coherent primary rays (profiles/r1_sweep_trace_refill.txt)
     int trace_ctas_per_sm = 6;        // persistent k_trace grid (PGRT_TRACE_CTAS_PER_SM)
+    unsigned trace_rays_per_cta = 1024;   // ... but no more CTAs than one per this many rays of level 0 (PGRT_TRACE_RAYS_PER_CTA)
     DevBuf<uint32_t> d_ids;
     DevBuf<uint4> flush_buf;          // pgrt_debug_flush_l2
     DevBuf<float4> acc_sum, acc_frames[4]; cudaEvent_t acc_event = nullptr;   // pgrt_render_accumulate
@@ -218,6 +219,7 @@ extern "C" int pgrt_create(pgrt_context** out, int device) {
     if (const char* e = getenv("PGRT_FUSE_RAYGEN")) ctx->fuse_raygen = atoi(e) != 0;
     if (const char* e = getenv("PGRT_GRAPHS")) ctx->use_graphs = atoi(e) != 0;
     if (const char* e = getenv("PGRT_TRACE_REFILL")) ctx->trace_refill = std::min(32, std::max(1, atoi(e)));
+    if (const char* e = getenv("PGRT_TRACE_RAYS_PER_CTA")) ctx->trace_rays_per_cta = (unsigned)std::min(1 << 20, std::max(128, atoi(e)));
     if (const char* e = getenv("PGRT_TRACE_CTAS_PER_SM")) ctx->trace_ctas_per_sm = std::min(16, std::max(1, atoi(e)));
     if (const char* e = getenv("PGRT_MIN_CLAIM")) ctx->min_claim = std::min(32, std::max(1, atoi(e)));
     if (const char* e = getenv("PGRT_KEEP_CTAS")) ctx->keep_ctas = std::min(1 << 16, std::max(1, atoi(e)));
@@ -775,8 +777,12 @@ static int record_frame(pgrt_context* ctx, FrameSlot& S) {
             }
             for (int l = 0; l < (hybrid ? 1 : n_levels); ++l) {
                 tm.begin(KC_TRACE, l);
-                if (count) k_trace<true><<<trace_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, S.levels[l], l, ctx->trace_refill, cnt);
-                else k_trace<false><<<trace_grid, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, S.levels[l], l, ctx->trace_refill, cnt);
+                // level 0 of a small batch (a shard of a frame): a grid sized to the rays -- one CTA per PGRT_TRACE_RAYS_PER_CTA (1024:
+                // eight 32-ray chunks per warp) -- so that warps refill instead of hundreds of CTAs starting for one chunk each (an
+                // eighth of C2 through the hybrid: 0.1117 ms with 888 CTAs, 0.1028 with 296: profiles/r2_sweep_shard_depth.txt)
+                const unsigned tg = l == 0 ? std::max(std::min(trace_grid, (unsigned)ctx->sm_count), std::min(trace_grid, div_up(n0, ctx->trace_rays_per_cta))) : trace_grid;
+                if (count) k_trace<true><<<tg, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, S.levels[l], l, ctx->trace_refill, cnt);
+                else k_trace<false><<<tg, 128, 0, st>>>(sc, *p, l == 0 ? g0 : gN, S.levels[l], l, ctx->trace_refill, cnt);
                 rs.launches++; rs.trace_launches++;
                 tm.end();
                 if (dest_mode == 2) break;
@@ -862,7 +868,7 @@ static uint64_t frame_key(pgrt_context* ctx, const FrameSlot& S) {
     h = fnv1a(S.levels, sizeof(LevelBufs) * (size_t)(S.n_levels + 1), h); h = fnv1a(&S.pool, sizeof S.pool, h);
     const void* extra[5] = {S.d_frame.p, S.d_counters.p, S.stream, S.sig_flag, S.sig_add ? (const void*)1 : nullptr};
     h = fnv1a(extra, sizeof extra, h);
-    const int flags[10] = {(S.fused ? 1 : 0) | (S.hybrid ? 2 : 0), ctx->fuse_raygen ? 1 : 0, S.frame_grid, ctx->trace_refill, ctx->trace_ctas_per_sm, S.fmt, ctx->min_claim, S.keep_ctas, ctx->claim_patience, ctx->pool_policy};
+    const int flags[10] = {(S.fused ? 1 : 0) | (S.hybrid ? 2 : 0), (ctx->fuse_raygen ? 1 : 0) | (int)(ctx->trace_rays_per_cta << 1), S.frame_grid, ctx->trace_refill, ctx->trace_ctas_per_sm, S.fmt, ctx->min_claim, S.keep_ctas, ctx->claim_patience, ctx->pool_policy};
     return fnv1a(flags, sizeof flags, h) | 1ull;
 }
 
