@@ -134,7 +134,7 @@ def test_shared_host_frames_fall_back_together_when_one_rank_fails():
     assert got == [(0, True, True, 0), (1, True, True, 0)], got
 
 
-def _flag_pipeline_worker(rank, world, port, depth, n_frames, q):
+def _flag_pipeline_worker(rank, world, port, depth, n_frames, q, counter_lock=None):
     """The flag protocol of dist.ShardedRenderer with host stores and polls in place of stream memory operations: every
     rank 'renders' its rows of a shared frame, rank 0 consumes the frame and releases the slot."""
     import ctypes
@@ -148,6 +148,13 @@ def _flag_pipeline_worker(rank, world, port, depth, n_frames, q):
     ptrs, views, keep = D.share_host_frames(rt, depth, rank, torch.device("cpu"))
     ctl = np.frombuffer(ctl_mm, dtype=np.uint32)
     assert ctl_base is not None and (ctl == 0).all()
+    # counter_lock: the "flags+counter" completion -- every rank's finished frame ADDS 1 to one word of the slot (on the GPU a
+    # system-scope atomic in rank 0's memory; here a locked read-modify-write on a second shared page), rank 0 waits once
+    cnt = None
+    if counter_lock is not None:
+        cnt_base, cnt_mm, cnt_keep = D.share_host_region(rt, 4096, rank, torch.device("cpu"), name="counters_test")
+        cnt = np.frombuffer(cnt_mm, dtype=np.uint32)
+        assert cnt_base is not None and (cnt == 0).all()
     frames = [np.ctypeslib.as_array((ctypes.c_float * (w * h * 4)).from_address(p)).reshape(h, w, 4) for p in ptrs]
     rng = np.random.default_rng(rank)
 
@@ -167,28 +174,43 @@ def _flag_pipeline_worker(rank, world, port, depth, n_frames, q):
         if rng.random() < 0.5:
             time.sleep(0.002 * rng.random())        # ranks drift against each other
         frames[s][rank::world] = float(k + 1)       # "render": this rank's rows of frame k
-        off, val = ops["signal"]; ctl[off // 4] = val
+        if cnt is not None:
+            with counter_lock:
+                cnt[ops["done_count"][0] // 4] += 1
+        else:
+            off, val = ops["signal"]; ctl[off // 4] = val
         if rank == 0:
-            for off, val in ops["done"]:
-                wait(off, val)
+            if cnt is not None:
+                off, val = ops["done_count"]
+                t0 = time.time()
+                while ((int(cnt[off // 4]) - val) & 0xFFFFFFFF) >= 0x80000000:      # cyclic >=, as cuStreamWaitValue32 compares
+                    assert time.time() - t0 < 60, "counter wait timed out"
+                    time.sleep(0)
+            else:
+                for off, val in ops["done"]:
+                    wait(off, val)
             ok &= bool((frames[s] == float(k + 1)).all())     # every rank's rows hold frame k: nobody ran ahead into this slot
             consumed_log.append(k)
     if rank == 0:
         q.put((ok, consumed_log == list(range(n_frames)), [int(x) for x in proto.count]))
     dist.barrier()
     D.release_host_region(rt, ctl_keep)
+    if cnt is not None:
+        del cnt
+        D.release_host_region(rt, cnt_keep)
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("depth", [1, 3])
-def test_flag_protocol_world2(depth):
+@pytest.mark.parametrize("depth,counter", [(1, False), (3, False), (3, True)])
+def test_flag_protocol_world2(depth, counter):
     """FlagProtocol at world size 2: tags agree without communication, no rank overwrites a slot before rank 0 has consumed
     it (depth 1: strict alternation), rank 0 never sees a frame before both ranks' rows are in place."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     n_frames = 40
-    procs = [ctx.Process(target=_flag_pipeline_worker, args=(r, 2, port, depth, n_frames, q)) for r in range(2)]
+    lock = ctx.Lock() if counter else None
+    procs = [ctx.Process(target=_flag_pipeline_worker, args=(r, 2, port, depth, n_frames, q, lock)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
@@ -208,3 +230,5 @@ def test_flag_protocol_offsets_and_tags():
     p.next_frame(2, 2)
     c = p.next_frame(0, 2)
     assert c["mark_consumed"] == (p.consumed_offset(2), 1) and c["before"] == [(p.consumed_offset(0), 1)] and c["signal"][1] == 2
+    # the counter form: one word per slot, every rank adds 1 per frame, rank 0 waits for frames * world
+    assert a["done_count"] == (0, 4) and b["done_count"] == (4, 4) and c["done_count"] == (0, 8)
