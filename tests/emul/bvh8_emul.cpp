@@ -16,7 +16,7 @@
 #include "../../pgi_raytracing_b200/csrc/traverse.cuh"
 
 namespace {
-const int PLOC_R = 16;
+const int PLOC_R = 8;
 
 struct Tree {
     std::vector<float4> b0, b1; std::vector<uint32_t> count, leaf_tri;
