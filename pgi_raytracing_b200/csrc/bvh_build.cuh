@@ -281,7 +281,8 @@ __global__ void __launch_bounds__(256) k_refit(const float* __restrict__ pos, co
 //
 // Binary tree layout shared with the collapse (Bvh2View in bvh8.cuh): leaves 0..N-1, internal nodes N..2N-2 in
 // creation order (root = 2N-2), b0 = (lo, left), b1 = (hi, right), count = triangles below.
-#define PLOC_R 8
+#define PLOC_R 8        // search radius.  8, not the 16 of round 1: better trees on every scene tried AND half the search (profiles/r2_ploc_radius.txt);
+                        // tests/emul/bvh8_emul.cpp carries the same constant (the GPU builder must reproduce the emulator's tree)
 #define PLOC_THREADS 256
 
 __global__ void __launch_bounds__(256) k_ploc_init(const float* __restrict__ pos, const uint32_t* __restrict__ vals, uint32_t n,
